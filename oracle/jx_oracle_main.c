@@ -1,0 +1,33 @@
+/* oracle/jx_oracle_main.c — TEST INFRASTRUCTURE ONLY.
+ * CLI around the C restatement, same flags as `regtools junctions extract`
+ * (junctions_extractor.cc:42-122), used by tests and by bench.py's CPU legs. */
+#define _GNU_SOURCE
+#include "jx_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+int main(int argc, char** argv) {
+    uint32_t a = 8, m = 70, M = 500000; int s = -1; const char *out = NULL, *reg = ".", *tag = "XS";
+    int c;
+    while ((c = getopt(argc, argv, "a:m:M:o:r:t:s:")) != -1) {
+        switch (c) {
+        case 'a': a = (uint32_t)atoi(optarg); break;
+        case 'm': m = (uint32_t)atoi(optarg); break;
+        case 'M': M = (uint32_t)atoi(optarg); break;
+        case 'o': out = optarg; break;
+        case 'r': reg = optarg; break;
+        case 't': tag = optarg; break;
+        case 's': s = !strcmp(optarg, "XS") ? 0 : !strcmp(optarg, "RF") ? 1 : !strcmp(optarg, "FR") ? 2 : -1; break;
+        default: return 1;
+        }
+    }
+    if (optind >= argc || s < 0) { fprintf(stderr, "usage: jx_oracle -s XS|RF|FR [-a -m -M -o -r -t] in.bam\n"); return 1; }
+    jxo_t* o = jxo_new(a, m, M, s, tag);
+    const char* err = NULL;
+    if (jxo_extract_bam(o, argv[optind], reg, &err)) { fprintf(stderr, "%s", err ? err : "error\n"); return 1; }
+    if (out) jxo_write_bed12_path(o, out); else jxo_write_bed12(o, stdout);
+    fprintf(stderr, "reads=%llu junctions=%zu\n", (unsigned long long)jxo_reads_seen(o), jxo_count(o));
+    jxo_free(o);
+    return 0;
+}
