@@ -1,0 +1,182 @@
+/* include/rtjx.h — C ABI of libregtools_jx.so, the B200-native drop-in for the
+ * `regtools junctions extract` hot path.
+ *
+ * The reference has no FFI; its boundary for this path is the C++ class JunctionsExtractor
+ * (/root/reference/src/junctions/junctions_extractor.h:149-248) driven by
+ * src/junctions/junctions_main.cc:45-59 and by
+ * src/cis-splice-effects/cis_splice_effects_identifier.cc:288-290.  Every entry point below
+ * names the reference member it replaces.  The C++ shim with the reference's own class and
+ * method names lives in regtools_b200/csrc/junctions_extractor.h; INTEGRATION.md shows the
+ * binding a maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 (RTJX_OK) or a negative
+ * rtjx_status and never throws; the message for the last failure of a handle is available
+ * from rtjx_last_error().  A handle is single-owner (one caller thread at a time); several
+ * handles may coexist.  There is NO CPU fallback: without a usable CUDA device every compute
+ * entry point fails with RTJX_E_CUDA.
+ */
+#ifndef RTJX_H
+#define RTJX_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    RTJX_OK            = 0,
+    RTJX_E_ARG         = -1,  /* bad argument / parameter combination                              */
+    RTJX_E_OPEN_BAM    = -2,  /* "Unable to open BAM/SAM file."          junctions_extractor.cc:505 */
+    RTJX_E_OPEN_INDEX  = -3,  /* "Unable to open BAM/SAM index. ..."     junctions_extractor.cc:510 */
+    RTJX_E_REGION      = -4,  /* "Unable to iterate to region within BAM." junctions_extractor.cc:521 */
+    RTJX_E_CUDA        = -5,  /* no device / CUDA runtime failure                                   */
+    RTJX_E_UNSUPPORTED = -6,  /* FASTA (intron-motif), -b barcodes, CRAM/SAM, .csi                  */
+    RTJX_E_NOMEM       = -7,
+    RTJX_E_STATE       = -8,  /* call order violated                                                */
+    RTJX_E_IO          = -9
+} rtjx_status;
+
+typedef struct rtjx_handle rtjx_t;
+
+/* Parameters = the private members the reference sets in parse_options() / the 8-arg ctor
+ * (junctions_extractor.h:151-181,199-205; CLI flags junctions_extractor.cc:46-110). */
+typedef struct {
+    uint32_t    struct_size;      /* = sizeof(rtjx_params), set by rtjx_params_default         */
+    const char* bam;              /* bam_      positional 1; may be NULL for add-only handles  */
+    const char* region;           /* region_   -r, default "."                                 */
+    const char* strand_tag;       /* strand_tag_ -t, default "XS" (first two chars used)       */
+    const char* fasta;            /* ref_      positional 2: must be NULL (RTJX_E_UNSUPPORTED) */
+    const char* barcode_out;      /* -b: must be NULL (RTJX_E_UNSUPPORTED)                     */
+    int32_t     strandness;       /* -s: 0 XS, 1 RF, 2 FR, 3 intron-motif(no FASTA => as FR)   */
+    uint32_t    min_anchor;       /* -a, default 8                                             */
+    uint32_t    min_intron;       /* -m, default 70                                            */
+    uint32_t    max_intron;       /* -M, default 500000                                        */
+    int32_t     device;           /* CUDA ordinal; -1 = host-only table handle (import/print)  */
+    int32_t     n_threads;        /* host BGZF inflate workers; 0 = all cores                  */
+    uint32_t    batch_reads;      /* reads per device batch; 0 = default                       */
+    uint32_t    table_log2;       /* initial junction hash capacity = 2^table_log2; 0 = default*/
+    int32_t     shard_rank;       /* contig shard of this handle (multi-GPU), default 0        */
+    int32_t     shard_world;      /* number of shards, default 1                               */
+    int32_t     inflate_mode;     /* 0 auto, 1 host zlib workers, 2 device inflate kernel      */
+    int32_t     profile;          /* 1: bracket every kernel with CUDA events (rtjx_get_stats) */
+} rtjx_params;
+
+/* One merged junction; same fields as the reference's struct Junction
+ * (junctions_extractor.h:39-112) minus the heap strings. */
+typedef struct {
+    int32_t  tid;                 /* index into the BAM header's targets (or interned name)   */
+    uint32_t start, end;          /* BED::start/end of the intron                             */
+    uint32_t thick_start, thick_end;
+    uint32_t read_count;
+    uint32_t name_index;          /* N of "JUNC%08d"                                          */
+    uint8_t  strand;              /* printed strand char                                      */
+    uint8_t  left_ok, right_ok;   /* has_left_min_anchor / has_right_min_anchor               */
+    uint8_t  pad;
+    uint64_t first_ord;           /* ordinal of the first supporting N op (naming order)      */
+} rtjx_junction;
+
+/* One candidate as the reference passes to add_junction(Junction) (before junction_qc). */
+typedef struct {
+    int32_t  tid;
+    uint32_t start, end, thick_start, thick_end;
+    uint8_t  strand;              /* strand char: '+', '-', anything else                     */
+    uint8_t  pad[3];
+} rtjx_candidate;
+
+/* A SoA batch of alignments, the unit handed to the cigar_scan kernel.
+ * Algorithmic bytes: 16*n_reads + 4*n_ops read.  meta = flag<<16 | mapq<<8 | strand_byte, where
+ * strand_byte is the value of the strand tag if its type is 'A', else 0.  cig_off has
+ * n_reads+1 entries indexing `cigar` (uint32 len<<4|op, htslib/sam.h:75-83). */
+typedef struct {
+    uint32_t        n_reads;
+    uint32_t        n_ops;
+    uint64_t        first_ordinal; /* ordinal of read 0 in iteration order                    */
+    uint32_t        n_junction_ops;/* number of N ops in `cigar` if known, else 0: the engine
+                                      then synchronises once after cigar_scan to size the merge */
+    uint32_t        reserved;
+    const int32_t*  tid;
+    const int32_t*  pos;
+    const uint32_t* meta;
+    const uint32_t* cig_off;
+    const uint32_t* cigar;
+} rtjx_batch;
+
+typedef struct {
+    uint64_t reads;               /* alignments iterated (incl. n_cigar<=1)                   */
+    uint64_t cigar_ops;
+    uint64_t candidates;          /* N ops emitted by cigar_scan                              */
+    uint64_t batches;
+    uint64_t kernel_launches;     /* launches of OUR kernels                                  */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t bgzf_blocks, compressed_bytes, inflated_bytes;
+    double   scan_ms, merge_ms, finalize_ms, inflate_kernel_ms;  /* device time, profile=1    */
+    double   host_inflate_s, host_parse_s, host_wait_s, total_s; /* wall, summed over threads */
+    uint32_t table_slots, table_grows;
+} rtjx_stats;
+
+#define RTJX_LOC_HOST   0
+#define RTJX_LOC_DEVICE 1
+
+void        rtjx_params_default(rtjx_params* p);
+
+/* JunctionsExtractor::JunctionsExtractor (junctions_extractor.h:184-205) */
+int         rtjx_create(const rtjx_params* p, rtjx_t** out);
+void        rtjx_destroy(rtjx_t* h);
+
+/* JunctionsExtractor::identify_junctions_from_BAM (junctions_extractor.cc:500-535):
+ * open + index + header + iterate region + per-read CIGAR walk + merge. */
+int         rtjx_run(rtjx_t* h);
+
+/* parse_alignment_into_junctions over a prepared batch (junctions_extractor.cc:377-497):
+ * launches cigar_scan + junction_merge on `stream` (a cudaStream_t, NULL = default stream).
+ * location = RTJX_LOC_HOST: arrays are host memory and are copied in; RTJX_LOC_DEVICE: the
+ * arrays already live in HBM (16-byte aligned) and are used in place. */
+int         rtjx_scan_batch(rtjx_t* h, const rtjx_batch* b, int location, void* stream);
+
+/* JunctionsExtractor::add_junction (junctions_extractor.cc:174-235) for n candidates, in order. */
+int         rtjx_add(rtjx_t* h, const rtjx_candidate* c, size_t n);
+
+/* Makes the merged table current (compaction, first-seen ranking, sort); implied by the getters. */
+int         rtjx_finalize(rtjx_t* h, void* stream);
+
+/* junctions_.size() after QC (get_new_junction_name, junctions_extractor.cc:152-157). */
+int64_t     rtjx_count(rtjx_t* h);
+/* get_all_junctions (junctions_extractor.cc:238-246): ALL junctions, sorted by
+ * compare_junctions (junctions_extractor.h:117-140), no anchor filter.  Returns the total
+ * number; fills at most cap. */
+int64_t     rtjx_get(rtjx_t* h, rtjx_junction* out, size_t cap);
+/* print_all_junctions (junctions_extractor.cc:249-280): BED12 of the anchor-filtered, sorted
+ * junctions to a file descriptor. */
+int         rtjx_write_bed12(rtjx_t* h, int fd);
+/* Entries of other shards (disjoint contigs) are appended; names are then ranked by
+ * (tid, first_ord), which equals BAM order for a coordinate-sorted file. */
+int         rtjx_import(rtjx_t* h, const rtjx_junction* j, size_t n);
+
+/* header->target_name[tid] (junctions_extractor.cc:384) / interning for add-only handles. */
+const char* rtjx_contig(rtjx_t* h, int32_t tid);
+int32_t     rtjx_n_contigs(rtjx_t* h);
+int32_t     rtjx_intern_contig(rtjx_t* h, const char* name);
+
+/* Contig -> shard assignment (LPT over compressed bytes per contig from the BAI pseudo-bin,
+ * hts.c:1092); assign[tid] in [0,world).  Returns n_contigs or a negative status. */
+int32_t     rtjx_plan_shards(const char* bam, int32_t world, int32_t* assign, size_t cap);
+
+int         rtjx_get_stats(rtjx_t* h, rtjx_stats* out);
+void        rtjx_reset_stats(rtjx_t* h);
+/* Drops all junctions but keeps device buffers (re-run on the same handle). */
+int         rtjx_clear(rtjx_t* h);
+
+/* Host feeder only (BGZF inflate + BAM record split into SoA): fills caller-allocated arrays
+ * for kernel-level tests and benches.  Pass NULL arrays to size: *n_reads / *n_ops are set. */
+int         rtjx_load_batch(rtjx_t* h, uint64_t* n_reads, uint64_t* n_ops, int32_t* tid, int32_t* pos,
+                            uint32_t* meta, uint32_t* cig_off, uint32_t* cigar);
+
+const char* rtjx_last_error(const rtjx_t* h);
+const char* rtjx_strerror(int status);
+const char* rtjx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTJX_H */

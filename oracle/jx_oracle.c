@@ -163,6 +163,9 @@ void jxo_read(jxo_t* o, int32_t tid, int32_t pos, uint32_t flag, uint8_t strand_
               const uint32_t* cigar, uint32_t n_cigar) {
     uint64_t ridx = o->reads_seen++;
     if (n_cigar <= 1) return;                                     /* :379 */
+    /* :383-384 `string chr(header->target_name[chr_id])` is undefined behaviour for a tid outside
+     * the header (the reference crashes); both the oracle and the product skip such reads. */
+    if (tid < 0) return;
     uint32_t start = (uint32_t)pos, thick_start = (uint32_t)pos, end = 0, thick_end = 0;
     int started = 0;
     uint32_t open_k = 0;  /* index of the N op that opened the pending junction */
@@ -513,7 +516,7 @@ static uint8_t rec_strand_byte(const rec_t* r, const char tag[2]) {
 static void feed(jxo_t* o, const rec_t* r) {
     uint8_t sb = 0;
     if (o->strandness == 0 && r->n_cigar > 1) sb = rec_strand_byte(r, o->tag);
-    jxo_read(o, r->tid, r->pos, r->flag, sb, (const uint32_t*)(r->data + r->l_qname), r->n_cigar);
+    jxo_read(o, r->tid >= o->n_contig ? -1 : r->tid, r->pos, r->flag, sb, (const uint32_t*)(r->data + r->l_qname), r->n_cigar);
 }
 
 /* hts_parse_decimal with HTS_PARSE_THOUSANDS_SEP, hts.c:1833-1875 (integers, commas, e-notation

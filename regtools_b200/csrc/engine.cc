@@ -1,0 +1,646 @@
+// regtools_b200/csrc/engine.cc — see engine.h.
+#include "engine.h"
+
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+namespace rtjx {
+
+static_assert(sizeof(rtjx_junction) == sizeof(OutJunction), "ABI junction layout must match the device layout");
+static_assert(offsetof(rtjx_junction, first_ord) == offsetof(OutJunction, first_ord), "layout");
+static_assert(offsetof(rtjx_junction, name_index) == offsetof(OutJunction, name_index), "layout");
+
+namespace {
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+uint32_t next_pow2(uint64_t x) {
+    uint64_t p = 1;
+    while (p < x) p <<= 1;
+    return (uint32_t)std::min<uint64_t>(p, 1ull << 31);
+}
+}  // namespace
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return fail(RTJX_E_CUDA, std::string(#call " failed: ") + cudaGetErrorString(e__));      \
+    } while (0)
+
+Engine::Engine(const rtjx_params& p) : prm_(p) {
+    bam_path_ = p.bam ? p.bam : "";
+    region_ = p.region ? p.region : ".";
+    tag_ = (p.strand_tag && p.strand_tag[0]) ? p.strand_tag : "XS";
+    if (tag_.size() < 2) tag_.push_back('\0');
+    prm_.bam = prm_.region = prm_.strand_tag = prm_.fasta = prm_.barcode_out = nullptr;
+    memset(&stats_, 0, sizeof stats_);
+}
+
+Engine::~Engine() {
+    if (dev_ready_) {
+        cudaSetDevice(prm_.device);
+        cudaDeviceSynchronize();
+        for (auto& pe : prof_pending_) { ev_pool_.push_back(pe.a); ev_pool_.push_back(pe.b); ev_pool_.push_back(pe.c); }
+        for (auto e : ev_pool_) cudaEventDestroy(e);
+        for (auto& d : dev_batch_) {
+            cudaFree(d.tid); cudaFree(d.pos); cudaFree(d.meta); cudaFree(d.cig_off); cudaFree(d.cigar);
+            if (d.free_ev) cudaEventDestroy(d.free_ev);
+        }
+        cudaFree(d_counters_); cudaFreeHost(h_counters_);
+        cudaFree(d_table_); cudaFree(d_spill_); cudaFree(d_cands_);
+        if (stream_) cudaStreamDestroy(stream_);
+        if (copy_stream_) cudaStreamDestroy(copy_stream_);
+    }
+}
+
+ScanParams Engine::scan_params() const {
+    ScanParams s;
+    s.strandness = prm_.strandness; s.min_anchor = prm_.min_anchor;
+    s.min_intron = prm_.min_intron; s.max_intron = prm_.max_intron;
+    return s;
+}
+
+cudaEvent_t Engine::get_event() {
+    if (!ev_pool_.empty()) { cudaEvent_t e = ev_pool_.back(); ev_pool_.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// There is no CPU fallback: a handle that has to compute needs a CUDA device.
+int Engine::ensure_device() {
+    if (dev_ready_) { cudaSetDevice(prm_.device); return RTJX_OK; }
+    if (host_only()) return fail(RTJX_E_CUDA, "this handle was created host-only (device = -1); compute entry points need a CUDA device");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(RTJX_E_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                                     "); regtools-b200 has no CPU fallback for the junction kernels");
+    if (prm_.device >= n) return fail(RTJX_E_CUDA, "CUDA device ordinal out of range");
+    CK(cudaSetDevice(prm_.device));
+    CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
+    CK(cudaMalloc(&d_counters_, CTR_COUNT * sizeof(uint32_t)));
+    CK(cudaMemset(d_counters_, 0, CTR_COUNT * sizeof(uint32_t)));
+    CK(cudaHostAlloc(&h_counters_, CTR_COUNT * sizeof(uint32_t), cudaHostAllocDefault));
+    spill_cap_ = 4096;
+    CK(cudaMalloc(&d_spill_, spill_cap_ * sizeof(Slot)));
+    dev_ready_ = true;
+    return RTJX_OK;
+}
+
+int Engine::sync_counters(cudaStream_t stream) {
+    CK(cudaMemcpyAsync(h_counters_, d_counters_, CTR_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    stats_.d2h_bytes += CTR_COUNT * sizeof(uint32_t);
+    if (h_counters_[CTR_CAND_OVERFLOW] || h_counters_[CTR_NSPILL])
+        return fail(RTJX_E_STATE, "internal: candidate buffer or junction table overflowed");
+    unique_upper_ = h_counters_[CTR_NUNIQUE];
+    stats_.candidates = (uint64_t)h_counters_[CTR_TOTAL_CAND64 + 1] << 32 | h_counters_[CTR_TOTAL_CAND64];
+    return RTJX_OK;
+}
+
+int Engine::ensure_cands(uint32_t n) {
+    if (n <= cand_cap_) return RTJX_OK;
+    CK(cudaDeviceSynchronize());
+    cudaFree(d_cands_); d_cands_ = nullptr;
+    uint32_t cap = std::max<uint32_t>(n + n / 4, 1u << 16);
+    CK(cudaMalloc(&d_cands_, (size_t)cap * sizeof(Cand)));
+    cand_cap_ = cap;
+    return RTJX_OK;
+}
+
+// Keeps the open-addressed table at load <= 0.5 even if every incoming candidate were a new key,
+// so an upsert can never run out of slots inside a kernel.
+int Engine::ensure_table(uint32_t incoming, cudaStream_t stream) {
+    if (!d_table_) {
+        uint32_t want = 1u << (prm_.table_log2 ? std::min<uint32_t>(prm_.table_log2, 30) : 22);
+        want = std::max(want, next_pow2(4ull * incoming));
+        CK(cudaMalloc(&d_table_, (size_t)want * sizeof(Slot)));
+        CK(cudaMemsetAsync(d_table_, 0, (size_t)want * sizeof(Slot), stream));
+        table_slots_ = want; unique_upper_ = 0;
+    }
+    if (2ull * (unique_upper_ + incoming) > table_slots_) {
+        int rc = sync_counters(stream);               // tighten the bound with the real count
+        if (rc) return rc;
+        if (2ull * (unique_upper_ + incoming) > table_slots_) {
+            uint32_t want = next_pow2(4ull * (unique_upper_ + incoming));
+            Slot* nt = nullptr;
+            CK(cudaMalloc(&nt, (size_t)want * sizeof(Slot)));
+            CK(cudaMemsetAsync(nt, 0, (size_t)want * sizeof(Slot), stream));
+            CK(cudaMemsetAsync(d_counters_ + CTR_NUNIQUE, 0, sizeof(uint32_t), stream));
+            launch_table_rehash(d_table_, table_slots_, nt, want - 1, d_counters_, stream);
+            stats_.kernel_launches++;
+            CK(cudaStreamSynchronize(stream));
+            cudaFree(d_table_);
+            d_table_ = nt; table_slots_ = want; stats_.table_grows++;
+        }
+    }
+    unique_upper_ += incoming;
+    return RTJX_OK;
+}
+
+// cand_bound = number of N ops in the batch when the producer knows it (the feeder counts them while
+// copying CIGARs); 0 = unknown: size the candidate buffer for the worst case and read the real
+// count back after cigar_scan (one stream synchronisation) before sizing the merge.
+int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaStream_t stream) {
+    int rc;
+    const bool known = cand_bound != 0;
+    if ((rc = ensure_cands(known ? cand_bound : std::max(v.n_ops, 1u)))) return rc;
+    if (known && (rc = ensure_table(cand_bound, stream))) return rc;
+    CK(cudaMemsetAsync(d_counters_ + CTR_NCAND, 0, sizeof(uint32_t), stream));
+    ProfEv pe{nullptr, nullptr, nullptr};
+    if (prm_.profile) { pe.a = get_event(); pe.b = get_event(); pe.c = get_event(); cudaEventRecord(pe.a, stream); }
+    launch_cigar_scan(v, scan_params(), d_cands_, cand_cap_, d_counters_, stream);
+    if (prm_.profile) cudaEventRecord(pe.b, stream);
+    if (!known) {
+        if ((rc = sync_counters(stream))) return rc;     // also tightens unique_upper_
+        cand_bound = h_counters_[CTR_NCAND];
+        if ((rc = ensure_table(std::max(cand_bound, 1u), stream))) return rc;
+    }
+    launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, cand_bound, scan_params(), d_table_, table_slots_ - 1,
+                          d_spill_, spill_cap_, d_counters_, stream);
+    if (prm_.profile) { cudaEventRecord(pe.c, stream); prof_pending_.push_back(pe); }
+    CK(cudaGetLastError());
+    stats_.kernel_launches += (v.n_reads ? 1 : 0) + (cand_bound ? 1 : 0);
+    stats_.reads += v.n_reads; stats_.cigar_ops += v.n_ops; stats_.batches++;
+    dirty_ = true; finalized_ = false;
+    if (prof_pending_.size() > 4096) resolve_profile_events();
+    return RTJX_OK;
+}
+
+void Engine::resolve_profile_events() {
+    for (auto& pe : prof_pending_) {
+        cudaEventSynchronize(pe.c);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) stats_.scan_ms += ms;
+        if (cudaEventElapsedTime(&ms, pe.b, pe.c) == cudaSuccess) stats_.merge_ms += ms;
+        ev_pool_.push_back(pe.a); ev_pool_.push_back(pe.b); ev_pool_.push_back(pe.c);
+    }
+    prof_pending_.clear();
+}
+
+int Engine::ensure_dev_batch(DevBatch& d, uint32_t reads, uint32_t ops) {
+    if (!d.free_ev) CK(cudaEventCreateWithFlags(&d.free_ev, cudaEventDisableTiming));
+    if (reads > d.cap_reads) {
+        CK(cudaEventSynchronize(d.free_ev));
+        cudaFree(d.tid); cudaFree(d.pos); cudaFree(d.meta); cudaFree(d.cig_off);
+        uint32_t cap = std::max(reads, 1u << 12);
+        CK(cudaMalloc(&d.tid, (size_t)cap * 4)); CK(cudaMalloc(&d.pos, (size_t)cap * 4));
+        CK(cudaMalloc(&d.meta, (size_t)cap * 4)); CK(cudaMalloc(&d.cig_off, ((size_t)cap + 4) * 4));
+        d.cap_reads = cap;
+    }
+    if (ops > d.cap_ops) {
+        CK(cudaEventSynchronize(d.free_ev));
+        cudaFree(d.cigar);
+        uint32_t cap = std::max(ops, 1u << 12);
+        CK(cudaMalloc(&d.cigar, ((size_t)cap + 4) * 4));
+        d.cap_ops = cap;
+    }
+    return RTJX_OK;
+}
+
+int Engine::scan_batch(const rtjx_batch& b, int location, cudaStream_t user_stream) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (b.n_reads == 0) return RTJX_OK;
+    if (!b.tid || !b.pos || !b.meta || !b.cig_off || (b.n_ops && !b.cigar)) return fail(RTJX_E_ARG, "null array in batch");
+    cudaStream_t st = user_stream ? user_stream : stream_;
+    BatchView v;
+    v.n_reads = b.n_reads; v.n_ops = b.n_ops; v.first_ordinal = b.first_ordinal;
+    if (location == RTJX_LOC_DEVICE) {
+        if ((reinterpret_cast<uintptr_t>(b.cigar) & 15u) != 0) return fail(RTJX_E_ARG, "device cigar array must be 16-byte aligned");
+        v.tid = b.tid; v.pos = b.pos; v.meta = b.meta; v.cig_off = b.cig_off; v.cigar = b.cigar;
+    } else if (location == RTJX_LOC_HOST) {
+        DevBatch& d = dev_batch_[dev_batch_next_]; dev_batch_next_ ^= 1;
+        if ((rc = ensure_dev_batch(d, b.n_reads, b.n_ops))) return rc;
+        CK(cudaStreamWaitEvent(st, d.free_ev, 0));
+        CK(cudaMemcpyAsync(d.tid, b.tid, (size_t)b.n_reads * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d.pos, b.pos, (size_t)b.n_reads * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d.meta, b.meta, (size_t)b.n_reads * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d.cig_off, b.cig_off, ((size_t)b.n_reads + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (b.n_ops) CK(cudaMemcpyAsync(d.cigar, b.cigar, (size_t)b.n_ops * 4, cudaMemcpyHostToDevice, st));
+        stats_.h2d_bytes += (size_t)b.n_reads * 16 + 4 + (size_t)b.n_ops * 4;
+        v.tid = d.tid; v.pos = d.pos; v.meta = d.meta; v.cig_off = d.cig_off; v.cigar = d.cigar;
+        rc = process_device_batch(v, b.n_junction_ops, st);
+        cudaEventRecord(d.free_ev, st);
+        return rc;
+    } else {
+        return fail(RTJX_E_ARG, "location must be RTJX_LOC_HOST or RTJX_LOC_DEVICE");
+    }
+    return process_device_batch(v, b.n_junction_ops, st);
+}
+
+int Engine::add(const rtjx_candidate* c, size_t n) {
+    int rc = ensure_device();
+    if (rc) return rc;
+    if (n == 0) return RTJX_OK;
+    if (!c) return fail(RTJX_E_ARG, "null candidates");
+    // add_junction is called once per candidate in order; order is carried by the ordinal.
+    const size_t CH = 1u << 20;
+    std::vector<Cand> h;
+    for (size_t o = 0; o < n; o += CH) {
+        size_t m = std::min(CH, n - o);
+        h.resize(m);
+        for (size_t i = 0; i < m; ++i) {
+            const rtjx_candidate& s = c[o + i];
+            Cand& d = h[i];
+            d.start = s.start; d.end = s.end; d.ts = s.thick_start; d.te = s.thick_end;
+            d.ord = (add_ord_ + i) << 16; d.tid = s.tid; d.strand = s.strand;
+        }
+        if ((rc = ensure_cands((uint32_t)m))) return rc;
+        if ((rc = ensure_table((uint32_t)m, stream_))) return rc;
+        CK(cudaMemcpyAsync(d_cands_, h.data(), m * sizeof(Cand), cudaMemcpyHostToDevice, stream_));
+        launch_junction_merge(d_cands_, nullptr, (uint32_t)m, scan_params(), d_table_, table_slots_ - 1, d_spill_, spill_cap_,
+                              d_counters_, stream_);
+        CK(cudaStreamSynchronize(stream_));
+        add_ord_ += m; stats_.kernel_launches++; stats_.h2d_bytes += m * sizeof(Cand);
+    }
+    dirty_ = true; finalized_ = false;
+    return RTJX_OK;
+}
+
+// ---- whole-file / region run ---------------------------------------------------------------------
+struct EngineSink : BatchSink {
+    static constexpr int NB = 3;
+    Engine* e; HostBatch hb[NB]; cudaEvent_t done[NB]; bool in_flight[NB]; int next = 0; int rc = 0;
+    uint32_t cap_reads, cap_ops;
+    EngineSink(Engine* eng, uint32_t reads, uint32_t ops) : e(eng), cap_reads(reads), cap_ops(ops) {
+        for (int i = 0; i < NB; ++i) { done[i] = nullptr; in_flight[i] = false; }
+    }
+    int init() {
+        for (int i = 0; i < NB; ++i) {
+            HostBatch& b = hb[i];
+            if (cudaHostAlloc(&b.tid, (size_t)cap_reads * 4, cudaHostAllocDefault) != cudaSuccess ||
+                cudaHostAlloc(&b.pos, (size_t)cap_reads * 4, cudaHostAllocDefault) != cudaSuccess ||
+                cudaHostAlloc(&b.meta, (size_t)cap_reads * 4, cudaHostAllocDefault) != cudaSuccess ||
+                cudaHostAlloc(&b.cig_off, ((size_t)cap_reads + 1) * 4, cudaHostAllocDefault) != cudaSuccess ||
+                cudaHostAlloc(&b.cigar, (size_t)cap_ops * 4, cudaHostAllocDefault) != cudaSuccess ||
+                cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess)
+                return e->fail(RTJX_E_CUDA, "pinned batch allocation failed");
+            b.cap_reads = cap_reads; b.cap_ops = cap_ops;
+        }
+        return RTJX_OK;
+    }
+    ~EngineSink() override {
+        for (int i = 0; i < NB; ++i) {
+            if (in_flight[i]) cudaEventSynchronize(done[i]);
+            cudaFreeHost(hb[i].tid); cudaFreeHost(hb[i].pos); cudaFreeHost(hb[i].meta);
+            cudaFreeHost(hb[i].cig_off); cudaFreeHost(hb[i].cigar);
+            if (done[i]) cudaEventDestroy(done[i]);
+        }
+    }
+    HostBatch* acquire() override {
+        int j = next; next = (next + 1) % NB;
+        if (in_flight[j]) { double t0 = now_s(); cudaEventSynchronize(done[j]); in_flight[j] = false; e->stats_.host_wait_s += now_s() - t0; }
+        return &hb[j];
+    }
+    void submit(HostBatch* b) override {
+        if (rc || b->n_reads == 0) return;
+        int j = (int)(b - hb);
+        rc = push(*b, j);
+    }
+    int push(HostBatch& b, int j) {
+        Engine::DevBatch& d = e->dev_batch_[e->dev_batch_next_]; e->dev_batch_next_ ^= 1;
+        int r = e->ensure_dev_batch(d, b.n_reads, b.n_ops);
+        if (r) return r;
+        cudaStream_t cs = e->copy_stream_, ks = e->stream_;
+        cudaStreamWaitEvent(cs, d.free_ev, 0);
+        cudaMemcpyAsync(d.tid, b.tid, (size_t)b.n_reads * 4, cudaMemcpyHostToDevice, cs);
+        cudaMemcpyAsync(d.pos, b.pos, (size_t)b.n_reads * 4, cudaMemcpyHostToDevice, cs);
+        cudaMemcpyAsync(d.meta, b.meta, (size_t)b.n_reads * 4, cudaMemcpyHostToDevice, cs);
+        cudaMemcpyAsync(d.cig_off, b.cig_off, ((size_t)b.n_reads + 1) * 4, cudaMemcpyHostToDevice, cs);
+        if (b.n_ops) cudaMemcpyAsync(d.cigar, b.cigar, (size_t)b.n_ops * 4, cudaMemcpyHostToDevice, cs);
+        cudaEventRecord(done[j], cs);
+        in_flight[j] = true;
+        e->stats_.h2d_bytes += (size_t)b.n_reads * 16 + 4 + (size_t)b.n_ops * 4;
+        cudaStreamWaitEvent(ks, done[j], 0);
+        BatchView v;
+        v.n_reads = b.n_reads; v.n_ops = b.n_ops; v.first_ordinal = b.first_ordinal;
+        v.tid = d.tid; v.pos = d.pos; v.meta = d.meta; v.cig_off = d.cig_off; v.cigar = d.cigar;
+        r = e->process_device_batch(v, b.n_junction_ops, ks);
+        cudaEventRecord(d.free_ev, ks);
+        return r;
+    }
+};
+
+int Engine::open_bam(std::unique_ptr<BamFile>* bam, BaiIndex* idx, IterSpec* spec) {
+    if (bam_path_.empty()) return fail(RTJX_E_ARG, "no BAM given");
+    std::string err;
+    bam->reset(new BamFile());
+    if (access(bam_path_.c_str(), R_OK) != 0) return fail(RTJX_E_OPEN_BAM, "Unable to open BAM/SAM file.\n\n");
+    bool csi = false;
+    const bool have_idx = BaiIndex::load_for_bam(bam_path_, idx, &csi);
+    if (!(*bam)->open(bam_path_, &err)) {
+        // the reference opens any readable file and fails later at the index or the header
+        if (!have_idx && !csi) return fail(RTJX_E_OPEN_INDEX, "Unable to open BAM/SAM index. Make sure alignments are indexed\n\n");
+        return fail(RTJX_E_REGION, "Unable to iterate to region within BAM.\n\n");
+    }
+    if (!have_idx) {
+        if (csi) return fail(RTJX_E_UNSUPPORTED, "only .bai indexes are supported by the B200 path (.csi found)");
+        return fail(RTJX_E_OPEN_INDEX, "Unable to open BAM/SAM index. Make sure alignments are indexed\n\n");
+    }
+    contigs_ = (*bam)->header().names;
+    if (!parse_region(**bam, region_, spec)) return fail(RTJX_E_REGION, "Unable to iterate to region within BAM.\n\n");
+    if (prm_.shard_world > 1) {
+        if (spec->kind != IterSpec::WholeFile) return fail(RTJX_E_ARG, "contig sharding needs region \".\"");
+        std::vector<int32_t> assign = plan_contig_shards(**bam, *idx, prm_.shard_world);
+        spec->kind = IterSpec::Contigs;
+        for (size_t t = 0; t < assign.size(); ++t) if (assign[t] == prm_.shard_rank) spec->contigs.push_back((int32_t)t);
+    } else if (spec->kind == IterSpec::WholeFile) {
+        uint64_t off0;
+        if (!idx->whole_file_start(&off0)) return fail(RTJX_E_REGION, "Unable to iterate to region within BAM.\n\n");
+    } else if (spec->kind == IterSpec::Region) {
+        if (spec->end < spec->beg || (size_t)spec->tid >= idx->refs.size())
+            return fail(RTJX_E_REGION, "Unable to iterate to region within BAM.\n\n");
+    }
+    return RTJX_OK;
+}
+
+int Engine::run() {
+    const double t_start = now_s();
+    std::unique_ptr<BamFile> bam; BaiIndex idx; IterSpec spec;
+    int rc = open_bam(&bam, &idx, &spec);
+    if (rc) return rc;
+    if ((rc = ensure_device())) return rc;
+    uint32_t reads = prm_.batch_reads ? prm_.batch_reads : (spec.kind == IterSpec::Region ? (1u << 15) : (1u << 20));
+    reads = std::max(reads, 1024u);
+    uint32_t ops = std::max<uint32_t>(2 * reads, 1u << 17);      // one read may carry 65535 ops
+    EngineSink sink(this, reads, ops);
+    if ((rc = sink.init())) return rc;
+    FeederOptions fo;
+    fo.n_threads = prm_.n_threads; fo.xs_mode = prm_.strandness == 0; fo.tag[0] = tag_[0]; fo.tag[1] = tag_[1];
+    FeederStats fs; std::string err;
+    uint64_t reads_before = stats_.reads;
+    if (!feed_alignments(*bam, idx, spec, fo, &sink, &fs, &err)) return fail(RTJX_E_REGION, "Unable to iterate to region within BAM.\n\n");
+    if (sink.rc) return sink.rc;
+    CK(cudaStreamSynchronize(copy_stream_));
+    CK(cudaStreamSynchronize(stream_));
+    (void)reads_before;
+    stats_.bgzf_blocks += fs.bgzf_blocks; stats_.compressed_bytes += fs.compressed_bytes; stats_.inflated_bytes += fs.inflated_bytes;
+    stats_.host_inflate_s += fs.inflate_s; stats_.host_parse_s += fs.parse_s; stats_.host_wait_s += fs.wait_s;
+    stats_.total_s += now_s() - t_start;
+    return RTJX_OK;
+}
+
+// ---- feeder-only: SoA arrays for kernel-level tests and benches ----------------------------------
+struct Engine::LoadedBatch {
+    std::vector<int32_t> tid, pos; std::vector<uint32_t> meta, off, cigar;
+};
+
+namespace {
+struct VectorSink : BatchSink {
+    HostBatch hb; std::vector<int32_t> tid, pos; std::vector<uint32_t> meta, off, cig;
+    std::vector<int32_t>* otid; std::vector<int32_t>* opos; std::vector<uint32_t>* ometa; std::vector<uint32_t>* ooff; std::vector<uint32_t>* ocig;
+    VectorSink(uint32_t reads, uint32_t ops) : tid(reads), pos(reads), meta(reads), off(reads + 1), cig(ops) {
+        hb.tid = tid.data(); hb.pos = pos.data(); hb.meta = meta.data(); hb.cig_off = off.data(); hb.cigar = cig.data();
+        hb.cap_reads = reads; hb.cap_ops = ops;
+    }
+    HostBatch* acquire() override { return &hb; }
+    void submit(HostBatch* b) override {
+        uint32_t base = (uint32_t)ocig->size();
+        otid->insert(otid->end(), b->tid, b->tid + b->n_reads);
+        opos->insert(opos->end(), b->pos, b->pos + b->n_reads);
+        ometa->insert(ometa->end(), b->meta, b->meta + b->n_reads);
+        for (uint32_t i = 0; i < b->n_reads; ++i) ooff->push_back(base + b->cig_off[i]);
+        ocig->insert(ocig->end(), b->cigar, b->cigar + b->n_ops);
+    }
+};
+}  // namespace
+
+int Engine::load_batch(uint64_t* n_reads, uint64_t* n_ops, int32_t* tid, int32_t* pos, uint32_t* meta,
+                       uint32_t* cig_off, uint32_t* cigar) {
+    if (!n_reads || !n_ops) return fail(RTJX_E_ARG, "n_reads/n_ops must not be NULL");
+    if (!loaded_) {
+        std::unique_ptr<BamFile> bam; BaiIndex idx; IterSpec spec;
+        int rc = open_bam(&bam, &idx, &spec);
+        if (rc) return rc;
+        loaded_.reset(new LoadedBatch());
+        VectorSink sink(1u << 18, 1u << 20);
+        sink.otid = &loaded_->tid; sink.opos = &loaded_->pos; sink.ometa = &loaded_->meta; sink.ooff = &loaded_->off; sink.ocig = &loaded_->cigar;
+        FeederOptions fo;
+        fo.n_threads = prm_.n_threads; fo.xs_mode = prm_.strandness == 0; fo.tag[0] = tag_[0]; fo.tag[1] = tag_[1];
+        FeederStats fs; std::string err;
+        if (!feed_alignments(*bam, idx, spec, fo, &sink, &fs, &err)) { loaded_.reset(); return fail(RTJX_E_REGION, "Unable to iterate to region within BAM.\n\n"); }
+        if (loaded_->cigar.size() > 0xffffffffull || loaded_->tid.size() > 0xfffffffeull) { loaded_.reset(); return fail(RTJX_E_ARG, "too many alignments for one batch; use a region"); }
+        loaded_->off.push_back((uint32_t)loaded_->cigar.size());
+    }
+    *n_reads = loaded_->tid.size(); *n_ops = loaded_->cigar.size();
+    if (tid && pos && meta && cig_off && (cigar || loaded_->cigar.empty())) {
+        memcpy(tid, loaded_->tid.data(), loaded_->tid.size() * 4);
+        memcpy(pos, loaded_->pos.data(), loaded_->pos.size() * 4);
+        memcpy(meta, loaded_->meta.data(), loaded_->meta.size() * 4);
+        memcpy(cig_off, loaded_->off.data(), loaded_->off.size() * 4);
+        if (!loaded_->cigar.empty()) memcpy(cigar, loaded_->cigar.data(), loaded_->cigar.size() * 4);
+        loaded_.reset();
+    }
+    return RTJX_OK;
+}
+
+// ---- finalize ------------------------------------------------------------------------------------
+namespace {
+// rank of each contig name in std::string order, equal names get equal ranks (compare_junctions,
+// junctions_extractor.h:120-126 compares the chrom strings)
+std::vector<uint32_t> contig_ranks(const std::vector<std::string>& names) {
+    std::vector<uint32_t> order(names.size()), rank(names.size());
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return names[a] < names[b]; });
+    uint32_t r = 0;
+    for (size_t i = 0; i < order.size(); ++i) {
+        if (i && names[order[i]] != names[order[i - 1]]) ++r;
+        rank[order[i]] = r;
+    }
+    return rank;
+}
+inline int name_cmp(uint32_t a, uint32_t b) {        // std::string compare of "JUNC%08d"
+    if (a == b) return 0;
+    if (a < 100000000u && b < 100000000u) return a < b ? -1 : 1;
+    char sa[16], sb[16];
+    snprintf(sa, sizeof sa, "%08d", (int)a); snprintf(sb, sizeof sb, "%08d", (int)b);
+    return strcmp(sa, sb);
+}
+}  // namespace
+
+void Engine::host_rank_and_sort() {
+    const bool sharded = !imported_.empty();
+    final_.insert(final_.end(), imported_.begin(), imported_.end());
+    std::vector<uint32_t> order(final_.size());
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const rtjx_junction &x = final_[a], &y = final_[b];
+        if (sharded && x.tid != y.tid) return x.tid < y.tid;
+        return x.first_ord < y.first_ord;
+    });
+    for (size_t r = 0; r < order.size(); ++r) final_[order[r]].name_index = (uint32_t)(r + 1);
+    std::vector<uint32_t> cr = contig_ranks(contigs_);
+    auto crank = [&](int32_t tid) { return (tid >= 0 && (size_t)tid < cr.size()) ? cr[(size_t)tid] : 0x40000000u + (uint32_t)tid; };
+    std::sort(final_.begin(), final_.end(), [&](const rtjx_junction& x, const rtjx_junction& y) {
+        uint32_t cx = crank(x.tid), cy = crank(y.tid);
+        if (cx != cy) return cx < cy;
+        if (x.thick_start != y.thick_start) return x.thick_start < y.thick_start;
+        if (x.thick_end != y.thick_end) return x.thick_end < y.thick_end;
+        return name_cmp(x.name_index, y.name_index) < 0;
+    });
+}
+
+int Engine::finalize(cudaStream_t user_stream) {
+    if (finalized_ && !dirty_) return RTJX_OK;
+    final_.clear();
+    uint32_t n = 0;
+    if (dev_ready_ && d_table_) {
+        cudaSetDevice(prm_.device);
+        cudaStream_t st = user_stream ? user_stream : stream_;
+        int rc = sync_counters(st);
+        if (rc) return rc;
+        n = h_counters_[CTR_NUNIQUE];
+        if (n) {
+            OutJunction *d_out = nullptr, *d_sorted = nullptr; void* ws = nullptr; uint32_t* d_rank = nullptr;
+            const size_t ws_bytes = finalize_sort_workspace_bytes(n);
+            std::vector<uint32_t> cr = contig_ranks(contigs_);
+            CK(cudaMalloc(&d_out, (size_t)n * sizeof(OutJunction)));
+            CK(cudaMalloc(&d_sorted, (size_t)n * sizeof(OutJunction)));
+            CK(cudaMalloc(&ws, ws_bytes));
+            CK(cudaMalloc(&d_rank, std::max<size_t>(cr.size(), 1) * 4));
+            if (!cr.empty()) CK(cudaMemcpyAsync(d_rank, cr.data(), cr.size() * 4, cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(d_counters_ + CTR_NOUT, 0, sizeof(uint32_t), st));
+            cudaEvent_t ea = nullptr, eb = nullptr;
+            if (prm_.profile) { ea = get_event(); eb = get_event(); cudaEventRecord(ea, st); }
+            launch_table_compact(d_table_, table_slots_, d_out, n, d_counters_ + CTR_NOUT, st);
+            launch_finalize_sort(d_out, d_sorted, n, d_rank, (uint32_t)cr.size(), ws, ws_bytes, st);
+            if (prm_.profile) cudaEventRecord(eb, st);
+            final_.resize(n);
+            CK(cudaMemcpyAsync(final_.data(), d_sorted, (size_t)n * sizeof(OutJunction), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            if (prm_.profile) { float ms = 0; if (cudaEventElapsedTime(&ms, ea, eb) == cudaSuccess) stats_.finalize_ms += ms; ev_pool_.push_back(ea); ev_pool_.push_back(eb); }
+            stats_.kernel_launches += 5;     // ours: compact + 3 key builders + gather (CUB's sort passes not counted)
+            stats_.d2h_bytes += (size_t)n * sizeof(OutJunction);
+            cudaFree(d_out); cudaFree(d_sorted); cudaFree(ws); cudaFree(d_rank);
+        }
+    }
+    if (!imported_.empty() || n >= 100000000u) host_rank_and_sort();
+    finalized_ = true; dirty_ = false;
+    return RTJX_OK;
+}
+
+int64_t Engine::count() {
+    int rc = finalize(nullptr);
+    return rc ? rc : (int64_t)final_.size();
+}
+
+int64_t Engine::get(rtjx_junction* out, size_t cap) {
+    int rc = finalize(nullptr);
+    if (rc) return rc;
+    if (out && cap) memcpy(out, final_.data(), std::min(cap, final_.size()) * sizeof(rtjx_junction));
+    return (int64_t)final_.size();
+}
+
+int Engine::import(const rtjx_junction* j, size_t n) {
+    if (n && !j) return fail(RTJX_E_ARG, "null junctions");
+    imported_.insert(imported_.end(), j, j + n);
+    finalized_ = false;
+    return RTJX_OK;
+}
+
+int Engine::clear() {
+    final_.clear(); imported_.clear(); finalized_ = false; dirty_ = false; unique_upper_ = 0; add_ord_ = 0;
+    if (dev_ready_) {
+        cudaSetDevice(prm_.device);
+        if (d_table_) CK(cudaMemsetAsync(d_table_, 0, (size_t)table_slots_ * sizeof(Slot), stream_));
+        CK(cudaMemsetAsync(d_counters_, 0, CTR_COUNT * sizeof(uint32_t), stream_));
+        CK(cudaStreamSynchronize(stream_));
+    }
+    return RTJX_OK;
+}
+
+// ---- BED12 (Junction::print, junctions_extractor.h:90-98; anchor filter junctions_extractor.cc:267)
+namespace {
+inline char* put_u32(char* p, uint32_t v) {
+    char tmp[10]; int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+}  // namespace
+
+int Engine::write_bed12(int fd) {
+    int rc = finalize(nullptr);
+    if (rc) return rc;
+    std::vector<char> buf;
+    buf.reserve(1u << 20);
+    auto flush = [&]() -> bool {
+        size_t off = 0;
+        while (off < buf.size()) {
+            ssize_t w = ::write(fd, buf.data() + off, buf.size() - off);
+            if (w <= 0) return false;
+            off += (size_t)w;
+        }
+        buf.clear();
+        return true;
+    };
+    for (const rtjx_junction& j : final_) {
+        if (!(j.left_ok && j.right_ok)) continue;
+        const char* chrom = contig(j.tid);
+        size_t cl = strlen(chrom);
+        size_t o = buf.size();
+        buf.resize(o + cl + 160);
+        char* p = buf.data() + o;
+        memcpy(p, chrom, cl); p += cl;
+        *p++ = '\t'; p = put_u32(p, j.thick_start);
+        *p++ = '\t'; p = put_u32(p, j.thick_end);
+        memcpy(p, "\tJUNC", 5); p += 5;
+        {   // setfill('0') << setw(8) << int
+            char tmp[12]; int n = snprintf(tmp, sizeof tmp, "%08d", (int)j.name_index);
+            memcpy(p, tmp, (size_t)n); p += n;
+        }
+        *p++ = '\t'; p = put_u32(p, j.read_count);
+        *p++ = '\t'; *p++ = (char)j.strand;
+        *p++ = '\t'; p = put_u32(p, j.thick_start);
+        *p++ = '\t'; p = put_u32(p, j.thick_end);
+        memcpy(p, "\t255,0,0\t2\t", 11); p += 11;
+        p = put_u32(p, j.start - j.thick_start); *p++ = ','; p = put_u32(p, j.thick_end - j.end);
+        memcpy(p, "\t0,", 3); p += 3;
+        p = put_u32(p, j.end - j.thick_start);
+        *p++ = '\n';
+        buf.resize((size_t)(p - buf.data()));
+        if (buf.size() > (1u << 20) - 4096) if (!flush()) return fail(RTJX_E_IO, "write failed");
+    }
+    if (!flush()) return fail(RTJX_E_IO, "write failed");
+    return RTJX_OK;
+}
+
+const char* Engine::contig(int32_t tid) {
+    if (tid >= 0 && (size_t)tid < contigs_.size()) return contigs_[(size_t)tid].c_str();
+    unknown_contig_ = "tid" + std::to_string(tid);
+    return unknown_contig_.c_str();
+}
+
+int32_t Engine::intern_contig(const char* name) {
+    if (!name) return -1;
+    for (size_t i = 0; i < contigs_.size(); ++i) if (contigs_[i] == name) return (int32_t)i;
+    contigs_.push_back(name);
+    finalized_ = false;
+    return (int32_t)contigs_.size() - 1;
+}
+
+void Engine::get_stats(rtjx_stats* out) {
+    if (dev_ready_) {
+        cudaSetDevice(prm_.device);
+        resolve_profile_events();
+    }
+    stats_.table_slots = table_slots_;
+    *out = stats_;
+}
+
+void Engine::reset_stats() {
+    if (dev_ready_) { cudaSetDevice(prm_.device); resolve_profile_events(); }
+    memset(&stats_, 0, sizeof stats_);
+}
+
+}  // namespace rtjx

@@ -1,0 +1,101 @@
+// regtools_b200/csrc/engine.h — per-handle state behind the C ABI (include/rtjx.h).
+//
+// Owns the device-side junction table, the candidate buffer, the pinned/HBM batch rings and the
+// host copy of the finalized table.  Mirrors the life cycle of the reference's JunctionsExtractor
+// object (/root/reference/src/junctions/junctions_extractor.h:149-248).
+#pragma once
+#include "../../include/rtjx.h"
+#include "bam_feeder.h"
+#include "jx_device.cuh"
+
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace rtjx {
+
+class Engine {
+public:
+    explicit Engine(const rtjx_params& p);
+    ~Engine();
+
+    int run();
+    int scan_batch(const rtjx_batch& b, int location, cudaStream_t stream);
+    int add(const rtjx_candidate* c, size_t n);
+    int finalize(cudaStream_t stream);
+    int64_t count();
+    int64_t get(rtjx_junction* out, size_t cap);
+    int write_bed12(int fd);
+    int import(const rtjx_junction* j, size_t n);
+    int clear();
+    int load_batch(uint64_t* n_reads, uint64_t* n_ops, int32_t* tid, int32_t* pos, uint32_t* meta,
+                   uint32_t* cig_off, uint32_t* cigar);
+
+    const char* contig(int32_t tid);
+    int32_t n_contigs() const { return (int32_t)contigs_.size(); }
+    int32_t intern_contig(const char* name);
+
+    void get_stats(rtjx_stats* out);
+    void reset_stats();
+    const char* last_error() const { return err_.c_str(); }
+    int fail(int status, const std::string& msg) { err_ = msg; return status; }
+    bool host_only() const { return prm_.device < 0; }
+
+private:
+    friend struct EngineSink;
+    int ensure_device();
+    int ensure_cands(uint32_t n);
+    int ensure_table(uint32_t incoming_bound, cudaStream_t stream);
+    int process_device_batch(const BatchView& v, uint32_t cand_bound, cudaStream_t stream);
+    int sync_counters(cudaStream_t stream);
+    int open_bam(std::unique_ptr<BamFile>* bam, BaiIndex* idx, IterSpec* spec);
+    void host_rank_and_sort();
+    void resolve_profile_events();
+    ScanParams scan_params() const;
+
+    rtjx_params prm_;
+    std::string bam_path_, region_, tag_;
+    std::string err_;
+    std::vector<std::string> contigs_;
+    std::string unknown_contig_;
+
+    // device state
+    bool dev_ready_ = false;
+    cudaStream_t stream_ = nullptr, copy_stream_ = nullptr;
+    uint32_t* d_counters_ = nullptr;
+    uint32_t* h_counters_ = nullptr;            // pinned mirror
+    Slot* d_table_ = nullptr; uint32_t table_slots_ = 0;
+    Slot* d_spill_ = nullptr; uint32_t spill_cap_ = 0;
+    Cand* d_cands_ = nullptr; uint32_t cand_cap_ = 0;
+    uint64_t unique_upper_ = 0;                 // host-side upper bound of occupied slots
+    uint64_t add_ord_ = 0;                      // ordinal of the next rtjx_add candidate
+    bool dirty_ = false;                        // device table changed since the last finalize
+
+    // device batch ring for host-resident input
+    struct DevBatch {
+        int32_t* tid = nullptr; int32_t* pos = nullptr; uint32_t* meta = nullptr; uint32_t* cig_off = nullptr;
+        uint32_t* cigar = nullptr; uint32_t cap_reads = 0, cap_ops = 0; cudaEvent_t free_ev = nullptr;
+    };
+    DevBatch dev_batch_[2];
+    int dev_batch_next_ = 0;
+    int ensure_dev_batch(DevBatch& d, uint32_t reads, uint32_t ops);
+
+    // finalized table (host)
+    std::vector<rtjx_junction> final_;
+    std::vector<rtjx_junction> imported_;
+    bool finalized_ = false;
+
+    // cached feeder output for load_batch
+    struct LoadedBatch;
+    std::unique_ptr<LoadedBatch> loaded_;
+
+    // profiling
+    struct ProfEv { cudaEvent_t a, b, c; };
+    std::vector<ProfEv> prof_pending_;
+    std::vector<cudaEvent_t> ev_pool_;
+    cudaEvent_t get_event();
+
+    rtjx_stats stats_;
+};
+
+}  // namespace rtjx

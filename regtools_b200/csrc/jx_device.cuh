@@ -1,0 +1,82 @@
+// regtools_b200/csrc/jx_device.cuh — device-side data layout shared by the kernels and the engine.
+//
+// Everything on the hot path is 32/64-bit integer work bounded by HBM bandwidth; there is no
+// GEMM-shaped step and therefore no tensor-core use.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rtjx {
+
+// One raw candidate = one N op of one alignment, written by cigar_scan, read by junction_merge.
+// 32 bytes, 16-byte aligned so a thread moves it as two 128-bit accesses.
+struct alignas(16) Cand {
+    uint32_t start, end;          // intron [start,end)                      (A.2: start_k, end_k)
+    uint32_t ts, te;              // thick_start / thick_end of THIS read
+    uint64_t ord;                 // read_ordinal << 16 | k   (k = index of the N op in the CIGAR)
+    int32_t  tid;
+    uint32_t strand;              // strand char of the read in the low byte
+};
+static_assert(sizeof(Cand) == 32, "Cand must be 32 bytes");
+
+// One slot of the device-wide open-addressed junction table (linear probing).
+// The 128-bit key is claimed with a single ATOMG.CAS.128; an all-zero slot is empty, so the
+// table is (re)initialised with cudaMemsetAsync.  min-reductions are stored complemented so that
+// zero is the identity of every field:
+//   count : atomicAdd        nts   : atomicMax(~thick_start)  te : atomicMax(thick_end)
+//   lr    : atomicOr (bit0 = left anchor ok, bit1 = right anchor ok)
+//   nfirst: atomicMax(~first_ord)   -> name rank  (first-seen,  junctions_extractor.cc:152-157,198)
+//   last  : atomicMax(read_ord<<8|strand_char) -> printed strand (last writer, :229), proxy 2 only
+struct alignas(16) Slot {
+    unsigned long long klo;       // start << 32 | end
+    unsigned long long khi;       // (tid + 1) << 2 | proxy      (non-zero for every real key)
+    uint32_t count, nts, te, lr;
+    unsigned long long nfirst, last;
+};
+static_assert(sizeof(Slot) == 48, "Slot must be 48 bytes");
+
+// Compacted table entry produced by finalize (same layout as rtjx_junction in include/rtjx.h).
+struct alignas(8) OutJunction {
+    int32_t  tid;
+    uint32_t start, end, ts, te, count, name_index;
+    uint8_t  strand, left_ok, right_ok, pad;
+    uint64_t first_ord;
+};
+static_assert(sizeof(OutJunction) == 40, "OutJunction must be 40 bytes");
+
+struct ScanParams {
+    int32_t  strandness;          // 0 XS, 1 RF, 2/3 FR
+    uint32_t min_anchor, min_intron, max_intron;
+};
+
+struct BatchView {
+    uint32_t n_reads, n_ops;
+    uint64_t first_ordinal;
+    const int32_t*  tid;
+    const int32_t*  pos;
+    const uint32_t* meta;
+    const uint32_t* cig_off;
+    const uint32_t* cigar;
+};
+
+// Launchers (kernels.cu).  All are asynchronous on `stream`.
+void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
+                       uint32_t* d_counters /* [0]=n_cand, [1]=overflowed */, cudaStream_t stream);
+void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound,
+                           const ScanParams& p, Slot* table, uint32_t table_mask,
+                           Slot* spill, uint32_t spill_cap, uint32_t* d_counters /* [2]=n_unique,[3]=n_spill */,
+                           cudaStream_t stream);
+void launch_table_rehash(const Slot* old_table, uint32_t old_slots, Slot* table, uint32_t table_mask,
+                         uint32_t* d_counters, cudaStream_t stream);
+void launch_table_compact(const Slot* table, uint32_t n_slots, OutJunction* out, uint32_t out_cap,
+                          uint32_t* d_n_out, cudaStream_t stream);
+// ranks entries by first_ord (name_index) and sorts them by (contig_rank[tid], ts, te, name_index)
+size_t finalize_sort_workspace_bytes(uint32_t n);
+void launch_finalize_sort(OutJunction* entries, OutJunction* scratch, uint32_t n, const uint32_t* contig_rank,
+                          uint32_t n_contigs, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// counters layout in d_counters (uint32 each)
+enum { CTR_NCAND = 0, CTR_CAND_OVERFLOW = 1, CTR_NUNIQUE = 2, CTR_NSPILL = 3, CTR_NOUT = 4,
+       CTR_TOTAL_CAND64 = 6 /* 64-bit, two words */, CTR_COUNT = 8 };
+
+}  // namespace rtjx

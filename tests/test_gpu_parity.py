@@ -1,0 +1,227 @@
+"""GPU parity tests: the CUDA path (through the C ABI) vs the CPU oracle and the reference's goldens.
+
+Bit-exact bar: every field of every junction (coordinates, counts, first-seen name index, printed
+strand, anchor flags) and the BED12 text must be identical.
+"""
+import io
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from oracle_py import Oracle
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _rt():
+    import regtools_b200 as rt
+    return rt
+
+
+def tables_equal(gpu, cpu):
+    assert len(gpu) == len(cpu), f"junction count {len(gpu)} vs oracle {len(cpu)}"
+    for f in ("tid", "start", "end", "thick_start", "thick_end", "read_count", "name_index", "strand", "left_ok", "right_ok"):
+        bad = np.nonzero(gpu[f] != cpu[f])[0]
+        assert bad.size == 0, f"field {f} differs at {bad[:5]}: gpu {gpu[f][bad[:5]]} oracle {cpu[f][bad[:5]]}"
+
+
+def run_gpu_batch(arrs, strandness=0, a=8, m=70, M=500000, contigs=("1", "10", "2"), device_resident=False, split=1):
+    rt = _rt()
+    ex = rt.JunctionsExtractor(strandness=strandness, min_anchor_length=a, min_intron_length=m, max_intron_length=M)
+    ex.set_contigs(list(contigs))
+    tid, pos, meta, off, cigar = arrs
+    n = len(tid)
+    bounds = np.linspace(0, n, split + 1).astype(int)
+    for i in range(split):
+        lo, hi = bounds[i], bounds[i + 1]
+        if hi == lo:
+            continue
+        o = off[lo:hi + 1].astype(np.uint32)
+        c = cigar[o[0]:o[-1]]
+        o = (o - o[0]).astype(np.uint32)
+        sub = (tid[lo:hi], pos[lo:hi], meta[lo:hi], o, c)
+        if device_resident:
+            dev = [torch.from_numpy(np.ascontiguousarray(x).view(np.int32)).cuda() for x in sub]
+            if dev[4].numel() == 0:
+                dev[4] = torch.zeros(4, dtype=torch.int32, device="cuda")[:0]
+            ex.scan_batch(*dev, first_ordinal=int(lo), n_junction_ops=synth.count_n_ops(c))
+            torch.cuda.synchronize()
+        else:
+            ex.scan_batch(*sub, first_ordinal=int(lo))
+    table = ex.junction_table()
+    buf = io.StringIO()
+    ex.print_all_junctions(buf)
+    stats = ex.stats()
+    ex.close()
+    return table, buf.getvalue(), stats
+
+
+def run_oracle_batch(arrs, strandness=0, a=8, m=70, M=500000, contigs=("1", "10", "2")):
+    o = Oracle(a, m, M, strandness, "XS", contigs=list(contigs))
+    o.batch(*arrs)
+    return o.table(), o.bed12()
+
+
+@pytest.mark.parametrize("strandness", [0, 1, 2])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_batches_match_oracle(seed, strandness):
+    arrs = synth.random_batch(seed, 20000)
+    g_tab, g_bed, _ = run_gpu_batch(arrs, strandness)
+    o_tab, o_bed = run_oracle_batch(arrs, strandness)
+    tables_equal(g_tab, o_tab)
+    assert g_bed == o_bed
+
+
+@pytest.mark.parametrize("device_resident", [False, True])
+def test_split_batches_and_device_resident(device_resident):
+    arrs = synth.random_batch(11, 50000, spliced_frac=0.3)
+    g_tab, g_bed, st = run_gpu_batch(arrs, 0, device_resident=device_resident, split=7)
+    o_tab, o_bed = run_oracle_batch(arrs, 0)
+    tables_equal(g_tab, o_tab)
+    assert g_bed == o_bed
+    assert st["kernel_launches"] >= 14 and st["reads"] == 50000
+
+
+@pytest.mark.parametrize("a,m,M", [(0, 0, 0xFFFFFFFF), (30, 70, 500000), (8, 8039, 8039), (1, 1, 69)])
+def test_parameter_corners(a, m, M):
+    arrs = synth.random_batch(5, 15000, spliced_frac=0.4)
+    g_tab, g_bed, _ = run_gpu_batch(arrs, 0, a, m, M)
+    o_tab, o_bed = run_oracle_batch(arrs, 0, a, m, M)
+    tables_equal(g_tab, o_tab)
+    assert g_bed == o_bed
+
+
+def test_known_answer_vectors():
+    """SURVEY 8a KAT table (verified against the reference binary)."""
+    C = synth.cig
+    p, m = ord("+"), ord("-")
+    reads = [
+        (0, 1000, 0, 60, p, C("50M100N50M")), (0, 1000, 0, 0, p, C("10S40M100N50M")),
+        (0, 1000, 0, 60, p, C("5H50M100N50M5H")), (0, 1000, 0, 60, p, C("20M2X28M100N50M")),
+        (0, 1000, 0, 60, p, C("20=30M100N25=25M")), (0, 1000, 0, 60, p, C("50M100N20M1I29M")),
+        (0, 1000, 0, 60, p, C("50M100N20M3D30M")),
+        (0, 2000, 0, 60, p, C("50M100N200N50M")), (0, 3000, 0, 60, m, C("50M100N30M200N20M")),
+        (0, 4000, 0, 60, p, C("50M100N")), (0, 5000, 0, 60, p, C("50M69N50M")), (0, 5500, 0, 60, p, C("50M70N50M")),
+        (0, 6000, 0, 60, p, C("7M100N50M")), (0, 6000, 0, 60, p, C("50M100N7M")),
+        (0, 6957, 0, 60, p, C("50M100N7M")), (0, 7000, 0, 60, p, C("7M100N50M")),
+        (0, 8000, 0, 60, ord("."), C("50M100N50M")), (0, 8000, 0, 60, 0, C("50M100N50M")),
+        (0, 9500, 0, 60, p, C("50M3P100N50M")), (0, 10000, 4, 0, p, C("50M100N50M")),
+        (0, 10000, 256 | 512 | 1024 | 2048, 0, p, C("50M100N50M")),
+        (0, 11000, 0, 60, p, C("50M500001N50M")), (0, 11000, 0, 60, p, C("50M500000N50M")),
+        (1, 100, 0, 60, p, C("50M100N50M")), (2, 100, 0, 60, p, C("50M100N50M")),
+    ]
+    arrs = synth.batch_from_reads(reads)
+    for a in (8, 0):
+        g_tab, g_bed, _ = run_gpu_batch(arrs, 0, a=a)
+        o_tab, o_bed = run_oracle_batch(arrs, 0, a=a)
+        tables_equal(g_tab, o_tab)
+        assert g_bed == o_bed
+    assert "1\t1000\t1200\tJUNC00000001\t6\t+\t1000\t1200\t255,0,0\t2\t50,50\t0,150\n" in g_bed
+    assert "1\t1000\t1190\tJUNC00000002\t1\t+\t1000\t1190\t255,0,0\t2\t40,50\t0,140\n" in g_bed
+
+
+def test_hot_junction_and_long_cigars():
+    """One junction supported by 200k reads (atomic contention) + reads with thousands of ops."""
+    C = synth.cig
+    reads = [(0, 5000 - (i % 90) - 1, 99, 60, ord("+"), C(f"{(i % 90) + 1}M1000N{100 - (i % 90)}M")) for i in range(200000)]
+    long_ops = []
+    for k in range(3000):
+        long_ops += C("5M80N")
+    reads.append((0, 900000, 0, 60, ord("-"), long_ops + C("5M")))
+    reads.append((1, 10, 0, 60, ord("-"), C("10M") * 40000 + C("70N10M")))
+    arrs = synth.batch_from_reads(reads)
+    g_tab, g_bed, _ = run_gpu_batch(arrs, 0)
+    o_tab, o_bed = run_oracle_batch(arrs, 0)
+    tables_equal(g_tab, o_tab)
+    assert g_bed == o_bed
+    assert g_tab["read_count"].max() == 200000
+
+
+def test_many_unique_junctions_grow_table():
+    rng = np.random.default_rng(7)
+    n = 300000
+    starts = np.sort(rng.integers(0, 2_000_000_000, n)).astype(np.int64)
+    lens = rng.integers(70, 5000, n)
+    reads = [(0, int(s), 0, 60, ord("+"), [50 << 4, int(l) << 4 | 3, 50 << 4]) for s, l in zip(starts, lens)]
+    arrs = synth.batch_from_reads(reads)
+    rt = _rt()
+    ex = rt.JunctionsExtractor(strandness=0, table_log2=12)
+    ex.set_contigs(["1"])
+    # a tiny first batch creates the 2^12-slot table; the rest forces a rehash into a larger one
+    tid, pos, meta, off, cigar = arrs
+    ex.scan_batch(tid[:100], pos[:100], meta[:100], off[:101], cigar[:off[100]])
+    o2 = (off[100:] - off[100]).astype(np.uint32)
+    ex.scan_batch(tid[100:], pos[100:], meta[100:], o2, cigar[off[100]:], first_ordinal=100)
+    g_tab = ex.junction_table()
+    st = ex.stats()
+    ex.close()
+    o_tab, _ = run_oracle_batch(arrs, 0, contigs=("1",))
+    tables_equal(g_tab, o_tab)
+    assert st["table_grows"] >= 1
+
+
+def test_add_junction_gtest_vectors():
+    """tests/lib/junctions/test_junctions_extractor.cc:75-141 (JunctionName, AddJunction)."""
+    rt = _rt()
+    jc = rt.JunctionsExtractor(strandness=0)
+    assert jc.get_new_junction_name() == "JUNC00000001"
+    jc.add_junction(rt.Junction("chr1", 10000, 10200, 9500, 10700, "+"))
+    assert jc.get_new_junction_name() == "JUNC00000002"
+    jc.close()
+    jc = rt.JunctionsExtractor(strandness=0)
+    for args in [("chr1", 10000, 10200, 9900, 10300, "+"), ("chr1", 10000, 10200, 9500, 10200, "+"),
+                 ("chr1", 10000, 10200, 9950, 10700, "+"), ("chr1", 8000, 8500, 7000, 10000, "+"),
+                 ("chr1", 8000, 8500, 7000, 10000, "-")]:
+        jc.add_junction(rt.Junction(*args))
+    buf = io.StringIO()
+    jc.print_all_junctions(buf)
+    jc.close()
+    expected = ("chr1\t7000\t10000\tJUNC00000002\t1\t+\t7000\t10000\t255,0,0\t2\t1000,1500\t0,1500\n"
+                "chr1\t7000\t10000\tJUNC00000003\t1\t-\t7000\t10000\t255,0,0\t2\t1000,1500\t0,1500\n"
+                "chr1\t9500\t10700\tJUNC00000001\t3\t+\t9500\t10700\t255,0,0\t2\t500,500\t0,700\n")
+    assert buf.getvalue() == expected
+
+
+GOLDENS = [
+    (["-s", "XS"], "expected-a.out"), (["-s", "XS", "-a", "30"], "expected-a30.out"),
+    (["-s", "RF"], "expected-stranded-a.out"), (["-s", "RF", "-a", "30"], "expected-stranded-a30.out"),
+    (["-s", "XS", "-m", "8039", "-M", "8039"], "expected-i8039-I8039.out"),
+    (["-s", "XS", "-r", "1:22405013-22405020"], "expected-r1:22405013-22405020.out"),
+]
+
+
+@pytest.mark.parametrize("args,golden", GOLDENS)
+def test_reference_goldens(args, golden, hcc_bam, golden_dir, tmp_path):
+    """tests/integration-test/test_junctions_extract.py:33-85 against the reference's own goldens."""
+    rt = _rt()
+    out = tmp_path / "extract.out"
+    rc = rt.junctions_extract(["extract"] + args + ["-o", str(out), hcc_bam])
+    assert rc == 0
+    assert out.read_text() == open(os.path.join(golden_dir, "hcc1395", golden)).read()
+
+
+def test_whole_bam_matches_oracle_fr_mode(hcc_bam):
+    rt = _rt()
+    ex = rt.JunctionsExtractor(hcc_bam, ".", 2, "XS", 8, 70, 500000)
+    ex.identify_junctions_from_BAM()
+    g_tab = ex.junction_table()
+    st = ex.stats()
+    ex.close()
+    o = Oracle(8, 70, 500000, 2)
+    o.extract_bam(hcc_bam)
+    tables_equal(g_tab, o.table())
+    assert st["reads"] == o.reads_seen() == 31678
+
+
+def test_exit_codes(hcc_bam, tmp_path):
+    """tests/integration-test/test_junctions_extract.py:87-109."""
+    rt = _rt()
+    out = str(tmp_path / "o")
+    assert rt.junctions_extract(["extract", "-s", "XS", "-o", out]) == 1
+    assert rt.junctions_extract(["extract", "-s", "XS", "-o", out, "does_not_exist.bam"]) == 1
+    assert rt.junctions_extract(["extract", "-o", out]) == 1
+    assert rt.junctions_extract(["extract", "-h"]) == 0
