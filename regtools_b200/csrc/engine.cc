@@ -54,6 +54,7 @@ Engine::~Engine() {
         }
         cudaFree(d_counters_); cudaFreeHost(h_counters_);
         cudaFree(d_table_); cudaFree(d_spill_); cudaFree(d_cands_);
+        cudaFree(d_out_); cudaFree(d_sorted_); cudaFree(d_ws_); cudaFree(d_rank_); cudaFreeHost(h_final_);
         if (stream_) cudaStreamDestroy(stream_);
         if (copy_stream_) cudaStreamDestroy(copy_stream_);
     }
@@ -346,7 +347,7 @@ int Engine::open_bam(std::unique_ptr<BamFile>* bam, BaiIndex* idx, IterSpec* spe
         if (csi) return fail(RTJX_E_UNSUPPORTED, "only .bai indexes are supported by the B200 path (.csi found)");
         return fail(RTJX_E_OPEN_INDEX, "Unable to open BAM/SAM index. Make sure alignments are indexed\n\n");
     }
-    contigs_ = (*bam)->header().names;
+    contigs_ = (*bam)->header().names; rank_dirty_ = true;
     if (!parse_region(**bam, region_, spec)) return fail(RTJX_E_REGION, "Unable to iterate to region within BAM.\n\n");
     if (prm_.shard_world > 1) {
         if (spec->kind != IterSpec::WholeFile) return fail(RTJX_E_ARG, "contig sharding needs region \".\"");
@@ -489,6 +490,34 @@ void Engine::host_rank_and_sort() {
     });
 }
 
+int Engine::ensure_finalize_buffers(uint32_t n, size_t n_contigs) {
+    if (n > fin_cap_) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(d_out_); cudaFree(d_sorted_); d_out_ = d_sorted_ = nullptr;
+        uint32_t cap = std::max<uint32_t>(n + n / 2, 1u << 16);
+        CK(cudaMalloc(&d_out_, (size_t)cap * sizeof(OutJunction)));
+        CK(cudaMalloc(&d_sorted_, (size_t)cap * sizeof(OutJunction)));
+        fin_cap_ = cap;
+        cudaFree(d_ws_); d_ws_ = nullptr;
+        ws_cap_ = finalize_sort_workspace_bytes(cap);
+        CK(cudaMalloc(&d_ws_, ws_cap_));
+    }
+    if (n > h_final_cap_) {
+        cudaFreeHost(h_final_); h_final_ = nullptr;
+        uint32_t cap = std::max<uint32_t>(n + n / 2, 1u << 16);
+        CK(cudaHostAlloc(&h_final_, (size_t)cap * sizeof(rtjx_junction), cudaHostAllocDefault));
+        h_final_cap_ = cap;
+    }
+    if (n_contigs > rank_cap_ || !d_rank_) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(d_rank_); d_rank_ = nullptr;
+        rank_cap_ = std::max<size_t>(n_contigs * 2, 64);
+        CK(cudaMalloc(&d_rank_, rank_cap_ * 4));
+        rank_dirty_ = true;
+    }
+    return RTJX_OK;
+}
+
 int Engine::finalize(cudaStream_t user_stream) {
     if (finalized_ && !dirty_) return RTJX_OK;
     final_.clear();
@@ -500,28 +529,28 @@ int Engine::finalize(cudaStream_t user_stream) {
         if (rc) return rc;
         n = h_counters_[CTR_NUNIQUE];
         if (n) {
-            OutJunction *d_out = nullptr, *d_sorted = nullptr; void* ws = nullptr; uint32_t* d_rank = nullptr;
-            const size_t ws_bytes = finalize_sort_workspace_bytes(n);
-            std::vector<uint32_t> cr = contig_ranks(contigs_);
-            CK(cudaMalloc(&d_out, (size_t)n * sizeof(OutJunction)));
-            CK(cudaMalloc(&d_sorted, (size_t)n * sizeof(OutJunction)));
-            CK(cudaMalloc(&ws, ws_bytes));
-            CK(cudaMalloc(&d_rank, std::max<size_t>(cr.size(), 1) * 4));
-            if (!cr.empty()) CK(cudaMemcpyAsync(d_rank, cr.data(), cr.size() * 4, cudaMemcpyHostToDevice, st));
+            if ((rc = ensure_finalize_buffers(n, contigs_.size()))) return rc;
+            std::vector<uint32_t> cr;
+            if (rank_dirty_) cr = contig_ranks(contigs_);
+            const size_t ws_bytes = ws_cap_;
+            if (rank_dirty_) {
+                if (!cr.empty()) CK(cudaMemcpyAsync(d_rank_, cr.data(), cr.size() * 4, cudaMemcpyHostToDevice, st));
+                CK(cudaStreamSynchronize(st));      // cr is a local
+                rank_dirty_ = false;
+            }
             CK(cudaMemsetAsync(d_counters_ + CTR_NOUT, 0, sizeof(uint32_t), st));
             cudaEvent_t ea = nullptr, eb = nullptr;
             if (prm_.profile) { ea = get_event(); eb = get_event(); cudaEventRecord(ea, st); }
-            launch_table_compact(d_table_, table_slots_, d_out, n, d_counters_ + CTR_NOUT, st);
-            launch_finalize_sort(d_out, d_sorted, n, d_rank, (uint32_t)cr.size(), ws, ws_bytes, st);
+            launch_table_compact(d_table_, table_slots_, d_out_, n, d_counters_ + CTR_NOUT, st);
+            launch_finalize_sort(d_out_, d_sorted_, n, d_rank_, (uint32_t)contigs_.size(), d_ws_, ws_bytes, st);
             if (prm_.profile) cudaEventRecord(eb, st);
-            final_.resize(n);
-            CK(cudaMemcpyAsync(final_.data(), d_sorted, (size_t)n * sizeof(OutJunction), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h_final_, d_sorted_, (size_t)n * sizeof(OutJunction), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
+            final_.assign(h_final_, h_final_ + n);
             if (prm_.profile) { float ms = 0; if (cudaEventElapsedTime(&ms, ea, eb) == cudaSuccess) stats_.finalize_ms += ms; ev_pool_.push_back(ea); ev_pool_.push_back(eb); }
             stats_.kernel_launches += 5;     // ours: compact + 3 key builders + gather (CUB's sort passes not counted)
             stats_.d2h_bytes += (size_t)n * sizeof(OutJunction);
-            cudaFree(d_out); cudaFree(d_sorted); cudaFree(ws); cudaFree(d_rank);
         }
     }
     if (!imported_.empty() || n >= 100000000u) host_rank_and_sort();
@@ -625,7 +654,7 @@ int32_t Engine::intern_contig(const char* name) {
     if (!name) return -1;
     for (size_t i = 0; i < contigs_.size(); ++i) if (contigs_[i] == name) return (int32_t)i;
     contigs_.push_back(name);
-    finalized_ = false;
+    finalized_ = false; rank_dirty_ = true;
     return (int32_t)contigs_.size() - 1;
 }
 

@@ -80,6 +80,13 @@ private:
     int dev_batch_next_ = 0;
     int ensure_dev_batch(DevBatch& d, uint32_t reads, uint32_t ops);
 
+    // finalize scratch (grow-only; cudaMalloc/cudaFree per call cost ~20 ms on a loaded context)
+    OutJunction* d_out_ = nullptr; OutJunction* d_sorted_ = nullptr; uint32_t fin_cap_ = 0;
+    void* d_ws_ = nullptr; size_t ws_cap_ = 0;
+    uint32_t* d_rank_ = nullptr; size_t rank_cap_ = 0; bool rank_dirty_ = true;
+    rtjx_junction* h_final_ = nullptr; uint32_t h_final_cap_ = 0;   // pinned D2H staging
+    int ensure_finalize_buffers(uint32_t n, size_t n_contigs);
+
     // finalized table (host)
     std::vector<rtjx_junction> final_;
     std::vector<rtjx_junction> imported_;

@@ -234,9 +234,270 @@ cigar_scan_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t 
     }
 }
 
+static int num_sms();
+
+// ------------------------------------------------------------------------------------------------
+// cigar_scan, persistent TMA-pipelined version (the one normally launched)
+// ------------------------------------------------------------------------------------------------
+// One CTA per half-SM loops over tiles of 1024 alignments.  The four metadata columns of a tile
+// (pos, meta, tid, cig_off: 16 KB) and its contiguous CIGAR slab are brought into a 3-stage shared
+// memory ring by 1-D bulk async copies (cp.async.bulk / UBLKCP) issued by one thread and tracked
+// by mbarriers, so the loads of tiles j+1 and j+2 are in flight while tile j is processed: the SM
+// always has tens of KB outstanding to HBM without spending issue slots on LDGs.  Only ~10 % of
+// alignments have more than one CIGAR op; a ballot/prefix-sum pass compacts their indices into a
+// shared work list so that the op walk runs on dense warps instead of diverging in every warp.
+constexpr int S2_THREADS = 256;
+constexpr int S2_TILE    = 1024;
+constexpr int S2_STAGES  = 3;
+constexpr int S2_SLAB    = 3072;                 // CIGAR words per stage (12 KB)
+constexpr int S2_OUT     = 512;                  // staged candidates per tile (16 KB)
+
+struct alignas(16) S2Stage {
+    uint32_t pos[S2_TILE];
+    uint32_t meta[S2_TILE];
+    uint32_t tid[S2_TILE];
+    uint32_t off[S2_TILE + 4];
+    uint32_t slab[S2_SLAB];
+};
+struct alignas(16) S2Smem {
+    S2Stage st[S2_STAGES];
+    uint4 out[S2_OUT * 2];
+    unsigned long long meta_full[S2_STAGES];
+    unsigned long long slab_full[S2_STAGES];
+    uint32_t slab_a0[S2_STAGES];                 // first staged word index (16-byte aligned)
+    uint32_t slab_direct[S2_STAGES];             // 1: slab not staged, walk reads global memory
+    uint32_t n_work[2], n_out[2];
+    uint32_t flush_base;
+    uint16_t work[S2_TILE];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct S2Emit {
+    S2Smem& sm; uint32_t buf; Cand* __restrict__ out; uint32_t cap; uint32_t* counters;
+    __device__ __forceinline__ void operator()(uint32_t start, uint32_t end, uint32_t left, uint32_t right,
+                                               uint64_t ord, int32_t tid, uint32_t strand) const {
+        uint4 a = make_uint4(start, end, start - left, end + right);
+        uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
+        uint32_t i = atomicAdd(&sm.n_out[buf], 1u);
+        if (i < S2_OUT) {
+            sm.out[2 * i] = a; sm.out[2 * i + 1] = b;
+        } else {
+            uint32_t g = atomicAdd(&counters[CTR_NCAND], 1u);
+            if (g < cap) { uint4* o = reinterpret_cast<uint4*>(out + g); o[0] = a; o[1] = b; }
+            else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
+        }
+    }
+};
+
+// closed-form walk, same arithmetic as scan_walk above
+template <bool FROM_SMEM, class Emit>
+__device__ __forceinline__ void walk_ops(const uint32_t* __restrict__ ops, uint32_t n, uint32_t pos, int32_t tid,
+                                         uint32_t strand, uint64_t read_ord, const Emit& emit) {
+    const uint32_t ANC = (1u << 0) | (1u << 7);
+    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
+    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
+    uint32_t cur = pos, run = 0;
+    bool pending = false;
+    uint32_t p_start = 0, p_end = 0, p_left = 0, p_k = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t w = FROM_SMEM ? ops[i] : __ldg(ops + i);
+        const uint32_t op = w & 0xfu, len = w >> 4, bit = 1u << op;
+        if (bit & BRK) {
+            if (pending) { emit(p_start, p_end, p_left, run, read_ord << 16 | (p_k > 0xffffu ? 0xffffu : p_k), tid, strand); pending = false; }
+            if (op == 3u) { pending = true; p_start = cur; p_end = cur + len; p_left = run; p_k = i; }
+            run = 0;
+        } else if (bit & ANC) {
+            run += len;
+        }
+        if (bit & REFC) cur += len;
+    }
+    if (pending) emit(p_start, p_end, p_left, run, read_ord << 16 | (p_k > 0xffffu ? 0xffffu : p_k), tid, strand);
+}
+
+__global__ void __launch_bounds__(S2_THREADS, 2)
+cigar_scan_tma_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
+    extern __shared__ __align__(128) unsigned char s2_raw[];
+    S2Smem& sm = *reinterpret_cast<S2Smem*>(s2_raw);
+    const uint32_t t = threadIdx.x, lane = t & 31u;
+    const uint32_t n_tiles = (b.n_reads + S2_TILE - 1) / S2_TILE;
+    const uint32_t n_ops_vec_end = b.n_ops & ~3u;          // bulk copies must not run past the array
+
+    if (t == 0) {
+        for (int s = 0; s < S2_STAGES; ++s) { mbar_init(&sm.meta_full[s], 1); mbar_init(&sm.slab_full[s], 1); }
+        sm.n_work[0] = sm.n_work[1] = 0; sm.n_out[0] = sm.n_out[1] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // metadata of `tile` -> stage s.  Full tiles whose cig_off window (1028 entries) lies inside the
+    // array use four bulk copies from one thread; the (at most two) ragged tiles at the end of the
+    // batch are loaded cooperatively.  Block-uniform; contains a barrier only on the ragged path.
+    auto issue_meta = [&](uint32_t tile, int s) {
+        const uint32_t base = tile * S2_TILE;
+        S2Stage& st = sm.st[s];
+        if (base + S2_TILE + 3 <= b.n_reads) {
+            if (t == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive_expect_tx(&sm.meta_full[s], 3 * S2_TILE * 4 + (S2_TILE + 4) * 4);
+                bulk_g2s(st.off, b.cig_off + base, (S2_TILE + 4) * 4, &sm.meta_full[s]);
+                bulk_g2s(st.pos, b.pos + base, S2_TILE * 4, &sm.meta_full[s]);
+                bulk_g2s(st.meta, b.meta + base, S2_TILE * 4, &sm.meta_full[s]);
+                bulk_g2s(st.tid, b.tid + base, S2_TILE * 4, &sm.meta_full[s]);
+            }
+        } else {
+            const uint32_t n_tile = min((uint32_t)S2_TILE, b.n_reads - base);
+            for (uint32_t r = t; r < n_tile; r += S2_THREADS) {
+                st.pos[r] = (uint32_t)b.pos[base + r]; st.meta[r] = b.meta[base + r]; st.tid[r] = (uint32_t)b.tid[base + r];
+            }
+            for (uint32_t r = t; r <= n_tile; r += S2_THREADS) st.off[r] = b.cig_off[base + r];
+            __syncthreads();
+            if (t == 0) mbar_arrive(&sm.meta_full[s]);
+        }
+    };
+    // CIGAR slab of the tile whose metadata is (or will be) in stage s.  Thread 0 only.
+    auto issue_slab = [&](uint32_t tile, int s, uint32_t parity) {
+        mbar_wait(&sm.meta_full[s], parity);
+        S2Stage& st = sm.st[s];
+        const uint32_t n_tile = min((uint32_t)S2_TILE, b.n_reads - tile * S2_TILE);
+        const uint32_t lo = st.off[0], hi = st.off[n_tile];
+        const uint32_t a0 = lo & ~3u, end4 = (hi + 3u) & ~3u;
+        sm.slab_a0[s] = a0;
+        if (hi <= lo) {                                       // no ops at all
+            sm.slab_direct[s] = 0; mbar_arrive(&sm.slab_full[s]);
+        } else if (end4 - a0 > (uint32_t)S2_SLAB || end4 > n_ops_vec_end) {
+            sm.slab_direct[s] = 1; mbar_arrive(&sm.slab_full[s]);
+        } else {
+            sm.slab_direct[s] = 0;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(&sm.slab_full[s], (end4 - a0) * 4);
+            bulk_g2s(st.slab, b.cigar + a0, (end4 - a0) * 4, &sm.slab_full[s]);
+        }
+    };
+
+    // prologue: metadata of the first S2_STAGES tiles of this CTA, slab of the first
+    for (int s = 0; s < S2_STAGES; ++s) {
+        const uint32_t tile = blockIdx.x + (uint32_t)s * gridDim.x;
+        if (tile < n_tiles) issue_meta(tile, s);
+    }
+    if (t == 0 && blockIdx.x < n_tiles) issue_slab(blockIdx.x, 0, 0);
+
+    uint32_t k = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+        const int s = (int)(k % S2_STAGES);
+        const uint32_t parity = (k / S2_STAGES) & 1u;
+        const uint32_t cb = k & 1u;                          // counter buffer of this iteration
+        const uint32_t next = tile + gridDim.x;
+        if (t == 0 && next < n_tiles) issue_slab(next, (int)((k + 1) % S2_STAGES), ((k + 1) / S2_STAGES) & 1u);
+        mbar_wait(&sm.meta_full[s], parity);
+        mbar_wait(&sm.slab_full[s], parity);
+        S2Stage& st = sm.st[s];
+        const uint32_t base = tile * S2_TILE;
+        const uint32_t n_tile = min((uint32_t)S2_TILE, b.n_reads - base);
+
+        // ---- phase A: compact the alignments that have more than one CIGAR op (junctions_extractor.cc:379)
+        {
+            const uint4 o = *reinterpret_cast<const uint4*>(&st.off[4 * t]);
+            const uint32_t o4 = st.off[4 * t + 4];
+            const uint32_t r0 = 4 * t;
+            uint32_t flags = 0;
+            if (r0 + 0 < n_tile && o.y - o.x > 1u) flags |= 1u;
+            if (r0 + 1 < n_tile && o.z - o.y > 1u) flags |= 2u;
+            if (r0 + 2 < n_tile && o.w - o.z > 1u) flags |= 4u;
+            if (r0 + 3 < n_tile && o4 - o.w > 1u) flags |= 8u;
+            const uint32_t cnt = __popc(flags);
+            uint32_t x = cnt;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
+            uint32_t wbase = 0;
+            if (lane == 31 && x) wbase = atomicAdd(&sm.n_work[cb], x);
+            wbase = __shfl_sync(0xffffffffu, wbase, 31);
+            uint32_t p = wbase + x - cnt;
+            if (flags & 1u) sm.work[p++] = (uint16_t)(r0 + 0);
+            if (flags & 2u) sm.work[p++] = (uint16_t)(r0 + 1);
+            if (flags & 4u) sm.work[p++] = (uint16_t)(r0 + 2);
+            if (flags & 8u) sm.work[p++] = (uint16_t)(r0 + 3);
+        }
+        __syncthreads();
+        if (t == 0) { sm.n_work[cb ^ 1u] = 0; sm.n_out[cb ^ 1u] = 0; }
+
+        // ---- phase B: walk the compacted alignments, one per thread
+        {
+            const uint32_t n_work = sm.n_work[cb];
+            const uint32_t a0 = sm.slab_a0[s];
+            const bool direct = sm.slab_direct[s] != 0;
+            const S2Emit emit{sm, cb, out, cap, counters};
+            for (uint32_t w = t; w < n_work; w += S2_THREADS) {
+                const uint32_t r = sm.work[w];
+                const int32_t tid = (int32_t)st.tid[r];
+                if (tid < 0) continue;
+                const uint32_t o0 = st.off[r], n = st.off[r + 1] - o0;
+                const uint32_t strand = read_strand(st.meta[r], prm.strandness);
+                const uint64_t read_ord = b.first_ordinal + base + r;
+                if (!direct) walk_ops<true>(st.slab + (o0 - a0), n, st.pos[r], tid, strand, read_ord, emit);
+                else walk_ops<false>(b.cigar + o0, n, st.pos[r], tid, strand, read_ord, emit);
+            }
+        }
+        __syncthreads();
+
+        // ---- stage s is drained: refill it with the tile S2_STAGES iterations ahead
+        {
+            const uint32_t refill = tile + (uint32_t)S2_STAGES * gridDim.x;
+            if (refill < n_tiles) issue_meta(refill, s);
+        }
+        // ---- flush the staged candidates with one reservation per tile
+        const uint32_t n_st = min(sm.n_out[cb], (uint32_t)S2_OUT);
+        if (n_st) {
+            if (t == 0) sm.flush_base = atomicAdd(&counters[CTR_NCAND], n_st);
+            __syncthreads();
+            const uint32_t fb = sm.flush_base;
+            uint4* o = reinterpret_cast<uint4*>(out);
+            for (uint32_t v = t; v < 2 * n_st; v += S2_THREADS) {
+                if (fb + (v >> 1) < cap) o[2ull * fb + v] = sm.out[v];
+                else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
+            }
+        }
+    }
+}
+
 void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
                        uint32_t* d_counters, cudaStream_t stream) {
     if (b.n_reads == 0) return;
+    const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
+                            reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
+                            reinterpret_cast<uintptr_t>(b.cigar);
+    if ((align & 15u) == 0) {            // bulk async copies need 16-byte aligned columns (cudaMalloc gives 256)
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(cigar_scan_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S2Smem));
+            attr_set = true;
+        }
+        const uint32_t tiles = (b.n_reads + S2_TILE - 1) / S2_TILE;
+        const uint32_t grid = min(tiles, (uint32_t)(2 * num_sms()));
+        cigar_scan_tma_kernel<<<grid, S2_THREADS, sizeof(S2Smem), stream>>>(b, p, cands, cand_cap, d_counters);
+        return;
+    }
     uint32_t grid = (b.n_reads + SCAN_TILE - 1) / SCAN_TILE;
     cigar_scan_kernel<<<grid, SCAN_THREADS, 0, stream>>>(b, p, cands, cand_cap, d_counters);
 }
