@@ -54,7 +54,7 @@ Engine::~Engine() {
         }
         cudaFree(d_counters_); cudaFreeHost(h_counters_);
         cudaFree(d_table_); cudaFree(d_spill_); cudaFree(d_cands_);
-        cudaFree(d_out_); cudaFree(d_sorted_); cudaFree(d_ws_); cudaFree(d_rank_); cudaFreeHost(h_final_);
+        cudaFree(d_out_); cudaFree(d_ws_); cudaFree(d_rank_); cudaFreeHost(h_final_); cudaFree(d_slot_list_);
         if (stream_) cudaStreamDestroy(stream_);
         if (copy_stream_) cudaStreamDestroy(copy_stream_);
     }
@@ -64,6 +64,8 @@ ScanParams Engine::scan_params() const {
     ScanParams s;
     s.strandness = prm_.strandness; s.min_anchor = prm_.min_anchor;
     s.min_intron = prm_.min_intron; s.max_intron = prm_.max_intron;
+    static const uint32_t dbg = getenv("RTJX_SCAN_DEBUG") ? (uint32_t)atoi(getenv("RTJX_SCAN_DEBUG")) : 0u;
+    s.debug = dbg;
     return s;
 }
 
@@ -124,6 +126,7 @@ int Engine::ensure_table(uint32_t incoming, cudaStream_t stream) {
         uint32_t want = 1u << (prm_.table_log2 ? std::min<uint32_t>(prm_.table_log2, 30) : 22);
         want = std::max(want, next_pow2(4ull * incoming));
         CK(cudaMalloc(&d_table_, (size_t)want * sizeof(Slot)));
+        CK(cudaMalloc(&d_slot_list_, (size_t)want * sizeof(uint32_t)));
         CK(cudaMemsetAsync(d_table_, 0, (size_t)want * sizeof(Slot), stream));
         table_slots_ = want; unique_upper_ = 0;
     }
@@ -132,15 +135,16 @@ int Engine::ensure_table(uint32_t incoming, cudaStream_t stream) {
         if (rc) return rc;
         if (2ull * (unique_upper_ + incoming) > table_slots_) {
             uint32_t want = next_pow2(4ull * (unique_upper_ + incoming));
-            Slot* nt = nullptr;
+            Slot* nt = nullptr; uint32_t* nl = nullptr;
             CK(cudaMalloc(&nt, (size_t)want * sizeof(Slot)));
+            CK(cudaMalloc(&nl, (size_t)want * sizeof(uint32_t)));
             CK(cudaMemsetAsync(nt, 0, (size_t)want * sizeof(Slot), stream));
             CK(cudaMemsetAsync(d_counters_ + CTR_NUNIQUE, 0, sizeof(uint32_t), stream));
-            launch_table_rehash(d_table_, table_slots_, nt, want - 1, d_counters_, stream);
+            launch_table_rehash(d_table_, table_slots_, TableRef{nt, want - 1, nl, want}, d_counters_, stream);
             stats_.kernel_launches++;
             CK(cudaStreamSynchronize(stream));
-            cudaFree(d_table_);
-            d_table_ = nt; table_slots_ = want; stats_.table_grows++;
+            cudaFree(d_table_); cudaFree(d_slot_list_);
+            d_table_ = nt; d_slot_list_ = nl; table_slots_ = want; stats_.table_grows++;
         }
     }
     unique_upper_ += incoming;
@@ -165,7 +169,7 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
         cand_bound = h_counters_[CTR_NCAND];
         if ((rc = ensure_table(std::max(cand_bound, 1u), stream))) return rc;
     }
-    launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, cand_bound, scan_params(), d_table_, table_slots_ - 1,
+    launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, cand_bound, scan_params(), table_ref(),
                           d_spill_, spill_cap_, d_counters_, stream);
     if (prm_.profile) { cudaEventRecord(pe.c, stream); prof_pending_.push_back(pe); }
     CK(cudaGetLastError());
@@ -258,7 +262,7 @@ int Engine::add(const rtjx_candidate* c, size_t n) {
         if ((rc = ensure_cands((uint32_t)m))) return rc;
         if ((rc = ensure_table((uint32_t)m, stream_))) return rc;
         CK(cudaMemcpyAsync(d_cands_, h.data(), m * sizeof(Cand), cudaMemcpyHostToDevice, stream_));
-        launch_junction_merge(d_cands_, nullptr, (uint32_t)m, scan_params(), d_table_, table_slots_ - 1, d_spill_, spill_cap_,
+        launch_junction_merge(d_cands_, nullptr, (uint32_t)m, scan_params(), table_ref(), d_spill_, spill_cap_,
                               d_counters_, stream_);
         CK(cudaStreamSynchronize(stream_));
         add_ord_ += m; stats_.kernel_launches++; stats_.h2d_bytes += m * sizeof(Cand);
@@ -493,10 +497,9 @@ void Engine::host_rank_and_sort() {
 int Engine::ensure_finalize_buffers(uint32_t n, size_t n_contigs) {
     if (n > fin_cap_) {
         CK(cudaDeviceSynchronize());
-        cudaFree(d_out_); cudaFree(d_sorted_); d_out_ = d_sorted_ = nullptr;
+        cudaFree(d_out_); d_out_ = nullptr;
         uint32_t cap = std::max<uint32_t>(n + n / 2, 1u << 16);
         CK(cudaMalloc(&d_out_, (size_t)cap * sizeof(OutJunction)));
-        CK(cudaMalloc(&d_sorted_, (size_t)cap * sizeof(OutJunction)));
         fin_cap_ = cap;
         cudaFree(d_ws_); d_ws_ = nullptr;
         ws_cap_ = finalize_sort_workspace_bytes(cap);
@@ -538,18 +541,17 @@ int Engine::finalize(cudaStream_t user_stream) {
                 CK(cudaStreamSynchronize(st));      // cr is a local
                 rank_dirty_ = false;
             }
-            CK(cudaMemsetAsync(d_counters_ + CTR_NOUT, 0, sizeof(uint32_t), st));
             cudaEvent_t ea = nullptr, eb = nullptr;
             if (prm_.profile) { ea = get_event(); eb = get_event(); cudaEventRecord(ea, st); }
-            launch_table_compact(d_table_, table_slots_, d_out_, n, d_counters_ + CTR_NOUT, st);
-            launch_finalize_sort(d_out_, d_sorted_, n, d_rank_, (uint32_t)contigs_.size(), d_ws_, ws_bytes, st);
+            launch_table_compact(table_ref(), n, d_out_, st);
+            launch_finalize_sort(d_out_, n, d_rank_, (uint32_t)contigs_.size(), d_ws_, ws_bytes, st);
             if (prm_.profile) cudaEventRecord(eb, st);
-            CK(cudaMemcpyAsync(h_final_, d_sorted_, (size_t)n * sizeof(OutJunction), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h_final_, d_out_, (size_t)n * sizeof(OutJunction), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
             final_.assign(h_final_, h_final_ + n);
             if (prm_.profile) { float ms = 0; if (cudaEventElapsedTime(&ms, ea, eb) == cudaSuccess) stats_.finalize_ms += ms; ev_pool_.push_back(ea); ev_pool_.push_back(eb); }
-            stats_.kernel_launches += 5;     // ours: compact + 3 key builders + gather (CUB's sort passes not counted)
+            stats_.kernel_launches += 2;     // ours: compact + name assignment (CUB's merge-sort passes not counted)
             stats_.d2h_bytes += (size_t)n * sizeof(OutJunction);
         }
     }
@@ -578,10 +580,15 @@ int Engine::import(const rtjx_junction* j, size_t n) {
 }
 
 int Engine::clear() {
+    const uint64_t known_unique = unique_upper_;      // upper bound of occupied slots
     final_.clear(); imported_.clear(); finalized_ = false; dirty_ = false; unique_upper_ = 0; add_ord_ = 0;
     if (dev_ready_) {
         cudaSetDevice(prm_.device);
-        if (d_table_) CK(cudaMemsetAsync(d_table_, 0, (size_t)table_slots_ * sizeof(Slot), stream_));
+        if (d_table_) {
+            // zero only the occupied slots when they are few, else the whole table
+            if (known_unique < table_slots_ / 16) { launch_table_clear(table_ref(), d_counters_ + CTR_NUNIQUE, (uint32_t)known_unique + 1, stream_); stats_.kernel_launches++; }
+            else CK(cudaMemsetAsync(d_table_, 0, (size_t)table_slots_ * sizeof(Slot), stream_));
+        }
         CK(cudaMemsetAsync(d_counters_, 0, CTR_COUNT * sizeof(uint32_t), stream_));
         CK(cudaStreamSynchronize(stream_));
     }

@@ -65,6 +65,8 @@ private:
     uint32_t* d_counters_ = nullptr;
     uint32_t* h_counters_ = nullptr;            // pinned mirror
     Slot* d_table_ = nullptr; uint32_t table_slots_ = 0;
+    uint32_t* d_slot_list_ = nullptr;           // slot index of the i-th distinct junction
+    TableRef table_ref() const { return TableRef{d_table_, table_slots_ - 1, d_slot_list_, table_slots_}; }
     Slot* d_spill_ = nullptr; uint32_t spill_cap_ = 0;
     Cand* d_cands_ = nullptr; uint32_t cand_cap_ = 0;
     uint64_t unique_upper_ = 0;                 // host-side upper bound of occupied slots
@@ -81,7 +83,7 @@ private:
     int ensure_dev_batch(DevBatch& d, uint32_t reads, uint32_t ops);
 
     // finalize scratch (grow-only; cudaMalloc/cudaFree per call cost ~20 ms on a loaded context)
-    OutJunction* d_out_ = nullptr; OutJunction* d_sorted_ = nullptr; uint32_t fin_cap_ = 0;
+    OutJunction* d_out_ = nullptr; uint32_t fin_cap_ = 0;
     void* d_ws_ = nullptr; size_t ws_cap_ = 0;
     uint32_t* d_rank_ = nullptr; size_t rank_cap_ = 0; bool rank_dirty_ = true;
     rtjx_junction* h_final_ = nullptr; uint32_t h_final_cap_ = 0;   // pinned D2H staging

@@ -47,6 +47,7 @@ static_assert(sizeof(OutJunction) == 40, "OutJunction must be 40 bytes");
 struct ScanParams {
     int32_t  strandness;          // 0 XS, 1 RF, 2/3 FR
     uint32_t min_anchor, min_intron, max_intron;
+    uint32_t debug;               // developer switches for A/B measurements (0 in production)
 };
 
 struct BatchView {
@@ -59,21 +60,28 @@ struct BatchView {
     const uint32_t* cigar;
 };
 
+// The device-wide junction table as the kernels see it.
+struct TableRef {
+    Slot*     slots;
+    uint32_t  mask;               // slots - 1 (power of two)
+    uint32_t* slot_list;          // slot index of the i-th distinct junction (i < CTR_NUNIQUE)
+    uint32_t  list_cap;
+};
+
 // Launchers (kernels.cu).  All are asynchronous on `stream`.
 void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
                        uint32_t* d_counters /* [0]=n_cand, [1]=overflowed */, cudaStream_t stream);
 void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound,
-                           const ScanParams& p, Slot* table, uint32_t table_mask,
-                           Slot* spill, uint32_t spill_cap, uint32_t* d_counters /* [2]=n_unique,[3]=n_spill */,
-                           cudaStream_t stream);
-void launch_table_rehash(const Slot* old_table, uint32_t old_slots, Slot* table, uint32_t table_mask,
-                         uint32_t* d_counters, cudaStream_t stream);
-void launch_table_compact(const Slot* table, uint32_t n_slots, OutJunction* out, uint32_t out_cap,
-                          uint32_t* d_n_out, cudaStream_t stream);
-// ranks entries by first_ord (name_index) and sorts them by (contig_rank[tid], ts, te, name_index)
+                           const ScanParams& p, const TableRef& tb, Slot* spill, uint32_t spill_cap,
+                           uint32_t* d_counters /* [2]=n_unique,[3]=n_spill */, cudaStream_t stream);
+void launch_table_rehash(const Slot* old_table, uint32_t old_slots, const TableRef& tb, uint32_t* d_counters,
+                         cudaStream_t stream);
+void launch_table_clear(const TableRef& tb, const uint32_t* d_n_unique, uint32_t n_bound, cudaStream_t stream);
+void launch_table_compact(const TableRef& tb, uint32_t n, OutJunction* out, cudaStream_t stream);
+// ranks entries by first_ord (name_index) and sorts them in place by (contig_rank[tid], ts, te, name_index)
 size_t finalize_sort_workspace_bytes(uint32_t n);
-void launch_finalize_sort(OutJunction* entries, OutJunction* scratch, uint32_t n, const uint32_t* contig_rank,
-                          uint32_t n_contigs, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+void launch_finalize_sort(OutJunction* entries, uint32_t n, const uint32_t* contig_rank, uint32_t n_contigs,
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // counters layout in d_counters (uint32 each)
 enum { CTR_NCAND = 0, CTR_CAND_OVERFLOW = 1, CTR_NUNIQUE = 2, CTR_NSPILL = 3, CTR_NOUT = 4,

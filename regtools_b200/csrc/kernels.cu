@@ -11,7 +11,8 @@
 // 128-bit loads, and the map is a device-wide open-addressed hash updated with atomics after a
 // shared-memory pre-aggregation per block.  Integer only; HBM-bound; no tensor cores.
 #include "jx_device.cuh"
-#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_merge_sort.cuh>
+#include <cstdlib>
 
 namespace rtjx {
 
@@ -236,41 +237,7 @@ cigar_scan_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t 
 
 static int num_sms();
 
-// ------------------------------------------------------------------------------------------------
-// cigar_scan, persistent TMA-pipelined version (the one normally launched)
-// ------------------------------------------------------------------------------------------------
-// One CTA per half-SM loops over tiles of 1024 alignments.  The four metadata columns of a tile
-// (pos, meta, tid, cig_off: 16 KB) and its contiguous CIGAR slab are brought into a 3-stage shared
-// memory ring by 1-D bulk async copies (cp.async.bulk / UBLKCP) issued by one thread and tracked
-// by mbarriers, so the loads of tiles j+1 and j+2 are in flight while tile j is processed: the SM
-// always has tens of KB outstanding to HBM without spending issue slots on LDGs.  Only ~10 % of
-// alignments have more than one CIGAR op; a ballot/prefix-sum pass compacts their indices into a
-// shared work list so that the op walk runs on dense warps instead of diverging in every warp.
-constexpr int S2_THREADS = 256;
-constexpr int S2_TILE    = 1024;
-constexpr int S2_STAGES  = 3;
-constexpr int S2_SLAB    = 3072;                 // CIGAR words per stage (12 KB)
-constexpr int S2_OUT     = 512;                  // staged candidates per tile (16 KB)
-
-struct alignas(16) S2Stage {
-    uint32_t pos[S2_TILE];
-    uint32_t meta[S2_TILE];
-    uint32_t tid[S2_TILE];
-    uint32_t off[S2_TILE + 4];
-    uint32_t slab[S2_SLAB];
-};
-struct alignas(16) S2Smem {
-    S2Stage st[S2_STAGES];
-    uint4 out[S2_OUT * 2];
-    unsigned long long meta_full[S2_STAGES];
-    unsigned long long slab_full[S2_STAGES];
-    uint32_t slab_a0[S2_STAGES];                 // first staged word index (16-byte aligned)
-    uint32_t slab_direct[S2_STAGES];             // 1: slab not staged, walk reads global memory
-    uint32_t n_work[2], n_out[2];
-    uint32_t flush_base;
-    uint16_t work[S2_TILE];
-};
-
+// ---- mbarrier / bulk-copy primitives (used by the warp-specialised variant) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -294,15 +261,65 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-struct S2Emit {
-    S2Smem& sm; uint32_t buf; Cand* __restrict__ out; uint32_t cap; uint32_t* counters;
+
+// ------------------------------------------------------------------------------------------------
+// cigar_scan, warp-specialised persistent version (variant 4, the one normally launched)
+// ------------------------------------------------------------------------------------------------
+// 8 consumer warps + 1 service warp per CTA, two CTAs per SM, tiles of 1024 alignments strided
+// over the grid.  The service warp is the only one that talks to HBM: it keeps a 3-stage ring of
+// tile metadata (pos, meta, tid, cig_off: 16 KB) and CIGAR slabs full with 1-D bulk async copies
+// (cp.async.bulk -> UBLKCP) that complete on mbarriers, and it drains the double-buffered
+// candidate staging area with one global reservation per tile.  Consumers never wait for a load
+// they could have been told about earlier, never wait for a flush, and synchronise among
+// themselves once per tile (named barrier after the compaction pass).
+constexpr int S4_CONSUMERS = 256;
+constexpr int S4_THREADS   = S4_CONSUMERS + 32;
+constexpr int S4_TILE      = 1024;
+constexpr int S4_STAGES    = 3;
+constexpr int S4_SLAB      = 2560;               // CIGAR words per stage (10 KB)
+constexpr int S4_OUT       = 384;                // staged candidates per buffer (12 KB), two buffers
+
+struct alignas(16) S4Stage {
+    uint32_t pos[S4_TILE];
+    uint32_t meta[S4_TILE];
+    uint32_t tid[S4_TILE];
+    uint32_t off[S4_TILE + 4];
+    uint32_t slab[S4_SLAB];
+};
+struct alignas(16) S4Smem {
+    S4Stage st[S4_STAGES];
+    uint4 out[2][S4_OUT * 2];
+    unsigned long long meta_full[S4_STAGES];
+    unsigned long long slab_full[S4_STAGES];
+    unsigned long long tile_done[2];
+    unsigned long long out_free[2];
+    uint32_t slab_a0[S4_STAGES];
+    uint32_t slab_direct[S4_STAGES];
+    uint32_t n_work[2], n_out[2];
+    uint16_t work[2][S4_TILE];
+};
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+constexpr int S4_L2_AHEAD = 3;                   // tiles prefetched into L2 beyond the shared-memory ring
+
+struct S4Emit {
+    S4Smem& sm; uint32_t buf; Cand* __restrict__ out; uint32_t cap; uint32_t* counters; uint32_t dbg;
     __device__ __forceinline__ void operator()(uint32_t start, uint32_t end, uint32_t left, uint32_t right,
                                                uint64_t ord, int32_t tid, uint32_t strand) const {
         uint4 a = make_uint4(start, end, start - left, end + right);
         uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
-        uint32_t i = atomicAdd(&sm.n_out[buf], 1u);
-        if (i < S2_OUT) {
-            sm.out[2 * i] = a; sm.out[2 * i + 1] = b;
+        if (dbg & 4u) { if ((a.x ^ a.y ^ a.z ^ a.w ^ b.x) == 0x9e3779b9u) sm.n_out[buf] = 1; return; }
+        // one shared-memory atomic per converged group of lanes instead of one per lane
+        const uint32_t mask = __activemask();
+        const uint32_t lane = threadIdx.x & 31u;
+        const int leader = __ffs(mask) - 1;
+        uint32_t i = 0;
+        if ((int)lane == leader) i = atomicAdd(&sm.n_out[buf], (uint32_t)__popc(mask));
+        i = __shfl_sync(mask, i, leader) + __popc(mask & ((1u << lane) - 1u));
+        if (i < S4_OUT) {
+            sm.out[buf][2 * i] = a; sm.out[buf][2 * i + 1] = b;
         } else {
             uint32_t g = atomicAdd(&counters[CTR_NCAND], 1u);
             if (g < cap) { uint4* o = reinterpret_cast<uint4*>(out + g); o[0] = a; o[1] = b; }
@@ -311,110 +328,167 @@ struct S2Emit {
     }
 };
 
-// closed-form walk, same arithmetic as scan_walk above
+// Walk with the first 8 ops preloaded by independent loads and a predicated (branch-free) state
+// update; only the emits diverge.  Same arithmetic as walk_lin; op code 15 is a transparent filler.
 template <bool FROM_SMEM, class Emit>
-__device__ __forceinline__ void walk_ops(const uint32_t* __restrict__ ops, uint32_t n, uint32_t pos, int32_t tid,
-                                         uint32_t strand, uint64_t read_ord, const Emit& emit) {
+__device__ __forceinline__ void walk_fast(const uint32_t* __restrict__ ops, uint32_t n, uint32_t pos, int32_t tid,
+                                          uint32_t strand, uint64_t read_ord, const Emit& emit) {
     const uint32_t ANC = (1u << 0) | (1u << 7);
     const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
     const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
+    uint32_t w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = (uint32_t)i < n ? (FROM_SMEM ? ops[i] : __ldg(ops + i)) : 0xfu;
     uint32_t cur = pos, run = 0;
     bool pending = false;
     uint32_t p_start = 0, p_end = 0, p_left = 0, p_k = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t w = FROM_SMEM ? ops[i] : __ldg(ops + i);
-        const uint32_t op = w & 0xfu, len = w >> 4, bit = 1u << op;
-        if (bit & BRK) {
-            if (pending) { emit(p_start, p_end, p_left, run, read_ord << 16 | (p_k > 0xffffu ? 0xffffu : p_k), tid, strand); pending = false; }
-            if (op == 3u) { pending = true; p_start = cur; p_end = cur + len; p_left = run; p_k = i; }
-            run = 0;
-        } else if (bit & ANC) {
-            run += len;
-        }
-        if (bit & REFC) cur += len;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t op = w[i] & 0xfu, len = w[i] >> 4, bit = 1u << op;
+        const bool brk = (bit & BRK) != 0, is_n = op == 3u;
+        if (pending && brk) emit(p_start, p_end, p_left, run, read_ord << 16 | p_k, tid, strand);
+        if (brk) pending = is_n;
+        if (is_n) { p_start = cur; p_end = cur + len; p_left = run; p_k = (uint32_t)i; }
+        run = brk ? 0u : run + ((bit & ANC) ? len : 0u);
+        cur += (bit & REFC) ? len : 0u;
+    }
+    for (uint32_t i = 8; i < n; ++i) {
+        const uint32_t x = FROM_SMEM ? ops[i] : __ldg(ops + i);
+        const uint32_t op = x & 0xfu, len = x >> 4, bit = 1u << op;
+        const bool brk = (bit & BRK) != 0, is_n = op == 3u;
+        if (pending && brk) emit(p_start, p_end, p_left, run, read_ord << 16 | (p_k > 0xffffu ? 0xffffu : p_k), tid, strand);
+        if (brk) pending = is_n;
+        if (is_n) { p_start = cur; p_end = cur + len; p_left = run; p_k = i; }
+        run = brk ? 0u : run + ((bit & ANC) ? len : 0u);
+        cur += (bit & REFC) ? len : 0u;
     }
     if (pending) emit(p_start, p_end, p_left, run, read_ord << 16 | (p_k > 0xffffu ? 0xffffu : p_k), tid, strand);
 }
 
-__global__ void __launch_bounds__(S2_THREADS, 2)
-cigar_scan_tma_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
-    extern __shared__ __align__(128) unsigned char s2_raw[];
-    S2Smem& sm = *reinterpret_cast<S2Smem*>(s2_raw);
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(S4_CONSUMERS) : "memory"); }
+
+// one warp copies the staged candidates of buffer `buf` to HBM with a single reservation
+__device__ __forceinline__ void s4_flush(S4Smem& sm, uint32_t buf, uint32_t lane, Cand* __restrict__ out, uint32_t cap,
+                                         uint32_t* counters) {
+    const uint32_t n_st = min(sm.n_out[buf], (uint32_t)S4_OUT);
+    __syncwarp();
+    if (n_st) {
+        uint32_t fb = 0;
+        if (lane == 0) fb = atomicAdd(&counters[CTR_NCAND], n_st);
+        fb = __shfl_sync(0xffffffffu, fb, 0);
+        uint4* o = reinterpret_cast<uint4*>(out);
+        for (uint32_t v = lane; v < 2 * n_st; v += 32) {
+            if (fb + (v >> 1) < cap) o[2ull * fb + v] = sm.out[buf][v];
+            else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) sm.n_out[buf] = 0;
+}
+
+__global__ void __launch_bounds__(S4_THREADS, 2)
+cigar_scan_ws_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
+    extern __shared__ __align__(128) unsigned char s4_raw[];
+    S4Smem& sm = *reinterpret_cast<S4Smem*>(s4_raw);
     const uint32_t t = threadIdx.x, lane = t & 31u;
-    const uint32_t n_tiles = (b.n_reads + S2_TILE - 1) / S2_TILE;
-    const uint32_t n_ops_vec_end = b.n_ops & ~3u;          // bulk copies must not run past the array
+    const uint32_t n_tiles = (b.n_reads + S4_TILE - 1) / S4_TILE;
+    const uint32_t n_ops_vec_end = b.n_ops & ~3u;
+    const uint32_t n_my = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    auto tile_of = [&](uint32_t kk) { return blockIdx.x + kk * gridDim.x; };
 
     if (t == 0) {
-        for (int s = 0; s < S2_STAGES; ++s) { mbar_init(&sm.meta_full[s], 1); mbar_init(&sm.slab_full[s], 1); }
+        for (int s = 0; s < S4_STAGES; ++s) { mbar_init(&sm.meta_full[s], 1); mbar_init(&sm.slab_full[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tile_done[i], S4_CONSUMERS / 32); mbar_init(&sm.out_free[i], 1); }
         sm.n_work[0] = sm.n_work[1] = 0; sm.n_out[0] = sm.n_out[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // metadata of `tile` -> stage s.  Full tiles whose cig_off window (1028 entries) lies inside the
-    // array use four bulk copies from one thread; the (at most two) ragged tiles at the end of the
-    // batch are loaded cooperatively.  Block-uniform; contains a barrier only on the ragged path.
-    auto issue_meta = [&](uint32_t tile, int s) {
-        const uint32_t base = tile * S2_TILE;
-        S2Stage& st = sm.st[s];
-        if (base + S2_TILE + 3 <= b.n_reads) {
-            if (t == 0) {
+    if (t >= (uint32_t)S4_CONSUMERS) {
+        // ======================= service warp: loads and stores =======================
+        auto issue_meta = [&](uint32_t tile, int s) {
+            const uint32_t base = tile * S4_TILE;
+            S4Stage& st = sm.st[s];
+            if (base + S4_TILE + 3 <= b.n_reads) {
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive_expect_tx(&sm.meta_full[s], 3 * S4_TILE * 4 + (S4_TILE + 4) * 4);
+                    bulk_g2s(st.off, b.cig_off + base, (S4_TILE + 4) * 4, &sm.meta_full[s]);
+                    bulk_g2s(st.pos, b.pos + base, S4_TILE * 4, &sm.meta_full[s]);
+                    bulk_g2s(st.meta, b.meta + base, S4_TILE * 4, &sm.meta_full[s]);
+                    bulk_g2s(st.tid, b.tid + base, S4_TILE * 4, &sm.meta_full[s]);
+                }
+            } else {                                           // ragged tail of the batch: plain loads
+                const uint32_t n_tile = min((uint32_t)S4_TILE, b.n_reads - base);
+                for (uint32_t r = lane; r < n_tile; r += 32) {
+                    st.pos[r] = (uint32_t)b.pos[base + r]; st.meta[r] = b.meta[base + r]; st.tid[r] = (uint32_t)b.tid[base + r];
+                }
+                for (uint32_t r = lane; r <= n_tile; r += 32) st.off[r] = b.cig_off[base + r];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.meta_full[s]);
+            }
+        };
+        auto issue_slab = [&](uint32_t kk) {                  // lane 0; tile index kk of this CTA
+            const int s = (int)(kk % S4_STAGES);
+            mbar_wait(&sm.meta_full[s], (kk / S4_STAGES) & 1u);
+            S4Stage& st = sm.st[s];
+            const uint32_t n_tile = min((uint32_t)S4_TILE, b.n_reads - tile_of(kk) * S4_TILE);
+            const uint32_t lo = st.off[0], hi = st.off[n_tile];
+            const uint32_t a0 = lo & ~3u, end4 = (hi + 3u) & ~3u;
+            sm.slab_a0[s] = a0;
+            if (hi <= lo) {
+                sm.slab_direct[s] = 0; mbar_arrive(&sm.slab_full[s]);
+            } else if (end4 - a0 > (uint32_t)S4_SLAB || end4 > n_ops_vec_end) {
+                sm.slab_direct[s] = 1; mbar_arrive(&sm.slab_full[s]);
+            } else {
+                sm.slab_direct[s] = 0;
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive_expect_tx(&sm.meta_full[s], 3 * S2_TILE * 4 + (S2_TILE + 4) * 4);
-                bulk_g2s(st.off, b.cig_off + base, (S2_TILE + 4) * 4, &sm.meta_full[s]);
-                bulk_g2s(st.pos, b.pos + base, S2_TILE * 4, &sm.meta_full[s]);
-                bulk_g2s(st.meta, b.meta + base, S2_TILE * 4, &sm.meta_full[s]);
-                bulk_g2s(st.tid, b.tid + base, S2_TILE * 4, &sm.meta_full[s]);
+                mbar_arrive_expect_tx(&sm.slab_full[s], (end4 - a0) * 4);
+                bulk_g2s(st.slab, b.cigar + a0, (end4 - a0) * 4, &sm.slab_full[s]);
             }
-        } else {
-            const uint32_t n_tile = min((uint32_t)S2_TILE, b.n_reads - base);
-            for (uint32_t r = t; r < n_tile; r += S2_THREADS) {
-                st.pos[r] = (uint32_t)b.pos[base + r]; st.meta[r] = b.meta[base + r]; st.tid[r] = (uint32_t)b.tid[base + r];
+        };
+        // L2 prefetch of a tile's metadata columns (lanes 0..3 take one column each): keeps more bytes in
+        // flight to HBM than the shared-memory ring alone can hold
+        auto prefetch_meta = [&](uint32_t kk) {
+            if (kk >= n_my || (prm.debug & 16u)) return;
+            const uint32_t base = tile_of(kk) * S4_TILE;
+            if (base + S4_TILE + 3 > b.n_reads) return;
+            if (lane == 0) bulk_prefetch_l2(b.cig_off + base, (S4_TILE + 4) * 4);
+            else if (lane == 1) bulk_prefetch_l2(b.pos + base, S4_TILE * 4);
+            else if (lane == 2) bulk_prefetch_l2(b.meta + base, S4_TILE * 4);
+            else if (lane == 3) bulk_prefetch_l2(b.tid + base, S4_TILE * 4);
+        };
+        for (uint32_t i = 0; i < (uint32_t)S4_STAGES && i < n_my; ++i) issue_meta(tile_of(i), (int)i);
+        for (uint32_t i = 0; i < (uint32_t)S4_L2_AHEAD; ++i) prefetch_meta(S4_STAGES + i);
+        if (lane == 0) for (uint32_t i = 0; i < (uint32_t)S4_STAGES && i < n_my; ++i) issue_slab(i);
+        for (uint32_t k = 0; k < n_my; ++k) {
+            const uint32_t cb = k & 1u;
+            mbar_wait(&sm.tile_done[cb], (k / 2) & 1u);        // every consumer warp is past tile k
+            if (k + S4_STAGES < n_my) issue_meta(tile_of(k + S4_STAGES), (int)(k % S4_STAGES));
+            prefetch_meta(k + S4_STAGES + S4_L2_AHEAD);
+            if (prm.debug & 8u) { if (lane == 0) sm.n_out[cb] = 0; } else s4_flush(sm, cb, lane, out, cap, counters);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&sm.out_free[cb]);
+                // the slab of tile k+3 goes out as soon as its cig_off column (issued above) has landed:
+                // the dependent load gets ~two tiles of slack before consumers need it
+                if (k + S4_STAGES < n_my) issue_slab(k + S4_STAGES);
             }
-            for (uint32_t r = t; r <= n_tile; r += S2_THREADS) st.off[r] = b.cig_off[base + r];
-            __syncthreads();
-            if (t == 0) mbar_arrive(&sm.meta_full[s]);
+            __syncwarp();
         }
-    };
-    // CIGAR slab of the tile whose metadata is (or will be) in stage s.  Thread 0 only.
-    auto issue_slab = [&](uint32_t tile, int s, uint32_t parity) {
-        mbar_wait(&sm.meta_full[s], parity);
-        S2Stage& st = sm.st[s];
-        const uint32_t n_tile = min((uint32_t)S2_TILE, b.n_reads - tile * S2_TILE);
-        const uint32_t lo = st.off[0], hi = st.off[n_tile];
-        const uint32_t a0 = lo & ~3u, end4 = (hi + 3u) & ~3u;
-        sm.slab_a0[s] = a0;
-        if (hi <= lo) {                                       // no ops at all
-            sm.slab_direct[s] = 0; mbar_arrive(&sm.slab_full[s]);
-        } else if (end4 - a0 > (uint32_t)S2_SLAB || end4 > n_ops_vec_end) {
-            sm.slab_direct[s] = 1; mbar_arrive(&sm.slab_full[s]);
-        } else {
-            sm.slab_direct[s] = 0;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive_expect_tx(&sm.slab_full[s], (end4 - a0) * 4);
-            bulk_g2s(st.slab, b.cigar + a0, (end4 - a0) * 4, &sm.slab_full[s]);
-        }
-    };
-
-    // prologue: metadata of the first S2_STAGES tiles of this CTA, slab of the first
-    for (int s = 0; s < S2_STAGES; ++s) {
-        const uint32_t tile = blockIdx.x + (uint32_t)s * gridDim.x;
-        if (tile < n_tiles) issue_meta(tile, s);
+        return;
     }
-    if (t == 0 && blockIdx.x < n_tiles) issue_slab(blockIdx.x, 0, 0);
 
-    uint32_t k = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-        const int s = (int)(k % S2_STAGES);
-        const uint32_t parity = (k / S2_STAGES) & 1u;
-        const uint32_t cb = k & 1u;                          // counter buffer of this iteration
-        const uint32_t next = tile + gridDim.x;
-        if (t == 0 && next < n_tiles) issue_slab(next, (int)((k + 1) % S2_STAGES), ((k + 1) / S2_STAGES) & 1u);
+    // ============================ consumer warps ============================
+    for (uint32_t k = 0; k < n_my; ++k) {
+        const uint32_t tile = tile_of(k);
+        const int s = (int)(k % S4_STAGES);
+        const uint32_t parity = (k / S4_STAGES) & 1u;
+        const uint32_t cb = k & 1u;
         mbar_wait(&sm.meta_full[s], parity);
-        mbar_wait(&sm.slab_full[s], parity);
-        S2Stage& st = sm.st[s];
-        const uint32_t base = tile * S2_TILE;
-        const uint32_t n_tile = min((uint32_t)S2_TILE, b.n_reads - base);
+        S4Stage& st = sm.st[s];
+        const uint32_t base = tile * S4_TILE;
+        const uint32_t n_tile = min((uint32_t)S4_TILE, b.n_reads - base);
 
         // ---- phase A: compact the alignments that have more than one CIGAR op (junctions_extractor.cc:379)
         {
@@ -434,50 +508,197 @@ cigar_scan_tma_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint3
             if (lane == 31 && x) wbase = atomicAdd(&sm.n_work[cb], x);
             wbase = __shfl_sync(0xffffffffu, wbase, 31);
             uint32_t p = wbase + x - cnt;
-            if (flags & 1u) sm.work[p++] = (uint16_t)(r0 + 0);
-            if (flags & 2u) sm.work[p++] = (uint16_t)(r0 + 1);
-            if (flags & 4u) sm.work[p++] = (uint16_t)(r0 + 2);
-            if (flags & 8u) sm.work[p++] = (uint16_t)(r0 + 3);
+            uint16_t* work = sm.work[cb];
+            if (flags & 1u) work[p++] = (uint16_t)(r0 + 0);
+            if (flags & 2u) work[p++] = (uint16_t)(r0 + 1);
+            if (flags & 4u) work[p++] = (uint16_t)(r0 + 2);
+            if (flags & 8u) work[p++] = (uint16_t)(r0 + 3);
         }
-        __syncthreads();
-        if (t == 0) { sm.n_work[cb ^ 1u] = 0; sm.n_out[cb ^ 1u] = 0; }
+        consumer_bar();
+        if (t == 0) sm.n_work[cb ^ 1u] = 0;                   // for tile k+1; nobody reads it any more
 
-        // ---- phase B: walk the compacted alignments, one per thread
+        // ---- phase B: walk the compacted alignments, one per thread, in rounds of 256
         {
-            const uint32_t n_work = sm.n_work[cb];
+            const uint32_t n_work = (prm.debug & 1u) ? 0u : sm.n_work[cb];
+            // unconditional: these waits also keep consumers at most two tiles ahead of the service warp,
+            // which the 1-bit phase parity of tile_done / slab_full relies on
+            mbar_wait(&sm.slab_full[s], parity);
+            if (k >= 2) mbar_wait(&sm.out_free[cb], ((k / 2) - 1u) & 1u);       // staging buffer drained (tile k-2)
             const uint32_t a0 = sm.slab_a0[s];
             const bool direct = sm.slab_direct[s] != 0;
-            const S2Emit emit{sm, cb, out, cap, counters};
-            for (uint32_t w = t; w < n_work; w += S2_THREADS) {
-                const uint32_t r = sm.work[w];
-                const int32_t tid = (int32_t)st.tid[r];
-                if (tid < 0) continue;
-                const uint32_t o0 = st.off[r], n = st.off[r + 1] - o0;
-                const uint32_t strand = read_strand(st.meta[r], prm.strandness);
-                const uint64_t read_ord = b.first_ordinal + base + r;
-                if (!direct) walk_ops<true>(st.slab + (o0 - a0), n, st.pos[r], tid, strand, read_ord, emit);
-                else walk_ops<false>(b.cigar + o0, n, st.pos[r], tid, strand, read_ord, emit);
+            const S4Emit emit{sm, cb, out, cap, counters, prm.debug};
+            const uint16_t* work = sm.work[cb];
+            for (uint32_t w0 = 0; w0 < n_work; w0 += S4_CONSUMERS) {
+                const uint32_t w = w0 + t;
+                if (w < n_work) {
+                    const uint32_t r = work[w];
+                    const int32_t tid = (int32_t)st.tid[r];
+                    if (tid >= 0) {
+                        const uint32_t o0 = st.off[r], n = st.off[r + 1] - o0;
+                        const uint32_t strand = read_strand(st.meta[r], prm.strandness);
+                        const uint64_t read_ord = b.first_ordinal + base + r;
+                        if (!direct) walk_fast<true>(st.slab + (o0 - a0), n, st.pos[r], tid, strand, read_ord, emit);
+                        else walk_fast<false>(b.cigar + o0, n, st.pos[r], tid, strand, read_ord, emit);
+                    }
+                }
+                if (w0 + S4_CONSUMERS < n_work) {              // dense tile: drain the staging buffer between rounds
+                    consumer_bar();
+                    if (t < 32) s4_flush(sm, cb, lane, out, cap, counters);
+                    consumer_bar();
+                }
             }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.tile_done[cb]);
+    }
+}
 
-        // ---- stage s is drained: refill it with the tile S2_STAGES iterations ahead
-        {
-            const uint32_t refill = tile + (uint32_t)S2_STAGES * gridDim.x;
-            if (refill < n_tiles) issue_meta(refill, s);
+// ------------------------------------------------------------------------------------------------
+// cigar_scan, many-small-blocks version (variant 5)
+// ------------------------------------------------------------------------------------------------
+// 128 threads per block, one tile of 512 alignments per block, ~18 KB of shared memory: up to 12
+// blocks are resident per SM and the hardware block scheduler overlaps their phases, so while some
+// blocks wait for their (data-dependent) CIGAR slab others are streaming metadata or walking.
+// Columns and slab go global -> shared with 16-byte cp.async (LDGSTS), no register staging.
+constexpr int S5_THREADS = 128;
+constexpr int S5_TILE    = 512;
+constexpr int S5_SLAB    = 1024;                 // CIGAR words staged per tile (4 KB)
+constexpr int S5_OUT     = 192;                  // staged candidates (6 KB)
+
+struct alignas(16) S5Smem {
+    uint32_t off[S5_TILE + 4];
+    uint32_t pos[S5_TILE];
+    uint32_t meta[S5_TILE];
+    uint32_t tid[S5_TILE];
+    uint32_t slab[S5_SLAB];
+    uint4 out[S5_OUT * 2];
+    uint32_t n_work, n_out;
+    uint16_t work[S5_TILE];
+};
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct S5Emit {
+    S5Smem& sm; Cand* __restrict__ out; uint32_t cap; uint32_t* counters;
+    __device__ __forceinline__ void operator()(uint32_t start, uint32_t end, uint32_t left, uint32_t right,
+                                               uint64_t ord, int32_t tid, uint32_t strand) const {
+        uint4 a = make_uint4(start, end, start - left, end + right);
+        uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
+        const uint32_t mask = __activemask();
+        const uint32_t lane = threadIdx.x & 31u;
+        const int leader = __ffs(mask) - 1;
+        uint32_t i = 0;
+        if ((int)lane == leader) i = atomicAdd(&sm.n_out, (uint32_t)__popc(mask));
+        i = __shfl_sync(mask, i, leader) + __popc(mask & ((1u << lane) - 1u));
+        if (i < S5_OUT) {
+            sm.out[2 * i] = a; sm.out[2 * i + 1] = b;
+        } else {
+            uint32_t g = atomicAdd(&counters[CTR_NCAND], 1u);
+            if (g < cap) { uint4* o = reinterpret_cast<uint4*>(out + g); o[0] = a; o[1] = b; }
+            else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
         }
-        // ---- flush the staged candidates with one reservation per tile
-        const uint32_t n_st = min(sm.n_out[cb], (uint32_t)S2_OUT);
+    }
+};
+
+__global__ void __launch_bounds__(S5_THREADS, 12)
+cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
+    __shared__ S5Smem sm;
+    const uint32_t t = threadIdx.x, lane = t & 31u;
+    const uint32_t base = blockIdx.x * S5_TILE;
+    const uint32_t n_tile = min((uint32_t)S5_TILE, b.n_reads - base);
+    const bool full = base + S5_TILE + 3 <= b.n_reads;        // the 516-entry cig_off window is in bounds
+
+    // ---- metadata columns: global -> shared, 16 bytes per cp.async
+    if (full) {
+        cp_async16(&sm.off[4 * t], b.cig_off + base + 4 * t);
+        cp_async16(&sm.pos[4 * t], b.pos + base + 4 * t);
+        cp_async16(&sm.meta[4 * t], b.meta + base + 4 * t);
+        cp_async16(&sm.tid[4 * t], b.tid + base + 4 * t);
+        if (t == 0) cp_async16(&sm.off[S5_TILE], b.cig_off + base + S5_TILE);
+    } else {
+        for (uint32_t r = t; r < n_tile; r += S5_THREADS) {
+            sm.pos[r] = (uint32_t)b.pos[base + r]; sm.meta[r] = b.meta[base + r]; sm.tid[r] = (uint32_t)b.tid[base + r];
+        }
+        for (uint32_t r = t; r <= n_tile; r += S5_THREADS) sm.off[r] = b.cig_off[base + r];
+    }
+    if (t == 0) { sm.n_work = 0; sm.n_out = 0; }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- CIGAR slab of the tile (data-dependent address): issue, then compact while it is in flight
+    const uint32_t lo = sm.off[0], hi = sm.off[n_tile];
+    const uint32_t a0 = lo & ~3u, end4 = (hi + 3u) & ~3u;
+    const bool direct = hi > lo && (end4 - a0 > (uint32_t)S5_SLAB || end4 > (b.n_ops & ~3u));
+    if (!direct && hi > lo) {
+        const uint32_t n_vec = (end4 - a0) >> 2;
+        for (uint32_t v = t; v < n_vec; v += S5_THREADS) cp_async16(&sm.slab[4 * v], b.cigar + a0 + 4 * v);
+    }
+    cp_async_commit();
+    {
+        const uint4 o = *reinterpret_cast<const uint4*>(&sm.off[4 * t]);
+        const uint32_t o4 = sm.off[4 * t + 4];
+        const uint32_t r0 = 4 * t;
+        uint32_t flags = 0;
+        if (r0 + 0 < n_tile && o.y - o.x > 1u) flags |= 1u;
+        if (r0 + 1 < n_tile && o.z - o.y > 1u) flags |= 2u;
+        if (r0 + 2 < n_tile && o.w - o.z > 1u) flags |= 4u;
+        if (r0 + 3 < n_tile && o4 - o.w > 1u) flags |= 8u;
+        const uint32_t cnt = __popc(flags);
+        uint32_t x = cnt;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
+        uint32_t wbase = 0;
+        if (lane == 31 && x) wbase = atomicAdd(&sm.n_work, x);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        uint32_t p = wbase + x - cnt;
+        if (flags & 1u) sm.work[p++] = (uint16_t)(r0 + 0);
+        if (flags & 2u) sm.work[p++] = (uint16_t)(r0 + 1);
+        if (flags & 4u) sm.work[p++] = (uint16_t)(r0 + 2);
+        if (flags & 8u) sm.work[p++] = (uint16_t)(r0 + 3);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- walk the compacted alignments, one per thread, in rounds of 128
+    const uint32_t n_work = (prm.debug & 1u) ? 0u : sm.n_work;
+    const S5Emit emit{sm, out, cap, counters};
+    auto flush = [&]() {                                        // warp 0
+        const uint32_t n_st = min(sm.n_out, (uint32_t)S5_OUT);
+        __syncwarp();
         if (n_st) {
-            if (t == 0) sm.flush_base = atomicAdd(&counters[CTR_NCAND], n_st);
-            __syncthreads();
-            const uint32_t fb = sm.flush_base;
+            uint32_t fb = 0;
+            if (lane == 0) fb = atomicAdd(&counters[CTR_NCAND], n_st);
+            fb = __shfl_sync(0xffffffffu, fb, 0);
             uint4* o = reinterpret_cast<uint4*>(out);
-            for (uint32_t v = t; v < 2 * n_st; v += S2_THREADS) {
+            for (uint32_t v = lane; v < 2 * n_st; v += 32) {
                 if (fb + (v >> 1) < cap) o[2ull * fb + v] = sm.out[v];
                 else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
             }
         }
+        __syncwarp();
+        if (lane == 0) sm.n_out = 0;
+    };
+    for (uint32_t w0 = 0; w0 < n_work; w0 += S5_THREADS) {
+        const uint32_t w = w0 + t;
+        if (w < n_work) {
+            const uint32_t r = sm.work[w];
+            const int32_t tid = (int32_t)sm.tid[r];
+            if (tid >= 0) {
+                const uint32_t o0 = sm.off[r], n = sm.off[r + 1] - o0;
+                const uint32_t strand = read_strand(sm.meta[r], prm.strandness);
+                const uint64_t read_ord = b.first_ordinal + base + r;
+                if (!direct) walk_fast<true>(sm.slab + (o0 - a0), n, sm.pos[r], tid, strand, read_ord, emit);
+                else walk_fast<false>(b.cigar + o0, n, sm.pos[r], tid, strand, read_ord, emit);
+            }
+        }
+        __syncthreads();
+        if (t < 32) flush();
+        if (w0 + S5_THREADS < n_work) __syncthreads();
     }
 }
 
@@ -487,15 +708,18 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
     const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
                             reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
                             reinterpret_cast<uintptr_t>(b.cigar);
-    if ((align & 15u) == 0) {            // bulk async copies need 16-byte aligned columns (cudaMalloc gives 256)
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(cigar_scan_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S2Smem));
-            attr_set = true;
-        }
-        const uint32_t tiles = (b.n_reads + S2_TILE - 1) / S2_TILE;
-        const uint32_t grid = min(tiles, (uint32_t)(2 * num_sms()));
-        cigar_scan_tma_kernel<<<grid, S2_THREADS, sizeof(S2Smem), stream>>>(b, p, cands, cand_cap, d_counters);
+    static int variant = -1;
+    if (variant < 0) { const char* v = getenv("RTJX_SCAN_VARIANT"); variant = v ? atoi(v) : 5; }
+    if ((align & 15u) == 0 && variant == 5) {
+        const uint32_t tiles = (b.n_reads + S5_TILE - 1) / S5_TILE;
+        cigar_scan_small_kernel<<<tiles, S5_THREADS, 0, stream>>>(b, p, cands, cand_cap, d_counters);
+        return;
+    }
+    if ((align & 15u) == 0 && variant == 4) {
+        static bool attr4 = false;
+        if (!attr4) { cudaFuncSetAttribute(cigar_scan_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S4Smem)); attr4 = true; }
+        const uint32_t tiles = (b.n_reads + S4_TILE - 1) / S4_TILE;
+        cigar_scan_ws_kernel<<<min(tiles, (uint32_t)(2 * num_sms())), S4_THREADS, sizeof(S4Smem), stream>>>(b, p, cands, cand_cap, d_counters);
         return;
     }
     uint32_t grid = (b.n_reads + SCAN_TILE - 1) / SCAN_TILE;
@@ -505,19 +729,23 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
 // ------------------------------------------------------------------------------------------------
 // device-wide junction table
 // ------------------------------------------------------------------------------------------------
-// Upsert of an (already aggregated) partial reduction into the global table.  Returns false if the
-// table has no free slot on the probe path (caller spills).
-__device__ __forceinline__ bool table_upsert(Slot* __restrict__ table, uint32_t mask, K128 key, uint32_t count,
-                                             uint32_t nts, uint32_t te, uint32_t lr, unsigned long long nfirst,
-                                             unsigned long long last, uint32_t* counters) {
+// Upsert of an (already aggregated) partial reduction into the global table.  The thread that wins
+// the 128-bit CAS on an empty slot also records the slot index in `slot_list` (position = running
+// count of distinct junctions), so finalize and clear touch only occupied slots.  Returns false
+// if the table has no free slot on the probe path (caller spills).
+__device__ __forceinline__ bool table_upsert(const TableRef& tb, K128 key, uint32_t count, uint32_t nts, uint32_t te,
+                                             uint32_t lr, unsigned long long nfirst, unsigned long long last,
+                                             uint32_t* counters) {
+    const uint32_t mask = tb.mask;
     uint32_t s = mix_key(key.lo, key.hi) & mask;
     for (uint32_t probe = 0; probe <= mask; ++probe, s = (s + 1) & mask) {
-        Slot* sl = table + s;
+        Slot* sl = tb.slots + s;
         K128 cur = ld128_relaxed(sl);
         if (cur.lo == 0ull && cur.hi == 0ull) {
             cur = cas128(sl, K128{0ull, 0ull}, key);
             if (cur.lo == 0ull && cur.hi == 0ull) {
-                atomicAdd(&counters[CTR_NUNIQUE], 1u);
+                const uint32_t idx = atomicAdd(&counters[CTR_NUNIQUE], 1u);
+                if (idx < tb.list_cap) tb.slot_list[idx] = s;
                 cur = key;
             }
         }
@@ -571,8 +799,8 @@ struct MergeSmem {
 
 __global__ void __launch_bounds__(MERGE_THREADS, 2)
 junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict__ d_n_cand, uint32_t n_bound,
-                      ScanParams prm, Slot* __restrict__ table, uint32_t mask, Slot* __restrict__ spill,
-                      uint32_t spill_cap, uint32_t* __restrict__ counters) {
+                      ScanParams prm, TableRef tb, Slot* __restrict__ spill, uint32_t spill_cap,
+                      uint32_t* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MergeSmem& sm = *reinterpret_cast<MergeSmem*>(smem_raw);
     const uint32_t t = threadIdx.x;
@@ -582,12 +810,12 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
         atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_TOTAL_CAND64), (unsigned long long)n);
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t tb = tile * MERGE_TILE;
+        const uint32_t tb0 = tile * MERGE_TILE;
         for (uint32_t s = t; s < MERGE_SLOTS; s += MERGE_THREADS) {
             sm.key[s] = SKEY_EMPTY; sm.nfirst[s] = 0ull; sm.last[s] = 0ull;
             sm.count[s] = 0u; sm.nts[s] = 0u; sm.te[s] = 0u; sm.lr[s] = 0u;
         }
-        if (t == 0) sm.base_tid = cands[tb].tid;
+        if (t == 0) sm.base_tid = cands[tb0].tid;
         __syncthreads();
         const int32_t base_tid = sm.base_tid;
 
@@ -595,7 +823,7 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
         uint4 ca[MERGE_CPT], cb[MERGE_CPT];
 #pragma unroll
         for (int j = 0; j < MERGE_CPT; ++j) {
-            uint32_t i = tb + t + j * MERGE_THREADS;
+            uint32_t i = tb0 + t + j * MERGE_THREADS;
             if (i < n) {
                 const uint4* p = reinterpret_cast<const uint4*>(cands + i);
                 ca[j] = ldg_stream_u4(p);
@@ -639,7 +867,7 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
             }
             if (!done) {
                 K128 key{(unsigned long long)start << 32 | end, ((unsigned long long)(uint32_t)(tid + 1)) << 2 | proxy};
-                if (!table_upsert(table, mask, key, 1u, ~ts, te, lr, nfirst, last, counters))
+                if (!table_upsert(tb, key, 1u, ~ts, te, lr, nfirst, last, counters))
                     spill_entry(spill, spill_cap, counters, key, 1u, ~ts, te, lr, nfirst, last);
             }
         }
@@ -651,7 +879,7 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
             const uint32_t start = (uint32_t)(k >> 30), ilen = (uint32_t)(k >> 2) & 0x0fffffffu, proxy = (uint32_t)k & 3u;
             K128 key{(unsigned long long)start << 32 | (uint32_t)(start + ilen),
                      ((unsigned long long)(uint32_t)(base_tid + 1)) << 2 | proxy};
-            if (!table_upsert(table, mask, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s], counters))
+            if (!table_upsert(tb, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s], counters))
                 spill_entry(spill, spill_cap, counters, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s]);
         }
         __syncthreads();
@@ -670,7 +898,7 @@ static int num_sms() {
 }
 
 void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound, const ScanParams& p,
-                           Slot* table, uint32_t table_mask, Slot* spill_slots, uint32_t spill_cap, uint32_t* d_counters,
+                           const TableRef& tb, Slot* spill_slots, uint32_t spill_cap, uint32_t* d_counters,
                            cudaStream_t stream) {
     if (n_cand_bound == 0) return;
     static bool attr_set = false;
@@ -681,148 +909,107 @@ void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t
     uint32_t tiles = (n_cand_bound + MERGE_TILE - 1) / MERGE_TILE;
     uint32_t grid = min(tiles, (uint32_t)(2 * num_sms()));
     junction_merge_kernel<<<grid, MERGE_THREADS, sizeof(MergeSmem), stream>>>(
-        cands, d_n_cand, n_cand_bound, p, table, table_mask, spill_slots, spill_cap, d_counters);
+        cands, d_n_cand, n_cand_bound, p, tb, spill_slots, spill_cap, d_counters);
 }
 
-// Re-inserts every occupied slot of `src` (an old table, or the spill list) into `table`.
+// Re-inserts every occupied slot of `src` (an old table, or the spill list) into the table.
 __global__ void __launch_bounds__(256)
-table_rehash_kernel(const Slot* __restrict__ src, uint32_t n_src, Slot* __restrict__ table, uint32_t mask,
-                    uint32_t* __restrict__ counters) {
+table_rehash_kernel(const Slot* __restrict__ src, uint32_t n_src, TableRef tb, uint32_t* __restrict__ counters) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
         Slot s = src[i];
         if (s.khi == 0ull) continue;
-        if (!table_upsert(table, mask, K128{s.klo, s.khi}, s.count, s.nts, s.te, s.lr, s.nfirst, s.last, counters))
+        if (!table_upsert(tb, K128{s.klo, s.khi}, s.count, s.nts, s.te, s.lr, s.nfirst, s.last, counters))
             atomicExch(&counters[CTR_CAND_OVERFLOW], 2u);
     }
 }
 
-void launch_table_rehash(const Slot* old_table, uint32_t old_slots, Slot* table, uint32_t table_mask,
-                         uint32_t* d_counters, cudaStream_t stream) {
+void launch_table_rehash(const Slot* old_table, uint32_t old_slots, const TableRef& tb, uint32_t* d_counters,
+                         cudaStream_t stream) {
     if (old_slots == 0) return;
     uint32_t grid = min((old_slots + 255u) / 256u, (uint32_t)(8 * num_sms()));
-    table_rehash_kernel<<<grid, 256, 0, stream>>>(old_table, old_slots, table, table_mask, d_counters);
+    table_rehash_kernel<<<grid, 256, 0, stream>>>(old_table, old_slots, tb, d_counters);
+}
+
+// Zeroes the occupied slots (rtjx_clear); 3 x 16 bytes per slot.
+__global__ void __launch_bounds__(256)
+table_clear_kernel(TableRef tb, const uint32_t* __restrict__ d_n_unique) {
+    const uint32_t n = min(*d_n_unique, tb.list_cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint4* p = reinterpret_cast<uint4*>(tb.slots + tb.slot_list[i]);
+        p[0] = make_uint4(0, 0, 0, 0); p[1] = make_uint4(0, 0, 0, 0); p[2] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+void launch_table_clear(const TableRef& tb, const uint32_t* d_n_unique, uint32_t n_bound, cudaStream_t stream) {
+    if (n_bound == 0) return;
+    uint32_t grid = min((n_bound + 255u) / 256u, (uint32_t)(8 * num_sms()));
+    table_clear_kernel<<<grid, 256, 0, stream>>>(tb, d_n_unique);
 }
 
 // ------------------------------------------------------------------------------------------------
 // finalize: compaction, first-seen ranking, sort
 // ------------------------------------------------------------------------------------------------
+// slot_list[i] -> OutJunction[i]; no scan of the (mostly empty) table.
 __global__ void __launch_bounds__(256)
-table_compact_kernel(const Slot* __restrict__ table, uint32_t n_slots, OutJunction* __restrict__ out, uint32_t out_cap,
-                     uint32_t* __restrict__ d_n_out) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t n_round = (n_slots + stride - 1) / stride * stride;     // keep warps converged for the ballot
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        Slot s;
-        bool occ = false;
-        if (i < n_slots) {
-            const uint4* p = reinterpret_cast<const uint4*>(table + i);
-            uint4 k = p[0];
-            occ = (k.z | k.w) != 0u;                                     // khi != 0
-            if (occ) {
-                uint4 v = p[1], w = p[2];
-                s.klo = (unsigned long long)k.y << 32 | k.x; s.khi = (unsigned long long)k.w << 32 | k.z;
-                s.count = v.x; s.nts = v.y; s.te = v.z; s.lr = v.w;
-                s.nfirst = (unsigned long long)w.y << 32 | w.x; s.last = (unsigned long long)w.w << 32 | w.z;
-            }
-        }
-        const uint32_t m = __ballot_sync(0xffffffffu, occ);
-        if (m == 0u) continue;
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(d_n_out, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (occ) {
-            uint32_t o = base + __popc(m & ((1u << lane) - 1u));
-            if (o < out_cap) {
-                OutJunction j;
-                const uint32_t proxy = (uint32_t)s.khi & 3u;
-                j.tid = (int32_t)(uint32_t)(s.khi >> 2) - 1;
-                j.start = (uint32_t)(s.klo >> 32); j.end = (uint32_t)s.klo;
-                j.ts = ~s.nts; j.te = s.te; j.count = s.count; j.name_index = 0;
-                j.strand = proxy == 0u ? '+' : (proxy == 1u ? '-' : (uint8_t)(s.last & 0xffu));
-                j.left_ok = s.lr & 1u; j.right_ok = (s.lr >> 1) & 1u; j.pad = 0;
-                j.first_ord = ~s.nfirst;
-                out[o] = j;
-            }
-        }
-    }
+table_compact_kernel(TableRef tb, uint32_t n, OutJunction* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* p = reinterpret_cast<const uint4*>(tb.slots + tb.slot_list[i]);
+    const uint4 k = p[0], v = p[1], w = p[2];
+    const unsigned long long khi = (unsigned long long)k.w << 32 | k.z;
+    const unsigned long long last = (unsigned long long)w.w << 32 | w.z;
+    const uint32_t proxy = (uint32_t)khi & 3u;
+    OutJunction j;
+    j.tid = (int32_t)(uint32_t)(khi >> 2) - 1;
+    j.start = k.y; j.end = k.x;                      // klo = start << 32 | end
+    j.ts = ~v.y; j.te = v.z; j.count = v.x; j.name_index = 0;
+    j.strand = proxy == 0u ? '+' : (proxy == 1u ? '-' : (uint8_t)(last & 0xffu));
+    j.left_ok = v.w & 1u; j.right_ok = (v.w >> 1) & 1u; j.pad = 0;
+    j.first_ord = ~((unsigned long long)w.y << 32 | w.x);
+    out[i] = j;
 }
 
-void launch_table_compact(const Slot* table, uint32_t n_slots, OutJunction* out, uint32_t out_cap, uint32_t* d_n_out,
-                          cudaStream_t stream) {
-    uint32_t grid = min((n_slots + 255u) / 256u, (uint32_t)(8 * num_sms()));
-    table_compact_kernel<<<grid, 256, 0, stream>>>(table, n_slots, out, out_cap, d_n_out);
+void launch_table_compact(const TableRef& tb, uint32_t n, OutJunction* out, cudaStream_t stream) {
+    if (n == 0) return;
+    table_compact_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(tb, n, out);
 }
 
-// key builders / gathers for the two-pass LSD sort
-__global__ void fin_keys_first(const OutJunction* __restrict__ e, uint32_t n, unsigned long long* __restrict__ k,
-                               uint32_t* __restrict__ v) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { k[i] = e[i].first_ord; v[i] = i; }
-}
-// after sorting by first_ord: v[r] = entry index with rank r  -> name_index = r+1; key = te<<32|name
-__global__ void fin_assign_names(OutJunction* __restrict__ e, uint32_t n, const uint32_t* __restrict__ v,
-                                 unsigned long long* __restrict__ k2) {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) {
-        uint32_t i = v[r];
-        e[i].name_index = r + 1u;
-        k2[r] = (unsigned long long)e[i].te << 32 | (r + 1u);
+struct ByFirstOrd {
+    __device__ __forceinline__ bool operator()(const OutJunction& a, const OutJunction& b) const { return a.first_ord < b.first_ord; }
+};
+// compare_junctions (junctions_extractor.h:117-140) with the contig string order precomputed as a rank
+struct ByBedOrder {
+    const uint32_t* contig_rank; uint32_t n_contigs;
+    __device__ __forceinline__ uint32_t cr(int32_t tid) const {
+        return (uint32_t)tid < n_contigs ? contig_rank[tid] : 0x40000000u + (uint32_t)tid;
     }
-}
-__global__ void fin_keys_major(const OutJunction* __restrict__ e, uint32_t n, const uint32_t* __restrict__ v,
-                               const uint32_t* __restrict__ contig_rank, uint32_t n_contigs,
-                               unsigned long long* __restrict__ k3) {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) {
-        const OutJunction& j = e[v[r]];
-        uint32_t cr = (uint32_t)j.tid < n_contigs ? contig_rank[j.tid] : 0x40000000u + (uint32_t)j.tid;
-        k3[r] = (unsigned long long)cr << 32 | j.ts;
+    __device__ __forceinline__ bool operator()(const OutJunction& a, const OutJunction& b) const {
+        const uint32_t ca = cr(a.tid), cb = cr(b.tid);
+        if (ca != cb) return ca < cb;
+        if (a.ts != b.ts) return a.ts < b.ts;
+        if (a.te != b.te) return a.te < b.te;
+        return a.name_index < b.name_index;
     }
-}
-__global__ void fin_gather(const OutJunction* __restrict__ e, uint32_t n, const uint32_t* __restrict__ v,
-                           OutJunction* __restrict__ out) {
+};
+__global__ void fin_assign_names(OutJunction* __restrict__ e, uint32_t n) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) out[r] = e[v[r]];
+    if (r < n) e[r].name_index = r + 1u;            // rank of first appearance (junctions_extractor.cc:152-157)
 }
-
-static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 size_t finalize_sort_workspace_bytes(uint32_t n) {
-    size_t cub_bytes = 0;
-    cub::DoubleBuffer<unsigned long long> dk(nullptr, nullptr);
-    cub::DoubleBuffer<uint32_t> dv(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, dk, dv, (int)n);
-    return align_up(cub_bytes, 256) + 2 * align_up((size_t)n * 8, 256) + 2 * align_up((size_t)n * 4, 256) + 256;
+    size_t a = 0, b = 0;
+    cub::DeviceMergeSort::SortKeys(nullptr, a, (OutJunction*)nullptr, (int)n, ByFirstOrd());
+    cub::DeviceMergeSort::SortKeys(nullptr, b, (OutJunction*)nullptr, (int)n, ByBedOrder{nullptr, 0});
+    return (a > b ? a : b) + 256;
 }
 
-// entries[0..n) -> scratch[0..n) sorted by (contig_rank, ts, te, name_index); names ranked by first_ord.
-void launch_finalize_sort(OutJunction* entries, OutJunction* scratch, uint32_t n, const uint32_t* contig_rank,
-                          uint32_t n_contigs, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+// entries[0..n): ranked by first_ord (name_index), then sorted in place by (contig string, ts, te, name).
+void launch_finalize_sort(OutJunction* entries, uint32_t n, const uint32_t* contig_rank, uint32_t n_contigs,
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (n == 0) return;
-    unsigned char* w = static_cast<unsigned char*>(workspace);
-    size_t kb = align_up((size_t)n * 8, 256), vb = align_up((size_t)n * 4, 256);
-    unsigned long long* k0 = reinterpret_cast<unsigned long long*>(w); w += kb;
-    unsigned long long* k1 = reinterpret_cast<unsigned long long*>(w); w += kb;
-    uint32_t* v0 = reinterpret_cast<uint32_t*>(w); w += vb;
-    uint32_t* v1 = reinterpret_cast<uint32_t*>(w); w += vb;
-    size_t cub_bytes = workspace_bytes - (size_t)(w - static_cast<unsigned char*>(workspace));
-    const uint32_t g = (n + 255u) / 256u;
-
-    cub::DoubleBuffer<unsigned long long> dk(k0, k1);
-    cub::DoubleBuffer<uint32_t> dv(v0, v1);
-    // 1. rank by first_ord
-    fin_keys_first<<<g, 256, 0, stream>>>(entries, n, dk.Current(), dv.Current());
-    cub::DeviceRadixSort::SortPairs(w, cub_bytes, dk, dv, (int)n, 0, 64, stream);
-    // 2. minor key (thick_end, name)
-    fin_assign_names<<<g, 256, 0, stream>>>(entries, n, dv.Current(), dk.Alternate());
-    dk.selector ^= 1;   // keys now live in the former alternate buffer, values stay current
-    cub::DeviceRadixSort::SortPairs(w, cub_bytes, dk, dv, (int)n, 0, 64, stream);
-    // 3. major key (contig string rank, thick_start); radix sort is stable
-    fin_keys_major<<<g, 256, 0, stream>>>(entries, n, dv.Current(), contig_rank, n_contigs, dk.Alternate());
-    dk.selector ^= 1;
-    cub::DeviceRadixSort::SortPairs(w, cub_bytes, dk, dv, (int)n, 0, 64, stream);
-    fin_gather<<<g, 256, 0, stream>>>(entries, n, dv.Current(), scratch);
+    cub::DeviceMergeSort::SortKeys(workspace, workspace_bytes, entries, (int)n, ByFirstOrd(), stream);
+    fin_assign_names<<<(n + 255u) / 256u, 256, 0, stream>>>(entries, n);
+    cub::DeviceMergeSort::SortKeys(workspace, workspace_bytes, entries, (int)n, ByBedOrder{contig_rank, n_contigs}, stream);
 }
 
 }  // namespace rtjx
