@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Generates tests/golden/kat/: small BAMs that exercise what the reference's own fixtures do not
+(S/H/P/=/X/B ops, adjacent and trailing N, odd XS tags, multi-contig naming, anchor OR across reads,
+intron-length bounds, unmapped-flagged reads, records straddling BGZF blocks, region queries) and the
+outputs of the UNMODIFIED reference (oracle/_ref/regtools_ref, built from /root/reference by
+oracle/Makefile) on them.  Run in the dev container only; the results are committed.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bamio  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref", "regtools_ref")
+BAMGEN = os.path.join(ROOT, "tools", "bamgen")
+OUT = os.path.join(HERE, "kat")
+
+XSP, XSM = b"XSA+", b"XSA-"
+CONTIGS = [("1", 30_000_000), ("10", 20_000_000), ("2", 25_000_000)]
+
+# (tid, pos, cigar, flag, mapq, aux) — SURVEY.md §8a KAT table and more
+KAT = [
+    (0, 1000, "50M100N50M", 0, 60, XSP), (0, 1000, "10S40M100N50M", 0, 0, XSP),
+    (0, 1000, "5H50M100N50M5H", 0, 60, XSP), (0, 1000, "20M2X28M100N50M", 0, 60, XSP),
+    (0, 1000, "20=30M100N25=25M", 0, 60, XSP), (0, 1000, "50M100N20M1I29M", 0, 60, XSP),
+    (0, 1000, "50M100N20M3D30M", 0, 60, XSP),
+    (0, 2000, "50M100N200N50M", 0, 60, XSP), (0, 3000, "50M100N30M200N20M", 16, 60, XSM),
+    (0, 4000, "50M100N", 0, 60, XSP), (0, 5000, "50M69N50M", 0, 60, XSP), (0, 5500, "50M70N50M", 0, 60, XSP),
+    (0, 6000, "7M100N50M", 0, 60, XSP), (0, 6000, "50M100N7M", 0, 60, XSP),
+    (0, 6957, "50M100N7M", 0, 60, XSP), (0, 7000, "7M100N50M", 0, 60, XSP),
+    (0, 8000, "50M100N50M", 0, 60, b"XSA."), (0, 8000, "50M100N50M", 0, 60, b""),
+    (0, 8500, "50M100N50M", 0, 60, b"XSC\x2b"), (0, 8600, "50M100N50M", 0, 60, b"NHC\x01XSA-"),
+    (0, 8700, "50M100N50M", 0, 60, b"XSZabc\0XSA+"), (0, 8800, "50M100N50M", 0, 60, b"ZZBc\x03\0\0\0\x01\x02\x03XSA+"),
+    (0, 9500, "50M3P100N50M", 0, 60, XSP), (0, 10000, "50M100N50M", 4, 0, XSP),
+    (0, 10000, "50M100N50M", 256 | 512 | 1024 | 2048, 0, XSP),
+    (0, 11000, "50M500001N50M", 0, 60, XSP), (0, 11000, "50M500000N50M", 0, 60, XSP),
+    (0, 12000, "30M5S", 0, 60, b""), (0, 12000, "100M", 0, 60, b""), (0, 12100, "", 4, 0, b""),
+    (0, 13000, "10M80N10M80N10M80N10M80N10M80N10M80N10M80N10M80N10M", 99, 60, XSM),
+    (0, 14000, "25M100N25M", 99, 60, b""), (0, 14000, "25M100N25M", 147, 60, b""),
+    (0, 14000, "25M100N25M", 83, 60, b""), (0, 14000, "25M100N25M", 163, 60, b""),
+    (0, 14000, "25M100N25M", 65, 60, b""), (0, 14000, "25M100N25M", 177, 60, b""),
+    (1, 100, "50M100N50M", 0, 60, XSP), (1, 200, "50M100N50M", 0, 60, XSM),
+    (2, 100, "50M100N50M", 0, 60, XSP), (2, 5_000_000, "40M3000N60M", 16, 3, XSM),
+]
+
+
+def build():
+    os.makedirs(OUT, exist_ok=True)
+    # kat.bam: tiny BGZF blocks so records straddle block boundaries
+    recs = [bamio.record(t, p, c, f, q, a, name=b"k%03d" % i) for i, (t, p, c, f, q, a) in enumerate(KAT)]
+    bam = os.path.join(OUT, "kat.bam")
+    bamio.write_bam(bam, CONTIGS, recs, block_size=300)
+    subprocess.check_call([BAMGEN, "index", bam])
+    # synth.bam: generator output (three contigs, ~6k reads), normal block size
+    syn = os.path.join(OUT, "synth.bam")
+    subprocess.check_call([BAMGEN, "gen", "--out", syn, "--config", "tiny", "--reads", "6000", "--seed", "99", "--threads", "2"],
+                          stdout=subprocess.DEVNULL)
+    runs = {
+        "kat": [["-s", "XS"], ["-s", "XS", "-a", "0"], ["-s", "RF"], ["-s", "FR", "-a", "0"], ["-s", "XS", "-t", "NH"],
+                ["-s", "XS", "-r", "1:5000-6200"], ["-s", "XS", "-r", "10"], ["-s", "XS", "-r", "2:5,000,050-5,000,060", "-a", "0"],
+                ["-s", "XS", "-m", "0", "-a", "0", "-M", "4294967295"]],
+        "synth": [["-s", "XS"], ["-s", "RF", "-a", "20"], ["-s", "FR"], ["-s", "XS", "-r", "10:500000-900000"],
+                  ["-s", "XS", "-r", "2"], ["-s", "XS", "-m", "100", "-M", "5000", "-a", "1"]],
+    }
+    manifest = []
+    for stem, arglists in runs.items():
+        for i, args in enumerate(arglists):
+            out = os.path.join(OUT, f"{stem}.{i}.bed")
+            p = subprocess.run([REF, "junctions", "extract"] + args + [os.path.join(OUT, stem + ".bam")],
+                               capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr
+            open(out, "w").write(p.stdout)
+            manifest.append(f"{stem}.bam\t{stem}.{i}.bed\t{' '.join(args)}")
+    # second caller: the 8-arg ctor (min_intron := min_anchor quirk, unfiltered get_all_junctions)
+    for i, (region, anchor) in enumerate([("1:5000-6200", 8), ("1:900-1300", 8), ("2", 8)]):
+        out = os.path.join(OUT, f"kat.ctor{i}.tsv")
+        p = subprocess.run([REF, "ctor", os.path.join(OUT, "kat.bam"), region, "0", "XS", str(anchor), "70", "500000"],
+                           capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        open(out, "w").write(p.stdout)
+        manifest.append(f"kat.bam\tkat.ctor{i}.tsv\tctor {region} 0 XS {anchor} 70 500000")
+    open(os.path.join(OUT, "MANIFEST.tsv"), "w").write("\n".join(manifest) + "\n")
+    print(f"wrote {len(manifest)} golden outputs to {OUT}")
+
+
+if __name__ == "__main__":
+    if not os.path.exists(REF):
+        sys.exit("oracle/_ref/regtools_ref missing: run `make -C oracle ref` in the dev container first")
+    build()

@@ -225,3 +225,127 @@ def test_exit_codes(hcc_bam, tmp_path):
     assert rt.junctions_extract(["extract", "-s", "XS", "-o", out, "does_not_exist.bam"]) == 1
     assert rt.junctions_extract(["extract", "-o", out]) == 1
     assert rt.junctions_extract(["extract", "-h"]) == 0
+
+
+def _manifest(golden_dir):
+    rows = []
+    for line in open(os.path.join(golden_dir, "kat", "MANIFEST.tsv")):
+        bam, out, args = line.rstrip("\n").split("\t")
+        rows.append((bam, out, args.split()))
+    return rows
+
+
+def test_kat_goldens_from_the_reference(golden_dir, tmp_path):
+    """Outputs of the unmodified reference on tests/golden/kat (make_golden.py): every op code, odd XS tags,
+    multi-contig naming, records straddling tiny BGZF blocks, -r / -t / -a / -m / -M."""
+    rt = _rt()
+    n = 0
+    for bam, out, args in _manifest(golden_dir):
+        if args[0] == "ctor":
+            continue
+        dst = tmp_path / out
+        rc = rt.junctions_extract(["extract"] + args + ["-o", str(dst), os.path.join(golden_dir, "kat", bam)])
+        assert rc == 0
+        assert dst.read_text() == open(os.path.join(golden_dir, "kat", out)).read(), (bam, args)
+        n += 1
+    assert n >= 15
+
+
+def test_ctor_goldens_second_caller(golden_dir):
+    """cis_splice_effects_identifier.cc:288-290: 8-arg ctor (min_intron := min_anchor) + unfiltered get_all_junctions."""
+    rt = _rt()
+    for bam, out, args in _manifest(golden_dir):
+        if args[0] != "ctor":
+            continue
+        _, region, strandness, tag, anchor, min_intron, max_intron = args
+        ex = rt.JunctionsExtractor.from_region(os.path.join(golden_dir, "kat", bam), region, int(strandness), tag,
+                                               int(anchor), int(min_intron), int(max_intron))
+        ex.identify_junctions_from_BAM()
+        lines = "".join(f"{j.chrom}\t{j.thick_start}\t{j.thick_end}\t{j.name}\t{j.read_count}\t{j.strand}\t{j.start}\t{j.end}"
+                        f"\t{int(j.has_left_min_anchor)}\t{int(j.has_right_min_anchor)}\n" for j in ex.get_all_junctions())
+        ex.close()
+        assert lines == open(os.path.join(golden_dir, "kat", out)).read(), args
+
+
+def test_cis_splice_effects_junction_goldens(golden_dir):
+    """The junction the reference's `cis-splice-effects identify -j` goldens hold for test_hcc1395.2.bam."""
+    rt = _rt()
+    bam = os.path.join(golden_dir, "hcc1395", "test_hcc1395.2.bam")
+    for strandness, name in ((0, "expected-cis-splice-effects-identify-default-junctions.out"),
+                             (1, "expected-cis-splice-effects-identify-default-stranded-junctions.out")):
+        want = open(os.path.join(golden_dir, "hcc1395", name)).read().split("\t")
+        ex = rt.JunctionsExtractor.from_region(bam, ".", strandness, "XS", 8, 70, 500000)
+        ex.identify_junctions_from_BAM()
+        js = ex.get_all_junctions()
+        ex.close()
+        hit = [j for j in js if str(j.thick_start) == want[1] and str(j.thick_end) == want[2]]
+        assert hit and str(hit[0].read_count) == want[4] and hit[0].bed12().split("\t")[10:] == want[10:]
+
+
+def test_cli_binary(golden_dir, hcc_bam, tmp_path):
+    """The `regtools` executable (C++ shim over the C ABI): same goldens, same exit codes."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(golden_dir), "..", "regtools_b200", "regtools")
+    out = tmp_path / "cli.bed"
+    p = subprocess.run([exe, "junctions", "extract", "-s", "XS", "-o", str(out), hcc_bam], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert "Program:\tregtools" in p.stderr and "Minimum junction anchor length: 8" in p.stderr
+    assert out.read_text() == open(os.path.join(golden_dir, "hcc1395", "expected-a.out")).read()
+    p = subprocess.run([exe, "junctions", "extract", "-s", "RF", "-a", "30", hcc_bam], capture_output=True, text=True)
+    assert p.returncode == 0 and p.stdout == open(os.path.join(golden_dir, "hcc1395", "expected-stranded-a30.out")).read()
+    assert subprocess.run([exe, "junctions", "extract", "-s", "XS", "nope.bam"], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "junctions", "extract", hcc_bam], capture_output=True).returncode == 1
+    assert subprocess.run([exe, "junctions", "extract", "-h"], capture_output=True).returncode == 0
+
+
+def test_contig_sharded_handles_merge_to_whole_file(golden_dir):
+    """Two shard handles (what two ranks run) + import on a host-only handle == single whole-file run."""
+    rt = _rt()
+    bam = os.path.join(golden_dir, "kat", "synth.bam")
+    whole = rt.JunctionsExtractor(bam, ".", 0)
+    whole.identify_junctions_from_BAM()
+    want = io.StringIO(); whole.print_all_junctions(want)
+    names = whole.contig_names()
+    whole.close()
+    merged = rt.JunctionsExtractor(bam, device=-1)
+    merged.set_contigs(names)
+    total = 0
+    for r in (1, 0):
+        ex = rt.JunctionsExtractor(bam, ".", 0, shard_rank=r, shard_world=2)
+        ex.identify_junctions_from_BAM()
+        t = ex.junction_table()
+        total += ex.stats()["reads"]
+        ex.close()
+        merged.import_table(t)
+    got = io.StringIO(); merged.print_all_junctions(got)
+    assert got.getvalue() == want.getvalue()
+    assert total == 6000
+
+
+def test_large_generated_bam_property_checks(tmp_path):
+    """Size-independent properties at a larger size: counts add up, output sorted, names a permutation,
+    idempotent re-run, and equality with the oracle."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bam = str(tmp_path / "big.bam")
+    subprocess.check_call([os.path.join(root, "tools", "bamgen"), "gen", "--out", bam, "--config", "tiny", "--reads", "2000000",
+                           "--seed", "77"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    rt = _rt()
+    ex = rt.JunctionsExtractor(bam, ".", 0)
+    ex.identify_junctions_from_BAM()
+    t1 = ex.junction_table()
+    st = ex.stats()
+    ex.clear()
+    ex.identify_junctions_from_BAM()
+    t2 = ex.junction_table()
+    ex.close()
+    assert np.array_equal(t1, t2)
+    assert st["reads"] == 2000000
+    assert sorted(t1["name_index"].tolist()) == list(range(1, len(t1) + 1))
+    key = list(zip(t1["tid"].tolist(), t1["thick_start"].tolist(), t1["thick_end"].tolist(), t1["name_index"].tolist()))
+    order = {0: 0, 1: 1, 2: 2}                       # contigs "1" < "10" < "2" are already in tid order
+    assert key == sorted(key, key=lambda k: (order[k[0]], k[1], k[2], k[3]))
+    o = Oracle(8, 70, 500000, 0)
+    o.extract_bam(bam)
+    tables_equal(t1, o.table())
+    assert int(t1["read_count"].sum()) == int(o.table()["read_count"].sum())

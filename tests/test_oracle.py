@@ -1,0 +1,121 @@
+"""CPU: the oracle (oracle/jx_oracle.c) is pinned to the reference's goldens, its gtest known answers and
+to outputs of the unmodified reference on the committed KAT fixtures (tests/golden/kat, make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from oracle_py import Oracle, ref_available, ref_extract
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+HCC = os.path.join(GOLD, "hcc1395", "test_hcc1395.bam")
+MODES = {"XS": 0, "RF": 1, "FR": 2}
+
+
+def run_oracle(bam, args):
+    a, m, M, s, r, t = 8, 70, 500000, 0, ".", "XS"
+    it = iter(args)
+    for k in it:
+        v = next(it)
+        if k == "-a": a = int(v)
+        elif k == "-m": m = int(v)
+        elif k == "-M": M = int(v)
+        elif k == "-s": s = MODES[v]
+        elif k == "-r": r = v
+        elif k == "-t": t = v
+    o = Oracle(a & 0xFFFFFFFF, m & 0xFFFFFFFF, M & 0xFFFFFFFF, s, t)
+    o.extract_bam(bam, r)
+    return o
+
+
+@pytest.mark.parametrize("args,golden", [
+    (["-s", "XS"], "expected-a.out"), (["-s", "XS", "-a", "30"], "expected-a30.out"),
+    (["-s", "RF"], "expected-stranded-a.out"), (["-s", "RF", "-a", "30"], "expected-stranded-a30.out"),
+    (["-s", "XS", "-m", "8039", "-M", "8039"], "expected-i8039-I8039.out"),
+    (["-s", "XS", "-r", "1:22405013-22405020"], "expected-r1:22405013-22405020.out")])
+def test_oracle_reference_goldens(args, golden):
+    assert run_oracle(HCC, args).bed12() == open(os.path.join(GOLD, "hcc1395", golden)).read()
+
+
+def manifest():
+    rows = []
+    for line in open(os.path.join(GOLD, "kat", "MANIFEST.tsv")):
+        bam, out, args = line.rstrip("\n").split("\t")
+        rows.append((bam, out, args.split()))
+    return rows
+
+
+@pytest.mark.parametrize("bam,out,args", [m for m in manifest() if not m[2][0] == "ctor"])
+def test_oracle_matches_reference_outputs_on_kat(bam, out, args):
+    assert run_oracle(os.path.join(GOLD, "kat", bam), args).bed12() == open(os.path.join(GOLD, "kat", out)).read()
+
+
+@pytest.mark.parametrize("bam,out,args", [m for m in manifest() if m[2][0] == "ctor"])
+def test_oracle_ctor_quirk(bam, out, args):
+    """8-arg ctor: min_intron := min_anchor, get_all_junctions unfiltered (junctions_extractor.h:199-205, .cc:238-246)."""
+    _, region, strandness, tag, anchor, _min_intron, max_intron = args
+    o = Oracle(int(anchor), int(anchor), int(max_intron), int(strandness), tag)
+    o.extract_bam(os.path.join(GOLD, "kat", bam), region)
+    lines = []
+    for j in o.table():
+        lines.append("\t".join(map(str, [o.l.jxo_contig(o.h, int(j["tid"])).decode(), j["thick_start"], j["thick_end"],
+                                         "JUNC%08d" % j["name_index"], j["read_count"], chr(j["strand"]), j["start"], j["end"],
+                                         j["left_ok"], j["right_ok"]])) + "\n")
+    assert "".join(lines) == open(os.path.join(GOLD, "kat", out)).read()
+
+
+def test_oracle_gtest_add_junction():
+    """tests/lib/junctions/test_junctions_extractor.cc:102-141."""
+    o = Oracle(contigs=["chr1"])
+    for a in [(10000, 10200, 9900, 10300, "+"), (10000, 10200, 9500, 10200, "+"), (10000, 10200, 9950, 10700, "+"),
+              (8000, 8500, 7000, 10000, "+"), (8000, 8500, 7000, 10000, "-")]:
+        o.add(0, *a)
+    assert o.bed12() == ("chr1\t7000\t10000\tJUNC00000002\t1\t+\t7000\t10000\t255,0,0\t2\t1000,1500\t0,1500\n"
+                         "chr1\t7000\t10000\tJUNC00000003\t1\t-\t7000\t10000\t255,0,0\t2\t1000,1500\t0,1500\n"
+                         "chr1\t9500\t10700\tJUNC00000001\t3\t+\t9500\t10700\t255,0,0\t2\t500,500\t0,700\n")
+
+
+def test_closed_form_equals_state_machine():
+    """SURVEY Appendix A.2 (what the CUDA kernel computes) vs the literal state machine, on random CIGARs."""
+    rng = np.random.default_rng(3)
+    REFC, BRK, ANC = {0, 7, 2, 8, 3}, {3, 2, 8, 1, 4}, {0, 7}
+    for _ in range(3000):
+        n = int(rng.integers(2, 12))
+        ops = [(int(rng.integers(0, 16)), int(rng.integers(0, 300))) for _ in range(n)]
+        words = np.array([l << 4 | o for o, l in ops], np.uint32)
+        pos = int(rng.integers(0, 1 << 20))
+        o = Oracle(0, 0, 0xFFFFFFFF, 0, contigs=["c"])
+        o.record_candidates()
+        o.batch(np.array([0], np.int32), np.array([pos], np.int32), np.array([ord("+")], np.uint32),
+                np.array([0, n], np.uint32), words)
+        got = [(int(c["start"]), int(c["end"]), int(c["thick_start"]), int(c["thick_end"]), int(c["k"])) for c in o.candidates()]
+        want = []
+        for k, (op, ln) in enumerate(ops):
+            if op != 3:
+                continue
+            start = pos + sum(l for (p, l) in ops[:k] if p in REFC)
+            left = 0
+            for p, l in reversed(ops[:k]):
+                if p in BRK: break
+                if p in ANC: left += l
+            right = 0
+            for p, l in ops[k + 1:]:
+                if p in BRK: break
+                if p in ANC: right += l
+            m = 0xFFFFFFFF
+            want.append((start & m, (start + ln) & m, (start - left) & m, (start + ln + right) & m, k))
+        assert got == want, (ops, got, want)
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref/regtools_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("args", [["-s", "XS"], ["-s", "RF", "-a", "3"], ["-s", "XS", "-r", "10:1-700000"]])
+def test_oracle_vs_live_reference_on_fresh_bam(args, tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bam = str(tmp_path / "fresh.bam")
+    subprocess.check_call([os.path.join(root, "tools", "bamgen"), "gen", "--out", bam, "--config", "tiny", "--reads", "30000",
+                           "--seed", "2024", "--threads", "2"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    rc, out = ref_extract(bam, args)
+    assert rc == 0
+    assert run_oracle(bam, args).bed12() == out
