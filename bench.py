@@ -330,7 +330,7 @@ def main():
                 "host_inflate_cpu_s": feeder["host_inflate_s"], "host_parse_s": feeder["host_parse_s"],
                 "feeder_wait_s": feeder["host_wait_s"]},
         "gpu_launches": int(round(launches_resident * args.steps)),
-        "roofline": {"bound": "hbm", "kernel": "cigar_scan_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "cigar_scan_small_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
