@@ -172,6 +172,11 @@ int         rtjx_clear(rtjx_t* h);
 int         rtjx_load_batch(rtjx_t* h, uint64_t* n_reads, uint64_t* n_ops, int32_t* tid, int32_t* pos,
                             uint32_t* meta, uint32_t* cig_off, uint32_t* cigar);
 
+/* Device BGZF inflate of the handle's BAM, from the first block, at most max_blocks blocks (0 = all):
+ * the inflated byte stream is copied to `out` (host, cap bytes); *out_len receives its length.
+ * Test hook for the inflate kernel (replaces bgzf.c:292-316 for whole-file runs). */
+int         rtjx_inflate_file(rtjx_t* h, uint64_t max_blocks, void* out, uint64_t cap, uint64_t* out_len);
+
 const char* rtjx_last_error(const rtjx_t* h);
 const char* rtjx_strerror(int status);
 const char* rtjx_version(void);

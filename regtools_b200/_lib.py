@@ -99,6 +99,7 @@ SIGNATURES = {
     "rtjx_clear": (C.c_int, [C.c_void_p]),
     "rtjx_load_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rtjx_inflate_file": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rtjx_last_error": (C.c_char_p, [C.c_void_p]),
     "rtjx_strerror": (C.c_char_p, [C.c_int]),
     "rtjx_version": (C.c_char_p, []),

@@ -708,6 +708,21 @@ bool feed_alignments(const BamFile& bam, const BaiIndex& idx, const IterSpec& sp
     return true;
 }
 
+uint64_t scan_bgzf_blocks(const BamFile& bam, uint64_t coff, uint64_t end_coff, size_t max_blocks, uint64_t max_comp_bytes,
+                          std::vector<BgzfBlockInfo>* out, bool* stop) {
+    *stop = false;
+    uint64_t taken = 0;
+    while (out->size() < max_blocks && taken < max_comp_bytes) {
+        if (coff >= end_coff) { *stop = true; break; }
+        BlockDesc d;
+        int rc = peek_block(bam.data(), bam.size(), coff, &d);
+        if (rc != 0 || d.isize == 0 || d.isize > 0x10000) { *stop = true; break; }
+        out->push_back(BgzfBlockInfo{d.coff, d.csize, d.isize});
+        coff = d.coff + d.csize; taken += d.csize;
+    }
+    return coff;
+}
+
 std::vector<int32_t> plan_contig_shards(const BamFile& bam, const BaiIndex& idx, int world) {
     const size_t n = bam.header().names.size();
     std::vector<int32_t> assign(n, 0);

@@ -106,6 +106,13 @@ struct FeederOptions {
 bool feed_alignments(const BamFile& bam, const BaiIndex& idx, const IterSpec& spec, const FeederOptions& opt,
                      BatchSink* sink, FeederStats* stats, std::string* err);
 
+// Walks BGZF block headers from compressed offset `coff` (bgzf.c:348-355,525-546): appends one descriptor per
+// block until `max_blocks`, `max_comp_bytes`, the end of file, an empty (ISIZE 0) block or a malformed header.
+// Returns the compressed offset after the last block taken; *stop is set when the stream ends there.
+struct BgzfBlockInfo { uint64_t coff; uint32_t csize, isize; };
+uint64_t scan_bgzf_blocks(const BamFile& bam, uint64_t coff, uint64_t end_coff, size_t max_blocks, uint64_t max_comp_bytes,
+                          std::vector<BgzfBlockInfo>* out, bool* stop);
+
 // LPT assignment of contigs to shards by compressed byte span.
 std::vector<int32_t> plan_contig_shards(const BamFile& bam, const BaiIndex& idx, int world);
 

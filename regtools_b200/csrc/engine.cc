@@ -394,6 +394,50 @@ int Engine::run() {
     return RTJX_OK;
 }
 
+// ---- device inflate test hook ----------------------------------------------------------------------
+int Engine::inflate_file(uint64_t max_blocks, void* out, uint64_t cap, uint64_t* out_len) {
+    if (!out_len) return fail(RTJX_E_ARG, "out_len must not be NULL");
+    int rc = ensure_device();
+    if (rc) return rc;
+    BamFile bam; std::string err;
+    if (bam_path_.empty() || !bam.open(bam_path_, &err)) return fail(RTJX_E_OPEN_BAM, "Unable to open BAM/SAM file.\n\n");
+    std::vector<BgzfBlockInfo> blocks; bool stop = false;
+    scan_bgzf_blocks(bam, 0, bam.size(), max_blocks ? (size_t)max_blocks : (size_t)-1, UINT64_MAX, &blocks, &stop);
+    std::vector<BgzfBlockDesc> desc(blocks.size());
+    uint64_t in_total = 0, out_total = 0;
+    for (size_t i = 0; i < blocks.size(); ++i) {
+        desc[i].in_off = (uint32_t)in_total; desc[i].in_len = blocks[i].csize - 26;
+        desc[i].out_off = (uint32_t)out_total; desc[i].out_len = blocks[i].isize;
+        in_total += (desc[i].in_len + 3u) & ~3u; out_total += blocks[i].isize;
+    }
+    if (in_total > 0xfff00000ull || out_total > 0xfff00000ull) return fail(RTJX_E_ARG, "file too large for the single-shot inflate hook");
+    *out_len = out_total;
+    if (out_total > cap || !out) return blocks.empty() ? RTJX_OK : (out ? fail(RTJX_E_ARG, "output buffer too small") : RTJX_OK);
+    std::vector<uint8_t> packed(in_total + 16, 0);
+    for (size_t i = 0; i < blocks.size(); ++i) memcpy(packed.data() + desc[i].in_off, bam.data() + blocks[i].coff + 18, desc[i].in_len);
+    uint8_t *d_in = nullptr, *d_out = nullptr; BgzfBlockDesc* d_desc = nullptr; uint32_t* d_status = nullptr;
+    CK(cudaMalloc(&d_in, packed.size())); CK(cudaMalloc(&d_out, out_total + 16));
+    CK(cudaMalloc(&d_desc, desc.size() * sizeof(BgzfBlockDesc) + 16)); CK(cudaMalloc(&d_status, desc.size() * 4 + 16));
+    CK(cudaMemcpyAsync(d_in, packed.data(), packed.size(), cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(d_desc, desc.data(), desc.size() * sizeof(BgzfBlockDesc), cudaMemcpyHostToDevice, stream_));
+    cudaEvent_t ea = get_event(), eb = get_event();
+    cudaEventRecord(ea, stream_);
+    launch_bgzf_inflate(d_in, d_desc, (uint32_t)desc.size(), d_out, d_status, stream_);
+    cudaEventRecord(eb, stream_);
+    std::vector<uint32_t> status(desc.size());
+    CK(cudaMemcpyAsync(status.data(), d_status, desc.size() * 4, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(out, d_out, out_total, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    CK(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, ea, eb); stats_.inflate_kernel_ms += ms;
+    ev_pool_.push_back(ea); ev_pool_.push_back(eb);
+    stats_.kernel_launches++; stats_.bgzf_blocks += blocks.size(); stats_.compressed_bytes += in_total; stats_.inflated_bytes += out_total;
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_desc); cudaFree(d_status);
+    for (size_t i = 0; i < status.size(); ++i)
+        if (status[i]) return fail(RTJX_E_IO, "device inflate failed on BGZF block " + std::to_string(i) + " (code " + std::to_string(status[i]) + ")");
+    return RTJX_OK;
+}
+
 // ---- feeder-only: SoA arrays for kernel-level tests and benches ----------------------------------
 struct Engine::LoadedBatch {
     std::vector<int32_t> tid, pos; std::vector<uint32_t> meta, off, cigar;

@@ -28,6 +28,7 @@ public:
     int write_bed12(int fd);
     int import(const rtjx_junction* j, size_t n);
     int clear();
+    int inflate_file(uint64_t max_blocks, void* out, uint64_t cap, uint64_t* out_len);
     int load_batch(uint64_t* n_reads, uint64_t* n_ops, int32_t* tid, int32_t* pos, uint32_t* meta,
                    uint32_t* cig_off, uint32_t* cigar);
 

@@ -1,0 +1,308 @@
+// regtools_b200/csrc/inflate.cu — BGZF/DEFLATE decompression on the device.
+//
+// Replaces, for whole-file runs, the per-block zlib inflate the reference performs on one host
+// thread (/root/reference/src/utils/htslib/bgzf.c:292-316 inflate_block, :421-546 read_block).
+// BGZF blocks are independent raw-DEFLATE streams of at most 64 KiB output, so the unit of
+// parallelism is the block: one warp per block.  Lane 0 decodes Huffman symbols (the inherently
+// serial part) 32 at a time into a shared-memory queue using 10-bit/9-bit lookup tables built per
+// DEFLATE block in shared memory; all 32 lanes then place the literals (one coalesced byte store
+// per lane) and perform the LZ77 copies cooperatively.  CRC32 is not checked (the reference does
+// not check it either).  Any malformed stream sets the block's status to non-zero; the host then
+// falls back to its own inflate for the whole run.
+#include "jx_device.cuh"
+
+namespace rtjx {
+
+constexpr int INF_WARPS   = 8;                   // warps (= BGZF blocks in flight) per CTA
+constexpr int LIT_BITS    = 10;
+constexpr int DIST_BITS   = 9;
+
+struct InflateWarpSmem {
+    uint16_t lit_fast[1 << LIT_BITS];            // sym << 4 | len  (0 = needs the slow path)
+    uint16_t dist_fast[1 << DIST_BITS];
+    uint16_t lit_count[16], dist_count[16];      // canonical decode (slow path): codes per length
+    uint16_t lit_sym[288], dist_sym[32];         // symbols sorted by (length, symbol)
+    uint8_t  lens[320];                          // code lengths of the current block (lit + dist)
+    uint32_t q[32];                              // decoded symbols: len << 16 | dist  or  0x80000000 | byte... see below
+};
+
+__constant__ uint16_t c_len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+__constant__ uint8_t c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+__constant__ uint16_t c_dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+__constant__ uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// LSB-first bit reader over global memory, 32-bit aligned refills (lane 0 only).
+struct BitReader {
+    const uint32_t* p;      // next aligned word
+    uint64_t bb;            // bit buffer
+    int nb;                 // valid bits
+    __device__ __forceinline__ void init(const uint8_t* src) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+        p = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const int mis = (int)(a & 3);
+        bb = (uint64_t)__ldg(p++) >> (8 * mis);
+        nb = 32 - 8 * mis;
+    }
+    __device__ __forceinline__ void need(int n) {         // n <= 32
+        if (nb < n) { bb |= (uint64_t)__ldg(p++) << nb; nb += 32; }
+    }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)bb & ((1u << n) - 1u); }
+    __device__ __forceinline__ void drop(int n) { bb >>= n; nb -= n; }
+    __device__ __forceinline__ uint32_t get(int n) { need(n); uint32_t v = peek(n); drop(n); return v; }
+    // byte position (relative to `base`) of the next unread byte after discarding partial-byte bits
+    __device__ __forceinline__ const uint8_t* byte_ptr() const {
+        return reinterpret_cast<const uint8_t*>(p) - (nb >> 3);
+    }
+};
+
+// canonical-code slow decode (one bit at a time), used for codes longer than the fast table
+__device__ __forceinline__ int slow_decode(BitReader& br, const uint16_t* count, const uint16_t* sym) {
+    int code = 0, first = 0, index = 0;
+    for (int len = 1; len <= 15; ++len) {
+        code |= (int)br.get(1);
+        const int c = count[len];
+        if (code - c < first) return sym[index + (code - first)];
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+// Builds count[]/sym[] (canonical order) and the fast table for `n` symbols with lengths `len[]`.
+// Executed by the whole warp; returns false (all lanes) on an over-subscribed code.
+__device__ bool build_tables(const uint8_t* len, int n, uint16_t* count, uint16_t* sym, uint16_t* fast, int fast_bits,
+                             uint32_t lane) {
+    for (int i = lane; i < 16; i += 32) count[i] = 0;
+    for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = 0; i < n; ++i) count[len[i]]++;
+    }
+    __syncwarp();
+    // offsets and over-subscription check (every lane computes the same small loop)
+    uint16_t offs[16];
+    int left = 1;
+    bool ok = true;
+    offs[1] = 0;
+    for (int l = 1; l <= 15; ++l) {
+        left <<= 1; left -= count[l];
+        if (left < 0) ok = false;
+        if (l < 15) offs[l + 1] = offs[l] + count[l];
+    }
+    if (!ok) return false;
+    // first canonical code of each length
+    uint32_t next_code[16];
+    {
+        uint32_t code = 0;
+        next_code[0] = 0;
+        for (int l = 1; l <= 15; ++l) { code = (code + (l > 1 ? count[l - 1] : 0)) << 1; next_code[l] = code; }
+    }
+    if (lane == 0) {
+        // symbol table in canonical order + fast-table fill (serial over symbols: <= 288)
+        uint16_t o[16];
+        for (int l = 0; l < 16; ++l) o[l] = offs[l < 1 ? 1 : l];
+        for (int s = 0; s < n; ++s) {
+            const int l = len[s];
+            if (!l) continue;
+            sym[o[l]++] = (uint16_t)s;
+            const uint32_t code = next_code[l]++;
+            if (l <= fast_bits) {
+                const uint32_t rev = __brev(code) >> (32 - l);                 // LSB-first bit order
+                const uint16_t e = (uint16_t)(s << 4 | l);
+                for (uint32_t k = rev; k < (1u << fast_bits); k += 1u << l) fast[k] = e;
+            }
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+struct BgzfBlock {   // same layout as BgzfBlockDesc (jx_device.cuh)
+    uint32_t in_off;     // offset of the raw deflate payload inside the compressed buffer
+    uint32_t in_len;
+    uint32_t out_off;    // offset inside the inflated buffer
+    uint32_t out_len;    // ISIZE
+};
+
+__global__ void __launch_bounds__(INF_WARPS * 32)
+bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, uint32_t n_blocks,
+                    uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
+    __shared__ InflateWarpSmem smem[INF_WARPS];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x * INF_WARPS + wib;
+    if (b >= n_blocks) return;
+    InflateWarpSmem& sm = smem[wib];
+    const BgzfBlock blk = blocks[b];
+    uint8_t* dst = out + blk.out_off;
+    const uint32_t cap = blk.out_len;
+    uint32_t opos = 0;                // bytes produced so far (uniform across the warp)
+    uint32_t err = 0;
+
+    BitReader br;                     // only lane 0's copy is meaningful
+    if (lane == 0) br.init(comp + blk.in_off);
+
+    for (bool last = false; !last && !err;) {
+        // ---- block header (lane 0), broadcast
+        uint32_t hdr = 0;
+        if (lane == 0) hdr = br.get(3);
+        hdr = __shfl_sync(0xffffffffu, hdr, 0);
+        last = hdr & 1u;
+        const uint32_t btype = hdr >> 1;
+        if (btype == 0) {
+            // ---- stored block: LEN, NLEN, raw bytes
+            uint32_t len = 0; const uint8_t* src = nullptr;
+            if (lane == 0) {
+                br.drop(br.nb & 7);                                   // to the next byte boundary
+                const uint32_t l = br.get(16), nl = br.get(16);
+                if ((l ^ nl) != 0xffffu) len = 0xffffffffu;
+                else { len = l; src = br.byte_ptr(); }
+            }
+            len = __shfl_sync(0xffffffffu, len, 0);
+            if (len == 0xffffffffu || opos + len > cap) { err = 2; break; }
+            const unsigned long long s64 = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(src), 0);
+            src = reinterpret_cast<const uint8_t*>((uintptr_t)s64);
+            for (uint32_t i = lane; i < len; i += 32) dst[opos + i] = __ldg(src + i);
+            opos += len;
+            if (lane == 0) br.init(src + len);
+            continue;
+        }
+        if (btype == 3) { err = 3; break; }
+        // ---- code lengths
+        int hlit = 288, hdist = 30;
+        if (btype == 1) {
+            for (int i = lane; i < 288; i += 32) sm.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+            for (int i = lane; i < 30; i += 32) sm.lens[288 + i] = 5;
+            __syncwarp();
+        } else {
+            uint32_t e2 = 0;
+            if (lane == 0) {
+                hlit = (int)br.get(5) + 257; hdist = (int)br.get(5) + 1;
+                const int hclen = (int)br.get(4) + 4;
+                if (hlit > 286 || hdist > 30) e2 = 4;
+                uint8_t cl[19];
+                for (int i = 0; i < 19; ++i) cl[i] = 0;
+                for (int i = 0; i < hclen; ++i) cl[c_clen_order[i]] = (uint8_t)br.get(3);
+                // canonical tables of the code-length code (7-bit max) in registers/local
+                uint16_t ccount[8], csym[19];
+                for (int i = 0; i < 8; ++i) ccount[i] = 0;
+                for (int i = 0; i < 19; ++i) ccount[cl[i]]++;
+                uint16_t coffs[8]; coffs[1] = 0;
+                for (int l = 1; l < 7; ++l) coffs[l + 1] = coffs[l] + ccount[l];
+                for (int i = 0; i < 19; ++i) if (cl[i]) csym[coffs[cl[i]]++] = (uint16_t)i;
+                ccount[0] = 0;
+                int idx = 0;
+                while (idx < hlit + hdist && !e2) {
+                    // decode one code-length symbol
+                    int code = 0, first = 0, index = 0, symv = -1;
+                    for (int l = 1; l <= 7; ++l) {
+                        code |= (int)br.get(1);
+                        const int c = ccount[l];
+                        if (code - c < first) { symv = csym[index + (code - first)]; break; }
+                        index += c; first += c; first <<= 1; code <<= 1;
+                    }
+                    if (symv < 0) { e2 = 5; break; }
+                    if (symv < 16) sm.lens[idx++] = (uint8_t)symv;
+                    else {
+                        int rep, val = 0;
+                        if (symv == 16) { if (idx == 0) { e2 = 6; break; } val = sm.lens[idx - 1]; rep = 3 + (int)br.get(2); }
+                        else if (symv == 17) rep = 3 + (int)br.get(3);
+                        else rep = 11 + (int)br.get(7);
+                        if (idx + rep > hlit + hdist) { e2 = 7; break; }
+                        while (rep--) sm.lens[idx++] = (uint8_t)val;
+                    }
+                }
+                if (!e2 && sm.lens[256] == 0) e2 = 8;                 // no end-of-block code
+                // move the distance lengths to a fixed place (288..)
+                if (!e2) {
+                    uint8_t tmp[30];
+                    for (int i = 0; i < hdist; ++i) tmp[i] = sm.lens[hlit + i];
+                    for (int i = hlit; i < 288; ++i) sm.lens[i] = 0;
+                    for (int i = 0; i < hdist; ++i) sm.lens[288 + i] = tmp[i];
+                    for (int i = hdist; i < 30; ++i) sm.lens[288 + i] = 0;
+                }
+            }
+            e2 = __shfl_sync(0xffffffffu, e2, 0);
+            if (e2) { err = e2; break; }
+            hlit = 288; hdist = 30;
+            __syncwarp();
+        }
+        if (!build_tables(sm.lens, hlit, sm.lit_count, sm.lit_sym, sm.lit_fast, LIT_BITS, lane)) { err = 9; break; }
+        // an incomplete distance code with a single symbol is legal; over-subscription is not
+        if (!build_tables(sm.lens + 288, hdist, sm.dist_count, sm.dist_sym, sm.dist_fast, DIST_BITS, lane)) { err = 10; break; }
+
+        // ---- symbols, 32 per round
+        for (bool eob = false; !eob && !err;) {
+            uint32_t n = 0, flag = 0;                 // flag: 1 = end of block seen, 2+ = error
+            if (lane == 0) {
+                while (n < 32) {
+                    br.need(32);
+                    int sym;
+                    uint32_t e = sm.lit_fast[br.peek(LIT_BITS)];
+                    if (e) { br.drop(e & 15); sym = (int)(e >> 4); }
+                    else { sym = slow_decode(br, sm.lit_count, sm.lit_sym); if (sym < 0) { flag = 11; break; } }
+                    if (sym < 256) { sm.q[n++] = 0x80000000u | (uint32_t)sym; continue; }
+                    if (sym == 256) { flag = 1; break; }
+                    sym -= 257;
+                    if (sym >= 29) { flag = 12; break; }
+                    br.need(32);
+                    const uint32_t len = c_len_base[sym] + br.get(c_len_extra[sym]);
+                    br.need(32);
+                    int ds;
+                    e = sm.dist_fast[br.peek(DIST_BITS)];
+                    if (e) { br.drop(e & 15); ds = (int)(e >> 4); }
+                    else { ds = slow_decode(br, sm.dist_count, sm.dist_sym); if (ds < 0) { flag = 13; break; } }
+                    if (ds >= 30) { flag = 14; break; }
+                    br.need(32);
+                    const uint32_t dist = c_dist_base[ds] + br.get(c_dist_extra[ds]);
+                    sm.q[n++] = len << 16 | dist;       // len <= 258, dist <= 32768 (stored as dist, 16 bits: 32768 -> 0x8000)
+                }
+            }
+            n = __shfl_sync(0xffffffffu, n, 0);
+            flag = __shfl_sync(0xffffffffu, flag, 0);
+            __syncwarp();
+            if (flag > 1) { err = flag; break; }
+            eob = flag == 1;
+            // ---- place the round: prefix sum of lengths, literals in parallel, matches in order
+            const uint32_t s = lane < n ? sm.q[lane] : 0u;
+            const bool is_lit = (s & 0x80000000u) != 0;
+            const uint32_t mylen = lane < n ? (is_lit ? 1u : (s >> 16)) : 0u;
+            uint32_t x = mylen;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((int)lane >= d) x += y; }
+            const uint32_t total = __shfl_sync(0xffffffffu, x, 31);
+            const uint32_t mypos = opos + x - mylen;
+            if (opos + total > cap) { err = 15; break; }
+            if (lane < n && is_lit) dst[mypos] = (uint8_t)s;
+            uint32_t mm = __ballot_sync(0xffffffffu, lane < n && !is_lit);
+            uint32_t bad = 0;
+            while (mm) {
+                const int j = __ffs(mm) - 1; mm &= mm - 1;
+                const uint32_t sj = __shfl_sync(0xffffffffu, s, j);
+                const uint32_t pj = __shfl_sync(0xffffffffu, mypos, j);
+                const uint32_t len = sj >> 16, dist = sj & 0xffffu;
+                if (dist > pj) { bad = 16; break; }
+                __syncwarp();                                             // earlier stores of this warp are visible
+                const uint8_t* srcp = dst + pj - dist;
+                if (dist >= len) {
+                    for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + k);
+                } else {                                                   // overlapping run: periodic with period dist
+                    for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + (k % dist));
+                }
+            }
+            if (bad) { err = bad; break; }
+            __syncwarp();
+            opos += total;
+        }
+    }
+    if (!err && opos != cap) err = 17;
+    if (lane == 0) status[b] = err;
+}
+
+void launch_bgzf_inflate(const uint8_t* comp, const void* blocks, uint32_t n_blocks, uint8_t* out, uint32_t* status,
+                         cudaStream_t stream) {
+    if (n_blocks == 0) return;
+    const uint32_t grid = (n_blocks + INF_WARPS - 1) / INF_WARPS;
+    bgzf_inflate_kernel<<<grid, INF_WARPS * 32, 0, stream>>>(comp, static_cast<const BgzfBlock*>(blocks), n_blocks, out, status);
+}
+
+}  // namespace rtjx

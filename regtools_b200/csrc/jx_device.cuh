@@ -83,6 +83,11 @@ size_t finalize_sort_workspace_bytes(uint32_t n);
 void launch_finalize_sort(OutJunction* entries, uint32_t n, const uint32_t* contig_rank, uint32_t n_contigs,
                           void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
+// BGZF inflate on the device (inflate.cu).  `blocks` is an array of BgzfBlockDesc in device memory.
+struct BgzfBlockDesc { uint32_t in_off, in_len, out_off, out_len; };
+void launch_bgzf_inflate(const uint8_t* comp, const void* blocks, uint32_t n_blocks, uint8_t* out, uint32_t* status,
+                         cudaStream_t stream);
+
 // counters layout in d_counters (uint32 each)
 enum { CTR_NCAND = 0, CTR_CAND_OVERFLOW = 1, CTR_NUNIQUE = 2, CTR_NSPILL = 3, CTR_NOUT = 4,
        CTR_TOTAL_CAND64 = 6 /* 64-bit, two words */, CTR_COUNT = 8 };

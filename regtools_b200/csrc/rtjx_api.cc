@@ -75,6 +75,10 @@ int rtjx_load_batch(rtjx_t* h, uint64_t* n_reads, uint64_t* n_ops, int32_t* tid,
     GUARD(h, h->e->load_batch(n_reads, n_ops, tid, pos, meta, cig_off, cigar))
 }
 
+int rtjx_inflate_file(rtjx_t* h, uint64_t max_blocks, void* out, uint64_t cap, uint64_t* out_len) {
+    GUARD(h, h->e->inflate_file(max_blocks, out, cap, out_len))
+}
+
 const char* rtjx_contig(rtjx_t* h, int32_t tid) { return h ? h->e->contig(tid) : ""; }
 int32_t rtjx_n_contigs(rtjx_t* h) { return h ? h->e->n_contigs() : 0; }
 int32_t rtjx_intern_contig(rtjx_t* h, const char* name) { return h ? h->e->intern_contig(name) : -1; }

@@ -318,6 +318,15 @@ class JunctionsExtractor:
                                           meta.ctypes.data, off.ctypes.data, cig.ctypes.data))
         return tid, pos, meta, off, cig[:no.value]
 
+    def inflate_file(self, max_blocks: int = 0) -> bytes:
+        """Device BGZF inflate of the BAM (test hook): returns the inflated byte stream."""
+        h = self._handle()
+        n = C.c_uint64()
+        self._check(L.lib.rtjx_inflate_file(h, max_blocks, None, 0, C.byref(n)))
+        buf = np.empty(max(n.value, 1), np.uint8)
+        self._check(L.lib.rtjx_inflate_file(h, max_blocks, buf.ctypes.data, n.value, C.byref(n)))
+        return buf[:n.value].tobytes()
+
     def import_table(self, table: np.ndarray):
         table = np.ascontiguousarray(table, dtype=JUNCTION_DTYPE)
         self._check(L.lib.rtjx_import(self._handle(), table.ctypes.data_as(C.POINTER(L.Junction)), len(table)))
