@@ -1,0 +1,237 @@
+// regtools_b200/csrc/device_feed.cu — BAM record split + field extraction on the device.
+//
+// Input: the inflated BGZF payload of a chunk of the file (inflate.cu), i.e. a byte stream of BAM
+// records `block_size:i32, core[32], qname, cigar[n_cigar], seq, qual, aux`
+// (/root/reference/src/utils/htslib/sam.c:399-432 bam_read1).  Output: the SoA alignment batch the
+// cigar_scan kernel consumes (tid, pos, meta, cig_off, cigar) — the same arrays the host feeder
+// (bam_feeder.cc) produces, bit for bit.
+//
+// Record boundaries form a sequential chain (each record's length sits in its first 4 bytes), so the
+// stream is cut at SEEDS — virtual offsets taken from the BAI (linear-index entries and bin-chunk
+// starts are record starts by construction, hts.c:1288-1350) — and one thread walks each segment.
+// Every walk must land exactly on the next seed; a miss raises a flag and the host falls back to
+// its own feeder, so exactness never depends on the index being right.
+#include "jx_device.cuh"
+#include <cub/device/device_scan.cuh>
+
+namespace rtjx {
+
+__device__ __forceinline__ uint32_t ld_u32_any(const uint8_t* p) {             // unaligned 32-bit load
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    const uint32_t lo = w[0];
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, w[1], sh);
+}
+__device__ __forceinline__ uint32_t ld_u16_any(const uint8_t* p) { return (uint32_t)p[0] | (uint32_t)p[1] << 8; }
+
+// bam_read1's validity checks (sam.c:399-432); `core` points at the 32-byte core.
+__device__ __forceinline__ bool record_ok(const uint8_t* core, int32_t block_len) {
+    const int32_t l_data = block_len - 32;
+    const int32_t l_qseq = (int32_t)ld_u32_any(core + 16);
+    const uint32_t l_qname = core[8];
+    if (l_data < 0 || l_qseq < 0 || l_qname < 1) return false;
+    const long long aux_off = (long long)l_qname + 4ll * ld_u16_any(core + 12) + ((long long)l_qseq + 1) / 2 + l_qseq;
+    return aux_off <= l_data;
+}
+
+// One thread per seed segment.  data = first byte of the chunk's inflated stream (negative offsets
+// reach into the carry headroom).  seeds[i] are offsets relative to data; seeds[0] is replaced by
+// -(carry length) when `use_carry`.  rec_off gets, per segment, the offsets of its records.
+__global__ void __launch_bounds__(128)
+record_walk_kernel(const uint8_t* __restrict__ data, int64_t data_len, int64_t limit, const int64_t* __restrict__ seeds,
+                   const uint32_t* __restrict__ seg_base, uint32_t n_seg, int use_carry, FeedState* __restrict__ state,
+                   int32_t* __restrict__ rec_off, uint32_t* __restrict__ seg_cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_seg) return;
+    int64_t p = seeds[i];
+    if (i == 0 && use_carry) p = -(int64_t)state->carry_len;
+    const bool last = i + 1 == n_seg;
+    const int64_t end = last ? data_len : seeds[i + 1];
+    const int64_t stop_at = limit < end ? limit : end;        // range end (contig shard) may cut the last segment
+    uint32_t n = 0;
+    int32_t* my = rec_off + seg_base[i];
+    const uint32_t cap = seg_base[i + 1] - seg_base[i];
+    int64_t carry_from = -1;
+    while (p < stop_at) {
+        if (p + 4 > data_len) { carry_from = p; break; }
+        const int32_t bl = (int32_t)ld_u32_any(data + p);
+        if (bl < 32) { atomicMin(&state->bad_offset, (long long)p); break; }          // malformed: iteration ends here
+        if (p + 4 + (int64_t)bl > data_len) { carry_from = p; break; }                  // record continues in the next chunk
+        if (!record_ok(data + p + 4, bl)) { atomicMin(&state->bad_offset, (long long)p); break; }
+        if (n < cap) my[n] = (int32_t)p;
+        else atomicOr(&state->flags, FEED_FLAG_CAPACITY);
+        ++n;
+        p += 4 + (int64_t)bl;
+    }
+    seg_cnt[i] = n < cap ? n : cap;
+    if (!last) {
+        if (carry_from >= 0 || (p != end && p < limit && state->bad_offset > p)) atomicOr(&state->flags, FEED_FLAG_SEED_MISS);
+    } else {
+        // bytes of an unfinished record are carried into the next chunk's headroom
+        state->next_carry_from = carry_from >= 0 ? carry_from : (p < data_len && p >= limit ? data_len : p);
+        if (p >= limit) state->reached_limit = 1;
+    }
+}
+
+// Gathers the per-segment record lists into one dense array; also fetches n_cigar for the scan.
+__global__ void __launch_bounds__(256)
+record_gather_kernel(const uint8_t* __restrict__ data, const int32_t* __restrict__ rec_off, const uint32_t* __restrict__ seg_base,
+                     const uint32_t* __restrict__ seg_cnt, const uint32_t* __restrict__ seg_scan, uint32_t n_seg,
+                     uint32_t cap_total, const FeedState* __restrict__ state, int32_t* __restrict__ dense,
+                     uint32_t* __restrict__ ncig) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= cap_total) return;
+    uint32_t lo = 0, hi = n_seg;                                   // last segment with seg_base <= s
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (seg_base[mid] <= s) lo = mid; else hi = mid; }
+    const uint32_t j = s - seg_base[lo];
+    if (j >= seg_cnt[lo]) return;
+    const int32_t off = rec_off[s];
+    const uint32_t r = seg_scan[lo] + j;
+    dense[r] = off;
+    ncig[r] = ld_u16_any(data + off + 4 + 12);
+}
+
+// bam_aux_get + bam_aux2A (sam.c:1254-1266, 1301-1307): value byte of the first `tag` if its type is 'A'.
+__device__ __forceinline__ uint32_t strand_tag_byte(const uint8_t* s, const uint8_t* e, uint32_t t0, uint32_t t1) {
+    while (s + 3 <= e) {
+        const bool match = s[0] == t0 && s[1] == t1;
+        const uint32_t type = s[2];
+        s += 3;
+        if (match) return (type == 'A' && s < e) ? *s : 0u;
+        switch (type) {
+        case 'A': case 'c': case 'C': s += 1; break;
+        case 's': case 'S': s += 2; break;
+        case 'i': case 'I': case 'f': s += 4; break;
+        case 'd': s += 8; break;
+        case 'Z': case 'H': while (s < e && *s) ++s; ++s; break;
+        case 'B': {
+            if (s + 5 > e) return 0u;
+            const uint32_t sub = s[0]; const uint32_t n = ld_u32_any(s + 1); s += 5;
+            const uint32_t sz = (sub == 'c' || sub == 'C' || sub == 'A') ? 1u : (sub == 's' || sub == 'S') ? 2u :
+                                (sub == 'i' || sub == 'I' || sub == 'f') ? 4u : sub == 'd' ? 8u : 0u;
+            if ((unsigned long long)(e - s) < (unsigned long long)sz * n) return 0u;
+            s += (size_t)sz * n; break; }
+        default: return 0u;
+        }
+    }
+    return 0u;
+}
+
+// One thread per record: core fields, CIGAR words, strand tag -> SoA batch.
+__global__ void __launch_bounds__(256)
+record_extract_kernel(const uint8_t* __restrict__ data, const int32_t* __restrict__ dense, const uint32_t* __restrict__ ncig_scan,
+                      const uint32_t* __restrict__ d_n_rec, int32_t n_ref, int xs_mode, uint32_t tag0, uint32_t tag1,
+                      int32_t* __restrict__ o_tid, int32_t* __restrict__ o_pos, uint32_t* __restrict__ o_meta,
+                      uint32_t* __restrict__ o_off, uint32_t* __restrict__ o_cigar, FeedState* __restrict__ state) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_rec = *d_n_rec;
+    if (r > n_rec) return;
+    if (r == n_rec) { o_off[r] = ncig_scan[r]; return; }          // closing offset (scan is over n_rec + 1 entries)
+    const uint8_t* rec = data + dense[r];
+    const int32_t bl = (int32_t)ld_u32_any(rec);
+    const uint8_t* core = rec + 4;
+    int32_t tid = (int32_t)ld_u32_any(core);
+    const uint32_t l_qname = core[8], mapq = core[9], n_cigar = ld_u16_any(core + 12), flag = ld_u16_any(core + 14);
+    const uint8_t* cig = core + 32 + l_qname;
+    const uint32_t o0 = ncig_scan[r];
+    uint32_t strand = 0, nn = 0;
+    for (uint32_t k = 0; k < n_cigar; ++k) {
+        const uint32_t w = ld_u32_any(cig + 4 * k);
+        o_cigar[o0 + k] = w;
+        nn += (w & 0xfu) == 3u;
+    }
+    if (n_cigar > 1) {
+        if (tid < 0 || tid >= n_ref) tid = -1;
+        if (xs_mode && nn) {
+            const int32_t l_qseq = (int32_t)ld_u32_any(core + 16);
+            const uint8_t* aux = cig + 4 * (size_t)n_cigar + ((size_t)l_qseq + 1) / 2 + (size_t)l_qseq;
+            strand = strand_tag_byte(aux, core + bl, tag0, tag1);
+        }
+        if (nn) atomicAdd(&state->n_junction_ops, nn);
+    }
+    o_tid[r] = tid;
+    o_pos[r] = (int32_t)ld_u32_any(core + 4);
+    o_meta[r] = flag << 16 | mapq << 8 | strand;
+    o_off[r] = o0;
+}
+
+// Moves the unfinished tail of this chunk in front of the next chunk's data and publishes counts.
+__global__ void feed_finish_kernel(const uint8_t* __restrict__ data, int64_t data_len, uint8_t* __restrict__ next_data,
+                                   uint32_t headroom, const uint32_t* __restrict__ seg_scan, uint32_t n_seg,
+                                   const uint32_t* __restrict__ ncig_scan, FeedState* __restrict__ state) {
+    __shared__ uint32_t s_len;
+    if (threadIdx.x == 0) {
+        long long from = state->next_carry_from;
+        if (state->bad_offset <= from) from = data_len;             // stream is dead: nothing to carry
+        long long len = data_len - from;
+        if (len < 0) len = 0;
+        if (len > (long long)headroom || len > data_len) { len = 0; state->flags |= FEED_FLAG_CARRY_TOO_BIG; }
+        s_len = (uint32_t)len;
+    }
+    __syncthreads();
+    const uint32_t len = s_len;
+    const uint8_t* src = data + (data_len - len);
+    for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) next_data[(long long)k - (long long)len] = src[k];
+    if (threadIdx.x == 0) state->carry_len = len;
+}
+
+__global__ void feed_count_kernel(const uint32_t* __restrict__ seg_scan, uint32_t n_seg, FeedState* __restrict__ state) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) state->n_rec = seg_scan[n_seg];
+}
+__global__ void feed_ops_kernel(const uint32_t* __restrict__ ncig_scan, FeedState* __restrict__ state) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) state->n_ops = ncig_scan[state->n_rec];
+}
+
+__global__ void feed_reset_kernel(FeedState* state, int keep_carry) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        state->bad_offset = 0x7fffffffffffffffll; state->next_carry_from = 0; state->flags = 0;
+        state->n_rec = state->n_ops = state->n_junction_ops = 0; state->reached_limit = 0;
+        if (!keep_carry) state->carry_len = 0;
+    }
+}
+void launch_feed_reset(FeedState* state, int keep_carry, cudaStream_t stream) { feed_reset_kernel<<<1, 32, 0, stream>>>(state, keep_carry); }
+
+size_t feed_scan_workspace_bytes(uint32_t n) {
+    size_t b = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)n);
+    return b + 256;
+}
+
+void launch_record_walk(const uint8_t* data, int64_t data_len, int64_t limit, const int64_t* seeds, const uint32_t* seg_base,
+                        uint32_t n_seg, int use_carry, FeedState* state, int32_t* rec_off, uint32_t* seg_cnt,
+                        cudaStream_t stream) {
+    if (!n_seg) return;
+    record_walk_kernel<<<(n_seg + 127) / 128, 128, 0, stream>>>(data, data_len, limit, seeds, seg_base, n_seg, use_carry, state,
+                                                                 rec_off, seg_cnt);
+}
+
+// seg_cnt[0..n_seg) -> seg_scan[0..n_seg] (exclusive, with total), gather, ncig -> ncig_scan[0..n_rec] (exclusive, with total)
+void launch_record_gather(const uint8_t* data, const int32_t* rec_off, const uint32_t* seg_base, uint32_t* seg_cnt,
+                          uint32_t* seg_scan, uint32_t n_seg, uint32_t cap_total, FeedState* state, int32_t* dense,
+                          uint32_t* ncig, uint32_t* ncig_scan, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (!n_seg) return;
+    // seg_cnt has one extra zero entry so the exclusive scan yields the total in seg_scan[n_seg]
+    cub::DeviceScan::ExclusiveSum(ws, ws_bytes, seg_cnt, seg_scan, (int)(n_seg + 1), stream);
+    feed_count_kernel<<<1, 32, 0, stream>>>(seg_scan, n_seg, state);
+    cudaMemsetAsync(ncig, 0, ((size_t)cap_total + 1) * sizeof(uint32_t), stream);
+    record_gather_kernel<<<(cap_total + 255) / 256, 256, 0, stream>>>(data, rec_off, seg_base, seg_cnt, seg_scan, n_seg, cap_total,
+                                                                       state, dense, ncig);
+    cub::DeviceScan::ExclusiveSum(ws, ws_bytes, ncig, ncig_scan, (int)(cap_total + 1), stream);
+    feed_ops_kernel<<<1, 32, 0, stream>>>(ncig_scan, state);
+}
+
+void launch_record_extract(const uint8_t* data, const int32_t* dense, const uint32_t* ncig_scan, uint32_t cap_total,
+                           FeedState* state, int32_t n_ref, int xs_mode, uint32_t tag0, uint32_t tag1, int32_t* o_tid,
+                           int32_t* o_pos, uint32_t* o_meta, uint32_t* o_off, uint32_t* o_cigar, cudaStream_t stream) {
+    record_extract_kernel<<<(cap_total + 1 + 255) / 256, 256, 0, stream>>>(data, dense, ncig_scan, &state->n_rec, n_ref, xs_mode, tag0, tag1,
+                                                                          o_tid, o_pos, o_meta, o_off, o_cigar, state);
+}
+
+void launch_feed_finish(const uint8_t* data, int64_t data_len, uint8_t* next_data, uint32_t headroom, const uint32_t* seg_scan,
+                        uint32_t n_seg, const uint32_t* ncig_scan, FeedState* state, cudaStream_t stream) {
+    feed_finish_kernel<<<1, 256, 0, stream>>>(data, data_len, next_data, headroom, seg_scan, n_seg, ncig_scan, state);
+}
+
+}  // namespace rtjx

@@ -46,6 +46,7 @@ Engine::~Engine() {
     if (dev_ready_) {
         cudaSetDevice(prm_.device);
         cudaDeviceSynchronize();
+        dfeed_.reset();
         for (auto& pe : prof_pending_) { ev_pool_.push_back(pe.a); ev_pool_.push_back(pe.b); ev_pool_.push_back(pe.c); }
         for (auto e : ev_pool_) cudaEventDestroy(e);
         for (auto& d : dev_batch_) {
@@ -374,6 +375,18 @@ int Engine::run() {
     int rc = open_bam(&bam, &idx, &spec);
     if (rc) return rc;
     if ((rc = ensure_device())) return rc;
+    // Whole-file and contig-shard runs inflate and split records on the GPU (inflate_mode 0 = auto, 2 = force);
+    // regions, tiny files and anything the device path declines go through the host feeder below.
+    const bool streamable = spec.kind == IterSpec::WholeFile || spec.kind == IterSpec::Contigs;
+    if (streamable && (prm_.inflate_mode == 2 || (prm_.inflate_mode == 0 && bam->size() >= (1u << 20)))) {
+        const rtjx_stats saved = stats_;
+        rc = run_device(*bam, idx, spec);
+        if (rc == RTJX_OK) return RTJX_OK;
+        if (rc < 0) return rc;
+        if ((rc = clear())) return rc;                        // declined: start over on the host path
+        stats_ = saved;
+        contigs_ = bam->header().names; rank_dirty_ = true;
+    }
     uint32_t reads = prm_.batch_reads ? prm_.batch_reads : (spec.kind == IterSpec::Region ? (1u << 15) : (1u << 20));
     reads = std::max(reads, 1024u);
     uint32_t ops = std::max<uint32_t>(2 * reads, 1u << 17);      // one read may carry 65535 ops

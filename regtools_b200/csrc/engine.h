@@ -50,6 +50,7 @@ private:
     int process_device_batch(const BatchView& v, uint32_t cand_bound, cudaStream_t stream);
     int sync_counters(cudaStream_t stream);
     int open_bam(std::unique_ptr<BamFile>* bam, BaiIndex* idx, IterSpec* spec);
+    int run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& spec);   // device_run.cc; +1 = declined
     void host_rank_and_sort();
     void resolve_profile_events();
     ScanParams scan_params() const;
@@ -98,6 +99,12 @@ private:
     // cached feeder output for load_batch
     struct LoadedBatch;
     std::unique_ptr<LoadedBatch> loaded_;
+
+    // device-side feeder (BGZF inflate + record split on the GPU), device_run.cc
+    struct DeviceFeed;
+    struct DeviceFeedDeleter { void operator()(DeviceFeed* p) const; };
+    std::unique_ptr<DeviceFeed, DeviceFeedDeleter> dfeed_;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> feed_prof_;
 
     // profiling
     struct ProfEv { cudaEvent_t a, b, c; };

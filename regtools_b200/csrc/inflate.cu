@@ -298,6 +298,16 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
     if (lane == 0) status[b] = err;
 }
 
+__global__ void inflate_status_reduce_kernel(const uint32_t* __restrict__ status, uint32_t n, uint32_t* __restrict__ flags) {
+    uint32_t bad = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) bad |= status[i];
+    if (__any_sync(0xffffffffu, bad != 0) && (threadIdx.x & 31u) == 0) atomicOr(flags, 8u);   // FEED_FLAG_INFLATE
+}
+void launch_inflate_status_reduce(const uint32_t* status, uint32_t n_blocks, uint32_t* flags, cudaStream_t stream) {
+    if (!n_blocks) return;
+    inflate_status_reduce_kernel<<<(n_blocks + 1023) / 1024 > 64 ? 64 : (n_blocks + 1023) / 1024, 256, 0, stream>>>(status, n_blocks, flags);
+}
+
 void launch_bgzf_inflate(const uint8_t* comp, const void* blocks, uint32_t n_blocks, uint8_t* out, uint32_t* status,
                          cudaStream_t stream) {
     if (n_blocks == 0) return;

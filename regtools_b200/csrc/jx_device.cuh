@@ -88,6 +88,32 @@ struct BgzfBlockDesc { uint32_t in_off, in_len, out_off, out_len; };
 void launch_bgzf_inflate(const uint8_t* comp, const void* blocks, uint32_t n_blocks, uint8_t* out, uint32_t* status,
                          cudaStream_t stream);
 
+void launch_inflate_status_reduce(const uint32_t* status, uint32_t n_blocks, uint32_t* flags, cudaStream_t stream);
+
+// Device-side BAM record split (device_feed.cu).
+struct FeedState {
+    long long bad_offset;         // smallest offset of a malformed record (LLONG_MAX: none)
+    long long next_carry_from;    // offset of the first byte that belongs to the next chunk
+    uint32_t carry_len;           // bytes carried in front of the next chunk's data
+    uint32_t flags;
+    uint32_t n_rec, n_ops, n_junction_ops;
+    uint32_t reached_limit;       // the range end (contig shard) lies in this chunk
+};
+enum { FEED_FLAG_SEED_MISS = 1, FEED_FLAG_CAPACITY = 2, FEED_FLAG_CARRY_TOO_BIG = 4, FEED_FLAG_INFLATE = 8 };
+size_t feed_scan_workspace_bytes(uint32_t n);
+void launch_feed_reset(FeedState* state, int keep_carry, cudaStream_t stream);
+void launch_record_walk(const uint8_t* data, int64_t data_len, int64_t limit, const int64_t* seeds, const uint32_t* seg_base,
+                        uint32_t n_seg, int use_carry, FeedState* state, int32_t* rec_off, uint32_t* seg_cnt,
+                        cudaStream_t stream);
+void launch_record_gather(const uint8_t* data, const int32_t* rec_off, const uint32_t* seg_base, uint32_t* seg_cnt,
+                          uint32_t* seg_scan, uint32_t n_seg, uint32_t cap_total, FeedState* state, int32_t* dense,
+                          uint32_t* ncig, uint32_t* ncig_scan, void* ws, size_t ws_bytes, cudaStream_t stream);
+void launch_record_extract(const uint8_t* data, const int32_t* dense, const uint32_t* ncig_scan, uint32_t cap_total,
+                           FeedState* state, int32_t n_ref, int xs_mode, uint32_t tag0, uint32_t tag1, int32_t* o_tid,
+                           int32_t* o_pos, uint32_t* o_meta, uint32_t* o_off, uint32_t* o_cigar, cudaStream_t stream);
+void launch_feed_finish(const uint8_t* data, int64_t data_len, uint8_t* next_data, uint32_t headroom, const uint32_t* seg_scan,
+                        uint32_t n_seg, const uint32_t* ncig_scan, FeedState* state, cudaStream_t stream);
+
 // counters layout in d_counters (uint32 each)
 enum { CTR_NCAND = 0, CTR_CAND_OVERFLOW = 1, CTR_NUNIQUE = 2, CTR_NSPILL = 3, CTR_NOUT = 4,
        CTR_TOTAL_CAND64 = 6 /* 64-bit, two words */, CTR_COUNT = 8 };
