@@ -723,6 +723,27 @@ uint64_t scan_bgzf_blocks(const BamFile& bam, uint64_t coff, uint64_t end_coff, 
     return coff;
 }
 
+uint64_t scan_bgzf_blocks_mem(const uint8_t* buf, size_t n, uint64_t base_coff, uint64_t end_coff,
+                              std::vector<BgzfBlockInfo>* out, bool* stop, bool* partial) {
+    *stop = false; *partial = false;
+    size_t o = 0;
+    for (;;) {
+        if (base_coff + o >= end_coff) { *stop = true; break; }
+        if (o + 18 > n) { *partial = true; break; }
+        const uint8_t* h = buf + o;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4) || rd16(h + 10) != 6 || h[12] != 'B' || h[13] != 'C' ||
+            rd16(h + 14) != 2) { *stop = true; break; }
+        const uint32_t bsize = (uint32_t)rd16(h + 16) + 1u;
+        if (bsize < 26) { *stop = true; break; }
+        if (o + bsize > n) { *partial = true; break; }
+        const uint32_t isize = rd32(h + bsize - 4);
+        if (isize == 0 || isize > 0x10000) { *stop = true; break; }
+        out->push_back(BgzfBlockInfo{base_coff + o, bsize, isize});
+        o += bsize;
+    }
+    return base_coff + o;
+}
+
 std::vector<int32_t> plan_contig_shards(const BamFile& bam, const BaiIndex& idx, int world) {
     const size_t n = bam.header().names.size();
     std::vector<int32_t> assign(n, 0);

@@ -76,6 +76,7 @@ public:
     const BamHeader& header() const { return hdr_; }
     const uint8_t* data() const { return map_; }
     size_t size() const { return size_; }
+    int fd() const { return fd_; }
     // bam_name2id (sam.c:262-277): last duplicate wins; -1 if unknown
     int32_t name2id(const std::string& name) const;
 private:
@@ -112,6 +113,11 @@ bool feed_alignments(const BamFile& bam, const BaiIndex& idx, const IterSpec& sp
 struct BgzfBlockInfo { uint64_t coff; uint32_t csize, isize; };
 uint64_t scan_bgzf_blocks(const BamFile& bam, uint64_t coff, uint64_t end_coff, size_t max_blocks, uint64_t max_comp_bytes,
                           std::vector<BgzfBlockInfo>* out, bool* stop);
+
+// Same walk over a memory copy of file bytes [base_coff, base_coff + n): stops before the first block that is not
+// completely inside the buffer (*partial = true) or at an empty / malformed block (*stop = true).
+uint64_t scan_bgzf_blocks_mem(const uint8_t* buf, size_t n, uint64_t base_coff, uint64_t end_coff,
+                              std::vector<BgzfBlockInfo>* out, bool* stop, bool* partial);
 
 // LPT assignment of contigs to shards by compressed byte span.
 std::vector<int32_t> plan_contig_shards(const BamFile& bam, const BaiIndex& idx, int world);

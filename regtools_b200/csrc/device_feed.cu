@@ -36,14 +36,26 @@ __device__ __forceinline__ bool record_ok(const uint8_t* core, int32_t block_len
     return aux_off <= l_data;
 }
 
-// One thread per seed segment.  data = first byte of the chunk's inflated stream (negative offsets
-// reach into the carry headroom).  seeds[i] are offsets relative to data; seeds[0] is replaced by
-// -(carry length) when `use_carry`.  rec_off gets, per segment, the offsets of its records.
-__global__ void __launch_bounds__(128)
+// One WARP per seed segment.  data = first byte of the chunk's inflated stream (negative offsets reach into
+// the carry headroom).  seeds[i] are offsets relative to data; seeds[0] is replaced by -(carry length) when
+// `use_carry`.  rec_off gets, per segment, the offsets of its records.
+// The chain of block_size fields is serial, but its latency need not be DRAM latency: the warp pulls the
+// stream through a 4 KB shared-memory window with coalesced loads (one memory round trip per ~19 records)
+// and lane 0 hops from record to record inside the window.
+constexpr int WALK_WARPS = 4;
+constexpr int WALK_WIN   = 4096;
+
+__device__ __forceinline__ uint32_t lds_u32_any(const uint8_t* p) {
+    return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
+}
+
+__global__ void __launch_bounds__(WALK_WARPS * 32)
 record_walk_kernel(const uint8_t* __restrict__ data, int64_t data_len, int64_t limit, const int64_t* __restrict__ seeds,
                    const uint32_t* __restrict__ seg_base, uint32_t n_seg, int use_carry, FeedState* __restrict__ state,
                    int32_t* __restrict__ rec_off, uint32_t* __restrict__ seg_cnt) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(16) uint32_t s_win[WALK_WARPS][WALK_WIN / 4 + 4];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * WALK_WARPS + wib;
     if (i >= n_seg) return;
     int64_t p = seeds[i];
     if (i == 0 && use_carry) p = -(int64_t)state->carry_len;
@@ -54,17 +66,49 @@ record_walk_kernel(const uint8_t* __restrict__ data, int64_t data_len, int64_t l
     int32_t* my = rec_off + seg_base[i];
     const uint32_t cap = seg_base[i + 1] - seg_base[i];
     int64_t carry_from = -1;
-    while (p < stop_at) {
-        if (p + 4 > data_len) { carry_from = p; break; }
-        const int32_t bl = (int32_t)ld_u32_any(data + p);
-        if (bl < 32) { atomicMin(&state->bad_offset, (long long)p); break; }          // malformed: iteration ends here
-        if (p + 4 + (int64_t)bl > data_len) { carry_from = p; break; }                  // record continues in the next chunk
-        if (!record_ok(data + p + 4, bl)) { atomicMin(&state->bad_offset, (long long)p); break; }
-        if (n < cap) my[n] = (int32_t)p;
-        else atomicOr(&state->flags, FEED_FLAG_CAPACITY);
-        ++n;
-        p += 4 + (int64_t)bl;
+    const uint8_t* win = reinterpret_cast<const uint8_t*>(s_win[wib]);
+    bool done = false;
+    while (!done) {
+        if (p >= stop_at) break;
+        // window [wbase, wbase + WALK_WIN) of the stream, 4-byte aligned (data itself is 256-byte aligned)
+        const int64_t wbase = (p >> 2) << 2;
+        int64_t wbytes = data_len + 8 - wbase;                 // the buffer is padded past data_len
+        if (wbytes > WALK_WIN) wbytes = WALK_WIN;
+        const uint32_t nw = (uint32_t)((wbytes + 3) >> 2);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(data + wbase);
+        for (uint32_t w = lane; w < nw; w += 32) s_win[wib][w] = src[w];
+        __syncwarp();
+        if (lane == 0) {
+            const int64_t wend = wbase + (int64_t)nw * 4;
+            while (p < stop_at) {
+                if (p + 4 > data_len) { carry_from = p; done = true; break; }
+                if (p + 24 > wend) {
+                    if (wend >= data_len) { carry_from = p; done = true; }              // header cut by the end of the chunk
+                    break;                                                              // else: reload the window at p
+                }
+                const int32_t bl = (int32_t)lds_u32_any(win + (p - wbase));
+                if (bl < 32) { atomicMin(&state->bad_offset, (long long)p); done = true; break; }     // malformed: iteration ends here
+                if (p + 4 + (int64_t)bl > data_len) { carry_from = p; done = true; break; }            // continues in the next chunk
+                {   // bam_read1's validity checks (sam.c:399-432) on the core fields inside the window
+                    const uint8_t* core = win + (p - wbase) + 4;
+                    const int32_t l_qseq = (int32_t)lds_u32_any(core + 16);
+                    const uint32_t l_qname = core[8];
+                    const uint32_t n_cigar = (uint32_t)core[12] | (uint32_t)core[13] << 8;
+                    const long long aux_off = (long long)l_qname + 4ll * n_cigar + ((long long)l_qseq + 1) / 2 + l_qseq;
+                    if (l_qseq < 0 || l_qname < 1 || aux_off > (long long)bl - 32) { atomicMin(&state->bad_offset, (long long)p); done = true; break; }
+                }
+                if (n < cap) my[n] = (int32_t)p;
+                else atomicOr(&state->flags, FEED_FLAG_CAPACITY);
+                ++n;
+                p += 4 + (int64_t)bl;
+            }
+            if (p >= stop_at) done = true;
+        }
+        p = __shfl_sync(0xffffffffu, p, 0);
+        done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
+        __syncwarp();
     }
+    if (lane != 0) return;
     seg_cnt[i] = n < cap ? n : cap;
     if (!last) {
         if (carry_from >= 0 || (p != end && p < limit && state->bad_offset > p)) atomicOr(&state->flags, FEED_FLAG_SEED_MISS);
@@ -124,7 +168,8 @@ __global__ void __launch_bounds__(256)
 record_extract_kernel(const uint8_t* __restrict__ data, const int32_t* __restrict__ dense, const uint32_t* __restrict__ ncig_scan,
                       const uint32_t* __restrict__ d_n_rec, int32_t n_ref, int xs_mode, uint32_t tag0, uint32_t tag1,
                       int32_t* __restrict__ o_tid, int32_t* __restrict__ o_pos, uint32_t* __restrict__ o_meta,
-                      uint32_t* __restrict__ o_off, uint32_t* __restrict__ o_cigar, FeedState* __restrict__ state) {
+                      uint32_t* __restrict__ o_off, uint32_t* __restrict__ o_cigar, uint32_t cigar_cap,
+                      FeedState* __restrict__ state) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_rec = *d_n_rec;
     if (r > n_rec) return;
@@ -136,6 +181,7 @@ record_extract_kernel(const uint8_t* __restrict__ data, const int32_t* __restric
     const uint32_t l_qname = core[8], mapq = core[9], n_cigar = ld_u16_any(core + 12), flag = ld_u16_any(core + 14);
     const uint8_t* cig = core + 32 + l_qname;
     const uint32_t o0 = ncig_scan[r];
+    if ((unsigned long long)o0 + n_cigar > cigar_cap) { atomicOr(&state->flags, FEED_FLAG_CAPACITY); return; }
     uint32_t strand = 0, nn = 0;
     for (uint32_t k = 0; k < n_cigar; ++k) {
         const uint32_t w = ld_u32_any(cig + 4 * k);
@@ -203,7 +249,7 @@ void launch_record_walk(const uint8_t* data, int64_t data_len, int64_t limit, co
                         uint32_t n_seg, int use_carry, FeedState* state, int32_t* rec_off, uint32_t* seg_cnt,
                         cudaStream_t stream) {
     if (!n_seg) return;
-    record_walk_kernel<<<(n_seg + 127) / 128, 128, 0, stream>>>(data, data_len, limit, seeds, seg_base, n_seg, use_carry, state,
+    record_walk_kernel<<<(n_seg + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, 0, stream>>>(data, data_len, limit, seeds, seg_base, n_seg, use_carry, state,
                                                                  rec_off, seg_cnt);
 }
 
@@ -224,9 +270,10 @@ void launch_record_gather(const uint8_t* data, const int32_t* rec_off, const uin
 
 void launch_record_extract(const uint8_t* data, const int32_t* dense, const uint32_t* ncig_scan, uint32_t cap_total,
                            FeedState* state, int32_t n_ref, int xs_mode, uint32_t tag0, uint32_t tag1, int32_t* o_tid,
-                           int32_t* o_pos, uint32_t* o_meta, uint32_t* o_off, uint32_t* o_cigar, cudaStream_t stream) {
+                           int32_t* o_pos, uint32_t* o_meta, uint32_t* o_off, uint32_t* o_cigar, uint32_t cigar_cap,
+                           cudaStream_t stream) {
     record_extract_kernel<<<(cap_total + 1 + 255) / 256, 256, 0, stream>>>(data, dense, ncig_scan, &state->n_rec, n_ref, xs_mode, tag0, tag1,
-                                                                          o_tid, o_pos, o_meta, o_off, o_cigar, state);
+                                                                          o_tid, o_pos, o_meta, o_off, o_cigar, cigar_cap, state);
 }
 
 void launch_feed_finish(const uint8_t* data, int64_t data_len, uint8_t* next_data, uint32_t headroom, const uint32_t* seg_scan,

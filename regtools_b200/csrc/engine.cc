@@ -1,5 +1,6 @@
 // regtools_b200/csrc/engine.cc — see engine.h.
 #include "engine.h"
+#include "buffer_cache.h"
 
 #include <unistd.h>
 
@@ -50,12 +51,12 @@ Engine::~Engine() {
         for (auto& pe : prof_pending_) { ev_pool_.push_back(pe.a); ev_pool_.push_back(pe.b); ev_pool_.push_back(pe.c); }
         for (auto e : ev_pool_) cudaEventDestroy(e);
         for (auto& d : dev_batch_) {
-            cudaFree(d.tid); cudaFree(d.pos); cudaFree(d.meta); cudaFree(d.cig_off); cudaFree(d.cigar);
+            cached_dev_free(d.tid); cached_dev_free(d.pos); cached_dev_free(d.meta); cached_dev_free(d.cig_off); cached_dev_free(d.cigar);
             if (d.free_ev) cudaEventDestroy(d.free_ev);
         }
-        cudaFree(d_counters_); cudaFreeHost(h_counters_);
-        cudaFree(d_table_); cudaFree(d_spill_); cudaFree(d_cands_);
-        cudaFree(d_out_); cudaFree(d_ws_); cudaFree(d_rank_); cudaFreeHost(h_final_); cudaFree(d_slot_list_);
+        cached_dev_free(d_counters_); cached_host_free(h_counters_);
+        cached_dev_free(d_table_); cached_dev_free(d_spill_); cached_dev_free(d_cands_);
+        cached_dev_free(d_out_); cached_dev_free(d_ws_); cached_dev_free(d_rank_); cached_host_free(h_final_); cached_dev_free(d_slot_list_);
         if (stream_) cudaStreamDestroy(stream_);
         if (copy_stream_) cudaStreamDestroy(copy_stream_);
     }
@@ -90,11 +91,11 @@ int Engine::ensure_device() {
     CK(cudaSetDevice(prm_.device));
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
-    CK(cudaMalloc(&d_counters_, CTR_COUNT * sizeof(uint32_t)));
+    CK(cached_dev_malloc(&d_counters_, CTR_COUNT * sizeof(uint32_t)));
     CK(cudaMemset(d_counters_, 0, CTR_COUNT * sizeof(uint32_t)));
-    CK(cudaHostAlloc(&h_counters_, CTR_COUNT * sizeof(uint32_t), cudaHostAllocDefault));
+    CK(cached_host_alloc(&h_counters_, CTR_COUNT * sizeof(uint32_t)));
     spill_cap_ = 4096;
-    CK(cudaMalloc(&d_spill_, spill_cap_ * sizeof(Slot)));
+    CK(cached_dev_malloc(&d_spill_, spill_cap_ * sizeof(Slot)));
     dev_ready_ = true;
     return RTJX_OK;
 }
@@ -113,9 +114,9 @@ int Engine::sync_counters(cudaStream_t stream) {
 int Engine::ensure_cands(uint32_t n) {
     if (n <= cand_cap_) return RTJX_OK;
     CK(cudaDeviceSynchronize());
-    cudaFree(d_cands_); d_cands_ = nullptr;
+    cached_dev_free(d_cands_); d_cands_ = nullptr;
     uint32_t cap = std::max<uint32_t>(n + n / 4, 1u << 16);
-    CK(cudaMalloc(&d_cands_, (size_t)cap * sizeof(Cand)));
+    CK(cached_dev_malloc(&d_cands_, (size_t)cap * sizeof(Cand)));
     cand_cap_ = cap;
     return RTJX_OK;
 }
@@ -126,8 +127,8 @@ int Engine::ensure_table(uint32_t incoming, cudaStream_t stream) {
     if (!d_table_) {
         uint32_t want = 1u << (prm_.table_log2 ? std::min<uint32_t>(prm_.table_log2, 30) : 22);
         want = std::max(want, next_pow2(4ull * incoming));
-        CK(cudaMalloc(&d_table_, (size_t)want * sizeof(Slot)));
-        CK(cudaMalloc(&d_slot_list_, (size_t)want * sizeof(uint32_t)));
+        CK(cached_dev_malloc(&d_table_, (size_t)want * sizeof(Slot)));
+        CK(cached_dev_malloc(&d_slot_list_, (size_t)want * sizeof(uint32_t)));
         CK(cudaMemsetAsync(d_table_, 0, (size_t)want * sizeof(Slot), stream));
         table_slots_ = want; unique_upper_ = 0;
     }
@@ -137,14 +138,14 @@ int Engine::ensure_table(uint32_t incoming, cudaStream_t stream) {
         if (2ull * (unique_upper_ + incoming) > table_slots_) {
             uint32_t want = next_pow2(4ull * (unique_upper_ + incoming));
             Slot* nt = nullptr; uint32_t* nl = nullptr;
-            CK(cudaMalloc(&nt, (size_t)want * sizeof(Slot)));
-            CK(cudaMalloc(&nl, (size_t)want * sizeof(uint32_t)));
+            CK(cached_dev_malloc(&nt, (size_t)want * sizeof(Slot)));
+            CK(cached_dev_malloc(&nl, (size_t)want * sizeof(uint32_t)));
             CK(cudaMemsetAsync(nt, 0, (size_t)want * sizeof(Slot), stream));
             CK(cudaMemsetAsync(d_counters_ + CTR_NUNIQUE, 0, sizeof(uint32_t), stream));
             launch_table_rehash(d_table_, table_slots_, TableRef{nt, want - 1, nl, want}, d_counters_, stream);
             stats_.kernel_launches++;
             CK(cudaStreamSynchronize(stream));
-            cudaFree(d_table_); cudaFree(d_slot_list_);
+            cached_dev_free(d_table_); cached_dev_free(d_slot_list_);
             d_table_ = nt; d_slot_list_ = nl; table_slots_ = want; stats_.table_grows++;
         }
     }
@@ -196,17 +197,17 @@ int Engine::ensure_dev_batch(DevBatch& d, uint32_t reads, uint32_t ops) {
     if (!d.free_ev) CK(cudaEventCreateWithFlags(&d.free_ev, cudaEventDisableTiming));
     if (reads > d.cap_reads) {
         CK(cudaEventSynchronize(d.free_ev));
-        cudaFree(d.tid); cudaFree(d.pos); cudaFree(d.meta); cudaFree(d.cig_off);
+        cached_dev_free(d.tid); cached_dev_free(d.pos); cached_dev_free(d.meta); cached_dev_free(d.cig_off);
         uint32_t cap = std::max(reads, 1u << 12);
-        CK(cudaMalloc(&d.tid, (size_t)cap * 4)); CK(cudaMalloc(&d.pos, (size_t)cap * 4));
-        CK(cudaMalloc(&d.meta, (size_t)cap * 4)); CK(cudaMalloc(&d.cig_off, ((size_t)cap + 4) * 4));
+        CK(cached_dev_malloc(&d.tid, (size_t)cap * 4)); CK(cached_dev_malloc(&d.pos, (size_t)cap * 4));
+        CK(cached_dev_malloc(&d.meta, (size_t)cap * 4)); CK(cached_dev_malloc(&d.cig_off, ((size_t)cap + 4) * 4));
         d.cap_reads = cap;
     }
     if (ops > d.cap_ops) {
         CK(cudaEventSynchronize(d.free_ev));
-        cudaFree(d.cigar);
+        cached_dev_free(d.cigar);
         uint32_t cap = std::max(ops, 1u << 12);
-        CK(cudaMalloc(&d.cigar, ((size_t)cap + 4) * 4));
+        CK(cached_dev_malloc(&d.cigar, ((size_t)cap + 4) * 4));
         d.cap_ops = cap;
     }
     return RTJX_OK;
@@ -283,11 +284,11 @@ struct EngineSink : BatchSink {
     int init() {
         for (int i = 0; i < NB; ++i) {
             HostBatch& b = hb[i];
-            if (cudaHostAlloc(&b.tid, (size_t)cap_reads * 4, cudaHostAllocDefault) != cudaSuccess ||
-                cudaHostAlloc(&b.pos, (size_t)cap_reads * 4, cudaHostAllocDefault) != cudaSuccess ||
-                cudaHostAlloc(&b.meta, (size_t)cap_reads * 4, cudaHostAllocDefault) != cudaSuccess ||
-                cudaHostAlloc(&b.cig_off, ((size_t)cap_reads + 1) * 4, cudaHostAllocDefault) != cudaSuccess ||
-                cudaHostAlloc(&b.cigar, (size_t)cap_ops * 4, cudaHostAllocDefault) != cudaSuccess ||
+            if (cached_host_alloc(&b.tid, (size_t)cap_reads * 4) != cudaSuccess ||
+                cached_host_alloc(&b.pos, (size_t)cap_reads * 4) != cudaSuccess ||
+                cached_host_alloc(&b.meta, (size_t)cap_reads * 4) != cudaSuccess ||
+                cached_host_alloc(&b.cig_off, ((size_t)cap_reads + 1) * 4) != cudaSuccess ||
+                cached_host_alloc(&b.cigar, (size_t)cap_ops * 4) != cudaSuccess ||
                 cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess)
                 return e->fail(RTJX_E_CUDA, "pinned batch allocation failed");
             b.cap_reads = cap_reads; b.cap_ops = cap_ops;
@@ -297,8 +298,8 @@ struct EngineSink : BatchSink {
     ~EngineSink() override {
         for (int i = 0; i < NB; ++i) {
             if (in_flight[i]) cudaEventSynchronize(done[i]);
-            cudaFreeHost(hb[i].tid); cudaFreeHost(hb[i].pos); cudaFreeHost(hb[i].meta);
-            cudaFreeHost(hb[i].cig_off); cudaFreeHost(hb[i].cigar);
+            cached_host_free(hb[i].tid); cached_host_free(hb[i].pos); cached_host_free(hb[i].meta);
+            cached_host_free(hb[i].cig_off); cached_host_free(hb[i].cigar);
             if (done[i]) cudaEventDestroy(done[i]);
         }
     }
@@ -426,11 +427,11 @@ int Engine::inflate_file(uint64_t max_blocks, void* out, uint64_t cap, uint64_t*
     if (in_total > 0xfff00000ull || out_total > 0xfff00000ull) return fail(RTJX_E_ARG, "file too large for the single-shot inflate hook");
     *out_len = out_total;
     if (out_total > cap || !out) return blocks.empty() ? RTJX_OK : (out ? fail(RTJX_E_ARG, "output buffer too small") : RTJX_OK);
-    std::vector<uint8_t> packed(in_total + 16, 0);
+    std::vector<uint8_t> packed(in_total + 64, 0);
     for (size_t i = 0; i < blocks.size(); ++i) memcpy(packed.data() + desc[i].in_off, bam.data() + blocks[i].coff + 18, desc[i].in_len);
     uint8_t *d_in = nullptr, *d_out = nullptr; BgzfBlockDesc* d_desc = nullptr; uint32_t* d_status = nullptr;
-    CK(cudaMalloc(&d_in, packed.size())); CK(cudaMalloc(&d_out, out_total + 16));
-    CK(cudaMalloc(&d_desc, desc.size() * sizeof(BgzfBlockDesc) + 16)); CK(cudaMalloc(&d_status, desc.size() * 4 + 16));
+    CK(cached_dev_malloc(&d_in, packed.size())); CK(cached_dev_malloc(&d_out, out_total + 16));
+    CK(cached_dev_malloc(&d_desc, desc.size() * sizeof(BgzfBlockDesc) + 16)); CK(cached_dev_malloc(&d_status, desc.size() * 4 + 16));
     CK(cudaMemcpyAsync(d_in, packed.data(), packed.size(), cudaMemcpyHostToDevice, stream_));
     CK(cudaMemcpyAsync(d_desc, desc.data(), desc.size() * sizeof(BgzfBlockDesc), cudaMemcpyHostToDevice, stream_));
     cudaEvent_t ea = get_event(), eb = get_event();
@@ -445,7 +446,7 @@ int Engine::inflate_file(uint64_t max_blocks, void* out, uint64_t cap, uint64_t*
     float ms = 0; cudaEventElapsedTime(&ms, ea, eb); stats_.inflate_kernel_ms += ms;
     ev_pool_.push_back(ea); ev_pool_.push_back(eb);
     stats_.kernel_launches++; stats_.bgzf_blocks += blocks.size(); stats_.compressed_bytes += in_total; stats_.inflated_bytes += out_total;
-    cudaFree(d_in); cudaFree(d_out); cudaFree(d_desc); cudaFree(d_status);
+    cached_dev_free(d_in); cached_dev_free(d_out); cached_dev_free(d_desc); cached_dev_free(d_status);
     for (size_t i = 0; i < status.size(); ++i)
         if (status[i]) return fail(RTJX_E_IO, "device inflate failed on BGZF block " + std::to_string(i) + " (code " + std::to_string(status[i]) + ")");
     return RTJX_OK;
@@ -554,25 +555,25 @@ void Engine::host_rank_and_sort() {
 int Engine::ensure_finalize_buffers(uint32_t n, size_t n_contigs) {
     if (n > fin_cap_) {
         CK(cudaDeviceSynchronize());
-        cudaFree(d_out_); d_out_ = nullptr;
+        cached_dev_free(d_out_); d_out_ = nullptr;
         uint32_t cap = std::max<uint32_t>(n + n / 2, 1u << 16);
-        CK(cudaMalloc(&d_out_, (size_t)cap * sizeof(OutJunction)));
+        CK(cached_dev_malloc(&d_out_, (size_t)cap * sizeof(OutJunction)));
         fin_cap_ = cap;
-        cudaFree(d_ws_); d_ws_ = nullptr;
+        cached_dev_free(d_ws_); d_ws_ = nullptr;
         ws_cap_ = finalize_sort_workspace_bytes(cap);
-        CK(cudaMalloc(&d_ws_, ws_cap_));
+        CK(cached_dev_malloc(&d_ws_, ws_cap_));
     }
     if (n > h_final_cap_) {
-        cudaFreeHost(h_final_); h_final_ = nullptr;
+        cached_host_free(h_final_); h_final_ = nullptr;
         uint32_t cap = std::max<uint32_t>(n + n / 2, 1u << 16);
-        CK(cudaHostAlloc(&h_final_, (size_t)cap * sizeof(rtjx_junction), cudaHostAllocDefault));
+        CK(cached_host_alloc(&h_final_, (size_t)cap * sizeof(rtjx_junction)));
         h_final_cap_ = cap;
     }
     if (n_contigs > rank_cap_ || !d_rank_) {
         CK(cudaDeviceSynchronize());
-        cudaFree(d_rank_); d_rank_ = nullptr;
+        cached_dev_free(d_rank_); d_rank_ = nullptr;
         rank_cap_ = std::max<size_t>(n_contigs * 2, 64);
-        CK(cudaMalloc(&d_rank_, rank_cap_ * 4));
+        CK(cached_dev_malloc(&d_rank_, rank_cap_ * 4));
         rank_dirty_ = true;
     }
     return RTJX_OK;

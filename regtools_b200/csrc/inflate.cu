@@ -10,6 +10,7 @@
 // not check it either).  Any malformed stream sets the block's status to non-zero; the host then
 // falls back to its own inflate for the whole run.
 #include "jx_device.cuh"
+#include <cstdlib>
 
 namespace rtjx {
 
@@ -55,6 +56,54 @@ struct BitReader {
         return reinterpret_cast<const uint8_t*>(p) - (nb >> 3);
     }
 };
+
+// Word-window bit reader for the symbol loop of the warp-per-block kernel (lane 0): the stream position is
+// (w0 | w1 | w2 = three consecutive aligned words, `off` = bit offset into w0).  A 32-bit window at any bit
+// offset is ONE funnel shift; consuming bits is one add; a new word is needed once per 32 consumed bits and is
+// requested one word ahead so that its latency overlaps the decoding of the current word.
+struct WinReader {
+    const uint32_t* p;      // address of the word after w2
+    uint32_t w0, w1, w2;
+    uint32_t off;           // 0..31 (+ consumed, normalised by advance())
+    __device__ __forceinline__ void init(const uint8_t* src) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+        p = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        off = (uint32_t)(a & 3) * 8;
+        w0 = __ldg(p++); w1 = __ldg(p++); w2 = __ldg(p++);
+    }
+    __device__ __forceinline__ uint32_t window() const { return __funnelshift_r(w0, w1, off); }   // 32 valid bits
+    __device__ __forceinline__ void consume(uint32_t n) {                                            // n <= 32
+        off += n;
+        if (off >= 32u) { off -= 32u; w0 = w1; w1 = w2; w2 = __ldg(p++); }
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t n) { const uint32_t v = window() & ((1u << n) - 1u); consume(n); return v; }   // n <= 31
+    // from / to the generic reader (block headers keep using BitReader)
+    __device__ __forceinline__ void from(const BitReader& br) {
+        // BitReader state: next unread bit is (nb) bits before the end of the words fetched so far
+        const uint8_t* byte = reinterpret_cast<const uint8_t*>(br.p) - ((br.nb + 7) >> 3);
+        const uint32_t bit_in_byte = (uint32_t)((8 - (br.nb & 7)) & 7);
+        init(byte);
+        off += bit_in_byte;
+        if (off >= 32u) { off -= 32u; w0 = w1; w1 = w2; w2 = __ldg(p++); }
+    }
+    __device__ __forceinline__ void to(BitReader& br) const {
+        const uint8_t* w0_addr = reinterpret_cast<const uint8_t*>(p - 3);
+        br.init(w0_addr + (off >> 3));
+        br.drop((int)(off & 7u));
+    }
+};
+
+__device__ __forceinline__ int slow_decode_w(WinReader& wr, const uint16_t* count, const uint16_t* sym) {
+    int code = 0, first = 0, index = 0;
+    uint32_t win = wr.window();
+    for (int len = 1; len <= 15; ++len) {
+        code |= (int)(win & 1u); win >>= 1;
+        const int c = count[len];
+        if (code - c < first) { wr.consume((uint32_t)len); return sym[index + (code - first)]; }
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
 
 // canonical-code slow decode (one bit at a time), used for codes longer than the fast table
 __device__ __forceinline__ int slow_decode(BitReader& br, const uint16_t* count, const uint16_t* sym) {
@@ -231,30 +280,30 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
         if (!build_tables(sm.lens + 288, hdist, sm.dist_count, sm.dist_sym, sm.dist_fast, DIST_BITS, lane)) { err = 10; break; }
 
         // ---- symbols, 32 per round
+        WinReader wr;
+        if (lane == 0) wr.from(br);
         for (bool eob = false; !eob && !err;) {
             uint32_t n = 0, flag = 0;                 // flag: 1 = end of block seen, 2+ = error
             if (lane == 0) {
                 while (n < 32) {
-                    br.need(32);
+                    uint32_t win = wr.window();
                     int sym;
-                    uint32_t e = sm.lit_fast[br.peek(LIT_BITS)];
-                    if (e) { br.drop(e & 15); sym = (int)(e >> 4); }
-                    else { sym = slow_decode(br, sm.lit_count, sm.lit_sym); if (sym < 0) { flag = 11; break; } }
+                    uint32_t e = sm.lit_fast[win & ((1u << LIT_BITS) - 1u)];
+                    if (e) { wr.consume(e & 15u); sym = (int)(e >> 4); }
+                    else { sym = slow_decode_w(wr, sm.lit_count, sm.lit_sym); if (sym < 0) { flag = 11; break; } }
                     if (sym < 256) { sm.q[n++] = 0x80000000u | (uint32_t)sym; continue; }
                     if (sym == 256) { flag = 1; break; }
                     sym -= 257;
                     if (sym >= 29) { flag = 12; break; }
-                    br.need(32);
-                    const uint32_t len = c_len_base[sym] + br.get(c_len_extra[sym]);
-                    br.need(32);
+                    const uint32_t len = c_len_base[sym] + wr.get(c_len_extra[sym]);
                     int ds;
-                    e = sm.dist_fast[br.peek(DIST_BITS)];
-                    if (e) { br.drop(e & 15); ds = (int)(e >> 4); }
-                    else { ds = slow_decode(br, sm.dist_count, sm.dist_sym); if (ds < 0) { flag = 13; break; } }
+                    win = wr.window();
+                    e = sm.dist_fast[win & ((1u << DIST_BITS) - 1u)];
+                    if (e) { wr.consume(e & 15u); ds = (int)(e >> 4); }
+                    else { ds = slow_decode_w(wr, sm.dist_count, sm.dist_sym); if (ds < 0) { flag = 13; break; } }
                     if (ds >= 30) { flag = 14; break; }
-                    br.need(32);
-                    const uint32_t dist = c_dist_base[ds] + br.get(c_dist_extra[ds]);
-                    sm.q[n++] = len << 16 | dist;       // len <= 258, dist <= 32768 (stored as dist, 16 bits: 32768 -> 0x8000)
+                    const uint32_t dist = c_dist_base[ds] + wr.get(c_dist_extra[ds]);
+                    sm.q[n++] = len << 16 | dist;       // len <= 258, dist <= 32768
                 }
             }
             n = __shfl_sync(0xffffffffu, n, 0);
@@ -273,29 +322,219 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
             const uint32_t mypos = opos + x - mylen;
             if (opos + total > cap) { err = 15; break; }
             if (lane < n && is_lit) dst[mypos] = (uint8_t)s;
-            uint32_t mm = __ballot_sync(0xffffffffu, lane < n && !is_lit);
+            // A match whose source lies entirely before this round's first byte depends on nothing the round
+            // writes: every lane copies its own (short) match at once, one L2 round trip for the whole round.
+            // Matches that read bytes produced in this round, and long ones, go through the ordered path below.
+            const uint32_t mlen = s >> 16, mdist = s & 0xffffu;
+            const bool is_match = lane < n && !is_lit;
+            const bool indep = is_match && mlen <= 32u && mypos - opos + (mlen < mdist ? mlen : mdist) <= mdist;
             uint32_t bad = 0;
-            while (mm) {
-                const int j = __ffs(mm) - 1; mm &= mm - 1;
-                const uint32_t sj = __shfl_sync(0xffffffffu, s, j);
-                const uint32_t pj = __shfl_sync(0xffffffffu, mypos, j);
-                const uint32_t len = sj >> 16, dist = sj & 0xffffu;
-                if (dist > pj) { bad = 16; break; }
-                __syncwarp();                                             // earlier stores of this warp are visible
-                const uint8_t* srcp = dst + pj - dist;
-                if (dist >= len) {
-                    for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + k);
-                } else {                                                   // overlapping run: periodic with period dist
-                    for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + (k % dist));
+            if (__ballot_sync(0xffffffffu, is_match && mdist > mypos)) bad = 16;
+            if (!bad) {
+                __syncwarp();
+                if (indep) {
+                    const uint8_t* srcp = dst + mypos - mdist;
+                    if (mdist >= mlen) { for (uint32_t k = 0; k < mlen; ++k) dst[mypos + k] = __ldcg(srcp + k); }
+                    else { for (uint32_t k = 0; k < mlen; ++k) dst[mypos + k] = __ldcg(srcp + (k % mdist)); }
+                }
+                uint32_t mm = __ballot_sync(0xffffffffu, is_match && !indep);
+                while (mm) {
+                    const int j = __ffs(mm) - 1; mm &= mm - 1;
+                    const uint32_t sj = __shfl_sync(0xffffffffu, s, j);
+                    const uint32_t pj = __shfl_sync(0xffffffffu, mypos, j);
+                    const uint32_t len = sj >> 16, dist = sj & 0xffffu;
+                    __syncwarp();                                         // earlier stores of this warp are visible
+                    const uint8_t* srcp = dst + pj - dist;
+                    if (dist >= len) {
+                        for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + k);
+                    } else {                                               // overlapping run: periodic with period dist
+                        for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + (k % dist));
+                    }
                 }
             }
             if (bad) { err = bad; break; }
             __syncwarp();
             opos += total;
         }
+        if (lane == 0) wr.to(br);
     }
     if (!err && opos != cap) err = 17;
     if (lane == 0) status[b] = err;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT variant: one THREAD per BGZF block
+// ------------------------------------------------------------------------------------------------
+// The warp-per-block kernel above spends ~30 issue slots per symbol on a single active lane.  When a
+// launch covers thousands of blocks it is better to let every lane decode its own block: the symbol
+// loop then runs 32 blocks per instruction.  Each thread owns a 1668-byte table region in shared
+// memory (8-bit literal/length and 6-bit distance lookup tables + per-length code counts); the stride is an
+// odd number of words so that equal indices of different lanes fall into different banks.  Lanes diverge only between the literal and the match path and
+// at DEFLATE block headers.
+constexpr int SI_THREADS   = 32;
+constexpr int SI_LIT_BITS  = 8;
+constexpr int SI_DIST_BITS = 6;
+constexpr int SI_STRIDE    = 708;                // bytes per thread in shared memory (177 words: odd, lanes on distinct banks)
+constexpr int SI_OFF_DFAST = 512, SI_OFF_LCNT = 640, SI_OFF_DCNT = 672;
+// the canonical symbol arrays (codes longer than the lookup tables) and the code-length scratch are touched
+// rarely and live in per-thread local memory (L1-cached) so that ~10 warps per SM fit
+
+// per-thread canonical table build; returns false on an over-subscribed code
+__device__ bool si_build(const uint8_t* len, int n, uint16_t* count, uint16_t* sym, uint16_t* fast, int fast_bits) {
+    for (int i = 0; i < 16; ++i) count[i] = 0;
+    for (int i = 0; i < (1 << fast_bits); ++i) fast[i] = 0;
+    for (int i = 0; i < n; ++i) count[len[i]]++;
+    uint16_t offs[16];
+    uint32_t next_code[16];
+    int left = 1;
+    offs[1] = 0; next_code[0] = 0;
+    uint32_t code = 0;
+    for (int l = 1; l <= 15; ++l) {
+        left <<= 1; left -= count[l];
+        if (left < 0) return false;
+        if (l < 15) offs[l + 1] = offs[l] + count[l];
+        code = (code + (l > 1 ? count[l - 1] : 0)) << 1; next_code[l] = code;
+    }
+    for (int s = 0; s < n; ++s) {
+        const int l = len[s];
+        if (!l) continue;
+        sym[offs[l]++] = (uint16_t)s;
+        const uint32_t c = next_code[l]++;
+        if (l <= fast_bits) {
+            const uint32_t rev = __brev(c) >> (32 - l);
+            const uint16_t e = (uint16_t)(s << 4 | l);
+            for (uint32_t k = rev; k < (1u << fast_bits); k += 1u << l) fast[k] = e;
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(SI_THREADS)
+bgzf_inflate_simt_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, uint32_t n_blocks,
+                         uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t si_smem[];
+    const uint32_t b = blockIdx.x * SI_THREADS + threadIdx.x;
+    if (b >= n_blocks) return;
+    uint8_t* T = si_smem + threadIdx.x * SI_STRIDE;
+    uint16_t* lit_fast = reinterpret_cast<uint16_t*>(T);
+    uint16_t* dist_fast = reinterpret_cast<uint16_t*>(T + SI_OFF_DFAST);
+    uint16_t* lit_count = reinterpret_cast<uint16_t*>(T + SI_OFF_LCNT);
+    uint16_t* dist_count = reinterpret_cast<uint16_t*>(T + SI_OFF_DCNT);
+    uint16_t lit_sym[288], dist_sym[32];
+    uint8_t lens[320];
+
+    const BgzfBlock blk = blocks[b];
+    uint8_t* dst = out + blk.out_off;
+    const uint32_t cap = blk.out_len;
+    uint32_t opos = 0, err = 0;
+    BitReader br;
+    br.init(comp + blk.in_off);
+
+    for (bool last = false; !last && !err;) {
+        const uint32_t hdr = br.get(3);
+        last = hdr & 1u;
+        const uint32_t btype = hdr >> 1;
+        if (btype == 0) {
+            br.drop(br.nb & 7);
+            const uint32_t l = br.get(16), nl = br.get(16);
+            if ((l ^ nl) != 0xffffu || opos + l > cap) { err = 2; break; }
+            const uint8_t* src = br.byte_ptr();
+            for (uint32_t i = 0; i < l; ++i) dst[opos + i] = __ldg(src + i);
+            opos += l;
+            br.init(src + l);
+            continue;
+        }
+        if (btype == 3) { err = 3; break; }
+        if (btype == 1) {
+            for (int i = 0; i < 288; ++i) lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+            for (int i = 0; i < 30; ++i) lens[288 + i] = 5;
+        } else {
+            const int hlit = (int)br.get(5) + 257, hdist = (int)br.get(5) + 1, hclen = (int)br.get(4) + 4;
+            if (hlit > 286 || hdist > 30) { err = 4; break; }
+            // the code-length code: lengths packed 4 bits each in a 76-bit register pair, canonical decode by counts
+            uint8_t cl[19];
+#pragma unroll
+            for (int i = 0; i < 19; ++i) cl[i] = 0;
+            for (int i = 0; i < hclen; ++i) cl[c_clen_order[i]] = (uint8_t)br.get(3);
+            uint16_t ccount[8], csym[19], coffs[8];
+            for (int i = 0; i < 8; ++i) ccount[i] = 0;
+            for (int i = 0; i < 19; ++i) ccount[cl[i]]++;
+            coffs[1] = 0;
+            for (int l = 1; l < 7; ++l) coffs[l + 1] = coffs[l] + ccount[l];
+            for (int i = 0; i < 19; ++i) if (cl[i]) csym[coffs[cl[i]]++] = (uint16_t)i;
+            int idx = 0;
+            while (idx < hlit + hdist && !err) {
+                int code = 0, first = 0, index = 0, symv = -1;
+                for (int l = 1; l <= 7; ++l) {
+                    code |= (int)br.get(1);
+                    const int c = ccount[l];
+                    if (code - c < first) { symv = csym[index + (code - first)]; break; }
+                    index += c; first += c; first <<= 1; code <<= 1;
+                }
+                if (symv < 0) { err = 5; break; }
+                if (symv < 16) lens[idx++] = (uint8_t)symv;
+                else {
+                    int rep, val = 0;
+                    if (symv == 16) { if (idx == 0) { err = 6; break; } val = lens[idx - 1]; rep = 3 + (int)br.get(2); }
+                    else if (symv == 17) rep = 3 + (int)br.get(3);
+                    else rep = 11 + (int)br.get(7);
+                    if (idx + rep > hlit + hdist) { err = 7; break; }
+                    while (rep--) lens[idx++] = (uint8_t)val;
+                }
+            }
+            if (err) break;
+            if (lens[256] == 0) { err = 8; break; }
+            // distance lengths to their fixed place (288..317); iterate downwards: the ranges may overlap
+            for (int i = hdist - 1; i >= 0; --i) lens[288 + i] = lens[hlit + i];
+            for (int i = hlit; i < 288; ++i) lens[i] = 0;
+            for (int i = hdist; i < 30; ++i) lens[288 + i] = 0;
+        }
+        if (!si_build(lens, 288, lit_count, lit_sym, lit_fast, SI_LIT_BITS)) { err = 9; break; }
+        if (!si_build(lens + 288, 30, dist_count, dist_sym, dist_fast, SI_DIST_BITS)) { err = 10; break; }
+
+        for (;;) {
+            br.need(32);
+            int sym;
+            uint32_t e = lit_fast[br.peek(SI_LIT_BITS)];
+            if (e) { br.drop(e & 15); sym = (int)(e >> 4); }
+            else { sym = slow_decode(br, lit_count, lit_sym); if (sym < 0) { err = 11; break; } }
+            if (sym < 256) {
+                if (opos >= cap) { err = 15; break; }
+                dst[opos++] = (uint8_t)sym;
+                continue;
+            }
+            if (sym == 256) break;
+            sym -= 257;
+            if (sym >= 29) { err = 12; break; }
+            br.need(32);
+            const uint32_t len = c_len_base[sym] + br.get(c_len_extra[sym]);
+            br.need(32);
+            int ds;
+            e = dist_fast[br.peek(SI_DIST_BITS)];
+            if (e) { br.drop(e & 15); ds = (int)(e >> 4); }
+            else { ds = slow_decode(br, dist_count, dist_sym); if (ds < 0) { err = 13; break; } }
+            if (ds >= 30) { err = 14; break; }
+            br.need(32);
+            const uint32_t dist = c_dist_base[ds] + br.get(c_dist_extra[ds]);
+            if (dist > opos) { err = 16; break; }
+            if (opos + len > cap) { err = 15; break; }
+            const uint8_t* srcp = dst + opos - dist;
+            uint8_t* d = dst + opos;
+            if (dist >= len) {                       // no overlap: loads first, then stores (4-way ILP)
+                uint32_t k = 0;
+                for (; k + 4 <= len; k += 4) {
+                    const uint8_t a0 = srcp[k], a1 = srcp[k + 1], a2 = srcp[k + 2], a3 = srcp[k + 3];
+                    d[k] = a0; d[k + 1] = a1; d[k + 2] = a2; d[k + 3] = a3;
+                }
+                for (; k < len; ++k) d[k] = srcp[k];
+            } else {
+                for (uint32_t k = 0; k < len; ++k) d[k] = *(volatile const uint8_t*)(srcp + k);   // run: each byte may depend on the previous store
+            }
+            opos += len;
+        }
+    }
+    if (!err && opos != cap) err = 17;
+    status[b] = err;
 }
 
 __global__ void inflate_status_reduce_kernel(const uint32_t* __restrict__ status, uint32_t n, uint32_t* __restrict__ flags) {
@@ -311,6 +550,15 @@ void launch_inflate_status_reduce(const uint32_t* status, uint32_t n_blocks, uin
 void launch_bgzf_inflate(const uint8_t* comp, const void* blocks, uint32_t n_blocks, uint8_t* out, uint32_t* status,
                          cudaStream_t stream) {
     if (n_blocks == 0) return;
+    static int mode = -1;                                  // RTJX_INFLATE_VARIANT: 0 auto, 1 warp per block, 2 thread per block
+    if (mode < 0) { const char* v = getenv("RTJX_INFLATE_VARIANT"); mode = v ? atoi(v) : 0; }
+    if (mode == 2) {        // thread-per-block only pays with >~100k blocks in one launch; opt-in for now
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(bgzf_inflate_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_THREADS * SI_STRIDE); attr = true; }
+        bgzf_inflate_simt_kernel<<<(n_blocks + SI_THREADS - 1) / SI_THREADS, SI_THREADS, SI_THREADS * SI_STRIDE, stream>>>(
+            comp, static_cast<const BgzfBlock*>(blocks), n_blocks, out, status);
+        return;
+    }
     const uint32_t grid = (n_blocks + INF_WARPS - 1) / INF_WARPS;
     bgzf_inflate_kernel<<<grid, INF_WARPS * 32, 0, stream>>>(comp, static_cast<const BgzfBlock*>(blocks), n_blocks, out, status);
 }

@@ -110,7 +110,7 @@ void launch_record_gather(const uint8_t* data, const int32_t* rec_off, const uin
                           uint32_t* ncig, uint32_t* ncig_scan, void* ws, size_t ws_bytes, cudaStream_t stream);
 void launch_record_extract(const uint8_t* data, const int32_t* dense, const uint32_t* ncig_scan, uint32_t cap_total,
                            FeedState* state, int32_t n_ref, int xs_mode, uint32_t tag0, uint32_t tag1, int32_t* o_tid,
-                           int32_t* o_pos, uint32_t* o_meta, uint32_t* o_off, uint32_t* o_cigar, cudaStream_t stream);
+                           int32_t* o_pos, uint32_t* o_meta, uint32_t* o_off, uint32_t* o_cigar, uint32_t cigar_cap, cudaStream_t stream);
 void launch_feed_finish(const uint8_t* data, int64_t data_len, uint8_t* next_data, uint32_t headroom, const uint32_t* seg_scan,
                         uint32_t n_seg, const uint32_t* ncig_scan, FeedState* state, cudaStream_t stream);
 
