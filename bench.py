@@ -13,8 +13,10 @@ One "step" = one pass of the hot path over the whole workload.
           finalize (compaction, first-seen ranking, sort) + D2H of the junction table
           [+ all-gather for N > 1]; CUDA events on the launching stream, max over ranks.
   e2e   : reads/s through the public call (JunctionsExtractor.identify_junctions_from_BAM +
-          print_all_junctions, i.e. rtjx_run + rtjx_write_bed12): BGZF inflate on the host cores,
-          pinned H2D copies, kernels, BED12 file written — wall clock, everything inside.
+          print_all_junctions, i.e. rtjx_run + rtjx_write_bed12) on the BAM FILE (host buffers: page
+          cache): compressed bytes staged through pinned memory and copied H2D, BGZF inflate + BAM
+          record split + CIGAR scan + merge on the GPU, junction table D2H, BED12 file written —
+          wall clock, everything inside, a fresh handle per step.
   roofline : cigar_scan kernel, algorithmic bytes 16*R + 4*C over its CUDA-event duration.
   cpu_baseline : the UNMODIFIED reference (oracle/_ref/regtools_ref, built by oracle/Makefile)
           timed on the host cores on a bounded region sample of the same BAM.
@@ -326,9 +328,12 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1000.0 * float(e2e_t.item()), "steps": e2e_steps,
-                "region": "rtjx_run (BGZF inflate on host threads + pinned H2D + kernels) + BED12 file write",
-                "host_inflate_cpu_s": feeder["host_inflate_s"], "host_parse_s": feeder["host_parse_s"],
-                "feeder_wait_s": feeder["host_wait_s"]},
+                "region": "fresh handle + rtjx_run (BAM file -> pinned staging -> H2D of compressed bytes -> device BGZF inflate "
+                          "+ record split + cigar_scan + junction_merge) + finalize + BED12 file write",
+                "feeder": "device" if feeder["host_parse_s"] == 0.0 and feeder["inflated_bytes"] else "host",
+                "compressed_bytes": int(feeder["compressed_bytes"]), "inflated_bytes": int(feeder["inflated_bytes"]),
+                "host_staging_s": feeder["host_inflate_s"], "host_parse_s": feeder["host_parse_s"],
+                "gpu_wait_s": feeder["host_wait_s"], "gpu_launches": int(feeder["kernel_launches"])},
         "gpu_launches": int(round(launches_resident * args.steps)),
         "roofline": {"bound": "hbm", "kernel": "cigar_scan_small_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,

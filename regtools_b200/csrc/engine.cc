@@ -55,7 +55,7 @@ Engine::~Engine() {
             if (d.free_ev) cudaEventDestroy(d.free_ev);
         }
         cached_dev_free(d_counters_); cached_host_free(h_counters_);
-        cached_dev_free(d_table_); cached_dev_free(d_spill_); cached_dev_free(d_cands_);
+        cached_dev_free(d_table_); cached_dev_free(d_spill_); cached_dev_free(d_cands_); cached_dev_free(d_tile_off_);
         cached_dev_free(d_out_); cached_dev_free(d_ws_); cached_dev_free(d_rank_); cached_host_free(h_final_); cached_dev_free(d_slot_list_);
         if (stream_) cudaStreamDestroy(stream_);
         if (copy_stream_) cudaStreamDestroy(copy_stream_);
@@ -164,7 +164,16 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
     CK(cudaMemsetAsync(d_counters_ + CTR_NCAND, 0, sizeof(uint32_t), stream));
     ProfEv pe{nullptr, nullptr, nullptr};
     if (prm_.profile) { pe.a = get_event(); pe.b = get_event(); pe.c = get_event(); cudaEventRecord(pe.a, stream); }
-    launch_cigar_scan(v, scan_params(), d_cands_, cand_cap_, d_counters_, stream);
+    {
+        const uint32_t need = cigar_scan_tiles(v.n_reads) + 2;
+        if (need > tile_off_cap_) {
+            CK(cudaStreamSynchronize(stream));
+            cached_dev_free(d_tile_off_); d_tile_off_ = nullptr;
+            tile_off_cap_ = need + need / 4 + 1024;
+            CK(cached_dev_malloc(&d_tile_off_, (size_t)tile_off_cap_ * 4));
+        }
+    }
+    launch_cigar_scan(v, scan_params(), d_cands_, cand_cap_, d_counters_, d_tile_off_, stream);
     if (prm_.profile) cudaEventRecord(pe.b, stream);
     if (!known) {
         if ((rc = sync_counters(stream))) return rc;     // also tightens unique_upper_
@@ -175,7 +184,7 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
                           d_spill_, spill_cap_, d_counters_, stream);
     if (prm_.profile) { cudaEventRecord(pe.c, stream); prof_pending_.push_back(pe); }
     CK(cudaGetLastError());
-    stats_.kernel_launches += (v.n_reads ? 1 : 0) + (cand_bound ? 1 : 0);
+    stats_.kernel_launches += (v.n_reads ? 2 : 0) + (cand_bound ? 1 : 0);   // tile-offset pre-pass + cigar_scan, junction_merge
     stats_.reads += v.n_reads; stats_.cigar_ops += v.n_ops; stats_.batches++;
     dirty_ = true; finalized_ = false;
     if (prof_pending_.size() > 4096) resolve_profile_events();

@@ -69,8 +69,10 @@ struct TableRef {
 };
 
 // Launchers (kernels.cu).  All are asynchronous on `stream`.
+// tile_off_scratch: cigar_scan_tiles(n_reads) + 1 words of device scratch for the per-tile CIGAR offsets (may be NULL)
+uint32_t cigar_scan_tiles(uint32_t n_reads);
 void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
-                       uint32_t* d_counters /* [0]=n_cand, [1]=overflowed */, cudaStream_t stream);
+                       uint32_t* d_counters /* [0]=n_cand, [1]=overflowed */, uint32_t* tile_off_scratch, cudaStream_t stream);
 void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound,
                            const ScanParams& p, const TableRef& tb, Slot* spill, uint32_t spill_cap,
                            uint32_t* d_counters /* [2]=n_unique,[3]=n_spill */, cudaStream_t stream);

@@ -336,14 +336,15 @@ __device__ __forceinline__ void walk_fast(const uint32_t* __restrict__ ops, uint
     const uint32_t ANC = (1u << 0) | (1u << 7);
     const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
     const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
-    uint32_t w[8];
+    constexpr int PRE = 4;                        // ops preloaded by independent loads (covers 50M100N50M, 5S45M100N50M, ...)
+    uint32_t w[PRE];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) w[i] = (uint32_t)i < n ? (FROM_SMEM ? ops[i] : __ldg(ops + i)) : 0xfu;
+    for (int i = 0; i < PRE; ++i) w[i] = (uint32_t)i < n ? (FROM_SMEM ? ops[i] : __ldg(ops + i)) : 0xfu;
     uint32_t cur = pos, run = 0;
     bool pending = false;
     uint32_t p_start = 0, p_end = 0, p_left = 0, p_k = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < PRE; ++i) {
         const uint32_t op = w[i] & 0xfu, len = w[i] >> 4, bit = 1u << op;
         const bool brk = (bit & BRK) != 0, is_n = op == 3u;
         if (pending && brk) emit(p_start, p_end, p_left, run, read_ord << 16 | p_k, tid, strand);
@@ -352,7 +353,7 @@ __device__ __forceinline__ void walk_fast(const uint32_t* __restrict__ ops, uint
         run = brk ? 0u : run + ((bit & ANC) ? len : 0u);
         cur += (bit & REFC) ? len : 0u;
     }
-    for (uint32_t i = 8; i < n; ++i) {
+    for (uint32_t i = PRE; i < n; ++i) {
         const uint32_t x = FROM_SMEM ? ops[i] : __ldg(ops + i);
         const uint32_t op = x & 0xfu, len = x >> 4, bit = 1u << op;
         const bool brk = (bit & BRK) != 0, is_n = op == 3u;
@@ -605,7 +606,8 @@ struct S5Emit {
 };
 
 __global__ void __launch_bounds__(S5_THREADS, 12)
-cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
+cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters,
+                        const uint32_t* __restrict__ tile_off) {
     __shared__ S5Smem sm;
     const uint32_t t = threadIdx.x, lane = t & 31u;
     const uint32_t base = blockIdx.x * S5_TILE;
@@ -627,17 +629,20 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
     }
     if (t == 0) { sm.n_work = 0; sm.n_out = 0; }
     cp_async_commit();
-    cp_async_wait_all();
-    __syncthreads();
-
-    // ---- CIGAR slab of the tile (data-dependent address): issue, then compact while it is in flight
-    const uint32_t lo = sm.off[0], hi = sm.off[n_tile];
+    // ---- CIGAR slab of the tile.  Its address depends on cig_off; the per-tile offsets gathered by the pre-pass
+    // (tile_offsets_kernel, L2-resident) let the slab request go out together with the metadata instead of one
+    // DRAM round trip later.
+    uint32_t lo, hi;
+    if (tile_off) { lo = __ldg(tile_off + blockIdx.x); hi = __ldg(tile_off + blockIdx.x + 1); }
+    else { cp_async_wait_all(); __syncthreads(); lo = sm.off[0]; hi = sm.off[n_tile]; }
     const uint32_t a0 = lo & ~3u, end4 = (hi + 3u) & ~3u;
     const bool direct = hi > lo && (end4 - a0 > (uint32_t)S5_SLAB || end4 > (b.n_ops & ~3u));
     if (!direct && hi > lo) {
         const uint32_t n_vec = (end4 - a0) >> 2;
         for (uint32_t v = t; v < n_vec; v += S5_THREADS) cp_async16(&sm.slab[4 * v], b.cigar + a0 + 4 * v);
     }
+    cp_async_commit();
+    if (tile_off) { cp_async_wait_all(); __syncthreads(); }
     cp_async_commit();
     {
         const uint4 o = *reinterpret_cast<const uint4*>(&sm.off[4 * t]);
@@ -702,8 +707,15 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
     }
 }
 
+// pre-pass: tile_off[t] = cig_off[min(t * S5_TILE, n_reads)] (one 4-byte load per tile; the result stays in L2)
+__global__ void tile_offsets_kernel(const uint32_t* __restrict__ cig_off, uint32_t n_reads, uint32_t n_tiles, uint32_t* __restrict__ tile_off) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t <= n_tiles) tile_off[t] = cig_off[min(t * (uint32_t)S5_TILE, n_reads)];
+}
+uint32_t cigar_scan_tiles(uint32_t n_reads) { return (n_reads + S5_TILE - 1) / S5_TILE; }
+
 void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
-                       uint32_t* d_counters, cudaStream_t stream) {
+                       uint32_t* d_counters, uint32_t* tile_off_scratch, cudaStream_t stream) {
     if (b.n_reads == 0) return;
     const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
                             reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
@@ -712,7 +724,14 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
     if (variant < 0) { const char* v = getenv("RTJX_SCAN_VARIANT"); variant = v ? atoi(v) : 5; }
     if ((align & 15u) == 0 && variant == 5) {
         const uint32_t tiles = (b.n_reads + S5_TILE - 1) / S5_TILE;
-        cigar_scan_small_kernel<<<tiles, S5_THREADS, 0, stream>>>(b, p, cands, cand_cap, d_counters);
+        static int prepass = -1;
+        if (prepass < 0) { const char* v = getenv("RTJX_SCAN_PREPASS"); prepass = v ? atoi(v) : 0; }   // measured: no gain on B200 (the block scheduler already overlaps the two round trips)
+        const uint32_t* toff = nullptr;
+        if (prepass && tile_off_scratch && tiles >= 64) {
+            tile_offsets_kernel<<<(tiles + 1 + 255) / 256, 256, 0, stream>>>(b.cig_off, b.n_reads, tiles, tile_off_scratch);
+            toff = tile_off_scratch;
+        }
+        cigar_scan_small_kernel<<<tiles, S5_THREADS, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff);
         return;
     }
     if ((align & 15u) == 0 && variant == 4) {
