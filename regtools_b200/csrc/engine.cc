@@ -55,7 +55,7 @@ Engine::~Engine() {
             if (d.free_ev) cudaEventDestroy(d.free_ev);
         }
         cached_dev_free(d_counters_); cached_host_free(h_counters_);
-        cached_dev_free(d_table_); cached_dev_free(d_spill_); cached_dev_free(d_cands_); cached_dev_free(d_tile_off_);
+        cached_dev_free(d_table_); cached_dev_free(d_spill_); cached_dev_free(d_cands_); cached_dev_free(d_tile_off_); cached_dev_free(d_regions_); cached_dev_free(d_region_cnt_);
         cached_dev_free(d_out_); cached_dev_free(d_ws_); cached_dev_free(d_rank_); cached_host_free(h_final_); cached_dev_free(d_slot_list_);
         if (stream_) cudaStreamDestroy(stream_);
         if (copy_stream_) cudaStreamDestroy(copy_stream_);
@@ -162,6 +162,7 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
     if ((rc = ensure_cands(known ? cand_bound : std::max(v.n_ops, 1u)))) return rc;
     if (known && (rc = ensure_table(cand_bound, stream))) return rc;
     CK(cudaMemsetAsync(d_counters_ + CTR_NCAND, 0, sizeof(uint32_t), stream));
+    CK(cudaMemsetAsync(d_counters_ + CTR_NREGION, 0, sizeof(uint32_t), stream));
     ProfEv pe{nullptr, nullptr, nullptr};
     if (prm_.profile) { pe.a = get_event(); pe.b = get_event(); pe.c = get_event(); cudaEventRecord(pe.a, stream); }
     {
@@ -173,14 +174,29 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
             CK(cached_dev_malloc(&d_tile_off_, (size_t)tile_off_cap_ * 4));
         }
     }
-    launch_cigar_scan(v, scan_params(), d_cands_, cand_cap_, d_counters_, d_tile_off_, stream);
+    CandRegions rgn{nullptr, nullptr, 0, 0};
+    {
+        uint32_t nr = 0, rcap = 0;
+        cigar_scan_region_layout(v.n_reads, &nr, &rcap);
+        if (nr) {
+            if ((size_t)nr * rcap > regions_cap_ || nr > region_cnt_cap_) {
+                CK(cudaStreamSynchronize(stream));
+                cached_dev_free(d_regions_); cached_dev_free(d_region_cnt_); d_regions_ = nullptr; d_region_cnt_ = nullptr;
+                regions_cap_ = (size_t)nr * rcap + (size_t)nr * rcap / 8; region_cnt_cap_ = nr + nr / 8 + 64;
+                CK(cached_dev_malloc(&d_regions_, regions_cap_ * sizeof(Cand)));
+                CK(cached_dev_malloc(&d_region_cnt_, region_cnt_cap_ * sizeof(uint32_t)));
+            }
+            rgn = CandRegions{d_regions_, d_region_cnt_, nr, rcap};
+        }
+    }
+    launch_cigar_scan(v, scan_params(), d_cands_, cand_cap_, d_counters_, d_tile_off_, rgn, stream);
     if (prm_.profile) cudaEventRecord(pe.b, stream);
     if (!known) {
         if ((rc = sync_counters(stream))) return rc;     // also tightens unique_upper_
-        cand_bound = h_counters_[CTR_NCAND];
+        cand_bound = h_counters_[CTR_NCAND] + h_counters_[CTR_NREGION];
         if ((rc = ensure_table(std::max(cand_bound, 1u), stream))) return rc;
     }
-    launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, cand_bound, scan_params(), table_ref(),
+    launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, cand_bound, rgn, scan_params(), table_ref(),
                           d_spill_, spill_cap_, d_counters_, stream);
     if (prm_.profile) { cudaEventRecord(pe.c, stream); prof_pending_.push_back(pe); }
     CK(cudaGetLastError());
@@ -273,7 +289,7 @@ int Engine::add(const rtjx_candidate* c, size_t n) {
         if ((rc = ensure_cands((uint32_t)m))) return rc;
         if ((rc = ensure_table((uint32_t)m, stream_))) return rc;
         CK(cudaMemcpyAsync(d_cands_, h.data(), m * sizeof(Cand), cudaMemcpyHostToDevice, stream_));
-        launch_junction_merge(d_cands_, nullptr, (uint32_t)m, scan_params(), table_ref(), d_spill_, spill_cap_,
+        launch_junction_merge(d_cands_, nullptr, (uint32_t)m, CandRegions{nullptr, nullptr, 0, 0}, scan_params(), table_ref(), d_spill_, spill_cap_,
                               d_counters_, stream_);
         CK(cudaStreamSynchronize(stream_));
         add_ord_ += m; stats_.kernel_launches++; stats_.h2d_bytes += m * sizeof(Cand);

@@ -60,6 +60,18 @@ struct BatchView {
     const uint32_t* cigar;
 };
 
+// Per-tile candidate regions: cigar_scan writes the first round of every tile into a fixed region of
+// `cap` candidates (no global reservation, so the block never waits for an atomic round trip); later rounds
+// of dense tiles and staging overflow go to the dense overflow list.  junction_merge reads both.
+struct CandRegions {
+    Cand*     base;               // n_regions * cap candidates; NULL = regions not in use
+    uint32_t* cnt;                // candidates stored in each region
+    uint32_t  n_regions;
+    uint32_t  cap;
+};
+// Layout the scan kernel will use for a batch of n_reads alignments (n_regions = number of tiles).
+void cigar_scan_region_layout(uint32_t n_reads, uint32_t* n_regions, uint32_t* cap);
+
 // The device-wide junction table as the kernels see it.
 struct TableRef {
     Slot*     slots;
@@ -72,8 +84,9 @@ struct TableRef {
 // tile_off_scratch: cigar_scan_tiles(n_reads) + 1 words of device scratch for the per-tile CIGAR offsets (may be NULL)
 uint32_t cigar_scan_tiles(uint32_t n_reads);
 void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
-                       uint32_t* d_counters /* [0]=n_cand, [1]=overflowed */, uint32_t* tile_off_scratch, cudaStream_t stream);
-void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound,
+                       uint32_t* d_counters /* [0]=n_cand, [1]=overflowed */, uint32_t* tile_off_scratch,
+                       const CandRegions& regions, cudaStream_t stream);
+void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound, const CandRegions& regions,
                            const ScanParams& p, const TableRef& tb, Slot* spill, uint32_t spill_cap,
                            uint32_t* d_counters /* [2]=n_unique,[3]=n_spill */, cudaStream_t stream);
 void launch_table_rehash(const Slot* old_table, uint32_t old_slots, const TableRef& tb, uint32_t* d_counters,
@@ -117,7 +130,7 @@ void launch_feed_finish(const uint8_t* data, int64_t data_len, uint8_t* next_dat
                         uint32_t n_seg, const uint32_t* ncig_scan, FeedState* state, cudaStream_t stream);
 
 // counters layout in d_counters (uint32 each)
-enum { CTR_NCAND = 0, CTR_CAND_OVERFLOW = 1, CTR_NUNIQUE = 2, CTR_NSPILL = 3, CTR_NOUT = 4,
+enum { CTR_NCAND = 0, CTR_CAND_OVERFLOW = 1, CTR_NUNIQUE = 2, CTR_NSPILL = 3, CTR_NOUT = 4, CTR_NREGION = 5 /* candidates in regions */,
        CTR_TOTAL_CAND64 = 6 /* 64-bit, two words */, CTR_COUNT = 8 };
 
 }  // namespace rtjx

@@ -561,12 +561,11 @@ cigar_scan_ws_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32
 // blocks are resident per SM and the hardware block scheduler overlaps their phases, so while some
 // blocks wait for their (data-dependent) CIGAR slab others are streaming metadata or walking.
 // Columns and slab go global -> shared with 16-byte cp.async (LDGSTS), no register staging.
-constexpr int S5_THREADS = 128;
-constexpr int S5_TILE    = 512;
-constexpr int S5_SLAB    = 1024;                 // CIGAR words staged per tile (4 KB)
-constexpr int S5_OUT     = 192;                  // staged candidates (6 KB)
-
-struct alignas(16) S5Smem {
+// Template parameters: threads per block (tile = 4 alignments per thread), CIGAR words staged per tile,
+// candidates staged per tile.  The default instantiation is <128, 1024, 192>: 512-alignment tiles, 19.5 KB.
+template <int S5_THREADS, int S5_SLAB, int S5_OUT>
+struct alignas(16) S5SmemT {
+    static constexpr int S5_TILE = S5_THREADS * 4;
     uint32_t off[S5_TILE + 4];
     uint32_t pos[S5_TILE];
     uint32_t meta[S5_TILE];
@@ -583,12 +582,14 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+template <class Smem, int S5_OUT>
 struct S5Emit {
-    S5Smem& sm; Cand* __restrict__ out; uint32_t cap; uint32_t* counters;
+    Smem& sm; Cand* __restrict__ out; uint32_t cap; uint32_t* counters; uint32_t dbg;
     __device__ __forceinline__ void operator()(uint32_t start, uint32_t end, uint32_t left, uint32_t right,
                                                uint64_t ord, int32_t tid, uint32_t strand) const {
         uint4 a = make_uint4(start, end, start - left, end + right);
         uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
+        if (dbg & 4u) { if ((a.x ^ a.y ^ a.z ^ a.w ^ b.x) == 0x9e3779b9u) sm.n_out = 1; return; }
         const uint32_t mask = __activemask();
         const uint32_t lane = threadIdx.x & 31u;
         const int leader = __ffs(mask) - 1;
@@ -605,10 +606,13 @@ struct S5Emit {
     }
 };
 
-__global__ void __launch_bounds__(S5_THREADS, 12)
+template <int S5_THREADS, int S5_SLAB, int S5_OUT>
+__global__ void __launch_bounds__(S5_THREADS)
 cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters,
-                        const uint32_t* __restrict__ tile_off) {
-    __shared__ S5Smem sm;
+                        const uint32_t* __restrict__ tile_off, CandRegions rg) {
+    using Smem = S5SmemT<S5_THREADS, S5_SLAB, S5_OUT>;
+    constexpr int S5_TILE = Smem::S5_TILE;
+    __shared__ Smem sm;
     const uint32_t t = threadIdx.x, lane = t & 31u;
     const uint32_t base = blockIdx.x * S5_TILE;
     const uint32_t n_tile = min((uint32_t)S5_TILE, b.n_reads - base);
@@ -671,9 +675,9 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
 
     // ---- walk the compacted alignments, one per thread, in rounds of 128
     const uint32_t n_work = (prm.debug & 1u) ? 0u : sm.n_work;
-    const S5Emit emit{sm, out, cap, counters};
+    const S5Emit<Smem, S5_OUT> emit{sm, out, cap, counters, prm.debug};
     auto flush = [&]() {                                        // warp 0
-        const uint32_t n_st = min(sm.n_out, (uint32_t)S5_OUT);
+        const uint32_t n_st = (prm.debug & 8u) ? 0u : min(sm.n_out, (uint32_t)S5_OUT);
         __syncwarp();
         if (n_st) {
             uint32_t fb = 0;
@@ -702,36 +706,70 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
             }
         }
         __syncthreads();
-        if (t < 32) flush();
-        if (w0 + S5_THREADS < n_work) __syncthreads();
+        if (w0 == 0 && rg.base && !(prm.debug & 8u)) {
+            // first round -> this tile's own region: plain stores by every thread, nobody waits for an atomic
+            const uint32_t n_st = min(sm.n_out, (uint32_t)S5_OUT);
+            uint4* o = reinterpret_cast<uint4*>(rg.base + (size_t)blockIdx.x * rg.cap);
+            for (uint32_t v = t; v < 2 * n_st; v += S5_THREADS) o[v] = sm.out[v];
+            if (t == 0) { rg.cnt[blockIdx.x] = n_st; if (n_st) atomicAdd(&counters[CTR_NREGION], n_st); }   // no return value used: a RED, nobody waits
+            if (w0 + S5_THREADS < n_work) { __syncthreads(); if (t == 0) sm.n_out = 0; __syncthreads(); }
+        } else {
+            if (t < 32) flush();
+            if (w0 + S5_THREADS < n_work) __syncthreads();
+        }
     }
+    if (n_work == 0 && rg.base && t == 0) rg.cnt[blockIdx.x] = 0;
 }
 
 // pre-pass: tile_off[t] = cig_off[min(t * S5_TILE, n_reads)] (one 4-byte load per tile; the result stays in L2)
-__global__ void tile_offsets_kernel(const uint32_t* __restrict__ cig_off, uint32_t n_reads, uint32_t n_tiles, uint32_t* __restrict__ tile_off) {
+__global__ void tile_offsets_kernel(const uint32_t* __restrict__ cig_off, uint32_t n_reads, uint32_t n_tiles, uint32_t tile, uint32_t* __restrict__ tile_off) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t <= n_tiles) tile_off[t] = cig_off[min(t * (uint32_t)S5_TILE, n_reads)];
+    if (t <= n_tiles) tile_off[t] = cig_off[min(t * tile, n_reads)];
 }
-uint32_t cigar_scan_tiles(uint32_t n_reads) { return (n_reads + S5_TILE - 1) / S5_TILE; }
+uint32_t cigar_scan_tiles(uint32_t n_reads) { return (n_reads + 255) / 256; }   // upper bound over the tile sizes in use
+static int scan_variant() {
+    static int variant = -1;
+    if (variant < 0) { const char* v = getenv("RTJX_SCAN_VARIANT"); variant = v ? atoi(v) : 5; }
+    return variant;
+}
+static int scan_cfg() {
+    static int cfg = -1;
+    if (cfg < 0) { const char* v = getenv("RTJX_SCAN_CFG"); cfg = v ? atoi(v) : 0; }
+    return cfg;
+}
+void cigar_scan_region_layout(uint32_t n_reads, uint32_t* n_regions, uint32_t* cap) {
+    static int use = -1;
+    if (use < 0) { const char* v = getenv("RTJX_SCAN_REGIONS"); use = v ? atoi(v) : 0; }   // measured: no gain (A/B option)
+    if (use && scan_variant() == 5 && scan_cfg() == 0) { *n_regions = (n_reads + 511) / 512; *cap = 192; }
+    else { *n_regions = 0; *cap = 0; }
+}
 
 void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
-                       uint32_t* d_counters, uint32_t* tile_off_scratch, cudaStream_t stream) {
+                       uint32_t* d_counters, uint32_t* tile_off_scratch, const CandRegions& regions, cudaStream_t stream) {
     if (b.n_reads == 0) return;
     const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
                             reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
                             reinterpret_cast<uintptr_t>(b.cigar);
-    static int variant = -1;
-    if (variant < 0) { const char* v = getenv("RTJX_SCAN_VARIANT"); variant = v ? atoi(v) : 5; }
+    const int variant = scan_variant();
     if ((align & 15u) == 0 && variant == 5) {
-        const uint32_t tiles = (b.n_reads + S5_TILE - 1) / S5_TILE;
         static int prepass = -1;
-        if (prepass < 0) { const char* v = getenv("RTJX_SCAN_PREPASS"); prepass = v ? atoi(v) : 0; }   // measured: no gain on B200 (the block scheduler already overlaps the two round trips)
+        const int cfg = scan_cfg();
+        if (prepass < 0) { const char* v = getenv("RTJX_SCAN_PREPASS"); prepass = v ? atoi(v) : 0; }   // measured: no gain on B200
+        const uint32_t threads = cfg == 2 ? 64u : cfg == 3 ? 256u : 128u;
+        const uint32_t tile = threads * 4, tiles = (b.n_reads + tile - 1) / tile;
         const uint32_t* toff = nullptr;
         if (prepass && tile_off_scratch && tiles >= 64) {
-            tile_offsets_kernel<<<(tiles + 1 + 255) / 256, 256, 0, stream>>>(b.cig_off, b.n_reads, tiles, tile_off_scratch);
+            tile_offsets_kernel<<<(tiles + 1 + 255) / 256, 256, 0, stream>>>(b.cig_off, b.n_reads, tiles, tile, tile_off_scratch);
             toff = tile_off_scratch;
         }
-        cigar_scan_small_kernel<<<tiles, S5_THREADS, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff);
+        CandRegions none{nullptr, nullptr, 0, 0};
+        switch (cfg) {          // A/B configurations (RTJX_SCAN_CFG); 0 is the production one
+        case 1: cigar_scan_small_kernel<128, 768, 128><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
+        case 2: cigar_scan_small_kernel<64, 512, 96><<<tiles, 64, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
+        case 3: cigar_scan_small_kernel<256, 2048, 384><<<tiles, 256, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
+        case 4: cigar_scan_small_kernel<128, 1024, 96><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
+        default: cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions); break;
+        }
         return;
     }
     if ((align & 15u) == 0 && variant == 4) {
@@ -807,6 +845,7 @@ constexpr int MERGE_TILE    = MERGE_THREADS * MERGE_CPT;     // 2048 candidates
 constexpr int MERGE_SLOTS   = 2048;                          // shared-memory hash slots (power of 2)
 constexpr int MERGE_PROBES  = 32;
 constexpr unsigned long long SKEY_EMPTY = ~0ull;
+constexpr int MERGE_RGROUP = 32;                            // scan tiles (candidate regions) per merge tile
 
 struct MergeSmem {
     unsigned long long key[MERGE_SLOTS];
@@ -814,94 +853,126 @@ struct MergeSmem {
     unsigned long long last[MERGE_SLOTS];
     uint32_t count[MERGE_SLOTS], nts[MERGE_SLOTS], te[MERGE_SLOTS], lr[MERGE_SLOTS];
     int32_t base_tid;
+    uint32_t rpre[MERGE_RGROUP + 1];             // prefix of the region counts of a region tile
 };
 
 __global__ void __launch_bounds__(MERGE_THREADS, 2)
-junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict__ d_n_cand, uint32_t n_bound,
+junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict__ d_n_cand, uint32_t n_bound, CandRegions rg,
                       ScanParams prm, TableRef tb, Slot* __restrict__ spill, uint32_t spill_cap,
                       uint32_t* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MergeSmem& sm = *reinterpret_cast<MergeSmem*>(smem_raw);
     const uint32_t t = threadIdx.x;
-    uint32_t n = d_n_cand ? min(*d_n_cand, n_bound) : n_bound;
-    const uint32_t n_tiles = (n + MERGE_TILE - 1) / MERGE_TILE;
+    const uint32_t n = d_n_cand ? min(*d_n_cand, n_bound) : n_bound;
+    const uint32_t n_otiles = (n + MERGE_TILE - 1) / MERGE_TILE;                                   // dense overflow list
+    const uint32_t n_rtiles = rg.base ? (rg.n_regions + MERGE_RGROUP - 1) / MERGE_RGROUP : 0u;     // per-tile regions
     if (blockIdx.x == 0 && t == 0)
         atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_TOTAL_CAND64), (unsigned long long)n);
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t tb0 = tile * MERGE_TILE;
-        for (uint32_t s = t; s < MERGE_SLOTS; s += MERGE_THREADS) {
-            sm.key[s] = SKEY_EMPTY; sm.nfirst[s] = 0ull; sm.last[s] = 0ull;
-            sm.count[s] = 0u; sm.nts[s] = 0u; sm.te[s] = 0u; sm.lr[s] = 0u;
-        }
-        if (t == 0) sm.base_tid = cands[tb0].tid;
-        __syncthreads();
-        const int32_t base_tid = sm.base_tid;
-
-        // all loads of the tile first (two 128-bit loads per candidate, coalesced across the warp)
-        uint4 ca[MERGE_CPT], cb[MERGE_CPT];
+    for (uint32_t tile = blockIdx.x; tile < n_rtiles + n_otiles; tile += gridDim.x) {
+        // ---- where this tile's candidates are
+        const bool is_region = tile < n_rtiles;
+        uint32_t total, g0 = 0;
+        if (is_region) {
+            g0 = tile * MERGE_RGROUP;
+            const uint32_t ng = min((uint32_t)MERGE_RGROUP, rg.n_regions - g0);
+            if (t < 32) {                                       // warp 0: inclusive scan of the region counts
+                uint32_t c = t < ng ? min(rg.cnt[g0 + t], rg.cap) : 0u, x = c;
 #pragma unroll
-        for (int j = 0; j < MERGE_CPT; ++j) {
-            uint32_t i = tb0 + t + j * MERGE_THREADS;
-            if (i < n) {
-                const uint4* p = reinterpret_cast<const uint4*>(cands + i);
-                ca[j] = ldg_stream_u4(p);
-                cb[j] = ldg_stream_u4(p + 1);
-            } else {
-                ca[j] = make_uint4(0, 0, 0, 0);
-                cb[j] = make_uint4(0, 0, 0xffffffffu, 0);      // tid = -1: skipped
+                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((int)t >= d) x += y; }
+                sm.rpre[t + 1] = x;
+                if (t == 0) sm.rpre[0] = 0;
             }
+            __syncthreads();
+            total = sm.rpre[MERGE_RGROUP];
+            if (t == 0 && total) atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_TOTAL_CAND64), (unsigned long long)total);
+        } else {
+            const uint32_t tb0 = (tile - n_rtiles) * MERGE_TILE;
+            total = min((uint32_t)MERGE_TILE, n - tb0);
         }
+        auto cand_ptr = [&](uint32_t i) -> const uint4* {       // i-th candidate of the tile
+            if (!is_region) return reinterpret_cast<const uint4*>(cands + (size_t)(tile - n_rtiles) * MERGE_TILE + i);
+            uint32_t lo = 0, hi = MERGE_RGROUP;                 // last g with rpre[g] <= i
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.rpre[mid] <= i) lo = mid; else hi = mid; }
+            return reinterpret_cast<const uint4*>(rg.base + (size_t)(g0 + lo) * rg.cap + (i - sm.rpre[lo]));
+        };
+
+        for (uint32_t c0 = 0; c0 < total; c0 += MERGE_TILE) {   // a region tile may hold more than MERGE_TILE candidates
+            const uint32_t m = min((uint32_t)MERGE_TILE, total - c0);
+            for (uint32_t s = t; s < MERGE_SLOTS; s += MERGE_THREADS) {
+                sm.key[s] = SKEY_EMPTY; sm.nfirst[s] = 0ull; sm.last[s] = 0ull;
+                sm.count[s] = 0u; sm.nts[s] = 0u; sm.te[s] = 0u; sm.lr[s] = 0u;
+            }
+            if (t == 0) sm.base_tid = (int32_t)cand_ptr(c0)[1].z;
+            __syncthreads();
+            const int32_t base_tid = sm.base_tid;
+
+            // all loads of the chunk first (two 128-bit loads per candidate)
+            uint4 ca[MERGE_CPT], cb[MERGE_CPT];
 #pragma unroll
-        for (int j = 0; j < MERGE_CPT; ++j) {
-            const uint32_t start = ca[j].x, end = ca[j].y, ts = ca[j].z, te = ca[j].w;
-            const int32_t tid = (int32_t)cb[j].z;
-            if (tid < 0) continue;
-            const uint32_t ilen = end - start;                                   // uint32, :161-162
-            if (ilen < prm.min_intron || ilen > prm.max_intron) continue;         // junction_qc
-            const uint32_t lr = ((start - ts) >= prm.min_anchor ? 1u : 0u) | ((te - end) >= prm.min_anchor ? 2u : 0u);
-            const uint32_t sc = cb[j].w & 0xffu;
-            const uint32_t proxy = sc == '+' ? 0u : (sc == '-' ? 1u : 2u);         // :186-193
-            const unsigned long long ord = (unsigned long long)cb[j].y << 32 | cb[j].x;
-            const unsigned long long nfirst = ~ord;
-            const unsigned long long last = proxy == 2u ? ((ord >> 16) << 8 | sc) : 0ull;
-            bool done = false;
-            if (tid == base_tid && ilen < (1u << 28)) {
-                const unsigned long long k = (unsigned long long)start << 30 | (unsigned long long)ilen << 2 | proxy;
-                uint32_t s = mix_key(k, 0ull) & (MERGE_SLOTS - 1);
-                for (int probe = 0; probe < MERGE_PROBES; ++probe, s = (s + 1) & (MERGE_SLOTS - 1)) {
-                    unsigned long long cur = sm.key[s];
-                    if (cur == SKEY_EMPTY) cur = atomicCAS(&sm.key[s], SKEY_EMPTY, k);
-                    if (cur == SKEY_EMPTY || cur == k) {
-                        atomicAdd(&sm.count[s], 1u);
-                        atomicMax(&sm.nts[s], ~ts);
-                        atomicMax(&sm.te[s], te);
-                        if (lr) atomicOr(&sm.lr[s], lr);
-                        atomicMax(&sm.nfirst[s], nfirst);
-                        if (last) atomicMax(&sm.last[s], last);
-                        done = true;
-                        break;
-                    }
+            for (int j = 0; j < MERGE_CPT; ++j) {
+                const uint32_t i = t + j * MERGE_THREADS;
+                if (i < m) {
+                    const uint4* p = cand_ptr(c0 + i);
+                    ca[j] = ldg_stream_u4(p);
+                    cb[j] = ldg_stream_u4(p + 1);
+                } else {
+                    ca[j] = make_uint4(0, 0, 0, 0);
+                    cb[j] = make_uint4(0, 0, 0xffffffffu, 0);      // tid = -1: skipped
                 }
             }
-            if (!done) {
-                K128 key{(unsigned long long)start << 32 | end, ((unsigned long long)(uint32_t)(tid + 1)) << 2 | proxy};
-                if (!table_upsert(tb, key, 1u, ~ts, te, lr, nfirst, last, counters))
-                    spill_entry(spill, spill_cap, counters, key, 1u, ~ts, te, lr, nfirst, last);
+#pragma unroll
+            for (int j = 0; j < MERGE_CPT; ++j) {
+                const uint32_t start = ca[j].x, end = ca[j].y, ts = ca[j].z, te = ca[j].w;
+                const int32_t tid = (int32_t)cb[j].z;
+                if (tid < 0) continue;
+                const uint32_t ilen = end - start;                                   // uint32, :161-162
+                if (ilen < prm.min_intron || ilen > prm.max_intron) continue;         // junction_qc
+                const uint32_t lr = ((start - ts) >= prm.min_anchor ? 1u : 0u) | ((te - end) >= prm.min_anchor ? 2u : 0u);
+                const uint32_t sc = cb[j].w & 0xffu;
+                const uint32_t proxy = sc == '+' ? 0u : (sc == '-' ? 1u : 2u);         // :186-193
+                const unsigned long long ord = (unsigned long long)cb[j].y << 32 | cb[j].x;
+                const unsigned long long nfirst = ~ord;
+                const unsigned long long last = proxy == 2u ? ((ord >> 16) << 8 | sc) : 0ull;
+                bool done = false;
+                if (tid == base_tid && ilen < (1u << 28)) {
+                    const unsigned long long k = (unsigned long long)start << 30 | (unsigned long long)ilen << 2 | proxy;
+                    uint32_t s = mix_key(k, 0ull) & (MERGE_SLOTS - 1);
+                    for (int probe = 0; probe < MERGE_PROBES; ++probe, s = (s + 1) & (MERGE_SLOTS - 1)) {
+                        unsigned long long cur = sm.key[s];
+                        if (cur == SKEY_EMPTY) cur = atomicCAS(&sm.key[s], SKEY_EMPTY, k);
+                        if (cur == SKEY_EMPTY || cur == k) {
+                            atomicAdd(&sm.count[s], 1u);
+                            atomicMax(&sm.nts[s], ~ts);
+                            atomicMax(&sm.te[s], te);
+                            if (lr) atomicOr(&sm.lr[s], lr);
+                            atomicMax(&sm.nfirst[s], nfirst);
+                            if (last) atomicMax(&sm.last[s], last);
+                            done = true;
+                            break;
+                        }
+                    }
+                }
+                if (!done) {
+                    K128 key{(unsigned long long)start << 32 | end, ((unsigned long long)(uint32_t)(tid + 1)) << 2 | proxy};
+                    if (!table_upsert(tb, key, 1u, ~ts, te, lr, nfirst, last, counters))
+                        spill_entry(spill, spill_cap, counters, key, 1u, ~ts, te, lr, nfirst, last);
+                }
             }
+            __syncthreads();
+            // one global upsert per distinct junction of the chunk
+            for (uint32_t s = t; s < MERGE_SLOTS; s += MERGE_THREADS) {
+                const unsigned long long k = sm.key[s];
+                if (k == SKEY_EMPTY) continue;
+                const uint32_t start = (uint32_t)(k >> 30), ilen = (uint32_t)(k >> 2) & 0x0fffffffu, proxy = (uint32_t)k & 3u;
+                K128 key{(unsigned long long)start << 32 | (uint32_t)(start + ilen),
+                         ((unsigned long long)(uint32_t)(base_tid + 1)) << 2 | proxy};
+                if (!table_upsert(tb, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s], counters))
+                    spill_entry(spill, spill_cap, counters, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        // one global upsert per distinct junction of the tile
-        for (uint32_t s = t; s < MERGE_SLOTS; s += MERGE_THREADS) {
-            const unsigned long long k = sm.key[s];
-            if (k == SKEY_EMPTY) continue;
-            const uint32_t start = (uint32_t)(k >> 30), ilen = (uint32_t)(k >> 2) & 0x0fffffffu, proxy = (uint32_t)k & 3u;
-            K128 key{(unsigned long long)start << 32 | (uint32_t)(start + ilen),
-                     ((unsigned long long)(uint32_t)(base_tid + 1)) << 2 | proxy};
-            if (!table_upsert(tb, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s], counters))
-                spill_entry(spill, spill_cap, counters, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s]);
-        }
-        __syncthreads();
+        __syncthreads();            // rpre is rewritten by the next region tile
     }
 }
 
@@ -916,19 +987,19 @@ static int num_sms() {
     return g_num_sms;
 }
 
-void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound, const ScanParams& p,
-                           const TableRef& tb, Slot* spill_slots, uint32_t spill_cap, uint32_t* d_counters,
+void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound, const CandRegions& regions,
+                           const ScanParams& p, const TableRef& tb, Slot* spill_slots, uint32_t spill_cap, uint32_t* d_counters,
                            cudaStream_t stream) {
-    if (n_cand_bound == 0) return;
+    if (n_cand_bound == 0 && !regions.base) return;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(junction_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem));
         attr_set = true;
     }
-    uint32_t tiles = (n_cand_bound + MERGE_TILE - 1) / MERGE_TILE;
-    uint32_t grid = min(tiles, (uint32_t)(2 * num_sms()));
+    uint32_t tiles = (n_cand_bound + MERGE_TILE - 1) / MERGE_TILE + (regions.base ? (regions.n_regions + MERGE_RGROUP - 1) / MERGE_RGROUP : 0u);
+    uint32_t grid = max(1u, min(tiles, (uint32_t)(2 * num_sms())));
     junction_merge_kernel<<<grid, MERGE_THREADS, sizeof(MergeSmem), stream>>>(
-        cands, d_n_cand, n_cand_bound, p, tb, spill_slots, spill_cap, d_counters);
+        cands, d_n_cand, n_cand_bound, regions, p, tb, spill_slots, spill_cap, d_counters);
 }
 
 // Re-inserts every occupied slot of `src` (an old table, or the spill list) into the table.
