@@ -60,7 +60,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -230,7 +230,6 @@ def main():
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
     st = ex.stats()
-    clocks = sampler.stop() if rank == 0 else None
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     reads_t = torch.tensor([R], dtype=torch.int64, device=dev)
     if world > 1:
@@ -282,6 +281,7 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = reads_all / float(e2e_t.item())
+    clocks = sampler.stop() if rank == 0 else None       # sampled across both timed regions (resident steps + e2e steps)
 
     if rank != 0:
         if world > 1:

@@ -39,21 +39,20 @@ __device__ __forceinline__ bool record_ok(const uint8_t* core, int32_t block_len
 // One WARP per seed segment.  data = first byte of the chunk's inflated stream (negative offsets reach into
 // the carry headroom).  seeds[i] are offsets relative to data; seeds[0] is replaced by -(carry length) when
 // `use_carry`.  rec_off gets, per segment, the offsets of its records.
-// The chain of block_size fields is serial, but its latency need not be DRAM latency: the warp pulls the
-// stream through a 4 KB shared-memory window with coalesced loads (one memory round trip per ~19 records)
-// and lane 0 hops from record to record inside the window.
+// The chain of block_size fields is serial, but its latency need not be DRAM latency: the stream is pulled
+// through a shared-memory ring of four 2 KB windows with 16-byte cp.async — while lane 0 hops from record
+// to record inside window w (two aligned LDS + a funnel shift per hop; w and w+1 are resident, a header may
+// straddle them), windows w+2 and w+3 are in flight.  Only block_size is looked at here; bam_read1's consistency checks run in parallel in the gather
+// kernel.
 constexpr int WALK_WARPS = 4;
-constexpr int WALK_WIN   = 4096;
-
-__device__ __forceinline__ uint32_t lds_u32_any(const uint8_t* p) {
-    return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
-}
+constexpr int WALK_WIN   = 2048;                 // bytes per window
+constexpr int WALK_NWIN  = 4;                    // windows in the ring (power of two)
 
 __global__ void __launch_bounds__(WALK_WARPS * 32)
 record_walk_kernel(const uint8_t* __restrict__ data, int64_t data_len, int64_t limit, const int64_t* __restrict__ seeds,
                    const uint32_t* __restrict__ seg_base, uint32_t n_seg, int use_carry, FeedState* __restrict__ state,
                    int32_t* __restrict__ rec_off, uint32_t* __restrict__ seg_cnt) {
-    __shared__ __align__(16) uint32_t s_win[WALK_WARPS][WALK_WIN / 4 + 4];
+    __shared__ __align__(16) uint32_t s_ring[WALK_WARPS][WALK_NWIN * WALK_WIN / 4];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     const uint32_t i = blockIdx.x * WALK_WARPS + wib;
     if (i >= n_seg) return;
@@ -66,46 +65,65 @@ record_walk_kernel(const uint8_t* __restrict__ data, int64_t data_len, int64_t l
     int32_t* my = rec_off + seg_base[i];
     const uint32_t cap = seg_base[i + 1] - seg_base[i];
     int64_t carry_from = -1;
-    const uint8_t* win = reinterpret_cast<const uint8_t*>(s_win[wib]);
-    bool done = false;
-    while (!done) {
-        if (p >= stop_at) break;
-        // window [wbase, wbase + WALK_WIN) of the stream, 4-byte aligned (data itself is 256-byte aligned)
-        const int64_t wbase = (p >> 2) << 2;
-        int64_t wbytes = data_len + 8 - wbase;                 // the buffer is padded past data_len
-        if (wbytes > WALK_WIN) wbytes = WALK_WIN;
-        const uint32_t nw = (uint32_t)((wbytes + 3) >> 2);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(data + wbase);
-        for (uint32_t w = lane; w < nw; w += 32) s_win[wib][w] = src[w];
-        __syncwarp();
-        if (lane == 0) {
-            const int64_t wend = wbase + (int64_t)nw * 4;
-            while (p < stop_at) {
-                if (p + 4 > data_len) { carry_from = p; done = true; break; }
-                if (p + 24 > wend) {
-                    if (wend >= data_len) { carry_from = p; done = true; }              // header cut by the end of the chunk
-                    break;                                                              // else: reload the window at p
-                }
-                const int32_t bl = (int32_t)lds_u32_any(win + (p - wbase));
-                if (bl < 32) { atomicMin(&state->bad_offset, (long long)p); done = true; break; }     // malformed: iteration ends here
-                if (p + 4 + (int64_t)bl > data_len) { carry_from = p; done = true; break; }            // continues in the next chunk
-                {   // bam_read1's validity checks (sam.c:399-432) on the core fields inside the window
-                    const uint8_t* core = win + (p - wbase) + 4;
-                    const int32_t l_qseq = (int32_t)lds_u32_any(core + 16);
-                    const uint32_t l_qname = core[8];
-                    const uint32_t n_cigar = (uint32_t)core[12] | (uint32_t)core[13] << 8;
-                    const long long aux_off = (long long)l_qname + 4ll * n_cigar + ((long long)l_qseq + 1) / 2 + l_qseq;
-                    if (l_qseq < 0 || l_qname < 1 || aux_off > (long long)bl - 32) { atomicMin(&state->bad_offset, (long long)p); done = true; break; }
-                }
-                if (n < cap) my[n] = (int32_t)p;
-                else atomicOr(&state->flags, FEED_FLAG_CAPACITY);
-                ++n;
-                p += 4 + (int64_t)bl;
-            }
-            if (p >= stop_at) done = true;
+    uint32_t* ring = s_ring[wib];
+    const int64_t padded_len = data_len + 32;                 // the inflated buffer is padded past data_len
+
+    // window w covers stream bytes [A + w*WIN, A + (w+1)*WIN) and lives in ring slot (w % NWIN)
+    constexpr uint32_t RING_MASK = WALK_NWIN * WALK_WIN / 4 - 1;
+    auto load_window = [&](int64_t A, int64_t w) {
+        const int64_t wstart = A + w * WALK_WIN;
+        uint32_t* dst = ring + (w & (WALK_NWIN - 1)) * (WALK_WIN / 4);
+#pragma unroll
+        for (int k = 0; k < WALK_WIN / 16 / 32; ++k) {
+            const int64_t o = wstart + ((int64_t)k * 32 + lane) * 16;
+            if (o + 16 <= padded_len)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + (k * 32 + lane) * 4)), "l"(data + o) : "memory");
         }
-        p = __shfl_sync(0xffffffffu, p, 0);
-        done = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    bool done = p >= stop_at;
+    while (!done) {
+        // (re)start the ring at p: windows 0..3 requested, 0 and 1 awaited
+        const int64_t A = (p >> 4) << 4;                      // 16-byte aligned (data itself is 256-byte aligned)
+        load_window(A, 0); load_window(A, 1); load_window(A, 2); load_window(A, 3);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncwarp();
+        int64_t w = 0;                                         // window lane 0 is walking; w and w+1 are resident
+        bool restart = false;
+        while (!done && !restart) {
+            int64_t new_p = p;
+            int flag = 0;                                      // 1 done, 2 window exhausted, 3 far jump (restart the ring)
+            if (lane == 0) {
+                const int64_t wend = A + (w + 1) * WALK_WIN;   // records STARTING before wend are handled in this window
+                while (true) {
+                    if (new_p >= stop_at) { flag = 1; break; }
+                    if (new_p >= wend) { flag = new_p >= wend + WALK_WIN ? 3 : 2; break; }
+                    if (new_p + 4 > data_len) { carry_from = new_p; flag = 1; break; }
+                    const uint32_t bi = (uint32_t)(new_p - A);
+                    const uint32_t w0 = ring[(bi >> 2) & RING_MASK], w1 = ring[((bi >> 2) + 1) & RING_MASK];
+                    const int32_t bl = (int32_t)__funnelshift_r(w0, w1, (bi & 3u) * 8u);
+                    if (bl < 32) { atomicMin(&state->bad_offset, (long long)new_p); flag = 1; break; }      // malformed: iteration ends here
+                    if (new_p + 4 + (int64_t)bl > data_len) { carry_from = new_p; flag = 1; break; }         // continues in the next chunk
+                    if (n < cap) my[n] = (int32_t)new_p;
+                    else atomicOr(&state->flags, FEED_FLAG_CAPACITY);
+                    ++n;
+                    new_p += 4 + (int64_t)bl;
+                }
+            }
+            flag = __shfl_sync(0xffffffffu, flag, 0);
+            p = __shfl_sync(0xffffffffu, new_p, 0);
+            if (flag == 1) done = true;
+            else if (flag == 3) restart = true;
+            else {                                             // advance: window w is consumed, its slot takes w+4
+                load_window(A, w + WALK_NWIN);
+                // walking w+1 needs w+1 and w+2 resident: everything but the two newest requests
+                asm volatile("cp.async.wait_group 2;" ::: "memory");
+                __syncwarp();
+                ++w;
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
     }
     if (lane != 0) return;
@@ -123,7 +141,7 @@ record_walk_kernel(const uint8_t* __restrict__ data, int64_t data_len, int64_t l
 __global__ void __launch_bounds__(256)
 record_gather_kernel(const uint8_t* __restrict__ data, const int32_t* __restrict__ rec_off, const uint32_t* __restrict__ seg_base,
                      const uint32_t* __restrict__ seg_cnt, const uint32_t* __restrict__ seg_scan, uint32_t n_seg,
-                     uint32_t cap_total, const FeedState* __restrict__ state, int32_t* __restrict__ dense,
+                     uint32_t cap_total, FeedState* __restrict__ state, int32_t* __restrict__ dense,
                      uint32_t* __restrict__ ncig) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= cap_total) return;
@@ -135,6 +153,8 @@ record_gather_kernel(const uint8_t* __restrict__ data, const int32_t* __restrict
     const uint32_t r = seg_scan[lo] + j;
     dense[r] = off;
     ncig[r] = ld_u16_any(data + off + 4 + 12);
+    // bam_read1's consistency checks (sam.c:399-432); a failing record ends the reference's iteration -> host path
+    if (!record_ok(data + off + 4, (int32_t)ld_u32_any(data + off))) atomicMin(&state->bad_offset, (long long)off);
 }
 
 // bam_aux_get + bam_aux2A (sam.c:1254-1266, 1301-1307): value byte of the first `tag` if its type is 'A'.

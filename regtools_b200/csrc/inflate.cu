@@ -120,14 +120,14 @@ __device__ __forceinline__ int slow_decode(BitReader& br, const uint16_t* count,
 // Builds count[]/sym[] (canonical order) and the fast table for `n` symbols with lengths `len[]`.
 // Executed by the whole warp; returns false (all lanes) on an over-subscribed code.
 __device__ bool build_tables(const uint8_t* len, int n, uint16_t* count, uint16_t* sym, uint16_t* fast, int fast_bits,
-                             uint32_t lane) {
-    for (int i = lane; i < 16; i += 32) count[i] = 0;
-    for (int i = lane; i < (1 << fast_bits); i += 32) fast[i] = 0;
-    __syncwarp();
+                             uint32_t lane, uint32_t L, uint32_t gmask) {
+    for (int i = lane; i < 16; i += L) count[i] = 0;
+    for (int i = lane; i < (1 << fast_bits); i += L) fast[i] = 0;
+    __syncwarp(gmask);
     if (lane == 0) {
         for (int i = 0; i < n; ++i) count[len[i]]++;
     }
-    __syncwarp();
+    __syncwarp(gmask);
     // offsets and over-subscription check (every lane computes the same small loop)
     uint16_t offs[16];
     int left = 1;
@@ -162,7 +162,7 @@ __device__ bool build_tables(const uint8_t* len, int n, uint16_t* count, uint16_
             }
         }
     }
-    __syncwarp();
+    __syncwarp(gmask);
     return true;
 }
 
@@ -173,12 +173,21 @@ struct BgzfBlock {   // same layout as BgzfBlockDesc (jx_device.cuh)
     uint32_t out_len;    // ISIZE
 };
 
+// L = lanes per decoder (32, 16 or 8).  With L < 32 a warp decodes 32/L BGZF blocks at once: the leaders of the
+// lane groups run the (serial) symbol loop in lockstep, so one issued instruction advances 32/L streams, and
+// each group of L lanes places its own round of L symbols.  Every warp-level primitive below is restricted to
+// the group's lane mask.
+template <int L>
 __global__ void __launch_bounds__(INF_WARPS * 32)
 bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, uint32_t n_blocks,
                     uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
-    __shared__ InflateWarpSmem smem[INF_WARPS];
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const uint32_t b = blockIdx.x * INF_WARPS + wib;
+    constexpr int DEC_PER_CTA = INF_WARPS * 32 / L;
+    extern __shared__ __align__(16) unsigned char inf_smem_raw[];
+    InflateWarpSmem* smem = reinterpret_cast<InflateWarpSmem*>(inf_smem_raw);
+    const uint32_t lane = threadIdx.x % L, wib = threadIdx.x / L;               // lane within the group, group within the CTA
+    const uint32_t gshift = (threadIdx.x & 31u) / L * L;                          // first warp lane of the group
+    const uint32_t gmask = (L == 32 ? 0xffffffffu : ((1u << (L & 31)) - 1u) << gshift);
+    const uint32_t b = blockIdx.x * DEC_PER_CTA + wib;
     if (b >= n_blocks) return;
     InflateWarpSmem& sm = smem[wib];
     const BgzfBlock blk = blocks[b];
@@ -194,7 +203,7 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
         // ---- block header (lane 0), broadcast
         uint32_t hdr = 0;
         if (lane == 0) hdr = br.get(3);
-        hdr = __shfl_sync(0xffffffffu, hdr, 0);
+        hdr = __shfl_sync(gmask, hdr, 0, L);
         last = hdr & 1u;
         const uint32_t btype = hdr >> 1;
         if (btype == 0) {
@@ -206,11 +215,11 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
                 if ((l ^ nl) != 0xffffu) len = 0xffffffffu;
                 else { len = l; src = br.byte_ptr(); }
             }
-            len = __shfl_sync(0xffffffffu, len, 0);
+            len = __shfl_sync(gmask, len, 0, L);
             if (len == 0xffffffffu || opos + len > cap) { err = 2; break; }
-            const unsigned long long s64 = __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(src), 0);
+            const unsigned long long s64 = __shfl_sync(gmask, (unsigned long long)reinterpret_cast<uintptr_t>(src), 0, L);
             src = reinterpret_cast<const uint8_t*>((uintptr_t)s64);
-            for (uint32_t i = lane; i < len; i += 32) dst[opos + i] = __ldg(src + i);
+            for (uint32_t i = lane; i < len; i += L) dst[opos + i] = __ldg(src + i);
             opos += len;
             if (lane == 0) br.init(src + len);
             continue;
@@ -219,9 +228,9 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
         // ---- code lengths
         int hlit = 288, hdist = 30;
         if (btype == 1) {
-            for (int i = lane; i < 288; i += 32) sm.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
-            for (int i = lane; i < 30; i += 32) sm.lens[288 + i] = 5;
-            __syncwarp();
+            for (int i = lane; i < 288; i += L) sm.lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+            for (int i = lane; i < 30; i += L) sm.lens[288 + i] = 5;
+            __syncwarp(gmask);
         } else {
             uint32_t e2 = 0;
             if (lane == 0) {
@@ -270,14 +279,14 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
                     for (int i = hdist; i < 30; ++i) sm.lens[288 + i] = 0;
                 }
             }
-            e2 = __shfl_sync(0xffffffffu, e2, 0);
+            e2 = __shfl_sync(gmask, e2, 0, L);
             if (e2) { err = e2; break; }
             hlit = 288; hdist = 30;
-            __syncwarp();
+            __syncwarp(gmask);
         }
-        if (!build_tables(sm.lens, hlit, sm.lit_count, sm.lit_sym, sm.lit_fast, LIT_BITS, lane)) { err = 9; break; }
+        if (!build_tables(sm.lens, hlit, sm.lit_count, sm.lit_sym, sm.lit_fast, LIT_BITS, lane, L, gmask)) { err = 9; break; }
         // an incomplete distance code with a single symbol is legal; over-subscription is not
-        if (!build_tables(sm.lens + 288, hdist, sm.dist_count, sm.dist_sym, sm.dist_fast, DIST_BITS, lane)) { err = 10; break; }
+        if (!build_tables(sm.lens + 288, hdist, sm.dist_count, sm.dist_sym, sm.dist_fast, DIST_BITS, lane, L, gmask)) { err = 10; break; }
 
         // ---- symbols, 32 per round
         WinReader wr;
@@ -285,7 +294,7 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
         for (bool eob = false; !eob && !err;) {
             uint32_t n = 0, flag = 0;                 // flag: 1 = end of block seen, 2+ = error
             if (lane == 0) {
-                while (n < 32) {
+                while (n < (uint32_t)L) {
                     uint32_t win = wr.window();
                     int sym;
                     uint32_t e = sm.lit_fast[win & ((1u << LIT_BITS) - 1u)];
@@ -306,9 +315,9 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
                     sm.q[n++] = len << 16 | dist;       // len <= 258, dist <= 32768
                 }
             }
-            n = __shfl_sync(0xffffffffu, n, 0);
-            flag = __shfl_sync(0xffffffffu, flag, 0);
-            __syncwarp();
+            n = __shfl_sync(gmask, n, 0, L);
+            flag = __shfl_sync(gmask, flag, 0, L);
+            __syncwarp(gmask);
             if (flag > 1) { err = flag; break; }
             eob = flag == 1;
             // ---- place the round: prefix sum of lengths, literals in parallel, matches in order
@@ -317,8 +326,8 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
             const uint32_t mylen = lane < n ? (is_lit ? 1u : (s >> 16)) : 0u;
             uint32_t x = mylen;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((int)lane >= d) x += y; }
-            const uint32_t total = __shfl_sync(0xffffffffu, x, 31);
+            for (int d = 1; d < L; d <<= 1) { uint32_t y = __shfl_up_sync(gmask, x, d, L); if ((int)lane >= d) x += y; }
+            const uint32_t total = __shfl_sync(gmask, x, L - 1, L);
             const uint32_t mypos = opos + x - mylen;
             if (opos + total > cap) { err = 15; break; }
             if (lane < n && is_lit) dst[mypos] = (uint8_t)s;
@@ -329,31 +338,31 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
             const bool is_match = lane < n && !is_lit;
             const bool indep = is_match && mlen <= 32u && mypos - opos + (mlen < mdist ? mlen : mdist) <= mdist;
             uint32_t bad = 0;
-            if (__ballot_sync(0xffffffffu, is_match && mdist > mypos)) bad = 16;
+            if (__ballot_sync(gmask, is_match && mdist > mypos)) bad = 16;
             if (!bad) {
-                __syncwarp();
+                __syncwarp(gmask);
                 if (indep) {
                     const uint8_t* srcp = dst + mypos - mdist;
                     if (mdist >= mlen) { for (uint32_t k = 0; k < mlen; ++k) dst[mypos + k] = __ldcg(srcp + k); }
                     else { for (uint32_t k = 0; k < mlen; ++k) dst[mypos + k] = __ldcg(srcp + (k % mdist)); }
                 }
-                uint32_t mm = __ballot_sync(0xffffffffu, is_match && !indep);
+                uint32_t mm = __ballot_sync(gmask, is_match && !indep) >> gshift;
                 while (mm) {
                     const int j = __ffs(mm) - 1; mm &= mm - 1;
-                    const uint32_t sj = __shfl_sync(0xffffffffu, s, j);
-                    const uint32_t pj = __shfl_sync(0xffffffffu, mypos, j);
+                    const uint32_t sj = __shfl_sync(gmask, s, j, L);
+                    const uint32_t pj = __shfl_sync(gmask, mypos, j, L);
                     const uint32_t len = sj >> 16, dist = sj & 0xffffu;
-                    __syncwarp();                                         // earlier stores of this warp are visible
+                    __syncwarp(gmask);                                         // earlier stores of this warp are visible
                     const uint8_t* srcp = dst + pj - dist;
                     if (dist >= len) {
-                        for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + k);
+                        for (uint32_t k = lane; k < len; k += L) dst[pj + k] = __ldcg(srcp + k);
                     } else {                                               // overlapping run: periodic with period dist
-                        for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + (k % dist));
+                        for (uint32_t k = lane; k < len; k += L) dst[pj + k] = __ldcg(srcp + (k % dist));
                     }
                 }
             }
             if (bad) { err = bad; break; }
-            __syncwarp();
+            __syncwarp(gmask);
             opos += total;
         }
         if (lane == 0) wr.to(br);
@@ -559,8 +568,23 @@ void launch_bgzf_inflate(const uint8_t* comp, const void* blocks, uint32_t n_blo
             comp, static_cast<const BgzfBlock*>(blocks), n_blocks, out, status);
         return;
     }
-    const uint32_t grid = (n_blocks + INF_WARPS - 1) / INF_WARPS;
-    bgzf_inflate_kernel<<<grid, INF_WARPS * 32, 0, stream>>>(comp, static_cast<const BgzfBlock*>(blocks), n_blocks, out, status);
+    // lanes per decoder: 32 = one BGZF block per warp, 16 / 8 = two / four blocks per warp (RTJX_INFLATE_LANES)
+    static int lanes = -1;
+    if (lanes < 0) { const char* v = getenv("RTJX_INFLATE_LANES"); lanes = v ? atoi(v) : 16; }
+    const BgzfBlock* bl = static_cast<const BgzfBlock*>(blocks);
+    if (lanes == 8) {
+        constexpr int D = INF_WARPS * 32 / 8; const size_t sh = D * sizeof(InflateWarpSmem);
+        static bool a8 = false; if (!a8) { cudaFuncSetAttribute(bgzf_inflate_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); a8 = true; }
+        bgzf_inflate_kernel<8><<<(n_blocks + D - 1) / D, INF_WARPS * 32, sh, stream>>>(comp, bl, n_blocks, out, status);
+    } else if (lanes == 16) {
+        constexpr int D = INF_WARPS * 32 / 16; const size_t sh = D * sizeof(InflateWarpSmem);
+        static bool a16 = false; if (!a16) { cudaFuncSetAttribute(bgzf_inflate_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); a16 = true; }
+        bgzf_inflate_kernel<16><<<(n_blocks + D - 1) / D, INF_WARPS * 32, sh, stream>>>(comp, bl, n_blocks, out, status);
+    } else {
+        constexpr int D = INF_WARPS; const size_t sh = D * sizeof(InflateWarpSmem);
+        static bool a32 = false; if (!a32) { cudaFuncSetAttribute(bgzf_inflate_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); a32 = true; }
+        bgzf_inflate_kernel<32><<<(n_blocks + D - 1) / D, INF_WARPS * 32, sh, stream>>>(comp, bl, n_blocks, out, status);
+    }
 }
 
 }  // namespace rtjx
