@@ -158,7 +158,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     }
     auto grow_dev = [&](void** p, size_t* cap, size_t want, size_t elem) -> cudaError_t {
         if (want <= *cap) return cudaSuccess;
-        cudaStreamSynchronize(stream_); cudaStreamSynchronize(copy_stream_);
+        if (*p) { cudaStreamSynchronize(stream_); cudaStreamSynchronize(copy_stream_); }   // only a live buffer needs the streams drained
         cached_dev_free(*p); *p = nullptr;
         size_t c = want + want / 8;
         cudaError_t e = cached_dev_malloc(p, c * elem + 256);
@@ -254,7 +254,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             struct TA2 { double* acc; double t0; bool on; ~TA2() { if (on) *acc += now_s() - t0; } } ta2{&t_alloc, ta0, true};
             if (DeviceFeed::HEAD + G.out_total + 64 > F.infl_cap) {
                 // the headroom of the old buffer holds the record carried over from the previous group: keep it
-                cudaStreamSynchronize(stream_);
+                if (F.d_infl) cudaStreamSynchronize(stream_);
                 const size_t want = DeviceFeed::HEAD + G.out_total + 64;
                 const size_t cap = want + want / 8;
                 uint8_t* nb2 = nullptr;
@@ -265,13 +265,13 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             }
             CKD(grow_dev((void**)&F.d_cigar, &F.cigar_cap, (DeviceFeed::HEAD + G.out_total) / 32 + 4096, 4));   // > 12.5 % of the bytes being CIGAR -> capacity flag
             if ((size_t)nb + 2 > F.desc_cap) {
-                cudaStreamSynchronize(stream_);
+                if (F.d_desc) cudaStreamSynchronize(stream_);
                 cached_dev_free(F.d_desc); cached_dev_free(F.d_status); F.d_desc = nullptr; F.d_status = nullptr;
                 F.desc_cap = (size_t)nb * 2 + 1024;
                 CKD(cached_dev_malloc(&F.d_desc, F.desc_cap * sizeof(BgzfBlockDesc))); CKD(cached_dev_malloc(&F.d_status, F.desc_cap * 4));
             }
             if ((size_t)n_seg + 2 > F.seed_cap) {
-                cudaStreamSynchronize(stream_);
+                if (F.d_seeds) cudaStreamSynchronize(stream_);
                 cached_dev_free(F.d_seeds); cached_dev_free(F.d_segbase); cached_dev_free(F.d_segcnt); cached_dev_free(F.d_segscan);
                 F.d_seeds = nullptr; F.d_segbase = F.d_segcnt = F.d_segscan = nullptr;
                 F.seed_cap = (size_t)n_seg * 2 + 1024;
@@ -279,7 +279,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                 CKD(cached_dev_malloc(&F.d_segcnt, F.seed_cap * 4)); CKD(cached_dev_malloc(&F.d_segscan, F.seed_cap * 4));
             }
             if ((size_t)cap_total + 8 > F.rec_cap) {
-                cudaStreamSynchronize(stream_);
+                if (F.d_recoff) cudaStreamSynchronize(stream_);
                 const size_t cap = (size_t)cap_total + cap_total / 8 + 1024;
                 cached_dev_free(F.d_recoff); cached_dev_free(F.d_dense); cached_dev_free(F.d_ncig); cached_dev_free(F.d_ncigscan);
                 cached_dev_free(F.d_tid); cached_dev_free(F.d_pos); cached_dev_free(F.d_meta); cached_dev_free(F.d_off); cached_dev_free(F.d_ws);
@@ -347,7 +347,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                     if (want > F.group_cap[gbuf]) {
                         const double ta = now_s();
                         struct TA { double* acc; double t0; ~TA() { *acc += now_s() - t0; } } ta_guard{&t_alloc, ta};
-                        cudaStreamSynchronize(stream_); cudaStreamSynchronize(copy_stream_);
+                        if (F.d_comp_group[gbuf]) { cudaStreamSynchronize(stream_); cudaStreamSynchronize(copy_stream_); }
                         cached_dev_free(F.d_comp_group[gbuf]); F.d_comp_group[gbuf] = nullptr;
                         CKD(cached_dev_malloc(&F.d_comp_group[gbuf], want + want / 16));
                         F.group_cap[gbuf] = want + want / 16;
