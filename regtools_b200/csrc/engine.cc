@@ -67,7 +67,11 @@ ScanParams Engine::scan_params() const {
     s.strandness = prm_.strandness; s.min_anchor = prm_.min_anchor;
     s.min_intron = prm_.min_intron; s.max_intron = prm_.max_intron;
     static const uint32_t dbg = getenv("RTJX_SCAN_DEBUG") ? (uint32_t)atoi(getenv("RTJX_SCAN_DEBUG")) : 0u;
-    s.debug = dbg;
+    static const int env_variant = getenv("RTJX_SCAN_VARIANT") ? atoi(getenv("RTJX_SCAN_VARIANT")) : 0;
+    static const int env_cfg = getenv("RTJX_SCAN_CFG") ? atoi(getenv("RTJX_SCAN_CFG")) : 0;
+    s.debug = prm_.scan_debug ? prm_.scan_debug : dbg;
+    s.variant = prm_.scan_variant ? prm_.scan_variant : (env_variant ? env_variant : 5);
+    s.cfg = prm_.scan_cfg ? prm_.scan_cfg : env_cfg;
     return s;
 }
 
@@ -159,6 +163,23 @@ int Engine::ensure_table(uint32_t incoming, cudaStream_t stream) {
 int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaStream_t stream) {
     int rc;
     const bool known = cand_bound != 0;
+    const ScanParams sp = scan_params();
+    if (sp.variant == 6 && known && ((reinterpret_cast<uintptr_t>(v.tid) | reinterpret_cast<uintptr_t>(v.pos) |
+                                      reinterpret_cast<uintptr_t>(v.meta) | reinterpret_cast<uintptr_t>(v.cig_off) |
+                                      reinterpret_cast<uintptr_t>(v.cigar)) & 15u) == 0) {
+        // fused path: one kernel walks the CIGARs and updates the junction table; no candidate list
+        if ((rc = ensure_table(cand_bound, stream))) return rc;
+        ProfEv pe{nullptr, nullptr, nullptr};
+        if (prm_.profile) { pe.a = get_event(); pe.b = get_event(); pe.c = get_event(); cudaEventRecord(pe.a, stream); }
+        launch_cigar_scan_fused(v, sp, table_ref(), d_spill_, spill_cap_, d_counters_, stream);
+        if (prm_.profile) { cudaEventRecord(pe.b, stream); cudaEventRecord(pe.c, stream); prof_pending_.push_back(pe); }
+        CK(cudaGetLastError());
+        stats_.kernel_launches += v.n_reads ? 1 : 0;
+        stats_.reads += v.n_reads; stats_.cigar_ops += v.n_ops; stats_.batches++;
+        dirty_ = true; finalized_ = false;
+        if (prof_pending_.size() > 4096) resolve_profile_events();
+        return RTJX_OK;
+    }
     if ((rc = ensure_cands(known ? cand_bound : std::max(v.n_ops, 1u)))) return rc;
     if (known && (rc = ensure_table(cand_bound, stream))) return rc;
     CK(cudaMemsetAsync(d_counters_ + CTR_NCAND, 0, sizeof(uint32_t), stream));

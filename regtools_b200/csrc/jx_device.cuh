@@ -48,6 +48,8 @@ struct ScanParams {
     int32_t  strandness;          // 0 XS, 1 RF, 2/3 FR
     uint32_t min_anchor, min_intron, max_intron;
     uint32_t debug;               // developer switches for A/B measurements (0 in production)
+    int32_t  variant;             // cigar_scan variant: 5 = scan -> candidates -> junction_merge (default), 6 = fused scan + table update
+    int32_t  cfg;                 // tile configuration of the variant (0 = production)
 };
 
 struct BatchView {
@@ -86,6 +88,12 @@ uint32_t cigar_scan_tiles(uint32_t n_reads);
 void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
                        uint32_t* d_counters /* [0]=n_cand, [1]=overflowed */, uint32_t* tile_off_scratch,
                        const CandRegions& regions, cudaStream_t stream);
+// Fused path (variant 6): CIGAR walk, junction_qc and the per-tile pre-aggregation happen in one kernel that upserts
+// straight into the junction table; no candidate ever travels through HBM.  The caller must have sized
+// the table for the batch (load <= 0.5 with every N op a new key).  Returns false when the batch cannot take this path
+// (arrays not 16-byte aligned): use launch_cigar_scan + launch_junction_merge then.
+bool launch_cigar_scan_fused(const BatchView& b, const ScanParams& p, const TableRef& tb, Slot* spill, uint32_t spill_cap,
+                             uint32_t* d_counters, cudaStream_t stream);
 void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound, const CandRegions& regions,
                            const ScanParams& p, const TableRef& tb, Slot* spill, uint32_t spill_cap,
                            uint32_t* d_counters /* [2]=n_unique,[3]=n_spill */, cudaStream_t stream);

@@ -13,6 +13,7 @@
 #include "jx_device.cuh"
 #include <cub/device/device_merge_sort.cuh>
 #include <cstdlib>
+#include <cstdio>
 
 namespace rtjx {
 
@@ -639,11 +640,14 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
     uint32_t lo, hi;
     if (tile_off) { lo = __ldg(tile_off + blockIdx.x); hi = __ldg(tile_off + blockIdx.x + 1); }
     else { cp_async_wait_all(); __syncthreads(); lo = sm.off[0]; hi = sm.off[n_tile]; }
-    const uint32_t a0 = lo & ~3u, end4 = (hi + 3u) & ~3u;
-    const bool direct = hi > lo && (end4 - a0 > (uint32_t)S5_SLAB || end4 > (b.n_ops & ~3u));
-    if (!direct && hi > lo) {
-        const uint32_t n_vec = (end4 - a0) >> 2;
-        for (uint32_t v = t; v < n_vec; v += S5_THREADS) cp_async16(&sm.slab[4 * v], b.cigar + a0 + 4 * v);
+    const uint32_t a0 = lo & ~3u;
+    // words of the tile's slab staged in shared memory (from a0): all of it unless the tile is denser than S5_SLAB or
+    // touches the ragged end of the array; alignments outside the staged window read their ops from global memory
+    uint32_t n_st = 0;
+    if (hi > lo) {
+        const uint32_t end = min(min((hi + 3u) & ~3u, a0 + (uint32_t)S5_SLAB), b.n_ops & ~3u);
+        n_st = end > a0 ? end - a0 : 0u;
+        for (uint32_t v = t; v < (n_st >> 2); v += S5_THREADS) cp_async16(&sm.slab[4 * v], b.cigar + a0 + 4 * v);
     }
     cp_async_commit();
     if (tile_off) { cp_async_wait_all(); __syncthreads(); }
@@ -701,7 +705,7 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
                 const uint32_t o0 = sm.off[r], n = sm.off[r + 1] - o0;
                 const uint32_t strand = read_strand(sm.meta[r], prm.strandness);
                 const uint64_t read_ord = b.first_ordinal + base + r;
-                if (!direct) walk_fast<true>(sm.slab + (o0 - a0), n, sm.pos[r], tid, strand, read_ord, emit);
+                if ((o0 - a0) + n <= n_st) walk_fast<true>(sm.slab + (o0 - a0), n, sm.pos[r], tid, strand, read_ord, emit);
                 else walk_fast<false>(b.cigar + o0, n, sm.pos[r], tid, strand, read_ord, emit);
             }
         }
@@ -729,7 +733,7 @@ __global__ void tile_offsets_kernel(const uint32_t* __restrict__ cig_off, uint32
 uint32_t cigar_scan_tiles(uint32_t n_reads) { return (n_reads + 255) / 256; }   // upper bound over the tile sizes in use
 static int scan_variant() {
     static int variant = -1;
-    if (variant < 0) { const char* v = getenv("RTJX_SCAN_VARIANT"); variant = v ? atoi(v) : 5; }
+    if (variant < 0) { const char* v = getenv("RTJX_SCAN_VARIANT"); variant = v ? atoi(v) : 5; if (variant != 1 && variant != 4) variant = 5; }
     return variant;
 }
 static int scan_cfg() {
@@ -750,10 +754,10 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
     const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
                             reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
                             reinterpret_cast<uintptr_t>(b.cigar);
-    const int variant = scan_variant();
+    const int variant = (p.variant == 1 || p.variant == 4) ? p.variant : scan_variant();
     if ((align & 15u) == 0 && variant == 5) {
         static int prepass = -1;
-        const int cfg = scan_cfg();
+        const int cfg = p.variant == 5 && p.cfg ? p.cfg : scan_cfg();
         if (prepass < 0) { const char* v = getenv("RTJX_SCAN_PREPASS"); prepass = v ? atoi(v) : 0; }   // measured: no gain on B200
         const uint32_t threads = cfg == 2 ? 64u : cfg == 3 ? 256u : 128u;
         const uint32_t tile = threads * 4, tiles = (b.n_reads + tile - 1) / tile;
@@ -768,6 +772,9 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
         case 2: cigar_scan_small_kernel<64, 512, 96><<<tiles, 64, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
         case 3: cigar_scan_small_kernel<256, 2048, 384><<<tiles, 256, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
         case 4: cigar_scan_small_kernel<128, 1024, 96><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
+        case 5: cigar_scan_small_kernel<128, 2048, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
+        case 6: cigar_scan_small_kernel<128, 2048, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
+        case 7: cigar_scan_small_kernel<128, 1536, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
         default: cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions); break;
         }
         return;
@@ -1000,6 +1007,454 @@ void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t
     uint32_t grid = max(1u, min(tiles, (uint32_t)(2 * num_sms())));
     junction_merge_kernel<<<grid, MERGE_THREADS, sizeof(MergeSmem), stream>>>(
         cands, d_n_cand, n_cand_bound, regions, p, tb, spill_slots, spill_cap, d_counters);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cigar_scan, fused version (variant 6; opt-in: rtjx_params.scan_variant = 6)
+// ------------------------------------------------------------------------------------------------
+// parse_alignment_into_junctions (:377-497) + set_junction_strand (:345-359) + junction_qc (:160-170) +
+// add_junction (:174-235) in ONE kernel: no candidate list in HBM, no second kernel.
+// Measured on the 10M-read C2 batch: 117 us for scan + merge in one launch against 71 + 58 us for the default
+// two-kernel path (variant 5); variant 5 stays the default because its scan kernel alone is the path's roofline line.
+//
+// Shape, as measured on B200 (tools/ab_scan.py):
+//  * one block = one tile of 4*THREADS consecutive alignments, many small blocks per SM whose phases the block
+//    scheduler overlaps (persistent rings with deeper prefetch were measured and are slower on this path);
+//  * tiles are REGISTER-staged: 128-bit ld.global of the four metadata columns -> st.shared, then (its address is
+//    the only data-dependent one) the tile's CIGAR slab the same way.  cp.async/LDGSTS and bulk copies top out at
+//    ~0.66 of the copy peak for this tile pattern, plain loads reach 0.76 (the practical ceiling for 212 MB);
+//  * while the slab is in flight the n_cigar > 1 alignments are compacted (ballot + warp prefix) into a work list;
+//  * one thread per compacted alignment walks the CIGAR (closed form, SURVEY App. A.2, first four ops loaded
+//    independently, up to two candidates kept in registers) and applies QC;
+//  * the lanes of a warp that hold the same junction are combined by a leader-election loop (ballot + redux; a
+//    BAM is coordinate sorted, so a warp usually holds 1-5 distinct junctions), the leaders accumulate into the
+//    block's 128-slot shared-memory table (32-bit tile-local ordinals);
+//  * one upsert per distinct junction of the tile goes to the device-wide table (128-bit CAS claim + REDs).
+constexpr int S6_HS = 128;                                   // shared-memory table slots per block
+constexpr int S6_PROBES = 16;
+constexpr int S6_SV = 4;                                     // slab vectors (16 B) staged per thread: 2048 words cover a fully spliced tile
+template <int THREADS>
+struct alignas(16) S6Smem {
+    uint32_t off[THREADS * 4 + 4];
+    uint32_t pos[THREADS * 4];
+    uint32_t meta[THREADS * 4];
+    uint32_t tid[THREADS * 4];
+    uint32_t slab[THREADS * 4 * S6_SV];
+    unsigned long long hkey[S6_HS];
+    uint32_t hval[6][S6_HS];                                 // count, ~thick_start, thick_end, lr, ~first(local), last(local)
+    uint16_t work[THREADS * 4];
+    uint32_t n_work, sink;
+};
+
+struct WalkCand { uint32_t start, end, left, right, k; };
+
+// Forward walk that records the first two N ops in registers (c0, c1) and counts all of them.  Predicated, no
+// branches and no calls: same arithmetic as walk_fast, the first four ops are fetched by independent loads (op code
+// 15 is a transparent filler), the rest in a loop.  Alignments with more than two N ops (rare) are finished by
+// fused_walk_rest.  Returns the number of N ops.
+template <bool FROM_SMEM>
+__device__ __forceinline__ uint32_t walk_collect(const uint32_t* __restrict__ ops, uint32_t n, uint32_t pos,
+                                                 WalkCand& c0, WalkCand& c1) {
+    const uint32_t ANC = (1u << 0) | (1u << 7);
+    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
+    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
+    constexpr int PRE = 4;
+    uint32_t w[PRE];
+#pragma unroll
+    for (int i = 0; i < PRE; ++i) w[i] = (uint32_t)i < n ? (FROM_SMEM ? ops[i] : __ldg(ops + i)) : 0xfu;
+    uint32_t cur = pos, run = 0, nc = 0;
+    bool pending = false;
+    auto step = [&](uint32_t x, uint32_t i) {
+        const uint32_t op = x & 0xfu, len = x >> 4, bit = 1u << op;
+        const bool brk = (bit & BRK) != 0, is_n = op == 3u;
+        const bool close = pending && brk;                  // the open junction ends here: right anchor = run
+        c0.right = (close && nc == 1u) ? run : c0.right;
+        c1.right = (close && nc == 2u) ? run : c1.right;
+        const bool open0 = is_n && nc == 0u, open1 = is_n && nc == 1u;
+        const uint32_t kk = i > 0xffffu ? 0xffffu : i;
+        c0.start = open0 ? cur : c0.start; c0.end = open0 ? cur + len : c0.end; c0.left = open0 ? run : c0.left; c0.k = open0 ? kk : c0.k;
+        c1.start = open1 ? cur : c1.start; c1.end = open1 ? cur + len : c1.end; c1.left = open1 ? run : c1.left; c1.k = open1 ? kk : c1.k;
+        nc += is_n ? 1u : 0u;
+        pending = brk ? is_n : pending;
+        run = brk ? 0u : run + ((bit & ANC) ? len : 0u);
+        cur += (bit & REFC) ? len : 0u;
+    };
+#pragma unroll
+    for (int i = 0; i < PRE; ++i) step(w[i], (uint32_t)i);
+    for (uint32_t i = PRE; i < n; ++i) step(FROM_SMEM ? ops[i] : __ldg(ops + i), i);
+    c0.right = (pending && nc == 1u) ? run : c0.right;
+    c1.right = (pending && nc == 2u) ? run : c1.right;
+    return nc;
+}
+
+struct FusedCtx { TableRef tb; Slot* spill; uint32_t spill_cap; uint32_t* counters; };
+
+// One (already combined) update of the device-wide table; tile-local 32-bit ordinals become global here.
+// Kept out of line: it has several call sites and the scan kernel's hot path has to stay small.
+__device__ __noinline__ void fused_global_upsert(const FusedCtx& cx, uint64_t ord0, uint32_t start, uint32_t end, int32_t tid,
+                                                 uint32_t proxy, uint32_t count, uint32_t nts, uint32_t te, uint32_t lr,
+                                                 uint32_t nfirst_l, uint32_t last_l) {
+    const uint32_t lord = ~nfirst_l;
+    const unsigned long long nfirst = ~(((ord0 + (lord >> 16)) << 16) | (lord & 0xffffu));
+    const unsigned long long last = last_l ? ((ord0 + (last_l >> 8)) << 8 | (last_l & 0xffu)) : 0ull;
+    const K128 key{(unsigned long long)start << 32 | end, ((unsigned long long)(uint32_t)(tid + 1)) << 2 | proxy};
+    if (!table_upsert(cx.tb, key, count, nts, te, lr, nfirst, last, cx.counters))
+    spill_entry(cx.spill, cx.spill_cap, cx.counters, key, count, nts, te, lr, nfirst, last);
+}
+
+// The third and later N ops of one alignment (long-read style CIGARs; rare): plain walk from global memory, QC,
+// one global upsert each.  Out of line so that the hot walk carries no call.
+__device__ __noinline__ void fused_walk_rest(const FusedCtx& cx, const ScanParams& prm, uint64_t ord0, const uint32_t* __restrict__ ops,
+                                             uint32_t n, uint32_t pos, uint32_t r, int32_t tid, uint32_t sc) {
+    const uint32_t ANC = (1u << 0) | (1u << 7);
+    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
+    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
+    const uint32_t proxy = sc == '+' ? 0u : (sc == '-' ? 1u : 2u);
+    uint32_t cur = pos, run = 0, nc = 0;
+    bool pending = false;
+    WalkCand c{0, 0, 0, 0, 0};
+    auto emit = [&]() {
+        const uint32_t ilen = c.end - c.start;
+        if (nc <= 2u || ilen < prm.min_intron || ilen > prm.max_intron) return;
+        fused_global_upsert(cx, ord0, c.start, c.end, tid, proxy, 1u, ~(c.start - c.left), c.end + c.right,
+                            (c.left >= prm.min_anchor ? 1u : 0u) | (c.right >= prm.min_anchor ? 2u : 0u),
+                            ~(r << 16 | c.k), proxy == 2u ? (r << 8 | sc) : 0u);
+    };
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t x = __ldg(ops + i), op = x & 0xfu, len = x >> 4, bit = 1u << op;
+        if (bit & BRK) {
+            if (pending) { c.right = run; emit(); }
+            pending = op == 3u;
+            if (pending) { c.start = cur; c.end = cur + len; c.left = run; c.k = i > 0xffffu ? 0xffffu : i; ++nc; }
+            run = 0;
+        } else if (bit & ANC) {
+            run += len;
+        }
+        if (bit & REFC) cur += len;
+    }
+    if (pending) { c.right = run; emit(); }
+}
+
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+cigar_scan_fused_kernel(BatchView b, ScanParams prm, TableRef tb, Slot* __restrict__ spill, uint32_t spill_cap,
+                        uint32_t* __restrict__ counters) {
+    using Smem = S6Smem<THREADS>;
+    constexpr uint32_t TILE = THREADS * 4, SLAB = THREADS * 4 * S6_SV;
+    __shared__ Smem sm;
+    const uint32_t t = threadIdx.x, lane = t & 31u;
+    const uint32_t base = blockIdx.x * TILE;
+    const uint32_t n_tile = min(TILE, b.n_reads - base);
+    const uint32_t vec_end = b.n_ops & ~3u;
+
+    // ---- phase 1: the four metadata columns, 128-bit loads -> registers -> shared memory
+    if (base + TILE + 3 <= b.n_reads) {
+        const uint4 o = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cig_off + base) + t);
+        const uint4 p = ldg_stream_u4(reinterpret_cast<const uint4*>(b.pos + base) + t);
+        const uint4 m = ldg_stream_u4(reinterpret_cast<const uint4*>(b.meta + base) + t);
+        const uint4 d = ldg_stream_u4(reinterpret_cast<const uint4*>(b.tid + base) + t);
+        if (t == 0) sm.off[TILE] = __ldg(b.cig_off + base + TILE);
+        *reinterpret_cast<uint4*>(&sm.off[4 * t]) = o;
+        *reinterpret_cast<uint4*>(&sm.pos[4 * t]) = p;
+        *reinterpret_cast<uint4*>(&sm.meta[4 * t]) = m;
+        *reinterpret_cast<uint4*>(&sm.tid[4 * t]) = d;
+    } else {                                                 // ragged tail of the batch
+        for (uint32_t r = t; r < n_tile; r += THREADS) {
+            sm.pos[r] = (uint32_t)b.pos[base + r]; sm.meta[r] = b.meta[base + r]; sm.tid[r] = (uint32_t)b.tid[base + r];
+        }
+        for (uint32_t r = t; r <= n_tile; r += THREADS) sm.off[r] = b.cig_off[base + r];
+    }
+    for (uint32_t s = t; s < (uint32_t)S6_HS; s += THREADS) {
+        sm.hkey[s] = SKEY_EMPTY;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) sm.hval[f][s] = 0u;
+    }
+    if (t == 0) { sm.n_work = 0; sm.sink = 0; }
+    __syncthreads();
+    if (prm.debug & 16u) return;
+
+    // ---- phase 2: the tile's CIGAR slab [lo, hi) (the only data-dependent address of the path); at most SLAB words
+    // are staged, the rest of a dense tile is warmed in L2 and read from there
+    const uint32_t lo = sm.off[0], hi = sm.off[n_tile], a0 = lo & ~3u;
+    uint32_t n_st = 0;
+    if (hi > lo) {
+        const uint32_t end = min(min((hi + 3u) & ~3u, a0 + SLAB), vec_end);
+        n_st = end > a0 ? end - a0 : 0u;
+    }
+    uint4 sv[S6_SV];
+#pragma unroll
+    for (int j = 0; j < S6_SV; ++j) {
+        const uint32_t v = t + j * THREADS;
+        if (4u * v < n_st) sv[j] = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cigar + a0) + v);
+    }
+    if (t == 32 % THREADS && hi > lo) {
+        const uint32_t end = min((hi + 3u) & ~3u, vec_end);
+        if (end > a0 + n_st) bulk_prefetch_l2(b.cigar + a0 + n_st, (end - a0 - n_st) * 4u);
+    }
+    // ---- while the slab is in flight: compact the alignments with more than one CIGAR op (junctions_extractor.cc:379)
+    {
+        const uint4 o = *reinterpret_cast<const uint4*>(&sm.off[4 * t]);
+        const uint32_t o4 = sm.off[4 * t + 4];
+        const uint32_t r0 = 4 * t;
+        uint32_t flags = 0;
+        if (r0 + 0 < n_tile && o.y - o.x > 1u) flags |= 1u;
+        if (r0 + 1 < n_tile && o.z - o.y > 1u) flags |= 2u;
+        if (r0 + 2 < n_tile && o.w - o.z > 1u) flags |= 4u;
+        if (r0 + 3 < n_tile && o4 - o.w > 1u) flags |= 8u;
+        const uint32_t cnt = __popc(flags);
+        uint32_t x = cnt;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
+        uint32_t wbase = 0;
+        if (lane == 31 && x) wbase = atomicAdd(&sm.n_work, x);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        uint32_t p = wbase + x - cnt;
+        if (flags & 1u) sm.work[p++] = (uint16_t)(r0 + 0);
+        if (flags & 2u) sm.work[p++] = (uint16_t)(r0 + 1);
+        if (flags & 4u) sm.work[p++] = (uint16_t)(r0 + 2);
+        if (flags & 8u) sm.work[p++] = (uint16_t)(r0 + 3);
+    }
+#pragma unroll
+    for (int j = 0; j < S6_SV; ++j) {
+        const uint32_t v = t + j * THREADS;
+        if (4u * v < n_st) *reinterpret_cast<uint4*>(&sm.slab[4 * v]) = sv[j];
+    }
+    __syncthreads();
+    const uint32_t n_work = (prm.debug & 1u) ? 0u : sm.n_work;
+    if (n_work == 0) return;
+
+    // ---- phase 3: walk, QC, combine, accumulate
+    const FusedCtx cx{tb, spill, spill_cap, counters};
+    const int32_t base_tid = (int32_t)sm.tid[0];
+    const uint64_t ord0 = b.first_ordinal + base;
+    uint32_t my_cands = 0;
+    for (uint32_t w0 = 0; w0 < n_work; w0 += THREADS) {      // warp-uniform trip count
+        const uint32_t i = w0 + t;
+        uint32_t nc = 0, r = 0, sc = 0;
+        int32_t tid = -1;
+        WalkCand c0{0, 0, 0, 0, 0}, c1{0, 0, 0, 0, 0};
+        if (i < n_work) {
+            r = sm.work[i];
+            tid = (int32_t)sm.tid[r];
+            if (tid >= 0) {
+                const uint32_t o0 = sm.off[r], n = sm.off[r + 1] - o0;
+                sc = read_strand(sm.meta[r], prm.strandness);
+                nc = (o0 - a0) + n <= n_st ? walk_collect<true>(sm.slab + (o0 - a0), n, sm.pos[r], c0, c1)
+                                           : walk_collect<false>(b.cigar + o0, n, sm.pos[r], c0, c1);
+                my_cands += nc;
+                if (nc > 2u && !(prm.debug & 2u)) fused_walk_rest(cx, prm, ord0, b.cigar + o0, n, sm.pos[r], r, tid, sc);
+            }
+        }
+        // junction_qc (:160-170) + add_junction (:174-235): warp-uniform passes over the (at most two) register
+        // candidates of every lane
+        for (uint32_t pass = 0; pass < 2u; ++pass) {
+            bool has = nc > pass;
+            if (!__any_sync(0xffffffffu, has)) break;
+            const WalkCand c = pass ? c1 : c0;
+            const uint32_t ilen = c.end - c.start;                                      // uint32, :161-162
+            has = has && ilen >= prm.min_intron && ilen <= prm.max_intron;
+            const uint32_t nts = ~(c.start - c.left), te = c.end + c.right;
+            const uint32_t lr = (c.left >= prm.min_anchor ? 1u : 0u) | (c.right >= prm.min_anchor ? 2u : 0u);
+            const uint32_t proxy = sc == '+' ? 0u : (sc == '-' ? 1u : 2u);               // :186-193
+            const uint32_t nfirst_l = ~(r << 16 | c.k);
+            const uint32_t last_l = proxy == 2u ? (r << 8 | sc) : 0u;
+            if (prm.debug & 2u) { if (has && (nts ^ te ^ lr ^ nfirst_l ^ last_l) == 0x9e3779b9u) sm.sink = 1; continue; }
+            if (has && (tid != base_tid || ilen >= (1u << 28))) {                      // not expressible in the block table's key
+                fused_global_upsert(cx, ord0, c.start, c.end, tid, proxy, 1u, nts, te, lr, nfirst_l, last_l);
+                has = false;
+            }
+            const unsigned long long key = (unsigned long long)c.start << 30 | (unsigned long long)ilen << 2 | proxy;
+            // leader election: every distinct junction of the warp is reduced onto its first lane
+            uint32_t todo = __ballot_sync(0xffffffffu, has);
+            bool leader = false;
+            uint32_t g_cnt = 0, g_nts = 0, g_te = 0, g_lr = 0, g_nf = 0, g_last = 0;
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                const unsigned long long k = __shfl_sync(0xffffffffu, key, src);
+                const bool in = has && key == k;
+                const uint32_t grp = __ballot_sync(0xffffffffu, in);
+                const uint32_t a1 = __reduce_max_sync(0xffffffffu, in ? nts : 0u), a2 = __reduce_max_sync(0xffffffffu, in ? te : 0u);
+                const uint32_t a3 = __reduce_or_sync(0xffffffffu, in ? lr : 0u), a4 = __reduce_max_sync(0xffffffffu, in ? nfirst_l : 0u);
+                const uint32_t a5 = __reduce_max_sync(0xffffffffu, in ? last_l : 0u);
+                if ((int)lane == src) { leader = true; g_cnt = __popc(grp); g_nts = a1; g_te = a2; g_lr = a3; g_nf = a4; g_last = a5; }
+                todo &= ~grp;
+            }
+            if (leader) {                                    // all leaders of the pass insert in parallel (distinct keys)
+                uint32_t s = ((uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u) >> 25;   // 7 bits: S6_HS = 128
+                bool done = false;
+                for (int probe = 0; probe < S6_PROBES && !done; ++probe, s = (s + 1u) & (S6_HS - 1)) {
+                    unsigned long long curk = sm.hkey[s];
+                    if (curk == SKEY_EMPTY) curk = atomicCAS(&sm.hkey[s], SKEY_EMPTY, key);
+                    if (curk == SKEY_EMPTY || curk == key) {
+                        atomicAdd(&sm.hval[0][s], g_cnt);
+                        atomicMax(&sm.hval[1][s], g_nts);
+                        atomicMax(&sm.hval[2][s], g_te);
+                        if (g_lr) atomicOr(&sm.hval[3][s], g_lr);
+                        atomicMax(&sm.hval[4][s], g_nf);
+                        if (g_last) atomicMax(&sm.hval[5][s], g_last);
+                        done = true;
+                    }
+                }
+                if (!done) fused_global_upsert(cx, ord0, c.start, c.end, tid, proxy, g_cnt, g_nts, g_te, g_lr, g_nf, g_last);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- phase 4: one global upsert per distinct junction of the tile
+    if (!(prm.debug & 8u)) {
+        for (uint32_t s = t; s < (uint32_t)S6_HS; s += THREADS) {
+            const unsigned long long key = sm.hkey[s];
+            if (key == SKEY_EMPTY) continue;
+            const uint32_t start = (uint32_t)(key >> 30), ilen = (uint32_t)(key >> 2) & 0x0fffffffu;
+            fused_global_upsert(cx, ord0, start, start + ilen, base_tid, (uint32_t)key & 3u, sm.hval[0][s], sm.hval[1][s], sm.hval[2][s],
+                                sm.hval[3][s], sm.hval[4][s], sm.hval[5][s]);
+        }
+    }
+    // statistics: N ops seen (before QC), one 64-bit RED per warp
+    my_cands = __reduce_add_sync(0xffffffffu, my_cands);
+    if (lane == 0 && my_cands) atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_TOTAL_CAND64), (unsigned long long)my_cands);
+}
+
+// A/B probe (scan_debug bit 5): reads the five arrays of the batch once with plain 128-bit loads and nothing else —
+// the practical read ceiling of the device for a batch of this size, next to which cigar_scan's time is judged.
+__global__ void __launch_bounds__(256)
+stream_probe_kernel(BatchView b, uint32_t* __restrict__ counters) {
+    const uint4* cols[5] = {reinterpret_cast<const uint4*>(b.tid), reinterpret_cast<const uint4*>(b.pos),
+                            reinterpret_cast<const uint4*>(b.meta), reinterpret_cast<const uint4*>(b.cig_off),
+                            reinterpret_cast<const uint4*>(b.cigar)};
+    const size_t nvec[5] = {b.n_reads / 4u, b.n_reads / 4u, b.n_reads / 4u, b.n_reads / 4u, b.n_ops / 4u};
+    uint32_t acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        size_t i = t0;
+        for (; i + 3 * stride < nvec[c]; i += 4 * stride) {
+            const uint4 x0 = ldg_stream_u4(cols[c] + i), x1 = ldg_stream_u4(cols[c] + i + stride);
+            const uint4 x2 = ldg_stream_u4(cols[c] + i + 2 * stride), x3 = ldg_stream_u4(cols[c] + i + 3 * stride);
+            acc ^= x0.x ^ x0.y ^ x0.z ^ x0.w ^ x1.x ^ x1.y ^ x1.z ^ x1.w ^ x2.x ^ x2.y ^ x2.z ^ x2.w ^ x3.x ^ x3.y ^ x3.z ^ x3.w;
+        }
+        for (; i < nvec[c]; i += stride) { const uint4 x = ldg_stream_u4(cols[c] + i); acc ^= x.x ^ x.y ^ x.z ^ x.w; }
+    }
+    if (acc == 0x9e3779b9u) atomicAdd(&counters[CTR_NOUT], 1u);
+}
+
+// A/B probe (scan_debug bit 6): the SAME access pattern as cigar_scan (512-alignment tiles: 2 KB of each of the four
+// columns + the tile's CIGAR slab, tiles strided over a persistent grid) but with plain register loads and no shared
+// memory: separates "the pattern" from "the cp.async staging".
+template <bool STAGE>
+__global__ void __launch_bounds__(128)
+tile_probe_kernel(BatchView b, uint32_t* __restrict__ counters) {
+    __shared__ uint4 stage[STAGE ? 680 : 1];
+    const uint32_t t = threadIdx.x, n_tiles = b.n_reads / 512u;
+    uint32_t acc = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t base = tile * 512u;
+        const uint4 o = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cig_off + base) + t);
+        const uint4 p = ldg_stream_u4(reinterpret_cast<const uint4*>(b.pos + base) + t);
+        const uint4 m = ldg_stream_u4(reinterpret_cast<const uint4*>(b.meta + base) + t);
+        const uint4 d = ldg_stream_u4(reinterpret_cast<const uint4*>(b.tid + base) + t);
+        const uint32_t lo = __shfl_sync(0xffffffffu, o.x, 0);           // warp 0's lane 0 holds cig_off[base]; good enough for a probe
+        const uint32_t a0 = (lo & ~3u) + 4u * t;
+        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+        if (a0 + 4u <= b.n_ops) c0 = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cigar + a0));
+        if (t < 40u && a0 + 516u <= b.n_ops) c1 = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cigar + a0 + 512u));
+        if (STAGE) {                                          // register-staged copy into shared memory + block barrier per tile
+            __syncthreads();
+            stage[t] = o; stage[128 + t] = p; stage[256 + t] = m; stage[384 + t] = d; stage[512 + t] = c0;
+            if (t < 40u) stage[640 + t] = c1;
+            __syncthreads();
+            acc ^= stage[(t * 7u) % 680u].y;
+        } else {
+            acc ^= o.x ^ o.w ^ p.x ^ p.w ^ m.x ^ m.w ^ d.x ^ d.w ^ c0.x ^ c0.w ^ c1.x ^ c1.w;
+        }
+    }
+    if (acc == 0x9e3779b9u) atomicAdd(&counters[CTR_NOUT], 1u);
+}
+
+// A/B probe (scan_debug bit 18 with bit 6; hint in bits 16-17): the tile pattern through cp.async (LDGSTS) into a 2-deep shared-memory
+// ring, with an optional L2 prefetch-size hint on the copies.  HINT: 0 none, 1 L2::128B, 2 L2::256B.
+template <int HINT>
+__device__ __forceinline__ void cp_async16_hint(void* dst, const void* src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    if (HINT == 2) asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    else if (HINT == 1) asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+template <int HINT>
+__global__ void __launch_bounds__(128)
+tile_probe_async_kernel(BatchView b, uint32_t* __restrict__ counters) {
+    __shared__ uint4 ring[2][768];
+    const uint32_t t = threadIdx.x, n_tiles = b.n_reads / 512u;
+    const uint32_t words_per_tile = (b.n_ops / n_tiles) & ~3u;          // stand-in for the slab address: no dependent load in a probe
+    uint32_t acc = 0, it = 0;
+    auto issue = [&](uint32_t tile, uint4* buf) {
+        const uint32_t base = tile * 512u;
+        cp_async16_hint<HINT>(buf + t, reinterpret_cast<const uint4*>(b.cig_off + base) + t);
+        cp_async16_hint<HINT>(buf + 128 + t, reinterpret_cast<const uint4*>(b.pos + base) + t);
+        cp_async16_hint<HINT>(buf + 256 + t, reinterpret_cast<const uint4*>(b.meta + base) + t);
+        cp_async16_hint<HINT>(buf + 384 + t, reinterpret_cast<const uint4*>(b.tid + base) + t);
+        const uint32_t a0 = tile * words_per_tile + 4u * t;
+        if (a0 + 4u <= b.n_ops) cp_async16_hint<HINT>(buf + 512 + t, b.cigar + a0);
+        if (t < 40u && a0 + 516u <= b.n_ops) cp_async16_hint<HINT>(buf + 640 + t, b.cigar + a0 + 512u);
+    };
+    if (blockIdx.x < n_tiles) issue(blockIdx.x, ring[0]);
+    cp_async_commit();
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        if (tile + gridDim.x < n_tiles) issue(tile + gridDim.x, ring[(it + 1) & 1]);
+        cp_async_commit();
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        acc ^= ring[it & 1][(t * 7u) % 680u].y;
+        __syncthreads();
+    }
+    if (acc == 0x9e3779b9u) atomicAdd(&counters[CTR_NOUT], 1u);
+}
+
+template <int THREADS, int MIN_BLOCKS>
+static void launch_fused_cfg(const BatchView& b, const ScanParams& p, const TableRef& tb, Slot* spill, uint32_t spill_cap,
+                             uint32_t* d_counters, cudaStream_t stream) {
+    static bool once = false;
+    if (!once) {
+        once = true;
+        cudaFuncSetAttribute(cigar_scan_fused_kernel<THREADS, MIN_BLOCKS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (getenv("RTJX_TRACE")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cigar_scan_fused_kernel<THREADS, MIN_BLOCKS>, THREADS, 0);
+            fprintf(stderr, "[rtjx] cigar_scan_fused<%d,%d>: %zu B shared memory, %d blocks/SM, %d SMs\n", THREADS, MIN_BLOCKS,
+                    sizeof(S6Smem<THREADS>), nb, num_sms());
+        }
+    }
+    const uint32_t tiles = (b.n_reads + THREADS * 4 - 1) / (THREADS * 4);
+    cigar_scan_fused_kernel<THREADS, MIN_BLOCKS><<<tiles, THREADS, 0, stream>>>(b, p, tb, spill, spill_cap, d_counters);
+}
+
+bool launch_cigar_scan_fused(const BatchView& b, const ScanParams& p, const TableRef& tb, Slot* spill, uint32_t spill_cap,
+                             uint32_t* d_counters, cudaStream_t stream) {
+    if (b.n_reads == 0) return true;
+    const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
+                            reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
+                            reinterpret_cast<uintptr_t>(b.cigar);
+    if (align & 15u) return false;
+    if (p.debug & 32u) { stream_probe_kernel<<<num_sms() * 8, 256, 0, stream>>>(b, d_counters); return true; }
+    if (p.debug & 64u) {
+        const uint32_t per_sm = ((p.debug >> 8) & 0xffu) ? ((p.debug >> 8) & 0xffu) : 16u;
+        if (p.debug & (1u << 18)) {
+            const uint32_t hint = (p.debug >> 16) & 3u;
+            if (hint == 2) tile_probe_async_kernel<2><<<num_sms() * per_sm, 128, 0, stream>>>(b, d_counters);
+            else if (hint == 1) tile_probe_async_kernel<1><<<num_sms() * per_sm, 128, 0, stream>>>(b, d_counters);
+            else tile_probe_async_kernel<0><<<num_sms() * per_sm, 128, 0, stream>>>(b, d_counters);
+        } else if (p.debug & 128u) tile_probe_kernel<true><<<num_sms() * per_sm, 128, 0, stream>>>(b, d_counters);
+        else tile_probe_kernel<false><<<num_sms() * per_sm, 128, 0, stream>>>(b, d_counters);
+        return true;
+    }
+    switch (p.cfg) {            // A/B configurations; 0 is the production one
+    case 1: launch_fused_cfg<128, 10>(b, p, tb, spill, spill_cap, d_counters, stream); break;
+    case 2: launch_fused_cfg<64, 16>(b, p, tb, spill, spill_cap, d_counters, stream); break;
+    case 3: launch_fused_cfg<256, 4>(b, p, tb, spill, spill_cap, d_counters, stream); break;
+    case 4: launch_fused_cfg<128, 6>(b, p, tb, spill, spill_cap, d_counters, stream); break;
+    default: launch_fused_cfg<128, 8>(b, p, tb, spill, spill_cap, d_counters, stream); break;
+    }
+    return true;
 }
 
 // Re-inserts every occupied slot of `src` (an old table, or the spill list) into the table.

@@ -29,9 +29,12 @@ def tables_equal(gpu, cpu):
         assert bad.size == 0, f"field {f} differs at {bad[:5]}: gpu {gpu[f][bad[:5]]} oracle {cpu[f][bad[:5]]}"
 
 
-def run_gpu_batch(arrs, strandness=0, a=8, m=70, M=500000, contigs=("1", "10", "2"), device_resident=False, split=1):
+def run_gpu_batch(arrs, strandness=0, a=8, m=70, M=500000, contigs=("1", "10", "2"), device_resident=False, split=1,
+                  variant=0, cfg=0, known=True):
+    """variant 0/5 = cigar_scan + junction_merge, 6 = fused cigar_scan (needs the N-op count: known=True)."""
     rt = _rt()
-    ex = rt.JunctionsExtractor(strandness=strandness, min_anchor_length=a, min_intron_length=m, max_intron_length=M)
+    ex = rt.JunctionsExtractor(strandness=strandness, min_anchor_length=a, min_intron_length=m, max_intron_length=M,
+                               scan_variant=variant, scan_cfg=cfg)
     ex.set_contigs(list(contigs))
     tid, pos, meta, off, cigar = arrs
     n = len(tid)
@@ -51,7 +54,7 @@ def run_gpu_batch(arrs, strandness=0, a=8, m=70, M=500000, contigs=("1", "10", "
             ex.scan_batch(*dev, first_ordinal=int(lo), n_junction_ops=synth.count_n_ops(c))
             torch.cuda.synchronize()
         else:
-            ex.scan_batch(*sub, first_ordinal=int(lo))
+            ex.scan_batch(*sub, first_ordinal=int(lo), n_junction_ops=synth.count_n_ops(c) if known else 0)
     table = ex.junction_table()
     buf = io.StringIO()
     ex.print_all_junctions(buf)
@@ -66,11 +69,13 @@ def run_oracle_batch(arrs, strandness=0, a=8, m=70, M=500000, contigs=("1", "10"
     return o.table(), o.bed12()
 
 
+@pytest.mark.parametrize("variant,known", [(0, True), (6, True), (0, False)])
 @pytest.mark.parametrize("strandness", [0, 1, 2])
 @pytest.mark.parametrize("seed", [1, 2, 3])
-def test_random_batches_match_oracle(seed, strandness):
+def test_random_batches_match_oracle(seed, strandness, variant, known):
     arrs = synth.random_batch(seed, 20000)
-    g_tab, g_bed, _ = run_gpu_batch(arrs, strandness)
+    g_tab, g_bed, st = run_gpu_batch(arrs, strandness, variant=variant, known=known)
+    assert st["candidates"] == synth.count_n_ops(arrs[4]) - 1      # read 3 has tid -1: its N op is never emitted
     o_tab, o_bed = run_oracle_batch(arrs, strandness)
     tables_equal(g_tab, o_tab)
     assert g_bed == o_bed
@@ -83,7 +88,31 @@ def test_split_batches_and_device_resident(device_resident):
     o_tab, o_bed = run_oracle_batch(arrs, 0)
     tables_equal(g_tab, o_tab)
     assert g_bed == o_bed
-    assert st["kernel_launches"] >= 14 and st["reads"] == 50000
+    assert st["kernel_launches"] >= 7 and st["reads"] == 50000
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("n_reads", [1, 511, 512, 513, 4099, 70001])
+def test_fused_scan_tile_configs_and_ragged_sizes(cfg, n_reads):
+    """Every tile configuration of the fused kernel, batch sizes around the tile boundaries, dense splicing
+    (alignments outside the staged slab window read their ops from global memory)."""
+    arrs = synth.random_batch(100 + n_reads, n_reads, spliced_frac=0.6 if n_reads < 5000 else 0.2)
+    g_tab, g_bed, _ = run_gpu_batch(arrs, 0, variant=6, cfg=cfg)
+    o_tab, o_bed = run_oracle_batch(arrs, 0)
+    tables_equal(g_tab, o_tab)
+    assert g_bed == o_bed
+
+
+def test_fused_scan_large_batch_matches_two_kernel_path():
+    """300k reads, 1200 junctions: fused (6) and two-kernel (5) paths against the oracle on a device-resident batch."""
+    arrs = synth.random_batch(9, 300000, spliced_frac=0.1, catalog_per_contig=400)
+    big = tuple(arrs)
+    g_tab, g_bed, _ = run_gpu_batch(big, 0, variant=6, device_resident=True, split=1)
+    v5_tab, v5_bed, _ = run_gpu_batch(big, 0, variant=5, device_resident=True, split=1)
+    o_tab, o_bed = run_oracle_batch(big, 0)
+    tables_equal(g_tab, o_tab)
+    tables_equal(v5_tab, o_tab)
+    assert g_bed == o_bed == v5_bed
 
 
 @pytest.mark.parametrize("a,m,M", [(0, 0, 0xFFFFFFFF), (30, 70, 500000), (8, 8039, 8039), (1, 1, 69)])
@@ -134,11 +163,12 @@ def test_hot_junction_and_long_cigars():
     reads.append((0, 900000, 0, 60, ord("-"), long_ops + C("5M")))
     reads.append((1, 10, 0, 60, ord("-"), C("10M") * 40000 + C("70N10M")))
     arrs = synth.batch_from_reads(reads)
-    g_tab, g_bed, _ = run_gpu_batch(arrs, 0)
     o_tab, o_bed = run_oracle_batch(arrs, 0)
-    tables_equal(g_tab, o_tab)
-    assert g_bed == o_bed
-    assert g_tab["read_count"].max() == 200000
+    for variant in (6, 5):
+        g_tab, g_bed, _ = run_gpu_batch(arrs, 0, variant=variant)
+        tables_equal(g_tab, o_tab)
+        assert g_bed == o_bed
+        assert g_tab["read_count"].max() == 200000
 
 
 def test_many_unique_junctions_grow_table():
