@@ -37,6 +37,9 @@ struct jxo {
     int record; jxo_candidate* cand; size_t n_cand, cap_cand;
     uint64_t reads_seen;
     char errbuf[256];
+    /* FASTA (intron-motif strand inference, junctions_extractor.cc:325-359,548-584) */
+    int has_fasta, fasta_error;
+    int32_t n_seq; char** seq_name; uint8_t** seq; int64_t* seq_len;
 };
 
 jxo_t* jxo_new(uint32_t min_anchor, uint32_t min_intron, uint32_t max_intron,
@@ -55,7 +58,92 @@ jxo_t* jxo_new(uint32_t min_anchor, uint32_t min_intron, uint32_t max_intron,
 void jxo_free(jxo_t* o) {
     if (!o) return;
     for (int32_t i = 0; i < o->n_contig; ++i) free(o->contig[i]);
-    free(o->contig); free(o->e); free(o->bucket); free(o->cand); free(o);
+    free(o->contig); free(o->e); free(o->bucket); free(o->cand);
+    for (int32_t i = 0; i < o->n_seq; ++i) { free(o->seq_name[i]); free(o->seq[i]); }
+    free(o->seq_name); free(o->seq); free(o->seq_len);
+    free(o);
+}
+
+/* FASTA as faidx sees it (htslib faidx.c:82-155 fai_build_core): a sequence's name is the header up to the first
+ * white space, its bases are the isgraph() characters of the following lines, duplicates of a name are ignored.
+ * Returns 0, or -1 if the file cannot be read. */
+int jxo_set_fasta(jxo_t* o, const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return -1;
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    char* buf = (char*)malloc((size_t)sz + 1);
+    if (fread(buf, 1, (size_t)sz, f) != (size_t)sz) { fclose(f); free(buf); return -1; }
+    fclose(f); buf[sz] = 0;
+    long i = 0;
+    while (i < sz) {
+        if (buf[i] != '>') { ++i; continue; }
+        long j = i + 1;
+        while (j < sz && buf[j] != '\n' && (buf[j] == ' ' || buf[j] == '\t')) ++j;    /* leading blanks before the name */
+        long n0 = j;
+        while (j < sz && !(buf[j] == ' ' || buf[j] == '\t' || buf[j] == '\n' || buf[j] == '\r' || buf[j] == '\v' || buf[j] == '\f')) ++j;
+        char* name = strndup(buf + n0, (size_t)(j - n0));
+        while (j < sz && buf[j] != '\n') ++j;
+        long k = j;
+        while (k < sz && buf[k] != '>') ++k;            /* sequence lines run to the next header (a '>' inside a line is not handled) */
+        int dup = 0;
+        for (int32_t q = 0; q < o->n_seq; ++q) if (!strcmp(o->seq_name[q], name)) dup = 1;
+        if (!dup) {
+            uint8_t* sq = (uint8_t*)malloc((size_t)(k - j) + 1);
+            int64_t l = 0;
+            for (long q = j; q < k; ++q) if ((unsigned char)buf[q] > 32 && (unsigned char)buf[q] < 127) sq[l++] = (uint8_t)buf[q];
+            o->seq_name = (char**)realloc(o->seq_name, sizeof(char*) * (size_t)(o->n_seq + 1));
+            o->seq = (uint8_t**)realloc(o->seq, sizeof(uint8_t*) * (size_t)(o->n_seq + 1));
+            o->seq_len = (int64_t*)realloc(o->seq_len, sizeof(int64_t) * (size_t)(o->n_seq + 1));
+            o->seq_name[o->n_seq] = name; o->seq[o->n_seq] = sq; o->seq_len[o->n_seq] = l; o->n_seq++;
+        } else free(name);
+        i = k;
+    }
+    free(buf);
+    o->has_fasta = 1;
+    return 0;
+}
+const char* jxo_error(const jxo_t* o) { return o->fasta_error ? o->errbuf : NULL; }
+
+/* fai_fetch (faidx.c:341-415) for "chrom:b-e" with 1-based inclusive b, e: bases [b-1, e) clipped to the sequence. */
+static int fetch2(const jxo_t* o, int32_t q, int64_t b1, int64_t e1, uint8_t out[2]) {
+    int64_t len = o->seq_len[q], beg = b1, end = e1;
+    if (beg > 0) --beg;
+    if (beg >= len) beg = len;
+    if (end >= len) end = len;
+    if (beg > end) beg = end;
+    int n = 0;
+    for (int64_t x = beg; x < end && n < 2; ++x) out[n++] = o->seq[q][x];
+    return (int)(end - beg);
+}
+static uint8_t comp_base(uint8_t c) {                    /* common.h:59-83 rev_comp */
+    switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return 'N'; }
+}
+/* get_splice_site (:564-584) + set_junction_strand_intron_motif (:325-342).  prev = strand the Junction object
+ * carries from the previous junction of the same read (0 for the first).  Returns '+', '-' or '?'. */
+static uint8_t motif_strand(jxo_t* o, int32_t tid, uint32_t start, uint32_t end, uint8_t prev) {
+    const char* chrom = jxo_contig(o, tid);
+    int32_t q = -1;
+    for (int32_t i = 0; i < o->n_seq; ++i) if (!strcmp(o->seq_name[i], chrom)) { q = i; break; }
+    if (q < 0) {                                          /* fai_fetch returns NULL -> runtime_error (:553-555) */
+        if (!o->fasta_error) {
+            o->fasta_error = 1;
+            snprintf(o->errbuf, sizeof o->errbuf, "Unable to extract FASTA sequence for position %s:%u-%u\n\n", chrom,
+                     start + 1u, start + 2u);
+        }
+        return '?';
+    }
+    uint8_t s1[2] = {0, 0}, s2[2] = {0, 0};
+    int l1 = fetch2(o, q, (int64_t)(uint32_t)(start + 1u), (int64_t)(uint32_t)(start + 2u), s1);
+    int l2 = fetch2(o, q, (int64_t)(uint32_t)(end + 1u - 2u), (int64_t)(uint32_t)(end + 1u - 1u), s2);
+    if (l1 != 2 || l2 != 2) return '?';                   /* a shorter string cannot equal any 5-character motif */
+    uint8_t m[4];
+    if (prev == '-') { m[0] = comp_base(s2[1]); m[1] = comp_base(s2[0]); m[2] = comp_base(s1[1]); m[3] = comp_base(s1[0]); }
+    else { m[0] = s1[0]; m[1] = s1[1]; m[2] = s2[0]; m[3] = s2[1]; }
+    static const char* plus[3] = {"GTAG", "GCAG", "ATAC"};
+    static const char* minus[3] = {"CTAC", "CTGC", "GTAT"};
+    for (int i = 0; i < 3; ++i) if (!memcmp(m, plus[i], 4)) return '+';
+    for (int i = 0; i < 3; ++i) if (!memcmp(m, minus[i], 4)) return '-';
+    return '?';
 }
 
 void jxo_set_contigs(jxo_t* o, int32_t n, const char* const* names) {
@@ -143,8 +231,18 @@ static uint8_t read_strand(const jxo_t* o, uint32_t flag, uint8_t strand_byte) {
     return first_strand ? '+' : '-';
 }
 
+/* `strand` is the read's XS/flag strand; with a FASTA the motif decides first and the read's strand is only the
+ * fall-back for '?' (set_junction_strand :345-359).  *jstrand is the strand field of the reference's reused
+ * Junction object j1. */
 static void emit(jxo_t* o, int32_t tid, uint32_t start, uint32_t end, uint32_t ts, uint32_t te,
-                 uint8_t strand, uint64_t read_index, uint32_t k) {
+                 uint8_t strand, uint64_t read_index, uint32_t k, uint8_t* jstrand) {
+    if (o->fasta_error) return;                           /* the reference has thrown: nothing else is added */
+    if (o->has_fasta) {
+        uint8_t m = motif_strand(o, tid, start, end, *jstrand);
+        if (o->fasta_error) return;
+        if (m != '?') strand = m;
+    }
+    *jstrand = strand;
     if (o->record) {
         if (o->n_cand == o->cap_cand) {
             o->cap_cand = o->cap_cand ? o->cap_cand * 2 : 1024;
@@ -170,6 +268,7 @@ void jxo_read(jxo_t* o, int32_t tid, int32_t pos, uint32_t flag, uint8_t strand_
     int started = 0;
     uint32_t open_k = 0;  /* index of the N op that opened the pending junction */
     uint8_t strand = read_strand(o, flag, strand_byte);
+    uint8_t jstrand = 0;                                          /* j1.strand == "" before the first junction */
     for (uint32_t i = 0; i < n_cigar; ++i) {
         uint32_t op = cigar[i] & 0xf, len = cigar[i] >> 4;         /* htslib/sam.h:75-83 */
         switch (op) {
@@ -177,7 +276,7 @@ void jxo_read(jxo_t* o, int32_t tid, int32_t pos, uint32_t flag, uint8_t strand_
             if (!started) {
                 end = start + len; thick_end = end; started = 1; open_k = i;
             } else {
-                emit(o, tid, start, end, thick_start, thick_end, strand, ridx, open_k);
+                emit(o, tid, start, end, thick_start, thick_end, strand, ridx, open_k, &jstrand);
                 thick_start = end; start = thick_end; end = start + len; thick_end = end;
                 started = 1; open_k = i;
             }
@@ -188,7 +287,7 @@ void jxo_read(jxo_t* o, int32_t tid, int32_t pos, uint32_t flag, uint8_t strand_
         case 2: case 8: /* D, X :440-459 */
             if (!started) { start += len; thick_start = start; }
             else {
-                emit(o, tid, start, end, thick_start, thick_end, strand, ridx, open_k);
+                emit(o, tid, start, end, thick_start, thick_end, strand, ridx, open_k, &jstrand);
                 start = thick_end + len; thick_start = start;
             }
             started = 0;
@@ -196,7 +295,7 @@ void jxo_read(jxo_t* o, int32_t tid, int32_t pos, uint32_t flag, uint8_t strand_
         case 1: case 4: /* I, S :460-478 */
             if (!started) thick_start = start;
             else {
-                emit(o, tid, start, end, thick_start, thick_end, strand, ridx, open_k);
+                emit(o, tid, start, end, thick_start, thick_end, strand, ridx, open_k, &jstrand);
                 start = thick_end; thick_start = start;
             }
             started = 0;
@@ -208,7 +307,7 @@ void jxo_read(jxo_t* o, int32_t tid, int32_t pos, uint32_t flag, uint8_t strand_
         }
     }
     if (started)                                                  /* :485-495 */
-        emit(o, tid, start, end, thick_start, thick_end, strand, ridx, open_k);
+        emit(o, tid, start, end, thick_start, thick_end, strand, ridx, open_k, &jstrand);
 }
 
 void jxo_batch(jxo_t* o, uint32_t n_reads, const int32_t* tid, const int32_t* pos,
@@ -700,5 +799,6 @@ done:
     free(off); free(rec.data); bai_free(idx);
     if (fp->file && fp->size) munmap((void*)fp->file, fp->size);
     free(fp);
+    if (rc == 0 && o->fasta_error) { if (err) *err = o->errbuf; return 1; }   /* get_reference_sequence threw (:553-555) */
     return rc;
 }

@@ -18,12 +18,15 @@ int main(int argc, char** argv) {
         case 'o': out = optarg; break;
         case 'r': reg = optarg; break;
         case 't': tag = optarg; break;
-        case 's': s = !strcmp(optarg, "XS") ? 0 : !strcmp(optarg, "RF") ? 1 : !strcmp(optarg, "FR") ? 2 : -1; break;
+        case 's': s = !strcmp(optarg, "XS") ? 0 : !strcmp(optarg, "RF") ? 1 : !strcmp(optarg, "FR") ? 2 :
+                      !strcmp(optarg, "intron-motif") ? 3 : -1; break;
         default: return 1;
         }
     }
-    if (optind >= argc || s < 0) { fprintf(stderr, "usage: jx_oracle -s XS|RF|FR [-a -m -M -o -r -t] in.bam\n"); return 1; }
+    if (optind >= argc || s < 0) { fprintf(stderr, "usage: jx_oracle -s XS|RF|FR|intron-motif [-a -m -M -o -r -t] in.bam [ref.fa]\n"); return 1; }
+    if (s == 3 && optind + 1 >= argc) { fprintf(stderr, "Strandness mode 'intron-motif' requires a fasta file!\n\n"); return 1; }
     jxo_t* o = jxo_new(a, m, M, s, tag);
+    if (optind + 1 < argc && jxo_set_fasta(o, argv[optind + 1])) { fprintf(stderr, "cannot read %s\n", argv[optind + 1]); return 1; }
     const char* err = NULL;
     if (jxo_extract_bam(o, argv[optind], reg, &err)) { fprintf(stderr, "%s", err ? err : "error\n"); return 1; }
     if (out) jxo_write_bed12_path(o, out); else jxo_write_bed12(o, stdout);

@@ -88,7 +88,39 @@ def build():
     print(f"wrote {len(manifest)} golden outputs to {OUT}")
 
 
+MOTIF_RUNS = [
+    ("kat.bam", "kat", ["-s", "XS"]), ("kat.bam", "kat", ["-s", "intron-motif", "-a", "0"]),
+    ("kat.bam", "kat", ["-s", "RF", "-m", "0", "-a", "0", "-M", "4294967295"]),
+    ("synth.bam", "synth", ["-s", "XS"]), ("synth.bam", "synth", ["-s", "RF", "-a", "20"]),
+    ("synth.bam", "synth", ["-s", "intron-motif"]), ("synth.bam", "synth", ["-s", "FR", "-r", "2"]),
+    ("kat.bam", "kat_no10", ["-s", "XS"]),
+]
+
+
+def build_motif():
+    """tests/golden/motif/: the reference with a FASTA as second positional argument (strand from the intron motif,
+    junctions_extractor.cc:325-359) on the FASTAs tests/fasta_fixture.py generates."""
+    import tempfile
+    import fasta_fixture as ff
+    out_dir = os.path.join(HERE, "motif")
+    os.makedirs(out_dir, exist_ok=True)
+    manifest = []
+    with tempfile.TemporaryDirectory() as tmp:
+        fas = {"kat": ff.write_kat_fasta(os.path.join(tmp, "kat.fa")), "synth": ff.write_synth_fasta(os.path.join(tmp, "synth.fa")),
+               "kat_no10": ff.write_kat_fasta(os.path.join(tmp, "kat_no10.fa"), drop="10")}
+        for i, (bam, fa, args) in enumerate(MOTIF_RUNS):
+            p = subprocess.run([REF, "junctions", "extract"] + args + [os.path.join(OUT, bam), fas[fa]], capture_output=True, text=True)
+            name = f"motif.{i}.bed"
+            open(os.path.join(out_dir, name), "w").write(p.stdout)
+            err = [l for l in p.stderr.splitlines() if l.startswith("Unable")]
+            manifest.append(f"{bam}\t{fa}\t{name}\t{p.returncode}\t{' '.join(args)}\t{err[0] if err else ''}")
+    open(os.path.join(out_dir, "MANIFEST.tsv"), "w").write("\n".join(manifest) + "\n")
+    print(f"wrote {len(manifest)} intron-motif golden outputs to {out_dir}")
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         sys.exit("oracle/_ref/regtools_ref missing: run `make -C oracle ref` in the dev container first")
-    build()
+    if "--motif-only" not in sys.argv:
+        build()
+    build_motif()

@@ -45,6 +45,10 @@ def lib():
         l.jxo_new.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_char_p]
         l.jxo_free.argtypes = [C.c_void_p]
         l.jxo_set_contigs.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p)]
+        l.jxo_set_fasta.restype = C.c_int
+        l.jxo_set_fasta.argtypes = [C.c_void_p, C.c_char_p]
+        l.jxo_error.restype = C.c_char_p
+        l.jxo_error.argtypes = [C.c_void_p]
         l.jxo_batch.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 5
         l.jxo_add.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint8]
         l.jxo_record_candidates.argtypes = [C.c_void_p, C.c_int]
@@ -68,11 +72,17 @@ def lib():
 class Oracle:
     """CPU restatement of JunctionsExtractor (oracle/jx_oracle.c)."""
 
-    def __init__(self, min_anchor=8, min_intron=70, max_intron=500000, strandness=0, tag="XS", contigs=None):
+    def __init__(self, min_anchor=8, min_intron=70, max_intron=500000, strandness=0, tag="XS", contigs=None, fasta=None):
         self.l = lib()
         self.h = C.c_void_p(self.l.jxo_new(min_anchor, min_intron, max_intron, strandness, tag.encode()))
         if contigs is not None:
             self.set_contigs(contigs)
+        if fasta is not None and self.l.jxo_set_fasta(self.h, os.fsencode(fasta)):
+            raise RuntimeError(f"cannot read {fasta}")
+
+    def error(self):
+        e = self.l.jxo_error(self.h)
+        return e.decode() if e else None
 
     def set_contigs(self, names):
         arr = (C.c_char_p * len(names))(*[n.encode() for n in names])

@@ -10,10 +10,10 @@ from oracle_py import Oracle, ref_available, ref_extract
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 HCC = os.path.join(GOLD, "hcc1395", "test_hcc1395.bam")
-MODES = {"XS": 0, "RF": 1, "FR": 2}
+MODES = {"XS": 0, "RF": 1, "FR": 2, "intron-motif": 3}
 
 
-def run_oracle(bam, args):
+def run_oracle(bam, args, fasta=None, check=True):
     a, m, M, s, r, t = 8, 70, 500000, 0, ".", "XS"
     it = iter(args)
     for k in it:
@@ -24,8 +24,14 @@ def run_oracle(bam, args):
         elif k == "-s": s = MODES[v]
         elif k == "-r": r = v
         elif k == "-t": t = v
-    o = Oracle(a & 0xFFFFFFFF, m & 0xFFFFFFFF, M & 0xFFFFFFFF, s, t)
-    o.extract_bam(bam, r)
+    o = Oracle(a & 0xFFFFFFFF, m & 0xFFFFFFFF, M & 0xFFFFFFFF, s, t, fasta=fasta)
+    if check:
+        o.extract_bam(bam, r)
+    else:
+        try:
+            o.extract_bam(bam, r)
+        except RuntimeError as e:
+            o.failed = str(e)
     return o
 
 
@@ -119,3 +125,24 @@ def test_oracle_vs_live_reference_on_fresh_bam(args, tmp_path):
     rc, out = ref_extract(bam, args)
     assert rc == 0
     assert run_oracle(bam, args).bed12() == out
+
+
+from conftest import motif_manifest  # noqa: E402
+
+
+@pytest.mark.parametrize("bam,fa,out,rc,args,err", motif_manifest())
+def test_oracle_intron_motif_goldens(bam, fa, out, rc, args, err, motif_fastas):
+    """FASTA given: strand from the intron motif, XS/flag only for '?', reverse-complement quirk of the reused
+    Junction object, clipped fetches, missing contig -> runtime_error (junctions_extractor.cc:325-359,548-584)."""
+    o = run_oracle(os.path.join(GOLD, "kat", bam), args, fasta=motif_fastas[fa], check=False)
+    if rc:
+        assert getattr(o, "failed", "").startswith(err)
+    else:
+        assert o.bed12() == open(os.path.join(GOLD, "motif", out)).read()
+
+
+def test_fasta_fixtures_are_reproducible(motif_fastas):
+    import hashlib
+    got = {k: hashlib.sha256(open(v, "rb").read()).hexdigest() for k, v in motif_fastas.items()}
+    want = dict(line.split() for line in open(os.path.join(GOLD, "motif", "FASTA.sha256")))
+    assert got == want
