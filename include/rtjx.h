@@ -31,10 +31,10 @@ typedef enum {
     RTJX_E_OPEN_INDEX  = -3,  /* "Unable to open BAM/SAM index. ..."     junctions_extractor.cc:510 */
     RTJX_E_REGION      = -4,  /* "Unable to iterate to region within BAM." junctions_extractor.cc:521 */
     RTJX_E_CUDA        = -5,  /* no device / CUDA runtime failure                                   */
-    RTJX_E_UNSUPPORTED = -6,  /* FASTA (intron-motif), -b barcodes, CRAM/SAM, .csi                  */
+    RTJX_E_UNSUPPORTED = -6,  /* -b barcodes, CRAM/SAM, .csi, compressed FASTA                      */
     RTJX_E_NOMEM       = -7,
     RTJX_E_STATE       = -8,  /* call order violated                                                */
-    RTJX_E_IO          = -9
+    RTJX_E_IO          = -9   /* also "Unable to extract FASTA sequence ..."  junctions_extractor.cc:553 */
 } rtjx_status;
 
 typedef struct rtjx_handle rtjx_t;
@@ -46,7 +46,8 @@ typedef struct {
     const char* bam;              /* bam_      positional 1; may be NULL for add-only handles  */
     const char* region;           /* region_   -r, default "."                                 */
     const char* strand_tag;       /* strand_tag_ -t, default "XS" (first two chars used)       */
-    const char* fasta;            /* ref_      positional 2: must be NULL (RTJX_E_UNSUPPORTED) */
+    const char* fasta;            /* ref_      positional 2: uncompressed FASTA; strand from the
+                                     intron motif first, -s only for '?' (junctions_extractor.cc:325-359) */
     const char* barcode_out;      /* -b: must be NULL (RTJX_E_UNSUPPORTED)                     */
     int32_t     strandness;       /* -s: 0 XS, 1 RF, 2 FR, 3 intron-motif(no FASTA => as FR)   */
     uint32_t    min_anchor;       /* -a, default 8                                             */

@@ -39,6 +39,7 @@ Engine::Engine(const rtjx_params& p) : prm_(p) {
     region_ = p.region ? p.region : ".";
     tag_ = (p.strand_tag && p.strand_tag[0]) ? p.strand_tag : "XS";
     if (tag_.size() < 2) tag_.push_back('\0');
+    fasta_path_ = p.fasta ? p.fasta : "";
     prm_.bam = prm_.region = prm_.strand_tag = prm_.fasta = prm_.barcode_out = nullptr;
     memset(&stats_, 0, sizeof stats_);
 }
@@ -54,6 +55,7 @@ Engine::~Engine() {
             cached_dev_free(d.tid); cached_dev_free(d.pos); cached_dev_free(d.meta); cached_dev_free(d.cig_off); cached_dev_free(d.cigar);
             if (d.free_ev) cudaEventDestroy(d.free_ev);
         }
+        cached_dev_free(d_genome_); cached_dev_free(d_g_off_); cached_dev_free(d_g_len_);
         cached_dev_free(d_counters_); cached_host_free(h_counters_);
         cached_dev_free(d_table_); cached_dev_free(d_spill_); cached_dev_free(d_cands_); cached_dev_free(d_tile_off_); cached_dev_free(d_regions_); cached_dev_free(d_region_cnt_);
         cached_dev_free(d_out_); cached_dev_free(d_ws_); cached_dev_free(d_rank_); cached_host_free(h_final_); cached_dev_free(d_slot_list_);
@@ -72,6 +74,8 @@ ScanParams Engine::scan_params() const {
     s.debug = prm_.scan_debug ? prm_.scan_debug : dbg;
     s.variant = prm_.scan_variant ? prm_.scan_variant : (env_variant ? env_variant : 5);
     s.cfg = prm_.scan_cfg ? prm_.scan_cfg : env_cfg;
+    s.genome = d_genome_; s.g_off = d_g_off_; s.g_len = d_g_len_; s.g_n = d_genome_ ? g_n_ : 0u;
+    if (d_genome_) { s.variant = 5; s.cfg = 0; }      // the intron-motif mode lives in the default scan kernel only
     return s;
 }
 
@@ -110,6 +114,11 @@ int Engine::sync_counters(cudaStream_t stream) {
     stats_.d2h_bytes += CTR_COUNT * sizeof(uint32_t);
     if (h_counters_[CTR_CAND_OVERFLOW] || h_counters_[CTR_NSPILL])
         return fail(RTJX_E_STATE, "internal: candidate buffer or junction table overflowed");
+    if (h_counters_[CTR_GENOME_MISS]) {               // get_reference_sequence threw (junctions_extractor.cc:553-555)
+        const uint32_t s0 = h_counters_[CTR_GENOME_MISS_POS];
+        return fail(RTJX_E_IO, std::string("Unable to extract FASTA sequence for position ") + contig((int32_t)h_counters_[CTR_GENOME_MISS] - 1) +
+                                   ":" + std::to_string(s0 + 1u) + "-" + std::to_string(s0 + 2u) + "\n\n");
+    }
     unique_upper_ = h_counters_[CTR_NUNIQUE];
     stats_.candidates = (uint64_t)h_counters_[CTR_TOTAL_CAND64 + 1] << 32 | h_counters_[CTR_TOTAL_CAND64];
     return RTJX_OK;
@@ -157,13 +166,52 @@ int Engine::ensure_table(uint32_t incoming, cudaStream_t stream) {
     return RTJX_OK;
 }
 
+// The genome goes to HBM once per handle; the tid -> sequence map follows the contig list (header of the BAM, or
+// the names interned by add-only handles).
+int Engine::ensure_genome() {
+    if (fasta_path_.empty()) return RTJX_OK;
+    if (!genome_loaded_) {
+        std::string err;
+        if (!load_fasta(fasta_path_, &genome_, &err)) return fail(RTJX_E_IO, err);
+        CK(cached_dev_malloc(&d_genome_, genome_.bases.size()));
+        CK(cudaMemcpy(d_genome_, genome_.bases.data(), genome_.bases.size(), cudaMemcpyHostToDevice));
+        stats_.h2d_bytes += genome_.bases.size();
+        std::vector<uint8_t>().swap(genome_.bases);
+        genome_loaded_ = true;
+    }
+    if (genome_map_for_ != contigs_ || !d_g_off_) {
+        const size_t n = std::max<size_t>(contigs_.size(), 1);
+        if (n > g_cap_) {
+            CK(cudaDeviceSynchronize());
+            cached_dev_free(d_g_off_); cached_dev_free(d_g_len_); d_g_off_ = d_g_len_ = nullptr;
+            g_cap_ = (uint32_t)(n * 2 + 64);
+            CK(cached_dev_malloc(&d_g_off_, (size_t)g_cap_ * 8)); CK(cached_dev_malloc(&d_g_len_, (size_t)g_cap_ * 8));
+        }
+        std::vector<unsigned long long> off(n, 0ull), len(n, ~0ull);
+        for (size_t t = 0; t < contigs_.size(); ++t) {
+            const int q = genome_.find(contigs_[t]);
+            if (q >= 0) { off[t] = genome_.offset[(size_t)q]; len[t] = genome_.length[(size_t)q]; }
+        }
+        CK(cudaDeviceSynchronize());                  // kernels in flight may still read the old map
+        CK(cudaMemcpy(d_g_off_, off.data(), n * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_g_len_, len.data(), n * 8, cudaMemcpyHostToDevice));
+        g_n_ = (uint32_t)contigs_.size();
+        genome_map_for_ = contigs_;
+    }
+    return RTJX_OK;
+}
+
 // cand_bound = number of N ops in the batch when the producer knows it (the feeder counts them while
 // copying CIGARs); 0 = unknown: size the candidate buffer for the worst case and read the real
 // count back after cigar_scan (one stream synchronisation) before sizing the merge.
 int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaStream_t stream) {
     int rc;
     const bool known = cand_bound != 0;
+    if ((rc = ensure_genome())) return rc;
     const ScanParams sp = scan_params();
+    if (sp.genome && ((reinterpret_cast<uintptr_t>(v.tid) | reinterpret_cast<uintptr_t>(v.pos) | reinterpret_cast<uintptr_t>(v.meta) |
+                       reinterpret_cast<uintptr_t>(v.cig_off) | reinterpret_cast<uintptr_t>(v.cigar)) & 15u))
+        return fail(RTJX_E_ARG, "device batch arrays must be 16-byte aligned when a FASTA is given");
     if (sp.variant == 6 && known && ((reinterpret_cast<uintptr_t>(v.tid) | reinterpret_cast<uintptr_t>(v.pos) |
                                       reinterpret_cast<uintptr_t>(v.meta) | reinterpret_cast<uintptr_t>(v.cig_off) |
                                       reinterpret_cast<uintptr_t>(v.cigar)) & 15u) == 0) {
@@ -417,6 +465,13 @@ int Engine::open_bam(std::unique_ptr<BamFile>* bam, BaiIndex* idx, IterSpec* spe
 }
 
 int Engine::run() {
+    int rc = run_impl();
+    // with a FASTA the reference throws inside identify_junctions_from_BAM when a junction lies on a contig the FASTA lacks
+    if (rc == RTJX_OK && !fasta_path_.empty() && dev_ready_) rc = sync_counters(stream_);
+    return rc;
+}
+
+int Engine::run_impl() {
     const double t_start = now_s();
     std::unique_ptr<BamFile> bam; BaiIndex idx; IterSpec spec;
     int rc = open_bam(&bam, &idx, &spec);

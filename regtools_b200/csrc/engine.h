@@ -6,6 +6,7 @@
 #pragma once
 #include "../../include/rtjx.h"
 #include "bam_feeder.h"
+#include "fasta.h"
 #include "jx_device.cuh"
 
 #include <memory>
@@ -19,7 +20,7 @@ public:
     explicit Engine(const rtjx_params& p);
     ~Engine();
 
-    int run();
+    int run();                                   // identify_junctions_from_BAM
     int scan_batch(const rtjx_batch& b, int location, cudaStream_t stream);
     int add(const rtjx_candidate* c, size_t n);
     int finalize(cudaStream_t stream);
@@ -45,6 +46,8 @@ public:
 private:
     friend struct EngineSink;
     int ensure_device();
+    int run_impl();
+    int ensure_genome();                         // FASTA -> HBM (once) + per-contig map (whenever the contig list changed)
     int ensure_cands(uint32_t n);
     int ensure_table(uint32_t incoming_bound, cudaStream_t stream);
     int process_device_batch(const BatchView& v, uint32_t cand_bound, cudaStream_t stream);
@@ -56,7 +59,7 @@ private:
     ScanParams scan_params() const;
 
     rtjx_params prm_;
-    std::string bam_path_, region_, tag_;
+    std::string bam_path_, region_, tag_, fasta_path_;
     std::string err_;
     std::vector<std::string> contigs_;
     std::string unknown_contig_;
@@ -76,6 +79,13 @@ private:
     uint64_t unique_upper_ = 0;                 // host-side upper bound of occupied slots
     uint64_t add_ord_ = 0;                      // ordinal of the next rtjx_add candidate
     bool dirty_ = false;                        // device table changed since the last finalize
+
+    // intron-motif mode: genome in HBM (one byte per base) and the BAM-tid -> sequence map
+    bool genome_loaded_ = false;
+    FastaGenome genome_;                        // names / offsets / lengths (bases are dropped after the upload)
+    uint8_t* d_genome_ = nullptr;
+    unsigned long long* d_g_off_ = nullptr; unsigned long long* d_g_len_ = nullptr; uint32_t g_n_ = 0, g_cap_ = 0;
+    std::vector<std::string> genome_map_for_;   // contig list the device map was built for
 
     // device batch ring for host-resident input
     struct DevBatch {

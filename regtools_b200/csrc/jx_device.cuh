@@ -50,6 +50,11 @@ struct ScanParams {
     uint32_t debug;               // developer switches for A/B measurements (0 in production)
     int32_t  variant;             // cigar_scan variant: 5 = scan -> candidates -> junction_merge (default), 6 = fused scan + table update
     int32_t  cfg;                 // tile configuration of the variant (0 = production)
+    // intron-motif strand mode (a FASTA was given): the genome as one byte per base in HBM.  NULL = off.
+    const uint8_t*            genome;
+    const unsigned long long* g_off;      // per BAM tid: start of the contig in `genome`
+    const unsigned long long* g_len;      // per BAM tid: length, ~0ull = the FASTA has no such sequence
+    uint32_t                  g_n;        // entries of g_off / g_len
 };
 
 struct BatchView {
@@ -139,6 +144,7 @@ void launch_feed_finish(const uint8_t* data, int64_t data_len, uint8_t* next_dat
 
 // counters layout in d_counters (uint32 each)
 enum { CTR_NCAND = 0, CTR_CAND_OVERFLOW = 1, CTR_NUNIQUE = 2, CTR_NSPILL = 3, CTR_NOUT = 4, CTR_NREGION = 5 /* candidates in regions */,
-       CTR_TOTAL_CAND64 = 6 /* 64-bit, two words */, CTR_COUNT = 8 };
+       CTR_TOTAL_CAND64 = 6 /* 64-bit, two words */, CTR_GENOME_MISS = 8 /* 1 + tid of a contig the FASTA lacks */,
+       CTR_GENOME_MISS_POS = 9 /* start of one such junction */, CTR_COUNT = 10 };
 
 }  // namespace rtjx

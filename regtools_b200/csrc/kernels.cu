@@ -76,6 +76,37 @@ __device__ __forceinline__ uint32_t read_strand(uint32_t meta, int strandness) {
     return fs != ss ? (uint32_t)'?' : (fs ? (uint32_t)'+' : (uint32_t)'-');
 }
 
+// Strand from the intron motif (get_splice_site :564-584 + set_junction_strand_intron_motif :325-342 with fai_fetch's
+// clipping, faidx.c:386-397).  `prev` is the strand the reference's reused Junction object carries from the previous
+// junction of the same alignment (0 before the first): when it is '-', the two 2-mers are reverse-complemented and
+// swapped before the comparison.  Returns '+', '-' or '?' ('?' = fall back to the XS tag / flag strand, :352-358).
+__device__ __forceinline__ uint32_t comp_base(uint32_t c) {            // common.h:59-83
+    return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+}
+__device__ __noinline__ uint32_t motif_strand(const ScanParams& p, int32_t tid, uint32_t start, uint32_t end, uint32_t prev,
+                                              uint32_t* counters) {
+    const unsigned long long len = (uint32_t)tid < p.g_n ? p.g_len[tid] : ~0ull;
+    if (len == ~0ull) {                                                // fai_fetch returns NULL -> runtime_error (:553-555)
+        if (atomicCAS(&counters[CTR_GENOME_MISS], 0u, (uint32_t)tid + 1u) == 0u) counters[CTR_GENOME_MISS_POS] = start;
+        return '?';
+    }
+    const uint8_t* g = p.genome + p.g_off[tid];
+    // "chrom:start+1-start+2" and "chrom:end-1-end", 1-based inclusive -> [b, e) clipped to the sequence
+    unsigned long long b1 = start, e1 = (unsigned long long)start + 2ull;
+    unsigned long long b2 = end >= 2u ? end - 2u : 0u, e2 = end;
+    b1 = b1 < len ? b1 : len; e1 = e1 < len ? e1 : len; b2 = b2 < len ? b2 : len; e2 = e2 < len ? e2 : len;
+    if (e1 - b1 != 2ull || e2 < b2 || e2 - b2 != 2ull) return '?';   // a shorter string equals no 5-character motif
+    uint32_t m0 = g[b1], m1 = g[b1 + 1], m2 = g[b2], m3 = g[b2 + 1];
+    if (prev == '-') {
+        const uint32_t a0 = comp_base(m3), a1 = comp_base(m2), a2 = comp_base(m1), a3 = comp_base(m0);
+        m0 = a0; m1 = a1; m2 = a2; m3 = a3;
+    }
+    const uint32_t code = m0 << 24 | m1 << 16 | m2 << 8 | m3;
+    if (code == 0x47544147u /*GTAG*/ || code == 0x47434147u /*GCAG*/ || code == 0x41544143u /*ATAC*/) return '+';
+    if (code == 0x43544143u /*CTAC*/ || code == 0x43544743u /*CTGC*/ || code == 0x47544154u /*GTAT*/) return '-';
+    return '?';
+}
+
 // ------------------------------------------------------------------------------------------------
 // cigar_scan
 // ------------------------------------------------------------------------------------------------
@@ -583,11 +614,17 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <class Smem, int S5_OUT>
+template <class Smem, int S5_OUT, bool MOTIF>
 struct S5Emit {
     Smem& sm; Cand* __restrict__ out; uint32_t cap; uint32_t* counters; uint32_t dbg;
+    const ScanParams* prm; uint32_t* jstrand;                 // intron-motif mode: parameters + the alignment's running strand
     __device__ __forceinline__ void operator()(uint32_t start, uint32_t end, uint32_t left, uint32_t right,
                                                uint64_t ord, int32_t tid, uint32_t strand) const {
+        if (MOTIF) {                                           // set_junction_strand with a FASTA (:345-359): motif first
+            const uint32_t m = motif_strand(*prm, tid, start, end, *jstrand, counters);
+            if (m != '?') strand = m;
+            *jstrand = strand;
+        }
         uint4 a = make_uint4(start, end, start - left, end + right);
         uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
         if (dbg & 4u) { if ((a.x ^ a.y ^ a.z ^ a.w ^ b.x) == 0x9e3779b9u) sm.n_out = 1; return; }
@@ -607,7 +644,7 @@ struct S5Emit {
     }
 };
 
-template <int S5_THREADS, int S5_SLAB, int S5_OUT>
+template <int S5_THREADS, int S5_SLAB, int S5_OUT, bool MOTIF = false>
 __global__ void __launch_bounds__(S5_THREADS)
 cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters,
                         const uint32_t* __restrict__ tile_off, CandRegions rg) {
@@ -679,7 +716,8 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
 
     // ---- walk the compacted alignments, one per thread, in rounds of 128
     const uint32_t n_work = (prm.debug & 1u) ? 0u : sm.n_work;
-    const S5Emit<Smem, S5_OUT> emit{sm, out, cap, counters, prm.debug};
+    uint32_t jstrand = 0;                                      // j1.strand == "" before an alignment's first junction
+    const S5Emit<Smem, S5_OUT, MOTIF> emit{sm, out, cap, counters, prm.debug, &prm, &jstrand};
     auto flush = [&]() {                                        // warp 0
         const uint32_t n_st = (prm.debug & 8u) ? 0u : min(sm.n_out, (uint32_t)S5_OUT);
         __syncwarp();
@@ -705,6 +743,7 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
                 const uint32_t o0 = sm.off[r], n = sm.off[r + 1] - o0;
                 const uint32_t strand = read_strand(sm.meta[r], prm.strandness);
                 const uint64_t read_ord = b.first_ordinal + base + r;
+                if (MOTIF) jstrand = 0;
                 if ((o0 - a0) + n <= n_st) walk_fast<true>(sm.slab + (o0 - a0), n, sm.pos[r], tid, strand, read_ord, emit);
                 else walk_fast<false>(b.cigar + o0, n, sm.pos[r], tid, strand, read_ord, emit);
             }
@@ -754,7 +793,7 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
     const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
                             reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
                             reinterpret_cast<uintptr_t>(b.cigar);
-    const int variant = (p.variant == 1 || p.variant == 4) ? p.variant : scan_variant();
+    const int variant = p.genome ? 5 : ((p.variant == 1 || p.variant == 4) ? p.variant : scan_variant());   // only variant 5 knows the intron-motif mode
     if ((align & 15u) == 0 && variant == 5) {
         static int prepass = -1;
         const int cfg = p.variant == 5 && p.cfg ? p.cfg : scan_cfg();
@@ -775,7 +814,10 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
         case 5: cigar_scan_small_kernel<128, 2048, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
         case 6: cigar_scan_small_kernel<128, 2048, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
         case 7: cigar_scan_small_kernel<128, 1536, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
-        default: cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions); break;
+        default:
+            if (p.genome) cigar_scan_small_kernel<128, 1024, 192, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions);
+            else cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions);
+            break;
         }
         return;
     }

@@ -30,7 +30,6 @@ int rtjx_create(const rtjx_params* p, rtjx_t** out) {
     if (!p || !out) return RTJX_E_ARG;
     *out = nullptr;
     if (p->struct_size != sizeof(rtjx_params)) { snprintf(g_create_err, sizeof g_create_err, "rtjx_params.struct_size mismatch"); return RTJX_E_ARG; }
-    if (p->fasta) { snprintf(g_create_err, sizeof g_create_err, "intron-motif strand inference from a FASTA is not built into the B200 path"); return RTJX_E_UNSUPPORTED; }
     if (p->barcode_out) { snprintf(g_create_err, sizeof g_create_err, "single-cell barcode output (-b) is not built into the B200 path"); return RTJX_E_UNSUPPORTED; }
     if (p->strandness < 0 || p->strandness > 3) { snprintf(g_create_err, sizeof g_create_err, "strandness must be 0..3"); return RTJX_E_ARG; }
     if (p->shard_world > 1 && (p->shard_rank < 0 || p->shard_rank >= p->shard_world)) { snprintf(g_create_err, sizeof g_create_err, "shard_rank out of range"); return RTJX_E_ARG; }

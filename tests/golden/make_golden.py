@@ -112,7 +112,7 @@ def build_motif():
             p = subprocess.run([REF, "junctions", "extract"] + args + [os.path.join(OUT, bam), fas[fa]], capture_output=True, text=True)
             name = f"motif.{i}.bed"
             open(os.path.join(out_dir, name), "w").write(p.stdout)
-            err = [l for l in p.stderr.splitlines() if l.startswith("Unable")]
+            err = [l[l.index("Unable"):] for l in p.stderr.splitlines() if "Unable" in l]      # "Unknown cigar P" has no newline
             manifest.append(f"{bam}\t{fa}\t{name}\t{p.returncode}\t{' '.join(args)}\t{err[0] if err else ''}")
     open(os.path.join(out_dir, "MANIFEST.tsv"), "w").write("\n".join(manifest) + "\n")
     print(f"wrote {len(manifest)} intron-motif golden outputs to {out_dir}")

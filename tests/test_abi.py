@@ -34,7 +34,7 @@ def test_struct_sizes_match_header():
 
 def test_unsupported_modes_are_refused():
     from regtools_b200 import _lib
-    for field in ("fasta", "barcode_out"):
+    for field in ("barcode_out",):
         p = _lib.Params()
         _lib.lib.rtjx_params_default(C.byref(p))
         setattr(p, field, b"x")

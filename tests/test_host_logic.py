@@ -195,3 +195,4 @@ def test_name_index_above_1e8_sorts_as_string():
     h.set_contigs(["c"])
     h.import_table(t)
     assert [int(x) for x in h.junction_table()["name_index"]] == [1, 2, 3]
+
