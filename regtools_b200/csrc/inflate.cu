@@ -93,10 +93,22 @@ struct WinReader {
     }
 };
 
-__device__ __forceinline__ int slow_decode_w(WinReader& wr, const uint16_t* count, const uint16_t* sym) {
-    int code = 0, first = 0, index = 0;
+// Canonical decode of a code LONGER than the fast table's `fast_bits`: the fast table has already established that no
+// code of up to fast_bits bits matches, so the bit-by-bit recurrence starts at length fast_bits + 1 with the state it
+// would have reached there — code = the first fast_bits stream bits MSB-first (one brev), first/index = the table's
+// constants `pre` (slow_decode_pre).  On worst-case-entropy BAMs (random SEQ/QUAL) ~12 % of the symbols take this path;
+// restarting from length 1 made it 61 % of the kernel's instructions (profiles/r1_bgzf_inflate_stall_lines.txt).
+struct SlowPre { int first, index; };
+__device__ __forceinline__ SlowPre slow_decode_pre(const uint16_t* count, int fast_bits) {
+    SlowPre p{0, 0};
+    for (int len = 1; len <= fast_bits; ++len) { const int c = count[len]; p.index += c; p.first += c; p.first <<= 1; }
+    return p;
+}
+__device__ __forceinline__ int slow_decode_w(WinReader& wr, const uint16_t* count, const uint16_t* sym, int fast_bits, SlowPre pre) {
     uint32_t win = wr.window();
-    for (int len = 1; len <= 15; ++len) {
+    int code = (int)(__brev(win) >> (32 - fast_bits)) << 1, first = pre.first, index = pre.index;
+    win >>= fast_bits;
+    for (int len = fast_bits + 1; len <= 15; ++len) {
         code |= (int)(win & 1u); win >>= 1;
         const int c = count[len];
         if (code - c < first) { wr.consume((uint32_t)len); return sym[index + (code - first)]; }
@@ -290,7 +302,8 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
 
         // ---- symbols, 32 per round
         WinReader wr;
-        if (lane == 0) wr.from(br);
+        SlowPre lit_pre{0, 0}, dist_pre{0, 0};
+        if (lane == 0) { wr.from(br); lit_pre = slow_decode_pre(sm.lit_count, LIT_BITS); dist_pre = slow_decode_pre(sm.dist_count, DIST_BITS); }
         for (bool eob = false; !eob && !err;) {
             uint32_t n = 0, flag = 0;                 // flag: 1 = end of block seen, 2+ = error
             if (lane == 0) {
@@ -299,7 +312,7 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
                     int sym;
                     uint32_t e = sm.lit_fast[win & ((1u << LIT_BITS) - 1u)];
                     if (e) { wr.consume(e & 15u); sym = (int)(e >> 4); }
-                    else { sym = slow_decode_w(wr, sm.lit_count, sm.lit_sym); if (sym < 0) { flag = 11; break; } }
+                    else { sym = slow_decode_w(wr, sm.lit_count, sm.lit_sym, LIT_BITS, lit_pre); if (sym < 0) { flag = 11; break; } }
                     if (sym < 256) { sm.q[n++] = 0x80000000u | (uint32_t)sym; continue; }
                     if (sym == 256) { flag = 1; break; }
                     sym -= 257;
@@ -309,7 +322,7 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
                     win = wr.window();
                     e = sm.dist_fast[win & ((1u << DIST_BITS) - 1u)];
                     if (e) { wr.consume(e & 15u); ds = (int)(e >> 4); }
-                    else { ds = slow_decode_w(wr, sm.dist_count, sm.dist_sym); if (ds < 0) { flag = 13; break; } }
+                    else { ds = slow_decode_w(wr, sm.dist_count, sm.dist_sym, DIST_BITS, dist_pre); if (ds < 0) { flag = 13; break; } }
                     if (ds >= 30) { flag = 14; break; }
                     const uint32_t dist = c_dist_base[ds] + wr.get(c_dist_extra[ds]);
                     sm.q[n++] = len << 16 | dist;       // len <= 258, dist <= 32768
