@@ -134,6 +134,16 @@ void        rtjx_destroy(rtjx_t* h);
  * open + index + header + iterate region + per-read CIGAR walk + merge. */
 int         rtjx_run(rtjx_t* h);
 
+/* The second caller of the path, batched (src/cis-splice-effects/cis_splice_effects_identifier.cc:267-311 builds one
+ * JunctionsExtractor per variant region on the same BAM: `JunctionsExtractor je1(bam_, variant_region, ...);
+ * je1.identify_junctions_from_BAM(); je1.get_all_junctions()`).  rtjx_run_regions computes the table of EVERY region
+ * in one pass over the file; region i then answers exactly what a fresh handle created with region = regions[i]
+ * would: own JUNC numbering, sorted by compare_junctions, no anchor filter.  The handle must have been created with
+ * region "." (parameters, strand mode and FASTA apply to all regions); its own table is left empty. */
+int         rtjx_run_regions(rtjx_t* h, const char* const* regions, size_t n_regions);
+int64_t     rtjx_region_count(rtjx_t* h, size_t region);
+int64_t     rtjx_region_get(rtjx_t* h, size_t region, rtjx_junction* out, size_t cap);
+
 /* parse_alignment_into_junctions over a prepared batch (junctions_extractor.cc:377-497):
  * launches cigar_scan + junction_merge on `stream` (a cudaStream_t, NULL = default stream).
  * location = RTJX_LOC_HOST: arrays are host memory and are copied in; RTJX_LOC_DEVICE: the

@@ -84,6 +84,9 @@ SIGNATURES = {
     "rtjx_create": (C.c_int, [C.POINTER(Params), C.POINTER(C.c_void_p)]),
     "rtjx_destroy": (None, [C.c_void_p]),
     "rtjx_run": (C.c_int, [C.c_void_p]),
+    "rtjx_run_regions": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_size_t]),
+    "rtjx_region_count": (C.c_int64, [C.c_void_p, C.c_size_t]),
+    "rtjx_region_get": (C.c_int64, [C.c_void_p, C.c_size_t, C.POINTER(Junction), C.c_size_t]),
     "rtjx_scan_batch": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int, C.c_void_p]),
     "rtjx_add": (C.c_int, [C.c_void_p, C.POINTER(Candidate), C.c_size_t]),
     "rtjx_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),

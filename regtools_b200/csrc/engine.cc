@@ -20,6 +20,7 @@ namespace {
 double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+std::vector<uint32_t> contig_ranks(const std::vector<std::string>& names);      // defined with finalize below
 uint32_t next_pow2(uint64_t x) {
     uint64_t p = 1;
     while (p < x) p <<= 1;
@@ -56,6 +57,8 @@ Engine::~Engine() {
             if (d.free_ev) cudaEventDestroy(d.free_ev);
         }
         cached_dev_free(d_genome_); cached_dev_free(d_g_off_); cached_dev_free(d_g_len_);
+        cached_dev_free(d_vr_tid_); cached_dev_free(d_vr_beg_); cached_dev_free(d_vr_end_);
+        cached_dev_free(d_out_r_); cached_dev_free(d_ws_r_); cached_host_free(h_final_r_);
         cached_dev_free(d_counters_); cached_host_free(h_counters_);
         cached_dev_free(d_table_); cached_dev_free(d_spill_); cached_dev_free(d_cands_); cached_dev_free(d_tile_off_); cached_dev_free(d_regions_); cached_dev_free(d_region_cnt_);
         cached_dev_free(d_out_); cached_dev_free(d_ws_); cached_dev_free(d_rank_); cached_host_free(h_final_); cached_dev_free(d_slot_list_);
@@ -75,7 +78,8 @@ ScanParams Engine::scan_params() const {
     s.variant = prm_.scan_variant ? prm_.scan_variant : (env_variant ? env_variant : 5);
     s.cfg = prm_.scan_cfg ? prm_.scan_cfg : env_cfg;
     s.genome = d_genome_; s.g_off = d_g_off_; s.g_len = d_g_len_; s.g_n = d_genome_ ? g_n_ : 0u;
-    if (d_genome_) { s.variant = 5; s.cfg = 0; }      // the intron-motif mode lives in the default scan kernel only
+    s.vr = vr_;
+    if (d_genome_ || vr_.n) { s.variant = 5; s.cfg = 0; }   // the intron-motif and variant-region modes live in the default scan kernel only
     return s;
 }
 
@@ -226,6 +230,35 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
         stats_.reads += v.n_reads; stats_.cigar_ops += v.n_ops; stats_.batches++;
         dirty_ = true; finalized_ = false;
         if (prof_pending_.size() > 4096) resolve_profile_events();
+        return RTJX_OK;
+    }
+    if (sp.vr.n) {
+        // variant-region mode: an alignment yields one candidate per region it belongs to, so the candidate count is only
+        // known after the scan: scan, read the count back, grow and re-scan if the buffer was too small, then merge
+        if ((rc = ensure_cands(std::max(std::max(cand_bound, v.n_ops / 4u) * 2u, 1u << 16)))) return rc;
+        for (int attempt = 0;; ++attempt) {
+            CK(cudaMemsetAsync(d_counters_ + CTR_NCAND, 0, 2 * sizeof(uint32_t), stream));       // NCAND + CAND_OVERFLOW
+            launch_cigar_scan(v, sp, d_cands_, cand_cap_, d_counters_, nullptr, CandRegions{nullptr, nullptr, 0, 0}, stream);
+            CK(cudaMemcpyAsync(h_counters_, d_counters_, CTR_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CK(cudaStreamSynchronize(stream));
+            stats_.kernel_launches++;
+            if (h_counters_[CTR_NCAND] <= cand_cap_) break;
+            if (attempt) return fail(RTJX_E_STATE, "internal: candidate buffer overflowed twice in variant-region mode");
+            const uint32_t need = h_counters_[CTR_NCAND];
+            CK(cudaMemsetAsync(d_counters_ + CTR_CAND_OVERFLOW, 0, sizeof(uint32_t), stream));
+            if ((rc = ensure_cands(need))) return rc;
+        }
+        const uint32_t n_cand = h_counters_[CTR_NCAND];
+        unique_upper_ = h_counters_[CTR_NUNIQUE];
+        if (n_cand) {
+            if ((rc = ensure_table(n_cand, stream))) return rc;
+            launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, n_cand, CandRegions{nullptr, nullptr, 0, 0}, sp, table_ref(),
+                                  d_spill_, spill_cap_, d_counters_, stream);
+            stats_.kernel_launches++;
+        }
+        CK(cudaGetLastError());
+        stats_.reads += v.n_reads; stats_.cigar_ops += v.n_ops; stats_.batches++;
+        dirty_ = true; finalized_ = false;
         return RTJX_OK;
     }
     if ((rc = ensure_cands(known ? cand_bound : std::max(v.n_ops, 1u)))) return rc;
@@ -507,6 +540,115 @@ int Engine::run_impl() {
     stats_.host_inflate_s += fs.inflate_s; stats_.host_parse_s += fs.parse_s; stats_.host_wait_s += fs.wait_s;
     stats_.total_s += now_s() - t_start;
     return RTJX_OK;
+}
+
+// ---- batched variant regions (second caller of the path) --------------------------------------------
+// The reference builds one JunctionsExtractor per variant (cis_splice_effects_identifier.cc:288-290): open, index load,
+// iterate the region, merge, sort — 50k times on the same BAM.  Here every region becomes a row of a sorted interval
+// table in HBM, ONE pass over the file feeds cigar_scan, which emits a candidate once per region its alignment belongs
+// to, and the region index is part of the junction key; finalize ranks the names per region (each region is its own
+// extractor with its own JUNC numbering) and sorts per region.
+int Engine::run_regions(const char* const* regions, size_t n) {
+    if (n && !regions) return fail(RTJX_E_ARG, "null region list");
+    if (n >= (1u << 29)) return fail(RTJX_E_ARG, "too many regions");
+    if (region_ != ".") return fail(RTJX_E_ARG, "rtjx_run_regions needs a handle created with region \".\"");
+    std::unique_ptr<BamFile> bam; BaiIndex idx; IterSpec spec;
+    int rc = open_bam(&bam, &idx, &spec);
+    if (rc) return rc;
+    if ((rc = ensure_device())) return rc;
+    struct R { int32_t tid, beg, end; uint32_t orig; };
+    std::vector<R> rs(n);
+    uint32_t max_len = 1;
+    for (size_t i = 0; i < n; ++i) {
+        IterSpec one;
+        if (!regions[i] || !parse_region(*bam, regions[i], &one) || one.kind != IterSpec::Region || one.end < one.beg ||
+            (size_t)one.tid >= idx.refs.size())
+            return fail(RTJX_E_REGION, "Unable to iterate to region within BAM.\n\n");
+        const int64_t b = std::max<int64_t>(one.beg, 0), e = std::min<int64_t>(one.end, INT32_MAX);
+        rs[i] = R{one.tid, (int32_t)b, (int32_t)e, (uint32_t)i};
+        max_len = std::max<uint32_t>(max_len, (uint32_t)(e - b));
+    }
+    std::sort(rs.begin(), rs.end(), [](const R& a, const R& b) { return a.tid != b.tid ? a.tid < b.tid : (a.beg != b.beg ? a.beg < b.beg : a.orig < b.orig); });
+    region_tables_.assign(n, {});
+    vr_orig_.resize(n);
+    if ((rc = clear())) return rc;
+    if (n == 0) return RTJX_OK;
+    if (n > vr_cap_) {
+        CK(cudaDeviceSynchronize());
+        cached_dev_free(d_vr_tid_); cached_dev_free(d_vr_beg_); cached_dev_free(d_vr_end_); d_vr_tid_ = d_vr_beg_ = d_vr_end_ = nullptr;
+        vr_cap_ = (uint32_t)(n + n / 4 + 64);
+        CK(cached_dev_malloc(&d_vr_tid_, (size_t)vr_cap_ * 4)); CK(cached_dev_malloc(&d_vr_beg_, (size_t)vr_cap_ * 4));
+        CK(cached_dev_malloc(&d_vr_end_, (size_t)vr_cap_ * 4));
+    }
+    {
+        std::vector<int32_t> t(n), b(n), e(n);
+        for (size_t i = 0; i < n; ++i) { t[i] = rs[i].tid; b[i] = rs[i].beg; e[i] = rs[i].end; vr_orig_[i] = rs[i].orig; }
+        CK(cudaMemcpy(d_vr_tid_, t.data(), n * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_vr_beg_, b.data(), n * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_vr_end_, e.data(), n * 4, cudaMemcpyHostToDevice));
+        stats_.h2d_bytes += n * 12;
+    }
+    vr_ = VariantRegions{d_vr_tid_, d_vr_beg_, d_vr_end_, (uint32_t)n, max_len};
+    rc = run();                                        // whole-file pass; the scan kernel does the region membership
+    if (rc == RTJX_OK) rc = finalize_regions();
+    vr_ = VariantRegions{nullptr, nullptr, nullptr, 0, 0};
+    const int rc2 = clear();                           // the handle's own table stays empty: results live in region_tables_
+    return rc ? rc : rc2;
+}
+
+int Engine::finalize_regions() {
+    cudaStream_t st = stream_;
+    int rc = sync_counters(st);
+    if (rc) return rc;
+    const uint32_t n = d_table_ ? h_counters_[CTR_NUNIQUE] : 0u;
+    if (!n) return RTJX_OK;
+    if (n > fin_r_cap_) {
+        CK(cudaDeviceSynchronize());
+        cached_dev_free(d_out_r_); cached_dev_free(d_ws_r_); d_out_r_ = nullptr; d_ws_r_ = nullptr;
+        const uint32_t cap = std::max<uint32_t>(n + n / 2, 1u << 14);
+        CK(cached_dev_malloc(&d_out_r_, (size_t)cap * sizeof(OutJunctionR)));
+        ws_r_cap_ = finalize_sort_regions_workspace_bytes(cap);
+        CK(cached_dev_malloc(&d_ws_r_, ws_r_cap_));
+        fin_r_cap_ = cap;
+    }
+    if (n > h_final_r_cap_) {
+        cached_host_free(h_final_r_); h_final_r_ = nullptr;
+        const uint32_t cap = std::max<uint32_t>(n + n / 2, 1u << 14);
+        CK(cached_host_alloc(&h_final_r_, (size_t)cap * sizeof(OutJunctionR)));
+        h_final_r_cap_ = cap;
+    }
+    if ((rc = ensure_finalize_buffers(1, contigs_.size()))) return rc;     // contig ranks
+    if (rank_dirty_) {
+        std::vector<uint32_t> cr = contig_ranks(contigs_);
+        if (!cr.empty()) CK(cudaMemcpy(d_rank_, cr.data(), cr.size() * 4, cudaMemcpyHostToDevice));
+        rank_dirty_ = false;
+    }
+    launch_table_compact_regions(table_ref(), n, d_out_r_, st);
+    launch_finalize_sort_regions(d_out_r_, n, d_rank_, (uint32_t)contigs_.size(), d_ws_r_, ws_r_cap_, st);
+    CK(cudaMemcpyAsync(h_final_r_, d_out_r_, (size_t)n * sizeof(OutJunctionR), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    stats_.kernel_launches += 2; stats_.d2h_bytes += (size_t)n * sizeof(OutJunctionR);
+    for (uint32_t i = 0; i < n; ++i) {
+        const OutJunctionR& r = h_final_r_[i];
+        if (r.region == 0 || r.region > vr_orig_.size()) return fail(RTJX_E_STATE, "internal: junction without a region");
+        rtjx_junction j;
+        memcpy(&j, &r.j, sizeof j);
+        region_tables_[vr_orig_[r.region - 1]].push_back(j);
+    }
+    return RTJX_OK;
+}
+
+int64_t Engine::region_count(size_t i) {
+    if (i >= region_tables_.size()) return fail(RTJX_E_ARG, "region index out of range");
+    return (int64_t)region_tables_[i].size();
+}
+
+int64_t Engine::region_get(size_t i, rtjx_junction* out, size_t cap) {
+    if (i >= region_tables_.size()) return fail(RTJX_E_ARG, "region index out of range");
+    const std::vector<rtjx_junction>& t = region_tables_[i];
+    if (out && cap) memcpy(out, t.data(), std::min(cap, t.size()) * sizeof(rtjx_junction));
+    return (int64_t)t.size();
 }
 
 // ---- device inflate test hook ----------------------------------------------------------------------

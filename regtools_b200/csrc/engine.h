@@ -21,6 +21,10 @@ public:
     ~Engine();
 
     int run();                                   // identify_junctions_from_BAM
+    // cis_splice_effects_identifier.cc:267-311 batched: every region's table from ONE pass over the BAM
+    int run_regions(const char* const* regions, size_t n);
+    int64_t region_count(size_t i);
+    int64_t region_get(size_t i, rtjx_junction* out, size_t cap);
     int scan_batch(const rtjx_batch& b, int location, cudaStream_t stream);
     int add(const rtjx_candidate* c, size_t n);
     int finalize(cudaStream_t stream);
@@ -86,6 +90,15 @@ private:
     uint8_t* d_genome_ = nullptr;
     unsigned long long* d_g_off_ = nullptr; unsigned long long* d_g_len_ = nullptr; uint32_t g_n_ = 0, g_cap_ = 0;
     std::vector<std::string> genome_map_for_;   // contig list the device map was built for
+
+    // batched variant regions: device copy sorted by (tid, beg) + per-region results in the caller's order
+    int32_t* d_vr_tid_ = nullptr; int32_t* d_vr_beg_ = nullptr; int32_t* d_vr_end_ = nullptr; uint32_t vr_cap_ = 0;
+    VariantRegions vr_{nullptr, nullptr, nullptr, 0, 0};
+    std::vector<uint32_t> vr_orig_;             // sorted index -> caller's index
+    std::vector<std::vector<rtjx_junction>> region_tables_;
+    OutJunctionR* d_out_r_ = nullptr; uint32_t fin_r_cap_ = 0; void* d_ws_r_ = nullptr; size_t ws_r_cap_ = 0;
+    OutJunctionR* h_final_r_ = nullptr; uint32_t h_final_r_cap_ = 0;
+    int finalize_regions();
 
     // device batch ring for host-resident input
     struct DevBatch {

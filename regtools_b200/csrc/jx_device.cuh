@@ -36,6 +36,9 @@ struct alignas(16) Slot {
 static_assert(sizeof(Slot) == 48, "Slot must be 48 bytes");
 
 // Compacted table entry produced by finalize (same layout as rtjx_junction in include/rtjx.h).
+// In the batched variant-region mode the table key carries the region in khi bits 34.. (khi = (region + 1) << 34 |
+// (tid + 1) << 2 | proxy) and finalize works on this wider record.
+struct OutJunctionR;
 struct alignas(8) OutJunction {
     int32_t  tid;
     uint32_t start, end, ts, te, count, name_index;
@@ -43,6 +46,18 @@ struct alignas(8) OutJunction {
     uint64_t first_ord;
 };
 static_assert(sizeof(OutJunction) == 40, "OutJunction must be 40 bytes");
+struct alignas(8) OutJunctionR { OutJunction j; uint32_t region; uint32_t pad; };
+static_assert(sizeof(OutJunctionR) == 48, "OutJunctionR must be 48 bytes");
+
+// Batched variant regions (second caller of the path, cis_splice_effects_identifier.cc:267-311: one extractor per
+// variant region on the same BAM).  Sorted by (tid, beg); [beg, end) is the 0-based half-open interval hts_itr_query
+// iterates (hts.c:1897-1922): an alignment belongs to a region iff tid matches, pos < end and endpos > beg
+// (hts.c:1941-1963).  n == 0: mode off.
+struct VariantRegions {
+    const int32_t* tid; const int32_t* beg; const int32_t* end;
+    uint32_t n;
+    uint32_t max_len;             // max(end - beg), bounds the backward search
+};
 
 struct ScanParams {
     int32_t  strandness;          // 0 XS, 1 RF, 2/3 FR
@@ -55,6 +70,7 @@ struct ScanParams {
     const unsigned long long* g_off;      // per BAM tid: start of the contig in `genome`
     const unsigned long long* g_len;      // per BAM tid: length, ~0ull = the FASTA has no such sequence
     uint32_t                  g_n;        // entries of g_off / g_len
+    VariantRegions            vr;         // batched variant regions; candidates then carry (region index + 1) << 8 in `strand`
 };
 
 struct BatchView {
@@ -106,6 +122,11 @@ void launch_table_rehash(const Slot* old_table, uint32_t old_slots, const TableR
                          cudaStream_t stream);
 void launch_table_clear(const TableRef& tb, const uint32_t* d_n_unique, uint32_t n_bound, cudaStream_t stream);
 void launch_table_compact(const TableRef& tb, uint32_t n, OutJunction* out, cudaStream_t stream);
+// variant-region mode: compaction into OutJunctionR, names ranked per region, sorted by (region, contig, ts, te, name)
+void launch_table_compact_regions(const TableRef& tb, uint32_t n, OutJunctionR* out, cudaStream_t stream);
+size_t finalize_sort_regions_workspace_bytes(uint32_t n);
+void launch_finalize_sort_regions(OutJunctionR* entries, uint32_t n, const uint32_t* contig_rank, uint32_t n_contigs,
+                                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // ranks entries by first_ord (name_index) and sorts them in place by (contig_rank[tid], ts, te, name_index)
 size_t finalize_sort_workspace_bytes(uint32_t n);
 void launch_finalize_sort(OutJunction* entries, uint32_t n, const uint32_t* contig_rank, uint32_t n_contigs,

@@ -614,20 +614,12 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <class Smem, int S5_OUT, bool MOTIF>
+template <class Smem, int S5_OUT, bool MOTIF, bool VREG>
 struct S5Emit {
     Smem& sm; Cand* __restrict__ out; uint32_t cap; uint32_t* counters; uint32_t dbg;
     const ScanParams* prm; uint32_t* jstrand;                 // intron-motif mode: parameters + the alignment's running strand
-    __device__ __forceinline__ void operator()(uint32_t start, uint32_t end, uint32_t left, uint32_t right,
-                                               uint64_t ord, int32_t tid, uint32_t strand) const {
-        if (MOTIF) {                                           // set_junction_strand with a FASTA (:345-359): motif first
-            const uint32_t m = motif_strand(*prm, tid, start, end, *jstrand, counters);
-            if (m != '?') strand = m;
-            *jstrand = strand;
-        }
-        uint4 a = make_uint4(start, end, start - left, end + right);
-        uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
-        if (dbg & 4u) { if ((a.x ^ a.y ^ a.z ^ a.w ^ b.x) == 0x9e3779b9u) sm.n_out = 1; return; }
+    const int32_t* rspan;                                     // variant-region mode: [pos, endpos) of the alignment being walked
+    __device__ __forceinline__ void push(const uint4& a, const uint4& b) const {
         const uint32_t mask = __activemask();
         const uint32_t lane = threadIdx.x & 31u;
         const int leader = __ffs(mask) - 1;
@@ -642,9 +634,35 @@ struct S5Emit {
             else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
         }
     }
+    __device__ __forceinline__ void operator()(uint32_t start, uint32_t end, uint32_t left, uint32_t right,
+                                               uint64_t ord, int32_t tid, uint32_t strand) const {
+        if (MOTIF) {                                           // set_junction_strand with a FASTA (:345-359): motif first
+            const uint32_t m = motif_strand(*prm, tid, start, end, *jstrand, counters);
+            if (m != '?') strand = m;
+            *jstrand = strand;
+        }
+        const uint4 a = make_uint4(start, end, start - left, end + right);
+        const uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
+        if (dbg & 4u) { if ((a.x ^ a.y ^ a.z ^ a.w ^ b.x) == 0x9e3779b9u) sm.n_out = 1; return; }
+        if (!VREG) { push(a, b); return; }
+        // one candidate per variant region the ALIGNMENT belongs to (tid, pos < end, endpos > beg; hts.c:1941-1963)
+        const VariantRegions& vr = prm->vr;
+        const int32_t rp = rspan[0], re = rspan[1];
+        uint32_t lo = 0, hi = vr.n;                            // first region with (tid, beg) >= (tid, endpos)
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const int32_t mt = vr.tid[mid];
+            if (mt < tid || (mt == tid && vr.beg[mid] < re)) lo = mid + 1; else hi = mid;
+        }
+        for (uint32_t i = lo; i-- > 0;) {
+            if (vr.tid[i] != tid) break;
+            if ((long long)vr.beg[i] + (long long)vr.max_len <= (long long)rp) break;    // no earlier region can reach pos
+            if (vr.end[i] > rp) push(a, make_uint4(b.x, b.y, b.z, strand | (i + 1u) << 8));
+        }
+    }
 };
 
-template <int S5_THREADS, int S5_SLAB, int S5_OUT, bool MOTIF = false>
+template <int S5_THREADS, int S5_SLAB, int S5_OUT, bool MOTIF = false, bool VREG = false>
 __global__ void __launch_bounds__(S5_THREADS)
 cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters,
                         const uint32_t* __restrict__ tile_off, CandRegions rg) {
@@ -717,7 +735,8 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
     // ---- walk the compacted alignments, one per thread, in rounds of 128
     const uint32_t n_work = (prm.debug & 1u) ? 0u : sm.n_work;
     uint32_t jstrand = 0;                                      // j1.strand == "" before an alignment's first junction
-    const S5Emit<Smem, S5_OUT, MOTIF> emit{sm, out, cap, counters, prm.debug, &prm, &jstrand};
+    int32_t rspan[2] = {0, 0};
+    const S5Emit<Smem, S5_OUT, MOTIF, VREG> emit{sm, out, cap, counters, prm.debug, &prm, &jstrand, rspan};
     auto flush = [&]() {                                        // warp 0
         const uint32_t n_st = (prm.debug & 8u) ? 0u : min(sm.n_out, (uint32_t)S5_OUT);
         __syncwarp();
@@ -744,6 +763,15 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
                 const uint32_t strand = read_strand(sm.meta[r], prm.strandness);
                 const uint64_t read_ord = b.first_ordinal + base + r;
                 if (MOTIF) jstrand = 0;
+                if (VREG) {                                    // endpos = pos + reference length of the CIGAR (sam.c:327-342)
+                    const bool in_smem = (o0 - a0) + n <= n_st;
+                    uint32_t rl = 0;
+                    for (uint32_t q = 0; q < n; ++q) {
+                        const uint32_t x = in_smem ? sm.slab[o0 - a0 + q] : __ldg(b.cigar + o0 + q);
+                        if ((0x18Du >> (x & 0xfu)) & 1u) rl += x >> 4;      // M, D, N, =, X consume the reference
+                    }
+                    rspan[0] = (int32_t)sm.pos[r]; rspan[1] = (int32_t)(sm.pos[r] + rl);
+                }
                 if ((o0 - a0) + n <= n_st) walk_fast<true>(sm.slab + (o0 - a0), n, sm.pos[r], tid, strand, read_ord, emit);
                 else walk_fast<false>(b.cigar + o0, n, sm.pos[r], tid, strand, read_ord, emit);
             }
@@ -793,7 +821,7 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
     const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
                             reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
                             reinterpret_cast<uintptr_t>(b.cigar);
-    const int variant = p.genome ? 5 : ((p.variant == 1 || p.variant == 4) ? p.variant : scan_variant());   // only variant 5 knows the intron-motif mode
+    const int variant = (p.genome || p.vr.n) ? 5 : ((p.variant == 1 || p.variant == 4) ? p.variant : scan_variant());   // only variant 5 knows the intron-motif and variant-region modes
     if ((align & 15u) == 0 && variant == 5) {
         static int prepass = -1;
         const int cfg = p.variant == 5 && p.cfg ? p.cfg : scan_cfg();
@@ -815,7 +843,9 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
         case 6: cigar_scan_small_kernel<128, 2048, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
         case 7: cigar_scan_small_kernel<128, 1536, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
         default:
-            if (p.genome) cigar_scan_small_kernel<128, 1024, 192, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions);
+            if (p.vr.n && p.genome) cigar_scan_small_kernel<128, 1024, 192, true, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
+            else if (p.vr.n) cigar_scan_small_kernel<128, 1024, 192, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
+            else if (p.genome) cigar_scan_small_kernel<128, 1024, 192, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions);
             else cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions);
             break;
         }
@@ -902,6 +932,7 @@ struct MergeSmem {
     unsigned long long last[MERGE_SLOTS];
     uint32_t count[MERGE_SLOTS], nts[MERGE_SLOTS], te[MERGE_SLOTS], lr[MERGE_SLOTS];
     int32_t base_tid;
+    uint32_t base_vreg;
     uint32_t rpre[MERGE_RGROUP + 1];             // prefix of the region counts of a region tile
 };
 
@@ -952,9 +983,10 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
                 sm.key[s] = SKEY_EMPTY; sm.nfirst[s] = 0ull; sm.last[s] = 0ull;
                 sm.count[s] = 0u; sm.nts[s] = 0u; sm.te[s] = 0u; sm.lr[s] = 0u;
             }
-            if (t == 0) sm.base_tid = (int32_t)cand_ptr(c0)[1].z;
+            if (t == 0) { const uint4 f = cand_ptr(c0)[1]; sm.base_tid = (int32_t)f.z; sm.base_vreg = f.w >> 8; }
             __syncthreads();
             const int32_t base_tid = sm.base_tid;
+            const uint32_t base_vreg = sm.base_vreg;
 
             // all loads of the chunk first (two 128-bit loads per candidate)
             uint4 ca[MERGE_CPT], cb[MERGE_CPT];
@@ -978,13 +1010,13 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
                 const uint32_t ilen = end - start;                                   // uint32, :161-162
                 if (ilen < prm.min_intron || ilen > prm.max_intron) continue;         // junction_qc
                 const uint32_t lr = ((start - ts) >= prm.min_anchor ? 1u : 0u) | ((te - end) >= prm.min_anchor ? 2u : 0u);
-                const uint32_t sc = cb[j].w & 0xffu;
+                const uint32_t sc = cb[j].w & 0xffu, vreg = cb[j].w >> 8;           // vreg = variant region + 1 (0 outside that mode)
                 const uint32_t proxy = sc == '+' ? 0u : (sc == '-' ? 1u : 2u);         // :186-193
                 const unsigned long long ord = (unsigned long long)cb[j].y << 32 | cb[j].x;
                 const unsigned long long nfirst = ~ord;
                 const unsigned long long last = proxy == 2u ? ((ord >> 16) << 8 | sc) : 0ull;
                 bool done = false;
-                if (tid == base_tid && ilen < (1u << 28)) {
+                if (tid == base_tid && vreg == base_vreg && ilen < (1u << 28)) {
                     const unsigned long long k = (unsigned long long)start << 30 | (unsigned long long)ilen << 2 | proxy;
                     uint32_t s = mix_key(k, 0ull) & (MERGE_SLOTS - 1);
                     for (int probe = 0; probe < MERGE_PROBES; ++probe, s = (s + 1) & (MERGE_SLOTS - 1)) {
@@ -1003,7 +1035,7 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
                     }
                 }
                 if (!done) {
-                    K128 key{(unsigned long long)start << 32 | end, ((unsigned long long)(uint32_t)(tid + 1)) << 2 | proxy};
+                    K128 key{(unsigned long long)start << 32 | end, (unsigned long long)vreg << 34 | ((unsigned long long)(uint32_t)(tid + 1)) << 2 | proxy};
                     if (!table_upsert(tb, key, 1u, ~ts, te, lr, nfirst, last, counters))
                         spill_entry(spill, spill_cap, counters, key, 1u, ~ts, te, lr, nfirst, last);
                 }
@@ -1015,7 +1047,7 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
                 if (k == SKEY_EMPTY) continue;
                 const uint32_t start = (uint32_t)(k >> 30), ilen = (uint32_t)(k >> 2) & 0x0fffffffu, proxy = (uint32_t)k & 3u;
                 K128 key{(unsigned long long)start << 32 | (uint32_t)(start + ilen),
-                         ((unsigned long long)(uint32_t)(base_tid + 1)) << 2 | proxy};
+                         (unsigned long long)base_vreg << 34 | ((unsigned long long)(uint32_t)(base_tid + 1)) << 2 | proxy};
                 if (!table_upsert(tb, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s], counters))
                     spill_entry(spill, spill_cap, counters, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s]);
             }
@@ -1547,7 +1579,7 @@ table_compact_kernel(TableRef tb, uint32_t n, OutJunction* __restrict__ out) {
     const unsigned long long last = (unsigned long long)w.w << 32 | w.z;
     const uint32_t proxy = (uint32_t)khi & 3u;
     OutJunction j;
-    j.tid = (int32_t)(uint32_t)(khi >> 2) - 1;
+    j.tid = (int32_t)(uint32_t)(khi >> 2) - 1;          // (uint32_t) drops the variant-region bits 34..
     j.start = k.y; j.end = k.x;                      // klo = start << 32 | end
     j.ts = ~v.y; j.te = v.z; j.count = v.x; j.name_index = 0;
     j.strand = proxy == 0u ? '+' : (proxy == 1u ? '-' : (uint8_t)(last & 0xffu));
@@ -1597,6 +1629,66 @@ void launch_finalize_sort(OutJunction* entries, uint32_t n, const uint32_t* cont
     cub::DeviceMergeSort::SortKeys(workspace, workspace_bytes, entries, (int)n, ByFirstOrd(), stream);
     fin_assign_names<<<(n + 255u) / 256u, 256, 0, stream>>>(entries, n);
     cub::DeviceMergeSort::SortKeys(workspace, workspace_bytes, entries, (int)n, ByBedOrder{contig_rank, n_contigs}, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize, batched variant-region mode
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+table_compact_regions_kernel(TableRef tb, uint32_t n, OutJunctionR* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* p = reinterpret_cast<const uint4*>(tb.slots + tb.slot_list[i]);
+    const uint4 k = p[0], v = p[1], w = p[2];
+    const unsigned long long khi = (unsigned long long)k.w << 32 | k.z;
+    const unsigned long long last = (unsigned long long)w.w << 32 | w.z;
+    const uint32_t proxy = (uint32_t)khi & 3u;
+    OutJunctionR r;
+    r.j.tid = (int32_t)((uint32_t)(khi >> 2)) - 1;
+    r.j.start = k.y; r.j.end = k.x;
+    r.j.ts = ~v.y; r.j.te = v.z; r.j.count = v.x; r.j.name_index = 0;
+    r.j.strand = proxy == 0u ? '+' : (proxy == 1u ? '-' : (uint8_t)(last & 0xffu));
+    r.j.left_ok = v.w & 1u; r.j.right_ok = (v.w >> 1) & 1u; r.j.pad = 0;
+    r.j.first_ord = ~((unsigned long long)w.y << 32 | w.x);
+    r.region = (uint32_t)(khi >> 34); r.pad = 0;          // region index + 1
+    out[i] = r;
+}
+void launch_table_compact_regions(const TableRef& tb, uint32_t n, OutJunctionR* out, cudaStream_t stream) {
+    if (n == 0) return;
+    table_compact_regions_kernel<<<(n + 255u) / 256u, 256, 0, stream>>>(tb, n, out);
+}
+struct ByRegionFirstOrd {
+    __device__ __forceinline__ bool operator()(const OutJunctionR& a, const OutJunctionR& b) const {
+        return a.region != b.region ? a.region < b.region : a.j.first_ord < b.j.first_ord;
+    }
+};
+struct ByRegionBedOrder {
+    ByBedOrder inner;
+    __device__ __forceinline__ bool operator()(const OutJunctionR& a, const OutJunctionR& b) const {
+        return a.region != b.region ? a.region < b.region : inner(a.j, b.j);
+    }
+};
+// every region is its own extractor: JUNC numbering restarts at 1 (junctions_extractor.cc:152-157 on a fresh object)
+__global__ void fin_assign_names_regions(OutJunctionR* __restrict__ e, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t rg = e[i].region;
+    uint32_t lo = 0, hi = i;                              // first index of this region in the (region, first_ord)-sorted array
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (e[mid].region < rg) lo = mid + 1; else hi = mid; }
+    e[i].j.name_index = i - lo + 1u;
+}
+size_t finalize_sort_regions_workspace_bytes(uint32_t n) {
+    size_t a = 0, b = 0;
+    cub::DeviceMergeSort::SortKeys(nullptr, a, (OutJunctionR*)nullptr, (int)n, ByRegionFirstOrd());
+    cub::DeviceMergeSort::SortKeys(nullptr, b, (OutJunctionR*)nullptr, (int)n, ByRegionBedOrder{ByBedOrder{nullptr, 0}});
+    return (a > b ? a : b) + 256;
+}
+void launch_finalize_sort_regions(OutJunctionR* entries, uint32_t n, const uint32_t* contig_rank, uint32_t n_contigs,
+                                  void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (n == 0) return;
+    cub::DeviceMergeSort::SortKeys(workspace, workspace_bytes, entries, (int)n, ByRegionFirstOrd(), stream);
+    fin_assign_names_regions<<<(n + 255u) / 256u, 256, 0, stream>>>(entries, n);
+    cub::DeviceMergeSort::SortKeys(workspace, workspace_bytes, entries, (int)n, ByRegionBedOrder{ByBedOrder{contig_rank, n_contigs}}, stream);
 }
 
 }  // namespace rtjx

@@ -54,6 +54,9 @@ void rtjx_destroy(rtjx_t* h) {
     catch (...) { return (h)->e->fail(RTJX_E_STATE, "unknown internal error"); }
 
 int rtjx_run(rtjx_t* h) { GUARD(h, h->e->run()) }
+int rtjx_run_regions(rtjx_t* h, const char* const* regions, size_t n) { GUARD(h, h->e->run_regions(regions, n)) }
+int64_t rtjx_region_count(rtjx_t* h, size_t region) { GUARD(h, h->e->region_count(region)) }
+int64_t rtjx_region_get(rtjx_t* h, size_t region, rtjx_junction* out, size_t cap) { GUARD(h, h->e->region_get(region, out, cap)) }
 
 int rtjx_scan_batch(rtjx_t* h, const rtjx_batch* b, int location, void* stream) {
     if (!h) return RTJX_E_ARG;

@@ -213,6 +213,22 @@ class JunctionsExtractor:
         self._check(L.lib.rtjx_run(self._handle()))
         return 0
 
+    def identify_junctions_in_regions(self, regions: Sequence[str]) -> List[np.ndarray]:
+        """Batched form of the per-variant loop of cis-splice-effects (cis_splice_effects_identifier.cc:267-311): the
+        junction table of every region from one pass over the BAM.  Element i equals what
+        ``JunctionsExtractor(bam, regions[i], ...)`` + ``identify_junctions_from_BAM`` + ``junction_table`` returns."""
+        h = self._handle()
+        arr = (C.c_char_p * max(len(regions), 1))(*[r.encode() for r in regions])
+        self._check(L.lib.rtjx_run_regions(h, arr, len(regions)))
+        out = []
+        for i in range(len(regions)):
+            n = self._check(L.lib.rtjx_region_count(h, i))
+            t = np.zeros(n, dtype=JUNCTION_DTYPE)
+            if n:
+                self._check(L.lib.rtjx_region_get(h, i, t.ctypes.data_as(C.POINTER(L.Junction)), n))
+            out.append(t)
+        return out
+
     def get_new_junction_name(self) -> str:
         """get_new_junction_name (junctions_extractor.cc:152-157)."""
         n = self._check(L.lib.rtjx_count(self._handle()))

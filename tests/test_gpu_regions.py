@@ -1,0 +1,93 @@
+"""GPU parity of the batched variant-region mode (rtjx_run_regions): the second caller of the hot path,
+cis_splice_effects_identifier.cc:267-311, builds one JunctionsExtractor per variant region; here all regions come from
+ONE pass over the BAM.  Region i must equal a fresh extractor on regions[i]: checked against the oracle run region by
+region, against the reference's own 8-arg-ctor outputs (tests/golden/kat/kat.ctor*.tsv) and against the product's
+single-region path."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle_py import Oracle
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIELDS = ("tid", "start", "end", "thick_start", "thick_end", "read_count", "name_index", "strand", "left_ok", "right_ok")
+
+
+def _check(bam, regions, strandness=0, a=8, m=70, M=500000, fasta=None, **kw):
+    import regtools_b200 as rt
+    ex = rt.JunctionsExtractor(bam, ".", strandness, "XS", a, m, M, fasta or "NA", **kw)
+    got = ex.identify_junctions_in_regions(regions)
+    st = ex.stats()
+    assert len(ex.junction_table()) == 0                         # the handle's own table stays empty
+    ex.close()
+    assert len(got) == len(regions)
+    n_total = 0
+    for reg, g in zip(regions, got):
+        o = Oracle(a, m, M, strandness, fasta=fasta)
+        o.extract_bam(bam, reg)
+        w = o.table()
+        assert len(g) == len(w), (reg, len(g), len(w))
+        for f in FIELDS:
+            assert np.array_equal(g[f], w[f]), (reg, f)
+        n_total += len(w)
+    return n_total, st
+
+
+def test_kat_regions_match_oracle_and_reference_ctor_outputs(golden_dir):
+    bam = os.path.join(golden_dir, "kat", "kat.bam")
+    regions = ["1:5000-6200", "1:900-1300", "2", "1:1-100", "10", "1:1000-1001", "1:1150-1151", "1:2000-14100", "1:5000-6200",
+               "2:5,000,050-5,000,060", "1:3100-3200", "10:150-160", "1"]
+    n, _ = _check(bam, regions, a=8, m=8)                        # 8-arg ctor quirk: min_intron := min_anchor
+    assert n > 40
+    # the reference's own outputs for three of them (regtools_ref ctor ..., unfiltered get_all_junctions)
+    import regtools_b200 as rt
+    ex = rt.JunctionsExtractor.from_region(bam, ".", 0, "XS", 8, 70, 500000)
+    got = ex.identify_junctions_in_regions(regions[:3])
+    contigs = ["1", "10", "2"]
+    for i, t in enumerate(got):
+        lines = ["\t".join(map(str, [contigs[j["tid"]], j["thick_start"], j["thick_end"], "JUNC%08d" % j["name_index"], j["read_count"],
+                                     chr(j["strand"]), j["start"], j["end"], int(j["left_ok"]), int(j["right_ok"])])) + "\n" for j in t]
+        assert "".join(lines) == open(os.path.join(golden_dir, "kat", f"kat.ctor{i}.tsv")).read()
+    ex.close()
+
+
+@pytest.mark.parametrize("strandness", [0, 1])
+def test_many_overlapping_windows_on_synth(strandness, golden_dir):
+    """400 variant-like windows (nested, overlapping, empty, duplicated) on the generator BAM."""
+    bam = os.path.join(golden_dir, "kat", "synth.bam")
+    rng = np.random.default_rng(17)
+    lens = {"1": 3000000, "10": 2000000, "2": 2500000}
+    regions = []
+    for _ in range(400):
+        c = ["1", "10", "2"][int(rng.integers(0, 3))]
+        centre = int(rng.integers(1, lens[c]))
+        w = int(rng.choice([1, 50, 500, 5000, 60000]))
+        regions.append(f"{c}:{max(1, centre - w)}-{centre + w}")
+    regions += regions[:5] + ["2:1-2500000"]
+    n, st = _check(bam, regions, strandness, a=8, m=8)
+    assert n > 500
+
+
+def test_regions_with_fasta_and_device_feeder(tmp_path, motif_fastas):
+    """Intron-motif strand mode + variant regions on a BAM large enough for the device feeder."""
+    bam = str(tmp_path / "gen.bam")
+    subprocess.check_call([os.path.join(ROOT, "tools", "bamgen"), "gen", "--out", bam, "--config", "tiny", "--reads", "400000", "--seed", "5"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    rng = np.random.default_rng(3)
+    regions = [f"{c}:{s}-{s + w}" for c, s, w in zip(rng.choice(["1", "10", "2"], 60), rng.integers(1, 1900000, 60), rng.choice([200, 2000, 20000], 60))]
+    n, st = _check(bam, regions, 3, a=8, m=8, fasta=motif_fastas["synth"])
+    assert n > 300 and st["inflated_bytes"] > 0
+
+
+def test_bad_region_is_an_error(golden_dir):
+    import regtools_b200 as rt
+    ex = rt.JunctionsExtractor(os.path.join(golden_dir, "kat", "kat.bam"), ".", 0)
+    with pytest.raises(RuntimeError, match="Unable to iterate to region"):
+        ex.identify_junctions_in_regions(["1:100-200", "nope:1-2"])
+    assert [len(t) for t in ex.identify_junctions_in_regions([])] == []
+    ex.close()
