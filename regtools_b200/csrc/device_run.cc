@@ -123,6 +123,9 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     const int copy_threads = std::min(n_threads, 8);
     const uint64_t STAGE = 16ull << 20;                  // compressed bytes per pinned staging chunk (pinned allocation costs ~0.5 ms/MB)
     static const uint64_t GROUP = [] { const char* v = getenv("RTJX_GROUP_MB"); return (uint64_t)(v ? atoi(v) : 512) << 20; }();
+    // the first group of a range is smaller: the GPU starts after a few ms of staging instead of a full group's worth
+    // (192 MB measured best on the 1.27 GB C2 file: 117 -> 107 ms end to end; irrelevant for files of many groups)
+    static const uint64_t FIRST_GROUP = [] { const char* v = getenv("RTJX_FIRST_GROUP_MB"); return (uint64_t)(v ? atoi(v) : 192) << 20; }();
 
     // ---- ranges to stream (same as the host feeder)
     std::vector<Chunk64> ranges;
@@ -141,6 +144,15 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     // (the 16 kb linear index: one record start per window that holds reads; already in file order for a sorted BAM)
     for (const BaiIndex::Ref& r : idx.refs)
         for (uint64_t v : r.ioffset) if (v && (seeds_all.empty() || v != seeds_all.back())) seeds_all.push_back(v);
+    // (the binning index: every chunk begins at a record and ends right after one (hts_idx_push, hts.c:1288-1350).  Where
+    // spliced and unspliced reads alternate between a leaf bin and its ancestors — exactly the deep-coverage windows whose
+    // single 16 kb linear-index entry spans megabytes — the chunk list cuts the stream every few BGZF blocks: 5x the
+    // seeds and half the longest segment on the C2 BAM.  The pseudo-bin's second "chunk" holds counts, not offsets.)
+    for (const BaiIndex::Ref& r : idx.refs)
+        for (const BaiIndex::Bin& b : r.bins) {
+            if (b.bin == BaiIndex::META_BIN) continue;
+            for (const Chunk64& c : b.chunks) { if (c.beg) seeds_all.push_back(c.beg); if (c.end) seeds_all.push_back(c.end); }
+        }
     if (!std::is_sorted(seeds_all.begin(), seeds_all.end())) std::sort(seeds_all.begin(), seeds_all.end());
     seeds_all.erase(std::unique(seeds_all.begin(), seeds_all.end()), seeds_all.end());
 
@@ -369,7 +381,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                 stats_.h2d_bytes += bytes; stats_.compressed_bytes += bytes;
             }
             // ---- close the group?
-            if (!g.desc.empty() && (g.comp_bytes >= GROUP || stream_ends)) {
+            if (!g.desc.empty() && (g.comp_bytes >= (first_group ? std::min(GROUP, FIRST_GROUP) : GROUP) || stream_ends)) {
                 if ((rc = harvest())) return rc;                              // previous group: scan + merge (its SoA is about to be overwritten)
                 if (declined || reached_limit) break;
                 if ((rc = launch(g))) return rc;

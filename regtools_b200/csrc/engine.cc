@@ -909,32 +909,38 @@ inline char* put_u32(char* p, uint32_t v) {
 int Engine::write_bed12(int fd) {
     int rc = finalize(nullptr);
     if (rc) return rc;
-    std::vector<char> buf;
-    buf.reserve(1u << 20);
+    // one pass into a 4 MB buffer, no per-line allocation or printf (43k lines used to cost 5 ms of a 120 ms run)
+    const size_t CAP = 4u << 20;
+    std::vector<char> buf(CAP);
+    char* const base = buf.data();
+    char* p = base;
     auto flush = [&]() -> bool {
-        size_t off = 0;
-        while (off < buf.size()) {
-            ssize_t w = ::write(fd, buf.data() + off, buf.size() - off);
+        size_t off = 0; const size_t n = (size_t)(p - base);
+        while (off < n) {
+            ssize_t w = ::write(fd, base + off, n - off);
             if (w <= 0) return false;
             off += (size_t)w;
         }
-        buf.clear();
+        p = base;
         return true;
     };
+    std::vector<size_t> clen(contigs_.size());
+    for (size_t i = 0; i < contigs_.size(); ++i) clen[i] = contigs_[i].size();
     for (const rtjx_junction& j : final_) {
         if (!(j.left_ok && j.right_ok)) continue;
-        const char* chrom = contig(j.tid);
-        size_t cl = strlen(chrom);
-        size_t o = buf.size();
-        buf.resize(o + cl + 160);
-        char* p = buf.data() + o;
+        const bool known = j.tid >= 0 && (size_t)j.tid < contigs_.size();
+        const char* chrom = known ? contigs_[(size_t)j.tid].c_str() : contig(j.tid);
+        const size_t cl = known ? clen[(size_t)j.tid] : strlen(chrom);
+        if ((size_t)(p - base) + cl + 192 > CAP) { if (!flush()) return fail(RTJX_E_IO, "write failed"); }
+        if (cl + 192 > CAP) return fail(RTJX_E_ARG, "contig name too long");
         memcpy(p, chrom, cl); p += cl;
         *p++ = '\t'; p = put_u32(p, j.thick_start);
         *p++ = '\t'; p = put_u32(p, j.thick_end);
         memcpy(p, "\tJUNC", 5); p += 5;
-        {   // setfill('0') << setw(8) << int
-            char tmp[12]; int n = snprintf(tmp, sizeof tmp, "%08d", (int)j.name_index);
-            memcpy(p, tmp, (size_t)n); p += n;
+        {   // setfill('0') << setw(8) << int (junctions_extractor.cc:152-157)
+            const int v = (int)j.name_index;
+            if (v >= 0 && v < 100000000) { uint32_t x = (uint32_t)v; for (int d = 7; d >= 0; --d) { p[d] = (char)('0' + x % 10); x /= 10; } p += 8; }
+            else { p += snprintf(p, 16, "%08d", v); }
         }
         *p++ = '\t'; p = put_u32(p, j.read_count);
         *p++ = '\t'; *p++ = (char)j.strand;
@@ -945,8 +951,6 @@ int Engine::write_bed12(int fd) {
         memcpy(p, "\t0,", 3); p += 3;
         p = put_u32(p, j.end - j.thick_start);
         *p++ = '\n';
-        buf.resize((size_t)(p - buf.data()));
-        if (buf.size() > (1u << 20) - 4096) if (!flush()) return fail(RTJX_E_IO, "write failed");
     }
     if (!flush()) return fail(RTJX_E_IO, "write failed");
     return RTJX_OK;
