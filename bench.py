@@ -4,9 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R]
 
 N = 1 workload (BASELINE.json configs[1]): synthetic 10M-read single-chromosome BAM, 101 bp, ~8 %
-spliced, generated on the box by tools/bamgen (seed 1234).  N > 1 (weak scaling): whole-genome
-24-contig BAM with N x 10M reads, contigs sharded across ranks, junction tables all-gathered
-over NCCL (the path's only exchange step).
+spliced, generated on the box by tools/bamgen (seed 1234).  N > 1 (weak scaling): the same shape N
+times in one BAM — N contigs of the chr1 length, N x 10M reads — so every GPU does exactly the N = 1
+work on its contig shard; junction tables are all-gathered over NCCL (the path's only exchange).
 
 One "step" = one pass of the hot path over the whole workload.
   value : reads/s with the SoA batch already resident in HBM: cigar_scan + junction_merge +
@@ -148,7 +148,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     n = max(args.gpus, 1)
-    config = "c2" if n == 1 else "c3"
+    config = "c2" if n == 1 else f"c2x{n}"
     reads = args.reads * n
     bam = ensure_bam(config, reads, args.level)
     # bounded sample: a region holding ~1/5 of a 10M-read workload keeps each step to a few seconds
@@ -180,6 +180,9 @@ def run_reference_arm(args):
 def workload_name(config, reads):
     if config == "c2":
         return f"synthetic {reads}-read single-chrom BAM (chr1), 101 bp, ~8% spliced, seed 1234 (BASELINE configs[1])"
+    if config.startswith("c2x"):
+        return (f"synthetic {reads}-read BAM of {config[3:]} contigs, each the configs[1] chromosome (101 bp, ~8% spliced, seed 1234): "
+                "one contig shard per GPU, the N=1 work per GPU")
     return f"synthetic {reads}-read whole-genome BAM (24 contigs), 150 bp paired, 12% spliced, seed 1234, contig-sharded"
 
 
@@ -213,9 +216,20 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its log (with NCCL_DEBUG=VERSION/WARN/INFO at least "NCCL version ...") to stdout: keep fd 1 for the ONE
+        # JSON line by pointing it at stderr while the communicator is created
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     n = max(args.gpus, world)
-    config = "c2" if n == 1 else "c3"
+    config = "c2" if n == 1 else f"c2x{n}"
     reads_total = args.reads * n
     if rank == 0:
         bam = ensure_bam(config, reads_total, args.level)

@@ -698,9 +698,7 @@ bool feed_alignments(const BamFile& bam, const BaiIndex& idx, const IterSpec& sp
         feed_region(bam, idx.query(spec.tid, spec.beg, spec.end), spec, w, stats);
         break; }
     case IterSpec::Contigs: {
-        std::vector<Chunk64> ranges;
-        for (int32_t tid : spec.contigs) { Chunk64 c; if (idx.contig_range(tid, &c)) ranges.push_back(c); }
-        feed_stream(bam, ranges, opt, w, stats);
+        feed_stream(bam, coalesced_contig_ranges(idx, spec.contigs), opt, w, stats);
         break; }
     }
     w.finish();
@@ -744,25 +742,74 @@ uint64_t scan_bgzf_blocks_mem(const uint8_t* buf, size_t n, uint64_t base_coff, 
     return base_coff + o;
 }
 
+// Contigs -> shards.  Each shard is a run of CONSECUTIVE contigs (so that a rank streams one contiguous byte range of
+// the coordinate-sorted file: a shard made of scattered contigs is a dozen small ranges, each with its own partly filled
+// inflate launches — measured 3.5x slower end to end), balanced on compressed bytes from the BAI pseudo-bin (hts.c:1092):
+// the smallest achievable maximum load over all contiguous partitions, then spare ranks split the heaviest runs.
 std::vector<int32_t> plan_contig_shards(const BamFile& bam, const BaiIndex& idx, int world) {
     const size_t n = bam.header().names.size();
     std::vector<int32_t> assign(n, 0);
-    if (world <= 1) return assign;
-    std::vector<std::pair<uint64_t, int32_t>> w;
+    if (world <= 1 || n == 0) return assign;
+    std::vector<uint64_t> w(n, 0);
+    uint64_t total = 0, wmax = 0;
     for (size_t t = 0; t < n; ++t) {
-        Chunk64 c; uint64_t bytes = 0;
-        if (idx.contig_range((int32_t)t, &c)) bytes = (c.end >> 16) - (c.beg >> 16) + 1;
-        w.emplace_back(bytes, (int32_t)t);
+        Chunk64 c;
+        if (idx.contig_range((int32_t)t, &c)) w[t] = (c.end >> 16) - (c.beg >> 16) + 1;
+        total += w[t]; wmax = std::max(wmax, w[t]);
     }
-    std::sort(w.begin(), w.end(), [](const std::pair<uint64_t, int32_t>& a, const std::pair<uint64_t, int32_t>& b) {
-        return a.first != b.first ? a.first > b.first : a.second < b.second; });
-    std::vector<uint64_t> load((size_t)world, 0);
-    for (auto& x : w) {
-        int best = 0;
-        for (int r = 1; r < world; ++r) if (load[r] < load[best]) best = r;
-        assign[(size_t)x.second] = best; load[best] += x.first;
+    auto groups_needed = [&](uint64_t cap) {
+        int g = 1; uint64_t cur = 0;
+        for (size_t t = 0; t < n; ++t) { if (cur + w[t] > cap && cur) { ++g; cur = 0; } cur += w[t]; }
+        return g;
+    };
+    uint64_t lo = wmax, hi = std::max(total, wmax);
+    while (lo < hi) { const uint64_t mid = lo + (hi - lo) / 2; if (groups_needed(mid) <= world) hi = mid; else lo = mid + 1; }
+    // cut points under the optimal cap
+    std::vector<size_t> start{0};                      // first contig of every run
+    { uint64_t cur = 0; for (size_t t = 0; t < n; ++t) { if (cur + w[t] > lo && cur) { start.push_back(t); cur = 0; } cur += w[t]; } }
+    // spare ranks: split the heaviest run that still holds two contigs with reads, at its most balanced point
+    while ((int)start.size() < world) {
+        size_t best = SIZE_MAX, best_cut = 0; uint64_t best_load = 0;
+        for (size_t g = 0; g < start.size(); ++g) {
+            const size_t a0 = start[g], a1 = g + 1 < start.size() ? start[g + 1] : n;
+            uint64_t load = 0; size_t nz = 0;
+            for (size_t t = a0; t < a1; ++t) { load += w[t]; nz += w[t] != 0; }
+            if (nz < 2 || load <= best_load) continue;
+            uint64_t left = 0, best_diff = UINT64_MAX; size_t cut = 0;
+            for (size_t t = a0; t + 1 < a1; ++t) {
+                left += w[t];
+                if (left == 0 || left == load) continue;
+                const uint64_t diff = left > load - left ? left - (load - left) : (load - left) - left;
+                if (diff < best_diff) { best_diff = diff; cut = t + 1; }
+            }
+            if (cut) { best = g; best_cut = cut; best_load = load; }
+        }
+        if (best == SIZE_MAX) break;
+        start.insert(start.begin() + (long)best + 1, best_cut);
+    }
+    for (size_t g = 0; g < start.size(); ++g) {
+        const size_t a1 = g + 1 < start.size() ? start[g + 1] : n;
+        for (size_t t = start[g]; t < a1; ++t) assign[t] = (int32_t)g;
     }
     return assign;
+}
+
+// Byte ranges of a set of contigs; contigs that follow each other in the file (nothing but read-less contigs in
+// between) become ONE range.
+std::vector<Chunk64> coalesced_contig_ranges(const BaiIndex& idx, const std::vector<int32_t>& contigs) {
+    std::vector<int32_t> tids(contigs);
+    std::sort(tids.begin(), tids.end());
+    std::vector<Chunk64> ranges;
+    int32_t last = -2;
+    for (int32_t tid : tids) {
+        Chunk64 c;
+        if (!idx.contig_range(tid, &c)) continue;
+        bool adjacent = !ranges.empty() && c.beg >= ranges.back().end;
+        for (int32_t t = last + 1; adjacent && t < tid; ++t) { Chunk64 x; if (idx.contig_range(t, &x)) adjacent = false; }
+        if (adjacent) ranges.back().end = c.end; else ranges.push_back(c);
+        last = tid;
+    }
+    return ranges;
 }
 
 }  // namespace rtjx

@@ -119,7 +119,9 @@ uint64_t scan_bgzf_blocks(const BamFile& bam, uint64_t coff, uint64_t end_coff, 
 uint64_t scan_bgzf_blocks_mem(const uint8_t* buf, size_t n, uint64_t base_coff, uint64_t end_coff,
                               std::vector<BgzfBlockInfo>* out, bool* stop, bool* partial);
 
-// LPT assignment of contigs to shards by compressed byte span.
+// Contigs -> shards: runs of consecutive contigs, balanced on compressed bytes (min-max contiguous partition); and the
+// byte ranges of such a run, coalesced into one range per run.
 std::vector<int32_t> plan_contig_shards(const BamFile& bam, const BaiIndex& idx, int world);
+std::vector<Chunk64> coalesced_contig_ranges(const BaiIndex& idx, const std::vector<int32_t>& contigs);
 
 }  // namespace rtjx

@@ -135,7 +135,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
         if (off0 == 0) off0 = bam.header().first_record_voffset;
         ranges.push_back(Chunk64{off0, UINT64_MAX});
     } else if (spec.kind == IterSpec::Contigs) {
-        for (int32_t tid : spec.contigs) { Chunk64 c; if (idx.contig_range(tid, &c)) ranges.push_back(c); }
+        ranges = coalesced_contig_ranges(idx, spec.contigs);   // a shard of consecutive contigs streams as one range
     } else {
         return 1;
     }

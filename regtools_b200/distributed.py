@@ -14,28 +14,69 @@ import numpy as np
 from .extractor import JUNCTION_DTYPE, JunctionsExtractor
 
 
+_PINNED = {}
+
+
+def _pinned(nbytes: int, tag: str):
+    """Grow-only pinned staging buffers (a fresh cudaHostAlloc per call costs more than the exchange itself)."""
+    import torch
+    buf = _PINNED.get(tag)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+        _PINNED[tag] = buf
+    return buf
+
+
 def all_gather_tables(table: np.ndarray, device=None) -> List[np.ndarray]:
-    """all-gatherv of rtjx_junction tables: sizes first, then bytes padded to the largest table."""
+    """all-gatherv of rtjx_junction tables: sizes first, then bytes padded to the largest table.
+    NCCL: two all_gather_into_tensor calls on device buffers, pinned staging on both sides (one H2D of this rank's
+    table, one D2H of the gathered tables).  gloo (CPU tests): the list form on host tensors."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size()
     backend = dist.get_backend()
-    dev = device if device is not None else ("cuda" if backend == "nccl" else "cpu")
-    n = torch.tensor([len(table)], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(sizes, n)
-    sizes = [int(s.item()) for s in sizes]
-    cap = max(max(sizes), 1) * JUNCTION_DTYPE.itemsize
-    raw = np.zeros(cap, np.uint8)
-    raw[:len(table) * JUNCTION_DTYPE.itemsize] = np.ascontiguousarray(table, dtype=JUNCTION_DTYPE).view(np.uint8)
-    mine = torch.from_numpy(raw).to(dev)
-    bufs = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
-    dist.all_gather(bufs, mine)
-    out = []
-    for r in range(world):
-        b = bufs[r].cpu().numpy()[:sizes[r] * JUNCTION_DTYPE.itemsize]
-        out.append(b.view(JUNCTION_DTYPE).copy())
-    return out
+    isz = JUNCTION_DTYPE.itemsize
+    mine_np = np.ascontiguousarray(table, dtype=JUNCTION_DTYPE).view(np.uint8).reshape(-1)
+    if backend != "nccl":
+        n = torch.tensor([len(table)], dtype=torch.int64)
+        sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        sizes = [int(s.item()) for s in sizes]
+        cap = max(max(sizes), 1) * isz
+        raw = np.zeros(cap, np.uint8)
+        raw[:mine_np.size] = mine_np
+        bufs = [torch.empty(cap, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(bufs, torch.from_numpy(raw))
+        return [bufs[r].numpy()[:sizes[r] * isz].view(JUNCTION_DTYPE).copy() for r in range(world)]
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    # one collective per call in the steady state: every rank sends [count:int64][table bytes] in a slot of `cap` bytes;
+    # the slot only grows (and the exchange is repeated once) when some rank's table does not fit
+    global _SLOT
+    while True:
+        cap = _SLOT
+        stage = _pinned(cap, "send")
+        sview = stage.numpy()
+        sview[:8] = np.frombuffer(np.int64(len(table)).tobytes(), np.uint8)
+        fit = 8 + mine_np.size <= cap
+        if fit:
+            sview[8:8 + mine_np.size] = mine_np
+        mine = torch.empty(cap, dtype=torch.uint8, device=dev)
+        used = 8 + (mine_np.size if fit else 0)
+        mine[:used].copy_(stage[:used], non_blocking=True)
+        out = torch.empty(world * cap, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, mine)
+        host = _pinned(world * cap, "recv")
+        host[:world * cap].copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = host.numpy()
+        sizes = [int(np.frombuffer(h[r * cap:r * cap + 8].tobytes(), np.int64)[0]) for r in range(world)]
+        need = 8 + max(sizes) * isz
+        if need <= cap:
+            return [h[r * cap + 8:r * cap + 8 + sizes[r] * isz].view(JUNCTION_DTYPE).copy() for r in range(world)]
+        _SLOT = (need + need // 4 + 4095) & ~4095
+
+
+_SLOT = 256 << 10
 
 
 def merge_tables(bam: str, tables: List[np.ndarray], min_anchor: int = 8) -> JunctionsExtractor:

@@ -1,7 +1,7 @@
 // tools/bamgen.cc — bench/test infrastructure: deterministic synthetic RNA-seq BAM generator with
 // multi-threaded BGZF deflate, and a BAI indexer.  Not part of the product path.
 //
-//   bamgen gen --out x.bam --config c2|c3|tiny --reads N [--seed 1234] [--level 6] [--threads T] [--qual8]
+//   bamgen gen --out x.bam --config c2|c2xN|c3|tiny --reads N [--seed 1234] [--level 6] [--threads T] [--qual8]
 //   bamgen index x.bam            (writes x.bam.bai)
 //
 // Workload shape follows SURVEY.md §8(d): junction catalog of one intron per 12 kb with Zipf(1)
@@ -190,6 +190,11 @@ Config make_config(const std::string& name) {
     c.window = 1 << 20;
     if (name == "c2") {
         c.contigs = {{"chr1", 248956422}};
+        c.read_len = 101; c.spliced = 0.08; c.paired_only = false;
+    } else if (name.rfind("c2x", 0) == 0 && atoi(name.c_str() + 3) > 0) {
+        // weak-scaling shape: N contigs, each the c2 chromosome (one contig per GPU when sharded N ways)
+        const int n = atoi(name.c_str() + 3);
+        for (int i = 0; i < n; ++i) c.contigs.push_back({"chr" + std::to_string(i + 1), 248956422});
         c.read_len = 101; c.spliced = 0.08; c.paired_only = false;
     } else if (name == "c3") {
         static const int64_t L[24] = {248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
