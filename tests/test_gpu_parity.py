@@ -379,3 +379,55 @@ def test_large_generated_bam_property_checks(tmp_path):
     o.extract_bam(bam)
     tables_equal(t1, o.table())
     assert int(t1["read_count"].sum()) == int(o.table()["read_count"].sum())
+
+
+def test_full_size_c2_three_paths_agree():
+    """BASELINE configs[1] at full size (10M reads, the bench's BAM): size-independent properties.  The device feeder
+    (GPU inflate + record split), the host feeder and the kernel-level batch path must give the same table; names are a
+    permutation of 1..U; order is compare_junctions'; read counts add up to the QC-passing candidates; the fused scan
+    (variant 6) agrees; a sub-region agrees with the oracle run on that region."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    rt = _rt()
+    bam = bench.ensure_bam("c2", 10_000_000, 6)
+    dev = rt.JunctionsExtractor(bam, ".", 0, inflate_mode=2)
+    dev.identify_junctions_from_BAM()
+    t_dev, st_dev = dev.junction_table(), dev.stats()
+    dev.close()
+    host = rt.JunctionsExtractor(bam, ".", 0, inflate_mode=1)
+    host.identify_junctions_from_BAM()
+    t_host, st_host = host.junction_table(), host.stats()
+    host.close()
+    assert st_dev["reads"] == st_host["reads"] == 10_000_000 and st_dev["inflated_bytes"] == st_host["inflated_bytes"]
+    assert st_dev["candidates"] == st_host["candidates"]
+    assert np.array_equal(t_dev, t_host)
+    ld = rt.JunctionsExtractor(bam, ".", 0, device=-1)
+    arrs = ld.load_batch()
+    ld.close()
+    n_n = synth.count_n_ops(arrs[4])
+    assert n_n == st_dev["candidates"]
+    d = [torch.from_numpy(x.view(np.int32)).cuda() for x in arrs]
+    for variant in (5, 6):
+        ex = rt.JunctionsExtractor(bam, ".", 0, scan_variant=variant)
+        ex.set_contigs(["chr1"])
+        ex.scan_batch(*d, n_junction_ops=n_n)
+        t = ex.junction_table()
+        ex.close()
+        assert np.array_equal(t, t_dev), variant
+    U = len(t_dev)
+    assert sorted(t_dev["name_index"].tolist()) == list(range(1, U + 1))
+    key = list(zip(t_dev["thick_start"].tolist(), t_dev["thick_end"].tolist(), t_dev["name_index"].tolist()))
+    assert key == sorted(key)
+    # every N op whose intron length passes junction_qc is counted exactly once
+    cig = arrs[4]
+    ln = (cig[(cig & 0xF) == 3] >> 4).astype(np.int64)
+    multi = np.diff(arrs[3].astype(np.int64)) > 1                  # all reads of this BAM are mapped to chr1
+    assert multi.any()
+    assert int(t_dev["read_count"].sum()) == int(np.count_nonzero((ln >= 70) & (ln <= 500000)))
+    o = Oracle(8, 70, 500000, 0)
+    o.extract_bam(bam, "chr1:100000000-100400000")
+    sub = rt.JunctionsExtractor(bam, "chr1:100000000-100400000", 0)
+    sub.identify_junctions_from_BAM()
+    tables_equal(sub.junction_table(), o.table())
+    sub.close()

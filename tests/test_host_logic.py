@@ -150,6 +150,27 @@ def test_plan_shards_balances_contigs():
     assert len(set(rt().plan_shards(SYN, 8))) == 3
 
 
+def test_plan_shards_are_contiguous_runs_of_contigs(tmp_path):
+    """A shard is a run of consecutive contigs (one contiguous byte range of the sorted file per rank), balanced on
+    compressed bytes: min-max over contiguous partitions, spare ranks split the heaviest runs."""
+    bam = str(tmp_path / "wg.bam")
+    subprocess.check_call([os.path.join(ROOT, "tools", "bamgen"), "gen", "--out", bam, "--config", "c3", "--reads", "120000", "--seed", "3",
+                           "--threads", "2"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    sizes = None
+    for world in (2, 3, 4, 8, 24, 40):
+        a = rt().plan_shards(bam, world)
+        assert len(a) == 24 and a == sorted(a) and a[0] == 0                     # runs of consecutive contigs, in file order
+        assert set(a) == set(range(min(world, 24)))                              # every rank that can get a contig gets one
+        if sizes is None:
+            ex = rt().JunctionsExtractor(bam, ".", 0, device=-1)
+            tid = ex.load_batch()[0]
+            ex.close()
+            sizes = np.bincount(tid[tid >= 0], minlength=24).astype(float)
+        load = np.array([sizes[[t for t in range(24) if a[t] == r]].sum() for r in range(min(world, 24))])
+        # no contiguous partition can beat max(largest contig, average); allow 35 % on top (reads ~ bytes only roughly)
+        assert load.max() <= 1.35 * max(sizes.max(), sizes.sum() / min(world, 24)), (world, load)
+
+
 def _oracle_table_as_rtjx(o, first_ord_base=0):
     r = rt()
     t = o.table()
