@@ -148,6 +148,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     // spliced and unspliced reads alternate between a leaf bin and its ancestors — exactly the deep-coverage windows whose
     // single 16 kb linear-index entry spans megabytes — the chunk list cuts the stream every few BGZF blocks: 5x the
     // seeds and half the longest segment on the C2 BAM.  The pseudo-bin's second "chunk" holds counts, not offsets.)
+    if (!feed_linear_seeds_only_)
     for (const BaiIndex::Ref& r : idx.refs)
         for (const BaiIndex::Bin& b : r.bins) {
             if (b.bin == BaiIndex::META_BIN) continue;
@@ -196,7 +197,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
         stats_.host_wait_s += now_s() - tw;
         stats_.d2h_bytes += sizeof(FeedState);
         const FeedState st = *F.h_state;
-        if (st.flags || st.bad_offset != LLONG_MAX) { declined = true; return 0; }
+        if (st.flags || st.bad_offset != LLONG_MAX) { declined = true; feed_decline_flags_ = st.flags; return 0; }
         if (st.n_rec) {
             BatchView v;
             v.n_reads = st.n_rec; v.n_ops = st.n_ops; v.first_ordinal = ordinal;

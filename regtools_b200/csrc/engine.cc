@@ -515,12 +515,20 @@ int Engine::run_impl() {
     const bool streamable = spec.kind == IterSpec::WholeFile || spec.kind == IterSpec::Contigs;
     if (streamable && (prm_.inflate_mode == 2 || (prm_.inflate_mode == 0 && bam->size() >= (1u << 20)))) {
         const rtjx_stats saved = stats_;
-        rc = run_device(*bam, idx, spec);
-        if (rc == RTJX_OK) return RTJX_OK;
-        if (rc < 0) return rc;
-        if ((rc = clear())) return rc;                        // declined: start over on the host path
-        stats_ = saved;
-        contigs_ = bam->header().names; rank_dirty_ = true;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            // first with every record start the index knows (linear index + bin chunk boundaries); if that run is declined
+            // — e.g. an index whose chunk ends are not record boundaries — once more with the linear index alone
+            feed_linear_seeds_only_ = attempt == 1;
+            feed_decline_flags_ = 0;
+            rc = run_device(*bam, idx, spec);
+            if (rc == RTJX_OK) return RTJX_OK;
+            if (rc < 0) return rc;
+            if ((rc = clear())) return rc;                    // declined: start over
+            stats_ = saved;
+            contigs_ = bam->header().names; rank_dirty_ = true;
+            // (a walk started at a bogus seed can also end in a "malformed record" report, so any decline of the first
+            // attempt is retried; a genuinely malformed file costs one more device pass before the host path below)
+        }
     }
     uint32_t reads = prm_.batch_reads ? prm_.batch_reads : (spec.kind == IterSpec::Region ? (1u << 15) : (1u << 20));
     reads = std::max(reads, 1024u);

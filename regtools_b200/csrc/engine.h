@@ -130,6 +130,8 @@ private:
     struct DeviceFeedDeleter { void operator()(DeviceFeed* p) const; };
     std::unique_ptr<DeviceFeed, DeviceFeedDeleter> dfeed_;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> feed_prof_;
+    bool feed_linear_seeds_only_ = false;       // retry of a declined device run without the bin-chunk seeds
+    uint32_t feed_decline_flags_ = 0;           // FEED_FLAG_* of the group that made the device path decline
 
     // profiling
     struct ProfEv { cudaEvent_t a, b, c; };

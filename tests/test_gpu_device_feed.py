@@ -115,3 +115,34 @@ def test_malformed_record_falls_back(tmp_path):
     o.extract_bam(broken)
     assert st["reads"] == o.reads_seen() == 1500
     assert bed == o.bed12()
+
+
+def test_bad_bin_chunk_boundaries_retry_with_linear_index(tmp_path):
+    """The record walk is seeded by the linear index AND by the bin chunk boundaries.  An index whose chunk boundaries
+    are not record starts makes a walk miss its seed: the run is repeated on the device with the linear index alone
+    (no host inflate), and stays exact."""
+    import struct
+    bam = str(tmp_path / "g.bam")
+    subprocess.check_call([BAMGEN, "gen", "--out", bam, "--config", "tiny", "--reads", "300000", "--seed", "21"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    want_t, want_bed, _ = run(bam, 1)
+    d = bytearray(open(bam + ".bai", "rb").read())
+    n_ref = struct.unpack_from("<i", d, 4)[0]
+    o = 8
+    patched = 0
+    for _ in range(n_ref):
+        n_bin = struct.unpack_from("<i", d, o)[0]; o += 4
+        for _ in range(n_bin):
+            binid, n_chunk = struct.unpack_from("<Ii", d, o); o += 8
+            for c in range(n_chunk):
+                beg, end = struct.unpack_from("<QQ", d, o)
+                if binid != 37450 and c == 0 and n_chunk > 1 and (end & 0xffff) > 8:
+                    struct.pack_into("<Q", d, o + 8, end - 3)          # chunk end 3 bytes inside the previous record
+                    patched += 1
+                o += 16
+        n_intv = struct.unpack_from("<i", d, o)[0]; o += 4 + 8 * n_intv
+    assert patched > 10
+    open(bam + ".bai", "wb").write(bytes(d))
+    got_t, got_bed, st = run(bam, 2)
+    assert got_bed == want_bed and np.array_equal(got_t, want_t)
+    assert st["host_parse_s"] == 0.0 and st["inflated_bytes"] > 0           # second device attempt, not the host feeder
