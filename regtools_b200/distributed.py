@@ -47,7 +47,7 @@ def all_gather_tables(table: np.ndarray, device=None) -> List[np.ndarray]:
         raw[:mine_np.size] = mine_np
         bufs = [torch.empty(cap, dtype=torch.uint8) for _ in range(world)]
         dist.all_gather(bufs, torch.from_numpy(raw))
-        return [bufs[r].numpy()[:sizes[r] * isz].view(JUNCTION_DTYPE).copy() for r in range(world)]
+        return [bufs[r].numpy()[:sizes[r] * isz].copy().view(JUNCTION_DTYPE) for r in range(world)]
     dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
     # one collective per call in the steady state: every rank sends [count:int64][table bytes] in a slot of `cap` bytes;
     # the slot only grows (and the exchange is repeated once) when some rank's table does not fit
@@ -60,10 +60,9 @@ def all_gather_tables(table: np.ndarray, device=None) -> List[np.ndarray]:
         fit = 8 + mine_np.size <= cap
         if fit:
             sview[8:8 + mine_np.size] = mine_np
-        mine = torch.empty(cap, dtype=torch.uint8, device=dev)
+        mine, out = _device_slots(cap, world, dev)           # persistent: the same addresses every call
         used = 8 + (mine_np.size if fit else 0)
         mine[:used].copy_(stage[:used], non_blocking=True)
-        out = torch.empty(world * cap, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(out, mine)
         host = _pinned(world * cap, "recv")
         host[:world * cap].copy_(out, non_blocking=True)
@@ -72,11 +71,23 @@ def all_gather_tables(table: np.ndarray, device=None) -> List[np.ndarray]:
         sizes = [int(np.frombuffer(h[r * cap:r * cap + 8].tobytes(), np.int64)[0]) for r in range(world)]
         need = 8 + max(sizes) * isz
         if need <= cap:
-            return [h[r * cap + 8:r * cap + 8 + sizes[r] * isz].view(JUNCTION_DTYPE).copy() for r in range(world)]
+            # copy as BYTES, then view: numpy copies a structured array element by element (27 ns per junction, measured)
+            return [h[r * cap + 8:r * cap + 8 + sizes[r] * isz].copy().view(JUNCTION_DTYPE) for r in range(world)]
         _SLOT = (need + need // 4 + 4095) & ~4095
 
 
 _SLOT = 256 << 10
+_DEV = {}
+
+
+def _device_slots(cap: int, world: int, dev):
+    """Send slot and gather buffer on the device, allocated once per (cap, world, device)."""
+    import torch
+    key = (cap, world, str(dev))
+    if key not in _DEV:
+        _DEV.clear()
+        _DEV[key] = (torch.empty(cap, dtype=torch.uint8, device=dev), torch.empty(world * cap, dtype=torch.uint8, device=dev))
+    return _DEV[key]
 
 
 def merge_tables(bam: str, tables: List[np.ndarray], min_anchor: int = 8) -> JunctionsExtractor:

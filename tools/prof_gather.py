@@ -38,9 +38,8 @@ for it in range(13):
     stage = D._pinned(cap, "send"); sview = stage.numpy()
     sview[:8] = np.frombuffer(np.int64(len(tab)).tobytes(), np.uint8); sview[8:8 + mine_np.size] = mine_np
     p.append(time.perf_counter())
-    mine = torch.empty(cap, dtype=torch.uint8, device=dev); used = 8 + mine_np.size
+    mine, out = D._device_slots(cap, world, dev); used = 8 + mine_np.size
     mine[:used].copy_(stage[:used], non_blocking=True)
-    out = torch.empty(world * cap, dtype=torch.uint8, device=dev)
     torch.cuda.synchronize(); p.append(time.perf_counter())
     dist.all_gather_into_tensor(out, mine)
     p.append(time.perf_counter())
@@ -53,6 +52,6 @@ for it in range(13):
     p.append(time.perf_counter())
     dist.barrier(); torch.cuda.synchronize(); p.append(time.perf_counter())
     if it >= 3: P += np.diff(p)
-print(f"rank {rank}: slot {D._SLOT} stage {P[0]*100:.3f} h2d {P[1]*100:.3f} nccl_call {P[2]*100:.3f} nccl_wait {P[3]*100:.3f} d2h {P[4]*100:.3f} split {P[5]*100:.3f} barrier {P[6]*100:.3f} ms", flush=True)
-print(f"rank {rank}: clear {T[0]*100:.2f} scan_call {T[1]*100:.2f} finalize {T[2]*100:.2f} table {T[3]*100:.2f} gather {T[4]*100:.2f} barrier {T[5]*100:.2f} ms/step (avg of 10)", flush=True)
+print(f"\nrank {rank}: slot {D._SLOT} stage {P[0]*100:.3f} h2d {P[1]*100:.3f} nccl_call {P[2]*100:.3f} nccl_wait {P[3]*100:.3f} d2h {P[4]*100:.3f} split {P[5]*100:.3f} barrier {P[6]*100:.3f} ms", flush=True)
+print(f"\nrank {rank}: clear {T[0]*100:.2f} scan_call {T[1]*100:.2f} finalize {T[2]*100:.2f} table {T[3]*100:.2f} gather {T[4]*100:.2f} barrier {T[5]*100:.2f} ms/step (avg of 10)", flush=True)
 dist.destroy_process_group()
