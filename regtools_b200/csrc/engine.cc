@@ -781,7 +781,65 @@ inline int name_cmp(uint32_t a, uint32_t b) {        // std::string compare of "
 }
 }  // namespace
 
+// Union of per-shard tables without sorting anything (the rank-0 step of a multi-GPU run).  Shards are runs of
+// consecutive contigs (plan_contig_shards), every shard's table arrives sorted by compare_junctions with names ranked
+// inside the shard, and a coordinate-sorted BAM visits contigs in tid order: the global name of a junction is its local
+// name plus the sizes of the shards before it, and the global order is a merge of the (already sorted) tables.  Every
+// assumption is checked in O(n); anything else takes the general path below.
+bool Engine::merge_sorted_shards() {
+    if (!final_.empty() || import_sizes_.empty() || imported_.size() >= 100000000ull) return false;
+    std::vector<uint32_t> cr = contig_ranks(contigs_);
+    auto crank = [&](int32_t tid) { return (tid >= 0 && (size_t)tid < cr.size()) ? cr[(size_t)tid] : 0x40000000u + (uint32_t)tid; };
+    auto bed_less = [&](const rtjx_junction& x, const rtjx_junction& y) {
+        const uint32_t cx = crank(x.tid), cy = crank(y.tid);
+        if (cx != cy) return cx < cy;
+        if (x.thick_start != y.thick_start) return x.thick_start < y.thick_start;
+        if (x.thick_end != y.thick_end) return x.thick_end < y.thick_end;
+        return x.name_index < y.name_index;
+    };
+    struct Part { size_t lo, hi; int32_t tmin, tmax; };
+    std::vector<Part> parts;
+    size_t off = 0;
+    for (size_t n : import_sizes_) { if (n) parts.push_back(Part{off, off + n, INT32_MAX, INT32_MIN}); off += n; }
+    std::vector<const rtjx_junction*> by_name;
+    for (Part& p : parts) {
+        const size_t n = p.hi - p.lo;
+        by_name.assign(n, nullptr);
+        for (size_t i = p.lo; i < p.hi; ++i) {
+            const rtjx_junction& j = imported_[i];
+            if (j.name_index == 0 || j.name_index > n || by_name[j.name_index - 1]) return false;      // names: a permutation of 1..n
+            by_name[j.name_index - 1] = &j;
+            if (i > p.lo && bed_less(j, imported_[i - 1])) return false;                                 // sorted as delivered
+            p.tmin = std::min(p.tmin, j.tid); p.tmax = std::max(p.tmax, j.tid);
+        }
+        for (size_t r = 1; r < n; ++r) {                                                               // name order == (tid, first seen)
+            const rtjx_junction &a = *by_name[r - 1], &b = *by_name[r];
+            if (a.tid > b.tid || (a.tid == b.tid && a.first_ord >= b.first_ord)) return false;
+        }
+    }
+    std::sort(parts.begin(), parts.end(), [](const Part& a, const Part& b) { return a.tmin < b.tmin; });
+    for (size_t k = 1; k < parts.size(); ++k) if (parts[k].tmin <= parts[k - 1].tmax) return false;     // disjoint runs of contigs
+    uint32_t name_base = 0;
+    final_.clear();
+    final_.reserve(imported_.size());
+    std::vector<rtjx_junction> tmp;
+    for (const Part& p : parts) {
+        const size_t mid = final_.size();
+        for (size_t i = p.lo; i < p.hi; ++i) { rtjx_junction j = imported_[i]; j.name_index += name_base; final_.push_back(j); }
+        name_base += (uint32_t)(p.hi - p.lo);
+        if (mid) {
+            tmp.resize(final_.size());
+            std::merge(final_.begin(), final_.begin() + (long)mid, final_.begin() + (long)mid, final_.end(), tmp.begin(), bed_less);
+            final_.swap(tmp);
+        }
+    }
+    return true;
+}
+
 void Engine::host_rank_and_sort() {
+    const bool trace = getenv("RTJX_TRACE") != nullptr;
+    if (merge_sorted_shards()) { if (trace) fprintf(stderr, "[rtjx] shard merge: %zu tables merged without sorting\n", import_sizes_.size()); return; }
+    if (trace && !imported_.empty()) fprintf(stderr, "[rtjx] shard merge: general path (re-rank + sort)\n");
     const bool sharded = !imported_.empty();
     final_.insert(final_.end(), imported_.begin(), imported_.end());
     std::vector<uint32_t> order(final_.size());
@@ -884,13 +942,14 @@ int64_t Engine::get(rtjx_junction* out, size_t cap) {
 int Engine::import(const rtjx_junction* j, size_t n) {
     if (n && !j) return fail(RTJX_E_ARG, "null junctions");
     imported_.insert(imported_.end(), j, j + n);
+    import_sizes_.push_back(n);
     finalized_ = false;
     return RTJX_OK;
 }
 
 int Engine::clear() {
     const uint64_t known_unique = unique_upper_;      // upper bound of occupied slots
-    final_.clear(); imported_.clear(); finalized_ = false; dirty_ = false; unique_upper_ = 0; add_ord_ = 0;
+    final_.clear(); imported_.clear(); import_sizes_.clear(); finalized_ = false; dirty_ = false; unique_upper_ = 0; add_ord_ = 0;
     if (dev_ready_) {
         cudaSetDevice(prm_.device);
         if (d_table_) {

@@ -119,6 +119,8 @@ private:
     // finalized table (host)
     std::vector<rtjx_junction> final_;
     std::vector<rtjx_junction> imported_;
+    std::vector<size_t> import_sizes_;          // one entry per rtjx_import call (= one shard's table)
+    bool merge_sorted_shards();
     bool finalized_ = false;
 
     // cached feeder output for load_batch

@@ -217,3 +217,46 @@ def test_name_index_above_1e8_sorts_as_string():
     h.import_table(t)
     assert [int(x) for x in h.junction_table()["name_index"]] == [1, 2, 3]
 
+
+
+def test_sorted_shard_tables_merge_without_sorting(capfd, monkeypatch):
+    """Rank 0 of a multi-GPU run: shard tables (runs of consecutive contigs, sorted, names ranked inside the shard) are
+    merged in O(n); tables that break an assumption take the general re-rank + sort path.  Both must print the whole
+    file's BED12."""
+    monkeypatch.setenv("RTJX_TRACE", "1")
+    r = rt()
+    whole = Oracle(8, 70, 500000, 0)
+    whole.extract_bam(SYN)
+    want = whole.bed12()
+
+    def shard(region, tid_ord_base):
+        o = Oracle(8, 70, 500000, 0)
+        o.extract_bam(SYN, region)
+        t = o.table()
+        part = np.zeros(len(t), r.JUNCTION_DTYPE)
+        for f in ("tid", "start", "end", "thick_start", "thick_end", "read_count", "name_index", "strand", "left_ok", "right_ok"):
+            part[f] = t[f]
+        part["first_ord"] = tid_ord_base + t["name_index"].astype(np.uint64)      # monotone in the shard's name order
+        return part
+
+    parts = [shard("1", 0), shard("10", 1 << 32), shard("2", 2 << 32)]
+    for order, expect in (((0, 1, 2), "merged without sorting"), ((2, 0, 1), "merged without sorting")):
+        ex = r.JunctionsExtractor(SYN, ".", 0, device=-1)
+        ex.set_contigs(["1", "10", "2"])
+        for k in order:
+            ex.import_table(parts[k])
+        buf = io.StringIO()
+        ex.print_all_junctions(buf)
+        ex.close()
+        assert buf.getvalue() == want
+        assert expect in capfd.readouterr().err
+    broken = [p.copy() for p in parts]
+    broken[1]["name_index"][:] = broken[1]["name_index"][::-1]                   # names no longer follow (tid, first_ord)
+    ex = r.JunctionsExtractor(SYN, ".", 0, device=-1)
+    ex.set_contigs(["1", "10", "2"])
+    for p in broken:
+        ex.import_table(p)
+    buf = io.StringIO()
+    ex.print_all_junctions(buf)
+    ex.close()
+    assert buf.getvalue() == want and "general path" in capfd.readouterr().err
