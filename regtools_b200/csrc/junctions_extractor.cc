@@ -168,6 +168,36 @@ vector<Junction> JunctionsExtractor::get_all_junctions() {
     return out;
 }
 
+static Junction to_junction(rtjx_t* h, const rtjx_junction& r) {
+    Junction j(rtjx_contig(h, r.tid), r.start, r.end, r.thick_start, r.thick_end, string(1, (char)r.strand));
+    stringstream name_ss;
+    name_ss << "JUNC" << setfill('0') << setw(8) << (int)r.name_index;
+    j.name = name_ss.str();
+    j.read_count = r.read_count;
+    { stringstream s; s << r.read_count; j.score = s.str(); }
+    j.has_left_min_anchor = r.left_ok; j.has_right_min_anchor = r.right_ok;
+    j.added = true;
+    return j;
+}
+
+vector<vector<Junction> > JunctionsExtractor::get_all_junctions_in_regions(const vector<string>& regions) {
+    rtjx_t* h = handle();
+    vector<const char*> ptrs(regions.size());
+    for (size_t i = 0; i < regions.size(); ++i) ptrs[i] = regions[i].c_str();
+    check(rtjx_run_regions(h, ptrs.data(), ptrs.size()));
+    vector<vector<Junction> > out(regions.size());
+    vector<rtjx_junction> raw;
+    for (size_t i = 0; i < regions.size(); ++i) {
+        const int64_t n = rtjx_region_count(h, i);
+        check((int)(n < 0 ? n : 0));
+        raw.resize((size_t)n);
+        if (n) check((int)min<int64_t>(rtjx_region_get(h, i, raw.data(), raw.size()), 0));
+        out[i].reserve((size_t)n);
+        for (size_t k = 0; k < raw.size(); ++k) out[i].push_back(to_junction(h, raw[k]));
+    }
+    return out;
+}
+
 void JunctionsExtractor::print_all_junctions(ostream& out) {
     rtjx_t* h = handle();
     if (output_file_ != string("NA")) {

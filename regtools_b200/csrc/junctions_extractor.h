@@ -92,6 +92,11 @@ public:
     std::string get_bam();                                                  // :146-148
     int add_junction(Junction j1);                                          // :174-235
 
+    // Not in the reference: the per-variant loop of cis_splice_effects_identifier.cc:267-311 in one pass over the BAM.
+    // Element i is what `JunctionsExtractor(bam, regions[i], ...)` + identify + get_all_junctions() returns; the object
+    // must have been constructed with region "." (rtjx_run_regions).
+    std::vector<std::vector<Junction> > get_all_junctions_in_regions(const std::vector<std::string>& regions);
+
     // B200-specific knobs (not in the reference): CUDA device, host inflate threads, contig shard
     void set_device(int device) { device_ = device; }
     void set_threads(int n) { n_threads_ = n; }
