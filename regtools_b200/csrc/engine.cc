@@ -890,7 +890,7 @@ int Engine::ensure_finalize_buffers(uint32_t n, size_t n_contigs) {
 
 int Engine::finalize(cudaStream_t user_stream) {
     if (finalized_ && !dirty_) return RTJX_OK;
-    final_.clear();
+    final_.clear(); pinned_final_n_ = 0;
     uint32_t n = 0;
     if (dev_ready_ && d_table_) {
         cudaSetDevice(prm_.device);
@@ -916,27 +916,30 @@ int Engine::finalize(cudaStream_t user_stream) {
             CK(cudaMemcpyAsync(h_final_, d_out_, (size_t)n * sizeof(OutJunction), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
-            final_.assign(h_final_, h_final_ + n);
+            pinned_final_n_ = n;                           // the table stays in the pinned buffer: count/get/print read it there
             if (prm_.profile) { float ms = 0; if (cudaEventElapsedTime(&ms, ea, eb) == cudaSuccess) stats_.finalize_ms += ms; ev_pool_.push_back(ea); ev_pool_.push_back(eb); }
             stats_.kernel_launches += 2;     // ours: compact + name assignment (CUB's merge-sort passes not counted)
             stats_.d2h_bytes += (size_t)n * sizeof(OutJunction);
         }
     }
-    if (!imported_.empty() || n >= 100000000u) host_rank_and_sort();
+    if (!imported_.empty() || n >= 100000000u) {
+        if (pinned_final_n_) { final_.assign(h_final_, h_final_ + pinned_final_n_); pinned_final_n_ = 0; }
+        host_rank_and_sort();
+    }
     finalized_ = true; dirty_ = false;
     return RTJX_OK;
 }
 
 int64_t Engine::count() {
     int rc = finalize(nullptr);
-    return rc ? rc : (int64_t)final_.size();
+    return rc ? rc : (int64_t)final_size();
 }
 
 int64_t Engine::get(rtjx_junction* out, size_t cap) {
     int rc = finalize(nullptr);
     if (rc) return rc;
-    if (out && cap) memcpy(out, final_.data(), std::min(cap, final_.size()) * sizeof(rtjx_junction));
-    return (int64_t)final_.size();
+    if (out && cap) memcpy(out, final_data(), std::min(cap, final_size()) * sizeof(rtjx_junction));
+    return (int64_t)final_size();
 }
 
 int Engine::import(const rtjx_junction* j, size_t n) {
@@ -949,7 +952,7 @@ int Engine::import(const rtjx_junction* j, size_t n) {
 
 int Engine::clear() {
     const uint64_t known_unique = unique_upper_;      // upper bound of occupied slots
-    final_.clear(); imported_.clear(); import_sizes_.clear(); finalized_ = false; dirty_ = false; unique_upper_ = 0; add_ord_ = 0;
+    final_.clear(); pinned_final_n_ = 0; imported_.clear(); import_sizes_.clear(); finalized_ = false; dirty_ = false; unique_upper_ = 0; add_ord_ = 0;
     if (dev_ready_) {
         cudaSetDevice(prm_.device);
         if (d_table_) {
@@ -993,7 +996,9 @@ int Engine::write_bed12(int fd) {
     };
     std::vector<size_t> clen(contigs_.size());
     for (size_t i = 0; i < contigs_.size(); ++i) clen[i] = contigs_[i].size();
-    for (const rtjx_junction& j : final_) {
+    const rtjx_junction* fin = final_data();
+    for (size_t fi = 0, fn = final_size(); fi < fn; ++fi) {
+        const rtjx_junction& j = fin[fi];
         if (!(j.left_ok && j.right_ok)) continue;
         const bool known = j.tid >= 0 && (size_t)j.tid < contigs_.size();
         const char* chrom = known ? contigs_[(size_t)j.tid].c_str() : contig(j.tid);

@@ -116,8 +116,11 @@ private:
     rtjx_junction* h_final_ = nullptr; uint32_t h_final_cap_ = 0;   // pinned D2H staging
     int ensure_finalize_buffers(uint32_t n, size_t n_contigs);
 
-    // finalized table (host)
+    // finalized table (host): in the pinned D2H buffer when it came straight from the device (no copy), else in final_
     std::vector<rtjx_junction> final_;
+    uint32_t pinned_final_n_ = 0;
+    const rtjx_junction* final_data() const { return pinned_final_n_ ? h_final_ : final_.data(); }
+    size_t final_size() const { return pinned_final_n_ ? pinned_final_n_ : final_.size(); }
     std::vector<rtjx_junction> imported_;
     std::vector<size_t> import_sizes_;          // one entry per rtjx_import call (= one shard's table)
     bool merge_sorted_shards();

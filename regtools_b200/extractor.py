@@ -249,7 +249,7 @@ class JunctionsExtractor:
         """All junctions (sorted, unfiltered) as a structured numpy array of rtjx_junction."""
         h = self._handle()
         n = self._check(L.lib.rtjx_count(h))
-        arr = np.zeros(n, dtype=JUNCTION_DTYPE)
+        arr = np.empty(n, dtype=JUNCTION_DTYPE)          # rtjx_get fills every byte (40-byte records, pad included)
         if n:
             self._check(L.lib.rtjx_get(h, arr.ctypes.data_as(C.POINTER(L.Junction)), n))
         return arr
