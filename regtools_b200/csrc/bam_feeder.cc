@@ -511,9 +511,46 @@ bool BaiIndex::load(const std::string& path) {
         got += (size_t)r;
     }
     close(fd);
-    if (got != buf.size() || buf.size() < 8 || memcmp(buf.data(), "BAI\1", 4) != 0) return false;
+    if (got != buf.size() || buf.size() < 8) return false;
+    // hts_idx_load_local reads the index through bgzf_open (hts.c:1575): a .csi is BGZF-compressed, a .bai is plain
+    if (buf[0] == 0x1f && buf[1] == 0x8b) {
+        std::vector<uint8_t> raw;
+        size_t o = 0;
+        while (o + 18 <= buf.size()) {
+            if (buf[o] != 0x1f || buf[o + 1] != 0x8b) return false;
+            const size_t bsize = (size_t)(buf[o + 16] | buf[o + 17] << 8) + 1;
+            if (bsize < 26 || o + bsize > buf.size()) return false;
+            const uint32_t isize = rd32(buf.data() + o + bsize - 4);
+            const size_t at = raw.size();
+            raw.resize(at + isize);
+            if (isize) {
+                z_stream zs; memset(&zs, 0, sizeof zs);
+                if (inflateInit2(&zs, -15) != Z_OK) return false;
+                zs.next_in = buf.data() + o + 18; zs.avail_in = (uInt)(bsize - 26);
+                zs.next_out = raw.data() + at; zs.avail_out = isize;
+                const int zr = inflate(&zs, Z_FINISH);
+                inflateEnd(&zs);
+                if (zr != Z_STREAM_END || zs.avail_out != 0) return false;
+            }
+            o += bsize;
+        }
+        buf.swap(raw);
+        if (buf.size() < 8) return false;
+    }
     const uint8_t* p = buf.data() + 4; const uint8_t* e = buf.data() + buf.size();
     auto need = [&](size_t n) { return (size_t)(e - p) >= n; };
+    if (memcmp(buf.data(), "CSI\1", 4) == 0) {                  // hts.c:1580-1594
+        if (!need(12)) return false;
+        min_shift = rdi32(p); n_lvls = rdi32(p + 4); const int32_t l_aux = rdi32(p + 8); p += 12;
+        if (min_shift < 0 || min_shift > 30 || n_lvls < 1 || n_lvls > 9 || l_aux < 0 || !need((size_t)l_aux)) return false;
+        p += l_aux;
+        is_csi = true;
+    } else if (memcmp(buf.data(), "BAI\1", 4) == 0) {
+        min_shift = 14; n_lvls = 5; is_csi = false;
+    } else {
+        return false;
+    }
+    if (!need(4)) return false;
     int32_t n_ref = rdi32(p); p += 4;
     if (n_ref < 0) return false;
     refs.assign((size_t)n_ref, Ref());
@@ -524,14 +561,18 @@ bool BaiIndex::load(const std::string& path) {
         if (n_bin < 0) return false;
         r.bins.reserve((size_t)n_bin);
         for (int32_t j = 0; j < n_bin; ++j) {
-            if (!need(8)) return false;
-            Bin b; b.bin = rd32(p); b.loff = 0; int32_t n_chunk = rdi32(p + 4); p += 8;
+            if (!need(is_csi ? 16 : 8)) return false;
+            Bin b; b.bin = rd32(p); p += 4;
+            b.loff = 0;
+            if (is_csi) { b.loff = rd64(p); p += 8; }              // hts_idx_load_core, hts.c:1535-1538
+            int32_t n_chunk = rdi32(p); p += 4;
             if (n_chunk < 0 || !need((size_t)n_chunk * 16)) return false;
             b.chunks.resize((size_t)n_chunk);
             for (int32_t k = 0; k < n_chunk; ++k) { b.chunks[k].beg = rd64(p); b.chunks[k].end = rd64(p + 8); p += 16; }
             r.bins.push_back(std::move(b));
         }
         std::sort(r.bins.begin(), r.bins.end(), [](const Bin& a, const Bin& b) { return a.bin < b.bin; });
+        if (is_csi) continue;                                     // no linear index in a CSI
         if (!need(4)) return false;
         int32_t n_intv = rdi32(p); p += 4;
         if (n_intv < 0 || !need((size_t)n_intv * 8)) return false;
@@ -556,7 +597,10 @@ bool BaiIndex::load_for_bam(const std::string& bam, BaiIndex* out, bool* csi_pre
     auto exists = [](const std::string& f) { struct stat st; return stat(f.c_str(), &st) == 0; };
     std::string stem = bam;
     for (size_t i = bam.size(); i-- > 1;) if (bam[i] == '.') { stem = bam.substr(0, i); break; }
-    if (csi_present) *csi_present = exists(bam + ".csi") || exists(stem + ".csi");   // tried first by hts.c:2031-2042
+    if (csi_present) *csi_present = false;
+    // hts_idx_load (hts.c:2031-2042): ".csi" first (next to the file, then with the extension replaced), then ".bai"
+    if (exists(bam + ".csi")) { if (csi_present) *csi_present = true; return out->load(bam + ".csi"); }
+    if (exists(stem + ".csi")) { if (csi_present) *csi_present = true; return out->load(stem + ".csi"); }
     if (exists(bam + ".bai")) return out->load(bam + ".bai");
     if (exists(stem + ".bai")) return out->load(stem + ".bai");
     return false;
@@ -565,7 +609,7 @@ bool BaiIndex::load_for_bam(const std::string& bam, BaiIndex* out, bool* csi_pre
 bool BaiIndex::whole_file_start(uint64_t* voff) const {
     uint64_t off0 = UINT64_MAX;
     for (const Ref& r : refs) {
-        const Bin* m = r.find(META_BIN);
+        const Bin* m = r.find(meta_bin());
         if (m && !m->chunks.empty() && off0 > m->chunks[0].beg) off0 = m->chunks[0].beg;
     }
     if (off0 == UINT64_MAX && n_no_coor) off0 = 0;
@@ -576,7 +620,7 @@ bool BaiIndex::whole_file_start(uint64_t* voff) const {
 
 bool BaiIndex::contig_range(int32_t tid, Chunk64* out) const {
     if (tid < 0 || (size_t)tid >= refs.size()) return false;
-    const Bin* m = refs[tid].find(META_BIN);
+    const Bin* m = refs[tid].find(meta_bin());
     if (!m || m->chunks.empty()) return false;
     *out = m->chunks[0];
     return out->end > out->beg;
@@ -589,7 +633,7 @@ std::vector<Chunk64> BaiIndex::query(int32_t tid, int64_t beg, int64_t end) cons
     // min_off: hts.c:1765-1776
     uint64_t min_off = 0;
     {
-        uint32_t bin = 4681u + (uint32_t)(beg >> 14);
+        uint32_t bin = ((1u << (3 * n_lvls)) - 1u) / 7u + (uint32_t)(beg >> min_shift);      // hts_bin_first(n_lvls)
         const Bin* k = nullptr;
         do {
             k = r.find(bin);
@@ -603,11 +647,11 @@ std::vector<Chunk64> BaiIndex::query(int32_t tid, int64_t beg, int64_t end) cons
     // reg2bins: hts.c:1690-1706
     if (beg < end) {
         int64_t e = end;
-        int s = 14 + 15;
+        int s = min_shift + 3 * n_lvls;
         if (e >= (1ll << s)) e = 1ll << s;
         --e;
         int t = 0;
-        for (int l = 0; l <= 5; s -= 3, t += 1 << (3 * l), ++l)
+        for (int l = 0; l <= n_lvls; s -= 3, t += 1 << (3 * l), ++l)
             for (int64_t b = t + (beg >> s); b <= t + (e >> s); ++b) {
                 const Bin* k = r.find((uint32_t)b);
                 if (!k) continue;
@@ -685,7 +729,7 @@ bool feed_alignments(const BamFile& bam, const BaiIndex& idx, const IterSpec& sp
     case IterSpec::NoCoor: {
         uint64_t off0 = UINT64_MAX;
         if (!idx.refs.empty()) {
-            const BaiIndex::Bin* m = idx.refs.back().find(BaiIndex::META_BIN);
+            const BaiIndex::Bin* m = idx.refs.back().find(idx.meta_bin());
             if (m && !m->chunks.empty()) off0 = m->chunks[0].end;
         }
         if (off0 == UINT64_MAX && idx.n_no_coor) off0 = 0;

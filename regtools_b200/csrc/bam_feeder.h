@@ -25,15 +25,19 @@ struct BamHeader {
 
 struct Chunk64 { uint64_t beg, end; };  // virtual offsets
 
-// Parsed .bai (hts.c:1569-1624).
+// Parsed .bai or .csi (hts.c:1569-1624).  A CSI is BGZF-compressed, carries min_shift / depth, stores a loff per bin
+// and has no linear index; everything else (bins, chunks, pseudo-bin, query) is the same code with those two numbers.
 struct BaiIndex {
     struct Bin { uint32_t bin; uint64_t loff; std::vector<Chunk64> chunks; };
     struct Ref { std::vector<Bin> bins; std::vector<uint64_t> ioffset; const Bin* find(uint32_t bin) const; };
     std::vector<Ref> refs;
     uint64_t n_no_coor = 0;
+    int min_shift = 14, n_lvls = 5;               // BAI: fixed; CSI: from the file header
+    bool is_csi = false;
     static constexpr uint32_t META_BIN = 37450;   // hts.c:1092 for min_shift 14 / 5 levels
+    uint32_t meta_bin() const { return ((1u << (3 * n_lvls + 3)) - 1u) / 7u + 1u; }    // hts.c:1092 META_BIN(idx)
 
-    // hts_idx_getfn order: <bam>.bai then <stem>.bai (hts.c:2009-2029).  Returns false if absent/bad.
+    // hts_idx_load order (hts.c:2009-2042): <bam>.csi, <stem>.csi, <bam>.bai, <stem>.bai.  Returns false if absent/bad.
     static bool load_for_bam(const std::string& bam, BaiIndex* out, bool* csi_present);
     bool load(const std::string& path);
     // HTS_IDX_START offset (hts.c:1721-1731); false => iterator would be NULL.

@@ -151,7 +151,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     if (!feed_linear_seeds_only_)
     for (const BaiIndex::Ref& r : idx.refs)
         for (const BaiIndex::Bin& b : r.bins) {
-            if (b.bin == BaiIndex::META_BIN) continue;
+            if (b.bin == idx.meta_bin()) continue;
             for (const Chunk64& c : b.chunks) { if (c.beg) seeds_all.push_back(c.beg); if (c.end) seeds_all.push_back(c.end); }
         }
     if (!std::is_sorted(seeds_all.begin(), seeds_all.end())) std::sort(seeds_all.begin(), seeds_all.end());

@@ -477,7 +477,6 @@ int Engine::open_bam(std::unique_ptr<BamFile>* bam, BaiIndex* idx, IterSpec* spe
         return fail(RTJX_E_REGION, "Unable to iterate to region within BAM.\n\n");
     }
     if (!have_idx) {
-        if (csi) return fail(RTJX_E_UNSUPPORTED, "only .bai indexes are supported by the B200 path (.csi found)");
         return fail(RTJX_E_OPEN_INDEX, "Unable to open BAM/SAM index. Make sure alignments are indexed\n\n");
     }
     contigs_ = (*bam)->header().names; rank_dirty_ = true;

@@ -260,3 +260,42 @@ def test_sorted_shard_tables_merge_without_sorting(capfd, monkeypatch):
     ex.print_all_junctions(buf)
     ex.close()
     assert buf.getvalue() == want and "general path" in capfd.readouterr().err
+
+
+CSI_CASES = [("kat.bam", "kat.min14.csi"), ("kat.bam", "kat.min12.csi"), ("synth.bam", "synth.min14.csi")]
+
+
+def _with_csi(tmp_path, bam, csi, also_bai=False):
+    """Copy of a fixture BAM that has only a .csi next to it (built by the reference's htslib: oracle/ref_index.c)."""
+    import shutil
+    dst = str(tmp_path / bam)
+    shutil.copy(os.path.join(GOLD, "kat", bam), dst)
+    shutil.copy(os.path.join(GOLD, "csi", csi), dst + ".csi")
+    if also_bai:
+        shutil.copy(os.path.join(GOLD, "kat", bam + ".bai"), dst + ".bai")
+    return dst
+
+
+@pytest.mark.parametrize("bam,csi", CSI_CASES)
+def test_csi_index_gives_the_same_alignments_as_bai(bam, csi, tmp_path):
+    """hts_idx_load prefers <bam>.csi (hts.c:2031-2042); a CSI is BGZF-compressed, has its own min_shift / depth, a loff
+    per bin and no linear index (hts.c:1580-1594, 1535-1538).  Every region must yield exactly the BAI's alignments."""
+    src = _with_csi(tmp_path, bam, csi)
+    regions = [".", "1", "10", "2", "1:5000-6200", "1:900-1300", "10:500000-900000", "2:5,000,050-5,000,060", "1:1-1", "2:2400000-2500000"]
+    for reg in regions:
+        a = rt().JunctionsExtractor(src, reg, 0, device=-1)
+        b = rt().JunctionsExtractor(os.path.join(GOLD, "kat", bam), reg, 0, device=-1)
+        xa, xb = a.load_batch(), b.load_batch()
+        a.close(); b.close()
+        assert all(np.array_equal(u, v) for u, v in zip(xa, xb)), (csi, reg)
+        if reg == ".":
+            assert len(xa[0]) > 40
+    assert rt().plan_shards(src, 2) == rt().plan_shards(os.path.join(GOLD, "kat", bam), 2)
+
+
+def test_csi_takes_precedence_over_bai(tmp_path):
+    src = _with_csi(tmp_path, "kat.bam", "kat.min12.csi", also_bai=True)
+    open(src + ".bai", "wb").write(b"not an index")                 # would fail if it were read
+    ex = rt().JunctionsExtractor(src, "1:5000-6200", 0, device=-1)
+    assert len(ex.load_batch()[0]) > 0
+    ex.close()
