@@ -31,7 +31,7 @@ typedef enum {
     RTJX_E_OPEN_INDEX  = -3,  /* "Unable to open BAM/SAM index. ..."     junctions_extractor.cc:510 */
     RTJX_E_REGION      = -4,  /* "Unable to iterate to region within BAM." junctions_extractor.cc:521 */
     RTJX_E_CUDA        = -5,  /* no device / CUDA runtime failure                                   */
-    RTJX_E_UNSUPPORTED = -6,  /* -b barcodes, CRAM/SAM, .csi, compressed FASTA                      */
+    RTJX_E_UNSUPPORTED = -6,  /* -b barcodes, CRAM/SAM input, compressed FASTA                      */
     RTJX_E_NOMEM       = -7,
     RTJX_E_STATE       = -8,  /* call order violated                                                */
     RTJX_E_IO          = -9   /* also "Unable to extract FASTA sequence ..."  junctions_extractor.cc:553 */
