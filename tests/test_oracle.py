@@ -146,3 +146,21 @@ def test_fasta_fixtures_are_reproducible(motif_fastas):
     got = {k: hashlib.sha256(open(v, "rb").read()).hexdigest() for k, v in motif_fastas.items()}
     want = dict(line.split() for line in open(os.path.join(GOLD, "motif", "FASTA.sha256")))
     assert got == want
+
+
+@pytest.mark.skipif(not ref_available(), reason="oracle/_ref/regtools_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("args", [["-s", "XS"], ["-s", "intron-motif", "-a", "3"], ["-s", "RF", "-r", "10:1-700000"]])
+def test_oracle_vs_live_reference_with_fasta_on_fresh_bam(args, tmp_path, motif_fastas):
+    """Differential run against the unmodified reference with a FASTA (intron-motif strand first) on a BAM neither has seen."""
+    import subprocess
+    from oracle_py import REF_BIN
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bam = str(tmp_path / "fresh.bam")
+    subprocess.check_call([os.path.join(root, "tools", "bamgen"), "gen", "--out", bam, "--config", "tiny", "--reads", "20000",
+                           "--seed", "4242", "--threads", "2"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    fa = motif_fastas["synth"]                                   # contigs 1/10/2 of the `tiny` shape
+    p = subprocess.run([REF_BIN, "junctions", "extract"] + args + [bam, fa], capture_output=True, text=True)
+    assert p.returncode == 0
+    o = run_oracle(bam, args, fasta=fa)
+    assert o.bed12() == p.stdout
+    assert len(set(l.split("\t")[5] for l in p.stdout.splitlines())) >= 2
