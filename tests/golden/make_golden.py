@@ -118,9 +118,44 @@ def build_motif():
     print(f"wrote {len(manifest)} intron-motif golden outputs to {out_dir}")
 
 
+def build_barcodes():
+    """tests/golden/barcodes/: `-b` single-cell mode of the reference (set_junction_barcode, print_barcodes:
+    junctions_extractor.cc:362-374, .h:99-111) on a fixture with CB:Z tags (5 and 60 distinct barcodes per locus, reads
+    without CB, CB before and after XS)."""
+    import random
+    out_dir = os.path.join(HERE, "barcodes")
+    os.makedirs(out_dir, exist_ok=True)
+    rnd = random.Random(7)
+    bcs = [("".join(rnd.choice("ACGT") for _ in range(16)) + "-1").encode() for _ in range(60)]
+    loci = [(1000, "50M100N50M"), (5000, "40M300N60M"), (9000, "30M1000N70M"), (9000, "30M1000N20M500N50M")]
+    reads = []
+    for _ in range(400):
+        pos, cg = rnd.choice(loci)
+        r = rnd.random()
+        if r < 0.05:
+            aux = b"XSA+"
+        else:
+            bc = rnd.choice(bcs[:5 if pos == 1000 else 60])
+            aux = b"XSA+CBZ" + bc + b"\0" if r < 0.9 else b"CBZ" + bc + b"\0XSA-"
+        reads.append((pos, cg, aux))
+    reads.sort(key=lambda x: x[0])
+    recs = [bamio.record(0, p, c, 0, 60, a, name=b"q%04d" % i) for i, (p, c, a) in enumerate(reads)]
+    bam = os.path.join(out_dir, "bc.bam")
+    bamio.write_bam(bam, [("1", 100000)], recs)
+    subprocess.check_call([BAMGEN, "index", bam])
+    p = subprocess.run([REF, "junctions", "extract", "-s", "XS", "-b", os.path.join(out_dir, "bc.barcodes"), "-o",
+                        os.path.join(out_dir, "bc.bed"), bam], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    print(f"wrote the barcode golden to {out_dir}")
+
+
 if __name__ == "__main__":
+    if "--barcodes-only" in sys.argv:
+        build_barcodes()
+        sys.exit(0)
     if not os.path.exists(REF):
         sys.exit("oracle/_ref/regtools_ref missing: run `make -C oracle ref` in the dev container first")
     if "--motif-only" not in sys.argv:
         build()
+        build_barcodes()
     build_motif()

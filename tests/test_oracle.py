@@ -164,3 +164,63 @@ def test_oracle_vs_live_reference_with_fasta_on_fresh_bam(args, tmp_path, motif_
     o = run_oracle(bam, args, fasta=fa)
     assert o.bed12() == p.stdout
     assert len(set(l.split("\t")[5] for l in p.stdout.splitlines())) >= 2
+
+
+def test_barcode_file_order_is_first_seen_insertion_replay():
+    """F10 (`-b`, not built in the product): the reference's barcode file (tests/golden/barcodes, made by the unmodified
+    reference) lists a junction's barcodes in std::unordered_map iteration order after one copy-assignment per read.
+    That order equals inserting the junction's distinct barcodes in FIRST-SEEN order into one map (oracle/bc_replay.cc):
+    checked here by re-deriving candidates and barcodes from the BAM with the test-side BAM reader."""
+    import collections
+    import struct
+    import subprocess
+    import zlib
+    d = os.path.join(GOLD, "barcodes")
+    raw, data, o = open(os.path.join(d, "bc.bam"), "rb").read(), b"", 0
+    while o + 18 <= len(raw):
+        bs = struct.unpack_from("<H", raw, o + 16)[0] + 1
+        data += zlib.decompress(raw[o + 18:o + bs - 8], -15)
+        o += bs
+    l_text = struct.unpack_from("<i", data, 4)[0]
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", data, p)[0]; p += 4
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", data, p)[0]; p += 8 + l_name
+    per = collections.OrderedDict()
+    while p + 4 <= len(data):
+        bl = struct.unpack_from("<i", data, p)[0]
+        tid, pos, l_rn, mapq, bin_, n_cig, flag, l_seq = struct.unpack_from("<iiBBHHHi", data, p + 4)
+        q = p + 36 + l_rn
+        cig = struct.unpack_from(f"<{n_cig}I", data, q); q += 4 * n_cig + (l_seq + 1) // 2 + l_seq
+        aux, strand, bc = data[q:p + 4 + bl], "?", "?"
+        a = 0
+        while a + 3 <= len(aux):                                   # only A and Z tags occur in this fixture
+            tag, ty = aux[a:a + 2], aux[a + 2:a + 3]
+            if ty == b"A":
+                if tag == b"XS": strand = chr(aux[a + 3])
+                a += 4
+            else:
+                e = aux.index(b"\0", a + 3)
+                if tag == b"CB": bc = aux[a + 3:e].decode()
+                a = e + 1
+        cur = pos
+        for w in cig:
+            if w & 0xF == 3:
+                dd = per.setdefault((cur, cur + (w >> 4), strand), collections.OrderedDict())
+                dd[bc] = dd.get(bc, 0) + 1
+            if w & 0xF in (0, 2, 3, 7, 8):
+                cur += w >> 4
+        p += 4 + bl
+    lines = []
+    for f in (l.split("\t") for l in open(os.path.join(d, "bc.bed")).read().splitlines()):
+        left, right = (int(x) for x in f[10].split(","))
+        v = per[(int(f[1]) + left, int(f[2]) - right, f[5])]
+        assert sum(v.values()) == int(f[4])
+        lines.append(" ".join(f"{b} {c}" for b, c in v.items()))
+    oracle_dir = os.path.join(os.path.dirname(os.path.dirname(GOLD)), "oracle")
+    exe = os.path.join(oracle_dir, "_ref", "bc_replay")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", oracle_dir, "-s"])
+    got = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True).stdout
+    assert got == open(os.path.join(d, "bc.barcodes")).read()
+    assert max(len(v) for v in per.values()) > 40                 # several rehashes of the map
