@@ -31,7 +31,7 @@ typedef enum {
     RTJX_E_OPEN_INDEX  = -3,  /* "Unable to open BAM/SAM index. ..."     junctions_extractor.cc:510 */
     RTJX_E_REGION      = -4,  /* "Unable to iterate to region within BAM." junctions_extractor.cc:521 */
     RTJX_E_CUDA        = -5,  /* no device / CUDA runtime failure                                   */
-    RTJX_E_UNSUPPORTED = -6,  /* -b barcodes, CRAM/SAM input, compressed FASTA                      */
+    RTJX_E_UNSUPPORTED = -6,  /* CRAM/SAM input, compressed FASTA, -b combined with shards/regions  */
     RTJX_E_NOMEM       = -7,
     RTJX_E_STATE       = -8,  /* call order violated                                                */
     RTJX_E_IO          = -9   /* also "Unable to extract FASTA sequence ..."  junctions_extractor.cc:553 */
@@ -48,7 +48,9 @@ typedef struct {
     const char* strand_tag;       /* strand_tag_ -t, default "XS" (first two chars used)       */
     const char* fasta;            /* ref_      positional 2: uncompressed FASTA; strand from the
                                      intron motif first, -s only for '?' (junctions_extractor.cc:325-359) */
-    const char* barcode_out;      /* -b: must be NULL (RTJX_E_UNSUPPORTED)                     */
+    const char* barcode_out;      /* output_barcodes_file_ -b: non-NULL switches the handle to the single-cell mode
+                                     (junctions_extractor.cc:203-215,362-374,393-395); the engine does not open the
+                                     path itself, the caller writes it with rtjx_write_barcodes       */
     int32_t     strandness;       /* -s: 0 XS, 1 RF, 2 FR, 3 intron-motif(no FASTA => as FR)   */
     uint32_t    min_anchor;       /* -a, default 8                                             */
     uint32_t    min_intron;       /* -m, default 70                                            */
@@ -66,6 +68,7 @@ typedef struct {
                                      junction table itself (needs rtjx_batch.n_junction_ops)          */
     int32_t     scan_cfg;         /* tile configuration of the variant, 0 = production (A/B knob)     */
     uint32_t    scan_debug;       /* developer switches for A/B timing; results are WRONG if non-zero */
+    const char* barcode_tag;      /* barcode_tag_ (junctions_extractor.h:181), NULL = "CB"; the reference has no flag for it */
 } rtjx_params;
 
 /* One merged junction; same fields as the reference's struct Junction
@@ -165,6 +168,20 @@ int64_t     rtjx_get(rtjx_t* h, rtjx_junction* out, size_t cap);
 /* print_all_junctions (junctions_extractor.cc:249-280): BED12 of the anchor-filtered, sorted
  * junctions to a file descriptor. */
 int         rtjx_write_bed12(rtjx_t* h, int fd);
+/* `-b` single-cell mode (handle created with rtjx_params.barcode_out != NULL; fed by rtjx_run only).
+ * rtjx_write_barcodes = Junction::print_barcodes (junctions_extractor.h:99-111) for every junction that
+ * print_all_junctions prints (junctions_extractor.cc:267-273), in the same order: "<n>\t<bc>:<count>,...\n" with the
+ * barcodes in the iteration order of the reference's std::unordered_map.
+ * rtjx_barcode_stats: distinct values of the barcode tag seen (incl. "?") and the number of n_cigar > 1 alignments
+ * without the tag (= the reference's "WARNING: No CB tag found ..." lines, junctions_extractor.cc:371).
+ * rtjx_barcode_name: dictionary entry `id` (NULL past the end).
+ * rtjx_load_barcodes: host feeder only, like rtjx_load_batch: the per-alignment dictionary ids (0 for n_cigar <= 1) of
+ * the handle's region in iteration order; returns the number of alignments, fills at most cap. */
+int         rtjx_write_barcodes(rtjx_t* h, int fd);
+int         rtjx_barcode_stats(rtjx_t* h, uint64_t* n_barcodes, uint64_t* n_missing);
+const char* rtjx_barcode_name(rtjx_t* h, uint32_t id);
+int64_t     rtjx_load_barcodes(rtjx_t* h, uint32_t* ids, size_t cap);
+
 /* Entries of other shards (disjoint contigs) are appended; names are then ranked by
  * (tid, first_ord), which equals BAM order for a coordinate-sorted file. */
 int         rtjx_import(rtjx_t* h, const rtjx_junction* j, size_t n);

@@ -25,6 +25,8 @@ typedef struct {
     uint32_t start, end, ts, te, count, name_index;
     uint8_t  strand, proxy, l_ok, r_ok;
     int32_t  next; /* hash chain */
+    /* -b: Junction::barcodes (junctions_extractor.h:57-58) as (dictionary id, count) pairs in FIRST-SEEN order */
+    uint32_t* bcs; uint32_t n_bcs, cap_bcs;
 } entry_t;
 
 struct jxo {
@@ -40,6 +42,11 @@ struct jxo {
     /* FASTA (intron-motif strand inference, junctions_extractor.cc:325-359,548-584) */
     int has_fasta, fasta_error;
     int32_t n_seq; char** seq_name; uint8_t** seq; int64_t* seq_len;
+    /* -b single-cell barcodes (junctions_extractor.cc:203-215,362-374) */
+    int bc_on; char bc_tag[2];
+    char** bc_name; uint32_t n_bc, cap_bc;
+    uint32_t cur_bc;                      /* barcode of the alignment being fed (j1.barcodes, one entry) */
+    uint64_t bc_missing;
 };
 
 jxo_t* jxo_new(uint32_t min_anchor, uint32_t min_intron, uint32_t max_intron,
@@ -58,6 +65,9 @@ jxo_t* jxo_new(uint32_t min_anchor, uint32_t min_intron, uint32_t max_intron,
 void jxo_free(jxo_t* o) {
     if (!o) return;
     for (int32_t i = 0; i < o->n_contig; ++i) free(o->contig[i]);
+    for (size_t i = 0; i < o->n; ++i) free(o->e[i].bcs);
+    for (uint32_t i = 0; i < o->n_bc; ++i) free(o->bc_name[i]);
+    free(o->bc_name);
     free(o->contig); free(o->e); free(o->bucket); free(o->cand);
     for (int32_t i = 0; i < o->n_seq; ++i) { free(o->seq_name[i]); free(o->seq[i]); }
     free(o->seq_name); free(o->seq); free(o->seq_len);
@@ -181,6 +191,37 @@ static void rehash(jxo_t* o) {
     }
 }
 
+/* -b mode: what set_junction_barcode (junctions_extractor.cc:362-374) puts into j1.barcodes for one alignment.
+ * The dictionary is a plain array searched linearly (test sizes). */
+void jxo_enable_barcodes(jxo_t* o, const char* tag) {
+    o->bc_on = 1;
+    o->bc_tag[0] = tag && tag[0] ? tag[0] : 'C';
+    o->bc_tag[1] = tag && tag[0] ? tag[1] : 'B';
+}
+void jxo_set_read_barcode(jxo_t* o, const char* bc) {
+    for (uint32_t i = 0; i < o->n_bc; ++i)
+        if (!strcmp(o->bc_name[i], bc)) { o->cur_bc = i; return; }
+    if (o->n_bc == o->cap_bc) {
+        o->cap_bc = o->cap_bc ? o->cap_bc * 2 : 256;
+        o->bc_name = (char**)realloc(o->bc_name, o->cap_bc * sizeof(char*));
+    }
+    o->bc_name[o->n_bc] = strdup(bc);
+    o->cur_bc = o->n_bc++;
+}
+uint64_t jxo_barcodes_missing(const jxo_t* o) { return o->bc_missing; }
+
+/* :203-215 — the stored map is replaced by a copy of itself with this read's barcode counted (found: ++, else insert) */
+static void entry_count_barcode(entry_t* x, uint32_t bc) {
+    for (uint32_t i = 0; i < x->n_bcs; ++i)
+        if (x->bcs[2 * i] == bc) { x->bcs[2 * i + 1] += 1; return; }
+    if (x->n_bcs == x->cap_bcs) {
+        x->cap_bcs = x->cap_bcs ? x->cap_bcs * 2 : 4;
+        x->bcs = (uint32_t*)realloc(x->bcs, 2 * (size_t)x->cap_bcs * sizeof(uint32_t));
+    }
+    x->bcs[2 * x->n_bcs] = bc; x->bcs[2 * x->n_bcs + 1] = 1;
+    x->n_bcs += 1;
+}
+
 /* add_junction = junction_qc + keyed merge.
  * junctions_extractor.cc:160-170 (qc), :174-235 (merge), :152-157 (name = map.size()+1). */
 void jxo_add(jxo_t* o, int32_t tid, uint32_t start, uint32_t end, uint32_t ts, uint32_t te,
@@ -199,6 +240,7 @@ void jxo_add(jxo_t* o, int32_t tid, uint32_t start, uint32_t end, uint32_t ts, u
             if (te > x->te) x->te = te;
             x->l_ok |= l_ok; x->r_ok |= r_ok;                     /* :225-226 */
             x->strand = strand_char;                              /* :229 stored object := new read's copy */
+            if (o->bc_on) entry_count_barcode(x, o->cur_bc);      /* :204-216 */
             return;
         }
     }
@@ -210,6 +252,8 @@ void jxo_add(jxo_t* o, int32_t tid, uint32_t start, uint32_t end, uint32_t ts, u
     x->tid = tid; x->start = start; x->end = end; x->ts = ts; x->te = te;
     x->count = 1; x->name_index = (uint32_t)(o->n + 1);           /* :152-157, :198 */
     x->strand = strand_char; x->proxy = proxy; x->l_ok = l_ok; x->r_ok = r_ok;
+    x->bcs = NULL; x->n_bcs = x->cap_bcs = 0;
+    if (o->bc_on) entry_count_barcode(x, o->cur_bc);              /* new junction: j1.barcodes = {barcode: 1} (:394,:229) */
     x->next = o->bucket[b];
     o->bucket[b] = (int32_t)o->n;
     o->n += 1;
@@ -382,6 +426,26 @@ int jxo_write_bed12(jxo_t* o, FILE* out) {
     }
     free(v);
     return 0;
+}
+
+/* The -b file (print_barcodes, junctions_extractor.h:99-111, for the junctions :267-273 prints, in that order) lists
+ * each junction's unordered_map in libstdc++ iteration order.  That order is a property of the library; the map went
+ * through one copy-assignment per read (copies keep bucket count and node order), so it equals the order of ONE map
+ * filled with the junction's distinct barcodes in first-seen order.  This writes that replay input, one line per printed
+ * junction: "bc count bc count ..."; oracle/bc_replay.cc (real std::unordered_map) turns it into the file's bytes. */
+int jxo_write_barcode_replay_path(jxo_t* o, const char* path) {
+    FILE* f = fopen(path, "w");
+    if (!f) return -1;
+    entry_t* v = sorted_copy(o);
+    for (size_t i = 0; i < o->n; ++i) {
+        const entry_t* x = &v[i];
+        if (!(x->l_ok && x->r_ok)) continue;
+        for (uint32_t k = 0; k < x->n_bcs; ++k)
+            fprintf(f, "%s%s %u", k ? " " : "", o->bc_name[x->bcs[2 * k]], x->bcs[2 * k + 1]);
+        fputc('\n', f);
+    }
+    free(v);
+    return fclose(f);
 }
 
 int jxo_write_bed12_path(jxo_t* o, const char* path) {
@@ -612,7 +676,40 @@ static uint8_t rec_strand_byte(const rec_t* r, const char tag[2]) {
     return 0;
 }
 
+/* bam_aux_get + bam_aux2Z (sam.c:1254-1266,1309-1315) for the barcode tag: 1 and *val = the string, 0 = absent.
+ * A tag of another type makes the reference construct std::string(NULL) and die; the oracle treats it as absent. */
+static int rec_barcode(const rec_t* r, const char tag[2], const char** val) {
+    const uint8_t* s = r->data + r->l_qname + 4 * r->n_cigar + (r->l_qseq + 1) / 2 + r->l_qseq;
+    const uint8_t* e = r->data + r->l_data;
+    while (s + 3 <= e) {
+        int match = s[0] == (uint8_t)tag[0] && s[1] == (uint8_t)tag[1];
+        uint8_t type = s[2];
+        s += 3;
+        if (match) { if (type != 'Z' && type != 'H') return 0; *val = (const char*)s; return 1; }
+        switch (type) {
+        case 'A': case 'c': case 'C': s += 1; break;
+        case 's': case 'S': s += 2; break;
+        case 'i': case 'I': case 'f': s += 4; break;
+        case 'd': s += 8; break;
+        case 'Z': case 'H': while (s < e && *s) ++s; ++s; break;
+        case 'B': {
+            if (s + 5 > e) return 0;
+            uint8_t sub = *s++; uint32_t n; memcpy(&n, s, 4); s += 4;
+            uint32_t sz = (sub == 'c' || sub == 'C' || sub == 'A') ? 1 : (sub == 's' || sub == 'S') ? 2 :
+                          (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : sub == 'd' ? 8 : 0;
+            s += (size_t)sz * n; break; }
+        default: return 0;
+        }
+    }
+    return 0;
+}
+
 static void feed(jxo_t* o, const rec_t* r) {
+    if (o->bc_on && r->n_cigar > 1) {                      /* set_junction_barcode, junctions_extractor.cc:393-395,362-374 */
+        const char* bc = NULL;
+        if (rec_barcode(r, o->bc_tag, &bc)) jxo_set_read_barcode(o, bc);
+        else { jxo_set_read_barcode(o, "?"); o->bc_missing += 1; }
+    }
     uint8_t sb = 0;
     if (o->strandness == 0 && r->n_cigar > 1) sb = rec_strand_byte(r, o->tag);
     jxo_read(o, r->tid >= o->n_contig ? -1 : r->tid, r->pos, r->flag, sb, (const uint32_t*)(r->data + r->l_qname), r->n_cigar);

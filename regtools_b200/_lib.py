@@ -34,6 +34,7 @@ class Params(C.Structure):
         ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
         ("inflate_mode", C.c_int32), ("profile", C.c_int32),
         ("scan_variant", C.c_int32), ("scan_cfg", C.c_int32), ("scan_debug", C.c_uint32),
+        ("barcode_tag", C.c_char_p),
     ]
 
 
@@ -93,6 +94,10 @@ SIGNATURES = {
     "rtjx_count": (C.c_int64, [C.c_void_p]),
     "rtjx_get": (C.c_int64, [C.c_void_p, C.POINTER(Junction), C.c_size_t]),
     "rtjx_write_bed12": (C.c_int, [C.c_void_p, C.c_int]),
+    "rtjx_write_barcodes": (C.c_int, [C.c_void_p, C.c_int]),
+    "rtjx_barcode_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "rtjx_barcode_name": (C.c_char_p, [C.c_void_p, C.c_uint32]),
+    "rtjx_load_barcodes": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "rtjx_import": (C.c_int, [C.c_void_p, C.POINTER(Junction), C.c_size_t]),
     "rtjx_contig": (C.c_char_p, [C.c_void_p, C.c_int32]),
     "rtjx_n_contigs": (C.c_int32, [C.c_void_p]),

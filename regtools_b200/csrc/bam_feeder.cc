@@ -146,6 +146,41 @@ inline uint8_t strand_tag_byte(const uint8_t* s, const uint8_t* e, const char ta
     return 0;
 }
 
+// ---- barcode tag: bam_aux_get + bam_aux2Z (sam.c:1254-1266, 1309-1315) ------------------------------
+// 0 = tag absent, 1 = Z/H value at [*val, *val + *len), 2 = tag present with another type
+inline int barcode_tag_value(const uint8_t* s, const uint8_t* e, const char tag[2], const uint8_t** val, size_t* len) {
+    while (s + 3 <= e) {
+        const bool match = s[0] == (uint8_t)tag[0] && s[1] == (uint8_t)tag[1];
+        const uint8_t type = s[2];
+        s += 3;
+        if (match) {
+            if (type != 'Z' && type != 'H') return 2;
+            const void* z = memchr(s, 0, (size_t)(e - s));
+            *val = s; *len = z ? (size_t)((const uint8_t*)z - s) : (size_t)(e - s);
+            return 1;
+        }
+        switch (type) {
+        case 'A': case 'c': case 'C': s += 1; break;
+        case 's': case 'S': s += 2; break;
+        case 'i': case 'I': case 'f': s += 4; break;
+        case 'd': s += 8; break;
+        case 'Z': case 'H': {
+            const void* z = memchr(s, 0, (size_t)(e - s));
+            if (!z) return 0;
+            s = (const uint8_t*)z + 1; break; }
+        case 'B': {
+            if (s + 5 > e) return 0;
+            uint8_t sub = s[0]; uint32_t n = rd32(s + 1); s += 5;
+            size_t sz = (sub == 'c' || sub == 'C' || sub == 'A') ? 1 : (sub == 's' || sub == 'S') ? 2 :
+                        (sub == 'i' || sub == 'I' || sub == 'f') ? 4 : sub == 'd' ? 8 : 0;
+            if ((size_t)(e - s) < sz * n) return 0;
+            s += sz * n; break; }
+        default: return 0;     // the reference abort()s on an unknown type (sam.c:1246-1247)
+        }
+    }
+    return 0;
+}
+
 // ---- batch writer --------------------------------------------------------------------------------
 class BatchWriter {
 public:
@@ -161,7 +196,7 @@ public:
         const uint32_t l_qname = core[8], mapq = core[9], flag = rd16(core + 14);
         const uint8_t* data = core + 32;
         const uint8_t* cig = data + l_qname;
-        uint32_t strand = 0;
+        uint32_t strand = 0, bc = 0;
         if (n_cigar > 1) {
             if (tid < 0 || tid >= n_ref_) tid = -1;
             uint32_t* dst = b.cigar + b.n_ops;
@@ -173,6 +208,17 @@ public:
                 const uint8_t* aux = cig + 4 * (size_t)n_cigar + ((size_t)l_qseq + 1) / 2 + (size_t)l_qseq;
                 strand = strand_tag_byte(aux, data + l_data, opt_.tag);
             }
+            if (opt_.barcodes) {                               // set_junction_barcode is called for every n_cigar > 1 alignment
+                const int32_t l_qseq = rdi32(core + 16);
+                const uint8_t* aux = cig + 4 * (size_t)n_cigar + ((size_t)l_qseq + 1) / 2 + (size_t)l_qseq;
+                const uint8_t* val = nullptr; size_t len = 0;
+                const int k = barcode_tag_value(aux, data + l_data, opt_.bc_tag, &val, &len);
+                if (k == 1) bc = opt_.barcodes->intern((const char*)val, len);
+                else {
+                    if (k == 0) ++opt_.barcodes->missing; else ++opt_.barcodes->bad_type;
+                    bc = opt_.barcodes->intern("?", 1);
+                }
+            }
         } else if (n_cigar == 1) {
             b.cigar[b.n_ops] = rd32(cig);
         }
@@ -180,6 +226,7 @@ public:
         b.pos[i] = rdi32(core + 4);
         b.meta[i] = flag << 16 | mapq << 8 | strand;
         b.cig_off[i] = b.n_ops;
+        if (opt_.barcodes) b.bc[i] = bc;
         b.n_ops += n_cigar;
         b.n_reads = i + 1;
         ++total_reads_;
@@ -201,6 +248,22 @@ private:
     HostBatch* cur_ = nullptr;
     uint64_t total_reads_ = 0, total_ops_ = 0;
 };
+
+}  // namespace
+struct BarcodeDict::Map { std::unordered_map<std::string, uint32_t> ids; std::string last; uint32_t last_id = 0; bool have_last = false; };
+BarcodeDict::BarcodeDict() : map_(new Map()) {}
+BarcodeDict::~BarcodeDict() { delete map_; }
+void BarcodeDict::clear() { names.clear(); missing = bad_type = 0; map_->ids.clear(); map_->have_last = false; }
+uint32_t BarcodeDict::intern(const char* s, size_t n) {
+    Map& m = *map_;
+    if (m.have_last && m.last.size() == n && memcmp(m.last.data(), s, n) == 0) return m.last_id;
+    m.last.assign(s, n);
+    auto it = m.ids.find(m.last);
+    if (it == m.ids.end()) { it = m.ids.emplace(m.last, (uint32_t)names.size()).first; names.push_back(m.last); }
+    m.last_id = it->second; m.have_last = true;
+    return m.last_id;
+}
+namespace {
 
 // bam_read1's validity checks (sam.c:399-432).  core = 32 bytes after block_size.
 inline bool record_ok(const uint8_t* core, int32_t block_len) {

@@ -55,6 +55,7 @@ struct HostBatch {
     uint32_t* meta = nullptr;
     uint32_t* cig_off = nullptr;   // cap_reads + 1
     uint32_t* cigar = nullptr;
+    uint32_t* bc = nullptr;        // cap_reads; `-b` mode only: barcode dictionary id of every n_cigar > 1 alignment
     uint32_t  cap_reads = 0, cap_ops = 0;
     uint32_t  n_reads = 0, n_ops = 0, n_junction_ops = 0;
     uint64_t  first_ordinal = 0;
@@ -99,10 +100,31 @@ struct BatchSink {
     virtual void submit(HostBatch* b) = 0;            // batch is full (or last)
 };
 
+// `-b` single-cell mode: the value of the barcode tag (barcode_tag_ = "CB", junctions_extractor.h:181,192,204) of every
+// alignment the reference hands to set_junction_barcode (junctions_extractor.cc:362-374,393-395: all alignments with
+// n_cigar > 1), dictionary-encoded in first-seen order.  "?" stands for a missing tag (:370).
+struct BarcodeDict {
+    std::vector<std::string> names;                       // id -> barcode
+    uint64_t missing = 0;                                 // alignments without the tag = WARNING lines of the reference (:371)
+    uint64_t bad_type = 0;                                // tag present but neither Z nor H: bam_aux2Z returns NULL (sam.c:1309-1315)
+                                                          // and the reference dies in std::string(NULL)
+    uint32_t intern(const char* s, size_t n);
+    void clear();
+    BarcodeDict();
+    ~BarcodeDict();
+    BarcodeDict(const BarcodeDict&) = delete;
+    BarcodeDict& operator=(const BarcodeDict&) = delete;
+private:
+    struct Map;
+    Map* map_;
+};
+
 struct FeederOptions {
     int n_threads = 0;            // inflate workers (0 = hardware concurrency)
     bool xs_mode = true;          // scan aux for the strand tag (only for n_cigar > 1)
     char tag[2] = {'X', 'S'};
+    BarcodeDict* barcodes = nullptr;   // non-NULL: `-b` mode, HostBatch::bc is filled
+    char bc_tag[2] = {'C', 'B'};
 };
 
 // Streams every alignment selected by `spec`, in the reference's iteration order, into batches.

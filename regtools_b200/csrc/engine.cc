@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <unordered_map>
 
 namespace rtjx {
 
@@ -41,6 +42,10 @@ Engine::Engine(const rtjx_params& p) : prm_(p) {
     tag_ = (p.strand_tag && p.strand_tag[0]) ? p.strand_tag : "XS";
     if (tag_.size() < 2) tag_.push_back('\0');
     fasta_path_ = p.fasta ? p.fasta : "";
+    bc_mode_ = p.barcode_out != nullptr;                  // output_barcodes_file_ != "NA" (junctions_extractor.cc:204,393)
+    if (p.barcode_tag && p.barcode_tag[0]) bc_tag_ = p.barcode_tag;
+    if (bc_tag_.size() < 2) bc_tag_.push_back('\0');
+    prm_.barcode_tag = nullptr;
     prm_.bam = prm_.region = prm_.strand_tag = prm_.fasta = prm_.barcode_out = nullptr;
     memset(&stats_, 0, sizeof stats_);
 }
@@ -54,11 +59,13 @@ Engine::~Engine() {
         for (auto e : ev_pool_) cudaEventDestroy(e);
         for (auto& d : dev_batch_) {
             cached_dev_free(d.tid); cached_dev_free(d.pos); cached_dev_free(d.meta); cached_dev_free(d.cig_off); cached_dev_free(d.cigar);
+            cached_dev_free(d.bc);
             if (d.free_ev) cudaEventDestroy(d.free_ev);
         }
         cached_dev_free(d_genome_); cached_dev_free(d_g_off_); cached_dev_free(d_g_len_);
         cached_dev_free(d_vr_tid_); cached_dev_free(d_vr_beg_); cached_dev_free(d_vr_end_);
         cached_dev_free(d_out_r_); cached_dev_free(d_ws_r_); cached_host_free(h_final_r_);
+        cached_dev_free(d_fold_table_); cached_dev_free(d_fold_list_); cached_dev_free(d_fold_counters_);
         cached_dev_free(d_counters_); cached_host_free(h_counters_);
         cached_dev_free(d_table_); cached_dev_free(d_spill_); cached_dev_free(d_cands_); cached_dev_free(d_tile_off_); cached_dev_free(d_regions_); cached_dev_free(d_region_cnt_);
         cached_dev_free(d_out_); cached_dev_free(d_ws_); cached_dev_free(d_rank_); cached_host_free(h_final_); cached_dev_free(d_slot_list_);
@@ -79,7 +86,7 @@ ScanParams Engine::scan_params() const {
     s.cfg = prm_.scan_cfg ? prm_.scan_cfg : env_cfg;
     s.genome = d_genome_; s.g_off = d_g_off_; s.g_len = d_g_len_; s.g_n = d_genome_ ? g_n_ : 0u;
     s.vr = vr_;
-    if (d_genome_ || vr_.n) { s.variant = 5; s.cfg = 0; }   // the intron-motif and variant-region modes live in the default scan kernel only
+    if (d_genome_ || vr_.n || bc_mode_) { s.variant = 5; s.cfg = 0; }   // the intron-motif and variant-region modes live in the default scan kernel only
     return s;
 }
 
@@ -105,7 +112,7 @@ int Engine::ensure_device() {
     CK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     CK(cached_dev_malloc(&d_counters_, CTR_COUNT * sizeof(uint32_t)));
     CK(cudaMemset(d_counters_, 0, CTR_COUNT * sizeof(uint32_t)));
-    CK(cached_host_alloc(&h_counters_, CTR_COUNT * sizeof(uint32_t)));
+    CK(cached_host_alloc(&h_counters_, 2 * CTR_COUNT * sizeof(uint32_t)));     // second half: counters of the `-b` fold table
     spill_cap_ = 4096;
     CK(cached_dev_malloc(&d_spill_, spill_cap_ * sizeof(Slot)));
     dev_ready_ = true;
@@ -280,7 +287,7 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
     {
         uint32_t nr = 0, rcap = 0;
         cigar_scan_region_layout(v.n_reads, &nr, &rcap);
-        if (nr) {
+        if (nr && !v.bc) {
             if ((size_t)nr * rcap > regions_cap_ || nr > region_cnt_cap_) {
                 CK(cudaStreamSynchronize(stream));
                 cached_dev_free(d_regions_); cached_dev_free(d_region_cnt_); d_regions_ = nullptr; d_region_cnt_ = nullptr;
@@ -328,6 +335,7 @@ int Engine::ensure_dev_batch(DevBatch& d, uint32_t reads, uint32_t ops) {
         uint32_t cap = std::max(reads, 1u << 12);
         CK(cached_dev_malloc(&d.tid, (size_t)cap * 4)); CK(cached_dev_malloc(&d.pos, (size_t)cap * 4));
         CK(cached_dev_malloc(&d.meta, (size_t)cap * 4)); CK(cached_dev_malloc(&d.cig_off, ((size_t)cap + 4) * 4));
+        if (bc_mode_) { cached_dev_free(d.bc); d.bc = nullptr; CK(cached_dev_malloc(&d.bc, (size_t)cap * 4)); }
         d.cap_reads = cap;
     }
     if (ops > d.cap_ops) {
@@ -343,6 +351,7 @@ int Engine::ensure_dev_batch(DevBatch& d, uint32_t reads, uint32_t ops) {
 int Engine::scan_batch(const rtjx_batch& b, int location, cudaStream_t user_stream) {
     int rc = ensure_device();
     if (rc) return rc;
+    if (bc_mode_) return fail(RTJX_E_UNSUPPORTED, "rtjx_scan_batch carries no barcodes: a -b handle is fed by rtjx_run");
     if (b.n_reads == 0) return RTJX_OK;
     if (!b.tid || !b.pos || !b.meta || !b.cig_off || (b.n_ops && !b.cigar)) return fail(RTJX_E_ARG, "null array in batch");
     cudaStream_t st = user_stream ? user_stream : stream_;
@@ -374,6 +383,7 @@ int Engine::scan_batch(const rtjx_batch& b, int location, cudaStream_t user_stre
 int Engine::add(const rtjx_candidate* c, size_t n) {
     int rc = ensure_device();
     if (rc) return rc;
+    if (bc_mode_) return fail(RTJX_E_UNSUPPORTED, "rtjx_add carries no barcodes: a -b handle is fed by rtjx_run");
     if (n == 0) return RTJX_OK;
     if (!c) return fail(RTJX_E_ARG, "null candidates");
     // add_junction is called once per candidate in order; order is carried by the ordinal.
@@ -416,6 +426,7 @@ struct EngineSink : BatchSink {
                 cached_host_alloc(&b.meta, (size_t)cap_reads * 4) != cudaSuccess ||
                 cached_host_alloc(&b.cig_off, ((size_t)cap_reads + 1) * 4) != cudaSuccess ||
                 cached_host_alloc(&b.cigar, (size_t)cap_ops * 4) != cudaSuccess ||
+                (e->bc_mode_ && cached_host_alloc(&b.bc, (size_t)cap_reads * 4) != cudaSuccess) ||
                 cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) != cudaSuccess)
                 return e->fail(RTJX_E_CUDA, "pinned batch allocation failed");
             b.cap_reads = cap_reads; b.cap_ops = cap_ops;
@@ -427,6 +438,7 @@ struct EngineSink : BatchSink {
             if (in_flight[i]) cudaEventSynchronize(done[i]);
             cached_host_free(hb[i].tid); cached_host_free(hb[i].pos); cached_host_free(hb[i].meta);
             cached_host_free(hb[i].cig_off); cached_host_free(hb[i].cigar);
+            if (hb[i].bc) cached_host_free(hb[i].bc);
             if (done[i]) cudaEventDestroy(done[i]);
         }
     }
@@ -451,6 +463,13 @@ struct EngineSink : BatchSink {
         cudaMemcpyAsync(d.meta, b.meta, (size_t)b.n_reads * 4, cudaMemcpyHostToDevice, cs);
         cudaMemcpyAsync(d.cig_off, b.cig_off, ((size_t)b.n_reads + 1) * 4, cudaMemcpyHostToDevice, cs);
         if (b.n_ops) cudaMemcpyAsync(d.cigar, b.cigar, (size_t)b.n_ops * 4, cudaMemcpyHostToDevice, cs);
+        if (e->bc_mode_) {
+            if (!b.bc || !d.bc) return e->fail(RTJX_E_STATE, "internal: barcode column missing");
+            if (e->bc_dict_.names.size() >= (1u << 24) - 1u)     // the id travels in 24 bits of the candidate
+                return e->fail(RTJX_E_UNSUPPORTED, "more than 16.7 million distinct barcodes");
+            cudaMemcpyAsync(d.bc, b.bc, (size_t)b.n_reads * 4, cudaMemcpyHostToDevice, cs);
+            e->stats_.h2d_bytes += (size_t)b.n_reads * 4;
+        }
         cudaEventRecord(done[j], cs);
         in_flight[j] = true;
         e->stats_.h2d_bytes += (size_t)b.n_reads * 16 + 4 + (size_t)b.n_ops * 4;
@@ -458,6 +477,7 @@ struct EngineSink : BatchSink {
         BatchView v;
         v.n_reads = b.n_reads; v.n_ops = b.n_ops; v.first_ordinal = b.first_ordinal;
         v.tid = d.tid; v.pos = d.pos; v.meta = d.meta; v.cig_off = d.cig_off; v.cigar = d.cigar;
+        v.bc = e->bc_mode_ ? d.bc : nullptr;
         r = e->process_device_batch(v, b.n_junction_ops, ks);
         cudaEventRecord(d.free_ev, ks);
         return r;
@@ -512,7 +532,10 @@ int Engine::run_impl() {
     // Whole-file and contig-shard runs inflate and split records on the GPU (inflate_mode 0 = auto, 2 = force);
     // regions, tiny files and anything the device path declines go through the host feeder below.
     const bool streamable = spec.kind == IterSpec::WholeFile || spec.kind == IterSpec::Contigs;
-    if (streamable && (prm_.inflate_mode == 2 || (prm_.inflate_mode == 0 && bam->size() >= (1u << 20)))) {
+    // `-b`: the barcode strings are dictionary-encoded by the host feeder, so that mode never takes the device feeder
+    if (bc_mode_ && prm_.shard_world > 1) return fail(RTJX_E_UNSUPPORTED, "-b barcodes are not exchanged between contig shards");
+    if (bc_mode_) bc_dict_.clear();
+    if (!bc_mode_ && streamable && (prm_.inflate_mode == 2 || (prm_.inflate_mode == 0 && bam->size() >= (1u << 20)))) {
         const rtjx_stats saved = stats_;
         for (int attempt = 0; attempt < 2; ++attempt) {
             // first with every record start the index knows (linear index + bin chunk boundaries); if that run is declined
@@ -536,6 +559,7 @@ int Engine::run_impl() {
     if ((rc = sink.init())) return rc;
     FeederOptions fo;
     fo.n_threads = prm_.n_threads; fo.xs_mode = prm_.strandness == 0; fo.tag[0] = tag_[0]; fo.tag[1] = tag_[1];
+    if (bc_mode_) { fo.barcodes = &bc_dict_; fo.bc_tag[0] = bc_tag_[0]; fo.bc_tag[1] = bc_tag_[1]; }
     FeederStats fs; std::string err;
     uint64_t reads_before = stats_.reads;
     if (!feed_alignments(*bam, idx, spec, fo, &sink, &fs, &err)) return fail(RTJX_E_REGION, "Unable to iterate to region within BAM.\n\n");
@@ -543,6 +567,8 @@ int Engine::run_impl() {
     CK(cudaStreamSynchronize(copy_stream_));
     CK(cudaStreamSynchronize(stream_));
     (void)reads_before;
+    if (bc_mode_ && bc_dict_.bad_type)      // bam_aux2Z returns NULL (sam.c:1309-1315) and std::string(NULL) ends the reference
+        return fail(RTJX_E_IO, "barcode tag " + bc_tag_.substr(0, 2) + " is present with a non-string type (the reference aborts on such a file)");
     stats_.bgzf_blocks += fs.bgzf_blocks; stats_.compressed_bytes += fs.compressed_bytes; stats_.inflated_bytes += fs.inflated_bytes;
     stats_.host_inflate_s += fs.inflate_s; stats_.host_parse_s += fs.parse_s; stats_.host_wait_s += fs.wait_s;
     stats_.total_s += now_s() - t_start;
@@ -559,6 +585,7 @@ int Engine::run_regions(const char* const* regions, size_t n) {
     if (n && !regions) return fail(RTJX_E_ARG, "null region list");
     if (n >= (1u << 29)) return fail(RTJX_E_ARG, "too many regions");
     if (region_ != ".") return fail(RTJX_E_ARG, "rtjx_run_regions needs a handle created with region \".\"");
+    if (bc_mode_) return fail(RTJX_E_UNSUPPORTED, "rtjx_run_regions has no barcode mode (the 8-arg ctor never sets -b, junctions_extractor.h:199-205)");
     std::unique_ptr<BamFile> bam; BaiIndex idx; IterSpec spec;
     int rc = open_bam(&bam, &idx, &spec);
     if (rc) return rc;
@@ -603,12 +630,7 @@ int Engine::run_regions(const char* const* regions, size_t n) {
     return rc ? rc : rc2;
 }
 
-int Engine::finalize_regions() {
-    cudaStream_t st = stream_;
-    int rc = sync_counters(st);
-    if (rc) return rc;
-    const uint32_t n = d_table_ ? h_counters_[CTR_NUNIQUE] : 0u;
-    if (!n) return RTJX_OK;
+int Engine::ensure_region_buffers(uint32_t n) {
     if (n > fin_r_cap_) {
         CK(cudaDeviceSynchronize());
         cached_dev_free(d_out_r_); cached_dev_free(d_ws_r_); d_out_r_ = nullptr; d_ws_r_ = nullptr;
@@ -624,6 +646,16 @@ int Engine::finalize_regions() {
         CK(cached_host_alloc(&h_final_r_, (size_t)cap * sizeof(OutJunctionR)));
         h_final_r_cap_ = cap;
     }
+    return RTJX_OK;
+}
+
+int Engine::finalize_regions() {
+    cudaStream_t st = stream_;
+    int rc = sync_counters(st);
+    if (rc) return rc;
+    const uint32_t n = d_table_ ? h_counters_[CTR_NUNIQUE] : 0u;
+    if (!n) return RTJX_OK;
+    if ((rc = ensure_region_buffers(n))) return rc;
     if ((rc = ensure_finalize_buffers(1, contigs_.size()))) return rc;     // contig ranks
     if (rank_dirty_) {
         std::vector<uint32_t> cr = contig_ranks(contigs_);
@@ -715,9 +747,12 @@ struct VectorSink : BatchSink {
         hb.tid = tid.data(); hb.pos = pos.data(); hb.meta = meta.data(); hb.cig_off = off.data(); hb.cigar = cig.data();
         hb.cap_reads = reads; hb.cap_ops = ops;
     }
+    std::vector<uint32_t> bcv; std::vector<uint32_t>* obc = nullptr;       // `-b` mode: per-alignment barcode ids
+    void want_barcodes(std::vector<uint32_t>* out) { bcv.resize(hb.cap_reads); hb.bc = bcv.data(); obc = out; }
     HostBatch* acquire() override { return &hb; }
     void submit(HostBatch* b) override {
         uint32_t base = (uint32_t)ocig->size();
+        if (obc) obc->insert(obc->end(), b->bc, b->bc + b->n_reads);
         otid->insert(otid->end(), b->tid, b->tid + b->n_reads);
         opos->insert(opos->end(), b->pos, b->pos + b->n_reads);
         ometa->insert(ometa->end(), b->meta, b->meta + b->n_reads);
@@ -754,6 +789,27 @@ int Engine::load_batch(uint64_t* n_reads, uint64_t* n_ops, int32_t* tid, int32_t
         loaded_.reset();
     }
     return RTJX_OK;
+}
+
+// Host feeder only (no device needed): the barcode dictionary ids of every alignment the handle's region iterates, as the
+// device batches of a -b run carry them; the dictionary stays in the handle (barcode_name / barcode_stats).
+int64_t Engine::load_barcodes(uint32_t* ids, size_t cap) {
+    if (!bc_mode_) return fail(RTJX_E_STATE, "the handle was not created in -b mode (rtjx_params.barcode_out)");
+    std::unique_ptr<BamFile> bam; BaiIndex idx; IterSpec spec;
+    int rc = open_bam(&bam, &idx, &spec);
+    if (rc) return rc;
+    LoadedBatch lb; std::vector<uint32_t> bc;
+    VectorSink sink(1u << 16, 1u << 18);
+    sink.otid = &lb.tid; sink.opos = &lb.pos; sink.ometa = &lb.meta; sink.ooff = &lb.off; sink.ocig = &lb.cigar;
+    sink.want_barcodes(&bc);
+    bc_dict_.clear();
+    FeederOptions fo;
+    fo.n_threads = prm_.n_threads; fo.xs_mode = prm_.strandness == 0; fo.tag[0] = tag_[0]; fo.tag[1] = tag_[1];
+    fo.barcodes = &bc_dict_; fo.bc_tag[0] = bc_tag_[0]; fo.bc_tag[1] = bc_tag_[1];
+    FeederStats fs; std::string err;
+    if (!feed_alignments(*bam, idx, spec, fo, &sink, &fs, &err)) return fail(RTJX_E_REGION, "Unable to iterate to region within BAM.\n\n");
+    if (ids && cap) memcpy(ids, bc.data(), std::min(cap, bc.size()) * sizeof(uint32_t));
+    return (int64_t)bc.size();
 }
 
 // ---- finalize ------------------------------------------------------------------------------------
@@ -897,6 +953,9 @@ int Engine::finalize(cudaStream_t user_stream) {
         int rc = sync_counters(st);
         if (rc) return rc;
         n = h_counters_[CTR_NUNIQUE];
+        TableRef tref = table_ref();
+        bc_pairs_n_ = 0;
+        if (bc_mode_ && n && (rc = fold_barcode_table(n, st, &tref, &n))) return rc;     // n: pairs -> junctions
         if (n) {
             if ((rc = ensure_finalize_buffers(n, contigs_.size()))) return rc;
             std::vector<uint32_t> cr;
@@ -909,7 +968,7 @@ int Engine::finalize(cudaStream_t user_stream) {
             }
             cudaEvent_t ea = nullptr, eb = nullptr;
             if (prm_.profile) { ea = get_event(); eb = get_event(); cudaEventRecord(ea, st); }
-            launch_table_compact(table_ref(), n, d_out_, st);
+            launch_table_compact(tref, n, d_out_, st);
             launch_finalize_sort(d_out_, n, d_rank_, (uint32_t)contigs_.size(), d_ws_, ws_bytes, st);
             if (prm_.profile) cudaEventRecord(eb, st);
             CK(cudaMemcpyAsync(h_final_, d_out_, (size_t)n * sizeof(OutJunction), cudaMemcpyDeviceToHost, st));
@@ -952,6 +1011,7 @@ int Engine::import(const rtjx_junction* j, size_t n) {
 int Engine::clear() {
     const uint64_t known_unique = unique_upper_;      // upper bound of occupied slots
     final_.clear(); pinned_final_n_ = 0; imported_.clear(); import_sizes_.clear(); finalized_ = false; dirty_ = false; unique_upper_ = 0; add_ord_ = 0;
+    bc_pairs_n_ = 0;
     if (dev_ready_) {
         cudaSetDevice(prm_.device);
         if (d_table_) {
@@ -963,6 +1023,113 @@ int Engine::clear() {
         CK(cudaStreamSynchronize(stream_));
     }
     return RTJX_OK;
+}
+
+// ---- `-b` single-cell barcodes ------------------------------------------------------------------------------
+// add_junction keeps an unordered_map<barcode, count> per junction (junctions_extractor.cc:203-215).  Here the device table
+// is keyed (junction, barcode id): count = reads of that barcode, nfirst = first supporting N op.  The junction-level
+// fields (count, thick ends, anchors, first/last ordinals) are associative reductions, so the table add_junction would
+// have built is the fold of the pair table over the barcode bits of the key — done on the device into a second table that
+// the normal compaction / naming / sort then reads.  The pairs travel to the host sorted by (junction, first ordinal).
+int Engine::fold_barcode_table(uint32_t n_pairs, cudaStream_t st, TableRef* folded, uint32_t* n_junctions) {
+    int rc;
+    const uint32_t want = std::max<uint32_t>(next_pow2(2ull * n_pairs), 1u << 16);
+    if (want > fold_slots_) {
+        CK(cudaDeviceSynchronize());
+        cached_dev_free(d_fold_table_); cached_dev_free(d_fold_list_); d_fold_table_ = nullptr; d_fold_list_ = nullptr;
+        CK(cached_dev_malloc(&d_fold_table_, (size_t)want * sizeof(Slot)));
+        CK(cached_dev_malloc(&d_fold_list_, (size_t)want * sizeof(uint32_t)));
+        fold_slots_ = want;
+    }
+    if (!d_fold_counters_) CK(cached_dev_malloc(&d_fold_counters_, CTR_COUNT * sizeof(uint32_t)));
+    if ((rc = ensure_region_buffers(n_pairs))) return rc;
+    const TableRef dst{d_fold_table_, fold_slots_ - 1, d_fold_list_, fold_slots_};
+    CK(cudaMemsetAsync(d_fold_table_, 0, (size_t)fold_slots_ * sizeof(Slot), st));
+    CK(cudaMemsetAsync(d_fold_counters_, 0, CTR_COUNT * sizeof(uint32_t), st));
+    launch_table_fold(table_ref(), n_pairs, dst, d_fold_counters_, st);
+    launch_table_compact_regions(table_ref(), n_pairs, d_out_r_, st);
+    launch_sort_barcode_pairs(d_out_r_, n_pairs, d_ws_r_, ws_r_cap_, st);
+    uint32_t* hc = h_counters_ + CTR_COUNT;
+    CK(cudaMemcpyAsync(hc, d_fold_counters_, CTR_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_final_r_, d_out_r_, (size_t)n_pairs * sizeof(OutJunctionR), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    stats_.kernel_launches += 2; stats_.d2h_bytes += (size_t)n_pairs * sizeof(OutJunctionR) + CTR_COUNT * sizeof(uint32_t);
+    if (hc[CTR_CAND_OVERFLOW] || hc[CTR_NUNIQUE] > n_pairs) return fail(RTJX_E_STATE, "internal: barcode fold table overflowed");
+    bc_pairs_n_ = n_pairs;
+    *folded = dst;
+    *n_junctions = hc[CTR_NUNIQUE];
+    return RTJX_OK;
+}
+
+// print_barcodes (junctions_extractor.h:99-111) for every junction print_all_junctions prints (:267-273), in its order.
+// The line lists an unordered_map in iteration order.  The reference's map went through one copy-assignment per
+// supporting read (:208,:214); a copy keeps bucket count and node order, so its final order is that of ONE map into which
+// the junction's distinct barcodes were inserted in first-seen order — replayed here with the same std::unordered_map.
+int Engine::write_barcodes(int fd) {
+    if (!bc_mode_) return fail(RTJX_E_STATE, "the handle was not created in -b mode (rtjx_params.barcode_out)");
+    int rc = finalize(nullptr);
+    if (rc) return rc;
+    const OutJunctionR* pairs = h_final_r_;
+    const uint32_t np = bc_pairs_n_;
+    auto proxy_of = [](uint8_t c) -> uint32_t { return c == '+' ? 0u : (c == '-' ? 1u : 2u); };
+    auto key_less = [&](const OutJunctionR& a, int32_t tid, uint32_t start, uint32_t end, uint32_t proxy) {
+        if (a.j.tid != tid) return a.j.tid < tid;
+        if (a.j.start != start) return a.j.start < start;
+        if (a.j.end != end) return a.j.end < end;
+        return proxy_of(a.j.strand) < proxy;
+    };
+    std::string out;
+    out.reserve(1u << 20);
+    auto flush = [&]() -> bool {
+        size_t off = 0;
+        while (off < out.size()) {
+            ssize_t w = ::write(fd, out.data() + off, out.size() - off);
+            if (w <= 0) return false;
+            off += (size_t)w;
+        }
+        out.clear();
+        return true;
+    };
+    const rtjx_junction* fin = final_data();
+    for (size_t fi = 0, fn = final_size(); fi < fn; ++fi) {
+        const rtjx_junction& j = fin[fi];
+        if (!(j.left_ok && j.right_ok)) continue;
+        const uint32_t proxy = proxy_of(j.strand);
+        uint32_t lo = 0, hi = np;
+        while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (key_less(pairs[mid], j.tid, j.start, j.end, proxy)) lo = mid + 1; else hi = mid; }
+        std::unordered_map<std::string, int> m;
+        uint64_t total = 0;
+        for (uint32_t k = lo; k < np; ++k) {
+            const OutJunctionR& r = pairs[k];
+            if (r.j.tid != j.tid || r.j.start != j.start || r.j.end != j.end || proxy_of(r.j.strand) != proxy) break;
+            if (r.region == 0 || r.region > bc_dict_.names.size()) return fail(RTJX_E_STATE, "internal: junction without a barcode");
+            m.insert(std::pair<std::string, int>(bc_dict_.names[r.region - 1], (int)r.j.count));
+            total += r.j.count;
+        }
+        if (total != j.read_count) return fail(RTJX_E_STATE, "internal: barcode counts do not add up to the junction's read count");
+        out += std::to_string(m.size());
+        out += '\t';
+        for (std::unordered_map<std::string, int>::const_iterator it = m.begin(); it != m.end(); ++it) {
+            if (it != m.begin()) out += ',';
+            out += it->first; out += ':'; out += std::to_string(it->second);
+        }
+        out += '\n';
+        if (out.size() > (1u << 20) && !flush()) return fail(RTJX_E_IO, "write failed");
+    }
+    if (!flush()) return fail(RTJX_E_IO, "write failed");
+    return RTJX_OK;
+}
+
+int Engine::barcode_stats(uint64_t* n_barcodes, uint64_t* n_missing) {
+    if (!bc_mode_) return fail(RTJX_E_STATE, "the handle was not created in -b mode (rtjx_params.barcode_out)");
+    if (n_barcodes) *n_barcodes = bc_dict_.names.size();
+    if (n_missing) *n_missing = bc_dict_.missing;
+    return RTJX_OK;
+}
+
+const char* Engine::barcode_name(uint32_t id) {
+    return id < bc_dict_.names.size() ? bc_dict_.names[id].c_str() : nullptr;
 }
 
 // ---- BED12 (Junction::print, junctions_extractor.h:90-98; anchor filter junctions_extractor.cc:267)

@@ -31,6 +31,12 @@ public:
     int64_t count();
     int64_t get(rtjx_junction* out, size_t cap);
     int write_bed12(int fd);
+    // `-b` single-cell mode (junctions_extractor.cc:203-215,362-374; print_barcodes junctions_extractor.h:99-111)
+    bool barcode_mode() const { return bc_mode_; }
+    int write_barcodes(int fd);
+    int barcode_stats(uint64_t* n_barcodes, uint64_t* n_missing);
+    const char* barcode_name(uint32_t id);
+    int64_t load_barcodes(uint32_t* ids, size_t cap);          // host feeder only: per-alignment dictionary ids
     int import(const rtjx_junction* j, size_t n);
     int clear();
     int inflate_file(uint64_t max_blocks, void* out, uint64_t cap, uint64_t* out_len);
@@ -99,11 +105,22 @@ private:
     OutJunctionR* d_out_r_ = nullptr; uint32_t fin_r_cap_ = 0; void* d_ws_r_ = nullptr; size_t ws_r_cap_ = 0;
     OutJunctionR* h_final_r_ = nullptr; uint32_t h_final_r_cap_ = 0;
     int finalize_regions();
+    int ensure_region_buffers(uint32_t n);
+
+    // `-b` mode: the device table is keyed (junction, barcode id + 1); finalize folds it into a junction-level table and
+    // keeps the pairs, sorted by (junction, first ordinal), in h_final_r_ for write_barcodes
+    bool bc_mode_ = false;
+    std::string bc_tag_ = "CB";
+    BarcodeDict bc_dict_;
+    Slot* d_fold_table_ = nullptr; uint32_t* d_fold_list_ = nullptr; uint32_t fold_slots_ = 0;
+    uint32_t* d_fold_counters_ = nullptr;
+    uint32_t bc_pairs_n_ = 0;
+    int fold_barcode_table(uint32_t n_pairs, cudaStream_t st, TableRef* folded, uint32_t* n_junctions);
 
     // device batch ring for host-resident input
     struct DevBatch {
         int32_t* tid = nullptr; int32_t* pos = nullptr; uint32_t* meta = nullptr; uint32_t* cig_off = nullptr;
-        uint32_t* cigar = nullptr; uint32_t cap_reads = 0, cap_ops = 0; cudaEvent_t free_ev = nullptr;
+        uint32_t* cigar = nullptr; uint32_t* bc = nullptr; uint32_t cap_reads = 0, cap_ops = 0; cudaEvent_t free_ev = nullptr;
     };
     DevBatch dev_batch_[2];
     int dev_batch_next_ = 0;

@@ -142,6 +142,13 @@ int JunctionsExtractor::add_junction(Junction j1) {
 int JunctionsExtractor::identify_junctions_from_BAM() {
     if (bam_.empty()) return 0;
     check(rtjx_run(handle()));
+    if (output_barcodes_file_ != "NA") {
+        // set_junction_barcode (junctions_extractor.cc:369-372): one line per n_cigar > 1 alignment without the tag;
+        // aln->id is never set by bam_read1 (bam_init1 callocs it), so the reference always prints 0
+        uint64_t n_bc = 0, n_missing = 0;
+        check(rtjx_barcode_stats(handle(), &n_bc, &n_missing));
+        for (uint64_t i = 0; i < n_missing; ++i) cerr << "WARNING: No " << barcode_tag_ << " tag found for alignment (id = 0)" << endl;
+    }
     return 0;
 }
 
@@ -198,8 +205,19 @@ vector<vector<Junction> > JunctionsExtractor::get_all_junctions_in_regions(const
     return out;
 }
 
+// print_barcodes lines of the printed junctions (junctions_extractor.cc:255-257,272-273,278-279)
+void JunctionsExtractor::print_barcodes_file() {
+    if (output_barcodes_file_ == string("NA")) return;
+    int fd = ::open(output_barcodes_file_.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return;        // an ofstream that failed to open swallows the lines
+    int rc = rtjx_write_barcodes(handle(), fd);
+    ::close(fd);
+    check(rc);
+}
+
 void JunctionsExtractor::print_all_junctions(ostream& out) {
     rtjx_t* h = handle();
+    print_barcodes_file();
     if (output_file_ != string("NA")) {
         int fd = ::open(output_file_.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
         if (fd < 0) return;    // the reference's ofstream silently fails too, then prints to `out`... keep quiet

@@ -39,7 +39,7 @@ public:
 #endif
 }  // namespace common
 
-// junctions_extractor.h:39-112 (barcodes map omitted: -b is not built into the B200 path)
+// junctions_extractor.h:39-112 (the barcodes map stays in the engine: rtjx_write_barcodes prints it)
 struct Junction : BED {
     unsigned int read_count;
     CHRPOS thick_start, thick_end;
@@ -105,6 +105,7 @@ public:
 
 private:
     void check(int rc);
+    void print_barcodes_file();                                             // Junction::print_barcodes, .h:99-111
     std::string bam_, ref_;
     uint32_t min_anchor_length_, min_intron_length_, max_intron_length_;
     std::string output_file_, output_barcodes_file_, region_;

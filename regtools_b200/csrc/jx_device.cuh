@@ -81,6 +81,10 @@ struct BatchView {
     const uint32_t* meta;
     const uint32_t* cig_off;
     const uint32_t* cigar;
+    // `-b` single-cell mode (set_junction_barcode, junctions_extractor.cc:362-374): dictionary id of the alignment's barcode
+    // (meaningful for n_cigar > 1 only).  NULL = mode off.  Candidates then carry (id + 1) << 8 in `strand`, exactly where
+    // the variant-region mode puts its region, so the (junction, barcode) pair is the table key.
+    const uint32_t* bc = nullptr;
 };
 
 // Per-tile candidate regions: cigar_scan writes the first round of every tile into a fixed region of
@@ -121,6 +125,13 @@ void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t
 void launch_table_rehash(const Slot* old_table, uint32_t old_slots, const TableRef& tb, uint32_t* d_counters,
                          cudaStream_t stream);
 void launch_table_clear(const TableRef& tb, const uint32_t* d_n_unique, uint32_t n_bound, cudaStream_t stream);
+// `-b` mode: the handle's table is keyed (junction, barcode).  Every field of a slot is an associative reduction (add, max,
+// max, or, max, max), so the junction-level table of add_junction is the fold of the pair table over the barcode bits of the
+// key: the n occupied slots of `src` are upserted into `dst` with khi bits 34.. cleared.  dst_counters: CTR_* of `dst`.
+void launch_table_fold(const TableRef& src, uint32_t n, const TableRef& dst, uint32_t* dst_counters, cudaStream_t stream);
+// (junction, barcode) pairs of a `-b` table, sorted by (tid, start, end, proxy, first_ord): one run per junction, barcodes in
+// first-seen order.  Workspace: finalize_sort_regions_workspace_bytes(n).
+void launch_sort_barcode_pairs(OutJunctionR* entries, uint32_t n, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 void launch_table_compact(const TableRef& tb, uint32_t n, OutJunction* out, cudaStream_t stream);
 // variant-region mode: compaction into OutJunctionR, names ranked per region, sorted by (region, contig, ts, te, name)
 void launch_table_compact_regions(const TableRef& tb, uint32_t n, OutJunctionR* out, cudaStream_t stream);

@@ -614,7 +614,7 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <class Smem, int S5_OUT, bool MOTIF, bool VREG>
+template <class Smem, int S5_OUT, bool MOTIF, bool VREG, bool BC = false>
 struct S5Emit {
     Smem& sm; Cand* __restrict__ out; uint32_t cap; uint32_t* counters; uint32_t dbg;
     const ScanParams* prm; uint32_t* jstrand;                 // intron-motif mode: parameters + the alignment's running strand
@@ -638,8 +638,13 @@ struct S5Emit {
                                                uint64_t ord, int32_t tid, uint32_t strand) const {
         if (MOTIF) {                                           // set_junction_strand with a FASTA (:345-359): motif first
             const uint32_t m = motif_strand(*prm, tid, start, end, *jstrand, counters);
-            if (m != '?') strand = m;
-            *jstrand = strand;
+            if (BC) {                                          // bits 8.. of `strand` carry the barcode id
+                if (m != '?') strand = (strand & ~0xffu) | m;
+                *jstrand = strand & 0xffu;
+            } else {
+                if (m != '?') strand = m;
+                *jstrand = strand;
+            }
         }
         const uint4 a = make_uint4(start, end, start - left, end + right);
         const uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
@@ -662,7 +667,7 @@ struct S5Emit {
     }
 };
 
-template <int S5_THREADS, int S5_SLAB, int S5_OUT, bool MOTIF = false, bool VREG = false>
+template <int S5_THREADS, int S5_SLAB, int S5_OUT, bool MOTIF = false, bool VREG = false, bool BC = false>
 __global__ void __launch_bounds__(S5_THREADS)
 cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters,
                         const uint32_t* __restrict__ tile_off, CandRegions rg) {
@@ -736,7 +741,7 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
     const uint32_t n_work = (prm.debug & 1u) ? 0u : sm.n_work;
     uint32_t jstrand = 0;                                      // j1.strand == "" before an alignment's first junction
     int32_t rspan[2] = {0, 0};
-    const S5Emit<Smem, S5_OUT, MOTIF, VREG> emit{sm, out, cap, counters, prm.debug, &prm, &jstrand, rspan};
+    const S5Emit<Smem, S5_OUT, MOTIF, VREG, BC> emit{sm, out, cap, counters, prm.debug, &prm, &jstrand, rspan};
     auto flush = [&]() {                                        // warp 0
         const uint32_t n_st = (prm.debug & 8u) ? 0u : min(sm.n_out, (uint32_t)S5_OUT);
         __syncwarp();
@@ -760,7 +765,8 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
             const int32_t tid = (int32_t)sm.tid[r];
             if (tid >= 0) {
                 const uint32_t o0 = sm.off[r], n = sm.off[r + 1] - o0;
-                const uint32_t strand = read_strand(sm.meta[r], prm.strandness);
+                uint32_t strand = read_strand(sm.meta[r], prm.strandness);
+                if (BC) strand |= (__ldg(b.bc + base + r) + 1u) << 8;      // set_junction_barcode (:362-374): one barcode per alignment
                 const uint64_t read_ord = b.first_ordinal + base + r;
                 if (MOTIF) jstrand = 0;
                 if (VREG) {                                    // endpos = pos + reference length of the CIGAR (sam.c:327-342)
@@ -821,10 +827,10 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
     const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
                             reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
                             reinterpret_cast<uintptr_t>(b.cigar);
-    const int variant = (p.genome || p.vr.n) ? 5 : ((p.variant == 1 || p.variant == 4) ? p.variant : scan_variant());   // only variant 5 knows the intron-motif and variant-region modes
+    const int variant = (p.genome || p.vr.n || b.bc) ? 5 : ((p.variant == 1 || p.variant == 4) ? p.variant : scan_variant());   // only variant 5 knows the intron-motif and variant-region modes
     if ((align & 15u) == 0 && variant == 5) {
         static int prepass = -1;
-        const int cfg = p.variant == 5 && p.cfg ? p.cfg : scan_cfg();
+        const int cfg = b.bc ? 0 : (p.variant == 5 && p.cfg ? p.cfg : scan_cfg());
         if (prepass < 0) { const char* v = getenv("RTJX_SCAN_PREPASS"); prepass = v ? atoi(v) : 0; }   // measured: no gain on B200
         const uint32_t threads = cfg == 2 ? 64u : cfg == 3 ? 256u : 128u;
         const uint32_t tile = threads * 4, tiles = (b.n_reads + tile - 1) / tile;
@@ -843,7 +849,9 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
         case 6: cigar_scan_small_kernel<128, 2048, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
         case 7: cigar_scan_small_kernel<128, 1536, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
         default:
-            if (p.vr.n && p.genome) cigar_scan_small_kernel<128, 1024, 192, true, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
+            if (b.bc && p.genome) cigar_scan_small_kernel<128, 1024, 192, true, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
+            else if (b.bc) cigar_scan_small_kernel<128, 1024, 192, false, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
+            else if (p.vr.n && p.genome) cigar_scan_small_kernel<128, 1024, 192, true, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
             else if (p.vr.n) cigar_scan_small_kernel<128, 1024, 192, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
             else if (p.genome) cigar_scan_small_kernel<128, 1024, 192, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions);
             else cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions);
@@ -1549,6 +1557,23 @@ void launch_table_rehash(const Slot* old_table, uint32_t old_slots, const TableR
     table_rehash_kernel<<<grid, 256, 0, stream>>>(old_table, old_slots, tb, d_counters);
 }
 
+// `-b` mode: pair table -> junction table (see jx_device.cuh).  Only the occupied slots are visited (slot_list).
+__global__ void __launch_bounds__(256)
+table_fold_kernel(TableRef src, uint32_t n, TableRef dst, uint32_t* __restrict__ dst_counters) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const Slot s = src.slots[src.slot_list[i]];
+        if (s.khi == 0ull) continue;
+        if (!table_upsert(dst, K128{s.klo, s.khi & ((1ull << 34) - 1ull)}, s.count, s.nts, s.te, s.lr, s.nfirst, s.last, dst_counters))
+            atomicExch(&dst_counters[CTR_CAND_OVERFLOW], 2u);
+    }
+}
+
+void launch_table_fold(const TableRef& src, uint32_t n, const TableRef& dst, uint32_t* dst_counters, cudaStream_t stream) {
+    if (n == 0) return;
+    uint32_t grid = min((n + 255u) / 256u, (uint32_t)(8 * num_sms()));
+    table_fold_kernel<<<grid, 256, 0, stream>>>(src, n, dst, dst_counters);
+}
+
 // Zeroes the occupied slots (rtjx_clear); 3 x 16 bytes per slot.
 __global__ void __launch_bounds__(256)
 table_clear_kernel(TableRef tb, const uint32_t* __restrict__ d_n_unique) {
@@ -1677,10 +1702,27 @@ __global__ void fin_assign_names_regions(OutJunctionR* __restrict__ e, uint32_t 
     while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (e[mid].region < rg) lo = mid + 1; else hi = mid; }
     e[i].j.name_index = i - lo + 1u;
 }
+// `-b` mode: runs of one junction key, barcodes in first-seen order (the order the reference inserted them, :203-215)
+struct ByJunctionFirstOrd {
+    __device__ __forceinline__ bool operator()(const OutJunctionR& a, const OutJunctionR& b) const {
+        if (a.j.tid != b.j.tid) return a.j.tid < b.j.tid;
+        if (a.j.start != b.j.start) return a.j.start < b.j.start;
+        if (a.j.end != b.j.end) return a.j.end < b.j.end;
+        const uint32_t pa = a.j.strand == '+' ? 0u : (a.j.strand == '-' ? 1u : 2u), pb = b.j.strand == '+' ? 0u : (b.j.strand == '-' ? 1u : 2u);
+        if (pa != pb) return pa < pb;
+        return a.j.first_ord < b.j.first_ord;
+    }
+};
+void launch_sort_barcode_pairs(OutJunctionR* entries, uint32_t n, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (n == 0) return;
+    cub::DeviceMergeSort::SortKeys(workspace, workspace_bytes, entries, (int)n, ByJunctionFirstOrd(), stream);
+}
 size_t finalize_sort_regions_workspace_bytes(uint32_t n) {
-    size_t a = 0, b = 0;
+    size_t a = 0, b = 0, c = 0;
+    cub::DeviceMergeSort::SortKeys(nullptr, c, (OutJunctionR*)nullptr, (int)n, ByJunctionFirstOrd());
     cub::DeviceMergeSort::SortKeys(nullptr, a, (OutJunctionR*)nullptr, (int)n, ByRegionFirstOrd());
     cub::DeviceMergeSort::SortKeys(nullptr, b, (OutJunctionR*)nullptr, (int)n, ByRegionBedOrder{ByBedOrder{nullptr, 0}});
+    if (c > a) a = c;
     return (a > b ? a : b) + 256;
 }
 void launch_finalize_sort_regions(OutJunctionR* entries, uint32_t n, const uint32_t* contig_rank, uint32_t n_contigs,

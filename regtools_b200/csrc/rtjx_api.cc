@@ -30,7 +30,7 @@ int rtjx_create(const rtjx_params* p, rtjx_t** out) {
     if (!p || !out) return RTJX_E_ARG;
     *out = nullptr;
     if (p->struct_size != sizeof(rtjx_params)) { snprintf(g_create_err, sizeof g_create_err, "rtjx_params.struct_size mismatch"); return RTJX_E_ARG; }
-    if (p->barcode_out) { snprintf(g_create_err, sizeof g_create_err, "single-cell barcode output (-b) is not built into the B200 path"); return RTJX_E_UNSUPPORTED; }
+    if (p->barcode_out && p->shard_world > 1) { snprintf(g_create_err, sizeof g_create_err, "-b barcodes are not exchanged between contig shards"); return RTJX_E_UNSUPPORTED; }
     if (p->strandness < 0 || p->strandness > 3) { snprintf(g_create_err, sizeof g_create_err, "strandness must be 0..3"); return RTJX_E_ARG; }
     if (p->shard_world > 1 && (p->shard_rank < 0 || p->shard_rank >= p->shard_world)) { snprintf(g_create_err, sizeof g_create_err, "shard_rank out of range"); return RTJX_E_ARG; }
     rtjx_handle* h = new (std::nothrow) rtjx_handle;
@@ -69,6 +69,10 @@ int rtjx_finalize(rtjx_t* h, void* stream) { GUARD(h, h->e->finalize(static_cast
 int64_t rtjx_count(rtjx_t* h) { GUARD(h, h->e->count()) }
 int64_t rtjx_get(rtjx_t* h, rtjx_junction* out, size_t cap) { GUARD(h, h->e->get(out, cap)) }
 int rtjx_write_bed12(rtjx_t* h, int fd) { GUARD(h, h->e->write_bed12(fd)) }
+int rtjx_write_barcodes(rtjx_t* h, int fd) { GUARD(h, h->e->write_barcodes(fd)) }
+int rtjx_barcode_stats(rtjx_t* h, uint64_t* n_barcodes, uint64_t* n_missing) { GUARD(h, h->e->barcode_stats(n_barcodes, n_missing)) }
+const char* rtjx_barcode_name(rtjx_t* h, uint32_t id) { return h ? h->e->barcode_name(id) : nullptr; }
+int64_t rtjx_load_barcodes(rtjx_t* h, uint32_t* ids, size_t cap) { GUARD(h, h->e->load_barcodes(ids, cap)) }
 int rtjx_import(rtjx_t* h, const rtjx_junction* j, size_t n) { GUARD(h, h->e->import(j, n)) }
 int rtjx_clear(rtjx_t* h) { GUARD(h, h->e->clear()) }
 

@@ -90,6 +90,7 @@ class JunctionsExtractor:
         self.ref_ = ref
         self.output_file_ = "NA"
         self.output_barcodes_file_ = "NA"
+        self.barcode_tag_ = "CB"                    # junctions_extractor.h:192,204
         self._opts = dict(device=device, n_threads=n_threads, batch_reads=batch_reads, shard_rank=shard_rank,
                           shard_world=shard_world, profile=int(profile), table_log2=table_log2,
                           inflate_mode=inflate_mode, scan_variant=scan_variant, scan_cfg=scan_cfg,
@@ -211,7 +212,59 @@ class JunctionsExtractor:
         if not self.bam_:
             return 0
         self._check(L.lib.rtjx_run(self._handle()))
+        if self.output_barcodes_file_ != "NA":
+            # set_junction_barcode (junctions_extractor.cc:369-372); aln->id is never set, the reference prints 0
+            _, n_missing = self.barcode_stats()
+            for _ in range(n_missing):
+                sys.stderr.write(f"WARNING: No {self.barcode_tag_} tag found for alignment (id = 0)\n")
         return 0
+
+    # ------------------------------------------------------------------ -b single-cell barcodes
+    def barcode_stats(self):
+        """(distinct barcode values seen incl. '?', n_cigar > 1 alignments without the tag)."""
+        nb, nm = C.c_uint64(), C.c_uint64()
+        self._check(L.lib.rtjx_barcode_stats(self._handle(), C.byref(nb), C.byref(nm)))
+        return int(nb.value), int(nm.value)
+
+    def barcode_names(self) -> List[str]:
+        h = self._handle()
+        return [L.lib.rtjx_barcode_name(h, i).decode() for i in range(self.barcode_stats()[0])]
+
+    def load_barcodes(self) -> np.ndarray:
+        """Host feeder only: the barcode dictionary id of every alignment the iterator visits (0 for n_cigar <= 1)."""
+        h = self._handle()
+        n = self._check(L.lib.rtjx_load_barcodes(h, None, 0))
+        ids = np.zeros(n, dtype=np.uint32)
+        if n:
+            self._check(L.lib.rtjx_load_barcodes(h, ids.ctypes.data, n))
+        return ids
+
+    def print_barcodes(self, out=None) -> None:
+        """Junction::print_barcodes (junctions_extractor.h:99-111) for every printed junction, in print order: to the
+        -b file (junctions_extractor.cc:255-257,272-273), or to `out` when given."""
+        h = self._handle()
+        if out is None:
+            fd = os.open(self.output_barcodes_file_, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+            try:
+                self._check(L.lib.rtjx_write_barcodes(h, fd))
+            finally:
+                os.close(fd)
+            return
+        out.write(self._capture(lambda w: L.lib.rtjx_write_barcodes(h, w)))
+
+    def _capture(self, writer) -> str:
+        r, w = os.pipe()
+        import threading
+        chunks = []
+        t = threading.Thread(target=lambda: chunks.append(_read_all(r)))
+        t.start()
+        try:
+            self._check(writer(w))
+        finally:
+            os.close(w)
+            t.join()
+            os.close(r)
+        return b"".join(chunks).decode()
 
     def identify_junctions_in_regions(self, regions: Sequence[str]) -> List[np.ndarray]:
         """Batched form of the per-variant loop of cis-splice-effects (cis_splice_effects_identifier.cc:267-311): the
@@ -269,6 +322,8 @@ class JunctionsExtractor:
     def print_all_junctions(self, out=None) -> None:
         """print_all_junctions (junctions_extractor.cc:249-280): -o file if set, else `out`/stdout."""
         h = self._handle()
+        if self.output_barcodes_file_ != "NA":
+            self.print_barcodes()
         if self.output_file_ != "NA":
             fd = os.open(self.output_file_, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
             try:

@@ -118,6 +118,14 @@ def build_motif():
     print(f"wrote {len(manifest)} intron-motif golden outputs to {out_dir}")
 
 
+BC2_VARIANTS = {
+    "xs": ["-s", "XS"],
+    "xs_a0": ["-s", "XS", "-a", "0"],
+    "rf_m50": ["-s", "RF", "-m", "50"],
+    "fr_region": ["-s", "FR", "-r", "10:1-60000"],
+}
+
+
 def build_barcodes():
     """tests/golden/barcodes/: `-b` single-cell mode of the reference (set_junction_barcode, print_barcodes:
     junctions_extractor.cc:362-374, .h:99-111) on a fixture with CB:Z tags (5 and 60 distinct barcodes per locus, reads
@@ -146,6 +154,16 @@ def build_barcodes():
     p = subprocess.run([REF, "junctions", "extract", "-s", "XS", "-b", os.path.join(out_dir, "bc.barcodes"), "-o",
                         os.path.join(out_dir, "bc.bed"), bam], capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
+    # bc2: the adversarial fixture of tests/bc_fixture.py (3 contigs, a hot junction with hundreds of barcodes, proxy-2
+    # strands, QC- and anchor-filtered junctions, CB behind other tags), several flag sets, all by the unmodified reference
+    import bc_fixture
+    bam2 = bc_fixture.make_barcode_bam(os.path.join(out_dir, "bc2.bam"), seed=11, n_reads=3000)
+    for tag, args in BC2_VARIANTS.items():
+        p = subprocess.run([REF, "junctions", "extract"] + args + ["-b", os.path.join(out_dir, f"bc2.{tag}.barcodes"), "-o",
+                            os.path.join(out_dir, f"bc2.{tag}.bed"), bam2], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        with open(os.path.join(out_dir, f"bc2.{tag}.warnings"), "w") as f:
+            f.write(str(p.stderr.count("WARNING: No CB tag found for alignment (id = 0)")) + "\n")
     print(f"wrote the barcode golden to {out_dir}")
 
 

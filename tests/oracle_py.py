@@ -63,6 +63,11 @@ def lib():
         l.jxo_get.restype = C.c_size_t
         l.jxo_get.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         l.jxo_write_bed12_path.argtypes = [C.c_void_p, C.c_char_p]
+        l.jxo_enable_barcodes.argtypes = [C.c_void_p, C.c_char_p]
+        l.jxo_set_read_barcode.argtypes = [C.c_void_p, C.c_char_p]
+        l.jxo_barcodes_missing.restype = C.c_uint64
+        l.jxo_barcodes_missing.argtypes = [C.c_void_p]
+        l.jxo_write_barcode_replay_path.argtypes = [C.c_void_p, C.c_char_p]
         l.jxo_contig.restype = C.c_char_p
         l.jxo_contig.argtypes = [C.c_void_p, C.c_int32]
         _lib = l
@@ -72,9 +77,12 @@ def lib():
 class Oracle:
     """CPU restatement of JunctionsExtractor (oracle/jx_oracle.c)."""
 
-    def __init__(self, min_anchor=8, min_intron=70, max_intron=500000, strandness=0, tag="XS", contigs=None, fasta=None):
+    def __init__(self, min_anchor=8, min_intron=70, max_intron=500000, strandness=0, tag="XS", contigs=None, fasta=None,
+                 barcodes=False):
         self.l = lib()
         self.h = C.c_void_p(self.l.jxo_new(min_anchor, min_intron, max_intron, strandness, tag.encode()))
+        if barcodes:
+            self.l.jxo_enable_barcodes(self.h, None)
         if contigs is not None:
             self.set_contigs(contigs)
         if fasta is not None and self.l.jxo_set_fasta(self.h, os.fsencode(fasta)):
@@ -137,6 +145,25 @@ class Oracle:
         with tempfile.NamedTemporaryFile(suffix=".bed") as f:
             self.l.jxo_write_bed12_path(self.h, f.name.encode())
             return open(f.name).read()
+
+
+    # -b single-cell mode
+    def set_read_barcode(self, bc):
+        self.l.jxo_set_read_barcode(self.h, bc.encode())
+
+    def barcodes_missing(self):
+        return self.l.jxo_barcodes_missing(self.h)
+
+    def barcodes(self):
+        """Bytes of the reference's -b file: first-seen lists of the printed junctions (C oracle) replayed through a real
+        std::unordered_map (oracle/bc_replay.cc)."""
+        import tempfile
+        exe = os.path.join(ORACLE_DIR, "_ref", "bc_replay")
+        if not os.path.exists(exe):
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+        with tempfile.NamedTemporaryFile(suffix=".replay") as f:
+            self.l.jxo_write_barcode_replay_path(self.h, f.name.encode())
+            return subprocess.run([exe], stdin=open(f.name), capture_output=True, text=True, check=True).stdout
 
 
 def ref_available():

@@ -33,14 +33,36 @@ def test_struct_sizes_match_header():
 
 
 def test_unsupported_modes_are_refused():
+    """-b barcodes are built (single handle); what stays refused is -b combined with contig shards."""
     from regtools_b200 import _lib
-    for field in ("barcode_out",):
-        p = _lib.Params()
-        _lib.lib.rtjx_params_default(C.byref(p))
-        setattr(p, field, b"x")
-        h = C.c_void_p()
-        assert _lib.lib.rtjx_create(C.byref(p), C.byref(h)) == _lib.RTJX_E_UNSUPPORTED
-        assert b"not built" in _lib.lib.rtjx_last_error(None)
+    p = _lib.Params()
+    _lib.lib.rtjx_params_default(C.byref(p))
+    p.barcode_out = b"x"
+    p.shard_world, p.shard_rank = 2, 0
+    h = C.c_void_p()
+    assert _lib.lib.rtjx_create(C.byref(p), C.byref(h)) == _lib.RTJX_E_UNSUPPORTED
+    assert b"shards" in _lib.lib.rtjx_last_error(None)
+    # a plain handle has no barcode table
+    p = _lib.Params()
+    _lib.lib.rtjx_params_default(C.byref(p))
+    p.device = -1
+    assert _lib.lib.rtjx_create(C.byref(p), C.byref(h)) == 0
+    assert _lib.lib.rtjx_write_barcodes(h, 1) == _lib.RTJX_E_STATE
+    assert _lib.lib.rtjx_barcode_stats(h, None, None) == _lib.RTJX_E_STATE
+    _lib.lib.rtjx_destroy(h)
+
+
+def test_barcode_mode_without_gpu_fails_loudly():
+    """-b has no CPU path either: the feeder's dictionary is host work, the tables are not."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import regtools_b200 as rt
+    ex = rt.JunctionsExtractor(os.path.join(ROOT, "tests", "golden", "barcodes", "bc.bam"), ".", 0)
+    ex.output_barcodes_file_ = os.devnull
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ex.identify_junctions_from_BAM()
+    ex.close()
 
 
 def test_compute_without_gpu_fails_loudly():

@@ -299,3 +299,74 @@ def test_csi_takes_precedence_over_bai(tmp_path):
     ex = rt().JunctionsExtractor(src, "1:5000-6200", 0, device=-1)
     assert len(ex.load_batch()[0]) > 0
     ex.close()
+
+
+# ---- `-b` single-cell mode: the host feeder's barcode column ---------------------------------------------------------
+def _py_barcodes(bam):
+    """Independent walk of the BAM (zlib + struct): per alignment (n_cigar, first CB:Z value or None)."""
+    import struct
+    import zlib
+    raw, data, o = open(bam, "rb").read(), b"", 0
+    while o + 18 <= len(raw):
+        bs = struct.unpack_from("<H", raw, o + 16)[0] + 1
+        data += zlib.decompress(raw[o + 18:o + bs - 8], -15)
+        o += bs
+    p = 8 + struct.unpack_from("<i", data, 4)[0]
+    n_ref = struct.unpack_from("<i", data, p)[0]; p += 4
+    for _ in range(n_ref):
+        p += 8 + struct.unpack_from("<i", data, p)[0]
+    size = {b"A": 1, b"c": 1, b"C": 1, b"s": 2, b"S": 2, b"i": 4, b"I": 4, b"f": 4, b"d": 8}
+    out = []
+    while p + 4 <= len(data):
+        bl = struct.unpack_from("<i", data, p)[0]
+        _tid, _pos, l_rn, _mq, _bin, n_cig, _flag, l_seq = struct.unpack_from("<iiBBHHHi", data, p + 4)
+        a = p + 36 + l_rn + 4 * n_cig + (l_seq + 1) // 2 + l_seq
+        e, bc = p + 4 + bl, None
+        while a + 3 <= e:
+            tag, ty = data[a:a + 2], data[a + 2:a + 3]
+            a += 3
+            if ty in (b"Z", b"H"):
+                z = data.index(b"\0", a)
+                if tag == b"CB":
+                    bc = data[a:z].decode(); break
+                a = z + 1
+            elif ty == b"B":
+                sub, n = data[a:a + 1], struct.unpack_from("<I", data, a + 1)[0]
+                a += 5 + size[sub] * n
+            else:
+                if tag == b"CB":
+                    break
+                a += size[ty]
+        out.append((n_cig, bc))
+        p += 4 + bl
+    return out
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_feeder_barcode_column(threads, tmp_path):
+    """rtjx_load_barcodes (host only): every n_cigar > 1 alignment carries the dictionary id of its first CB:Z value, "?"
+    when the tag is absent (set_junction_barcode, junctions_extractor.cc:362-374); ids are first-seen ranks."""
+    import bc_fixture
+    import regtools_b200 as rt
+    for bam in (os.path.join(ROOT, "tests", "golden", "barcodes", "bc2.bam"),
+                bc_fixture.make_barcode_bam(str(tmp_path / "f.bam"), seed=5, n_reads=1500, missing=0.2)):
+        ex = rt.JunctionsExtractor(bam, ".", 0, device=-1, n_threads=threads, batch_reads=1024)
+        ex.output_barcodes_file_ = os.devnull
+        ids = ex.load_barcodes()
+        names = ex.barcode_names()
+        n_bc, n_missing = ex.barcode_stats()
+        ex.close()
+        want = _py_barcodes(bam)
+        assert len(ids) == len(want) and n_bc == len(names) == len(set(names))
+        seen, missing = [], 0
+        for i, (n_cig, bc) in enumerate(want):
+            if n_cig <= 1:
+                assert ids[i] == 0
+                continue
+            if bc is None:
+                missing += 1
+                bc = "?"
+            if bc not in seen:
+                seen.append(bc)
+            assert names[ids[i]] == bc, i
+        assert names == seen and n_missing == missing and missing > 0

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import synth
-from oracle_py import Oracle, ref_available, ref_extract
+from oracle_py import REF_BIN, Oracle, ref_available, ref_extract
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 HCC = os.path.join(GOLD, "hcc1395", "test_hcc1395.bam")
@@ -224,3 +224,55 @@ def test_barcode_file_order_is_first_seen_insertion_replay():
     got = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True).stdout
     assert got == open(os.path.join(d, "bc.barcodes")).read()
     assert max(len(v) for v in per.values()) > 40                 # several rehashes of the map
+
+
+# ---- `-b` single-cell barcodes: the C oracle (+ bc_replay for the unordered_map order) against the reference ----------
+BC2 = {"xs": ["-s", "XS"], "xs_a0": ["-s", "XS", "-a", "0"], "rf_m50": ["-s", "RF", "-m", "50"],
+       "fr_region": ["-s", "FR", "-r", "10:1-60000"]}
+
+
+def _bc_oracle(bam, args):
+    from oracle_py import Oracle
+    kw = dict(a=8, m=70, s=0, r=".")
+    it = iter(args)
+    for k in it:
+        v = next(it)
+        kw[k[1]] = {"XS": 0, "RF": 1, "FR": 2}[v] if k == "-s" else (v if k == "-r" else int(v))
+    o = Oracle(kw["a"], kw["m"], 500000, kw["s"], barcodes=True)
+    o.extract_bam(bam, kw["r"])
+    return o
+
+
+def test_barcode_oracle_matches_reference_goldens():
+    """tests/golden/barcodes was written by the UNMODIFIED reference (make_golden.py --barcodes-only): BED12, the -b file
+    and the number of `WARNING: No CB tag` lines must come out of the oracle byte for byte."""
+    d = os.path.join(GOLD, "barcodes")
+    o = _bc_oracle(os.path.join(d, "bc.bam"), ["-s", "XS"])
+    assert o.bed12() == open(os.path.join(d, "bc.bed")).read()
+    assert o.barcodes() == open(os.path.join(d, "bc.barcodes")).read()
+    for tag, args in BC2.items():
+        o = _bc_oracle(os.path.join(d, "bc2.bam"), args)
+        assert o.bed12() == open(os.path.join(d, f"bc2.{tag}.bed")).read(), tag
+        want = open(os.path.join(d, f"bc2.{tag}.barcodes")).read()
+        assert o.barcodes() == want, tag
+        assert o.barcodes_missing() == int(open(os.path.join(d, f"bc2.{tag}.warnings")).read()), tag
+        assert len(want.splitlines()) == len(o.bed12().splitlines())
+    big = max(int(l.split("\t")[0]) for l in open(os.path.join(d, "bc2.xs.barcodes")))
+    assert big >= 150                                             # the hot junction: many rehashes of the reference's map
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs oracle/_ref/regtools_ref (dev container)")
+@pytest.mark.parametrize("seed", [21, 22])
+def test_barcode_oracle_live_differential(seed, tmp_path):
+    """Fresh seeded fixtures through the unmodified reference and the oracle: -b file, BED12, warning count."""
+    import subprocess
+    import bc_fixture
+    bam = bc_fixture.make_barcode_bam(str(tmp_path / "bc.bam"), seed=seed, n_reads=2500, n_barcodes=700, hot_barcodes=600)
+    for args in (["-s", "XS"], ["-s", "FR", "-a", "3", "-m", "60"], ["-s", "XS", "-r", "2"]):
+        p = subprocess.run([REF_BIN, "junctions", "extract"] + args + ["-b", str(tmp_path / "r.bc"), "-o", str(tmp_path / "r.bed"), bam],
+                           capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        o = _bc_oracle(bam, args)
+        assert o.bed12() == open(tmp_path / "r.bed").read()
+        assert o.barcodes() == open(tmp_path / "r.bc").read()
+        assert o.barcodes_missing() == p.stderr.count("WARNING: No CB tag found for alignment (id = 0)")
