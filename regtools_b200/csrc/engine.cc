@@ -223,6 +223,9 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
     if (sp.genome && ((reinterpret_cast<uintptr_t>(v.tid) | reinterpret_cast<uintptr_t>(v.pos) | reinterpret_cast<uintptr_t>(v.meta) |
                        reinterpret_cast<uintptr_t>(v.cig_off) | reinterpret_cast<uintptr_t>(v.cigar)) & 15u))
         return fail(RTJX_E_ARG, "device batch arrays must be 16-byte aligned when a FASTA is given");
+    if (v.bc && ((reinterpret_cast<uintptr_t>(v.tid) | reinterpret_cast<uintptr_t>(v.pos) | reinterpret_cast<uintptr_t>(v.meta) |
+                  reinterpret_cast<uintptr_t>(v.cig_off) | reinterpret_cast<uintptr_t>(v.cigar)) & 15u))
+        return fail(RTJX_E_STATE, "internal: -b batches must be 16-byte aligned (only the tiled scan kernel knows barcodes)");
     if (sp.variant == 6 && known && ((reinterpret_cast<uintptr_t>(v.tid) | reinterpret_cast<uintptr_t>(v.pos) |
                                       reinterpret_cast<uintptr_t>(v.meta) | reinterpret_cast<uintptr_t>(v.cig_off) |
                                       reinterpret_cast<uintptr_t>(v.cigar)) & 15u) == 0) {
@@ -534,7 +537,6 @@ int Engine::run_impl() {
     const bool streamable = spec.kind == IterSpec::WholeFile || spec.kind == IterSpec::Contigs;
     // `-b`: the barcode strings are dictionary-encoded by the host feeder, so that mode never takes the device feeder
     if (bc_mode_ && prm_.shard_world > 1) return fail(RTJX_E_UNSUPPORTED, "-b barcodes are not exchanged between contig shards");
-    if (bc_mode_) bc_dict_.clear();
     if (!bc_mode_ && streamable && (prm_.inflate_mode == 2 || (prm_.inflate_mode == 0 && bam->size() >= (1u << 20)))) {
         const rtjx_stats saved = stats_;
         for (int attempt = 0; attempt < 2; ++attempt) {
@@ -795,6 +797,7 @@ int Engine::load_batch(uint64_t* n_reads, uint64_t* n_ops, int32_t* tid, int32_t
 // device batches of a -b run carry them; the dictionary stays in the handle (barcode_name / barcode_stats).
 int64_t Engine::load_barcodes(uint32_t* ids, size_t cap) {
     if (!bc_mode_) return fail(RTJX_E_STATE, "the handle was not created in -b mode (rtjx_params.barcode_out)");
+    if (dirty_ || finalized_) return fail(RTJX_E_STATE, "rtjx_load_barcodes rebuilds the dictionary: use a fresh or cleared handle");
     std::unique_ptr<BamFile> bam; BaiIndex idx; IterSpec spec;
     int rc = open_bam(&bam, &idx, &spec);
     if (rc) return rc;
@@ -1012,6 +1015,7 @@ int Engine::clear() {
     const uint64_t known_unique = unique_upper_;      // upper bound of occupied slots
     final_.clear(); pinned_final_n_ = 0; imported_.clear(); import_sizes_.clear(); finalized_ = false; dirty_ = false; unique_upper_ = 0; add_ord_ = 0;
     bc_pairs_n_ = 0;
+    bc_dict_.clear();                                  // the ids live in the table keys: both go together
     if (dev_ready_) {
         cudaSetDevice(prm_.device);
         if (d_table_) {
