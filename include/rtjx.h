@@ -210,6 +210,29 @@ int         rtjx_load_batch(rtjx_t* h, uint64_t* n_reads, uint64_t* n_ops, int32
  * Test hook for the inflate kernel (replaces bgzf.c:292-316 for whole-file runs). */
 int         rtjx_inflate_file(rtjx_t* h, uint64_t max_blocks, void* out, uint64_t cap, uint64_t* out_len);
 
+/* ---- `regtools junctions annotate` (the downstream consumer of the BED12) -------------------------
+ * One call = junctions_annotate (src/junctions/junctions_main.cc:61-92): load the GTF (gtf_parser.cc), read the BED12
+ * junctions (BedFile), and for every line adjust_junction_ends + get_splice_site + annotate_junction_with_gtf
+ * (junctions_annotator.cc:66-81,94-114,367-388 -> overlap_ps/overlap_ns :128-311) + AnnotatedJunction::print
+ * (junctions_annotator.h:86-121).  The per-junction work runs on the device (one thread per junction over flat GTF
+ * arrays and the genome in HBM); parsing and the TSV text are host work.  Header + one line per junction go to out_fd.
+ * Errors keep the reference's order: a GTF problem fails before anything is written; a junction on a contig the FASTA
+ * lacks ("Unable to extract FASTA sequence for position ...", RTJX_E_IO) or a line that is not BED12 ends the run after
+ * the lines before it were written.  err (optional) receives the message. */
+typedef struct {
+    uint32_t    struct_size;          /* = sizeof(rtjx_annotate_params), set by rtjx_annotate_params_default        */
+    const char* junctions_bed;        /* junctions_.bedFile   positional 1                                          */
+    const char* fasta;                /* ref_                 positional 2 (uncompressed FASTA)                     */
+    const char* gtf;                  /* gtf_                 positional 3                                          */
+    int32_t     include_single_exon;  /* -S: skip_single_exon_genes_ = false (junctions_annotator.cc:411-413)       */
+    int32_t     device;               /* CUDA ordinal                                                               */
+    int32_t     chatter_fd;           /* >= 0: the reference's stderr lines ("position = ...", "Annotated N lines.") */
+    const char* out_path;             /* output_file_ -o: used when out_fd < 0; opened only after the GTF and the junctions
+                                         file were read, as set_ofstream_object is (junctions_main.cc:68-71)          */
+} rtjx_annotate_params;
+void        rtjx_annotate_params_default(rtjx_annotate_params* p);
+int         rtjx_annotate(const rtjx_annotate_params* p, int out_fd, uint64_t* n_lines, char* err, size_t err_cap);
+
 const char* rtjx_last_error(const rtjx_t* h);
 const char* rtjx_strerror(int status);
 const char* rtjx_version(void);

@@ -6,8 +6,8 @@ the reference's JunctionsExtractor interface.  Importing this package loads the 
 raises if it has not been built — there is no fallback implementation.
 """
 from . import _lib  # noqa: F401  (raises ImportError when libregtools_jx.so is missing)
-from .extractor import (CmdlineHelpException, Junction, JunctionsExtractor, JUNCTION_DTYPE,  # noqa: F401
-                        junctions_extract, plan_shards)
+from .extractor import (CmdlineHelpException, Junction, JunctionsAnnotator, JunctionsExtractor, JUNCTION_DTYPE,  # noqa: F401
+                        junctions_annotate, junctions_extract, plan_shards)
 
-__all__ = ["JunctionsExtractor", "Junction", "CmdlineHelpException", "junctions_extract", "plan_shards",
-           "JUNCTION_DTYPE"]
+__all__ = ["JunctionsExtractor", "JunctionsAnnotator", "Junction", "CmdlineHelpException", "junctions_extract",
+           "junctions_annotate", "plan_shards", "JUNCTION_DTYPE"]

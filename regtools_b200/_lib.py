@@ -65,6 +65,15 @@ class Batch(C.Structure):
     ]
 
 
+class AnnotateParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("junctions_bed", C.c_char_p), ("fasta", C.c_char_p), ("gtf", C.c_char_p),
+        ("include_single_exon", C.c_int32), ("device", C.c_int32), ("chatter_fd", C.c_int32),
+        ("out_path", C.c_char_p),
+    ]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("reads", C.c_uint64), ("cigar_ops", C.c_uint64), ("candidates", C.c_uint64),
@@ -109,6 +118,8 @@ SIGNATURES = {
     "rtjx_load_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rtjx_inflate_file": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "rtjx_annotate_params_default": (None, [C.POINTER(AnnotateParams)]),
+    "rtjx_annotate": (C.c_int, [C.POINTER(AnnotateParams), C.c_int, C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]),
     "rtjx_last_error": (C.c_char_p, [C.c_void_p]),
     "rtjx_strerror": (C.c_char_p, [C.c_int]),
     "rtjx_version": (C.c_char_p, []),

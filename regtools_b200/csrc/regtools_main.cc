@@ -1,12 +1,13 @@
 // regtools_b200/csrc/regtools_main.cc — the `regtools` CLI front-end of the B200 path.
 //
 // Same dispatch, banner and exit codes as /root/reference/src/regtools.cc:36-74 and
-// src/junctions/junctions_main.cc:45-59,96-107.  Only `junctions extract` is built here; the
-// other sub-commands are outside the hot path and say so.
+// src/junctions/junctions_main.cc:45-107.  `junctions extract` (the hot path) and `junctions annotate` (its downstream
+// consumer) are built here; the other sub-commands are outside the scope and say so.
 #include <cstring>
 #include <iostream>
 #include <string>
 
+#include "junctions_annotator.h"
 #include "junctions_extractor.h"
 
 using namespace std;
@@ -53,6 +54,22 @@ static int junctions_extract(int argc, char* argv[]) {
     return 0;
 }
 
+static int junctions_annotate(int argc, char* argv[]) {       // junctions_main.cc:61-92
+    JunctionsAnnotator anno;
+    if (const char* d = getenv("RTJX_DEVICE")) anno.set_device(atoi(d));
+    try {
+        anno.parse_options(argc, argv);
+        anno.annotate_all();                                 // prints "Annotated N lines." itself (chatter_fd)
+    } catch (const common::cmdline_help_exception& e) {
+        cerr << e.what() << endl;
+        return 0;
+    } catch (const runtime_error& e) {
+        cerr << e.what() << endl;
+        return 1;
+    }
+    return 0;
+}
+
 static int not_built(const char* what) {
     cerr << "regtools (B200 build): '" << what << "' is outside the junctions-extract hot path and is not built here." << endl;
     return 1;
@@ -66,7 +83,7 @@ int main(int argc, char* argv[]) {
             if (argc > 2) {
                 string sub2(argv[2]);
                 if (sub2 == "extract") return junctions_extract(argc - 2, argv + 2);
-                if (sub2 == "annotate") return not_built("junctions annotate");
+                if (sub2 == "annotate") return junctions_annotate(argc - 2, argv + 2);
             }
             return junctions_usage();
         }

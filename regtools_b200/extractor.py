@@ -462,6 +462,94 @@ def plan_shards(bam: str, world: int) -> List[int]:
     return list(arr[:n])
 
 
+ANNOTATE_USAGE = ("Usage:\t\tregtools junctions annotate [options] junctions.bed ref.fa annotations.gtf\n"
+                  "Options:\t-S include single exon genes\n"
+                  "\t\t-o FILE\tThe file to write output to. [STDOUT]\n\n")
+
+
+class JunctionsAnnotator:
+    """`regtools junctions annotate` over the C ABI (rtjx_annotate): the options and texts of the reference's
+    JunctionsAnnotator (junctions_annotator.cc:405-456); the per-line loop of junctions_main.cc:68-82 runs batched on the
+    device."""
+
+    def __init__(self, junctions: str = "", ref: str = "NA", gtf: str = "", *, device: int = 0):
+        self.junctions_, self.ref_, self.gtf_ = junctions, ref, gtf
+        self.skip_single_exon_genes_ = True
+        self.output_file_ = "NA"
+        self.device_ = device
+
+    def usage(self, out=None) -> int:
+        (out or sys.stderr).write(ANNOTATE_USAGE)
+        return 0
+
+    def parse_options(self, argv: Sequence[str]) -> int:
+        """argv[0] is the sub-command name, as in the reference's getopt call."""
+        try:
+            opts, args = getopt.getopt(list(argv[1:]), "So:h")
+        except getopt.GetoptError:
+            self.usage()
+            raise RuntimeError("Error parsing inputs!(1)\n\n")
+        for o, a in opts:
+            if o == "-S":
+                self.skip_single_exon_genes_ = False
+            elif o == "-o":
+                self.output_file_ = a
+            elif o == "-h":
+                raise CmdlineHelpException(ANNOTATE_USAGE)
+        if len(args) >= 3:
+            self.junctions_, self.ref_, self.gtf_ = args[0], args[1], args[2]
+            args = args[3:]
+        if args or self.ref_ == "NA" or not self.junctions_ or not self.gtf_:
+            self.usage()
+            raise RuntimeError("Error parsing inputs!(2)\n\n")
+        e = sys.stderr
+        e.write(f"Reference: {self.ref_}\nGTF: {self.gtf_}\nJunctions: {self.junctions_}\n")
+        if self.skip_single_exon_genes_:
+            e.write("Skipping single exon genes.\n")
+        if self.output_file_ != "NA":
+            e.write(f"Output file: {self.output_file_}\n")
+        e.write("\n")
+        return 0
+
+    def annotate_all(self, out_fd: Optional[int] = None, chatter_fd: int = -1) -> int:
+        """Header + one line per junction to -o / out_fd / stdout; returns the number of annotated lines."""
+        p = L.AnnotateParams()
+        L.lib.rtjx_annotate_params_default(C.byref(p))
+        p.junctions_bed, p.fasta, p.gtf = os.fsencode(self.junctions_), os.fsencode(self.ref_), os.fsencode(self.gtf_)
+        p.include_single_exon = 0 if self.skip_single_exon_genes_ else 1
+        p.device = self.device_
+        p.chatter_fd = chatter_fd
+        fd = out_fd
+        if fd is None:
+            if self.output_file_ != "NA":
+                fd, p.out_path = -1, os.fsencode(self.output_file_)
+            else:
+                sys.stdout.flush()
+                fd = 1
+        err = C.create_string_buffer(1024)
+        n = C.c_uint64()
+        rc = L.lib.rtjx_annotate(C.byref(p), fd, C.byref(n), err, len(err))
+        if rc != L.RTJX_OK:
+            raise RuntimeError(err.value.decode() or L.lib.rtjx_strerror(rc).decode())
+        return int(n.value)
+
+
+def junctions_annotate(argv: Sequence[str], device: int = 0) -> int:
+    """junctions_annotate (src/junctions/junctions_main.cc:61-92): exit code 0 / 1."""
+    anno = JunctionsAnnotator(device=device)
+    try:
+        anno.parse_options(argv)
+        sys.stderr.flush()
+        anno.annotate_all(chatter_fd=2)
+    except CmdlineHelpException as e:
+        sys.stderr.write(str(e) + "\n")
+        return 0
+    except RuntimeError as e:
+        sys.stderr.write(str(e) + "\n")
+        return 1
+    return 0
+
+
 def junctions_extract(argv: Sequence[str]) -> int:
     """junctions_extract (src/junctions/junctions_main.cc:45-59): exit code 0 / 1."""
     ex = JunctionsExtractor()

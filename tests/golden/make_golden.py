@@ -167,7 +167,41 @@ def build_barcodes():
     print(f"wrote the barcode golden to {out_dir}")
 
 
+REF_ANN = os.path.join(ROOT, "oracle", "_ref", "regtools_ref_annotate")
+ANN_CASES = {"s1": dict(seed=1), "s2": dict(seed=2, header=True), "s3": dict(seed=3, crlf=True)}
+
+
+def build_annotate():
+    """tests/golden/annotate/: `junctions annotate`.  hcc1395.* = the reference's own integration-test
+    inputs and expected output (tests/integration-test/data/{bed,fa,gtf,junctions-annotate}); s<N>.* = generated cases
+    (tests/ann_fixture.py) annotated by the UNMODIFIED reference (oracle/_ref/regtools_ref_annotate), with and without -S.
+    The FASTA of the generated cases is rebuilt by ann_fixture.write_fasta (explicit LCG), not committed."""
+    import shutil
+    import ann_fixture
+    out_dir = os.path.join(HERE, "annotate")
+    os.makedirs(out_dir, exist_ok=True)
+    d = "/root/reference/tests/integration-test/data"
+    for src, dst in (("bed/test_hcc1395_junctions.bed", "hcc1395.bed"), ("fa/test_chr22.fa", "hcc1395.fa"),
+                     ("gtf/test_ensemble_chr22.gtf", "hcc1395.gtf"), ("junctions-annotate/expected-annotate.out", "hcc1395.expected.tsv")):
+        shutil.copyfile(os.path.join(d, src), os.path.join(out_dir, dst))
+        os.chmod(os.path.join(out_dir, dst), 0o644)
+    fa = ann_fixture.write_fasta(os.path.join("/tmp", "ann_golden_ref.fa"))
+    for tag, kw in ANN_CASES.items():
+        tmp = os.path.join("/tmp", "ann_golden_" + tag)
+        bed, _, gtf = ann_fixture.make_annotation_case(tmp, **kw)
+        shutil.copyfile(bed, os.path.join(out_dir, tag + ".bed"))
+        shutil.copyfile(gtf, os.path.join(out_dir, tag + ".gtf"))
+        for flag, suffix in (([], ""), (["-S"], ".S")):
+            p = subprocess.run([REF_ANN, "junctions", "annotate"] + flag + ["-o", os.path.join(out_dir, f"{tag}{suffix}.expected.tsv"), bed, fa, gtf],
+                               capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr
+    print(f"wrote the annotate goldens to {out_dir}")
+
+
 if __name__ == "__main__":
+    if "--annotate-only" in sys.argv:
+        build_annotate()
+        sys.exit(0)
     if "--barcodes-only" in sys.argv:
         build_barcodes()
         sys.exit(0)
@@ -176,4 +210,5 @@ if __name__ == "__main__":
     if "--motif-only" not in sys.argv:
         build()
         build_barcodes()
+        build_annotate()
     build_motif()
