@@ -29,10 +29,10 @@ def write_fasta(path, contigs=CONTIGS, seed=7, width=70):
     return path
 
 
-def _gene_models(rnd):
+def _gene_models(rnd, contigs=None):
     """-> list of transcripts: dict(id, gene_name, gene_id, chrom, strand, exons=[(start, end)] ascending, 1-based inclusive)"""
     txs, tcount = [], 0
-    for chrom, length in CONTIGS[:3]:
+    for chrom, length in (contigs or CONTIGS)[:-1]:                             # the last contig carries no genes
         pos, g = 2000, 0
         while pos < length - 60000:
             g += 1
@@ -84,7 +84,8 @@ def write_gtf(path, txs, rnd):
     return path
 
 
-def write_bed(path, txs, rnd, header=False, crlf=False):
+def write_bed(path, txs, rnd, header=False, crlf=False, contigs=None):
+    contigs = contigs or CONTIGS
     rows, n = [], 0
 
     def add(chrom, e_end, next_start, strand):
@@ -121,10 +122,11 @@ def write_bed(path, txs, rnd, header=False, crlf=False):
         if rnd.random() < 0.3:
             add(c, max(1, ex[0][0] - rnd.randrange(200, 50000)), ex[0][0], st)       # ends at the first exon's start
     for _ in range(40):
-        c, ln = rnd.choice(CONTIGS)
+        c, ln = rnd.choice(contigs)
         a = rnd.randrange(100, ln - 2000)
         add(c, a, a + rnd.randrange(80, 1500), rnd.choice("+-"))                     # intergenic / contig without genes
-    add("2", 299990, 300400, "+")                                                    # past the end of the FASTA sequence (clipped)
+    if contigs is CONTIGS:
+        add("2", 299990, 300400, "+")                                                # past the end of the FASTA sequence (clipped)
     rnd.shuffle(rows)
     eol = "\r\n" if crlf else "\n"
     with open(path, "w", newline="") as f:
@@ -135,13 +137,33 @@ def write_bed(path, txs, rnd, header=False, crlf=False):
     return path
 
 
-def make_annotation_case(d, seed, header=False, crlf=False):
+def make_annotation_case(d, seed, header=False, crlf=False, contigs=None, fasta=True):
+    """contigs: [(name, length)], the last one without genes; default = the small CONTIGS the goldens were made with."""
     os.makedirs(d, exist_ok=True)
     rnd = random.Random(seed)
-    txs = _gene_models(rnd)
+    txs = _gene_models(rnd, contigs)
     gtf = write_gtf(os.path.join(d, "ann.gtf"), txs, rnd)
-    bed = write_bed(os.path.join(d, "junctions.bed"), txs, rnd, header=header, crlf=crlf)
+    bed = write_bed(os.path.join(d, "junctions.bed"), txs, rnd, header=header, crlf=crlf, contigs=contigs)
     fa = os.path.join(d, "ref.fa")
-    if not os.path.exists(fa):
-        write_fasta(fa)
+    if fasta and not os.path.exists(fa):
+        write_fasta(fa, contigs or CONTIGS)
     return bed, fa, gtf
+
+
+def write_fasta_numpy(path, contigs, seed=7, width=70):
+    """Large genomes (bench): numpy instead of the per-base LCG; not byte-compatible with write_fasta."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    alphabet = np.frombuffer(b"ACGTACGTACGTACGTACGTACGTACGTacgtN", dtype=np.uint8)
+    with open(path, "wb") as f:
+        for name, n in contigs:
+            f.write(b">" + name.encode() + b" generated\n")
+            full = (n // width) * width
+            s = alphabet[rng.integers(0, len(alphabet), n)]
+            body = np.empty((full // width, width + 1), dtype=np.uint8)
+            body[:, :width] = s[:full].reshape(-1, width)
+            body[:, width] = 10
+            f.write(body.tobytes())
+            if n > full:
+                f.write(s[full:].tobytes() + b"\n")
+    return path
