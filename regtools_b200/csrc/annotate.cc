@@ -12,6 +12,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -127,44 +129,84 @@ Status load_gtf(const std::string& path, GtfFlat* out) {
 }
 
 // ---- BED12 junctions (BedFile::GetHeader / GetNextBed / parseLine, adjust_junction_ends :66-81) ---------------
+// The file is read into one buffer and tokenised in place (tabs become NULs); the text columns the writer needs stay as
+// views into that buffer.  Same rules as the reference's getline-based Tokenize: consecutive tabs give empty fields, a
+// trailing tab gives none, an empty line gives no field at all.
+struct Tok { const char* p; uint32_t n; };
 struct JunctionLines {
-    std::vector<std::string> chrom, name, score, strand;
+    std::string buf;                                                          // the whole file
+    std::vector<Tok> chrom, name, score, strand;
     std::vector<uint32_t> start, end;                                         // adjusted
     Status stop;                                                              // why reading stopped early (error after the lines above)
 };
 
-bool is_integer(const std::string& s) {
-    if (s.empty()) return false;
+bool is_integer(const char* s) {                                              // s is NUL-terminated
+    if (!*s) return false;
     char* e = nullptr;
-    strtol(s.c_str(), &e, 10);
+    strtol(s, &e, 10);
     return *e == '\0';
 }
-bool is_header(const std::string& s) { return s.find("#") == 0 || s.find("browser") == 0 || s.find("track") == 0; }
+bool is_header(const char* s, size_t n) {
+    return (n >= 1 && s[0] == '#') || (n >= 7 && memcmp(s, "browser", 7) == 0) || (n >= 5 && memcmp(s, "track", 5) == 0);
+}
 
 Status read_junctions(const std::string& path, JunctionLines* out) {
-    std::ifstream f(path.c_str());
-    if (!f.is_open()) return fail(RTJX_E_IO, "Error: The requested file (" + path + ") could not be opened. Exiting!");
-    std::string line;
+    {
+        FILE* f = fopen(path.c_str(), "rb");
+        if (!f) return fail(RTJX_E_IO, "Error: The requested file (" + path + ") could not be opened. Exiting!");
+        char chunk[1 << 16];
+        size_t got;
+        while ((got = fread(chunk, 1, sizeof chunk, f)) > 0) out->buf.append(chunk, got);
+        fclose(f);
+    }
+    std::string& b = out->buf;
+    b.push_back('\n');                                                        // sentinel: every line ends in the buffer
+    const size_t total = b.size() - 1;
+    {
+        size_t lines = 0;
+        for (size_t k = 0; k < total; ++k) lines += b[k] == '\n';
+        out->chrom.reserve(lines + 1); out->name.reserve(lines + 1); out->score.reserve(lines + 1); out->strand.reserve(lines + 1);
+        out->start.reserve(lines + 1); out->end.reserve(lines + 1);
+    }
     bool header = true;
     size_t n_fields0 = 0;
-    while (std::getline(f, line)) {
-        if (header && is_header(line)) continue;                              // GetHeader
+    Tok fld[16];
+    for (size_t pos = 0; pos < total;) {
+        char* line = &b[pos];
+        char* nl = static_cast<char*>(memchr(line, '\n', b.size() - pos));
+        size_t len = (size_t)(nl - line);
+        pos += len + 1;
+        if (header && is_header(line, len)) continue;                         // GetHeader
         header = false;
-        if (!line.empty() && line[line.size() - 1] == '\r') line.resize(line.size() - 1);
-        const std::vector<std::string> fld = split(line, '\t');
-        if (fld.empty() || is_header(fld[0])) break;                          // BED_BLANK / BED_HEADER end get_single_junction's loop
-        if (fld.size() < 3) { out->stop = fail(RTJX_E_IO, "It looks as though you have less than 3 columns. Are you sure your files are tab-delimited?"); break; }
-        if (!is_integer(fld[1]) || !is_integer(fld[2])) { out->stop = fail(RTJX_E_IO, "Unexpected file format.  Please use tab-delimited BED, GFF, or VCF."); break; }
-        if (!n_fields0) n_fields0 = fld.size();
-        if (fld.size() != n_fields0) { out->stop = fail(RTJX_E_IO, "Differing number of BED fields encountered. Exiting..."); break; }
-        uint32_t start = (uint32_t)atoi(fld[1].c_str()), end = (uint32_t)atoi(fld[2].c_str());
-        if (fld.size() != 12 || fld[10].empty()) {                            // :70-75
-            out->stop = fail(RTJX_E_IO, "BED line not in BED12 format. start: " + fld[0] + ":" + std::to_string(start));
+        if (len && line[len - 1] == '\r') --len;
+        line[len] = '\0';
+        size_t nf = 0;                                                        // number of fields (all counted, 16 kept)
+        if (len) {
+            char* q = line;
+            for (;;) {
+                char* t = static_cast<char*>(memchr(q, '\t', (size_t)(line + len - q)));
+                char* e = t ? t : line + len;
+                if (!t && e == q) break;                                      // the line ended with a tab: no trailing empty field
+                if (nf < 16) fld[nf] = Tok{q, (uint32_t)(e - q)};
+                ++nf;
+                *e = '\0';
+                if (!t) break;
+                q = t + 1;
+            }
+        }
+        if (nf == 0 || is_header(fld[0].p, fld[0].n)) break;                  // BED_BLANK / BED_HEADER end get_single_junction's loop
+        if (nf < 3) { out->stop = fail(RTJX_E_IO, "It looks as though you have less than 3 columns. Are you sure your files are tab-delimited?"); break; }
+        if (!is_integer(fld[1].p) || !is_integer(fld[2].p)) { out->stop = fail(RTJX_E_IO, "Unexpected file format.  Please use tab-delimited BED, GFF, or VCF."); break; }
+        if (!n_fields0) n_fields0 = nf;
+        if (nf != n_fields0) { out->stop = fail(RTJX_E_IO, "Differing number of BED fields encountered. Exiting..."); break; }
+        uint32_t start = (uint32_t)atoi(fld[1].p), end = (uint32_t)atoi(fld[2].p);
+        if (nf != 12 || fld[10].n == 0) {                                     // :70-75
+            out->stop = fail(RTJX_E_IO, "BED line not in BED12 format. start: " + std::string(fld[0].p, fld[0].n) + ":" + std::to_string(start));
             break;
         }
-        const std::vector<std::string> bs = split(fld[10], ',');
-        start += (uint32_t)atoi(bs[0].c_str());
-        end -= (uint32_t)(atoi(bs.size() > 1 ? bs[1].c_str() : "0") - 1);
+        const char* comma = static_cast<const char*>(memchr(fld[10].p, ',', fld[10].n));      // Tokenize(blocksize_field, ints, ',')
+        start += (uint32_t)atoi(fld[10].p);                                   // atoi stops at the comma
+        end -= (uint32_t)(((comma && comma[1]) ? atoi(comma + 1) : 0) - 1);
         out->chrom.push_back(fld[0]); out->name.push_back(fld[3]); out->score.push_back(fld[4]); out->strand.push_back(fld[5]);
         out->start.push_back(start); out->end.push_back(end);
     }
@@ -202,15 +244,22 @@ bool write_all(int fd, const std::string& s) {
         if (e__ != cudaSuccess) return fail(RTJX_E_CUDA, std::string(#call " failed: ") + cudaGetErrorString(e__)); \
     } while (0)
 
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 Status annotate_impl(const rtjx_annotate_params& p, int out_fd, uint64_t* n_lines) {
     if (!p.junctions_bed || !p.fasta || !p.gtf) return fail(RTJX_E_ARG, "Error parsing inputs!(2)\n\n");
+    const bool trace = getenv("RTJX_TRACE") != nullptr;                       // stage timings on stderr
+    double t_prev = now_s();
+    auto lap = [&](const char* what) { if (trace) { const double t = now_s(); fprintf(stderr, "[rtjx annotate] %-22s %8.2f ms\n", what, (t - t_prev) * 1e3); t_prev = t; } };
     // junctions_main.cc:68-72: options, GTF, junctions file, then the output stream and the header
     GtfFlat gtf;
     Status st = load_gtf(p.gtf, &gtf);
     if (!st.ok()) return st;
+    lap("gtf load");
     JunctionLines jl;
     if (!(st = read_junctions(p.junctions_bed, &jl)).ok()) return st;
     const size_t n = jl.start.size();
+    lap("junctions read");
 
     // the annotation itself runs on the device only
     int n_dev = 0;
@@ -237,22 +286,30 @@ Status annotate_impl(const rtjx_annotate_params& p, int out_fd, uint64_t* n_line
         FastaGenome genome;
         std::string ferr;
         const bool have_fasta = load_fasta(p.fasta, &genome, &ferr);
+        lap("fasta load");
         std::map<std::string, int32_t> cdict;
         std::vector<int32_t> c_gtf, j_chrom(n);
         std::vector<unsigned long long> c_goff, c_glen;
         std::vector<uint8_t> j_strand(n);
+        Tok last{nullptr, 0}; int32_t last_id = -1;                             // a BED is usually sorted: one lookup per run of a chrom
         for (size_t i = 0; i < n; ++i) {
-            std::map<std::string, int32_t>::iterator it = cdict.find(jl.chrom[i]);
-            if (it == cdict.end()) {
-                it = cdict.insert(std::make_pair(jl.chrom[i], (int32_t)cdict.size())).first;
-                std::map<std::string, uint32_t>::const_iterator g = gtf.chrom_id.find(jl.chrom[i]);
-                c_gtf.push_back(g == gtf.chrom_id.end() ? -1 : (int32_t)g->second);
-                const int q = have_fasta ? genome.find(jl.chrom[i]) : -1;
-                c_goff.push_back(q >= 0 ? genome.offset[(size_t)q] : 0ull);
-                c_glen.push_back(q >= 0 ? genome.length[(size_t)q] : ~0ull);
+            const Tok c = jl.chrom[i];
+            if (!(last.p && last.n == c.n && memcmp(last.p, c.p, c.n) == 0)) {
+                const std::string name(c.p, c.n);
+                std::map<std::string, int32_t>::iterator it = cdict.find(name);
+                if (it == cdict.end()) {
+                    it = cdict.insert(std::make_pair(name, (int32_t)cdict.size())).first;
+                    std::map<std::string, uint32_t>::const_iterator g = gtf.chrom_id.find(name);
+                    c_gtf.push_back(g == gtf.chrom_id.end() ? -1 : (int32_t)g->second);
+                    const int q = have_fasta ? genome.find(name) : -1;
+                    c_goff.push_back(q >= 0 ? genome.offset[(size_t)q] : 0ull);
+                    c_glen.push_back(q >= 0 ? genome.length[(size_t)q] : ~0ull);
+                }
+                last = c; last_id = it->second;
             }
-            j_chrom[i] = it->second;
-            j_strand[i] = jl.strand[i] == "+" ? 0 : (jl.strand[i] == "-" ? 1 : 2);
+            j_chrom[i] = last_id;
+            const Tok st = jl.strand[i];
+            j_strand[i] = (st.n == 1 && st.p[0] == '+') ? 0 : ((st.n == 1 && st.p[0] == '-') ? 1 : 2);
         }
         cudaStream_t stream = nullptr;
         ACK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -278,6 +335,7 @@ Status annotate_impl(const rtjx_annotate_params& p, int out_fd, uint64_t* n_line
         jv.c_gtf = d_cgtf.as<int32_t>(); jv.c_goff = d_cgoff.as<unsigned long long>(); jv.c_glen = d_cglen.as<unsigned long long>();
         jv.genome = d_genome.as<uint8_t>();
 
+        lap("upload");
         unsigned long long cap = 16ull * n + (1ull << 16);
         if (const char* v = getenv("RTJX_ANNOTATE_ITEMS")) cap = strtoull(v, nullptr, 10);     // tests: force the grow-and-rerun path
         uint32_t ctr[ANN_CTR_COUNT];
@@ -299,57 +357,76 @@ Status annotate_impl(const rtjx_annotate_params& p, int out_fd, uint64_t* n_line
         ACK(cudaMemcpyAsync(res.data(), d_out.p, n * sizeof(AnnOut), cudaMemcpyDeviceToHost, stream));
         if (used) ACK(cudaMemcpyAsync(items.data(), d_items.p, (size_t)used * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         ACK(cudaStreamSynchronize(stream));
+        lap("kernel + download");
     }
 
     // ---- AnnotatedJunction::print (junctions_annotator.h:86-121), in file order; errors surface where the reference throws
-    std::string out;
-    out.reserve(1u << 20);
-    out += HEADER;
-    std::string chatter;
+    // genes_overlap is a set<vector<string>>: (gene_name, gene_id) pairs in lexicographic order -> rank every transcript's pair once
+    std::vector<std::pair<std::string, std::string> > gene_pairs;
+    std::vector<uint32_t> gene_rank(gtf.tx_id.size());
+    {
+        std::map<std::pair<std::string, std::string>, uint32_t> rank;
+        for (size_t t = 0; t < gtf.tx_id.size(); ++t) rank[std::make_pair(gtf.gene_name[t], gtf.gene_id[t])] = 0;
+        uint32_t r = 0;
+        for (std::map<std::pair<std::string, std::string>, uint32_t>::iterator it = rank.begin(); it != rank.end(); ++it) { it->second = r++; gene_pairs.push_back(it->first); }
+        for (size_t t = 0; t < gtf.tx_id.size(); ++t) gene_rank[t] = rank[std::make_pair(gtf.gene_name[t], gtf.gene_id[t])];
+    }
+    struct TextBuf {
+        std::string s;
+        void u32(uint32_t v) { char t[10]; int k = 0; do { t[k++] = (char)('0' + v % 10); v /= 10; } while (v); while (k) s.push_back(t[--k]); }
+        void tok(const Tok& t) { s.append(t.p, t.n); }
+        void position(const Tok& chrom, uint32_t a, uint32_t b) { tok(chrom); s.push_back(':'); u32(a); s.push_back('-'); u32(b); }
+    } out, chatter;
+    out.s.reserve((1u << 20) + 4096);
+    out.s += HEADER;
+    const bool chat = p.chatter_fd >= 0;
     uint64_t printed = 0;
     Status result;
+    std::vector<uint32_t> ranks;
     for (size_t i = 0; i < n; ++i) {
         const AnnOut& r = res[i];
-        const std::string p1 = jl.chrom[i] + ":" + std::to_string(jl.start[i] + 1u) + "-" + std::to_string(jl.start[i] + 2u);
-        if (p.chatter_fd >= 0) chatter += "position = " + p1 + "\n";
+        if (chat) { chatter.s += "position = "; chatter.position(jl.chrom[i], jl.start[i] + 1u, jl.start[i] + 2u); chatter.s.push_back('\n'); }
         if (r.flags & ANN_NO_CONTIG) {                                         // get_reference_sequence :391-402
-            result = fail(RTJX_E_IO, "Unable to extract FASTA sequence for position " + p1 + "\n\n");
+            TextBuf p1;
+            p1.position(jl.chrom[i], jl.start[i] + 1u, jl.start[i] + 2u);
+            result = fail(RTJX_E_IO, "Unable to extract FASTA sequence for position " + p1.s + "\n\n");
             break;
         }
-        if (p.chatter_fd >= 0)
-            chatter += "position = " + jl.chrom[i] + ":" + std::to_string(jl.end[i] - 2u) + "-" + std::to_string(jl.end[i] - 1u) + "\n";
-        out += jl.chrom[i]; out += '\t'; out += std::to_string(jl.start[i]); out += '\t'; out += std::to_string(jl.end[i]); out += '\t';
-        out += jl.name[i]; out += '\t'; out += jl.score[i]; out += '\t'; out += jl.strand[i]; out += '\t';
-        out.append(reinterpret_cast<const char*>(r.ss), r.ss_n[0]); out += '-'; out.append(reinterpret_cast<const char*>(r.ss + 3), r.ss_n[1]);
-        out += '\t'; out += std::to_string(r.n_acceptors); out += '\t'; out += std::to_string(r.n_exons); out += '\t'; out += std::to_string(r.n_donors);
+        if (chat) { chatter.s += "position = "; chatter.position(jl.chrom[i], jl.end[i] - 2u, jl.end[i] - 1u); chatter.s.push_back('\n'); }
+        std::string& o = out.s;
+        out.tok(jl.chrom[i]); o.push_back('\t'); out.u32(jl.start[i]); o.push_back('\t'); out.u32(jl.end[i]); o.push_back('\t');
+        out.tok(jl.name[i]); o.push_back('\t'); out.tok(jl.score[i]); o.push_back('\t'); out.tok(jl.strand[i]); o.push_back('\t');
+        o.append(reinterpret_cast<const char*>(r.ss), r.ss_n[0]); o.push_back('-'); o.append(reinterpret_cast<const char*>(r.ss + 3), r.ss_n[1]);
+        o.push_back('\t'); out.u32(r.n_acceptors); o.push_back('\t'); out.u32(r.n_exons); o.push_back('\t'); out.u32(r.n_donors);
         const bool kd = r.flags & ANN_KNOWN_DONOR, ka = r.flags & ANN_KNOWN_ACCEPTOR, kj = r.flags & ANN_KNOWN_JUNCTION;
-        out += '\t'; out += kj ? "DA" : (kd ? (ka ? "NDA" : "D") : (ka ? "A" : "N"));                  // annotate_anchor :314-328
-        out += '\t'; out += kd ? '1' : '0'; out += '\t'; out += ka ? '1' : '0'; out += '\t'; out += kj ? '1' : '0';
+        o.push_back('\t'); o += kj ? "DA" : (kd ? (ka ? "NDA" : "D") : (ka ? "A" : "N"));               // annotate_anchor :314-328
+        o.push_back('\t'); o.push_back(kd ? '1' : '0'); o.push_back('\t'); o.push_back(ka ? '1' : '0'); o.push_back('\t'); o.push_back(kj ? '1' : '0');
         if (r.n_tx) {
             const unsigned long long off = (unsigned long long)r.tx_off_hi << 32 | r.tx_off_lo;
-            std::set<std::pair<std::string, std::string> > genes;              // set<vector<string>>: (gene_name, gene_id) lexicographic
-            for (uint32_t k = 0; k < r.n_tx; ++k) {
-                const size_t t = (size_t)items[(size_t)off + k];
-                genes.insert(std::make_pair(gtf.gene_name[t], gtf.gene_id[t]));
-            }
-            out += '\t';
-            for (std::set<std::pair<std::string, std::string> >::iterator it = genes.begin(); it != genes.end(); ++it) { if (it != genes.begin()) out += ','; out += it->first; }
-            out += '\t';
-            for (std::set<std::pair<std::string, std::string> >::iterator it = genes.begin(); it != genes.end(); ++it) { if (it != genes.begin()) out += ','; out += it->second; }
-            out += '\t';
-            for (uint32_t k = 0; k < r.n_tx; ++k) { if (k) out += ','; out += gtf.tx_id[(size_t)items[(size_t)off + k]]; }
+            ranks.clear();
+            for (uint32_t k = 0; k < r.n_tx; ++k) ranks.push_back(gene_rank[(size_t)items[(size_t)off + k]]);
+            std::sort(ranks.begin(), ranks.end());
+            ranks.erase(std::unique(ranks.begin(), ranks.end()), ranks.end());
+            o.push_back('\t');
+            for (size_t k = 0; k < ranks.size(); ++k) { if (k) o.push_back(','); o += gene_pairs[ranks[k]].first; }
+            o.push_back('\t');
+            for (size_t k = 0; k < ranks.size(); ++k) { if (k) o.push_back(','); o += gene_pairs[ranks[k]].second; }
+            o.push_back('\t');
+            for (uint32_t k = 0; k < r.n_tx; ++k) { if (k) o.push_back(','); o += gtf.tx_id[(size_t)items[(size_t)off + k]]; }
         } else {
-            out += "\tNA\tNA\tNA";
+            o += "\tNA\tNA\tNA";
         }
-        out += '\n';
+        o.push_back('\n');
         ++printed;
-        if (out.size() > (1u << 20)) { if (!write_all(out_fd, out)) return fail(RTJX_E_IO, "write failed"); out.clear(); }
+        if (o.size() > (1u << 20)) { if (!write_all(out_fd, o)) return fail(RTJX_E_IO, "write failed"); o.clear(); }
+        if (chatter.s.size() > (1u << 20)) { write_all(p.chatter_fd, chatter.s); chatter.s.clear(); }
     }
-    if (!write_all(out_fd, out)) return fail(RTJX_E_IO, "write failed");
+    if (!write_all(out_fd, out.s)) return fail(RTJX_E_IO, "write failed");
+    lap("format + write");
     if (result.ok() && !jl.stop.ok()) result = jl.stop;                        // a malformed BED line ends the run after the lines before it
-    if (p.chatter_fd >= 0) {
-        if (result.ok()) chatter += "\nAnnotated " + std::to_string(printed) + " lines.\n";
-        write_all(p.chatter_fd, chatter);
+    if (chat) {
+        if (result.ok()) chatter.s += "\nAnnotated " + std::to_string(printed) + " lines.\n";
+        write_all(p.chatter_fd, chatter.s);
     }
     if (n_lines) *n_lines = printed;
     return result;
