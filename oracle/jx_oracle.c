@@ -45,6 +45,7 @@ struct jxo {
     /* -b single-cell barcodes (junctions_extractor.cc:203-215,362-374) */
     int bc_on; char bc_tag[2];
     char** bc_name; uint32_t n_bc, cap_bc;
+    int32_t* bc_hash; uint32_t n_bc_hash;  /* open addressing over bc_name (FNV-1a), -1 = empty */
     uint32_t cur_bc;                      /* barcode of the alignment being fed (j1.barcodes, one entry) */
     uint64_t bc_missing;
 };
@@ -67,7 +68,7 @@ void jxo_free(jxo_t* o) {
     for (int32_t i = 0; i < o->n_contig; ++i) free(o->contig[i]);
     for (size_t i = 0; i < o->n; ++i) free(o->e[i].bcs);
     for (uint32_t i = 0; i < o->n_bc; ++i) free(o->bc_name[i]);
-    free(o->bc_name);
+    free(o->bc_name); free(o->bc_hash);
     free(o->contig); free(o->e); free(o->bucket); free(o->cand);
     for (int32_t i = 0; i < o->n_seq; ++i) { free(o->seq_name[i]); free(o->seq[i]); }
     free(o->seq_name); free(o->seq); free(o->seq_len);
@@ -192,20 +193,34 @@ static void rehash(jxo_t* o) {
 }
 
 /* -b mode: what set_junction_barcode (junctions_extractor.cc:362-374) puts into j1.barcodes for one alignment.
- * The dictionary is a plain array searched linearly (test sizes). */
+ * The dictionary is an array of names with a small open-addressing index. */
 void jxo_enable_barcodes(jxo_t* o, const char* tag) {
     o->bc_on = 1;
     o->bc_tag[0] = tag && tag[0] ? tag[0] : 'C';
     o->bc_tag[1] = tag && tag[0] ? tag[1] : 'B';
 }
+static uint32_t bc_fnv(const char* s) { uint32_t h = 2166136261u; for (; *s; ++s) { h ^= (uint8_t)*s; h *= 16777619u; } return h; }
 void jxo_set_read_barcode(jxo_t* o, const char* bc) {
-    for (uint32_t i = 0; i < o->n_bc; ++i)
-        if (!strcmp(o->bc_name[i], bc)) { o->cur_bc = i; return; }
+    if (2 * (o->n_bc + 1) > o->n_bc_hash) {                  /* grow + rebuild, load <= 0.5 */
+        o->n_bc_hash = o->n_bc_hash ? o->n_bc_hash * 4 : 1024;
+        free(o->bc_hash);
+        o->bc_hash = (int32_t*)malloc(o->n_bc_hash * sizeof(int32_t));
+        memset(o->bc_hash, 0xff, o->n_bc_hash * sizeof(int32_t));
+        for (uint32_t i = 0; i < o->n_bc; ++i) {
+            uint32_t h = bc_fnv(o->bc_name[i]) & (o->n_bc_hash - 1);
+            while (o->bc_hash[h] >= 0) h = (h + 1) & (o->n_bc_hash - 1);
+            o->bc_hash[h] = (int32_t)i;
+        }
+    }
+    uint32_t h = bc_fnv(bc) & (o->n_bc_hash - 1);
+    for (; o->bc_hash[h] >= 0; h = (h + 1) & (o->n_bc_hash - 1))
+        if (!strcmp(o->bc_name[o->bc_hash[h]], bc)) { o->cur_bc = (uint32_t)o->bc_hash[h]; return; }
     if (o->n_bc == o->cap_bc) {
         o->cap_bc = o->cap_bc ? o->cap_bc * 2 : 256;
         o->bc_name = (char**)realloc(o->bc_name, o->cap_bc * sizeof(char*));
     }
     o->bc_name[o->n_bc] = strdup(bc);
+    o->bc_hash[h] = (int32_t)o->n_bc;
     o->cur_bc = o->n_bc++;
 }
 uint64_t jxo_barcodes_missing(const jxo_t* o) { return o->bc_missing; }

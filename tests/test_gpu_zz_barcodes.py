@@ -154,6 +154,23 @@ def test_untagged_bam_at_scale(tmp_path):
     assert n_bc == 1 and n_missing == o.barcodes_missing() > 10000
 
 
+def test_single_cell_shape_at_scale(tmp_path):
+    """bamgen --barcodes: 300k reads of the `tiny` shape (3 contigs, Zipf junction weights) with CB:Z drawn from 5000 skewed
+    barcodes on 97 % of the reads: ~50k (junction, barcode) pairs, hot junctions with thousands of distinct barcodes (the
+    replayed unordered_map rehashes a dozen times), several device batches, table growth from 2^10 slots."""
+    bam = str(tmp_path / "sc.bam")
+    subprocess.check_call([os.path.join(ROOT, "tools", "bamgen"), "gen", "--out", bam, "--config", "tiny", "--reads", "300000",
+                           "--seed", "17", "--barcodes", "5000"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    import contextlib
+    with open(os.devnull, "w") as dn, contextlib.redirect_stderr(dn):
+        bed, bc, (n_bc, n_missing), _ = _product(bam, ["-s", "XS"], tmp_path, batch_reads=65536, table_log2=10)
+    o = _oracle(bam, ["-s", "XS"])
+    assert bed == o.bed12()
+    assert bc == o.barcodes()
+    assert n_missing == o.barcodes_missing() > 500 and 3000 < n_bc <= 5001
+    assert max(int(l.split("\t")[0]) for l in bc.splitlines()) > 1000
+
+
 def test_cli_writes_the_barcode_file(tmp_path):
     exe = os.path.join(ROOT, "regtools_b200", "regtools")
     bam = os.path.join(GOLD, "bc2.bam")

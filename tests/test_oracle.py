@@ -276,3 +276,21 @@ def test_barcode_oracle_live_differential(seed, tmp_path):
         assert o.bed12() == open(tmp_path / "r.bed").read()
         assert o.barcodes() == open(tmp_path / "r.bc").read()
         assert o.barcodes_missing() == p.stderr.count("WARNING: No CB tag found for alignment (id = 0)")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs oracle/_ref/regtools_ref (dev container)")
+def test_barcode_oracle_on_a_single_cell_shaped_bam(tmp_path):
+    """bamgen --barcodes (the shape of the GPU at-scale test): 60k reads, 3000 skewed barcodes, a junction with > 800 of them."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(GOLD))
+    bam = str(tmp_path / "sc.bam")
+    subprocess.check_call([os.path.join(root, "tools", "bamgen"), "gen", "--out", bam, "--config", "tiny", "--reads", "60000", "--seed", "9",
+                           "--threads", "2", "--barcodes", "3000"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    p = subprocess.run([REF_BIN, "junctions", "extract", "-s", "XS", "-b", str(tmp_path / "r.bc"), "-o", str(tmp_path / "r.bed"), bam],
+                       capture_output=True, text=True)
+    assert p.returncode == 0
+    o = _bc_oracle(bam, ["-s", "XS"])
+    want = open(tmp_path / "r.bc").read()
+    assert o.bed12() == open(tmp_path / "r.bed").read() and o.barcodes() == want
+    assert o.barcodes_missing() == p.stderr.count("WARNING: No CB tag found for alignment (id = 0)") > 100
+    assert max(int(l.split("\t")[0]) for l in want.splitlines()) > 800

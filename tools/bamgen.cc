@@ -1,7 +1,7 @@
 // tools/bamgen.cc — bench/test infrastructure: deterministic synthetic RNA-seq BAM generator with
 // multi-threaded BGZF deflate, and a BAI indexer.  Not part of the product path.
 //
-//   bamgen gen --out x.bam --config c2|c2xN|c3|tiny --reads N [--seed 1234] [--level 6] [--threads T] [--qual8]
+//   bamgen gen --out x.bam --config c2|c2xN|c3|tiny --reads N [--seed 1234] [--level 6] [--threads T] [--qual8] [--barcodes N]
 //   bamgen index x.bam            (writes x.bam.bai)
 //
 // Workload shape follows SURVEY.md §8(d): junction catalog of one intron per 12 kb with Zipf(1)
@@ -222,7 +222,7 @@ struct Task {
 };
 
 struct Gen {
-    Config cfg; uint64_t seed; int level; bool qual8;
+    Config cfg; uint64_t seed; int level; bool qual8; uint64_t n_barcodes = 0;
     std::vector<Junc> cat;                             // sorted by (tid, donor)
 
     void junction_reads(const Junc& j, int64_t ws, int64_t we, std::vector<Rec>& out) const {
@@ -336,6 +336,16 @@ struct Gen {
             p += L;
             *p++ = 'N'; *p++ = 'H'; *p++ = 'C'; *p++ = 1;
             if (rc.xs) { *p++ = 'X'; *p++ = 'S'; *p++ = 'A'; *p++ = rc.xs; }
+            if (n_barcodes) {                                  // --barcodes N: CB:Z on 97 % of the reads, skewed towards low indices
+                const double u = r.uni();
+                if (r.uni() < 0.97) {
+                    uint64_t h = (uint64_t)((double)n_barcodes * u * u) * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+                    h ^= h >> 31; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 29;
+                    *p++ = 'C'; *p++ = 'B'; *p++ = 'Z';
+                    for (int b = 0; b < 16; ++b) *p++ = "ACGT"[(h >> (2 * b)) & 3];
+                    *p++ = '-'; *p++ = '1'; *p++ = 0;
+                }
+            }
             int32_t block_size = (int32_t)(p - rec_buf - 4);
             memcpy(rec_buf, &block_size, 4);
             raw.insert(raw.end(), rec_buf, p);
@@ -359,25 +369,27 @@ struct Gen {
 };
 
 void usage() {
-    fprintf(stderr, "usage: bamgen gen --out x.bam --config c2|c3|tiny --reads N [--seed S] [--level 1-9] [--threads T] [--qual8]\n"
+    fprintf(stderr, "usage: bamgen gen --out x.bam --config c2|c3|tiny --reads N [--seed S] [--level 1-9] [--threads T] [--qual8] [--barcodes N]\n"
                     "       bamgen index x.bam\n");
     exit(2);
 }
 
 // ------------------------------------------------------------------------------------------ gen
 int cmd_gen(int argc, char** argv) {
-    std::string out, cfgname = "c2"; uint64_t reads = 1000000, seed = 1234; int level = 6, threads = 0; bool qual8 = false;
+    std::string out, cfgname = "c2"; uint64_t reads = 1000000, seed = 1234; int level = 6, threads = 0; bool qual8 = false; uint64_t n_barcodes = 0;
     for (int i = 2; i < argc; ++i) {
         std::string a = argv[i];
         auto val = [&]() -> const char* { if (i + 1 >= argc) usage(); return argv[++i]; };
         if (a == "--out") out = val(); else if (a == "--config") cfgname = val();
         else if (a == "--reads") reads = strtoull(val(), nullptr, 10); else if (a == "--seed") seed = strtoull(val(), nullptr, 10);
         else if (a == "--level") level = atoi(val()); else if (a == "--threads") threads = atoi(val());
-        else if (a == "--qual8") qual8 = true; else usage();
+        else if (a == "--qual8") qual8 = true;
+        else if (a == "--barcodes") n_barcodes = strtoull(val(), nullptr, 10);      // single-cell shape: CB:Z tags for `-b`
+        else usage();
     }
     if (out.empty()) usage();
     if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
-    Gen g; g.cfg = make_config(cfgname); g.seed = seed; g.level = level; g.qual8 = qual8;
+    Gen g; g.cfg = make_config(cfgname); g.seed = seed; g.level = level; g.qual8 = qual8; g.n_barcodes = n_barcodes;
     const Config& cfg = g.cfg;
     const uint32_t L = cfg.read_len;
     // ---- catalog
