@@ -156,7 +156,7 @@ def test_untagged_bam_at_scale(tmp_path):
 
 def test_single_cell_shape_at_scale(tmp_path):
     """bamgen --barcodes: 300k reads of the `tiny` shape (3 contigs, Zipf junction weights) with CB:Z drawn from 5000 skewed
-    barcodes on 97 % of the reads: ~50k (junction, barcode) pairs, hot junctions with thousands of distinct barcodes (the
+    barcodes on 97 % of the reads: ~42k printed (junction, barcode) pairs, hot junctions with thousands of distinct barcodes (the
     replayed unordered_map rehashes a dozen times), several device batches, table growth from 2^10 slots."""
     bam = str(tmp_path / "sc.bam")
     subprocess.check_call([os.path.join(ROOT, "tools", "bamgen"), "gen", "--out", bam, "--config", "tiny", "--reads", "300000",
@@ -167,8 +167,8 @@ def test_single_cell_shape_at_scale(tmp_path):
     o = _oracle(bam, ["-s", "XS"])
     assert bed == o.bed12()
     assert bc == o.barcodes()
-    assert n_missing == o.barcodes_missing() > 500 and 3000 < n_bc <= 5001
-    assert max(int(l.split("\t")[0]) for l in bc.splitlines()) > 1000
+    assert n_missing == o.barcodes_missing() > 500 and 1000 < n_bc <= 5001
+    assert max(int(l.split("\t")[0]) for l in bc.splitlines()) > 2000          # 3067 distinct barcodes on the hottest junction
 
 
 def test_cli_writes_the_barcode_file(tmp_path):
