@@ -9,40 +9,44 @@
 #include "junctions_annotator.h"
 #include <cstring>
 
+// The driver loop: every call below is a method of the unmodified reference classes, in the order junctions_main.cc:68-82 uses.
+static int annotate_file(JunctionsAnnotator& a) {
+    std::ofstream tsv;
+    a.load_gtf();
+    a.open_junctions();
+    a.set_ofstream_object(tsv);
+    AnnotatedJunction rec;
+    rec.reset();
+    rec.print_header(tsv);
+    int done = 0;
+    for (; a.get_single_junction(rec); ++done) {
+        a.adjust_junction_ends(rec);
+        a.get_splice_site(rec);
+        a.annotate_junction_with_gtf(rec);
+        rec.print(tsv);
+        rec.reset();
+    }
+    a.close_ofstream();
+    std::cerr << std::endl << "Annotated " << done << " lines." << std::endl;
+    a.close_junctions();
+    return done;
+}
+
 int main(int argc, char** argv) {
-    int skip = 0;
+    int skip;
     if (argc >= 3 && !strcmp(argv[1], "junctions") && !strcmp(argv[2], "annotate")) skip = 2;
     else if (argc >= 2 && !strcmp(argv[1], "annotate")) skip = 1;
     else { std::cerr << "usage: regtools_ref_annotate junctions annotate [options] junctions.bed ref.fa annotations.gtf\n"; return 1; }
-    argc -= skip; argv += skip;
-    JunctionsAnnotator anno;
-    AnnotatedJunction line;
-    line.reset();
-    int linec = 0;
-    ofstream out;
+    JunctionsAnnotator annotator;
+    int rc = 0;
     try {
-        anno.parse_options(argc, argv);
-        anno.load_gtf();
-        anno.open_junctions();
-        anno.set_ofstream_object(out);
-        line.print_header(out);
-        while (anno.get_single_junction(line)) {
-            anno.adjust_junction_ends(line);
-            anno.get_splice_site(line);
-            anno.annotate_junction_with_gtf(line);
-            line.print(out);
-            line.reset();
-            linec++;
-        }
-        anno.close_ofstream();
-        cerr << endl << "Annotated " << linec << " lines." << endl;
-        anno.close_junctions();
-    } catch (const common::cmdline_help_exception& e) {
-        cerr << e.what() << endl;
-        return 0;
-    } catch (const runtime_error& e) {
-        cerr << e.what() << endl;
-        return 1;
+        annotator.parse_options(argc - skip, argv + skip);
+        annotate_file(annotator);
+    } catch (const common::cmdline_help_exception& help) {      // -h: exit 0 (junctions_main.cc:84-86)
+        std::cerr << help.what() << std::endl;
+    } catch (const std::runtime_error& err) {                   // exit 1 (:87-90)
+        std::cerr << err.what() << std::endl;
+        rc = 1;
     }
-    return 0;
+    return rc;
 }
