@@ -153,3 +153,17 @@ def test_shipped_library_has_no_cpu_path(tmp_path):
         rt.JunctionsAnnotator().parse_options(["annotate", "only.bed"])
     with pytest.raises(rt.CmdlineHelpException):
         rt.JunctionsAnnotator().parse_options(["annotate", "-h"])
+
+
+def test_side_bench_tool_runs_with_the_emulation_harness(tools, tmp_path):
+    """tools/bench_annotate.py (the measurement script of this row) end to end on a small workload, with the harness standing
+    in for the GPU: the JSON line parses and its parity field says the sample matched the CPU arm byte for byte."""
+    import json
+    import sys
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_annotate.py"), "--impl", "emul", "--contigs", "1", "--mb", "3",
+                        "--junctions", "3000", "--sample", "800", "--steps", "1", "--warmup", "0", "--dir", str(tmp_path)],
+                       capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    assert line["parity"] == "byte-identical on the sample" and line["value"] > 0 and line["cpu_baseline"]["value"] > 0
+    assert line["unit"] == "junctions/s" and line["impl"] == "emul"
