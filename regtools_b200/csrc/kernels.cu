@@ -667,8 +667,9 @@ struct S5Emit {
     }
 };
 
-template <int S5_THREADS, int S5_SLAB, int S5_OUT, bool MOTIF = false, bool VREG = false, bool BC = false>
-__global__ void __launch_bounds__(S5_THREADS)
+// MINB > 1 asks ptxas for that many resident blocks per SM (A/B configurations 8-10, see launch_cigar_scan)
+template <int S5_THREADS, int S5_SLAB, int S5_OUT, bool MOTIF = false, bool VREG = false, bool BC = false, int MINB = 1>
+__global__ void __launch_bounds__(S5_THREADS, MINB)
 cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters,
                         const uint32_t* __restrict__ tile_off, CandRegions rg) {
     using Smem = S5SmemT<S5_THREADS, S5_SLAB, S5_OUT>;
@@ -798,6 +799,135 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
     if (n_work == 0 && rg.base && t == 0) rg.cnt[blockIdx.x] = 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// cigar_scan, gather variant (variant 7; opt-in A/B build written at the end of round 1, NOT yet measured)
+// ------------------------------------------------------------------------------------------------
+// Why: Little's law on the round-1 numbers of the kernel above — 12 resident blocks x (8 KB columns + 2.7 KB slab) in flight
+// per SM over a ~6.5 us block life = 2.9 TB/s, which is the measured rate.  The 12 comes from two limits at once
+// (40 registers x 128 threads, 19.5 KB shared memory).  Only `cig_off` is needed for every alignment (to find n_cigar > 1);
+// pos / meta / tid matter for the ~17 % that go on the work list.  This kernel stages only `cig_off`, the slab and the
+// candidates (9.2 KB per block) and runs at <= 32 registers, so 16 blocks fit; the three columns of a work item are
+// fetched by its thread straight from global memory (neighbouring work items are ~6 alignments apart, so a warp touches a
+// handful of sectors per column) and that gather is issued BEFORE the wait for the slab, so it rides on the same round trip.
+template <int THREADS, int SLAB, int OUTN>
+struct alignas(16) S7SmemT {
+    static constexpr int S5_TILE = THREADS * 4;
+    uint32_t off[S5_TILE + 4];
+    uint32_t slab[SLAB];
+    uint4 out[OUTN * 2];
+    uint32_t n_work, n_out;
+    uint16_t work[S5_TILE];
+};
+
+template <int THREADS, int SLAB, int OUTN, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+cigar_scan_gather_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
+    using Smem = S7SmemT<THREADS, SLAB, OUTN>;
+    constexpr int TILE = Smem::S5_TILE;
+    __shared__ Smem sm;
+    const uint32_t t = threadIdx.x, lane = t & 31u;
+    const uint32_t base = blockIdx.x * TILE;
+    const uint32_t n_tile = min((uint32_t)TILE, b.n_reads - base);
+    const bool full = base + TILE + 3 <= b.n_reads;
+
+    // ---- cig_off of the tile: global -> shared
+    if (full) {
+        cp_async16(&sm.off[4 * t], b.cig_off + base + 4 * t);
+        if (t == 0) cp_async16(&sm.off[TILE], b.cig_off + base + TILE);
+    } else {
+        for (uint32_t r = t; r <= n_tile; r += THREADS) sm.off[r] = b.cig_off[base + r];
+    }
+    if (t == 0) { sm.n_work = 0; sm.n_out = 0; }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- CIGAR slab (same window rules as cigar_scan_small_kernel)
+    const uint32_t lo = sm.off[0], hi = sm.off[n_tile];
+    const uint32_t a0 = lo & ~3u;
+    uint32_t n_st = 0;
+    if (hi > lo) {
+        const uint32_t end = min(min((hi + 3u) & ~3u, a0 + (uint32_t)SLAB), b.n_ops & ~3u);
+        n_st = end > a0 ? end - a0 : 0u;
+        for (uint32_t v = t; v < (n_st >> 2); v += THREADS) cp_async16(&sm.slab[4 * v], b.cigar + a0 + 4 * v);
+    }
+    cp_async_commit();
+    // ---- work list of the alignments with n_cigar > 1 (junctions_extractor.cc:379)
+    {
+        const uint4 o = *reinterpret_cast<const uint4*>(&sm.off[4 * t]);
+        const uint32_t o4 = sm.off[4 * t + 4];
+        const uint32_t r0 = 4 * t;
+        uint32_t flags = 0;
+        if (r0 + 0 < n_tile && o.y - o.x > 1u) flags |= 1u;
+        if (r0 + 1 < n_tile && o.z - o.y > 1u) flags |= 2u;
+        if (r0 + 2 < n_tile && o.w - o.z > 1u) flags |= 4u;
+        if (r0 + 3 < n_tile && o4 - o.w > 1u) flags |= 8u;
+        const uint32_t cnt = __popc(flags);
+        uint32_t x = cnt;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
+        uint32_t wbase = 0;
+        if (lane == 31 && x) wbase = atomicAdd(&sm.n_work, x);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        uint32_t p = wbase + x - cnt;
+        if (flags & 1u) sm.work[p++] = (uint16_t)(r0 + 0);
+        if (flags & 2u) sm.work[p++] = (uint16_t)(r0 + 1);
+        if (flags & 4u) sm.work[p++] = (uint16_t)(r0 + 2);
+        if (flags & 8u) sm.work[p++] = (uint16_t)(r0 + 3);
+    }
+    __syncthreads();                                            // work list complete
+    const uint32_t n_work = sm.n_work;
+    // ---- columns of the first round's work item, requested before the slab is waited for
+    uint32_t g_r = 0, g_pos = 0, g_meta = 0;
+    int32_t g_tid = -1;
+    if (t < n_work) {
+        g_r = sm.work[t];
+        g_tid = __ldg(b.tid + base + g_r); g_pos = (uint32_t)__ldg(b.pos + base + g_r); g_meta = __ldg(b.meta + base + g_r);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    uint32_t jstrand = 0;
+    int32_t rspan[2] = {0, 0};
+    const S5Emit<Smem, OUTN, false, false, false> emit{sm, out, cap, counters, 0u, &prm, &jstrand, rspan};
+    auto flush = [&]() {                                        // warp 0
+        const uint32_t n_out = min(sm.n_out, (uint32_t)OUTN);
+        __syncwarp();
+        if (n_out) {
+            uint32_t fb = 0;
+            if (lane == 0) fb = atomicAdd(&counters[CTR_NCAND], n_out);
+            fb = __shfl_sync(0xffffffffu, fb, 0);
+            uint4* o = reinterpret_cast<uint4*>(out);
+            for (uint32_t v = lane; v < 2 * n_out; v += 32) {
+                if (fb + (v >> 1) < cap) o[2ull * fb + v] = sm.out[v];
+                else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) sm.n_out = 0;
+    };
+    for (uint32_t w0 = 0; w0 < n_work; w0 += THREADS) {
+        const uint32_t w = w0 + t;
+        if (w < n_work) {
+            uint32_t r = g_r, pos = g_pos, meta = g_meta;
+            int32_t tid = g_tid;
+            if (w0) {                                           // later rounds of a dense tile: plain loads
+                r = sm.work[w];
+                tid = __ldg(b.tid + base + r); pos = (uint32_t)__ldg(b.pos + base + r); meta = __ldg(b.meta + base + r);
+            }
+            if (tid >= 0) {
+                const uint32_t o0 = sm.off[r], n = sm.off[r + 1] - o0;
+                const uint32_t strand = read_strand(meta, prm.strandness);
+                const uint64_t read_ord = b.first_ordinal + base + r;
+                if ((o0 - a0) + n <= n_st) walk_fast<true>(sm.slab + (o0 - a0), n, pos, tid, strand, read_ord, emit);
+                else walk_fast<false>(b.cigar + o0, n, pos, tid, strand, read_ord, emit);
+            }
+        }
+        __syncthreads();
+        if (t < 32) flush();
+        if (w0 + THREADS < n_work) __syncthreads();
+    }
+}
+
 // pre-pass: tile_off[t] = cig_off[min(t * S5_TILE, n_reads)] (one 4-byte load per tile; the result stays in L2)
 __global__ void tile_offsets_kernel(const uint32_t* __restrict__ cig_off, uint32_t n_reads, uint32_t n_tiles, uint32_t tile, uint32_t* __restrict__ tile_off) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -827,7 +957,7 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
     const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
                             reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
                             reinterpret_cast<uintptr_t>(b.cigar);
-    const int variant = (p.genome || p.vr.n || b.bc) ? 5 : ((p.variant == 1 || p.variant == 4) ? p.variant : scan_variant());   // only variant 5 knows the intron-motif and variant-region modes
+    const int variant = (p.genome || p.vr.n || b.bc) ? 5 : ((p.variant == 1 || p.variant == 4 || p.variant == 7) ? p.variant : scan_variant());   // only variant 5 knows the intron-motif and variant-region modes
     if ((align & 15u) == 0 && variant == 5) {
         static int prepass = -1;
         const int cfg = b.bc ? 0 : (p.variant == 5 && p.cfg ? p.cfg : scan_cfg());
@@ -848,6 +978,13 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
         case 5: cigar_scan_small_kernel<128, 2048, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
         case 6: cigar_scan_small_kernel<128, 2048, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
         case 7: cigar_scan_small_kernel<128, 1536, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
+        // Occupancy experiments for round 2 (not yet measured).  Little's law on the round-1 numbers: 12 resident blocks x
+        // (8 KB columns + 2.7 KB slab) in flight per SM over a ~6.5 us block life = 2.9 TB/s, which IS the measured rate; the
+        // 12 comes from both limits at once (40 registers x 128 threads -> 12.8 blocks, 19.5 KB shared -> 11.6).  These
+        // configurations lift both: <= 32 registers (launch bound 16) and <= 14 KB shared memory per block.
+        case 8: cigar_scan_small_kernel<128, 768, 64, false, false, false, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
+        case 9: cigar_scan_small_kernel<128, 768, 96, false, false, false, 14><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
+        case 10: cigar_scan_small_kernel<128, 1024, 192, false, false, false, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;   // registers only
         default:
             if (b.bc && p.genome) cigar_scan_small_kernel<128, 1024, 192, true, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
             else if (b.bc) cigar_scan_small_kernel<128, 1024, 192, false, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
@@ -856,6 +993,17 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
             else if (p.genome) cigar_scan_small_kernel<128, 1024, 192, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions);
             else cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions);
             break;
+        }
+        return;
+    }
+    if ((align & 15u) == 0 && variant == 7) {                  // gather variant, A/B configurations via scan_cfg
+        const uint32_t tiles = (b.n_reads + 511u) / 512u;
+        switch (p.variant == 7 ? p.cfg : scan_cfg()) {
+        case 1: cigar_scan_gather_kernel<128, 1024, 96, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
+        case 2: cigar_scan_gather_kernel<128, 768, 96, 1><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
+        case 3: cigar_scan_gather_kernel<128, 1024, 192, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
+        case 4: cigar_scan_gather_kernel<128, 768, 96, 14><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
+        default: cigar_scan_gather_kernel<128, 768, 96, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
         }
         return;
     }
