@@ -52,7 +52,13 @@ bool load_fasta(const std::string& path, FastaGenome* g, std::string* err) {
         while (j < sz && p[j] != '>') {
             const void* e = memchr(p + j, '\n', sz - j);
             const size_t le = e ? (size_t)((const unsigned char*)e - p) : sz;
-            if (!dup) for (size_t q = j; q < le; ++q) if (is_graph(p[q])) g->bases.push_back(p[q]);
+            if (!dup) {
+                // a sequence line is normally all isgraph(): test the line in one vectorisable pass, then copy it whole
+                unsigned bad = 0;
+                for (size_t q = j; q < le; ++q) bad |= (unsigned)((unsigned char)(p[q] - 33) >= 94);
+                if (!bad) g->bases.insert(g->bases.end(), p + j, p + le);
+                else for (size_t q = j; q < le; ++q) if (is_graph(p[q])) g->bases.push_back(p[q]);
+            }
             j = e ? le + 1 : sz;
         }
         if (!dup) {
