@@ -482,6 +482,10 @@ class JunctionsAnnotator:
         (out or sys.stderr).write(ANNOTATE_USAGE)
         return 0
 
+    def gtf_file(self) -> str:
+        """gtf_file (junctions_annotator.cc:400-402)."""
+        return self.gtf_
+
     def parse_options(self, argv: Sequence[str]) -> int:
         """argv[0] is the sub-command name, as in the reference's getopt call."""
         try:

@@ -153,6 +153,31 @@ def test_shipped_library_has_no_cpu_path(tmp_path):
         rt.JunctionsAnnotator().parse_options(["annotate", "only.bed"])
     with pytest.raises(rt.CmdlineHelpException):
         rt.JunctionsAnnotator().parse_options(["annotate", "-h"])
+    # tests/lib/junctions/test_junctions_annotator.cc:35-45 (ParseInput)
+    ja1 = rt.JunctionsAnnotator()
+    assert ja1.parse_options(["annotate", "test.bed", "test.fa", "test.gtf"]) == 0 and ja1.gtf_file() == "test.gtf"
+
+
+def test_gtest_known_answers_of_the_gtf_parser(tools, tmp_path):
+    """tests/lib/gtf/test_gtf_parser.cc:86-121: the EP300 exon 22:12791-14103 files its transcript under bin 37359 (level 0 of
+    the reference's offsets, 32678 + 4681 + 0), gene EP300 / ENSG00000100393.  Seen from outside: a junction in that bin that
+    ends exactly on the exon's start finds the transcript, on either harness."""
+    gtf = tmp_path / "one.gtf"
+    attr = ('ccds_id "CCDS14010"; exon_id "ENSE00001343011"; exon_number "1"; gene_biotype "protein_coding"; gene_id "ENSG00000100393"; '
+            'gene_name "EP300"; gene_source "ensembl_havana"; p_id "P5137"; tag "CCDS"; transcript_id "ENST00000263253"; '
+            'transcript_name "EP300-001"; transcript_source "ensembl_havana"; tss_id "TSS138009"')
+    gtf.write_text("22\tprotein_coding\texon\t12791\t14103\t.\t+\t.\t" + attr + "\n"
+                   "22\tprotein_coding\texon\t38192\t38300\t.\t+\t.\t" + attr.replace('"1"', '"2"') + "\n")
+    bed = tmp_path / "j.bed"
+    # known junction 14103 -> 38192 (the first line of the reference's golden), and one ending on the first exon's start
+    bed.write_text("22\t14006\t38288\tJ1\t38\t+\t14006\t38288\t255,0,0\t2\t97,97\t0,24185\n"
+                   "22\t12000\t12890\tJ2\t1\t+\t12000\t12890\t255,0,0\t2\t50,100\t0,790\n")
+    for which in ("oracle", "emul"):
+        rc, out, err = _run(tools[which], [], str(bed), os.path.join(GOLD, "hcc1395.fa"), str(gtf), tmp_path / (which + ".tsv"))
+        assert rc == 0, err
+        rows = [l.split("\t") for l in out.splitlines()[1:]]
+        assert rows[0][:3] == ["22", "14103", "38192"] and rows[0][10:] == ["DA", "1", "1", "1", "EP300", "ENSG00000100393", "ENST00000263253"]
+        assert rows[1][:3] == ["22", "12050", "12791"] and rows[1][10:] == ["A", "0", "1", "0", "EP300", "ENSG00000100393", "ENST00000263253"]
 
 
 def test_side_bench_tool_runs_with_the_emulation_harness(tools, tmp_path):
