@@ -110,6 +110,9 @@ typedef struct {
     const uint32_t* meta;
     const uint32_t* cig_off;
     const uint32_t* cigar;
+    const uint32_t* bc;            /* `-b` handles only (else ignored, may be NULL): per alignment the id rtjx_intern_barcode
+                                      returned for its barcode (set_junction_barcode, junctions_extractor.cc:362-374: the CB:Z
+                                      value, "?" when absent); read for n_cigar > 1 alignments                          */
 } rtjx_batch;
 
 typedef struct {
@@ -169,7 +172,8 @@ int64_t     rtjx_get(rtjx_t* h, rtjx_junction* out, size_t cap);
 /* print_all_junctions (junctions_extractor.cc:249-280): BED12 of the anchor-filtered, sorted
  * junctions to a file descriptor. */
 int         rtjx_write_bed12(rtjx_t* h, int fd);
-/* `-b` single-cell mode (handle created with rtjx_params.barcode_out != NULL; fed by rtjx_run only).
+/* `-b` single-cell mode (handle created with rtjx_params.barcode_out != NULL; fed by rtjx_run, or by rtjx_scan_batch
+ * with rtjx_batch.bc; rtjx_add carries no barcode and refuses).
  * rtjx_write_barcodes = Junction::print_barcodes (junctions_extractor.h:99-111) for every junction that
  * print_all_junctions prints (junctions_extractor.cc:267-273), in the same order: "<n>\t<bc>:<count>,...\n" with the
  * barcodes in the iteration order of the reference's std::unordered_map.
@@ -178,6 +182,9 @@ int         rtjx_write_bed12(rtjx_t* h, int fd);
  * rtjx_barcode_name: dictionary entry `id` (NULL past the end).
  * rtjx_load_barcodes: host feeder only, like rtjx_load_batch: the per-alignment dictionary ids (0 for n_cigar <= 1) of
  * the handle's region in iteration order; returns the number of alignments, fills at most cap. */
+/* Batch-level `-b` (rtjx_scan_batch on a -b handle): registers a barcode string and returns its dictionary id (>= 0), the
+ * value to put into rtjx_batch.bc; a repeated string returns the same id. */
+int64_t     rtjx_intern_barcode(rtjx_t* h, const char* barcode);
 int         rtjx_write_barcodes(rtjx_t* h, int fd);
 int         rtjx_barcode_stats(rtjx_t* h, uint64_t* n_barcodes, uint64_t* n_missing);
 const char* rtjx_barcode_name(rtjx_t* h, uint32_t id);

@@ -376,6 +376,17 @@ void jxo_batch(jxo_t* o, uint32_t n_reads, const int32_t* tid, const int32_t* po
                  cigar + cig_off[i], cig_off[i + 1] - cig_off[i]);
 }
 
+/* -b over a SoA batch: names[bc[i]] is what set_junction_barcode (:362-374) would have found for alignment i (read for
+ * n_cigar > 1 alignments only, like the reference's call at :393-395). */
+void jxo_batch_barcodes(jxo_t* o, uint32_t n_reads, const int32_t* tid, const int32_t* pos, const uint32_t* meta,
+                        const uint32_t* cig_off, const uint32_t* cigar, const uint32_t* bc, const char* const* names) {
+    for (uint32_t i = 0; i < n_reads; ++i) {
+        const uint32_t n = cig_off[i + 1] - cig_off[i];
+        if (n > 1) jxo_set_read_barcode(o, names[bc[i]]);
+        jxo_read(o, tid[i], pos[i], meta[i] >> 16, (uint8_t)(meta[i] & 0xff), cigar + cig_off[i], n);
+    }
+}
+
 void jxo_record_candidates(jxo_t* o, int on) { o->record = on; }
 size_t jxo_candidates(const jxo_t* o, jxo_candidate* out, size_t cap) {
     size_t n = o->n_cand < cap ? o->n_cand : cap;

@@ -61,7 +61,7 @@ class Batch(C.Structure):
         ("n_reads", C.c_uint32), ("n_ops", C.c_uint32), ("first_ordinal", C.c_uint64),
         ("n_junction_ops", C.c_uint32), ("reserved", C.c_uint32),
         ("tid", C.c_void_p), ("pos", C.c_void_p), ("meta", C.c_void_p),
-        ("cig_off", C.c_void_p), ("cigar", C.c_void_p),
+        ("cig_off", C.c_void_p), ("cigar", C.c_void_p), ("bc", C.c_void_p),
     ]
 
 
@@ -103,6 +103,7 @@ SIGNATURES = {
     "rtjx_count": (C.c_int64, [C.c_void_p]),
     "rtjx_get": (C.c_int64, [C.c_void_p, C.POINTER(Junction), C.c_size_t]),
     "rtjx_write_bed12": (C.c_int, [C.c_void_p, C.c_int]),
+    "rtjx_intern_barcode": (C.c_int64, [C.c_void_p, C.c_char_p]),
     "rtjx_write_barcodes": (C.c_int, [C.c_void_p, C.c_int]),
     "rtjx_barcode_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "rtjx_barcode_name": (C.c_char_p, [C.c_void_p, C.c_uint32]),

@@ -354,7 +354,7 @@ int Engine::ensure_dev_batch(DevBatch& d, uint32_t reads, uint32_t ops) {
 int Engine::scan_batch(const rtjx_batch& b, int location, cudaStream_t user_stream) {
     int rc = ensure_device();
     if (rc) return rc;
-    if (bc_mode_) return fail(RTJX_E_UNSUPPORTED, "rtjx_scan_batch carries no barcodes: a -b handle is fed by rtjx_run");
+    if (bc_mode_ && !b.bc) return fail(RTJX_E_ARG, "a -b handle needs rtjx_batch.bc (ids from rtjx_intern_barcode)");
     if (b.n_reads == 0) return RTJX_OK;
     if (!b.tid || !b.pos || !b.meta || !b.cig_off || (b.n_ops && !b.cigar)) return fail(RTJX_E_ARG, "null array in batch");
     cudaStream_t st = user_stream ? user_stream : stream_;
@@ -363,6 +363,7 @@ int Engine::scan_batch(const rtjx_batch& b, int location, cudaStream_t user_stre
     if (location == RTJX_LOC_DEVICE) {
         if ((reinterpret_cast<uintptr_t>(b.cigar) & 15u) != 0) return fail(RTJX_E_ARG, "device cigar array must be 16-byte aligned");
         v.tid = b.tid; v.pos = b.pos; v.meta = b.meta; v.cig_off = b.cig_off; v.cigar = b.cigar;
+        if (bc_mode_) v.bc = b.bc;
     } else if (location == RTJX_LOC_HOST) {
         DevBatch& d = dev_batch_[dev_batch_next_]; dev_batch_next_ ^= 1;
         if ((rc = ensure_dev_batch(d, b.n_reads, b.n_ops))) return rc;
@@ -374,6 +375,11 @@ int Engine::scan_batch(const rtjx_batch& b, int location, cudaStream_t user_stre
         if (b.n_ops) CK(cudaMemcpyAsync(d.cigar, b.cigar, (size_t)b.n_ops * 4, cudaMemcpyHostToDevice, st));
         stats_.h2d_bytes += (size_t)b.n_reads * 16 + 4 + (size_t)b.n_ops * 4;
         v.tid = d.tid; v.pos = d.pos; v.meta = d.meta; v.cig_off = d.cig_off; v.cigar = d.cigar;
+        if (bc_mode_) {
+            CK(cudaMemcpyAsync(d.bc, b.bc, (size_t)b.n_reads * 4, cudaMemcpyHostToDevice, st));
+            stats_.h2d_bytes += (size_t)b.n_reads * 4;
+            v.bc = d.bc;
+        }
         rc = process_device_batch(v, b.n_junction_ops, st);
         cudaEventRecord(d.free_ev, st);
         return rc;
@@ -1123,6 +1129,13 @@ int Engine::write_barcodes(int fd) {
     }
     if (!flush()) return fail(RTJX_E_IO, "write failed");
     return RTJX_OK;
+}
+
+int64_t Engine::intern_barcode(const char* s) {
+    if (!bc_mode_) return fail(RTJX_E_STATE, "the handle was not created in -b mode (rtjx_params.barcode_out)");
+    if (!s) return fail(RTJX_E_ARG, "null barcode");
+    if (bc_dict_.names.size() >= (1u << 24) - 2u) return fail(RTJX_E_UNSUPPORTED, "more than 16.7 million distinct barcodes");
+    return (int64_t)bc_dict_.intern(s, strlen(s));
 }
 
 int Engine::barcode_stats(uint64_t* n_barcodes, uint64_t* n_missing) {

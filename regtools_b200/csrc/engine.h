@@ -34,6 +34,7 @@ public:
     // `-b` single-cell mode (junctions_extractor.cc:203-215,362-374; print_barcodes junctions_extractor.h:99-111)
     bool barcode_mode() const { return bc_mode_; }
     int write_barcodes(int fd);
+    int64_t intern_barcode(const char* s);
     int barcode_stats(uint64_t* n_barcodes, uint64_t* n_missing);
     const char* barcode_name(uint32_t id);
     int64_t load_barcodes(uint32_t* ids, size_t cap);          // host feeder only: per-alignment dictionary ids

@@ -69,6 +69,7 @@ int rtjx_finalize(rtjx_t* h, void* stream) { GUARD(h, h->e->finalize(static_cast
 int64_t rtjx_count(rtjx_t* h) { GUARD(h, h->e->count()) }
 int64_t rtjx_get(rtjx_t* h, rtjx_junction* out, size_t cap) { GUARD(h, h->e->get(out, cap)) }
 int rtjx_write_bed12(rtjx_t* h, int fd) { GUARD(h, h->e->write_bed12(fd)) }
+int64_t rtjx_intern_barcode(rtjx_t* h, const char* barcode) { GUARD(h, h->e->intern_barcode(barcode)) }
 int rtjx_write_barcodes(rtjx_t* h, int fd) { GUARD(h, h->e->write_barcodes(fd)) }
 int rtjx_barcode_stats(rtjx_t* h, uint64_t* n_barcodes, uint64_t* n_missing) { GUARD(h, h->e->barcode_stats(n_barcodes, n_missing)) }
 const char* rtjx_barcode_name(rtjx_t* h, uint32_t id) { return h ? h->e->barcode_name(id) : nullptr; }

@@ -350,8 +350,12 @@ class JunctionsExtractor:
         out.write(b"".join(chunks).decode())
 
     # ------------------------------------------------------------------ batch level (kernels)
+    def intern_barcode(self, barcode: str) -> int:
+        """-b handles: dictionary id of a barcode string, the value for scan_batch's `bc` column."""
+        return self._check(L.lib.rtjx_intern_barcode(self._handle(), barcode.encode()))
+
     def scan_batch(self, tid, pos, meta, cig_off, cigar, first_ordinal: int = 0, n_junction_ops: int = 0,
-                   stream: Optional[int] = None) -> int:
+                   stream: Optional[int] = None, bc=None) -> int:
         """parse_alignment_into_junctions over a SoA batch.  Arrays are numpy (host) or torch CUDA
         tensors (device, used in place); dtypes int32/int32/uint32-compatible, see include/rtjx.h."""
         h = self._handle()
@@ -369,7 +373,11 @@ class JunctionsExtractor:
                 if x.dtype.itemsize != 4:
                     raise ValueError("batch arrays must be 32-bit")
         b.tid, b.pos, b.meta, b.cig_off, b.cigar = ptr(tid), ptr(pos), ptr(meta), ptr(cig_off), ptr(cigar) if n_ops else None
-        self._keep = (tid, pos, meta, cig_off, cigar)
+        if bc is not None:                               # -b handles: per-alignment barcode ids (same residency as the batch)
+            if not is_dev:
+                bc = np.ascontiguousarray(bc, dtype=np.uint32)
+            b.bc = ptr(bc)
+        self._keep = (tid, pos, meta, cig_off, cigar, bc)
         self._check(L.lib.rtjx_scan_batch(h, C.byref(b), L.RTJX_LOC_DEVICE if is_dev else L.RTJX_LOC_HOST,
                                           C.c_void_p(stream) if stream else None))
         return 0

@@ -65,6 +65,7 @@ def lib():
         l.jxo_write_bed12_path.argtypes = [C.c_void_p, C.c_char_p]
         l.jxo_enable_barcodes.argtypes = [C.c_void_p, C.c_char_p]
         l.jxo_set_read_barcode.argtypes = [C.c_void_p, C.c_char_p]
+        l.jxo_batch_barcodes.argtypes = [C.c_void_p, C.c_uint32] + [C.c_void_p] * 6 + [C.POINTER(C.c_char_p)]
         l.jxo_barcodes_missing.restype = C.c_uint64
         l.jxo_barcodes_missing.argtypes = [C.c_void_p]
         l.jxo_write_barcode_replay_path.argtypes = [C.c_void_p, C.c_char_p]
@@ -150,6 +151,12 @@ class Oracle:
     # -b single-cell mode
     def set_read_barcode(self, bc):
         self.l.jxo_set_read_barcode(self.h, bc.encode())
+
+    def batch_barcodes(self, tid, pos, meta, cig_off, cigar, bc, names):
+        tid, pos, meta, cig_off, cigar, bc = (np.ascontiguousarray(x) for x in (tid, pos, meta, cig_off, cigar, bc))
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        self.l.jxo_batch_barcodes(self.h, len(tid), tid.ctypes.data, pos.ctypes.data, meta.ctypes.data, cig_off.ctypes.data,
+                                  cigar.ctypes.data, bc.ctypes.data, arr)
 
     def barcodes_missing(self):
         return self.l.jxo_barcodes_missing(self.h)

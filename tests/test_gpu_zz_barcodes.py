@@ -171,6 +171,44 @@ def test_single_cell_shape_at_scale(tmp_path):
     assert max(int(l.split("\t")[0]) for l in bc.splitlines()) > 2000          # 3067 distinct barcodes on the hottest junction
 
 
+@pytest.mark.parametrize("device_resident", [False, True])
+@pytest.mark.parametrize("strandness", [0, 1])
+def test_batch_level_barcodes_match_oracle(strandness, device_resident):
+    """rtjx_scan_batch with a `bc` column (ids from rtjx_intern_barcode) on random batches, split over several calls so a
+    junction's barcode list crosses batch boundaries; host-resident and device-resident input."""
+    import synth
+    import regtools_b200 as rt
+    arrs = synth.random_batch(11 + strandness, 40000, spliced_frac=0.3)
+    tid, pos, meta, off, cigar = arrs
+    rng = np.random.default_rng(5)
+    names = ["BC%05d-1" % i for i in range(700)] + ["?"]
+    bc_name_idx = np.minimum((len(names) * rng.random(len(tid)) ** 2).astype(np.int64), len(names) - 1)      # skewed
+    ex = rt.JunctionsExtractor(strandness=strandness)
+    ex.output_barcodes_file_ = os.devnull
+    ex.set_contigs(["1", "10", "2"])
+    ids = np.array([ex.intern_barcode(n) for n in reversed(names)], dtype=np.uint32)[::-1]              # ids != name index
+    bc = ids[bc_name_idx].astype(np.uint32)
+    bounds = np.linspace(0, len(tid), 4).astype(int)
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        o = off[lo:hi + 1].astype(np.uint32)
+        c = cigar[o[0]:o[-1]]
+        sub = [tid[lo:hi], pos[lo:hi], meta[lo:hi], (o - o[0]).astype(np.uint32), c, bc[lo:hi]]
+        if device_resident:
+            sub = [torch.from_numpy(np.ascontiguousarray(x).view(np.int32)).cuda() for x in sub]
+        ex.scan_batch(*sub[:5], first_ordinal=int(lo), n_junction_ops=synth.count_n_ops(c), bc=sub[5])
+        if device_resident:
+            torch.cuda.synchronize()
+    bed, bcs = io.StringIO(), io.StringIO()
+    ex.print_barcodes(bcs)
+    ex.print_all_junctions(bed)                                # (also writes the barcode lines to os.devnull)
+    ex.close()
+    orc = Oracle(8, 70, 500000, strandness, contigs=["1", "10", "2"], barcodes=True)
+    orc.batch_barcodes(tid, pos, meta, off, cigar, bc_name_idx.astype(np.uint32), names)
+    assert bed.getvalue() == orc.bed12()
+    assert bcs.getvalue() == orc.barcodes()
+    assert max(int(l.split("\t")[0]) for l in bcs.getvalue().splitlines()) > 20
+
+
 def test_cli_writes_the_barcode_file(tmp_path):
     exe = os.path.join(ROOT, "regtools_b200", "regtools")
     bam = os.path.join(GOLD, "bc2.bam")
@@ -201,7 +239,7 @@ def test_rerun_and_refusals(tmp_path):
         assert buf.getvalue() == open(os.path.join(GOLD, "bc2.xs.barcodes")).read()
     with pytest.raises(RuntimeError, match="carries no barcodes"):
         ex.add_junction(rt.Junction("1", 100, 300, 50, 350, "+"))
-    with pytest.raises(RuntimeError, match="carries no barcodes"):
+    with pytest.raises(RuntimeError, match="needs rtjx_batch.bc"):
         ex.scan_batch(np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(1, np.uint32), np.array([0, 1], np.uint32),
                       np.array([16], np.uint32))
     with pytest.raises(RuntimeError, match="no barcode mode"):
