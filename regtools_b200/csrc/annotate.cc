@@ -152,12 +152,15 @@ bool is_header(const char* s, size_t n) {
 
 Status read_junctions(const std::string& path, JunctionLines* out) {
     {
-        FILE* f = fopen(path.c_str(), "rb");
+        const bool from_stdin = path == "stdin" || path == "-";             // BedFile::Open (bedFile.cpp:99-101)
+        FILE* f = from_stdin ? stdin : fopen(path.c_str(), "rb");
         if (!f) return fail(RTJX_E_IO, "Error: The requested file (" + path + ") could not be opened. Exiting!");
         char chunk[1 << 16];
         size_t got;
         while ((got = fread(chunk, 1, sizeof chunk, f)) > 0) out->buf.append(chunk, got);
-        fclose(f);
+        if (!from_stdin) fclose(f);
+        if (out->buf.size() >= 2 && (unsigned char)out->buf[0] == 0x1f && (unsigned char)out->buf[1] == 0x8b)
+            return fail(RTJX_E_UNSUPPORTED, "gzip-compressed junction files are not read by the B200 path: " + path);
     }
     std::string& b = out->buf;
     b.push_back('\n');                                                        // sentinel: every line ends in the buffer

@@ -192,3 +192,12 @@ def test_side_bench_tool_runs_with_the_emulation_harness(tools, tmp_path):
     line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line["parity"] == "byte-identical on the sample" and line["value"] > 0 and line["cpu_baseline"]["value"] > 0
     assert line["unit"] == "junctions/s" and line["impl"] == "emul"
+
+
+def test_junctions_from_stdin(tools, gen_fasta, tmp_path):
+    """BedFile reads "stdin" / "-" (bedFile.cpp:99-101): `regtools junctions extract ... | regtools junctions annotate - ref.fa x.gtf`."""
+    bed, fa, gtf = _inputs("s2", gen_fasta)
+    for name in ("-", "stdin"):
+        p = subprocess.run([tools["emul"], "-o", str(tmp_path / "o.tsv"), name, fa, gtf], stdin=open(bed), capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        assert open(tmp_path / "o.tsv").read() == open(os.path.join(GOLD, "s2.expected.tsv")).read()
