@@ -220,11 +220,13 @@ void JunctionsExtractor::print_all_junctions(ostream& out) {
     print_barcodes_file();
     if (output_file_ != string("NA")) {
         int fd = ::open(output_file_.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-        if (fd < 0) return;    // the reference's ofstream silently fails too, then prints to `out`... keep quiet
-        int rc = rtjx_write_bed12(h, fd);
-        ::close(fd);
-        check(rc);
-        return;
+        if (fd >= 0) {
+            int rc = rtjx_write_bed12(h, fd);
+            ::close(fd);
+            check(rc);
+            return;
+        }
+        // an ofstream that failed to open: `fout.is_open()` is false and every junction goes to `out` (:269-272)
     }
     if (&out == &cout) {
         cout.flush();

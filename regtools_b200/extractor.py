@@ -325,12 +325,16 @@ class JunctionsExtractor:
         if self.output_barcodes_file_ != "NA":
             self.print_barcodes()
         if self.output_file_ != "NA":
-            fd = os.open(self.output_file_, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
             try:
-                self._check(L.lib.rtjx_write_bed12(h, fd))
-            finally:
-                os.close(fd)
-            return
+                fd = os.open(self.output_file_, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+            except OSError:
+                fd = -1        # an ofstream that failed to open: every junction goes to `out` (junctions_extractor.cc:269-272)
+            if fd >= 0:
+                try:
+                    self._check(L.lib.rtjx_write_bed12(h, fd))
+                finally:
+                    os.close(fd)
+                return
         if out is None:
             sys.stdout.flush()
             self._check(L.lib.rtjx_write_bed12(h, 1))
