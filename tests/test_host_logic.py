@@ -370,3 +370,54 @@ def test_feeder_barcode_column(threads, tmp_path):
                 seen.append(bc)
             assert names[ids[i]] == bc, i
         assert names == seen and n_missing == missing and missing > 0
+
+
+# ---- FASTA loader (fasta.cc): several threads, same result as one sequential faidx-style pass -------------------------
+def _py_fasta(path):
+    """faidx's view (fai_build_core, faidx.c:82-155): a record starts at '>' at the beginning of a line, the name runs to the
+    first white space, the bases are the isgraph() bytes of the following lines, a repeated name is ignored."""
+    seqs, order, cur = {}, [], None
+    for line in open(path, "rb").read().split(b"\n"):
+        if line.startswith(b">"):
+            name = line[1:].lstrip(b" \t\r\v\f").split(None, 1)
+            name = name[0] if name else b""
+            cur = None
+            if name not in seqs:
+                seqs[name] = bytearray(); order.append(name); cur = name
+        elif cur is not None:
+            seqs[cur] += bytes(c for c in line if 32 < c < 127)
+    return [(n, bytes(seqs[n])) for n in order]
+
+
+def _fnv(b):
+    h = 1469598103934665603
+    for c in b:
+        h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def test_fasta_loader_matches_a_sequential_reading(tmp_path):
+    import random
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emul"), "-s", "../../build/emul/fasta_dump"])
+    exe = os.path.join(ROOT, "build", "emul", "fasta_dump")
+    rnd = random.Random(3)
+    cases = {}
+    cases["plain"] = b">1 desc\nACGT\nacgtN\n>2\nGG\n"
+    cases["crlf_noeol"] = b">a\r\nAC GT\r\nNN\r\n>b x y\r\nTTTT"
+    cases["dups_junk"] = b"junk before\nmore\n>x\nAAAA\n>y\nCC\n>x\nGGGG\n>z\n\n\nT>T\n>\nAA\n"
+    big = bytearray()
+    for i in range(40):                                        # ~14 MB: several chunks, headers and duplicates inside chunks
+        big += b">seq%d some text\n" % (i % 33)
+        for _ in range(rnd.randrange(1, 6000)):
+            big += bytes(rnd.choice(b"ACGTacgtN") for _ in range(60)) + rnd.choice([b"\n", b"\n", b" \n", b"\r\n"])
+    cases["big"] = bytes(big)
+    for name, data in cases.items():
+        path = tmp_path / (name + ".fa")
+        path.write_bytes(data)
+        got = subprocess.run([exe, str(path)], capture_output=True, text=True, check=True).stdout.splitlines()
+        want = _py_fasta(str(path))
+        assert len(got) == len(want), name
+        for line, (n, s) in zip(got, want):
+            f = line.split("\t")
+            assert f[0] == n.decode() and int(f[1]) == len(s) and int(f[2], 16) == _fnv(s), (name, n)
