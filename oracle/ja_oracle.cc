@@ -12,7 +12,7 @@
 // C++ (not C) because the outputs are std::set<std::string> orders and std::sort's treatment of equal exon starts: both
 // are properties of libstdc++ that the restatement uses directly instead of imitating.
 //
-// Parity status: PINNED — tests/test_oracle_annotate.py checks it against the reference's own golden
+// Parity status: PINNED — tests/test_annotate_cpu.py checks it against the reference's own golden
 // (tests/integration-test/data/junctions-annotate/expected-annotate.out, copied to tests/golden/annotate/) and against
 // outputs of the UNMODIFIED reference (oracle/_ref/regtools_ref_annotate) on generated GTF/BED/FASTA fixtures.
 //
@@ -98,12 +98,16 @@ struct Gtf {
             t.exons.push_back(e);
             if (!t.has_gene) { t.gene_name = gname; t.gene_id = gid; t.has_gene = true; }
         }
-        for (std::map<string, Transcript>::iterator it = tx.begin(); it != tx.end(); ++it) {      // :192-208
-            vector<Exon>& ex = it->second.exons;
-            if (ex[0].strand == "+") std::sort(ex.begin(), ex.end(), [](const Exon& a, const Exon& b) { return a.start < b.start; });
-            else if (ex[0].strand == "-") std::sort(ex.begin(), ex.end(), [](const Exon& a, const Exon& b) { return a.start > b.start; });
-            else { std::cerr << "Undefined strand for exon " << ex[0].start << ex[0].end; exit(1); }
-        }
+        // GtfParser::load (:262-268) sorts TWICE: construct_junctions() sorts because transcripts_sorted_ is still false, then
+        // load() calls sort_exons_within_transcripts() again.  Each pass picks its direction from exons[0].strand AT THAT
+        // MOMENT (:192-208), so a transcript whose exons disagree on the strand can be re-sorted the other way round.
+        for (int pass = 0; pass < 2; ++pass)
+            for (std::map<string, Transcript>::iterator it = tx.begin(); it != tx.end(); ++it) {
+                vector<Exon>& ex = it->second.exons;
+                if (ex[0].strand == "+") std::sort(ex.begin(), ex.end(), [](const Exon& a, const Exon& b) { return a.start < b.start; });
+                else if (ex[0].strand == "-") std::sort(ex.begin(), ex.end(), [](const Exon& a, const Exon& b) { return a.start > b.start; });
+                else { std::cerr << "Undefined strand for exon " << ex[0].start << ex[0].end; exit(1); }
+            }
         for (std::map<string, Transcript>::iterator it = tx.begin(); it != tx.end(); ++it) {      // :149-169
             const vector<Exon>& ex = it->second.exons;
             chrbin[ex[0].chrom][get_bin(ex[0].start, ex[ex.size() - 1].end)].push_back(it->first);
@@ -274,6 +278,8 @@ int main(int argc, char** argv) {
         Fasta fasta; bool fasta_loaded = false, fasta_ok = false;
         string line; bool header = true; size_t n_fields0 = 0; int linec = 0;
         AJ j;
+        // (the BED reader's errors are exit(1) inside bedFile.h: automatic objects are not destroyed, so an ofstream that
+        // only holds the header so far is never flushed — the file stays empty)
         while (std::getline(bf, line)) {
             if (header && (line.find("#") == 0 || line.find("browser") == 0 || line.find("track") == 0)) continue;   // GetHeader
             header = false;
@@ -281,12 +287,20 @@ int main(int argc, char** argv) {
             vector<string> f = split(line, '\t');
             if (f.empty()) break;                                                  // BED_BLANK ends the loop
             if (f[0].find("#") == 0 || f[0].find("browser") == 0 || f[0].find("track") == 0) break;   // BED_HEADER too
-            if (f.size() < 3) { std::cerr << "It looks as though you have less than 3 columns" << std::endl; return 1; }
-            if (!is_integer(f[1]) || !is_integer(f[2])) { std::cerr << "Unexpected file format." << std::endl; return 1; }
+            if (f.size() < 3) { std::cerr << "It looks as though you have less than 3 columns" << std::endl; exit(1); }
+            if (!is_integer(f[1]) || !is_integer(f[2])) { std::cerr << "Unexpected file format." << std::endl; exit(1); }
             if (!n_fields0) n_fields0 = f.size();
-            if (f.size() != n_fields0) { std::cerr << "Differing number of BED fields encountered" << std::endl; return 1; }
+            if (f.size() != n_fields0) { std::cerr << "Differing number of BED fields encountered" << std::endl; exit(1); }
             j.reset();
-            j.chrom = f[0]; j.start = (uint32_t)atoi(f[1].c_str()); j.end = (uint32_t)atoi(f[2].c_str());
+            {   // parseBedLine, bedFile.h:685-760
+                const int is = atoi(f[1].c_str()), ie = atoi(f[2].c_str());
+                if (is < 0) { std::cerr << "Error: malformed BED entry. Start Coordinate detected that is < 0. Exiting." << std::endl; exit(1); }
+                if (ie < 0) { std::cerr << "Error: malformed BED entry. End Coordinate detected that is < 0. Exiting." << std::endl; exit(1); }
+                j.start = (uint32_t)is; j.end = (uint32_t)ie;
+                if (j.start == j.end) { j.start--; j.end++; }
+                if (j.start > j.end) { std::cerr << "Error: malformed BED entry. Start was greater than end. Exiting." << std::endl; exit(1); }
+            }
+            j.chrom = f[0];
             j.name = f.size() > 3 ? f[3] : ""; j.score = f.size() > 4 ? f[4] : ""; j.strand = f.size() > 5 ? f[5] : "";
             if (f.size() != 12 || f[10].empty()) throw std::runtime_error("BED line not in BED12 format. start: " + j.chrom + ":" + u2s(j.start));
             vector<string> bs = split(f[10], ',');                                 // adjust_junction_ends :66-81

@@ -101,12 +101,15 @@ Status load_gtf(const std::string& path, GtfFlat* out) {
     }
     // sort_exons_within_transcripts (:192-208): by the strand of the FIRST exon in file order; same std::sort, same input
     // order, same comparator results as the reference => the same arrangement of equal starts
-    for (std::map<std::string, Tx>::iterator it = txs.begin(); it != txs.end(); ++it) {
-        std::vector<ExonRec>& ex = it->second.exons;
-        if (ex[0].strand == 0) std::sort(ex.begin(), ex.end(), [](const ExonRec& a, const ExonRec& b) { return a.start < b.start; });
-        else if (ex[0].strand == 1) std::sort(ex.begin(), ex.end(), [](const ExonRec& a, const ExonRec& b) { return a.start > b.start; });
-        else return fail(RTJX_E_IO, "Undefined strand for exon " + std::to_string(ex[0].start) + std::to_string(ex[0].end));
-    }
+    // GtfParser::load (:262-268) sorts twice (construct_junctions() sorts first because transcripts_sorted_ is still false);
+    // each pass takes its direction from exons[0].strand at that moment, which matters for transcripts with mixed strands
+    for (int pass = 0; pass < 2; ++pass)
+        for (std::map<std::string, Tx>::iterator it = txs.begin(); it != txs.end(); ++it) {
+            std::vector<ExonRec>& ex = it->second.exons;
+            if (ex[0].strand == 0) std::sort(ex.begin(), ex.end(), [](const ExonRec& a, const ExonRec& b) { return a.start < b.start; });
+            else if (ex[0].strand == 1) std::sort(ex.begin(), ex.end(), [](const ExonRec& a, const ExonRec& b) { return a.start > b.start; });
+            else return fail(RTJX_E_IO, "Undefined strand for exon " + std::to_string(ex[0].start) + std::to_string(ex[0].end));
+        }
     // annotate_transcript_with_bins (:149-169) + flat arrays; transcripts are numbered in map (id) order
     std::map<unsigned long long, std::vector<uint32_t> > bins;
     out->tx_ex_off.push_back(0);
@@ -138,6 +141,9 @@ struct JunctionLines {
     std::vector<Tok> chrom, name, score, strand;
     std::vector<uint32_t> start, end;                                         // adjusted
     Status stop;                                                              // why reading stopped early (error after the lines above)
+    // every `stop` of read_junctions except "not BED12" is an exit(1) inside the reference's BedFile: its ofstream is never
+    // destroyed, so a header that no junction line (std::endl) has flushed yet never reaches the -o file
+    bool stop_is_exit = false;
 };
 
 bool is_integer(const char* s) {                                              // s is NUL-terminated
@@ -198,11 +204,17 @@ Status read_junctions(const std::string& path, JunctionLines* out) {
             }
         }
         if (nf == 0 || is_header(fld[0].p, fld[0].n)) break;                  // BED_BLANK / BED_HEADER end get_single_junction's loop
-        if (nf < 3) { out->stop = fail(RTJX_E_IO, "It looks as though you have less than 3 columns. Are you sure your files are tab-delimited?"); break; }
-        if (!is_integer(fld[1].p) || !is_integer(fld[2].p)) { out->stop = fail(RTJX_E_IO, "Unexpected file format.  Please use tab-delimited BED, GFF, or VCF."); break; }
+        if (nf < 3) { out->stop_is_exit = true; out->stop = fail(RTJX_E_IO, "It looks as though you have less than 3 columns. Are you sure your files are tab-delimited?"); break; }
+        if (!is_integer(fld[1].p) || !is_integer(fld[2].p)) { out->stop_is_exit = true; out->stop = fail(RTJX_E_IO, "Unexpected file format.  Please use tab-delimited BED, GFF, or VCF."); break; }
         if (!n_fields0) n_fields0 = nf;
-        if (nf != n_fields0) { out->stop = fail(RTJX_E_IO, "Differing number of BED fields encountered. Exiting..."); break; }
-        uint32_t start = (uint32_t)atoi(fld[1].p), end = (uint32_t)atoi(fld[2].p);
+        if (nf != n_fields0) { out->stop_is_exit = true; out->stop = fail(RTJX_E_IO, "Differing number of BED fields encountered. Exiting..."); break; }
+        // parseBedLine (bedFile.h:685-760): negative coordinates and start > end end the run (exit 1), start == end is widened
+        const int i_start = atoi(fld[1].p), i_end = atoi(fld[2].p);
+        if (i_start < 0) { out->stop_is_exit = true; out->stop = fail(RTJX_E_IO, "Error: malformed BED entry. Start Coordinate detected that is < 0. Exiting."); break; }
+        if (i_end < 0) { out->stop_is_exit = true; out->stop = fail(RTJX_E_IO, "Error: malformed BED entry. End Coordinate detected that is < 0. Exiting."); break; }
+        uint32_t start = (uint32_t)i_start, end = (uint32_t)i_end;
+        if (start == end) { --start; ++end; }                                 // zeroLength
+        if (start > end) { out->stop_is_exit = true; out->stop = fail(RTJX_E_IO, "Error: malformed BED entry. Start was greater than end. Exiting."); break; }
         if (nf != 12 || fld[10].n == 0) {                                     // :70-75
             out->stop = fail(RTJX_E_IO, "BED line not in BED12 format. start: " + std::string(fld[0].p, fld[0].n) + ":" + std::to_string(start));
             break;
@@ -424,7 +436,8 @@ Status annotate_impl(const rtjx_annotate_params& p, int out_fd, uint64_t* n_line
         if (o.size() > (1u << 20)) { if (!write_all(out_fd, o)) return fail(RTJX_E_IO, "write failed"); o.clear(); }
         if (chatter.s.size() > (1u << 20)) { write_all(p.chatter_fd, chatter.s); chatter.s.clear(); }
     }
-    if (!write_all(out_fd, out.s)) return fail(RTJX_E_IO, "write failed");
+    const bool header_lost = own.fd >= 0 && printed == 0 && result.ok() && jl.stop_is_exit;      // see JunctionLines::stop_is_exit
+    if (!header_lost && !write_all(out_fd, out.s)) return fail(RTJX_E_IO, "write failed");
     lap("format + write");
     if (result.ok() && !jl.stop.ok()) result = jl.stop;                        // a malformed BED line ends the run after the lines before it
     if (chat) {
