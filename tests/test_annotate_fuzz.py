@@ -140,3 +140,34 @@ def test_sort_ties_attributes_line_endings(block, env):
         assert ref == emu, f"product (emulated) differs from the reference, seed {seed}"
         done += ref[0][0] == 0
     assert done >= 5                                           # most runs get to the end (the rest stop at a missing contig)
+
+
+def test_wide_coordinates_reach_every_bin_level(env):
+    """Transcripts and junctions spread over up to ~2 Gb (far beyond the FASTA, so the 2-mers are clipped to nothing): the
+    junction's bin walk (junctions_annotator.cc:367-388) and getBin (bedFile.h) at all seven levels."""
+    d, fa = env
+    for seed in range(40):
+        rnd = random.Random(777 + seed)
+        scale = rnd.choice([1, 37, 1000, 16384, 131072, 400000])
+        lines = []
+        for t in range(rnd.randrange(1, 8)):
+            chrom, strand = rnd.choice(["1", "1", "2"]), rnd.choice("+-")
+            base = rnd.randrange(0, 3) * scale * 3
+            for _ in range(rnd.randrange(1, 7)):
+                s = base + rnd.randrange(1, 5000) * max(1, scale // 50)
+                ln = rnd.choice([1, 50, 200, 1000, scale])
+                lines.append(f'{chrom}\tx\texon\t{s}\t{s + ln}\t.\t{strand}\t.\tgene_id "g{t % 3}"; transcript_id "t{t}"; gene_name "n{t % 2}";')
+        rnd.shuffle(lines)
+        coords = sorted({int(l.split("\t")[3]) for l in lines} | {int(l.split("\t")[4]) for l in lines})
+        rows = []
+        for k in range(40):
+            a = rnd.choice(coords) + rnd.choice([0, 0, 0, 1, -1, 7]); b = rnd.choice(coords) + rnd.choice([0, 0, 0, 1, -1, -9])
+            if a > b:
+                a, b = b, a
+            b0, b1 = rnd.randrange(0, 30), rnd.randrange(0, 30)
+            s, e = a - b0, b - 1 + b1
+            if s < 0 or e < 0 or s > e or e >= 2 ** 31:
+                continue
+            rows.append("\t".join(map(str, [rnd.choice(["1", "1", "2"]), s, e, f"J{k}", k, rnd.choice("+-"), s, e, "255,0,0", 2, f"{b0},{b1}", "0,1"])))
+        ref, ora, emu = _three_way(d, fa, "\n".join(lines) + "\n", "\n".join(rows) + "\n")
+        assert ref[0][0] == 0 and ref == ora and ref == emu, f"seed {seed}, scale {scale}"
