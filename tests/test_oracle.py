@@ -294,3 +294,55 @@ def test_barcode_oracle_on_a_single_cell_shaped_bam(tmp_path):
     assert o.bed12() == open(tmp_path / "r.bed").read() and o.barcodes() == want
     assert o.barcodes_missing() == p.stderr.count("WARNING: No CB tag found for alignment (id = 0)") > 100
     assert max(int(l.split("\t")[0]) for l in want.splitlines()) > 800
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs oracle/_ref/regtools_ref (dev container)")
+@pytest.mark.parametrize("block", range(3))
+def test_barcode_differential_fuzz(block, tmp_path):
+    """-b against the unmodified reference on fuzzed aux layouts: CB as Z or H, before / after / between XS, NH, Z, B and f
+    tags, barcodes of 1-40 characters incl. ':' ',' '-', 1-200 distinct barcodes, reads without CB, XS of type Z (-> '?'),
+    small BGZF blocks.  BED12, barcode file and warning count from the oracle; the product's host feeder must report the same
+    number of untagged alignments and distinct barcodes (rtjx_load_barcodes, no GPU needed)."""
+    import random
+    import struct
+    import subprocess
+    import bamio
+    import regtools_b200 as rt
+    root = os.path.dirname(os.path.dirname(GOLD))
+    for seed in range(block * 12, block * 12 + 12):
+        rnd = random.Random(5000 + seed)
+        bcs = [("".join(rnd.choice("ACGT:,-_") for _ in range(rnd.choice([1, 4, 16, 40])))).encode() for _ in range(rnd.choice([1, 3, 20, 200]))]
+        loci = [(rnd.choice([0, 1, 2]), rnd.randrange(1000, 50000, 1000),
+                 rnd.choice(["50M100N50M", "20M300N30M500N50M", "5S45M1000N50M", "50M69N50M", "3M200N97M", "50M2D50M", "100M"]))
+                for _ in range(rnd.randrange(1, 8))]
+        reads = []
+        for _ in range(rnd.choice([5, 50, 400])):
+            tid, pos, cg = rnd.choice(loci)
+            xs = rnd.choice([b"XSA+", b"XSA-", b"XSA?", b"", b"XSZ+\0"])
+            r = rnd.random()
+            cb = b"" if r < 0.1 else (b"CBH" if r < 0.2 else b"CBZ") + rnd.choice(bcs) + b"\0"
+            other = rnd.choice([b"", b"NHC\x01", b"RGZx y\0", b"ZBBc" + struct.pack("<I", 2) + b"\x01\x02", b"XXf" + struct.pack("<f", 1.5)])
+            parts = [xs, cb, other]
+            rnd.shuffle(parts)
+            reads.append((tid, pos, cg, rnd.choice([0, 16, 99, 147]), b"".join(parts)))
+        reads.sort(key=lambda x: (x[0], x[1]))
+        recs = [bamio.record(t, p, c, f, 60, a, name=b"q%05d" % i) for i, (t, p, c, f, a) in enumerate(reads)]
+        bam = str(tmp_path / "f.bam")
+        bamio.write_bam(bam, [("1", 100000), ("10", 100000), ("2", 100000)], recs, block_size=rnd.choice([0x200, 0x4000, 0xff00]))
+        subprocess.check_call([os.path.join(root, "tools", "bamgen"), "index", bam], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for args in (["-s", "XS"], ["-s", "RF", "-a", "3"], ["-s", "XS", "-r", "10"]):
+            p = subprocess.run([REF_BIN, "junctions", "extract"] + args + ["-b", str(tmp_path / "r.bc"), "-o", str(tmp_path / "r.bed"), bam],
+                               capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr[-300:]
+            o = _bc_oracle(bam, args)
+            assert o.bed12() == open(tmp_path / "r.bed").read(), (seed, args)
+            assert o.barcodes() == open(tmp_path / "r.bc").read(), (seed, args)
+            warnings = p.stderr.count("WARNING: No CB tag found for alignment (id = 0)")
+            assert o.barcodes_missing() == warnings
+            ex = rt.JunctionsExtractor(bam, args[args.index("-r") + 1] if "-r" in args else ".", 0, device=-1)
+            ex.output_barcodes_file_ = os.devnull
+            ids = ex.load_barcodes()
+            n_bc, n_missing = ex.barcode_stats()
+            names = ex.barcode_names()
+            ex.close()
+            assert n_missing == warnings and n_bc == len(set(names)) == len(names) and (len(ids) == 0 or ids.max() < max(n_bc, 1))
