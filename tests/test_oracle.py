@@ -346,3 +346,42 @@ def test_barcode_differential_fuzz(block, tmp_path):
             names = ex.barcode_names()
             ex.close()
             assert n_missing == warnings and n_bc == len(set(names)) == len(names) and (len(ids) == 0 or ids.max() < max(n_bc, 1))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs oracle/_ref/regtools_ref (dev container)")
+@pytest.mark.parametrize("block", range(3))
+def test_cigar_differential_fuzz(block, tmp_path):
+    """Random CIGARs against the unmodified reference: every op incl. P / = / X / H, zero-length ops, N lengths on both QC
+    bounds, up to 20 ops, N first or last, flags incl. unmapped-with-CIGAR, XS of type A / C / absent / twice, tag NH as the
+    strand tag, -a/-m/-M corners, a region.  The index comes from the reference's own htslib (oracle/_ref/ref_index)."""
+    import random
+    import subprocess
+    import bamio
+    root = os.path.dirname(os.path.dirname(GOLD))
+    for seed in range(block * 10, block * 10 + 10):
+        rnd = random.Random(9000 + seed)
+        reads = []
+        for _ in range(rnd.choice([3, 30, 300])):
+            cig = []
+            for _k in range(rnd.choice([1, 2, 3, 3, 4, 5, 8, 20])):
+                op = rnd.choice("MMMMNNNIDSH=XP")
+                ln = rnd.choice([0, 1, 5, 50, 69, 70, 100, 500000, 500001]) if op == "N" else rnd.choice([0, 1, 3, 7, 8, 20, 50])
+                cig.append((ln << 4) | bamio.OPS.index(op))
+            reads.append((rnd.choice([0, 0, 1, 2]), rnd.randrange(0, 3000), cig, rnd.choice([0, 16, 4, 99, 147, 83, 163, 256, 1024, 2048 + 16]),
+                          rnd.choice([0, 1, 60, 255]), rnd.choice([b"XSA+", b"XSA-", b"XSA.", b"", b"XSC\x2b", b"NHC\x01XSA-", b"XSA+XSA-"])))
+        reads.sort(key=lambda x: (x[0], x[1]))
+        recs = [bamio.record(t, p, c, f, q, a, name=b"q%05d" % i, l_seq=10) for i, (t, p, c, f, q, a) in enumerate(reads)]
+        bam = str(tmp_path / "f.bam")
+        bamio.write_bam(bam, [("1", 20000000), ("10", 20000000), ("2", 20000000)], recs, block_size=rnd.choice([0x300, 0xff00]))
+        if os.path.exists(bam + ".bai"):
+            os.remove(bam + ".bai")
+        subprocess.check_call([os.path.join(root, "oracle", "_ref", "ref_index"), bam])
+        for args in (["-s", "XS"], ["-s", "RF", "-a", "0", "-m", "0", "-M", "4000000000"], ["-s", "FR", "-a", "1", "-m", "1"],
+                     ["-s", "XS", "-r", "1:100-2000"], ["-s", "XS", "-t", "NH"]):
+            rc, out = ref_extract(bam, args)
+            o = run_oracle(bam, args)
+            assert rc == 0 and o.bed12() == out, (seed, args)
+        # the generator's own BAI writer must serve the same BAM (it once crashed on CIGARs that consume no reference)
+        subprocess.check_call([os.path.join(root, "tools", "bamgen"), "index", bam], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        rc, out = ref_extract(bam, ["-s", "XS", "-r", "1:100-2000"])
+        assert rc == 0 and out == run_oracle(bam, ["-s", "XS", "-r", "1:100-2000"]).bed12()

@@ -590,6 +590,7 @@ int cmd_index(int argc, char** argv) {
         if (!(flag & 4) && n_cigar) {
             end = pos;
             for (uint32_t k = 0; k < n_cigar; ++k) { uint32_t w; memcpy(&w, c + 32 + l_qname + 4 * k, 4); uint32_t op = w & 0xf; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) end += (int32_t)(w >> 4); }
+            if (end == pos) end = pos + 1;            // bam_endpos (sam.c:336-342): a CIGAR that consumes no reference counts as 1
         }
         upos += 4 + (size_t)bs;
         // bgzf_tell after the record: if the block is exactly consumed htslib reports (next block, 0),
