@@ -1,0 +1,68 @@
+"""GPU parity on fuzzed BAMs (tests/fuzz_fixture.py): the CUDA path through the Python mirror against the oracle, which the
+CPU suite pins to the unmodified reference on the same generators (tests/test_oracle.py::test_cigar_differential_fuzz,
+::test_barcode_differential_fuzz).  Written at the end of round 1 without a GPU: sorts last in the suite."""
+import io
+import os
+
+import pytest
+
+import fuzz_fixture as ff
+from oracle_py import Oracle
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+MODES = {"XS": 0, "RF": 1, "FR": 2}
+
+
+def _kw(args):
+    kw = dict(a=8, m=70, M=500000, s=0, r=".", t="XS")
+    it = iter(args)
+    for k in it:
+        v = next(it)
+        if k in ("-a", "-m", "-M"):
+            kw[k[1]] = int(v) & 0xFFFFFFFF
+        elif k == "-s":
+            kw["s"] = MODES[v]
+        else:
+            kw[k[1]] = v
+    return kw
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_fuzzed_cigars_match_oracle(block, tmp_path):
+    import regtools_b200 as rt
+    for seed in range(block * 10, block * 10 + 10):
+        bam = ff.make_cigar_fuzz_bam(str(tmp_path / "f.bam"), seed)
+        for args in ff.CIGAR_FUZZ_ARGS:
+            k = _kw(args)
+            ex = rt.JunctionsExtractor(bam, k["r"], k["s"], k["t"], k["a"], k["m"], k["M"])
+            ex.identify_junctions_from_BAM()
+            buf = io.StringIO()
+            ex.print_all_junctions(buf)
+            ex.close()
+            o = Oracle(k["a"], k["m"], k["M"], k["s"], k["t"])
+            o.extract_bam(bam, k["r"])
+            assert buf.getvalue() == o.bed12(), (seed, args)
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_fuzzed_barcodes_match_oracle(block, tmp_path, capfd):
+    import regtools_b200 as rt
+    for seed in range(block * 12, block * 12 + 12):
+        bam = ff.make_barcode_fuzz_bam(str(tmp_path / "f.bam"), seed)
+        for args in ff.BARCODE_FUZZ_ARGS:
+            k = _kw(args)
+            ex = rt.JunctionsExtractor(bam, k["r"], k["s"], k["t"], k["a"], k["m"], k["M"])
+            ex.output_barcodes_file_ = os.devnull
+            ex.identify_junctions_from_BAM()
+            bed, bc = io.StringIO(), io.StringIO()
+            ex.print_barcodes(bc)
+            ex.print_all_junctions(bed)
+            n_missing = ex.barcode_stats()[1]
+            ex.close()
+            o = Oracle(k["a"], k["m"], k["M"], k["s"], k["t"], barcodes=True)
+            o.extract_bam(bam, k["r"])
+            assert bed.getvalue() == o.bed12(), (seed, args)
+            assert bc.getvalue() == o.barcodes(), (seed, args)
+            assert n_missing == o.barcodes_missing()
+    capfd.readouterr()

@@ -299,38 +299,16 @@ def test_barcode_oracle_on_a_single_cell_shaped_bam(tmp_path):
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs oracle/_ref/regtools_ref (dev container)")
 @pytest.mark.parametrize("block", range(3))
 def test_barcode_differential_fuzz(block, tmp_path):
-    """-b against the unmodified reference on fuzzed aux layouts: CB as Z or H, before / after / between XS, NH, Z, B and f
-    tags, barcodes of 1-40 characters incl. ':' ',' '-', 1-200 distinct barcodes, reads without CB, XS of type Z (-> '?'),
-    small BGZF blocks.  BED12, barcode file and warning count from the oracle; the product's host feeder must report the same
-    number of untagged alignments and distinct barcodes (rtjx_load_barcodes, no GPU needed)."""
-    import random
-    import struct
+    """-b against the unmodified reference on fuzzed aux layouts (tests/fuzz_fixture.py: CB as Z or H, anywhere among other
+    tags, odd barcode strings, reads without CB, XS of type Z, small BGZF blocks).  BED12, barcode file and warning count from
+    the oracle; the product's host feeder must report the same number of untagged alignments and distinct barcodes
+    (rtjx_load_barcodes, no GPU needed)."""
     import subprocess
-    import bamio
+    import fuzz_fixture as ff
     import regtools_b200 as rt
-    root = os.path.dirname(os.path.dirname(GOLD))
     for seed in range(block * 12, block * 12 + 12):
-        rnd = random.Random(5000 + seed)
-        bcs = [("".join(rnd.choice("ACGT:,-_") for _ in range(rnd.choice([1, 4, 16, 40])))).encode() for _ in range(rnd.choice([1, 3, 20, 200]))]
-        loci = [(rnd.choice([0, 1, 2]), rnd.randrange(1000, 50000, 1000),
-                 rnd.choice(["50M100N50M", "20M300N30M500N50M", "5S45M1000N50M", "50M69N50M", "3M200N97M", "50M2D50M", "100M"]))
-                for _ in range(rnd.randrange(1, 8))]
-        reads = []
-        for _ in range(rnd.choice([5, 50, 400])):
-            tid, pos, cg = rnd.choice(loci)
-            xs = rnd.choice([b"XSA+", b"XSA-", b"XSA?", b"", b"XSZ+\0"])
-            r = rnd.random()
-            cb = b"" if r < 0.1 else (b"CBH" if r < 0.2 else b"CBZ") + rnd.choice(bcs) + b"\0"
-            other = rnd.choice([b"", b"NHC\x01", b"RGZx y\0", b"ZBBc" + struct.pack("<I", 2) + b"\x01\x02", b"XXf" + struct.pack("<f", 1.5)])
-            parts = [xs, cb, other]
-            rnd.shuffle(parts)
-            reads.append((tid, pos, cg, rnd.choice([0, 16, 99, 147]), b"".join(parts)))
-        reads.sort(key=lambda x: (x[0], x[1]))
-        recs = [bamio.record(t, p, c, f, 60, a, name=b"q%05d" % i) for i, (t, p, c, f, a) in enumerate(reads)]
-        bam = str(tmp_path / "f.bam")
-        bamio.write_bam(bam, [("1", 100000), ("10", 100000), ("2", 100000)], recs, block_size=rnd.choice([0x200, 0x4000, 0xff00]))
-        subprocess.check_call([os.path.join(root, "tools", "bamgen"), "index", bam], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-        for args in (["-s", "XS"], ["-s", "RF", "-a", "3"], ["-s", "XS", "-r", "10"]):
+        bam = ff.make_barcode_fuzz_bam(str(tmp_path / "f.bam"), seed)
+        for args in ff.BARCODE_FUZZ_ARGS:
             p = subprocess.run([REF_BIN, "junctions", "extract"] + args + ["-b", str(tmp_path / "r.bc"), "-o", str(tmp_path / "r.bed"), bam],
                                capture_output=True, text=True)
             assert p.returncode == 0, p.stderr[-300:]
@@ -351,33 +329,15 @@ def test_barcode_differential_fuzz(block, tmp_path):
 @pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs oracle/_ref/regtools_ref (dev container)")
 @pytest.mark.parametrize("block", range(3))
 def test_cigar_differential_fuzz(block, tmp_path):
-    """Random CIGARs against the unmodified reference: every op incl. P / = / X / H, zero-length ops, N lengths on both QC
-    bounds, up to 20 ops, N first or last, flags incl. unmapped-with-CIGAR, XS of type A / C / absent / twice, tag NH as the
-    strand tag, -a/-m/-M corners, a region.  The index comes from the reference's own htslib (oracle/_ref/ref_index)."""
-    import random
+    """Random CIGARs against the unmodified reference (tests/fuzz_fixture.py: every op incl. P / = / X / H, zero-length ops, N
+    lengths on both QC bounds, up to 20 ops, flags incl. unmapped-with-CIGAR, XS of type A / C / absent / twice; tag NH as the
+    strand tag, -a/-m/-M corners, a region).  The index comes from the reference's own htslib (oracle/_ref/ref_index)."""
     import subprocess
-    import bamio
+    import fuzz_fixture as ff
     root = os.path.dirname(os.path.dirname(GOLD))
     for seed in range(block * 10, block * 10 + 10):
-        rnd = random.Random(9000 + seed)
-        reads = []
-        for _ in range(rnd.choice([3, 30, 300])):
-            cig = []
-            for _k in range(rnd.choice([1, 2, 3, 3, 4, 5, 8, 20])):
-                op = rnd.choice("MMMMNNNIDSH=XP")
-                ln = rnd.choice([0, 1, 5, 50, 69, 70, 100, 500000, 500001]) if op == "N" else rnd.choice([0, 1, 3, 7, 8, 20, 50])
-                cig.append((ln << 4) | bamio.OPS.index(op))
-            reads.append((rnd.choice([0, 0, 1, 2]), rnd.randrange(0, 3000), cig, rnd.choice([0, 16, 4, 99, 147, 83, 163, 256, 1024, 2048 + 16]),
-                          rnd.choice([0, 1, 60, 255]), rnd.choice([b"XSA+", b"XSA-", b"XSA.", b"", b"XSC\x2b", b"NHC\x01XSA-", b"XSA+XSA-"])))
-        reads.sort(key=lambda x: (x[0], x[1]))
-        recs = [bamio.record(t, p, c, f, q, a, name=b"q%05d" % i, l_seq=10) for i, (t, p, c, f, q, a) in enumerate(reads)]
-        bam = str(tmp_path / "f.bam")
-        bamio.write_bam(bam, [("1", 20000000), ("10", 20000000), ("2", 20000000)], recs, block_size=rnd.choice([0x300, 0xff00]))
-        if os.path.exists(bam + ".bai"):
-            os.remove(bam + ".bai")
-        subprocess.check_call([os.path.join(root, "oracle", "_ref", "ref_index"), bam])
-        for args in (["-s", "XS"], ["-s", "RF", "-a", "0", "-m", "0", "-M", "4000000000"], ["-s", "FR", "-a", "1", "-m", "1"],
-                     ["-s", "XS", "-r", "1:100-2000"], ["-s", "XS", "-t", "NH"]):
+        bam = ff.make_cigar_fuzz_bam(str(tmp_path / "f.bam"), seed)
+        for args in ff.CIGAR_FUZZ_ARGS:
             rc, out = ref_extract(bam, args)
             o = run_oracle(bam, args)
             assert rc == 0 and o.bed12() == out, (seed, args)

@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 O=gpurun_out
 {
-  echo "== new GPU test modules"; timeout 600 python -m pytest tests/test_gpu_zz_barcodes.py tests/test_gpu_zzz_annotate.py tests/test_gpu_zzzz_scan_gather.py -q 2>&1 | tail -25
+  echo "== new GPU test modules"; timeout 600 python -m pytest tests/test_gpu_zz_barcodes.py tests/test_gpu_zzz_annotate.py tests/test_gpu_zzzz_scan_gather.py tests/test_gpu_zzzzz_fuzz.py -q 2>&1 | tail -25
   echo "== cigar_scan A/B: production, launch-bounded configurations 8-10, gather variant 7 (DESIGN 9.1)"
   AB_CASES=5:0:0,5:8:0,5:9:0,5:10:0,7:0:0,7:1:0,7:2:0,7:3:0,7:4:0,5:0:0 timeout 600 python tools/ab_scan.py > $O/ab_scan_r2.json 2> $O/ab_scan_r2.log; tail -12 $O/ab_scan_r2.log
   echo "== annotate side bench (2M junctions, 8 x 30 Mb)"; timeout 900 python tools/bench_annotate.py --steps 3 --warmup 1 2>&1 | tail -3
