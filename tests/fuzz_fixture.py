@@ -72,3 +72,40 @@ def make_barcode_fuzz_bam(path, seed):
 
 
 BARCODE_FUZZ_ARGS = (["-s", "XS"], ["-s", "RF", "-a", "3"], ["-s", "XS", "-r", "10"])
+
+
+def make_motif_fuzz_case(d, seed):
+    """Intron-motif strand mode: a genome made of the six motif dimers (so GT-AG / CT-AC ... hits are common) with some lower
+    case and N, contig 2 shorter than its junctions (clipped fetch), contig 10 sometimes absent from the FASTA (the reference
+    throws), alignments with 1-3 junctions (the reused-Junction reverse-complement quirk).  -> (bam, fasta)"""
+    rnd = random.Random(4000 + seed)
+
+    def genome(n):
+        return "".join(rnd.choice(["GT", "AG", "GC", "AT", "AC", "CT", "gt", "NN"] if rnd.random() < 0.1 else ["GT", "AG", "GC", "AT", "AC", "CT"])
+                       for _ in range(n // 2))
+    contigs = [("1", 6000), ("10", 6000), ("2", 6000)]
+    fa = os.path.join(d, "g.fa")
+    drop10 = rnd.random() < 0.1
+    with open(fa, "w") as f:
+        for name, n in contigs:
+            if name == "10" and drop10:
+                continue
+            s = genome(n if name != "2" else 1500)
+            f.write(f">{name} d\n" + "\n".join(s[i:i + 50] for i in range(0, len(s), 50)) + "\n")
+    if os.path.exists(fa + ".fai"):
+        os.remove(fa + ".fai")
+    reads = []
+    for _ in range(rnd.choice([5, 60, 300])):
+        cig = [(rnd.choice([10, 11, 20, 21]) << 4) | 0]
+        for _k in range(rnd.choice([1, 1, 2, 3])):
+            cig.append((rnd.choice([70, 71, 100, 101, 200]) << 4) | 3)
+            cig.append((rnd.choice([10, 11, 30, 31]) << 4) | 0)
+        reads.append((rnd.choice([0, 1, 2]), rnd.randrange(0, 3000), cig, rnd.choice([0, 16, 99, 147]), 60, rnd.choice([b"XSA+", b"XSA-", b"", b"XSA?"])))
+    reads.sort(key=lambda x: (x[0], x[1]))
+    recs = [bamio.record(t, p, c, f, q, a, name=b"q%05d" % i, l_seq=10) for i, (t, p, c, f, q, a) in enumerate(reads)]
+    bam = os.path.join(d, "f.bam")
+    bamio.write_bam(bam, contigs, recs)
+    return _index(bam), fa
+
+
+MOTIF_FUZZ_ARGS = (["-s", "XS"], ["-s", "RF"], ["-s", "intron-motif"], ["-s", "FR", "-a", "0"])

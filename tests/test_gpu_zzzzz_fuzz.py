@@ -66,3 +66,32 @@ def test_fuzzed_barcodes_match_oracle(block, tmp_path, capfd):
             assert bc.getvalue() == o.barcodes(), (seed, args)
             assert n_missing == o.barcodes_missing()
     capfd.readouterr()
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_fuzzed_motif_genomes_match_oracle(block, tmp_path):
+    """Intron-motif strand mode on fuzzed genomes; a FASTA without contig 10 must raise the reference's text (which junction
+    is named first is not defined on the GPU, so only the prefix up to the contig is compared)."""
+    import regtools_b200 as rt
+    for seed in range(block * 10, block * 10 + 10):
+        bam, fa = ff.make_motif_fuzz_case(str(tmp_path), seed)
+        for args in ff.MOTIF_FUZZ_ARGS:
+            k = _kw(args) if args[1] != "intron-motif" else dict(_kw(["-s", "FR"] + args[2:]), s=3)
+            o = Oracle(k["a"], k["m"], k["M"], k["s"], k["t"], fasta=fa)
+            try:
+                o.extract_bam(bam, k["r"])
+                failed = None
+            except RuntimeError as e:
+                failed = str(e)
+            ex = rt.JunctionsExtractor(bam, k["r"], k["s"], k["t"], k["a"], k["m"], k["M"], fa)
+            if failed:
+                with pytest.raises(RuntimeError) as err:
+                    ex.identify_junctions_from_BAM()
+                assert str(err.value).startswith(failed.split(":")[0] + ":"), (seed, args)
+                ex.close()
+                continue
+            ex.identify_junctions_from_BAM()
+            buf = io.StringIO()
+            ex.print_all_junctions(buf)
+            ex.close()
+            assert buf.getvalue() == o.bed12(), (seed, args)

@@ -345,3 +345,22 @@ def test_cigar_differential_fuzz(block, tmp_path):
         subprocess.check_call([os.path.join(root, "tools", "bamgen"), "index", bam], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         rc, out = ref_extract(bam, ["-s", "XS", "-r", "1:100-2000"])
         assert rc == 0 and out == run_oracle(bam, ["-s", "XS", "-r", "1:100-2000"]).bed12()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs oracle/_ref/regtools_ref (dev container)")
+@pytest.mark.parametrize("block", range(3))
+def test_motif_differential_fuzz(block, tmp_path):
+    """Intron-motif strand mode against the unmodified reference on fuzzed genomes (tests/fuzz_fixture.py): BED12 bytes, and
+    where the FASTA lacks a contig the same runtime_error text and exit code 1."""
+    import subprocess
+    import fuzz_fixture as ff
+    for seed in range(block * 10, block * 10 + 10):
+        bam, fa = ff.make_motif_fuzz_case(str(tmp_path), seed)
+        for args in ff.MOTIF_FUZZ_ARGS:
+            p = subprocess.run([REF_BIN, "junctions", "extract"] + args + ["-o", str(tmp_path / "r.bed"), bam, fa], capture_output=True, text=True)
+            o = run_oracle(bam, args, fasta=fa, check=False)
+            failed = getattr(o, "failed", None)
+            if failed:
+                assert p.returncode == 1 and failed.strip() in p.stderr, (seed, args)
+            else:
+                assert p.returncode == 0 and o.bed12() == open(tmp_path / "r.bed").read(), (seed, args)
