@@ -421,3 +421,19 @@ def test_fasta_loader_matches_a_sequential_reading(tmp_path):
         for line, (n, s) in zip(got, want):
             f = line.split("\t")
             assert f[0] == n.decode() and int(f[1]) == len(s) and int(f[2], 16) == _fnv(s), (name, n)
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_feeder_on_fuzzed_bams(block, tmp_path):
+    """The product's host feeder on the fuzzed BAMs of tests/fuzz_fixture.py (random CIGARs incl. zero-length and P ops,
+    unmapped-with-CIGAR flags, strand tags of several types, tiny BGZF blocks; aux layouts with Z / H / B / f tags): its SoA
+    batch pushed through the oracle's walk must equal the oracle's own reader — which the CPU suite pins to the unmodified
+    reference on the same generators.  Whole file, a region, and NH as the strand tag; 1 and 3 inflate threads."""
+    import fuzz_fixture as ff
+    for seed in range(block * 8, block * 8 + 8):
+        bam = ff.make_cigar_fuzz_bam(str(tmp_path / "c.bam"), seed)
+        for region, strandness, tag, threads in ((".", 0, "XS", 3), ("1:100-2000", 0, "XS", 1), (".", 1, "XS", 1), (".", 0, "NH", 3), ("2", 2, "XS", 3)):
+            feeder_vs_oracle(bam, region, strandness, tag, threads)
+        bam = ff.make_barcode_fuzz_bam(str(tmp_path / "b.bam"), seed)
+        for region in (".", "10"):
+            feeder_vs_oracle(bam, region, 0, "XS", 2)
