@@ -437,3 +437,33 @@ def test_feeder_on_fuzzed_bams(block, tmp_path):
         bam = ff.make_barcode_fuzz_bam(str(tmp_path / "b.bam"), seed)
         for region in (".", "10"):
             feeder_vs_oracle(bam, region, 0, "XS", 2)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "regtools_ref")), reason="needs oracle/_ref/regtools_ref (dev container)")
+def test_odd_region_strings_three_way():
+    """hts_parse_reg / hts_parse_decimal corner cases (hts.c:1833-1922): exit code and BED12 of the unmodified reference, the
+    oracle's reader and the product's feeder (+ oracle walk) must agree on every spelling."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "regtools_ref")
+    regions = ["1", "1:", "1:5000", "1:5000-", "1:-6200", "1:5,000-6,200", "1:5000-6200", "1:6200-5000", "1:0-100", "1:1e3-9e3", "1:1.5e3-9e3",
+               "1:5000-6200 ", "10", "10:1", "2:1-1", "2:0", "x", "1:abc", "1:5000-abc", ":", "", "1:5000-6200:7", "1:-", "1:5000--6200", "01",
+               "1:+5000-6200", "1:5000-6200k", "1:5k-7k", "1:0.005M-0.007M", "1:1-3G", "*", "."]
+    for reg in regions:
+        p = subprocess.run([ref, "junctions", "extract", "-s", "XS", "-a", "0", "-m", "0", "-r", reg, KAT], capture_output=True, text=True)
+        o = Oracle(0, 0, 500000, 0)
+        try:
+            o.extract_bam(KAT, reg)
+            orc, ob = 0, o.bed12()
+        except RuntimeError:
+            orc, ob = 1, None
+        try:
+            ex = rt().JunctionsExtractor(KAT, reg, 0, "XS", 0, 0, 500000, device=-1)
+            arrs = ex.load_batch()
+            names = ex.contig_names()
+            ex.close()
+            a = Oracle(0, 0, 500000, 0, contigs=names)
+            a.batch(*arrs)
+            prc, pb = 0, a.bed12()
+        except RuntimeError:
+            prc, pb = 1, None
+        assert p.returncode == orc == prc, reg
+        assert orc == 1 or p.stdout == ob == pb, reg
