@@ -95,3 +95,27 @@ def test_fuzzed_motif_genomes_match_oracle(block, tmp_path):
             ex.print_all_junctions(buf)
             ex.close()
             assert buf.getvalue() == o.bed12(), (seed, args)
+
+
+@pytest.mark.parametrize("block", range(2))
+def test_fuzzed_variant_regions_match_oracle(block, tmp_path):
+    """rtjx_run_regions (all regions of a BAM in one pass) on fuzzed BAMs and regions: region i must equal what the oracle's
+    8-arg-ctor path (pinned to `regtools_ref ctor` by tests/test_oracle.py::test_ctor_differential_fuzz) gives for it."""
+    import numpy as np
+    import regtools_b200 as rt
+    from test_oracle import ctor_fuzz_queries
+    for seed in range(block * 10, block * 10 + 10):
+        bam = ff.make_cigar_fuzz_bam(str(tmp_path / "f.bam"), seed)
+        queries = ctor_fuzz_queries(seed)
+        for s, anchor, M in sorted({(q[1], q[2], q[3]) for q in queries}):
+            regs = [q[0] for q in queries if (q[1], q[2], q[3]) == (s, anchor, M)]
+            ex = rt.JunctionsExtractor.from_region(bam, ".", s, "XS", anchor, 70, M & 0xFFFFFFFF)
+            tables = ex.identify_junctions_in_regions(regs)
+            ex.close()
+            for reg, got in zip(regs, tables):
+                o = Oracle(anchor, anchor, M & 0xFFFFFFFF, s)
+                o.extract_bam(bam, reg)
+                want = o.table()
+                assert len(got) == len(want), (seed, reg)
+                for f in ("tid", "start", "end", "thick_start", "thick_end", "read_count", "name_index", "strand", "left_ok", "right_ok"):
+                    assert np.array_equal(got[f], want[f]), (seed, reg, f)

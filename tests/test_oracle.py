@@ -364,3 +364,36 @@ def test_motif_differential_fuzz(block, tmp_path):
                 assert p.returncode == 1 and failed.strip() in p.stderr, (seed, args)
             else:
                 assert p.returncode == 0 and o.bed12() == open(tmp_path / "r.bed").read(), (seed, args)
+
+
+def ctor_rows(o):
+    """get_all_junctions() of the oracle in the column layout of `regtools_ref ctor` (oracle/ref_main.cc)."""
+    return "".join(f"{o.l.jxo_contig(o.h, int(j['tid'])).decode()}\t{j['thick_start']}\t{j['thick_end']}\tJUNC{j['name_index']:08d}\t"
+                   f"{j['read_count']}\t{chr(j['strand'])}\t{j['start']}\t{j['end']}\t{j['left_ok']}\t{j['right_ok']}\n" for j in o.table())
+
+
+def ctor_fuzz_queries(seed):
+    import random
+    rnd = random.Random(seed)
+    out = []
+    for _ in range(6):
+        a = rnd.randrange(1, 4000)
+        out.append((f"{rnd.choice(['1', '10', '2'])}:{a}-{a + rnd.choice([1, 50, 3000, 600000])}", rnd.choice([0, 1, 2]), rnd.choice([0, 1, 8, 30]),
+                    rnd.choice([500000, 100, 4000000000])))
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="needs oracle/_ref/regtools_ref (dev container)")
+@pytest.mark.parametrize("block", range(2))
+def test_ctor_differential_fuzz(block, tmp_path):
+    """The second caller's path (8-arg ctor + get_all_junctions, cis_splice_effects_identifier.cc:288-290; min_intron :=
+    min_anchor, junctions_extractor.h:199-200) on fuzzed BAMs, regions and parameters, against `regtools_ref ctor`."""
+    import subprocess
+    import fuzz_fixture as ff
+    for seed in range(block * 10, block * 10 + 10):
+        bam = ff.make_cigar_fuzz_bam(str(tmp_path / "f.bam"), seed)
+        for reg, s, anchor, M in ctor_fuzz_queries(seed):
+            p = subprocess.run([REF_BIN, "ctor", bam, reg, str(s), "XS", str(anchor), "70", str(M)], capture_output=True, text=True)
+            o = Oracle(anchor, anchor, M & 0xFFFFFFFF, s)
+            o.extract_bam(bam, reg)
+            assert p.returncode == 0 and ctor_rows(o) == p.stdout, (seed, reg, s, anchor, M)
