@@ -135,7 +135,7 @@ def time_reference_all_cores(bam, contig_len, total_reads, contig="chr1"):
     """SURVEY 8(d)'s courtesy figure: the reference has no threading, so "all host cores" = one reference process per window
     of the contig (`-r chr1:a-b`), all started together, wall = the slowest.  NOT output-equivalent (names restart in every
     process, alignments across a window edge are seen twice) — a throughput figure only, labelled as such."""
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 64)
     exe = REF_BIN if os.path.exists(REF_BIN) else ORACLE_BIN
     step = -(-contig_len // cores)
     procs = []
@@ -147,6 +147,11 @@ def time_reference_all_cores(bam, contig_len, total_reads, contig="chr1"):
         procs.append(subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
     rcs = [p.wait() for p in procs]
     dt = time.perf_counter() - t0
+    for i in range(cores):
+        try:
+            os.remove(os.path.join(SCRATCH, f"rtjx_ref_{os.getpid()}_{i}.bed"))
+        except OSError:
+            pass
     if any(rcs):
         return None
     return {"value": total_reads / dt, "unit": "reads/s", "cores": cores, "seconds": dt,
