@@ -83,3 +83,39 @@ def test_compute_without_gpu_fails_loudly():
     host = rt.JunctionsExtractor(device=-1)
     with pytest.raises(RuntimeError, match="host-only"):
         host.add_junction(rt.Junction("chr1", 1, 100, 0, 120, "+"))
+
+
+def test_cli_option_handling_needs_no_gpu(tmp_path):
+    """The C++ front-end (regtools_b200/regtools): usage / help / argument errors of both sub-commands have the reference's
+    exit codes and texts (junctions_main.cc:45-107, junctions_extractor.cc:42-143, junctions_annotator.cc:405-456) and never
+    touch the device; a compute request on a box without a GPU fails loudly with exit code 1."""
+    import subprocess
+    exe = os.path.join(ROOT, "regtools_b200", "regtools")
+    run = lambda *a: subprocess.run([exe] + list(a), capture_output=True, text=True)
+    p = run()
+    assert p.returncode == 0 and "Usage:\t\tregtools <command> [options]" in p.stderr and "Version:\t1.0.0" in p.stderr
+    p = run("junctions")
+    assert p.returncode == 0 and "extract\t\tIdentify exon-exon junctions from alignments." in p.stdout and "annotate\tAnnotate the junctions." in p.stdout
+    p = run("junctions", "extract", "-h")
+    assert p.returncode == 0 and "Usage:\t\tregtools junctions extract [options] indexed_alignments.bam" in p.stderr
+    p = run("junctions", "extract", "x.bam")
+    assert p.returncode == 1 and "Please supply strandness mode" in p.stderr
+    p = run("junctions", "annotate", "-h")
+    assert p.returncode == 0 and "Usage:\t\tregtools junctions annotate [options] junctions.bed ref.fa annotations.gtf" in p.stderr
+    assert "-S include single exon genes" in p.stderr
+    p = run("junctions", "annotate", "a.bed", "b.fa")
+    assert p.returncode == 1 and "Error parsing inputs!(2)" in p.stderr
+    p = run("junctions", "annotate", "-x", "a.bed", "b.fa", "c.gtf")
+    assert p.returncode == 1 and "Error parsing inputs!(1)" in p.stderr
+    p = run("junctions", "annotate", "a.bed", "b.fa", str(tmp_path / "missing.gtf"))
+    assert p.returncode == 1 and "Unable to open GTF file." in p.stderr and "Reference: b.fa" in p.stderr and "Skipping single exon genes." in p.stderr
+    p = run("variants", "annotate")
+    assert p.returncode == 1 and "not built here" in p.stderr
+    import torch
+    if not torch.cuda.is_available():
+        gold = os.path.join(ROOT, "tests", "golden", "annotate")
+        p = run("junctions", "annotate", "-o", str(tmp_path / "o.tsv"), os.path.join(gold, "hcc1395.bed"), os.path.join(gold, "hcc1395.fa"),
+                os.path.join(gold, "hcc1395.gtf"))
+        assert p.returncode == 1 and "no CPU fallback" in p.stderr and not os.path.exists(tmp_path / "o.tsv")
+        p = run("junctions", "extract", "-s", "XS", os.path.join(ROOT, "tests", "golden", "hcc1395", "test_hcc1395.bam"))
+        assert p.returncode == 1 and "no CPU fallback" in p.stderr and p.stdout == ""
