@@ -64,7 +64,11 @@ static int junctions_annotate(int argc, char* argv[]) {       // junctions_main.
         cerr << e.what() << endl;
         return 0;
     } catch (const runtime_error& e) {
-        cerr << e.what() << endl;
+        // two GtfParser failures are `cerr << text; exit(1)` without a line end (gtf_parser.cc:52-55,202-206), the rest are
+        // runtime_errors printed with endl by the driver (junctions_main.cc:87-90)
+        const string msg(e.what());
+        if (msg.find("\nUnable to open GTF file.") == 0 || msg.find("Undefined strand for exon") == 0) cerr << msg;
+        else cerr << msg << endl;
         return 1;
     }
     return 0;
