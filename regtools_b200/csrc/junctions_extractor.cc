@@ -32,7 +32,9 @@ JunctionsExtractor::~JunctionsExtractor() { if (h_) rtjx_destroy(h_); }
 void JunctionsExtractor::check(int rc) {
     if (rc >= 0) return;
     switch (rc) {
-    case RTJX_E_OPEN_BAM: throw runtime_error("Unable to open BAM/SAM file.\n\n");
+    case RTJX_E_OPEN_BAM:
+        cerr << "[E::hts_open_format] fail to open file '" << bam_ << "'" << endl;      // htslib's own line (hts.c hts_open_format)
+        throw runtime_error("Unable to open BAM/SAM file.\n\n");
     case RTJX_E_OPEN_INDEX: throw runtime_error("Unable to open BAM/SAM index. Make sure alignments are indexed\n\n");
     case RTJX_E_REGION: throw runtime_error("Unable to iterate to region within BAM.\n\n");
     default: {

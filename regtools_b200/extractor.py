@@ -132,6 +132,8 @@ class JunctionsExtractor:
         if rc >= 0:
             return rc
         msg = _MESSAGES.get(rc) or (L.lib.rtjx_last_error(self._h) or b"").decode() or L.lib.rtjx_strerror(rc).decode()
+        if rc == L.RTJX_E_OPEN_BAM:                  # htslib's own stderr line before the reference's exception (hts_open_format)
+            sys.stderr.write(f"[E::hts_open_format] fail to open file '{self.bam_}'\n")
         raise RuntimeError(msg)
 
     def close(self):
