@@ -119,3 +119,23 @@ def test_cli_option_handling_needs_no_gpu(tmp_path):
         assert p.returncode == 1 and "no CPU fallback" in p.stderr and not os.path.exists(tmp_path / "o.tsv")
         p = run("junctions", "extract", "-s", "XS", os.path.join(ROOT, "tests", "golden", "hcc1395", "test_hcc1395.bam"))
         assert p.returncode == 1 and "no CPU fallback" in p.stderr and p.stdout == ""
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "regtools_ref_annotate")), reason="needs oracle/_ref (dev container)")
+def test_cli_texts_equal_the_reference(tmp_path):
+    """Exit code, stdout and stderr (after our three banner lines, which the reference's real CLI prints too but the test
+    drivers in oracle/ do not) of the option / error paths that need no device, byte for byte against the unmodified
+    reference classes."""
+    import subprocess
+    exe = os.path.join(ROOT, "regtools_b200", "regtools")
+    bam = os.path.join(ROOT, "tests", "golden", "hcc1395", "test_hcc1395.bam")
+    cases = [("regtools_ref", "extract", a) for a in (["-h"], ["x.bam"], ["-s", "XS"], ["-s", "bogus", bam], ["-s", "XS", "nonexist.bam"],
+                                                       ["-s", "intron-motif", bam], ["-q", "-s", "XS", bam], ["-s", "XS", "-o", "o", "-r", "1:2-3", "-t", "ZS", "-b", "b", "nonexist.bam"])]
+    cases += [("regtools_ref_annotate", "annotate", a) for a in (["-h"], ["a.bed", "b.fa"], ["-x", "a.bed", "b.fa", "c.gtf"], ["a.bed", "b.fa", "/nonexistent.gtf"],
+                                                                 ["-S", "-o", "o.tsv", "a.bed", "b.fa", "/nonexistent.gtf"], ["a", "b", "c", "d"])]
+    for ref_bin, sub, args in cases:
+        r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", ref_bin), "junctions", sub] + args, capture_output=True, cwd=tmp_path)
+        o = subprocess.run([exe, "junctions", sub] + args, capture_output=True, cwd=tmp_path)
+        assert o.stderr.startswith(b"\nProgram:\tregtools\nVersion:\t1.0.0\n")
+        ours_err = b"\n".join(o.stderr.split(b"\n")[3:])
+        assert (r.returncode, r.stdout, r.stderr) == (o.returncode, o.stdout, ours_err), (sub, args)
