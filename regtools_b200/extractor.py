@@ -156,7 +156,8 @@ class JunctionsExtractor:
         """parse_options (junctions_extractor.cc:42-122). argv[0] is the sub-command name."""
         try:
             opts, rest = getopt.getopt(list(argv[1:]), "ha:m:M:o:r:t:s:b:")
-        except getopt.GetoptError:
+        except getopt.GetoptError as e:
+            _glibc_getopt_line(argv[0], e)
             self.usage()
             raise RuntimeError("Error parsing inputs!(1)\n\n")
         atoi = _atoi
@@ -504,7 +505,8 @@ class JunctionsAnnotator:
         """argv[0] is the sub-command name, as in the reference's getopt call."""
         try:
             opts, args = getopt.getopt(list(argv[1:]), "So:h")
-        except getopt.GetoptError:
+        except getopt.GetoptError as e:
+            _glibc_getopt_line(argv[0], e)
             self.usage()
             raise RuntimeError("Error parsing inputs!(1)\n\n")
         for o, a in opts:
@@ -552,6 +554,12 @@ class JunctionsAnnotator:
         return int(n.value)
 
 
+def _glibc_getopt_line(prog: str, e: "getopt.GetoptError") -> None:
+    """The line glibc's getopt() itself writes to stderr before the reference's default: branch runs."""
+    what = "option requires an argument" if "requires argument" in e.msg else "invalid option"
+    sys.stderr.write(f"{prog}: {what} -- '{e.opt}'\n")
+
+
 def junctions_annotate(argv: Sequence[str], device: int = 0) -> int:
     """junctions_annotate (src/junctions/junctions_main.cc:61-92): exit code 0 / 1."""
     anno = JunctionsAnnotator(device=device)
@@ -563,7 +571,10 @@ def junctions_annotate(argv: Sequence[str], device: int = 0) -> int:
         sys.stderr.write(str(e) + "\n")
         return 0
     except RuntimeError as e:
-        sys.stderr.write(str(e) + "\n")
+        msg = str(e)
+        # two GtfParser failures are `cerr << text; exit(1)` without a line end (gtf_parser.cc:52-55,202-206)
+        bare = msg.startswith("\nUnable to open GTF file.") or msg.startswith("Undefined strand for exon")
+        sys.stderr.write(msg if bare else msg + "\n")
         return 1
     return 0
 

@@ -139,3 +139,22 @@ def test_cli_texts_equal_the_reference(tmp_path):
         assert o.stderr.startswith(b"\nProgram:\tregtools\nVersion:\t1.0.0\n")
         ours_err = b"\n".join(o.stderr.split(b"\n")[3:])
         assert (r.returncode, r.stdout, r.stderr) == (o.returncode, o.stdout, ours_err), (sub, args)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "regtools_ref_annotate")), reason="needs oracle/_ref (dev container)")
+def test_python_mirror_texts_equal_the_reference(tmp_path):
+    """regtools_b200.junctions_extract / junctions_annotate on the same option / error paths: exit code, stdout, stderr."""
+    import subprocess
+    import sys
+    bam = os.path.join(ROOT, "tests", "golden", "hcc1395", "test_hcc1395.bam")
+    runner = "import sys, regtools_b200 as rt\nsys.exit(getattr(rt, 'junctions_' + sys.argv[1])([sys.argv[1]] + sys.argv[2:]))"
+    cases = [("regtools_ref", "extract", a) for a in (["-h"], ["x.bam"], ["-s", "XS"], ["-s", "bogus", bam], ["-s", "XS", "nonexist.bam"],
+                                                       ["-s", "intron-motif", bam], ["-q", "-s", "XS", bam], ["-s", "XS", "-o"],
+                                                       ["-s", "XS", "-o", "o", "-r", "1:2-3", "-t", "ZS", "-b", "b", "-a", "3", "-m", "4", "-M", "5", "nonexist.bam"])]
+    cases += [("regtools_ref_annotate", "annotate", a) for a in (["-h"], ["a.bed", "b.fa"], ["-x", "a.bed", "b.fa", "c.gtf"], ["a.bed", "b.fa", "/nonexistent.gtf"],
+                                                                 ["-S", "-o", "o.tsv", "a.bed", "b.fa", "/nonexistent.gtf"], ["-o"], ["a", "b", "c", "d"])]
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    for ref_bin, sub, args in cases:
+        r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", ref_bin), "junctions", sub] + args, capture_output=True, cwd=tmp_path)
+        o = subprocess.run([sys.executable, "-c", runner, sub] + args, capture_output=True, cwd=tmp_path, env=env)
+        assert (r.returncode, r.stdout, r.stderr) == (o.returncode, o.stdout, o.stderr), (sub, args)
