@@ -282,6 +282,7 @@ int main(int argc, char** argv) {
         // only holds the header so far is never flushed — the file stays empty)
         while (std::getline(bf, line)) {
             if (header && (line.find("#") == 0 || line.find("browser") == 0 || line.find("track") == 0)) continue;   // GetHeader
+            if (header && bf.eof()) break;         // GetHeader's own getline hit EOF: the stream is not good() for GetNextBed (bedFile.cpp:208-214)
             header = false;
             if (!line.empty() && line[line.size() - 1] == '\r') line.resize(line.size() - 1);
             vector<string> f = split(line, '\t');

@@ -186,6 +186,9 @@ Status read_junctions(const std::string& path, JunctionLines* out) {
         size_t len = (size_t)(nl - line);
         pos += len + 1;
         if (header && is_header(line, len)) continue;                         // GetHeader
+        // GetHeader reads the first data line itself; if that getline hit the end of the file (no trailing newline) the
+        // stream is no longer good() and GetNextBed returns at once: a lone unterminated data line is never seen
+        if (header && pos > total) break;
         header = false;
         if (len && line[len - 1] == '\r') --len;
         line[len] = '\0';

@@ -171,3 +171,23 @@ def test_wide_coordinates_reach_every_bin_level(env):
             rows.append("\t".join(map(str, [rnd.choice(["1", "1", "2"]), s, e, f"J{k}", k, rnd.choice("+-"), s, e, "255,0,0", 2, f"{b0},{b1}", "0,1"])))
         ref, ora, emu = _three_way(d, fa, "\n".join(lines) + "\n", "\n".join(rows) + "\n")
         assert ref[0][0] == 0 and ref == ora and ref == emu, f"seed {seed}, scale {scale}"
+
+
+def test_degenerate_junction_files(env):
+    """Empty file, blank first line, header only, a lone data line without a trailing newline (GetHeader's own getline hits EOF
+    and GetNextBed never runs: zero junctions), trailing tab, space-separated, empty first block size, non-integer and negative
+    coordinates, padded integers."""
+    d, fa = env
+    gold = os.path.join(ROOT, "tests", "golden", "annotate")
+    gtf = open(os.path.join(gold, "hcc1395.gtf")).read()
+    fa = os.path.join(gold, "hcc1395.fa")
+    j = "22\t14006\t38288\tJ\t1\t+\t14006\t38288\t255,0,0\t2\t97,97\t0,1"
+    cases = ["", "\n", "#only header\n", "track x\n" + j, j + "\t\n", "22 14006 38288\n", j.replace("97,97", ",97") + "\n",
+             j.replace("14006\t38288\tJ", "1e3\t38288\tJ") + "\n", j.replace("14006\t38288\tJ", "-5\t38288\tJ") + "\n",
+             j.replace("14006\t38288\tJ", " 14006\t38288 \tJ") + "\n", j, j + "\n" + j, j + "\n\n" + j + "\n", j + "\r\n" + j + "\r\n"]
+    n_done = 0
+    for bed in cases:
+        ref, ora, emu = _three_way(d, fa, gtf, bed)
+        assert ref == ora and ref == emu, repr(bed[:40])
+        n_done += ref[0][0] == 0
+    assert n_done >= 9
