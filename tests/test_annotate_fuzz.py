@@ -191,3 +191,22 @@ def test_degenerate_junction_files(env):
         assert ref == ora and ref == emu, repr(bed[:40])
         n_done += ref[0][0] == 0
     assert n_done >= 9
+
+
+def test_degenerate_annotation_files(env):
+    """GTF corner cases on the reference's own test data: empty, comments only, CRLF, no trailing newline, no exon lines, no
+    transcript_id / gene_name attributes, a 10th column (format error), doubled or missing spaces between attributes."""
+    d, _ = env
+    gold = os.path.join(ROOT, "tests", "golden", "annotate")
+    fa = os.path.join(gold, "hcc1395.fa")
+    gtf = open(os.path.join(gold, "hcc1395.gtf")).read()
+    bed = open(os.path.join(gold, "hcc1395.bed")).read()
+    cases = {"empty": "", "comments": "#a\n#b\n", "crlf": gtf.replace("\n", "\r\n"), "no_trailing_nl": gtf.rstrip("\n"),
+             "only_cds": "\n".join(l for l in gtf.splitlines() if "\texon\t" not in l) + "\n",
+             "no_tid": gtf.replace("transcript_id", "transcript_idx"), "no_gene_name": gtf.replace("gene_name", "gene_nam"),
+             "ten_fields": gtf.replace("\n", "\textra\n", 1), "leading_space_attr": gtf.replace("; transcript_id", ";  transcript_id"),
+             "attr_nospace": gtf.replace("; gene_id", ";gene_id")}
+    for name, g in cases.items():
+        ref, ora, emu = _three_way(d, fa, g, bed)
+        assert ref == ora and ref == emu, name
+        assert ref[0][0] == (1 if name == "ten_fields" else 0), name
