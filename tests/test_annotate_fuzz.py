@@ -210,3 +210,28 @@ def test_degenerate_annotation_files(env):
         ref, ora, emu = _three_way(d, fa, g, bed)
         assert ref == ora and ref == emu, name
         assert ref[0][0] == (1 if name == "ten_fields" else 0), name
+
+
+def test_fasta_layouts_and_contig_ends(env, tmp_path):
+    """The splice-site 2-mers (get_splice_site, junctions_annotator.cc:94-114; fai_fetch clipping, faidx.c:341-415) on junctions
+    at both ends of the contig and on both strands, with the FASTA written in different layouts: line widths, lower case,
+    CRLF, no final newline, a duplicated and a second sequence, a description / tab after the name, a truncated sequence."""
+    d, _ = env
+    gold = os.path.join(ROOT, "tests", "golden", "annotate")
+    gtf = open(os.path.join(gold, "hcc1395.gtf")).read()
+    bed = open(os.path.join(gold, "hcc1395.bed")).read()
+    seq = open(os.path.join(gold, "hcc1395.fa")).read().split("\n", 1)[1].replace("\n", "")
+    wrap = lambda s, w: "\n".join(s[i:i + w] for i in range(0, len(s), w)) + "\n"
+    ends = [(0, 200, 0, 10, "+"), (0, 3, 0, 0, "-"), (1, 4, 1, 1, "+"), (110900, 111900, 10, 10, "-"), (111830, 111900, 0, 0, "+"),
+            (109990, 110003, 5, 1, "-"), (109990, 110004, 5, 1, "+")]
+    bed += "".join(f"22\t{a}\t{b}\tE{i}\t1\t{st}\t{a}\t{b}\t255,0,0\t2\t{b0},{b1}\t0,1\n" for i, (a, b, b0, b1, st) in enumerate(ends))
+    cases = {"plain60": ">22\n" + wrap(seq, 60), "lower": ">22 desc here\n" + wrap(seq.lower(), 60),
+             "crlf": (">22\n" + wrap(seq, 60)).replace("\n", "\r\n"), "w80_noeol": (">22\n" + wrap(seq, 80)).rstrip("\n"),
+             "dup": ">22\n" + wrap(seq, 60) + ">22\n" + wrap("ACGT" * 100, 60), "other_first": ">1\n" + wrap("ACGT" * 50, 60) + ">22\n" + wrap(seq, 60),
+             "short": ">22\n" + wrap(seq[:20000], 60), "tab_name": ">22\tx\n" + wrap(seq, 60)}
+    for name, text in cases.items():
+        fa = tmp_path / (name + ".fa")
+        with open(fa, "w", newline="") as f:
+            f.write(text)
+        ref, ora, emu = _three_way(d, str(fa), gtf, bed)
+        assert ref[0][0] == 0 and ref == ora and ref == emu, name
