@@ -505,7 +505,9 @@ static int bgzf_read_block_(bgzf_t* b) {
     uint32_t bsize = (h[16] | h[17] << 8) + 1u;
     if (addr + bsize > b->size || bsize < 26) return -1;
     z_stream zs; memset(&zs, 0, sizeof zs);
-    zs.next_in = (Bytef*)(h + 18); zs.avail_in = bsize - 18 - 8;   /* bgzf.c:298-299 */
+    /* bgzf.c:298-299 passes block_length - 16 bytes: deflate data + the 8-byte trailer + 2 bytes of whatever the buffer held
+     * behind the block (not reproducible); the trailer is offered here, a damaged stream may run on into it */
+    zs.next_in = (Bytef*)(h + 18); zs.avail_in = bsize - 18;
     zs.next_out = b->buf; zs.avail_out = sizeof b->buf;
     if (inflateInit2(&zs, -15) != Z_OK) return -1;
     int rc = inflate(&zs, Z_FINISH);

@@ -60,8 +60,11 @@ public:
     // returns inflated length or -1
     long run(const uint8_t* file, const BlockDesc& b, uint8_t* dst, uint32_t cap) {
         if (!ok_ || inflateReset(&zs_) != Z_OK) return -1;
+        // inflate_block (bgzf.c:292-316) hands zlib `block_length - 16` bytes: the deflate data, the 8-byte trailer and two
+        // bytes of whatever its buffer held beyond the block.  A well-formed stream ends before the trailer either way; a
+        // damaged one may run on into it, so the trailer is offered here too (the two stray bytes are not reproducible).
         zs_.next_in = const_cast<Bytef*>(file + b.coff + 18);
-        zs_.avail_in = b.csize - 18 - 8;
+        zs_.avail_in = b.csize - 18;
         zs_.next_out = dst; zs_.avail_out = cap;
         int rc = inflate(&zs_, Z_FINISH);
         if (rc != Z_STREAM_END) return -1;
@@ -324,11 +327,14 @@ constexpr uint32_t CHUNK_BLOCKS = 32;
 
 struct StreamChunk {
     std::vector<BlockDesc> blocks;
-    std::vector<uint32_t> out_off;       // placement of each block in buf (by ISIZE)
+    std::vector<uint32_t> out_off;       // placement of each block in buf: one 64 KB slot per block (the trailer's ISIZE is
+                                         // not trusted: htslib takes the block's length from zlib's total_out, bgzf.c:315)
     std::vector<int32_t> out_len;        // actual inflated length (-1: failed)
     std::vector<uint8_t> buf;
     bool ready = false;
     bool end_of_range = false;           // no further chunk belongs to the current range
+    bool stream_ends = false;            // the block after this chunk is missing / malformed / past EOF: bgzf_read_block fails or
+                                         // reads nothing there and hts_itr_next finishes the WHOLE iteration (hts.c:1928-1963)
     int range = 0;
     double inflate_s = 0;
 };
@@ -378,7 +384,7 @@ private:
         while (!sched_done_ && tail_ - head_ < ring_.size()) {
             StreamChunk* c = ring_[tail_ % ring_.size()].get();
             c->blocks.clear(); c->out_off.clear(); c->out_len.clear();
-            c->ready = false; c->end_of_range = false; c->range = sched_range_;
+            c->ready = false; c->end_of_range = false; c->stream_ends = false; c->range = sched_range_;
             const uint64_t end_coff = ranges_[sched_range_].end == UINT64_MAX ? UINT64_MAX : ranges_[sched_range_].end >> 16;
             const bool end_has_tail = ranges_[sched_range_].end != UINT64_MAX && (ranges_[sched_range_].end & 0xffff) != 0;
             uint32_t total = 0;
@@ -386,9 +392,9 @@ private:
                 if (next_coff_ > end_coff || (next_coff_ == end_coff && !end_has_tail)) { c->end_of_range = true; break; }
                 BlockDesc d;
                 int rc = peek_block(bam_.data(), bam_.size(), next_coff_, &d);
-                if (rc != 0 || d.isize == 0 || d.isize > 0x10000) { c->end_of_range = true; break; }  // EOF / empty block ends reading
+                if (rc != 0) { c->end_of_range = true; c->stream_ends = true; break; }   // end of file or a bad header: reading ends
                 c->blocks.push_back(d); c->out_off.push_back(total); c->out_len.push_back(-1);
-                total += d.isize;
+                total += 0x10000u;
                 next_coff_ = d.coff + d.csize;
                 blocks++; cbytes += d.csize;
             }
@@ -419,7 +425,7 @@ private:
             }
             double t0 = now_s();
             for (size_t i = 0; i < c->blocks.size(); ++i)
-                c->out_len[i] = (int32_t)inf.run(bam_.data(), c->blocks[i], c->buf.data() + c->out_off[i], c->blocks[i].isize);
+                c->out_len[i] = (int32_t)inf.run(bam_.data(), c->blocks[i], c->buf.data() + c->out_off[i], 0x10000u);
             c->inflate_s += now_s() - t0;
             { std::lock_guard<std::mutex> g(mu_); c->ready = true; }
             cv_done_.notify_all();
@@ -458,7 +464,9 @@ void feed_stream(const BamFile& bam, const std::vector<Chunk64>& ranges, const F
         const uint64_t end_voff = ranges[cur_range].end;
         bool range_done = false;
         for (size_t bi = 0; bi < c->blocks.size() && !dead && !range_done; ++bi) {
-            if (c->out_len[bi] != (int32_t)c->blocks[bi].isize) { dead = true; break; }   // corrupt block: stream ends
+            // inflate failed (bgzf_read_block < 0) or the block is empty (bgzf_read breaks, bam_read1 reports the end of the
+            // file, bgzf.c:559-561): the stream ends here, whatever the trailer's ISIZE says
+            if (c->out_len[bi] <= 0) { dead = true; break; }
             const uint8_t* p = c->buf.data() + c->out_off[bi];
             const uint8_t* const bstart = p;
             const uint8_t* e = p + c->out_len[bi];
@@ -491,6 +499,7 @@ void feed_stream(const BamFile& bam, const std::vector<Chunk64>& ranges, const F
                 p += 4 + (size_t)bl;
             }
         }
+        if (c->stream_ends && !range_done) dead = true;
         const bool eor = c->end_of_range;
         const int r = c->range;
         ps.release();
