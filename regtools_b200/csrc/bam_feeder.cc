@@ -838,8 +838,9 @@ uint64_t scan_bgzf_blocks(const BamFile& bam, uint64_t coff, uint64_t end_coff, 
 }
 
 uint64_t scan_bgzf_blocks_mem(const uint8_t* buf, size_t n, uint64_t base_coff, uint64_t end_coff,
-                              std::vector<BgzfBlockInfo>* out, bool* stop, bool* partial) {
+                              std::vector<BgzfBlockInfo>* out, bool* stop, bool* partial, bool* untrusted) {
     *stop = false; *partial = false;
+    if (untrusted) *untrusted = false;
     size_t o = 0;
     for (;;) {
         if (base_coff + o >= end_coff) { *stop = true; break; }
@@ -851,7 +852,12 @@ uint64_t scan_bgzf_blocks_mem(const uint8_t* buf, size_t n, uint64_t base_coff, 
         if (bsize < 26) { *stop = true; break; }
         if (o + bsize > n) { *partial = true; break; }
         const uint32_t isize = rd32(h + bsize - 4);
-        if (isize == 0 || isize > 0x10000) { *stop = true; break; }
+        if (isize == 0 || isize > 0x10000) {
+            // htslib never reads ISIZE (a block is as long as zlib says, bgzf.c:315).  The 28-byte empty block really is the end
+            // of the stream; any other block claiming 0 or > 64 KB is left to the host feeder, which inflates it to find out.
+            if (untrusted && !(isize == 0 && bsize == 28)) *untrusted = true;
+            *stop = true; break;
+        }
         out->push_back(BgzfBlockInfo{base_coff + o, bsize, isize});
         o += bsize;
     }

@@ -143,7 +143,7 @@ uint64_t scan_bgzf_blocks(const BamFile& bam, uint64_t coff, uint64_t end_coff, 
 // Same walk over a memory copy of file bytes [base_coff, base_coff + n): stops before the first block that is not
 // completely inside the buffer (*partial = true) or at an empty / malformed block (*stop = true).
 uint64_t scan_bgzf_blocks_mem(const uint8_t* buf, size_t n, uint64_t base_coff, uint64_t end_coff,
-                              std::vector<BgzfBlockInfo>* out, bool* stop, bool* partial);
+                              std::vector<BgzfBlockInfo>* out, bool* stop, bool* partial, bool* untrusted = nullptr);
 
 // Contigs -> shards: runs of consecutive contigs, balanced on compressed bytes (min-max contiguous partition); and the
 // byte ranges of such a run, coalesced into one range per run.

@@ -339,7 +339,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
         while (!stream_ends && !declined && !reached_limit) {
             // ---- stage one chunk of compressed bytes: page cache -> pinned -> device (group buffer)
             blocks.clear();
-            bool stop = false, partial = false;
+            bool stop = false, partial = false, untrusted = false;
             const uint64_t c_first = coff;
             { const double tq = now_s(); CKD(cudaEventSynchronize(F.comp_free[buf])); t_slot += now_s() - tq; }   // pinned slot free (its H2D two chunks back is done)
             const size_t want_bytes = (size_t)std::min<uint64_t>(STAGE + (1u << 16), bam.size() - c_first);
@@ -347,9 +347,10 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             const size_t got_bytes = parallel_pread(bam.fd(), F.h_comp[buf], want_bytes, c_first, copy_threads);
             t_stage += now_s() - t0; stats_.host_inflate_s += now_s() - t0;   // host staging time (nothing is inflated on the host)
             const double ts0 = now_s();
-            const uint64_t c_end = scan_bgzf_blocks_mem(F.h_comp[buf], got_bytes, c_first, end_coff, &blocks, &stop, &partial);
+            const uint64_t c_end = scan_bgzf_blocks_mem(F.h_comp[buf], got_bytes, c_first, end_coff, &blocks, &stop, &partial, &untrusted);
             t_scanhdr += now_s() - ts0;
             coff = c_end;
+            if (untrusted) { declined = true; break; }     // a trailer that cannot be taken at its word: the host feeder decides
             if (stop || c_end >= end_coff || (partial && c_first + got_bytes >= bam.size()) || blocks.empty()) stream_ends = true;
             if (!blocks.empty()) {
                 const size_t bytes = (size_t)(c_end - c_first);

@@ -109,3 +109,32 @@ def make_motif_fuzz_case(d, seed):
 
 
 MOTIF_FUZZ_ARGS = (["-s", "XS"], ["-s", "RF"], ["-s", "intron-motif"], ["-s", "FR", "-a", "0"])
+
+
+def damage_bam(src, dst, seed):
+    """A copy of `src` (+ its .bai) with one kind of damage: truncation, 1-3 flipped bits, 8 zeroed bytes, or a wrong ISIZE
+    trailer.  -> the kind"""
+    import shutil
+    rnd = random.Random(seed)
+    data = bytearray(open(src, "rb").read())
+    mode = rnd.choice(["trunc", "flip", "zero", "isize"])
+    if mode == "trunc":
+        data = data[:rnd.randrange(len(data) // 3, len(data))]
+    elif mode == "flip":
+        for _ in range(rnd.choice([1, 3])):
+            data[rnd.randrange(200, len(data))] ^= 1 << rnd.randrange(8)
+    elif mode == "zero":
+        i = rnd.randrange(200, len(data) - 8)
+        data[i:i + 8] = bytes(8)
+    else:
+        off, blocks = 0, []
+        while off + 18 <= len(data):
+            bs = struct.unpack_from("<H", data, off + 16)[0] + 1
+            blocks.append((off, bs))
+            off += bs
+        o, bs = rnd.choice(blocks[:-1])
+        data[o + bs - 4:o + bs] = struct.pack("<I", rnd.choice([0, 1, 70000, struct.unpack_from("<I", data, o + bs - 4)[0] + 1]))
+    with open(dst, "wb") as f:
+        f.write(data)
+    shutil.copy(src + ".bai", dst + ".bai")
+    return mode

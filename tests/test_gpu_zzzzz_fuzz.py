@@ -119,3 +119,34 @@ def test_fuzzed_variant_regions_match_oracle(block, tmp_path):
                 assert len(got) == len(want), (seed, reg)
                 for f in ("tid", "start", "end", "thick_start", "thick_end", "read_count", "name_index", "strand", "left_ok", "right_ok"):
                     assert np.array_equal(got[f], want[f]), (seed, reg, f)
+
+
+@pytest.mark.parametrize("block", range(2))
+def test_damaged_files_match_oracle(block, tmp_path):
+    """Truncated / bit-flipped / zeroed / wrong-ISIZE copies of fuzzed BAMs through the whole product: the BED12 must be what
+    the oracle prints (= what the unmodified reference prints before it stops, tests/test_host_logic.py::
+    test_feeder_on_damaged_files).  These files are small, so the host feeder runs; the device feeder on damaged files (it must
+    decline or agree: inflate status, record checks, untrusted ISIZE) is to be fuzzed with inflate_mode=2 in round 2."""
+    import regtools_b200 as rt
+    for seed in range(block * 12, block * 12 + 12):
+        bam = ff.make_cigar_fuzz_bam(str(tmp_path / "a.bam"), seed)
+        bad = str(tmp_path / "c.bam")
+        mode = ff.damage_bam(bam, bad, seed)
+        for reg in (".", "1:100-2000"):
+            o = Oracle(0, 0, 500000, 0)
+            try:
+                o.extract_bam(bad, reg)
+                want = o.bed12()
+            except RuntimeError:
+                want = None
+            for inflate_mode in (0, 1):
+                ex = rt.JunctionsExtractor(bad, reg, 0, "XS", 0, 0, 500000, inflate_mode=inflate_mode)
+                try:
+                    ex.identify_junctions_from_BAM()
+                    buf = io.StringIO()
+                    ex.print_all_junctions(buf)
+                    got = buf.getvalue()
+                except RuntimeError:
+                    got = None
+                ex.close()
+                assert got == want, (seed, mode, reg, inflate_mode)
