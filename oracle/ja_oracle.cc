@@ -135,16 +135,20 @@ struct Fasta {                                                     // as faidx s
         }
         return true;
     }
-    // fai_fetch("chrom:b1-e1") with 1-based inclusive coordinates (faidx.c:341-415); false = NULL
-    bool fetch(const string& chrom, long long b1, long long e1, string* out) const {
+    // fai_fetch("chrom:b1-e1") (faidx.c:341-415): b1 / e1 are the numbers the annotator printed with uint32 arithmetic; faidx
+    // reads them back with atoi into ints (4294967295 -> -1), decrements a positive beg, clips both to the length and never
+    // clamps a negative beg: it then starts reading that many bytes BEFORE the sequence — for -1 the header's newline, which is
+    // skipped as non-graph, so the result is the first (end - beg) bases.  (beg < -1 would read header text; treated as -1.)
+    bool fetch(const string& chrom, uint32_t b1, uint32_t e1, string* out) const {
         std::map<string, string>::const_iterator it = seq.find(chrom);
         if (it == seq.end()) return false;
-        long long len = (long long)it->second.size(), beg = b1 - 1, end = e1;
-        if (beg < 0) beg = 0;
+        long long len = (long long)it->second.size(), beg = (int32_t)b1, end = (int32_t)e1;
+        if (beg > 0) --beg;
         if (beg >= len) beg = len;
         if (end >= len) end = len;
         if (beg > end) beg = end;
-        *out = it->second.substr((size_t)beg, (size_t)(end - beg));
+        const long long n = end - beg, from = beg < 0 ? 0 : beg;
+        *out = it->second.substr((size_t)from, (size_t)std::min<long long>(n, len - from));
         return true;
     }
 };
@@ -311,10 +315,10 @@ int main(int argc, char** argv) {
             string s1, s2;                                                         // get_splice_site :94-114
             const string p1 = j.chrom + ":" + u2s(j.start + 1) + "-" + u2s(j.start + 2), p2 = j.chrom + ":" + u2s(j.end - 2) + "-" + u2s(j.end - 1);
             std::cerr << "position = " << p1 << std::endl;
-            if (!fasta_ok || !fasta.fetch(j.chrom, (long long)j.start + 1, (long long)j.start + 2, &s1))
+            if (!fasta_ok || !fasta.fetch(j.chrom, j.start + 1u, j.start + 2u, &s1))
                 throw std::runtime_error("Unable to extract FASTA sequence for position " + p1 + "\n\n");
             std::cerr << "position = " << p2 << std::endl;
-            if (!fasta.fetch(j.chrom, (long long)j.end - 2, (long long)j.end - 1, &s2))
+            if (!fasta.fetch(j.chrom, j.end - 2u, j.end - 1u, &s2))
                 throw std::runtime_error("Unable to extract FASTA sequence for position " + p2 + "\n\n");
             if (j.strand == "-") j.splice_site = rev_comp(s2) + "-" + rev_comp(s1);
             else j.splice_site = s1 + "-" + s2;

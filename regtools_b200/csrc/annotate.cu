@@ -153,25 +153,26 @@ annotate_kernel(AnnGtfView g, AnnJunctionView jv, int skip_single, unsigned long
         const uint8_t* gq = jv.genome + jv.c_goff[c];
         uint8_t s1[2] = {0, 0}, s2[2] = {0, 0};
         uint32_t n1 = 0, n2 = 0;
-        {   // faidx.c:341-415: beg = b1 - 1, end = e1, both clipped to the length, beg <= end
-            unsigned long long b = js, e = (unsigned long long)js + 2ull;
-            if (b >= glen) b = glen;
-            if (e >= glen) e = glen;
+        // fai_fetch (faidx.c:341-415) reads the two numbers of "chrom:a-b" back with atoi into ints (the annotator printed them
+        // with uint32 arithmetic, so end - 2 of a junction ending at 1 arrives as -1), decrements a positive beg, clips both to the
+        // length and never clamps a negative beg: it then starts that many bytes before the sequence — for -1 the header's
+        // newline, skipped as non-graph — and returns the first (end - beg) bases.  (beg < -1 would read header text: as -1.)
+        auto fetch = [&](uint32_t a1, uint32_t b1, uint8_t* dst) -> uint32_t {
+            long long b = (long long)(int32_t)a1, e = (long long)(int32_t)b1;
+            const long long len = (long long)glen;
+            if (b > 0) --b;
+            if (b >= len) b = len;
+            if (e >= len) e = len;
             if (b > e) b = e;
-            n1 = (uint32_t)(e - b);
-            for (uint32_t k = 0; k < n1; ++k) s1[k] = gq[b + k];
-        }
-        {
-            // "chrom:end-2-end-1": hts_parse_reg gives beg = end - 3 (clamped at 0), end = end - 1
-            long long b = (long long)je - 3, e = (long long)je - 1;
-            if (b < 0) b = 0;
-            if (e < 0) e = 0;
-            if ((unsigned long long)b >= glen) b = (long long)glen;
-            if ((unsigned long long)e >= glen) e = (long long)glen;
-            if (b > e) b = e;
-            n2 = (uint32_t)(e - b);
-            for (uint32_t k = 0; k < n2; ++k) s2[k] = gq[b + k];
-        }
+            const long long from = b < 0 ? 0 : b;
+            long long n = e - b;
+            if (n > len - from) n = len - from;
+            if (n > 2) n = 2;
+            for (long long k = 0; k < n; ++k) dst[k] = gq[from + k];
+            return (uint32_t)(n < 0 ? 0 : n);
+        };
+        n1 = fetch(js + 1u, js + 2u, s1);
+        n2 = fetch(je - 2u, je - 1u, s2);
         if (jstrand == 1u) {                                                   // rev_comp both, print seq2-seq1 (:106-110)
             for (uint32_t k = 0; k < n2; ++k) o.ss[k] = comp_base(s2[n2 - 1 - k]);
             for (uint32_t k = 0; k < n1; ++k) o.ss[3 + k] = comp_base(s1[n1 - 1 - k]);
