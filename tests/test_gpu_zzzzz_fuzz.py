@@ -150,3 +150,43 @@ def test_damaged_files_match_oracle(block, tmp_path):
                     got = None
                 ex.close()
                 assert got == want, (seed, mode, reg, inflate_mode)
+
+
+@pytest.mark.parametrize("block", range(2))
+def test_fuzzed_annotation_inputs_match_oracle(block, tmp_path):
+    """`junctions annotate` on the pathological GTF / BED generators of tests/test_annotate_fuzz.py (mixed-strand transcripts,
+    60-exon transcripts with equal starts, malformed intervals, CRLF, mid-file headers, missing contigs): exit status and the
+    bytes on disk of the CUDA path against the oracle, which the CPU suite pins to the unmodified reference on the same seeds."""
+    import random
+    import subprocess
+    import ann_fixture
+    import regtools_b200 as rt
+    from test_annotate_fuzz import _case_mixed, _case_ties
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    oracle = os.path.join(root, "oracle", "_ref", "ja_oracle")
+    if not os.path.exists(oracle):
+        subprocess.check_call(["make", "-C", os.path.join(root, "oracle"), "-s"])
+    fa = ann_fixture.write_fasta(str(tmp_path / "ref.fa"), [("1", 60000), ("2", 30000)])
+    for seed in range(block * 20, block * 20 + 20):
+        for gtf_text, bed_text in (_case_mixed(random.Random(seed), 0.05), _case_ties(random.Random(10_000 + seed))):
+            gtf, bed = tmp_path / "a.gtf", tmp_path / "j.bed"
+            gtf.write_text(gtf_text)
+            with open(bed, "w", newline="") as f:
+                f.write(bed_text)
+            for single in (False, True):
+                want_path, got_path = tmp_path / "want.tsv", tmp_path / "got.tsv"
+                for p in (want_path, got_path):
+                    if p.exists():
+                        p.unlink()
+                rc = subprocess.run([oracle] + (["-S"] if single else []) + ["-o", str(want_path), str(bed), fa, str(gtf)],
+                                    capture_output=True).returncode
+                a = rt.JunctionsAnnotator(str(bed), fa, str(gtf))
+                a.skip_single_exon_genes_ = not single
+                a.output_file_ = str(got_path)
+                try:
+                    a.annotate_all()
+                    got_rc = 0
+                except RuntimeError:
+                    got_rc = 1
+                assert got_rc == rc, (seed, single)
+                assert (got_path.read_text() if got_path.exists() else None) == (want_path.read_text() if want_path.exists() else None), (seed, single)
