@@ -121,6 +121,14 @@ def test_cli_option_handling_needs_no_gpu(tmp_path):
         assert p.returncode == 1 and "no CPU fallback" in p.stderr and p.stdout == ""
 
 
+# atoi() semantics of -a / -m / -M (junctions_extractor.cc:52-60), repeated and odd -s / -t / -r: the parameter echo on stderr
+# carries the parsed values, the missing BAM ends the run before any device work
+ODD_NUMERIC_ARGS = [("regtools_ref", "extract", ["-s", "XS"] + a + ["nonexist.bam"]) for a in (
+    ["-a", "12junk"], ["-a", "-5"], ["-a", "99999999999"], ["-m", "x"], ["-M", "0x10"], ["-a", "1e3"], ["-a", "+7"], ["-a", " 8"],
+    ["-m", "4294967296"], ["-M", "-1"], ["-a", "007"], ["-s", "RF"], ["-s", "0"], ["-s", "3"], ["-t", "X"], ["-t", "LONGTAG"],
+    ["-r", "1:1-2", "-r", "2"])]
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "regtools_ref_annotate")), reason="needs oracle/_ref (dev container)")
 def test_cli_texts_equal_the_reference(tmp_path):
     """Exit code, stdout and stderr (after our three banner lines, which the reference's real CLI prints too but the test
@@ -131,6 +139,7 @@ def test_cli_texts_equal_the_reference(tmp_path):
     bam = os.path.join(ROOT, "tests", "golden", "hcc1395", "test_hcc1395.bam")
     cases = [("regtools_ref", "extract", a) for a in (["-h"], ["x.bam"], ["-s", "XS"], ["-s", "bogus", bam], ["-s", "XS", "nonexist.bam"],
                                                        ["-s", "intron-motif", bam], ["-q", "-s", "XS", bam], ["-s", "XS", "-o", "o", "-r", "1:2-3", "-t", "ZS", "-b", "b", "nonexist.bam"])]
+    cases += ODD_NUMERIC_ARGS
     cases += [("regtools_ref_annotate", "annotate", a) for a in (["-h"], ["a.bed", "b.fa"], ["-x", "a.bed", "b.fa", "c.gtf"], ["a.bed", "b.fa", "/nonexistent.gtf"],
                                                                  ["-S", "-o", "o.tsv", "a.bed", "b.fa", "/nonexistent.gtf"], ["a", "b", "c", "d"])]
     for ref_bin, sub, args in cases:
@@ -151,6 +160,7 @@ def test_python_mirror_texts_equal_the_reference(tmp_path):
     cases = [("regtools_ref", "extract", a) for a in (["-h"], ["x.bam"], ["-s", "XS"], ["-s", "bogus", bam], ["-s", "XS", "nonexist.bam"],
                                                        ["-s", "intron-motif", bam], ["-q", "-s", "XS", bam], ["-s", "XS", "-o"],
                                                        ["-s", "XS", "-o", "o", "-r", "1:2-3", "-t", "ZS", "-b", "b", "-a", "3", "-m", "4", "-M", "5", "nonexist.bam"])]
+    cases += ODD_NUMERIC_ARGS
     cases += [("regtools_ref_annotate", "annotate", a) for a in (["-h"], ["a.bed", "b.fa"], ["-x", "a.bed", "b.fa", "c.gtf"], ["a.bed", "b.fa", "/nonexistent.gtf"],
                                                                  ["-S", "-o", "o.tsv", "a.bed", "b.fa", "/nonexistent.gtf"], ["-o"], ["a", "b", "c", "d"])]
     env = dict(os.environ, PYTHONPATH=ROOT)
