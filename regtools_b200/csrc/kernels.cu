@@ -777,7 +777,9 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
                         const uint32_t x = in_smem ? sm.slab[o0 - a0 + q] : __ldg(b.cigar + o0 + q);
                         if ((0x18Du >> (x & 0xfu)) & 1u) rl += x >> 4;      // M, D, N, =, X consume the reference
                     }
-                    rspan[0] = (int32_t)sm.pos[r]; rspan[1] = (int32_t)(sm.pos[r] + rl);
+                    // bam_endpos (sam.c:336-342): an alignment flagged BAM_FUNMAP spans one base whatever its CIGAR says
+                    const bool unmapped = ((sm.meta[r] >> 16) & 4u) != 0;
+                    rspan[0] = (int32_t)sm.pos[r]; rspan[1] = (int32_t)(sm.pos[r] + (unmapped ? 1u : rl));
                 }
                 if ((o0 - a0) + n <= n_st) walk_fast<true>(sm.slab + (o0 - a0), n, sm.pos[r], tid, strand, read_ord, emit);
                 else walk_fast<false>(b.cigar + o0, n, sm.pos[r], tid, strand, read_ord, emit);

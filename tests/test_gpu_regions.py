@@ -91,3 +91,22 @@ def test_bad_region_is_an_error(golden_dir):
         ex.identify_junctions_in_regions(["1:100-200", "nope:1-2"])
     assert [len(t) for t in ex.identify_junctions_in_regions([])] == []
     ex.close()
+
+
+def test_unmapped_flag_alignment_spans_one_base(tmp_path):
+    """bam_endpos (sam.c:336-342) is pos + 1 for an alignment flagged BAM_FUNMAP whatever its CIGAR says, and that is the
+    `end` hts_itr_next tests against the region (hts.c:1951-1955): a flag-4 read with `70M500000N50M` that starts before a
+    region is NOT in it, the same read without the flag is.  (Round-1 fuzz seed 0 failed on exactly this.)"""
+    import bamio
+    import fuzz_fixture as ff
+    bam = str(tmp_path / "u.bam")
+    recs = [bamio.record(1, 1071, "70M500000N50M", 4, 60, b"XSA+", name=b"unm"),
+            bamio.record(1, 1100, "70M400000N50M", 0, 60, b"XSA+", name=b"map"),
+            bamio.record(1, 3500, "20M100N30M", 4, 60, b"XSA-", name=b"unm_in"),
+            bamio.record(1, 3600, "30M", 4, 60, b"", name=b"unm_1op"),
+            bamio.record(1, 603458, "10M80N10M", 4, 60, b"XSA-", name=b"unm_last")]
+    bamio.write_bam(bam, ff.CONTIGS, recs)
+    ff._index(bam)
+    regions = ["10:3459-603459", "10:1072-1072", "10:1073-1200", "10:3501-3501", "10:3502-3600", "10:603459-603459", "10:603460-700000", "10"]
+    n, _ = _check(bam, regions, a=8, m=8)
+    assert n == 3 + 1 + 1 + 2 + 1 + 1 + 0 + 4
