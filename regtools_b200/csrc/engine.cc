@@ -82,11 +82,11 @@ ScanParams Engine::scan_params() const {
     static const int env_variant = getenv("RTJX_SCAN_VARIANT") ? atoi(getenv("RTJX_SCAN_VARIANT")) : 0;
     static const int env_cfg = getenv("RTJX_SCAN_CFG") ? atoi(getenv("RTJX_SCAN_CFG")) : 0;
     s.debug = prm_.scan_debug ? prm_.scan_debug : dbg;
-    s.variant = prm_.scan_variant ? prm_.scan_variant : (env_variant ? env_variant : 5);
+    s.variant = prm_.scan_variant ? prm_.scan_variant : (env_variant ? env_variant : 8);
     s.cfg = prm_.scan_cfg ? prm_.scan_cfg : env_cfg;
     s.genome = d_genome_; s.g_off = d_g_off_; s.g_len = d_g_len_; s.g_n = d_genome_ ? g_n_ : 0u;
     s.vr = vr_;
-    if (d_genome_ || vr_.n || bc_mode_) { s.variant = 5; s.cfg = 0; }   // the intron-motif and variant-region modes live in the default scan kernel only
+    if ((d_genome_ || vr_.n || bc_mode_) && s.variant != 5) { s.variant = 8; s.cfg = 0; }   // the intron-motif, variant-region and barcode modes live in the two tiled scan kernels only
     return s;
 }
 
@@ -245,7 +245,7 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
     if (sp.vr.n) {
         // variant-region mode: an alignment yields one candidate per region it belongs to, so the candidate count is only
         // known after the scan: scan, read the count back, grow and re-scan if the buffer was too small, then merge
-        if ((rc = ensure_cands(std::max(std::max(cand_bound, v.n_ops / 4u) * 2u, 1u << 16)))) return rc;
+        if ((rc = ensure_cands(std::max(std::max(cand_bound, v.n_ops / 4u) * 2u, 1u << 16) + cigar_scan_cand_slack()))) return rc;
         for (int attempt = 0;; ++attempt) {
             CK(cudaMemsetAsync(d_counters_ + CTR_NCAND, 0, 2 * sizeof(uint32_t), stream));       // NCAND + CAND_OVERFLOW
             launch_cigar_scan(v, sp, d_cands_, cand_cap_, d_counters_, nullptr, CandRegions{nullptr, nullptr, 0, 0}, stream);
@@ -256,7 +256,7 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
             if (attempt) return fail(RTJX_E_STATE, "internal: candidate buffer overflowed twice in variant-region mode");
             const uint32_t need = h_counters_[CTR_NCAND];
             CK(cudaMemsetAsync(d_counters_ + CTR_CAND_OVERFLOW, 0, sizeof(uint32_t), stream));
-            if ((rc = ensure_cands(need))) return rc;
+            if ((rc = ensure_cands(need + cigar_scan_cand_slack()))) return rc;
         }
         const uint32_t n_cand = h_counters_[CTR_NCAND];
         unique_upper_ = h_counters_[CTR_NUNIQUE];
@@ -271,7 +271,9 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
         dirty_ = true; finalized_ = false;
         return RTJX_OK;
     }
-    if ((rc = ensure_cands(known ? cand_bound : std::max(v.n_ops, 1u)))) return rc;
+    // cigar_scan reserves candidate slots in chunks: the list holds up to cigar_scan_cand_slack() padding entries (tid = -1)
+    const uint32_t slack = cigar_scan_cand_slack();
+    if ((rc = ensure_cands((known ? cand_bound : std::max(v.n_ops, 1u)) + slack))) return rc;
     if (known && (rc = ensure_table(cand_bound, stream))) return rc;
     CK(cudaMemsetAsync(d_counters_ + CTR_NCAND, 0, sizeof(uint32_t), stream));
     CK(cudaMemsetAsync(d_counters_ + CTR_NREGION, 0, sizeof(uint32_t), stream));
@@ -308,11 +310,11 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
         cand_bound = h_counters_[CTR_NCAND] + h_counters_[CTR_NREGION];
         if ((rc = ensure_table(std::max(cand_bound, 1u), stream))) return rc;
     }
-    launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, cand_bound, rgn, scan_params(), table_ref(),
+    launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, known ? cand_bound + slack : cand_bound, rgn, scan_params(), table_ref(),
                           d_spill_, spill_cap_, d_counters_, stream);
     if (prm_.profile) { cudaEventRecord(pe.c, stream); prof_pending_.push_back(pe); }
     CK(cudaGetLastError());
-    stats_.kernel_launches += (v.n_reads ? 2 : 0) + (cand_bound ? 1 : 0);   // tile-offset pre-pass + cigar_scan, junction_merge
+    stats_.kernel_launches += (v.n_reads ? 1 : 0) + (cand_bound ? 1 : 0);   // cigar_scan, junction_merge
     stats_.reads += v.n_reads; stats_.cigar_ops += v.n_ops; stats_.batches++;
     dirty_ = true; finalized_ = false;
     if (prof_pending_.size() > 4096) resolve_profile_events();

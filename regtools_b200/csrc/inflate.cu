@@ -577,6 +577,260 @@ bgzf_inflate_simt_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __re
     status[b] = err;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Lane-per-stream decoder (round 2; the default for launches with enough BGZF blocks)
+// ------------------------------------------------------------------------------------------------
+// The warp-per-block kernel above issues ~22-31 warp instructions per output byte because its symbol loop runs on one lane.
+// Here every LANE decodes its own BGZF block, so one issued instruction advances 32 streams.  What makes that work:
+//   * per-lane lookup tables in shared memory (LR-bit literal/length root table, DR-bit distance root table, canonical
+//     count/symbol arrays for the rare longer codes), lane stride an odd number of words so equal indices of different lanes
+//     fall into different banks; one warp per CTA, CTAs per SM bounded by shared memory (LR = 10: 2 x 32 streams per SM);
+//   * a flattened state machine — one loop, one symbol (or one DEFLATE block header) per lane per iteration — so lanes
+//     reconverge every iteration; zlib cuts DEFLATE blocks after a fixed number of symbols, so the lanes of a warp reach their
+//     block headers (the expensive, divergent table builds) in the same iteration;
+//   * the bit stream is read through a 64-bit buffer refilled from a word loaded one refill earlier, plus an L2 prefetch half
+//     a kilobyte ahead, so neither L2 nor DRAM latency sits on the symbol chain;
+//   * literals are combined into aligned 32-bit stores (a quarter of the store transactions); matches copy bytes from the
+//     lane's own earlier output in global memory (L1/L2).
+// Error codes are those of the kernel above; any non-zero status sends the run to the host feeder.
+template <int LR, int DR>
+struct LaneLayout {
+    static constexpr int LIT_FAST = 0;                                 // uint16[1 << LR]
+    static constexpr int DIST_FAST = LIT_FAST + (2 << LR);             // uint16[1 << DR]
+    static constexpr int LIT_COUNT = DIST_FAST + (2 << DR);            // uint16[16]
+    static constexpr int DIST_COUNT = LIT_COUNT + 32;                  // uint16[16]
+    static constexpr int LIT_SYM = DIST_COUNT + 32;                    // uint16[288]
+    static constexpr int DIST_SYM = LIT_SYM + 576;                     // uint16[32]
+    static constexpr int BYTES = DIST_SYM + 64;
+    static constexpr int STRIDE = ((BYTES / 4) | 1) * 4;               // odd number of words
+};
+
+// LSB-first bit reader of one lane: 64-bit buffer, 32-bit aligned refills, the next word always already requested.
+struct LaneBits {
+    const uint32_t* p;      // address of the word after `ahead`
+    const uint32_t* lim;    // first word that must not be read (end of this block's payload + slack)
+    uint64_t bb;
+    int nb;
+    uint32_t ahead;
+    __device__ __forceinline__ void init(const uint8_t* src, uint32_t len) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+        p = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        lim = reinterpret_cast<const uint32_t*>((a + len + 3) & ~(uintptr_t)3) + 2;    // BGZF trailer (CRC32, ISIZE) follows every payload
+        const int mis = (int)(a & 3);
+        bb = (uint64_t)__ldg(p++) >> (8 * mis);
+        nb = 32 - 8 * mis;
+        ahead = __ldg(p++);
+    }
+    __device__ __forceinline__ void refill() {                         // afterwards nb >= 33
+        if (nb <= 32) {
+            bb |= (uint64_t)ahead << nb; nb += 32;
+            if (p < lim) {
+                ahead = __ldg(p);
+                if ((reinterpret_cast<uintptr_t>(p) & 127u) == 0 && p + 128 < lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
+            } else ahead = 0;
+            ++p;
+        }
+    }
+    __device__ __forceinline__ bool overrun() const { return p > lim + 2; }
+    __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)bb & ((1u << n) - 1u); }
+    __device__ __forceinline__ void drop(int n) { bb >>= n; nb -= n; }
+    __device__ __forceinline__ uint32_t get(int n) { refill(); const uint32_t v = peek(n); drop(n); return v; }   // n <= 16
+    // address of the next unread byte after discarding the bits of a partial byte (stored blocks)
+    __device__ __forceinline__ const uint8_t* byte_ptr() const { return reinterpret_cast<const uint8_t*>(p - 1) - (nb >> 3); }
+};
+
+// canonical decode of a code longer than the root table (same recurrence as slow_decode_w): e = sym << 4 | len, 0 = invalid
+__device__ __forceinline__ uint32_t lane_slow_decode(uint64_t bb, const uint16_t* count, const uint16_t* sym, int root, int pre_first, int pre_index) {
+    uint32_t win = (uint32_t)bb;
+    int code = (int)(__brev(win) >> (32 - root)) << 1, first = pre_first, index = pre_index;
+    win >>= root;
+    for (int len = root + 1; len <= 15; ++len) {
+        code |= (int)(win & 1u); win >>= 1;
+        const int c = count[len];
+        if (code - c < first) return (uint32_t)sym[index + (code - first)] << 4 | (uint32_t)len;
+        index += c; first += c; first <<= 1; code <<= 1;
+    }
+    return 0u;
+}
+
+template <int LR, int DR>
+__global__ void __launch_bounds__(32)
+bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, uint32_t n_blocks,
+                          uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
+    using LL = LaneLayout<LR, DR>;
+    extern __shared__ __align__(16) uint8_t lane_smem[];
+    const uint32_t b = blockIdx.x * 32u + threadIdx.x;
+    if (b >= n_blocks) return;
+    uint8_t* T = lane_smem + threadIdx.x * LL::STRIDE;
+    uint16_t* lit_fast = reinterpret_cast<uint16_t*>(T + LL::LIT_FAST);
+    uint16_t* dist_fast = reinterpret_cast<uint16_t*>(T + LL::DIST_FAST);
+    uint16_t* lit_count = reinterpret_cast<uint16_t*>(T + LL::LIT_COUNT);
+    uint16_t* dist_count = reinterpret_cast<uint16_t*>(T + LL::DIST_COUNT);
+    uint16_t* lit_sym = reinterpret_cast<uint16_t*>(T + LL::LIT_SYM);
+    uint16_t* dist_sym = reinterpret_cast<uint16_t*>(T + LL::DIST_SYM);
+
+    const BgzfBlock blk = blocks[b];
+    uint8_t* dst = out + blk.out_off;
+    const uint32_t cap = blk.out_len;
+    uint32_t opos = 0, err = 0;
+    uint32_t wbuf = 0, pend = 0;                  // literals not yet stored: `pend` bytes ending at dst + opos, the first one 4-byte aligned
+    LaneBits br;
+    br.init(comp + blk.in_off, blk.in_len);
+    int lit_pf = 0, lit_pi = 0, dist_pf = 0, dist_pi = 0;               // slow-path constants of the current DEFLATE block
+    bool in_block = false, last = false;
+
+    auto flush_pending = [&]() {                  // pending literals as byte stores (before a match / at a block boundary)
+        for (uint32_t k = 0; k < pend; ++k) dst[opos - pend + k] = (uint8_t)(wbuf >> (8 * k));
+        pend = 0; wbuf = 0;
+    };
+
+    for (;;) {
+        if (!in_block) {
+            // ================= DEFLATE block header (divergent, a few times per BGZF block) =================
+            if (last || err) break;
+            const uint32_t hdr = br.get(3);
+            last = hdr & 1u;
+            const uint32_t btype = hdr >> 1;
+            if (btype == 0) {                      // stored: LEN, NLEN, raw bytes
+                br.drop(br.nb & 7);
+                const uint32_t l = br.get(16), nl = br.get(16);
+                if ((l ^ nl) != 0xffffu || opos + l > cap) { err = 2; continue; }
+                flush_pending();
+                const uint8_t* src = br.byte_ptr();
+                for (uint32_t i = 0; i < l; ++i) dst[opos + i] = __ldg(src + i);
+                opos += l;
+                br.init(src + l, (uint32_t)(reinterpret_cast<const uint8_t*>(br.lim - 2) - (src + l)));
+                continue;
+            }
+            if (btype == 3) { err = 3; continue; }
+            uint8_t lens[320];
+            if (btype == 1) {
+                for (int i = 0; i < 288; ++i) lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+                for (int i = 0; i < 30; ++i) lens[288 + i] = 5;
+            } else {
+                const int hlit = (int)br.get(5) + 257, hdist = (int)br.get(5) + 1, hclen = (int)br.get(4) + 4;
+                if (hlit > 286 || hdist > 30) { err = 4; continue; }
+                uint8_t cl[19];
+#pragma unroll
+                for (int i = 0; i < 19; ++i) cl[i] = 0;
+                for (int i = 0; i < hclen; ++i) cl[c_clen_order[i]] = (uint8_t)br.get(3);
+                uint16_t ccount[8], csym[19], coffs[8];
+                for (int i = 0; i < 8; ++i) ccount[i] = 0;
+                for (int i = 0; i < 19; ++i) ccount[cl[i]]++;
+                coffs[1] = 0;
+                for (int l = 1; l < 7; ++l) coffs[l + 1] = coffs[l] + ccount[l];
+                for (int i = 0; i < 19; ++i) if (cl[i]) csym[coffs[cl[i]]++] = (uint16_t)i;
+                int idx = 0;
+                while (idx < hlit + hdist && !err) {
+                    br.refill();
+                    int code = 0, first = 0, index = 0, symv = -1;
+                    for (int l = 1; l <= 7; ++l) {
+                        code |= (int)br.peek(1); br.drop(1);
+                        const int c = ccount[l];
+                        if (code - c < first) { symv = csym[index + (code - first)]; break; }
+                        index += c; first += c; first <<= 1; code <<= 1;
+                    }
+                    if (symv < 0) { err = 5; break; }
+                    if (symv < 16) lens[idx++] = (uint8_t)symv;
+                    else {
+                        int rep, val = 0;
+                        if (symv == 16) { if (idx == 0) { err = 6; break; } val = lens[idx - 1]; rep = 3 + (int)br.get(2); }
+                        else if (symv == 17) rep = 3 + (int)br.get(3);
+                        else rep = 11 + (int)br.get(7);
+                        if (idx + rep > hlit + hdist) { err = 7; break; }
+                        while (rep--) lens[idx++] = (uint8_t)val;
+                    }
+                    if (br.overrun()) err = 18;
+                }
+                if (err) continue;
+                if (lens[256] == 0) { err = 8; continue; }
+                // distance lengths to their fixed place (288..317); iterate downwards: the ranges may overlap
+                for (int i = hdist - 1; i >= 0; --i) lens[288 + i] = lens[hlit + i];
+                for (int i = hlit; i < 288; ++i) lens[i] = 0;
+                for (int i = hdist; i < 30; ++i) lens[288 + i] = 0;
+            }
+            if (!si_build(lens, 288, lit_count, lit_sym, lit_fast, LR)) { err = 9; continue; }
+            if (!si_build(lens + 288, 30, dist_count, dist_sym, dist_fast, DR)) { err = 10; continue; }
+            { const SlowPre a = slow_decode_pre(lit_count, LR), d = slow_decode_pre(dist_count, DR); lit_pf = a.first; lit_pi = a.index; dist_pf = d.first; dist_pi = d.index; }
+            in_block = true;
+            continue;
+        }
+        // ================= one symbol =================
+        br.refill();
+        uint32_t e = lit_fast[(uint32_t)br.bb & ((1u << LR) - 1u)];
+        if (e == 0u) {
+            e = lane_slow_decode(br.bb, lit_count, lit_sym, LR, lit_pf, lit_pi);
+            if (e == 0u) { err = 11; in_block = false; continue; }
+        }
+        br.drop((int)(e & 15u));
+        uint32_t sym = e >> 4;
+        if (sym < 256u) {
+            if (opos >= cap) { err = 15; in_block = false; continue; }
+            if (pend == 0u && ((reinterpret_cast<uintptr_t>(dst) + opos) & 3u) != 0u) {
+                dst[opos++] = (uint8_t)sym;                            // not on a word boundary yet (stream start / after a match)
+            } else {
+                wbuf |= sym << (8u * pend); ++pend; ++opos;
+                if (pend == 4u) { *reinterpret_cast<uint32_t*>(dst + opos - 4u) = wbuf; pend = 0; wbuf = 0; }
+            }
+            continue;
+        }
+        if (sym == 256u) { in_block = false; if (br.overrun()) err = 18; continue; }
+        sym -= 257u;
+        if (sym >= 29u) { err = 12; in_block = false; continue; }
+        // length: base and extra bits from the symbol (RFC 1951 3.2.5)
+        const uint32_t lx = sym < 8u ? 0u : (sym == 28u ? 0u : (sym - 4u) >> 2);
+        const uint32_t lbase = sym < 8u ? sym + 3u : (sym == 28u ? 258u : ((4u + (sym & 3u)) << lx) + 3u);
+        const uint32_t len = lbase + br.peek((int)lx);
+        br.drop((int)lx);
+        br.refill();
+        e = dist_fast[(uint32_t)br.bb & ((1u << DR) - 1u)];
+        if (e == 0u) {
+            e = lane_slow_decode(br.bb, dist_count, dist_sym, DR, dist_pf, dist_pi);
+            if (e == 0u) { err = 13; in_block = false; continue; }
+        }
+        br.drop((int)(e & 15u));
+        const uint32_t ds = e >> 4;
+        if (ds >= 30u) { err = 14; in_block = false; continue; }
+        const uint32_t dx = ds < 4u ? 0u : (ds - 2u) >> 1;
+        const uint32_t dbase = ds < 4u ? ds + 1u : ((2u + (ds & 1u)) << dx) + 1u;
+        const uint32_t dist = dbase + br.peek((int)dx);
+        br.drop((int)dx);
+        if (dist > opos) { err = 16; in_block = false; continue; }
+        if (opos + len > cap) { err = 15; in_block = false; continue; }
+        flush_pending();
+        {
+            const uint8_t* srcp = dst + opos - dist;
+            uint8_t* d = dst + opos;
+            if (dist >= len) {                       // no overlap: loads first, then stores (4-way ILP)
+                uint32_t k = 0;
+                for (; k + 4 <= len; k += 4) {
+                    const uint8_t a0 = srcp[k], a1 = srcp[k + 1], a2 = srcp[k + 2], a3 = srcp[k + 3];
+                    d[k] = a0; d[k + 1] = a1; d[k + 2] = a2; d[k + 3] = a3;
+                }
+                for (; k < len; ++k) d[k] = srcp[k];
+            } else {
+                for (uint32_t k = 0; k < len; ++k) d[k] = *(volatile const uint8_t*)(srcp + k);   // run: each byte may depend on the previous store
+            }
+        }
+        opos += len;
+    }
+    if (!err) flush_pending();
+    if (!err && opos != cap) err = 17;
+    status[b] = err;
+}
+
+template <int LR, int DR>
+static void launch_lanes(const uint8_t* comp, const BgzfBlock* bl, uint32_t n_blocks, uint8_t* out, uint32_t* status, cudaStream_t stream) {
+    constexpr int sh = 32 * LaneLayout<LR, DR>::STRIDE;
+    static bool attr = false;
+    if (!attr) {
+        attr = true;
+        cudaFuncSetAttribute(bgzf_inflate_lanes_kernel<LR, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, sh);
+        cudaFuncSetAttribute(bgzf_inflate_lanes_kernel<LR, DR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    }
+    bgzf_inflate_lanes_kernel<LR, DR><<<(n_blocks + 31) / 32, 32, sh, stream>>>(comp, bl, n_blocks, out, status);
+}
+
 __global__ void inflate_status_reduce_kernel(const uint32_t* __restrict__ status, uint32_t n, uint32_t* __restrict__ flags) {
     uint32_t bad = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) bad |= status[i];
@@ -590,8 +844,21 @@ void launch_inflate_status_reduce(const uint32_t* status, uint32_t n_blocks, uin
 void launch_bgzf_inflate(const uint8_t* comp, const void* blocks, uint32_t n_blocks, uint8_t* out, uint32_t* status,
                          cudaStream_t stream) {
     if (n_blocks == 0) return;
-    static int mode = -1;                                  // RTJX_INFLATE_VARIANT: 0 auto, 1 warp per block, 2 thread per block
-    if (mode < 0) { const char* v = getenv("RTJX_INFLATE_VARIANT"); mode = v ? atoi(v) : 0; }
+    // RTJX_INFLATE_VARIANT: 0 auto, 1 warp per block, 3 lane per stream (2: the round-1 thread-per-block build, kept for A/B).
+    // Read at every launch (a getenv, nanoseconds) so that tests can switch kernels inside one process.
+    int mode = 0;
+    { const char* v = getenv("RTJX_INFLATE_VARIANT"); mode = v ? atoi(v) : 0; }
+    // lane-per-stream decoder: default whenever the launch has enough blocks to occupy the lanes (RTJX_INFLATE_VARIANT=3 forces
+    // it, =1 forces the warp-per-block kernel); RTJX_INFLATE_ROOT picks the root-table width (10 default, 9 / 11 for A/B)
+    int root = 10;
+    { const char* v = getenv("RTJX_INFLATE_ROOT"); if (v) root = atoi(v); }
+    if (mode == 3 || (mode == 0 && n_blocks >= 2048)) {
+        const BgzfBlock* bl = static_cast<const BgzfBlock*>(blocks);
+        if (root == 9) launch_lanes<9, 7>(comp, bl, n_blocks, out, status, stream);
+        else if (root == 11) launch_lanes<11, 8>(comp, bl, n_blocks, out, status, stream);
+        else launch_lanes<10, 8>(comp, bl, n_blocks, out, status, stream);
+        return;
+    }
     if (mode == 2) {        // thread-per-block only pays with >~100k blocks in one launch; opt-in for now
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(bgzf_inflate_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_THREADS * SI_STRIDE); attr = true; }

@@ -63,7 +63,7 @@ struct ScanParams {
     int32_t  strandness;          // 0 XS, 1 RF, 2/3 FR
     uint32_t min_anchor, min_intron, max_intron;
     uint32_t debug;               // developer switches for A/B measurements (0 in production)
-    int32_t  variant;             // cigar_scan variant: 5 = scan -> candidates -> junction_merge (default), 6 = fused scan + table update
+    int32_t  variant;             // cigar_scan variant: 8 = warp-pipelined persistent scan -> candidates -> junction_merge (default), 5 = block per tile, 6 = fused scan + table update
     int32_t  cfg;                 // tile configuration of the variant (0 = production)
     // intron-motif strand mode (a FASTA was given): the genome as one byte per base in HBM.  NULL = off.
     const uint8_t*            genome;
@@ -110,6 +110,9 @@ struct TableRef {
 // Launchers (kernels.cu).  All are asynchronous on `stream`.
 // tile_off_scratch: cigar_scan_tiles(n_reads) + 1 words of device scratch for the per-tile CIGAR offsets (may be NULL)
 uint32_t cigar_scan_tiles(uint32_t n_reads);
+// Candidate slots cigar_scan may reserve beyond the N ops of a batch (chunked reservation, see the pipelined kernel):
+// size the candidate buffer, and junction_merge's bound, as N ops + this.
+uint32_t cigar_scan_cand_slack();
 void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
                        uint32_t* d_counters /* [0]=n_cand, [1]=overflowed */, uint32_t* tile_off_scratch,
                        const CandRegions& regions, cudaStream_t stream);

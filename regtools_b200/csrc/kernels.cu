@@ -930,6 +930,429 @@ cigar_scan_gather_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, ui
     }
 }
 
+struct WalkCand { uint32_t start, end, left, right, k; };
+
+// Forward walk that records the first two N ops in registers (c0, c1) and counts all of them.  Predicated, no
+// branches and no calls: same arithmetic as walk_fast, the first four ops are fetched by independent loads (op code
+// 15 is a transparent filler), the rest in a loop.  Alignments with more than two N ops (rare) are finished by
+// fused_walk_rest.  Returns the number of N ops.
+template <bool FROM_SMEM>
+__device__ __forceinline__ uint32_t walk_collect(const uint32_t* __restrict__ ops, uint32_t n, uint32_t pos,
+                                                 WalkCand& c0, WalkCand& c1) {
+    const uint32_t ANC = (1u << 0) | (1u << 7);
+    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
+    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
+    constexpr int PRE = 4;
+    uint32_t w[PRE];
+#pragma unroll
+    for (int i = 0; i < PRE; ++i) w[i] = (uint32_t)i < n ? (FROM_SMEM ? ops[i] : __ldg(ops + i)) : 0xfu;
+    uint32_t cur = pos, run = 0, nc = 0;
+    bool pending = false;
+    auto step = [&](uint32_t x, uint32_t i) {
+        const uint32_t op = x & 0xfu, len = x >> 4, bit = 1u << op;
+        const bool brk = (bit & BRK) != 0, is_n = op == 3u;
+        const bool close = pending && brk;                  // the open junction ends here: right anchor = run
+        c0.right = (close && nc == 1u) ? run : c0.right;
+        c1.right = (close && nc == 2u) ? run : c1.right;
+        const bool open0 = is_n && nc == 0u, open1 = is_n && nc == 1u;
+        const uint32_t kk = i > 0xffffu ? 0xffffu : i;
+        c0.start = open0 ? cur : c0.start; c0.end = open0 ? cur + len : c0.end; c0.left = open0 ? run : c0.left; c0.k = open0 ? kk : c0.k;
+        c1.start = open1 ? cur : c1.start; c1.end = open1 ? cur + len : c1.end; c1.left = open1 ? run : c1.left; c1.k = open1 ? kk : c1.k;
+        nc += is_n ? 1u : 0u;
+        pending = brk ? is_n : pending;
+        run = brk ? 0u : run + ((bit & ANC) ? len : 0u);
+        cur += (bit & REFC) ? len : 0u;
+    };
+#pragma unroll
+    for (int i = 0; i < PRE; ++i) step(w[i], (uint32_t)i);
+    for (uint32_t i = PRE; i < n; ++i) step(FROM_SMEM ? ops[i] : __ldg(ops + i), i);
+    c0.right = (pending && nc == 1u) ? run : c0.right;
+    c1.right = (pending && nc == 2u) ? run : c1.right;
+    return nc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cigar_scan, warp-pipelined persistent version (variant 8)
+// ------------------------------------------------------------------------------------------------
+// Round-1 finding (profiles/r1_scan_ab.md, r2_scan_ab_occupancy_variants.json): the block-per-tile kernels stream at 0.43-0.47
+// of the copy peak whatever their occupancy, because every block spends most of its life with no load in flight (columns ->
+// barrier -> dependent slab -> barrier -> walk -> atomic round trip -> flush).  Here nothing waits on a block:
+//   * a WARP owns tiles of PW alignments (its four 512-byte column slices + its CIGAR slab) and keeps a ring of NST stages
+//     in shared memory filled with 16-byte cp.async (LDGSTS); D = NST-1 tiles are always in flight per warp, so
+//     warps/SM x D x ~2.7 KB stay outstanding to HBM while the warp walks the tile that has landed;
+//   * the only data-dependent address — the slab, [cig_off[base], cig_off[base + PW]) — is resolved one iteration earlier by
+//     two scalar loads of the NEXT tile's bounds, so the slab request leaves together with the columns;
+//   * synchronisation is __syncwarp only (no __syncthreads, no named barriers, no mbarriers);
+//   * candidates go straight from registers to HBM (one 32-byte sector each, neighbouring lanes neighbouring sectors) into
+//     chunks of PCH slots the warp reserves with one atomic per chunk; a warp's unused tail is filled with tid = -1
+//     entries, which junction_merge skips.  CTR_NCAND therefore counts reserved slots, not candidates.
+// The plain mode keeps the first two N ops of an alignment in registers (walk_collect, branch-free) and stores them
+// after a warp prefix sum; the third and later N ops, and the intron-motif / variant-region / barcode modes, use the generic
+// per-candidate path (a shared-memory cursor into the warp's chunk).
+constexpr int PW  = 128;                          // alignments per warp tile (4 per lane)
+constexpr int PCH = 64;                           // candidate slots per reserved chunk
+
+template <int SL>
+struct alignas(16) PipeStage {
+    uint32_t off[PW + 4];
+    uint32_t pos[PW];
+    uint32_t meta[PW];
+    uint32_t tid[PW];
+    uint32_t slab[SL];
+};
+template <int SL, int NST>
+struct alignas(16) PipeWarpSmem {
+    PipeStage<SL> st[NST];
+    uint32_t cur, end;                            // generic path: cursor into the warp's reserved chunk
+    uint32_t pad[2];
+    uint8_t  work[PW];
+};
+
+__device__ __forceinline__ void store_cand(Cand* __restrict__ out, uint32_t cap, uint32_t* counters, uint32_t idx,
+                                           const uint4& a, const uint4& b) {
+    if (idx < cap) { uint4* o = reinterpret_cast<uint4*>(out + idx); o[0] = a; o[1] = b; }
+    else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
+}
+
+// generic per-candidate emit of the pipelined kernel (any lane, any time)
+template <class WS, bool MOTIF, bool VREG, bool BC>
+struct PipeEmit {
+    WS& ws; Cand* __restrict__ out; uint32_t cap; uint32_t* counters;
+    const ScanParams* prm; uint32_t* jstrand; const int32_t* rspan;
+    __device__ __forceinline__ void push(const uint4& a, const uint4& b) const {
+        uint32_t i = atomicAdd(&ws.cur, 1u);
+        if (i >= ws.end) i = atomicAdd(&counters[CTR_NCAND], 1u);          // chunk exhausted mid-round: one slot at a time
+        store_cand(out, cap, counters, i, a, b);
+    }
+    __device__ __forceinline__ void operator()(uint32_t start, uint32_t end, uint32_t left, uint32_t right,
+                                               uint64_t ord, int32_t tid, uint32_t strand) const {
+        if (MOTIF) {                                           // set_junction_strand with a FASTA (:345-359): motif first
+            const uint32_t m = motif_strand(*prm, tid, start, end, *jstrand, counters);
+            if (BC) { if (m != '?') strand = (strand & ~0xffu) | m; *jstrand = strand & 0xffu; }
+            else { if (m != '?') strand = m; *jstrand = strand; }
+        }
+        const uint4 a = make_uint4(start, end, start - left, end + right);
+        const uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
+        if (!VREG) { push(a, b); return; }
+        // one candidate per variant region the ALIGNMENT belongs to (tid, pos < end, endpos > beg; hts.c:1941-1963)
+        const VariantRegions& vr = prm->vr;
+        const int32_t rp = rspan[0], re = rspan[1];
+        uint32_t lo = 0, hi = vr.n;                            // first region with (tid, beg) >= (tid, endpos)
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const int32_t mt = vr.tid[mid];
+            if (mt < tid || (mt == tid && vr.beg[mid] < re)) lo = mid + 1; else hi = mid;
+        }
+        for (uint32_t i = lo; i-- > 0;) {
+            if (vr.tid[i] != tid) break;
+            if ((long long)vr.beg[i] + (long long)vr.max_len <= (long long)rp) break;    // no earlier region can reach pos
+            if (vr.end[i] > rp) push(a, make_uint4(b.x, b.y, b.z, strand | (i + 1u) << 8));
+        }
+    }
+};
+
+// third and later N ops of an alignment in the plain mode (rare): plain walk from global memory, one slot each
+__device__ __noinline__ void pipe_walk_rest(const uint32_t* __restrict__ ops, uint32_t n, uint32_t pos, int32_t tid, uint32_t strand,
+                                            uint64_t read_ord, Cand* __restrict__ out, uint32_t cap, uint32_t* counters) {
+    const uint32_t ANC = (1u << 0) | (1u << 7);
+    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
+    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
+    uint32_t cur = pos, run = 0, nc = 0;
+    bool pending = false;
+    uint32_t p_start = 0, p_end = 0, p_left = 0, p_k = 0;
+    auto emit = [&]() {
+        if (nc <= 2u) return;
+        const uint64_t ord = read_ord << 16 | p_k;
+        const uint32_t g = atomicAdd(&counters[CTR_NCAND], 1u);
+        store_cand(out, cap, counters, g, make_uint4(p_start, p_end, p_start - p_left, p_end + run),
+                   make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
+    };
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t x = __ldg(ops + i), op = x & 0xfu, len = x >> 4, bit = 1u << op;
+        if (bit & BRK) {
+            if (pending) emit();
+            pending = op == 3u;
+            if (pending) { p_start = cur; p_end = cur + len; p_left = run; p_k = i > 0xffffu ? 0xffffu : i; ++nc; }
+            run = 0;
+        } else if (bit & ANC) {
+            run += len;
+        }
+        if (bit & REFC) cur += len;
+    }
+    if (pending) emit();
+}
+
+template <int N> __device__ __forceinline__ void cp_async_wait_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Processes the tile that sits in stage `st` (PW alignments from `base`): work list, walk, candidate stores.
+template <int SL, class WS, bool MOTIF, bool VREG, bool BC>
+__device__ __forceinline__ void pipe_process_tile(WS& ws, PipeStage<SL>& st, const BatchView& b, const ScanParams& prm, uint32_t base,
+                                                  uint32_t lane, uint32_t vec_end, Cand* __restrict__ out, uint32_t cap,
+                                                  uint32_t* __restrict__ counters, uint32_t& c_cur, uint32_t& c_end) {
+    constexpr bool GENERIC = MOTIF || VREG || BC;
+    const uint32_t n_tile = min((uint32_t)PW, b.n_reads - base);
+    const uint32_t lo = st.off[0], hi = st.off[n_tile], a0 = lo & ~3u;
+    uint32_t n_st = 0;                                         // words of the slab staged in shared memory (from a0)
+    if (hi > lo) { const uint32_t end = min(min((hi + 3u) & ~3u, a0 + (uint32_t)SL), vec_end); n_st = end > a0 ? end - a0 : 0u; }
+
+    // ---- work list of the alignments with more than one CIGAR op (junctions_extractor.cc:379)
+    uint32_t n_work;
+    {
+        const uint4 o = *reinterpret_cast<const uint4*>(&st.off[4 * lane]);
+        const uint32_t o4 = st.off[4 * lane + 4];
+        const uint32_t r0 = 4 * lane;
+        uint32_t flags = 0;
+        if (r0 + 0 < n_tile && o.y - o.x > 1u) flags |= 1u;
+        if (r0 + 1 < n_tile && o.z - o.y > 1u) flags |= 2u;
+        if (r0 + 2 < n_tile && o.w - o.z > 1u) flags |= 4u;
+        if (r0 + 3 < n_tile && o4 - o.w > 1u) flags |= 8u;
+        const uint32_t cnt = __popc(flags);
+        uint32_t x = cnt;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
+        n_work = __shfl_sync(0xffffffffu, x, 31);
+        uint32_t p = x - cnt;
+        if (flags & 1u) ws.work[p++] = (uint8_t)(r0 + 0);
+        if (flags & 2u) ws.work[p++] = (uint8_t)(r0 + 1);
+        if (flags & 4u) ws.work[p++] = (uint8_t)(r0 + 2);
+        if (flags & 8u) ws.work[p++] = (uint8_t)(r0 + 3);
+    }
+    __syncwarp();
+
+    // ---- walk, one alignment per lane, rounds of 32
+    for (uint32_t w0 = 0; w0 < n_work; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        if (!GENERIC) {
+            uint32_t nc = 0, strand = 0;
+            int32_t tid = -1;
+            uint64_t read_ord = 0;
+            WalkCand c0{0, 0, 0, 0, 0}, c1{0, 0, 0, 0, 0};
+            if (w < n_work) {
+                const uint32_t r = ws.work[w];
+                tid = (int32_t)st.tid[r];
+                if (tid >= 0) {
+                    const uint32_t o0 = st.off[r], n = st.off[r + 1] - o0;
+                    strand = read_strand(st.meta[r], prm.strandness);
+                    read_ord = b.first_ordinal + base + r;
+                    const bool in_smem = (o0 - a0) + n <= n_st;
+                    nc = in_smem ? walk_collect<true>(st.slab + (o0 - a0), n, st.pos[r], c0, c1)
+                                 : walk_collect<false>(b.cigar + o0, n, st.pos[r], c0, c1);
+                    if (nc > 2u) pipe_walk_rest(b.cigar + o0, n, st.pos[r], tid, strand, read_ord, out, cap, counters);
+                }
+            }
+            const uint32_t n2 = min(nc, 2u);
+            uint32_t x = n2;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
+            const uint32_t tot = __shfl_sync(0xffffffffu, x, 31);
+            if (tot) {
+                const uint32_t rem = c_end - c_cur;
+                uint32_t nbase = 0;
+                if (tot > rem) {                              // the chunk runs out inside this round: the rest goes to a new one
+                    if (lane == 0) nbase = atomicAdd(&counters[CTR_NCAND], (uint32_t)PCH);
+                    nbase = __shfl_sync(0xffffffffu, nbase, 0);
+                }
+                const uint32_t j0 = x - n2;
+                if (n2 > 0u) {
+                    const uint64_t ord = read_ord << 16 | c0.k;
+                    store_cand(out, cap, counters, j0 < rem ? c_cur + j0 : nbase + (j0 - rem),
+                               make_uint4(c0.start, c0.end, c0.start - c0.left, c0.end + c0.right),
+                               make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
+                }
+                if (n2 > 1u) {
+                    const uint64_t ord = read_ord << 16 | c1.k;
+                    const uint32_t j1 = j0 + 1u;
+                    store_cand(out, cap, counters, j1 < rem ? c_cur + j1 : nbase + (j1 - rem),
+                               make_uint4(c1.start, c1.end, c1.start - c1.left, c1.end + c1.right),
+                               make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
+                }
+                if (tot > rem) { c_cur = nbase + (tot - rem); c_end = nbase + (uint32_t)PCH; } else c_cur += tot;
+            }
+        } else {
+            // make sure the round starts with a chunk that holds 64 more candidates; pad what is left of the old one
+            if (ws.end - min(ws.cur, ws.end) < 64u) {
+                const uint32_t pc = min(ws.cur, ws.end), pe = ws.end;
+                __syncwarp();
+                for (uint32_t i = pc + lane; i < pe; i += 32) store_cand(out, cap, counters, i, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0xffffffffu, 0));
+                uint32_t nbase = 0;
+                if (lane == 0) nbase = atomicAdd(&counters[CTR_NCAND], 2u * PCH);
+                nbase = __shfl_sync(0xffffffffu, nbase, 0);
+                if (lane == 0) { ws.cur = nbase; ws.end = nbase + 2u * PCH; }
+                __syncwarp();
+            }
+            if (w < n_work) {
+                const uint32_t r = ws.work[w];
+                const int32_t tid = (int32_t)st.tid[r];
+                if (tid >= 0) {
+                    const uint32_t o0 = st.off[r], n = st.off[r + 1] - o0;
+                    uint32_t strand = read_strand(st.meta[r], prm.strandness);
+                    if (BC) strand |= (__ldg(b.bc + base + r) + 1u) << 8;      // set_junction_barcode (:362-374): one barcode per alignment
+                    const uint64_t read_ord = b.first_ordinal + base + r;
+                    uint32_t jstrand = 0;                     // j1.strand == "" before an alignment's first junction
+                    int32_t rspan[2] = {0, 0};
+                    const bool in_smem = (o0 - a0) + n <= n_st;
+                    if (VREG) {                                // endpos = pos + reference length of the CIGAR (sam.c:327-342)
+                        uint32_t rl = 0;
+                        for (uint32_t q = 0; q < n; ++q) {
+                            const uint32_t x = in_smem ? st.slab[o0 - a0 + q] : __ldg(b.cigar + o0 + q);
+                            if ((0x18Du >> (x & 0xfu)) & 1u) rl += x >> 4;      // M, D, N, =, X consume the reference
+                        }
+                        // bam_endpos (sam.c:336-342): an alignment flagged BAM_FUNMAP spans one base whatever its CIGAR says
+                        const bool unmapped = ((st.meta[r] >> 16) & 4u) != 0;
+                        rspan[0] = (int32_t)st.pos[r]; rspan[1] = (int32_t)(st.pos[r] + (unmapped ? 1u : rl));
+                    }
+                    const PipeEmit<WS, MOTIF, VREG, BC> emit{ws, out, cap, counters, &prm, &jstrand, rspan};
+                    if (in_smem) walk_fast<true>(st.slab + (o0 - a0), n, st.pos[r], tid, strand, read_ord, emit);
+                    else walk_fast<false>(b.cigar + o0, n, st.pos[r], tid, strand, read_ord, emit);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// LOADS: 0 = cp.async (LDGSTS) into a ring of NST stages, NST - 1 tiles in flight per warp;
+//        1 = register-staged: the next tile's 128-bit loads are issued into registers before the current tile is walked and stored
+//            to the (single) stage afterwards — one tile in flight per warp, more warps per SM (NST must be 1).
+template <int SL, int NST, int NWARP, int MINB, int LOADS, bool MOTIF, bool VREG, bool BC>
+__global__ void __launch_bounds__(NWARP * 32, MINB)
+cigar_scan_pipe_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
+    using WS = PipeWarpSmem<SL, NST>;
+    constexpr bool GENERIC = MOTIF || VREG || BC;
+    static_assert(LOADS == 0 ? NST >= 2 : NST == 1, "ring depth does not fit the load mode");
+    static_assert(SL % 128 == 0, "slab window must be a multiple of 128 words");
+    constexpr int D = LOADS == 0 ? NST - 1 : 1;               // tiles in flight per warp
+    constexpr int SLV = SL / 128;                             // 16-byte slab vectors per lane
+    extern __shared__ __align__(16) unsigned char pipe_raw[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    WS& ws = reinterpret_cast<WS*>(pipe_raw)[warp];
+    const uint32_t n_wt = (b.n_reads + PW - 1) / PW;           // warp tiles in the batch
+    const uint32_t TW = gridDim.x * NWARP, gw = blockIdx.x * NWARP + warp;
+    const uint32_t n_my = gw < n_wt ? (n_wt - gw + TW - 1) / TW : 0u;
+    const uint32_t vec_end = b.n_ops & ~3u;
+    if (GENERIC) { if (lane == 0) { ws.cur = 0; ws.end = 0; } __syncwarp(); }
+    if (n_my == 0) return;
+
+    // Slab bounds (the only data-dependent address of a tile) are fetched 16 tiles at a time, one batch ahead: lane 2j holds
+    // cig_off[base] and lane 2j+1 cig_off[min(base + PW, n_reads)] of tile 16q + j, so no tile waits for them.
+    auto load_bq = [&](uint32_t q) -> uint32_t {
+        const uint32_t kk = q * 16u + (lane >> 1);
+        if (kk >= n_my) return 0u;
+        const uint32_t base = (gw + kk * TW) * PW;
+        return __ldg(b.cig_off + ((lane & 1u) ? min(base + (uint32_t)PW, b.n_reads) : base));
+    };
+    uint32_t bq_cur = load_bq(0), bq_next = load_bq(1);
+    auto bounds_of = [&](uint32_t kk, uint32_t& lo, uint32_t& hi) {   // called for kk = 0, 1, 2, ... in order, once each
+        if (kk != 0u && (kk & 15u) == 0u) { bq_cur = bq_next; bq_next = load_bq((kk >> 4) + 1u); }
+        lo = __shfl_sync(0xffffffffu, bq_cur, 2 * (kk & 15u));
+        hi = __shfl_sync(0xffffffffu, bq_cur, 2 * (kk & 15u) + 1);
+    };
+    uint32_t c_cur = 0, c_end = 0;                            // plain mode: the warp's chunk (uniform registers)
+
+    if (LOADS == 0) {
+        auto issue = [&](uint32_t kk) {
+            uint32_t lo, hi;
+            bounds_of(kk, lo, hi);
+            const uint32_t base = (gw + kk * TW) * PW;
+            PipeStage<SL>& st = ws.st[kk % NST];
+            if (base + PW + 3 <= b.n_reads) {                 // the (PW + 4)-entry cig_off window is in bounds
+                cp_async16(&st.off[4 * lane], b.cig_off + base + 4 * lane);
+                cp_async16(&st.pos[4 * lane], b.pos + base + 4 * lane);
+                cp_async16(&st.meta[4 * lane], b.meta + base + 4 * lane);
+                cp_async16(&st.tid[4 * lane], b.tid + base + 4 * lane);
+                if (lane == 0) cp_async16(&st.off[PW], b.cig_off + base + PW);
+            } else {                                          // ragged tail of the batch: plain loads
+                const uint32_t n_tile = min((uint32_t)PW, b.n_reads - base);
+                for (uint32_t r = lane; r < n_tile; r += 32) {
+                    st.pos[r] = (uint32_t)b.pos[base + r]; st.meta[r] = b.meta[base + r]; st.tid[r] = (uint32_t)b.tid[base + r];
+                }
+                for (uint32_t r = lane; r <= n_tile; r += 32) st.off[r] = b.cig_off[base + r];
+            }
+            if (hi > lo) {
+                const uint32_t a0 = lo & ~3u;
+                const uint32_t end = min(min((hi + 3u) & ~3u, a0 + (uint32_t)SL), vec_end);
+                const uint32_t nv = end > a0 ? (end - a0) >> 2 : 0u;
+                for (uint32_t v = lane; v < nv; v += 32) cp_async16(&st.slab[4 * v], b.cigar + a0 + 4 * v);
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < D; ++j) {                         // prologue: D tiles in flight
+            if ((uint32_t)j < n_my) issue(j);
+            cp_async_commit();
+        }
+        for (uint32_t k = 0; k < n_my; ++k) {
+            if (k + D < n_my) issue(k + D);
+            cp_async_commit();
+            cp_async_wait_n<D>();                             // this lane's copies of tile k have landed ...
+            __syncwarp();                                     // ... and so have every other lane's
+            pipe_process_tile<SL, WS, MOTIF, VREG, BC>(ws, ws.st[k % NST], b, prm, (gw + k * TW) * PW, lane, vec_end, out, cap, counters, c_cur, c_end);
+            __syncwarp();                                     // the stage and the work list are rewritten from the next iteration on
+        }
+    } else {
+        uint4 r_off, r_pos, r_meta, r_tid, r_sl[SLV];
+        uint32_t r_lo = 0, r_hi = 0;
+        auto load_tile = [&](uint32_t kk) {
+            bounds_of(kk, r_lo, r_hi);
+            const uint32_t base = (gw + kk * TW) * PW;
+            if (base + PW + 3 <= b.n_reads) {
+                r_off = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cig_off + base) + lane);
+                r_pos = ldg_stream_u4(reinterpret_cast<const uint4*>(b.pos + base) + lane);
+                r_meta = ldg_stream_u4(reinterpret_cast<const uint4*>(b.meta + base) + lane);
+                r_tid = ldg_stream_u4(reinterpret_cast<const uint4*>(b.tid + base) + lane);
+            }
+            if (r_hi > r_lo) {
+                const uint32_t a0 = r_lo & ~3u;
+                const uint32_t end = min(min((r_hi + 3u) & ~3u, a0 + (uint32_t)SL), vec_end);
+                const uint32_t nv = end > a0 ? (end - a0) >> 2 : 0u;
+#pragma unroll
+                for (int j = 0; j < SLV; ++j)
+                    if (lane + 32u * j < nv) r_sl[j] = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cigar + a0) + lane + 32u * j);
+            }
+        };
+        auto store_tile = [&](uint32_t kk) {                  // registers -> the stage (waits for the loads of tile kk)
+            const uint32_t base = (gw + kk * TW) * PW;
+            PipeStage<SL>& st = ws.st[0];
+            if (base + PW + 3 <= b.n_reads) {
+                *reinterpret_cast<uint4*>(&st.off[4 * lane]) = r_off;
+                *reinterpret_cast<uint4*>(&st.pos[4 * lane]) = r_pos;
+                *reinterpret_cast<uint4*>(&st.meta[4 * lane]) = r_meta;
+                *reinterpret_cast<uint4*>(&st.tid[4 * lane]) = r_tid;
+                if (lane == 0) st.off[PW] = r_hi;
+            } else {
+                const uint32_t n_tile = min((uint32_t)PW, b.n_reads - base);
+                for (uint32_t r = lane; r < n_tile; r += 32) {
+                    st.pos[r] = (uint32_t)b.pos[base + r]; st.meta[r] = b.meta[base + r]; st.tid[r] = (uint32_t)b.tid[base + r];
+                }
+                for (uint32_t r = lane; r <= n_tile; r += 32) st.off[r] = b.cig_off[base + r];
+            }
+            if (r_hi > r_lo) {
+                const uint32_t a0 = r_lo & ~3u;
+                const uint32_t end = min(min((r_hi + 3u) & ~3u, a0 + (uint32_t)SL), vec_end);
+                const uint32_t nv = end > a0 ? (end - a0) >> 2 : 0u;
+#pragma unroll
+                for (int j = 0; j < SLV; ++j)
+                    if (lane + 32u * j < nv) *reinterpret_cast<uint4*>(&st.slab[4 * (lane + 32u * j)]) = r_sl[j];
+            }
+        };
+        load_tile(0);
+        for (uint32_t k = 0; k < n_my; ++k) {
+            store_tile(k);
+            __syncwarp();
+            if (k + 1 < n_my) load_tile(k + 1);               // in flight while tile k is walked
+            pipe_process_tile<SL, WS, MOTIF, VREG, BC>(ws, ws.st[0], b, prm, (gw + k * TW) * PW, lane, vec_end, out, cap, counters, c_cur, c_end);
+            __syncwarp();
+        }
+    }
+    // ---- unused tail of the warp's last chunk: entries junction_merge skips
+    if (!GENERIC) {
+        for (uint32_t i = c_cur + lane; i < c_end; i += 32) store_cand(out, cap, counters, i, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0xffffffffu, 0));
+    } else {
+        __syncwarp();
+        const uint32_t pc = min(ws.cur, ws.end), pe = ws.end;
+        for (uint32_t i = pc + lane; i < pe; i += 32) store_cand(out, cap, counters, i, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0xffffffffu, 0));
+    }
+}
+
 // pre-pass: tile_off[t] = cig_off[min(t * S5_TILE, n_reads)] (one 4-byte load per tile; the result stays in L2)
 __global__ void tile_offsets_kernel(const uint32_t* __restrict__ cig_off, uint32_t n_reads, uint32_t n_tiles, uint32_t tile, uint32_t* __restrict__ tile_off) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -953,12 +1376,69 @@ void cigar_scan_region_layout(uint32_t n_reads, uint32_t* n_regions, uint32_t* c
     else { *n_regions = 0; *cap = 0; }
 }
 
+// Launch of the warp-pipelined kernel: persistent grid of BPS blocks per SM, NWARP warps each.
+template <int SL, int NST, int NWARP, int BPS, int LOADS, bool MOTIF, bool VREG, bool BC>
+static void launch_pipe_mode(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap, uint32_t* d_counters, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)NWARP * sizeof(PipeWarpSmem<SL, NST>);
+    static_assert((smem + 1024) * BPS <= 228u * 1024u, "pipelined scan: shared memory of the resident blocks exceeds an SM");
+    auto kern = cigar_scan_pipe_kernel<SL, NST, NWARP, BPS, LOADS, MOTIF, VREG, BC>;
+    static bool once = false;
+    if (!once) {
+        once = true;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (getenv("RTJX_TRACE")) {
+            int nb = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NWARP * 32, smem);
+            fprintf(stderr, "[rtjx] cigar_scan_pipe<SL %d, NST %d, %d warps, %d blocks/SM asked, loads %d>: %zu B shared memory per block, %d blocks/SM resident\n",
+                    SL, NST, NWARP, BPS, LOADS, smem, nb);
+        }
+    }
+    const uint32_t n_wt = (b.n_reads + PW - 1) / PW;
+    const uint32_t grid = max(1u, min((n_wt + NWARP - 1) / NWARP, (uint32_t)(num_sms() * BPS)));
+    kern<<<grid, NWARP * 32, smem, stream>>>(b, p, cands, cand_cap, d_counters);
+}
+template <int SL, int NST, int NWARP, int BPS, int LOADS = 0, bool SPECIAL = false>
+static void launch_pipe(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap, uint32_t* d_counters, cudaStream_t stream) {
+    if constexpr (SPECIAL) {                                  // intron-motif / variant-region / barcode modes
+        if (b.bc && p.genome) launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, true, false, true>(b, p, cands, cand_cap, d_counters, stream);
+        else if (b.bc) launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, false, false, true>(b, p, cands, cand_cap, d_counters, stream);
+        else if (p.vr.n && p.genome) launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, true, true, false>(b, p, cands, cand_cap, d_counters, stream);
+        else if (p.vr.n) launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, false, true, false>(b, p, cands, cand_cap, d_counters, stream);
+        else launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, true, false, false>(b, p, cands, cand_cap, d_counters, stream);
+    } else {
+        launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, false, false, false>(b, p, cands, cand_cap, d_counters, stream);
+    }
+}
+// Candidate slots cigar_scan may reserve beyond the number of N ops of a batch (every warp's last chunk is partly padding).
+uint32_t cigar_scan_cand_slack() { return (uint32_t)num_sms() * 64u * 2u * (uint32_t)PCH + 1024u; }
+
 void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
                        uint32_t* d_counters, uint32_t* tile_off_scratch, const CandRegions& regions, cudaStream_t stream) {
     if (b.n_reads == 0) return;
     const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
                             reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
                             reinterpret_cast<uintptr_t>(b.cigar);
+    if ((align & 15u) == 0 && p.variant == 8) {
+        const bool special = p.genome || p.vr.n || b.bc;
+        if (special) { launch_pipe<384, 3, 8, 2, 0, true>(b, p, cands, cand_cap, d_counters, stream); return; }
+        switch (p.cfg) {                   // A/B configurations; 0 is the production one
+        case 1: launch_pipe<384, 2, 8, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 24 warps/SM, 1 tile in flight each
+        case 2: launch_pipe<384, 4, 4, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 12 warps/SM, 3 in flight
+        case 3: launch_pipe<256, 2, 8, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 32 warps/SM, 1 in flight
+        case 4: launch_pipe<384, 3, 4, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 16 warps/SM as 4 small blocks
+        case 5: launch_pipe<256, 3, 8, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 24 warps/SM, 2 in flight
+        case 6: launch_pipe<384, 3, 8, 1>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 8 warps/SM (latency probe)
+        case 7: launch_pipe<384, 4, 5, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 15 warps/SM, 3 in flight
+        case 10: launch_pipe<384, 1, 8, 2, 1>(b, p, cands, cand_cap, d_counters, stream); break;  // register-staged: 16 warps/SM
+        case 11: launch_pipe<384, 1, 8, 3, 1>(b, p, cands, cand_cap, d_counters, stream); break;  // register-staged: 24 warps/SM
+        case 12: launch_pipe<384, 1, 8, 4, 1>(b, p, cands, cand_cap, d_counters, stream); break;  // register-staged: 32 warps/SM (64 registers)
+        case 13: launch_pipe<384, 1, 4, 5, 1>(b, p, cands, cand_cap, d_counters, stream); break;  // register-staged: 20 warps/SM
+        case 14: launch_pipe<256, 1, 8, 3, 1>(b, p, cands, cand_cap, d_counters, stream); break;  // register-staged, 256-word slab window: 24 warps/SM
+        default: launch_pipe<384, 3, 8, 2>(b, p, cands, cand_cap, d_counters, stream); break;     // cp.async: 16 warps/SM, 2 tiles in flight each
+        }
+        return;
+    }
     const int variant = (p.genome || p.vr.n || b.bc) ? 5 : ((p.variant == 1 || p.variant == 4 || p.variant == 7) ? p.variant : scan_variant());   // only variant 5 knows the intron-motif and variant-region modes
     if ((align & 15u) == 0 && variant == 5) {
         static int prepass = -1;
@@ -1082,6 +1562,7 @@ constexpr int MERGE_TILE    = MERGE_THREADS * MERGE_CPT;     // 2048 candidates
 constexpr int MERGE_SLOTS   = 2048;                          // shared-memory hash slots (power of 2)
 constexpr int MERGE_PROBES  = 32;
 constexpr unsigned long long SKEY_EMPTY = ~0ull;
+constexpr int MERGE_PAL = 4;                               // (contig, region) pairs per chunk in the shared-memory table's 62-bit key
 constexpr int MERGE_RGROUP = 32;                            // scan tiles (candidate regions) per merge tile
 
 struct MergeSmem {
@@ -1089,8 +1570,7 @@ struct MergeSmem {
     unsigned long long nfirst[MERGE_SLOTS];
     unsigned long long last[MERGE_SLOTS];
     uint32_t count[MERGE_SLOTS], nts[MERGE_SLOTS], te[MERGE_SLOTS], lr[MERGE_SLOTS];
-    int32_t base_tid;
-    uint32_t base_vreg;
+    unsigned long long pal[MERGE_PAL];           // region << 32 | tid of the (contig, region) pairs the chunk's shared-memory table knows
     uint32_t rpre[MERGE_RGROUP + 1];             // prefix of the region counts of a region tile
 };
 
@@ -1104,8 +1584,7 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
     const uint32_t n = d_n_cand ? min(*d_n_cand, n_bound) : n_bound;
     const uint32_t n_otiles = (n + MERGE_TILE - 1) / MERGE_TILE;                                   // dense overflow list
     const uint32_t n_rtiles = rg.base ? (rg.n_regions + MERGE_RGROUP - 1) / MERGE_RGROUP : 0u;     // per-tile regions
-    if (blockIdx.x == 0 && t == 0)
-        atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_TOTAL_CAND64), (unsigned long long)n);
+    uint32_t n_valid = 0;                                       // candidates seen (tid >= 0: not the padding of the scan's chunks)
 
     for (uint32_t tile = blockIdx.x; tile < n_rtiles + n_otiles; tile += gridDim.x) {
         // ---- where this tile's candidates are
@@ -1123,7 +1602,6 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
             }
             __syncthreads();
             total = sm.rpre[MERGE_RGROUP];
-            if (t == 0 && total) atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_TOTAL_CAND64), (unsigned long long)total);
         } else {
             const uint32_t tb0 = (tile - n_rtiles) * MERGE_TILE;
             total = min((uint32_t)MERGE_TILE, n - tb0);
@@ -1141,11 +1619,7 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
                 sm.key[s] = SKEY_EMPTY; sm.nfirst[s] = 0ull; sm.last[s] = 0ull;
                 sm.count[s] = 0u; sm.nts[s] = 0u; sm.te[s] = 0u; sm.lr[s] = 0u;
             }
-            if (t == 0) { const uint4 f = cand_ptr(c0)[1]; sm.base_tid = (int32_t)f.z; sm.base_vreg = f.w >> 8; }
-            __syncthreads();
-            const int32_t base_tid = sm.base_tid;
-            const uint32_t base_vreg = sm.base_vreg;
-
+            if (t < MERGE_PAL) sm.pal[t] = SKEY_EMPTY;
             // all loads of the chunk first (two 128-bit loads per candidate)
             uint4 ca[MERGE_CPT], cb[MERGE_CPT];
 #pragma unroll
@@ -1160,11 +1634,13 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
                     cb[j] = make_uint4(0, 0, 0xffffffffu, 0);      // tid = -1: skipped
                 }
             }
+            __syncthreads();
 #pragma unroll
             for (int j = 0; j < MERGE_CPT; ++j) {
                 const uint32_t start = ca[j].x, end = ca[j].y, ts = ca[j].z, te = ca[j].w;
                 const int32_t tid = (int32_t)cb[j].z;
                 if (tid < 0) continue;
+                ++n_valid;
                 const uint32_t ilen = end - start;                                   // uint32, :161-162
                 if (ilen < prm.min_intron || ilen > prm.max_intron) continue;         // junction_qc
                 const uint32_t lr = ((start - ts) >= prm.min_anchor ? 1u : 0u) | ((te - end) >= prm.min_anchor ? 2u : 0u);
@@ -1174,8 +1650,19 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
                 const unsigned long long nfirst = ~ord;
                 const unsigned long long last = proxy == 2u ? ((ord >> 16) << 8 | sc) : 0ull;
                 bool done = false;
-                if (tid == base_tid && vreg == base_vreg && ilen < (1u << 28)) {
-                    const unsigned long long k = (unsigned long long)start << 30 | (unsigned long long)ilen << 2 | proxy;
+                // (contig, region) -> palette index: the first MERGE_PAL distinct pairs of the chunk (a BAM is sorted: nearly always 1-2)
+                uint32_t pi = MERGE_PAL;
+                {
+                    const unsigned long long ck = (unsigned long long)vreg << 32 | (uint32_t)tid;
+#pragma unroll
+                    for (uint32_t q = 0; q < (uint32_t)MERGE_PAL; ++q) {
+                        unsigned long long cur = sm.pal[q];
+                        if (cur == SKEY_EMPTY) cur = atomicCAS(&sm.pal[q], SKEY_EMPTY, ck);
+                        if (cur == SKEY_EMPTY || cur == ck) { pi = q; break; }
+                    }
+                }
+                if (pi < (uint32_t)MERGE_PAL && ilen < (1u << 26)) {
+                    const unsigned long long k = (unsigned long long)start << 30 | (unsigned long long)ilen << 4 | pi << 2 | proxy;
                     uint32_t s = mix_key(k, 0ull) & (MERGE_SLOTS - 1);
                     for (int probe = 0; probe < MERGE_PROBES; ++probe, s = (s + 1) & (MERGE_SLOTS - 1)) {
                         unsigned long long cur = sm.key[s];
@@ -1203,9 +1690,10 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
             for (uint32_t s = t; s < MERGE_SLOTS; s += MERGE_THREADS) {
                 const unsigned long long k = sm.key[s];
                 if (k == SKEY_EMPTY) continue;
-                const uint32_t start = (uint32_t)(k >> 30), ilen = (uint32_t)(k >> 2) & 0x0fffffffu, proxy = (uint32_t)k & 3u;
+                const uint32_t start = (uint32_t)(k >> 30), ilen = (uint32_t)(k >> 4) & 0x03ffffffu, proxy = (uint32_t)k & 3u;
+                const unsigned long long ck = sm.pal[((uint32_t)k >> 2) & 3u];
                 K128 key{(unsigned long long)start << 32 | (uint32_t)(start + ilen),
-                         (unsigned long long)base_vreg << 34 | ((unsigned long long)(uint32_t)(base_tid + 1)) << 2 | proxy};
+                         (ck >> 32) << 34 | ((unsigned long long)((uint32_t)ck + 1u)) << 2 | proxy};
                 if (!table_upsert(tb, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s], counters))
                     spill_entry(spill, spill_cap, counters, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s]);
             }
@@ -1213,6 +1701,8 @@ junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict
         }
         __syncthreads();            // rpre is rewritten by the next region tile
     }
+    n_valid = __reduce_add_sync(0xffffffffu, n_valid);
+    if ((t & 31u) == 0 && n_valid) atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_TOTAL_CAND64), (unsigned long long)n_valid);
 }
 
 static int g_num_sms = 0;
@@ -1277,47 +1767,6 @@ struct alignas(16) S6Smem {
     uint16_t work[THREADS * 4];
     uint32_t n_work, sink;
 };
-
-struct WalkCand { uint32_t start, end, left, right, k; };
-
-// Forward walk that records the first two N ops in registers (c0, c1) and counts all of them.  Predicated, no
-// branches and no calls: same arithmetic as walk_fast, the first four ops are fetched by independent loads (op code
-// 15 is a transparent filler), the rest in a loop.  Alignments with more than two N ops (rare) are finished by
-// fused_walk_rest.  Returns the number of N ops.
-template <bool FROM_SMEM>
-__device__ __forceinline__ uint32_t walk_collect(const uint32_t* __restrict__ ops, uint32_t n, uint32_t pos,
-                                                 WalkCand& c0, WalkCand& c1) {
-    const uint32_t ANC = (1u << 0) | (1u << 7);
-    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
-    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
-    constexpr int PRE = 4;
-    uint32_t w[PRE];
-#pragma unroll
-    for (int i = 0; i < PRE; ++i) w[i] = (uint32_t)i < n ? (FROM_SMEM ? ops[i] : __ldg(ops + i)) : 0xfu;
-    uint32_t cur = pos, run = 0, nc = 0;
-    bool pending = false;
-    auto step = [&](uint32_t x, uint32_t i) {
-        const uint32_t op = x & 0xfu, len = x >> 4, bit = 1u << op;
-        const bool brk = (bit & BRK) != 0, is_n = op == 3u;
-        const bool close = pending && brk;                  // the open junction ends here: right anchor = run
-        c0.right = (close && nc == 1u) ? run : c0.right;
-        c1.right = (close && nc == 2u) ? run : c1.right;
-        const bool open0 = is_n && nc == 0u, open1 = is_n && nc == 1u;
-        const uint32_t kk = i > 0xffffu ? 0xffffu : i;
-        c0.start = open0 ? cur : c0.start; c0.end = open0 ? cur + len : c0.end; c0.left = open0 ? run : c0.left; c0.k = open0 ? kk : c0.k;
-        c1.start = open1 ? cur : c1.start; c1.end = open1 ? cur + len : c1.end; c1.left = open1 ? run : c1.left; c1.k = open1 ? kk : c1.k;
-        nc += is_n ? 1u : 0u;
-        pending = brk ? is_n : pending;
-        run = brk ? 0u : run + ((bit & ANC) ? len : 0u);
-        cur += (bit & REFC) ? len : 0u;
-    };
-#pragma unroll
-    for (int i = 0; i < PRE; ++i) step(w[i], (uint32_t)i);
-    for (uint32_t i = PRE; i < n; ++i) step(FROM_SMEM ? ops[i] : __ldg(ops + i), i);
-    c0.right = (pending && nc == 1u) ? run : c0.right;
-    c1.right = (pending && nc == 2u) ? run : c1.right;
-    return nc;
-}
 
 struct FusedCtx { TableRef tb; Slot* spill; uint32_t spill_cap; uint32_t* counters; };
 

@@ -15,6 +15,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
+# every test runs once per decoder: the warp-per-block kernel (1) and the lane-per-stream kernel (3) with each root-table width
+KERNELS = [("1", "10"), ("3", "10"), ("3", "9"), ("3", "11")]
+
+
+@pytest.fixture(autouse=True, params=KERNELS, ids=lambda k: f"variant{k[0]}-root{k[1]}")
+def inflate_kernel(request, monkeypatch):
+    monkeypatch.setenv("RTJX_INFLATE_VARIANT", request.param[0])
+    monkeypatch.setenv("RTJX_INFLATE_ROOT", request.param[1])
+    return request.param
+
+
 def device_inflate(path, max_blocks=0):
     import regtools_b200 as rt
     ex = rt.JunctionsExtractor(path, ".", 0)
