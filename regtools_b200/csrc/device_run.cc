@@ -74,6 +74,7 @@ struct Engine::DeviceFeed {
     BgzfBlockDesc* d_desc = nullptr; size_t desc_cap = 0;
     int64_t* d_seeds = nullptr; uint32_t* d_segbase = nullptr; size_t seed_cap = 0;
     uint32_t* d_status = nullptr;
+    void* d_inf_scratch = nullptr; size_t inf_scratch_cap = 0;   // match lists of the lane-per-stream inflate kernel
     uint8_t* d_infl = nullptr; size_t infl_cap = 0;      // HEAD + data + pad
     int32_t* d_recoff = nullptr; int32_t* d_dense = nullptr; uint32_t* d_ncig = nullptr; uint32_t* d_ncigscan = nullptr; size_t rec_cap = 0;
     uint32_t* d_segcnt = nullptr; uint32_t* d_segscan = nullptr;
@@ -94,7 +95,7 @@ struct Engine::DeviceFeed {
         cached_dev_free(d_desc); cached_dev_free(d_seeds); cached_dev_free(d_segbase); cached_dev_free(d_status); cached_dev_free(d_infl);
         cached_dev_free(d_recoff); cached_dev_free(d_dense); cached_dev_free(d_ncig); cached_dev_free(d_ncigscan); cached_dev_free(d_segcnt); cached_dev_free(d_segscan);
         cached_dev_free(d_tid); cached_dev_free(d_pos); cached_dev_free(d_meta); cached_dev_free(d_off); cached_dev_free(d_cigar); cached_dev_free(d_ws);
-        cached_dev_free(d_state); cached_host_free(h_state);
+        cached_dev_free(d_state); cached_host_free(h_state); cached_dev_free(d_inf_scratch);
     }
 };
 
@@ -283,6 +284,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                 F.desc_cap = (size_t)nb * 2 + 1024;
                 CKD(cached_dev_malloc(&F.d_desc, F.desc_cap * sizeof(BgzfBlockDesc))); CKD(cached_dev_malloc(&F.d_status, F.desc_cap * 4));
             }
+            CKD(grow_dev(&F.d_inf_scratch, &F.inf_scratch_cap, bgzf_inflate_scratch_bytes(nb), 1));
             if ((size_t)n_seg + 2 > F.seed_cap) {
                 if (F.d_seeds) cudaStreamSynchronize(stream_);
                 cached_dev_free(F.d_seeds); cached_dev_free(F.d_segbase); cached_dev_free(F.d_segcnt); cached_dev_free(F.d_segscan);
@@ -315,7 +317,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             CKD(cudaStreamWaitEvent(stream_, F.copies_done, 0));             // every staged chunk of the group has landed
             cudaEvent_t ea = nullptr, eb = nullptr;
             if (prm_.profile) { ea = get_event(); eb = get_event(); cudaEventRecord(ea, stream_); }
-            launch_bgzf_inflate(F.d_comp_group[gbuf], F.d_desc, nb, data, F.d_status, stream_);
+            launch_bgzf_inflate(F.d_comp_group[gbuf], F.d_desc, nb, data, F.d_status, F.d_inf_scratch, stream_);
             if (prm_.profile) { cudaEventRecord(eb, stream_); feed_prof_.push_back({ea, eb}); }
             CKD(cudaEventRecord(F.group_free[gbuf], stream_));               // this compressed buffer may be refilled after the inflate
             launch_record_walk(data, (int64_t)G.out_total, limit, F.d_seeds, F.d_segbase, n_seg, G.first_of_range ? 0 : 1, F.d_state,

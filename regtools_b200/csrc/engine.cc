@@ -728,7 +728,9 @@ int Engine::inflate_file(uint64_t max_blocks, void* out, uint64_t cap, uint64_t*
     CK(cudaMemcpyAsync(d_desc, desc.data(), desc.size() * sizeof(BgzfBlockDesc), cudaMemcpyHostToDevice, stream_));
     cudaEvent_t ea = get_event(), eb = get_event();
     cudaEventRecord(ea, stream_);
-    launch_bgzf_inflate(d_in, d_desc, (uint32_t)desc.size(), d_out, d_status, stream_);
+    void* d_scratch = nullptr;
+    CK(cached_dev_malloc(&d_scratch, bgzf_inflate_scratch_bytes((uint32_t)desc.size())));
+    launch_bgzf_inflate(d_in, d_desc, (uint32_t)desc.size(), d_out, d_status, d_scratch, stream_);
     cudaEventRecord(eb, stream_);
     std::vector<uint32_t> status(desc.size());
     CK(cudaMemcpyAsync(status.data(), d_status, desc.size() * 4, cudaMemcpyDeviceToHost, stream_));
@@ -738,7 +740,7 @@ int Engine::inflate_file(uint64_t max_blocks, void* out, uint64_t cap, uint64_t*
     float ms = 0; cudaEventElapsedTime(&ms, ea, eb); stats_.inflate_kernel_ms += ms;
     ev_pool_.push_back(ea); ev_pool_.push_back(eb);
     stats_.kernel_launches++; stats_.bgzf_blocks += blocks.size(); stats_.compressed_bytes += in_total; stats_.inflated_bytes += out_total;
-    cached_dev_free(d_in); cached_dev_free(d_out); cached_dev_free(d_desc); cached_dev_free(d_status);
+    cached_dev_free(d_in); cached_dev_free(d_out); cached_dev_free(d_desc); cached_dev_free(d_status); cached_dev_free(d_scratch);
     for (size_t i = 0; i < status.size(); ++i)
         if (status[i]) return fail(RTJX_E_IO, "device inflate failed on BGZF block " + std::to_string(i) + " (code " + std::to_string(status[i]) + ")");
     return RTJX_OK;

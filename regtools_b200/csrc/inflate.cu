@@ -403,207 +403,35 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// SIMT variant: one THREAD per BGZF block
-// ------------------------------------------------------------------------------------------------
-// The warp-per-block kernel above spends ~30 issue slots per symbol on a single active lane.  When a
-// launch covers thousands of blocks it is better to let every lane decode its own block: the symbol
-// loop then runs 32 blocks per instruction.  Each thread owns a 1668-byte table region in shared
-// memory (8-bit literal/length and 6-bit distance lookup tables + per-length code counts); the stride is an
-// odd number of words so that equal indices of different lanes fall into different banks.  Lanes diverge only between the literal and the match path and
-// at DEFLATE block headers.
-constexpr int SI_THREADS   = 32;
-constexpr int SI_LIT_BITS  = 8;
-constexpr int SI_DIST_BITS = 6;
-constexpr int SI_STRIDE    = 708;                // bytes per thread in shared memory (177 words: odd, lanes on distinct banks)
-constexpr int SI_OFF_DFAST = 512, SI_OFF_LCNT = 640, SI_OFF_DCNT = 672;
-// the canonical symbol arrays (codes longer than the lookup tables) and the code-length scratch are touched
-// rarely and live in per-thread local memory (L1-cached) so that ~10 warps per SM fit
-
-// per-thread canonical table build; returns false on an over-subscribed code
-__device__ bool si_build(const uint8_t* len, int n, uint16_t* count, uint16_t* sym, uint16_t* fast, int fast_bits) {
-    for (int i = 0; i < 16; ++i) count[i] = 0;
-    for (int i = 0; i < (1 << fast_bits); ++i) fast[i] = 0;
-    for (int i = 0; i < n; ++i) count[len[i]]++;
-    uint16_t offs[16];
-    uint32_t next_code[16];
-    int left = 1;
-    offs[1] = 0; next_code[0] = 0;
-    uint32_t code = 0;
-    for (int l = 1; l <= 15; ++l) {
-        left <<= 1; left -= count[l];
-        if (left < 0) return false;
-        if (l < 15) offs[l + 1] = offs[l] + count[l];
-        code = (code + (l > 1 ? count[l - 1] : 0)) << 1; next_code[l] = code;
-    }
-    for (int s = 0; s < n; ++s) {
-        const int l = len[s];
-        if (!l) continue;
-        sym[offs[l]++] = (uint16_t)s;
-        const uint32_t c = next_code[l]++;
-        if (l <= fast_bits) {
-            const uint32_t rev = __brev(c) >> (32 - l);
-            const uint16_t e = (uint16_t)(s << 4 | l);
-            for (uint32_t k = rev; k < (1u << fast_bits); k += 1u << l) fast[k] = e;
-        }
-    }
-    return true;
-}
-
-__global__ void __launch_bounds__(SI_THREADS)
-bgzf_inflate_simt_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, uint32_t n_blocks,
-                         uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
-    extern __shared__ __align__(16) uint8_t si_smem[];
-    const uint32_t b = blockIdx.x * SI_THREADS + threadIdx.x;
-    if (b >= n_blocks) return;
-    uint8_t* T = si_smem + threadIdx.x * SI_STRIDE;
-    uint16_t* lit_fast = reinterpret_cast<uint16_t*>(T);
-    uint16_t* dist_fast = reinterpret_cast<uint16_t*>(T + SI_OFF_DFAST);
-    uint16_t* lit_count = reinterpret_cast<uint16_t*>(T + SI_OFF_LCNT);
-    uint16_t* dist_count = reinterpret_cast<uint16_t*>(T + SI_OFF_DCNT);
-    uint16_t lit_sym[288], dist_sym[32];
-    uint8_t lens[320];
-
-    const BgzfBlock blk = blocks[b];
-    uint8_t* dst = out + blk.out_off;
-    const uint32_t cap = blk.out_len;
-    uint32_t opos = 0, err = 0;
-    BitReader br;
-    br.init(comp + blk.in_off);
-
-    for (bool last = false; !last && !err;) {
-        const uint32_t hdr = br.get(3);
-        last = hdr & 1u;
-        const uint32_t btype = hdr >> 1;
-        if (btype == 0) {
-            br.drop(br.nb & 7);
-            const uint32_t l = br.get(16), nl = br.get(16);
-            if ((l ^ nl) != 0xffffu || opos + l > cap) { err = 2; break; }
-            const uint8_t* src = br.byte_ptr();
-            for (uint32_t i = 0; i < l; ++i) dst[opos + i] = __ldg(src + i);
-            opos += l;
-            br.init(src + l);
-            continue;
-        }
-        if (btype == 3) { err = 3; break; }
-        if (btype == 1) {
-            for (int i = 0; i < 288; ++i) lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
-            for (int i = 0; i < 30; ++i) lens[288 + i] = 5;
-        } else {
-            const int hlit = (int)br.get(5) + 257, hdist = (int)br.get(5) + 1, hclen = (int)br.get(4) + 4;
-            if (hlit > 286 || hdist > 30) { err = 4; break; }
-            // the code-length code: lengths packed 4 bits each in a 76-bit register pair, canonical decode by counts
-            uint8_t cl[19];
-#pragma unroll
-            for (int i = 0; i < 19; ++i) cl[i] = 0;
-            for (int i = 0; i < hclen; ++i) cl[c_clen_order[i]] = (uint8_t)br.get(3);
-            uint16_t ccount[8], csym[19], coffs[8];
-            for (int i = 0; i < 8; ++i) ccount[i] = 0;
-            for (int i = 0; i < 19; ++i) ccount[cl[i]]++;
-            coffs[1] = 0;
-            for (int l = 1; l < 7; ++l) coffs[l + 1] = coffs[l] + ccount[l];
-            for (int i = 0; i < 19; ++i) if (cl[i]) csym[coffs[cl[i]]++] = (uint16_t)i;
-            int idx = 0;
-            while (idx < hlit + hdist && !err) {
-                int code = 0, first = 0, index = 0, symv = -1;
-                for (int l = 1; l <= 7; ++l) {
-                    code |= (int)br.get(1);
-                    const int c = ccount[l];
-                    if (code - c < first) { symv = csym[index + (code - first)]; break; }
-                    index += c; first += c; first <<= 1; code <<= 1;
-                }
-                if (symv < 0) { err = 5; break; }
-                if (symv < 16) lens[idx++] = (uint8_t)symv;
-                else {
-                    int rep, val = 0;
-                    if (symv == 16) { if (idx == 0) { err = 6; break; } val = lens[idx - 1]; rep = 3 + (int)br.get(2); }
-                    else if (symv == 17) rep = 3 + (int)br.get(3);
-                    else rep = 11 + (int)br.get(7);
-                    if (idx + rep > hlit + hdist) { err = 7; break; }
-                    while (rep--) lens[idx++] = (uint8_t)val;
-                }
-            }
-            if (err) break;
-            if (lens[256] == 0) { err = 8; break; }
-            // distance lengths to their fixed place (288..317); iterate downwards: the ranges may overlap
-            for (int i = hdist - 1; i >= 0; --i) lens[288 + i] = lens[hlit + i];
-            for (int i = hlit; i < 288; ++i) lens[i] = 0;
-            for (int i = hdist; i < 30; ++i) lens[288 + i] = 0;
-        }
-        if (!si_build(lens, 288, lit_count, lit_sym, lit_fast, SI_LIT_BITS)) { err = 9; break; }
-        if (!si_build(lens + 288, 30, dist_count, dist_sym, dist_fast, SI_DIST_BITS)) { err = 10; break; }
-
-        for (;;) {
-            br.need(32);
-            int sym;
-            uint32_t e = lit_fast[br.peek(SI_LIT_BITS)];
-            if (e) { br.drop(e & 15); sym = (int)(e >> 4); }
-            else { sym = slow_decode(br, lit_count, lit_sym); if (sym < 0) { err = 11; break; } }
-            if (sym < 256) {
-                if (opos >= cap) { err = 15; break; }
-                dst[opos++] = (uint8_t)sym;
-                continue;
-            }
-            if (sym == 256) break;
-            sym -= 257;
-            if (sym >= 29) { err = 12; break; }
-            br.need(32);
-            const uint32_t len = c_len_base[sym] + br.get(c_len_extra[sym]);
-            br.need(32);
-            int ds;
-            e = dist_fast[br.peek(SI_DIST_BITS)];
-            if (e) { br.drop(e & 15); ds = (int)(e >> 4); }
-            else { ds = slow_decode(br, dist_count, dist_sym); if (ds < 0) { err = 13; break; } }
-            if (ds >= 30) { err = 14; break; }
-            br.need(32);
-            const uint32_t dist = c_dist_base[ds] + br.get(c_dist_extra[ds]);
-            if (dist > opos) { err = 16; break; }
-            if (opos + len > cap) { err = 15; break; }
-            const uint8_t* srcp = dst + opos - dist;
-            uint8_t* d = dst + opos;
-            if (dist >= len) {                       // no overlap: loads first, then stores (4-way ILP)
-                uint32_t k = 0;
-                for (; k + 4 <= len; k += 4) {
-                    const uint8_t a0 = srcp[k], a1 = srcp[k + 1], a2 = srcp[k + 2], a3 = srcp[k + 3];
-                    d[k] = a0; d[k + 1] = a1; d[k + 2] = a2; d[k + 3] = a3;
-                }
-                for (; k < len; ++k) d[k] = srcp[k];
-            } else {
-                for (uint32_t k = 0; k < len; ++k) d[k] = *(volatile const uint8_t*)(srcp + k);   // run: each byte may depend on the previous store
-            }
-            opos += len;
-        }
-    }
-    if (!err && opos != cap) err = 17;
-    status[b] = err;
-}
-
-// ------------------------------------------------------------------------------------------------
 // Lane-per-stream decoder (round 2; the default for launches with enough BGZF blocks)
 // ------------------------------------------------------------------------------------------------
 // The warp-per-block kernel above issues ~22-31 warp instructions per output byte because its symbol loop runs on one lane.
-// Here every LANE decodes its own BGZF block, so one issued instruction advances 32 streams.  What makes that work:
-//   * per-lane lookup tables in shared memory (LR-bit literal/length root table, DR-bit distance root table, canonical
-//     count/symbol arrays for the rare longer codes), lane stride an odd number of words so equal indices of different lanes
-//     fall into different banks; one warp per CTA, CTAs per SM bounded by shared memory (LR = 10: 2 x 32 streams per SM);
-//   * a flattened state machine — one loop, one symbol (or one DEFLATE block header) per lane per iteration — so lanes
-//     reconverge every iteration; zlib cuts DEFLATE blocks after a fixed number of symbols, so the lanes of a warp reach their
-//     block headers (the expensive, divergent table builds) in the same iteration;
-//   * the bit stream is read through a 64-bit buffer refilled from a word loaded one refill earlier, plus an L2 prefetch half
-//     a kilobyte ahead, so neither L2 nor DRAM latency sits on the symbol chain;
-//   * literals are combined into aligned 32-bit stores (a quarter of the store transactions); matches copy bytes from the
-//     lane's own earlier output in global memory (L1/L2).
-// Error codes are those of the kernel above; any non-zero status sends the run to the host feeder.
-template <int LR, int DR>
-struct LaneLayout {
-    static constexpr int LIT_FAST = 0;                                 // uint16[1 << LR]
-    static constexpr int DIST_FAST = LIT_FAST + (2 << LR);             // uint16[1 << DR]
-    static constexpr int LIT_COUNT = DIST_FAST + (2 << DR);            // uint16[16]
-    static constexpr int DIST_COUNT = LIT_COUNT + 32;                  // uint16[16]
-    static constexpr int LIT_SYM = DIST_COUNT + 32;                    // uint16[288]
-    static constexpr int DIST_SYM = LIT_SYM + 576;                     // uint16[32]
-    static constexpr int BYTES = DIST_SYM + 64;
-    static constexpr int STRIDE = ((BYTES / 4) | 1) * 4;               // odd number of words
-};
+// Here every LANE decodes its own BGZF block, so one issued instruction advances 32 streams, in two kernels:
+//
+//  1. bgzf_inflate_lanes_kernel — Huffman decoding.  No lookup tables: a canonical code is decoded by COUNTING, over the 15
+//     code lengths, how many left-justified upper bounds `ub[len]` the next 15 stream bits (bit-reversed) reach — thirty
+//     compare/add instructions on registers, no branch, no memory access — followed by two small shared-memory reads
+//     (adj[len], then the symbol).  A lane therefore needs only 676 bytes of shared memory (symbols in canonical order +
+//     per-length adjustments), ten warps fit on an SM, and that occupancy — not table size — is what hides the symbol chain's
+//     latency.  (First round-2 build: 10-bit lookup tables, 3.2 KB per lane, two warps per SM: 337 ms for the 2.1 GB C2 stream
+//     against 74 ms for the kernel above; profiles/r2_inflate_lanes_v1.txt.)
+//     One loop, one symbol (or one DEFLATE block header) per lane per iteration, so lanes reconverge every iteration; zlib
+//     cuts DEFLATE blocks after a fixed number of symbols, so the lanes of a warp reach their block headers (the divergent
+//     part) in the same iteration.  Literals go straight to their final position, combined into aligned 32-bit stores.
+//     Matches are NOT copied here — a copy is a dependent global round trip that would stall all 32 lanes — they are
+//     appended to the block's match list (position, length, distance).
+//  2. bgzf_match_resolve_kernel — LZ77 copies.  One warp per BGZF block walks the match list 32 matches at a time: matches
+//     whose source lies before the round's first byte are copied by their own lanes in parallel, the others (and long ones)
+//     cooperatively in order — the placement logic of the warp-per-block kernel, without its decoder.
+//
+// Error codes are those of the kernel above (+18 input overrun, 19 match list full); any non-zero status sends the run to the
+// warp-per-block kernel's / host feeder's path.
+constexpr int LN_STRIDE = 676;                    // bytes of shared memory per lane: 169 words (odd: lanes on distinct banks)
+constexpr int LN_LIT_SYM = 0;                     // uint16[288] literal/length symbols in canonical order
+constexpr int LN_LIT_ADJ = 576;                   // int16[16]   offset[len] - first_code[len]
+constexpr int LN_DIST_ADJ = 608;                  // int16[16]
+constexpr int LN_DIST_SYM = 640;                  // uint8[32]
+constexpr int LN_WARPS_PER_SM = 10;
 
 // LSB-first bit reader of one lane: 64-bit buffer, 32-bit aligned refills, the next word always already requested.
 struct LaneBits {
@@ -615,7 +443,7 @@ struct LaneBits {
     __device__ __forceinline__ void init(const uint8_t* src, uint32_t len) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(src);
         p = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-        lim = reinterpret_cast<const uint32_t*>((a + len + 3) & ~(uintptr_t)3) + 2;    // BGZF trailer (CRC32, ISIZE) follows every payload
+        lim = reinterpret_cast<const uint32_t*>((a + len + 3) & ~(uintptr_t)3) + 2;    // the BGZF trailer (CRC32, ISIZE) follows every payload
         const int mis = (int)(a & 3);
         bb = (uint64_t)__ldg(p++) >> (8 * mis);
         nb = 32 - 8 * mis;
@@ -639,47 +467,73 @@ struct LaneBits {
     __device__ __forceinline__ const uint8_t* byte_ptr() const { return reinterpret_cast<const uint8_t*>(p - 1) - (nb >> 3); }
 };
 
-// canonical decode of a code longer than the root table (same recurrence as slow_decode_w): e = sym << 4 | len, 0 = invalid
-__device__ __forceinline__ uint32_t lane_slow_decode(uint64_t bb, const uint16_t* count, const uint16_t* sym, int root, int pre_first, int pre_index) {
-    uint32_t win = (uint32_t)bb;
-    int code = (int)(__brev(win) >> (32 - root)) << 1, first = pre_first, index = pre_index;
-    win >>= root;
-    for (int len = root + 1; len <= 15; ++len) {
-        code |= (int)(win & 1u); win >>= 1;
-        const int c = count[len];
-        if (code - c < first) return (uint32_t)sym[index + (code - first)] << 4 | (uint32_t)len;
-        index += c; first += c; first <<= 1; code <<= 1;
+// Canonical code of `n` symbols with lengths len[]: ub[l] (l = 1..15, registers), adj[l] and the symbol table (shared memory).
+// Returns false on an over-subscribed code.  ub[l] = (first_code[l] + count[l]) << (15 - l): a 15-bit left-justified window v
+// holds a code of length 1 + #{l : v >= ub[l]}.
+template <class SymT>
+__device__ __forceinline__ bool lane_build(const uint8_t* len, int n, uint32_t (&ub)[16], int16_t* adj, SymT* symtab) {
+    uint16_t count[16], offs[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) count[i] = 0;
+    for (int i = 0; i < n; ++i) count[len[i]]++;
+    int left = 1;
+    uint32_t code = 0, off = 0;
+    bool ok = true;
+#pragma unroll
+    for (int l = 1; l <= 15; ++l) {
+        const uint32_t c = count[l];
+        left <<= 1; left -= (int)c;
+        if (left < 0) ok = false;
+        ub[l] = (code + c) << (15 - l);
+        adj[l] = (int16_t)((int)off - (int)code);
+        offs[l] = (uint16_t)off;
+        off += c;
+        code = (code + c) << 1;
     }
-    return 0u;
+    if (!ok) return false;
+    for (int s = 0; s < n; ++s) {
+        const int l = len[s];
+        if (l) symtab[offs[l]++] = (SymT)s;
+    }
+    return true;
 }
 
-template <int LR, int DR>
+// code length of the 15-bit window v (MSB-first): 1 + the number of bounds it reaches; 16 = no code of this table
+__device__ __forceinline__ uint32_t lane_code_len(uint32_t v, const uint32_t (&ub)[16]) {
+    uint32_t cnt = 1;
+#pragma unroll
+    for (int l = 1; l <= 15; ++l) cnt += v >= ub[l] ? 1u : 0u;
+    return cnt;
+}
+
+constexpr uint32_t LN_MATCH_CAP = 12288;          // match records per BGZF block (a block of nothing but 5-byte matches)
+
 __global__ void __launch_bounds__(32)
 bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, uint32_t n_blocks,
-                          uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
-    using LL = LaneLayout<LR, DR>;
+                          uint8_t* __restrict__ out, uint32_t* __restrict__ status, uint2* __restrict__ mlist, uint32_t* __restrict__ mcount) {
     extern __shared__ __align__(16) uint8_t lane_smem[];
     const uint32_t b = blockIdx.x * 32u + threadIdx.x;
     if (b >= n_blocks) return;
-    uint8_t* T = lane_smem + threadIdx.x * LL::STRIDE;
-    uint16_t* lit_fast = reinterpret_cast<uint16_t*>(T + LL::LIT_FAST);
-    uint16_t* dist_fast = reinterpret_cast<uint16_t*>(T + LL::DIST_FAST);
-    uint16_t* lit_count = reinterpret_cast<uint16_t*>(T + LL::LIT_COUNT);
-    uint16_t* dist_count = reinterpret_cast<uint16_t*>(T + LL::DIST_COUNT);
-    uint16_t* lit_sym = reinterpret_cast<uint16_t*>(T + LL::LIT_SYM);
-    uint16_t* dist_sym = reinterpret_cast<uint16_t*>(T + LL::DIST_SYM);
+    uint8_t* T = lane_smem + threadIdx.x * LN_STRIDE;
+    uint16_t* lit_sym = reinterpret_cast<uint16_t*>(T + LN_LIT_SYM);
+    int16_t* lit_adj = reinterpret_cast<int16_t*>(T + LN_LIT_ADJ);
+    int16_t* dist_adj = reinterpret_cast<int16_t*>(T + LN_DIST_ADJ);
+    uint8_t* dist_sym = T + LN_DIST_SYM;
 
     const BgzfBlock blk = blocks[b];
     uint8_t* dst = out + blk.out_off;
     const uint32_t cap = blk.out_len;
-    uint32_t opos = 0, err = 0;
+    uint2* my_matches = mlist + (size_t)b * LN_MATCH_CAP;
+    uint32_t opos = 0, err = 0, n_match = 0;
     uint32_t wbuf = 0, pend = 0;                  // literals not yet stored: `pend` bytes ending at dst + opos, the first one 4-byte aligned
     LaneBits br;
     br.init(comp + blk.in_off, blk.in_len);
-    int lit_pf = 0, lit_pi = 0, dist_pf = 0, dist_pi = 0;               // slow-path constants of the current DEFLATE block
+    uint32_t ul[16], ud[16];                      // upper bounds per code length of the current DEFLATE block's two codes
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { ul[i] = 0; ud[i] = 0; }
     bool in_block = false, last = false;
 
-    auto flush_pending = [&]() {                  // pending literals as byte stores (before a match / at a block boundary)
+    auto flush_pending = [&]() {                  // pending literals as byte stores (at a block boundary / before stored bytes)
         for (uint32_t k = 0; k < pend; ++k) dst[opos - pend + k] = (uint8_t)(wbuf >> (8 * k));
         pend = 0; wbuf = 0;
     };
@@ -697,6 +551,7 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
                 if ((l ^ nl) != 0xffffu || opos + l > cap) { err = 2; continue; }
                 flush_pending();
                 const uint8_t* src = br.byte_ptr();
+                if (src + l > reinterpret_cast<const uint8_t*>(br.lim)) { err = 18; continue; }
                 for (uint32_t i = 0; i < l; ++i) dst[opos + i] = __ldg(src + i);
                 opos += l;
                 br.init(src + l, (uint32_t)(reinterpret_cast<const uint8_t*>(br.lim - 2) - (src + l)));
@@ -749,21 +604,18 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
                 for (int i = hlit; i < 288; ++i) lens[i] = 0;
                 for (int i = hdist; i < 30; ++i) lens[288 + i] = 0;
             }
-            if (!si_build(lens, 288, lit_count, lit_sym, lit_fast, LR)) { err = 9; continue; }
-            if (!si_build(lens + 288, 30, dist_count, dist_sym, dist_fast, DR)) { err = 10; continue; }
-            { const SlowPre a = slow_decode_pre(lit_count, LR), d = slow_decode_pre(dist_count, DR); lit_pf = a.first; lit_pi = a.index; dist_pf = d.first; dist_pi = d.index; }
+            if (!lane_build<uint16_t>(lens, 288, ul, lit_adj, lit_sym)) { err = 9; continue; }
+            if (!lane_build<uint8_t>(lens + 288, 30, ud, dist_adj, dist_sym)) { err = 10; continue; }
             in_block = true;
             continue;
         }
         // ================= one symbol =================
         br.refill();
-        uint32_t e = lit_fast[(uint32_t)br.bb & ((1u << LR) - 1u)];
-        if (e == 0u) {
-            e = lane_slow_decode(br.bb, lit_count, lit_sym, LR, lit_pf, lit_pi);
-            if (e == 0u) { err = 11; in_block = false; continue; }
-        }
-        br.drop((int)(e & 15u));
-        uint32_t sym = e >> 4;
+        uint32_t v = __brev((uint32_t)br.bb) >> 17;                    // next 15 bits, first bit most significant
+        uint32_t cl = lane_code_len(v, ul);
+        if (cl > 15u) { err = 11; in_block = false; continue; }
+        uint32_t sym = lit_sym[(int)(v >> (15u - cl)) + (int)lit_adj[cl]];
+        br.drop((int)cl);
         if (sym < 256u) {
             if (opos >= cap) { err = 15; in_block = false; continue; }
             if (pend == 0u && ((reinterpret_cast<uintptr_t>(dst) + opos) & 3u) != 0u) {
@@ -783,13 +635,11 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
         const uint32_t len = lbase + br.peek((int)lx);
         br.drop((int)lx);
         br.refill();
-        e = dist_fast[(uint32_t)br.bb & ((1u << DR) - 1u)];
-        if (e == 0u) {
-            e = lane_slow_decode(br.bb, dist_count, dist_sym, DR, dist_pf, dist_pi);
-            if (e == 0u) { err = 13; in_block = false; continue; }
-        }
-        br.drop((int)(e & 15u));
-        const uint32_t ds = e >> 4;
+        v = __brev((uint32_t)br.bb) >> 17;
+        cl = lane_code_len(v, ud);
+        if (cl > 15u) { err = 13; in_block = false; continue; }
+        const uint32_t ds = dist_sym[(int)(v >> (15u - cl)) + (int)dist_adj[cl]];
+        br.drop((int)cl);
         if (ds >= 30u) { err = 14; in_block = false; continue; }
         const uint32_t dx = ds < 4u ? 0u : (ds - 2u) >> 1;
         const uint32_t dbase = ds < 4u ? ds + 1u : ((2u + (ds & 1u)) << dx) + 1u;
@@ -797,38 +647,70 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
         br.drop((int)dx);
         if (dist > opos) { err = 16; in_block = false; continue; }
         if (opos + len > cap) { err = 15; in_block = false; continue; }
+        if (n_match >= LN_MATCH_CAP) { err = 19; in_block = false; continue; }
         flush_pending();
-        {
-            const uint8_t* srcp = dst + opos - dist;
-            uint8_t* d = dst + opos;
-            if (dist >= len) {                       // no overlap: loads first, then stores (4-way ILP)
-                uint32_t k = 0;
-                for (; k + 4 <= len; k += 4) {
-                    const uint8_t a0 = srcp[k], a1 = srcp[k + 1], a2 = srcp[k + 2], a3 = srcp[k + 3];
-                    d[k] = a0; d[k + 1] = a1; d[k + 2] = a2; d[k + 3] = a3;
-                }
-                for (; k < len; ++k) d[k] = srcp[k];
-            } else {
-                for (uint32_t k = 0; k < len; ++k) d[k] = *(volatile const uint8_t*)(srcp + k);   // run: each byte may depend on the previous store
-            }
-        }
+        my_matches[n_match++] = make_uint2(opos | len << 16, dist);     // the copy itself happens in bgzf_match_resolve_kernel
         opos += len;
     }
     if (!err) flush_pending();
     if (!err && opos != cap) err = 17;
     status[b] = err;
+    mcount[b] = err ? 0u : n_match;
 }
 
-template <int LR, int DR>
-static void launch_lanes(const uint8_t* comp, const BgzfBlock* bl, uint32_t n_blocks, uint8_t* out, uint32_t* status, cudaStream_t stream) {
-    constexpr int sh = 32 * LaneLayout<LR, DR>::STRIDE;
+// LZ77 copies of the blocks decoded by bgzf_inflate_lanes_kernel: one warp per BGZF block, 32 matches per round.
+constexpr int MR_WARPS = 8;
+__global__ void __launch_bounds__(MR_WARPS * 32)
+bgzf_match_resolve_kernel(const BgzfBlock* __restrict__ blocks, uint32_t n_blocks, uint8_t* __restrict__ out,
+                          const uint2* __restrict__ mlist, const uint32_t* __restrict__ mcount) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t b = blockIdx.x * MR_WARPS + (threadIdx.x >> 5);
+    if (b >= n_blocks) return;
+    const uint32_t nm = mcount[b];
+    if (nm == 0) return;
+    uint8_t* dst = out + blocks[b].out_off;
+    const uint2* ml = mlist + (size_t)b * LN_MATCH_CAP;
+    for (uint32_t r0 = 0; r0 < nm; r0 += 32) {
+        const bool have = r0 + lane < nm;
+        const uint2 m = have ? ml[r0 + lane] : make_uint2(0u, 1u);
+        const uint32_t mypos = m.x & 0xffffu, mlen = m.x >> 16, mdist = m.y;
+        const uint32_t round_first = __shfl_sync(0xffffffffu, mypos, 0);
+        // A match whose source lies entirely before this round's first byte depends on nothing the round writes
+        const bool indep = have && mlen <= 32u && mypos + (mlen < mdist ? mlen : mdist) <= round_first + mdist;
+        if (indep) {
+            const uint8_t* srcp = dst + mypos - mdist;
+            if (mdist >= mlen) { for (uint32_t k = 0; k < mlen; ++k) dst[mypos + k] = __ldcg(srcp + k); }
+            else { for (uint32_t k = 0; k < mlen; ++k) dst[mypos + k] = __ldcg(srcp + (k % mdist)); }
+        }
+        uint32_t mm = __ballot_sync(0xffffffffu, have && !indep);
+        while (mm) {
+            const int j = __ffs(mm) - 1; mm &= mm - 1;
+            const uint32_t pj = __shfl_sync(0xffffffffu, mypos, j), len = __shfl_sync(0xffffffffu, mlen, j), dist = __shfl_sync(0xffffffffu, mdist, j);
+            __syncwarp();                                          // earlier stores of this warp are visible
+            const uint8_t* srcp = dst + pj - dist;
+            if (dist >= len) {
+                for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + k);
+            } else {                                               // overlapping run: periodic with period dist
+                for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + (k % dist));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+size_t bgzf_inflate_scratch_bytes(uint32_t n_blocks) { return (size_t)n_blocks * LN_MATCH_CAP * sizeof(uint2) + (size_t)n_blocks * 4 + 256; }
+
+static void launch_lanes(const uint8_t* comp, const BgzfBlock* bl, uint32_t n_blocks, uint8_t* out, uint32_t* status, void* scratch, cudaStream_t stream) {
+    constexpr int sh = 32 * LN_STRIDE;
     static bool attr = false;
     if (!attr) {
         attr = true;
-        cudaFuncSetAttribute(bgzf_inflate_lanes_kernel<LR, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, sh);
-        cudaFuncSetAttribute(bgzf_inflate_lanes_kernel<LR, DR>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaFuncSetAttribute(bgzf_inflate_lanes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     }
-    bgzf_inflate_lanes_kernel<LR, DR><<<(n_blocks + 31) / 32, 32, sh, stream>>>(comp, bl, n_blocks, out, status);
+    uint32_t* mcount = static_cast<uint32_t*>(scratch);
+    uint2* mlist = reinterpret_cast<uint2*>(static_cast<uint8_t*>(scratch) + (((size_t)n_blocks * 4 + 255) & ~(size_t)255));
+    bgzf_inflate_lanes_kernel<<<(n_blocks + 31) / 32, 32, sh, stream>>>(comp, bl, n_blocks, out, status, mlist, mcount);
+    bgzf_match_resolve_kernel<<<(n_blocks + MR_WARPS - 1) / MR_WARPS, MR_WARPS * 32, 0, stream>>>(bl, n_blocks, out, mlist, mcount);
 }
 
 __global__ void inflate_status_reduce_kernel(const uint32_t* __restrict__ status, uint32_t n, uint32_t* __restrict__ flags) {
@@ -842,34 +724,21 @@ void launch_inflate_status_reduce(const uint32_t* status, uint32_t n_blocks, uin
 }
 
 void launch_bgzf_inflate(const uint8_t* comp, const void* blocks, uint32_t n_blocks, uint8_t* out, uint32_t* status,
-                         cudaStream_t stream) {
+                         void* scratch, cudaStream_t stream) {
     if (n_blocks == 0) return;
-    // RTJX_INFLATE_VARIANT: 0 auto, 1 warp per block, 3 lane per stream (2: the round-1 thread-per-block build, kept for A/B).
-    // Read at every launch (a getenv, nanoseconds) so that tests can switch kernels inside one process.
+    // RTJX_INFLATE_VARIANT: 0 auto, 1 warp per block, 3 lane per stream.  Read at every launch (a getenv, nanoseconds) so that
+    // tests can switch kernels inside one process.  The lane-per-stream pair needs `scratch` (bgzf_inflate_scratch_bytes) and
+    // pays once a launch has enough blocks to occupy the lanes.
     int mode = 0;
     { const char* v = getenv("RTJX_INFLATE_VARIANT"); mode = v ? atoi(v) : 0; }
-    // lane-per-stream decoder: default whenever the launch has enough blocks to occupy the lanes (RTJX_INFLATE_VARIANT=3 forces
-    // it, =1 forces the warp-per-block kernel); RTJX_INFLATE_ROOT picks the root-table width (10 default, 9 / 11 for A/B)
-    int root = 10;
-    { const char* v = getenv("RTJX_INFLATE_ROOT"); if (v) root = atoi(v); }
-    if (mode == 3 || (mode == 0 && n_blocks >= 2048)) {
-        const BgzfBlock* bl = static_cast<const BgzfBlock*>(blocks);
-        if (root == 9) launch_lanes<9, 7>(comp, bl, n_blocks, out, status, stream);
-        else if (root == 11) launch_lanes<11, 8>(comp, bl, n_blocks, out, status, stream);
-        else launch_lanes<10, 8>(comp, bl, n_blocks, out, status, stream);
-        return;
-    }
-    if (mode == 2) {        // thread-per-block only pays with >~100k blocks in one launch; opt-in for now
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(bgzf_inflate_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SI_THREADS * SI_STRIDE); attr = true; }
-        bgzf_inflate_simt_kernel<<<(n_blocks + SI_THREADS - 1) / SI_THREADS, SI_THREADS, SI_THREADS * SI_STRIDE, stream>>>(
-            comp, static_cast<const BgzfBlock*>(blocks), n_blocks, out, status);
+    const BgzfBlock* bl = static_cast<const BgzfBlock*>(blocks);
+    if (scratch && (mode == 3 || (mode == 0 && n_blocks >= 1024))) {
+        launch_lanes(comp, bl, n_blocks, out, status, scratch, stream);
         return;
     }
     // lanes per decoder: 32 = one BGZF block per warp, 16 / 8 = two / four blocks per warp (RTJX_INFLATE_LANES)
     static int lanes = -1;
     if (lanes < 0) { const char* v = getenv("RTJX_INFLATE_LANES"); lanes = v ? atoi(v) : 16; }
-    const BgzfBlock* bl = static_cast<const BgzfBlock*>(blocks);
     if (lanes == 8) {
         constexpr int D = INF_WARPS * 32 / 8; const size_t sh = D * sizeof(InflateWarpSmem);
         static bool a8 = false; if (!a8) { cudaFuncSetAttribute(bgzf_inflate_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh); a8 = true; }

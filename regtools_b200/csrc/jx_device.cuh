@@ -148,8 +148,11 @@ void launch_finalize_sort(OutJunction* entries, uint32_t n, const uint32_t* cont
 
 // BGZF inflate on the device (inflate.cu).  `blocks` is an array of BgzfBlockDesc in device memory.
 struct BgzfBlockDesc { uint32_t in_off, in_len, out_off, out_len; };
+// scratch: bgzf_inflate_scratch_bytes(n_blocks) bytes of device memory for the lane-per-stream decoder's match lists
+// (NULL: only the warp-per-block kernel is used).
+size_t bgzf_inflate_scratch_bytes(uint32_t n_blocks);
 void launch_bgzf_inflate(const uint8_t* comp, const void* blocks, uint32_t n_blocks, uint8_t* out, uint32_t* status,
-                         cudaStream_t stream);
+                         void* scratch, cudaStream_t stream);
 
 void launch_inflate_status_reduce(const uint32_t* status, uint32_t n_blocks, uint32_t* flags, cudaStream_t stream);
 

@@ -1000,12 +1000,21 @@ struct alignas(16) PipeStage {
     uint32_t tid[PW];
     uint32_t slab[SL];
 };
-template <int SL, int NST>
+constexpr int PQ_OPS = 6;                         // CIGAR ops kept per queued alignment (longer CIGARs take the out-of-line walk)
+constexpr int PQ_CAP = 64;                        // queue slots per warp (< 32 left over + <= 32 new per filter round)
+// Plain mode: alignments that carry an N op wait here, with everything their walk needs, until 32 of them fill a round.
+struct alignas(16) PipeQueue {
+    uint32_t pos[PQ_CAP], meta[PQ_CAP], ordlo[PQ_CAP], o0[PQ_CAP], n[PQ_CAP];
+    int32_t  tid[PQ_CAP];
+    uint32_t op[PQ_OPS][PQ_CAP];
+};
+template <int SL, int NST, bool QUEUE>
 struct alignas(16) PipeWarpSmem {
     PipeStage<SL> st[NST];
     uint32_t cur, end;                            // generic path: cursor into the warp's reserved chunk
     uint32_t pad[2];
     uint8_t  work[PW];
+    PipeQueue q[QUEUE ? 1 : 0];
 };
 
 __device__ __forceinline__ void store_cand(Cand* __restrict__ out, uint32_t cap, uint32_t* counters, uint32_t idx,
@@ -1084,12 +1093,12 @@ __device__ __noinline__ void pipe_walk_rest(const uint32_t* __restrict__ ops, ui
 
 template <int N> __device__ __forceinline__ void cp_async_wait_n() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Processes the tile that sits in stage `st` (PW alignments from `base`): work list, walk, candidate stores.
+// Intron-motif / variant-region / barcode modes: processes the tile that sits in stage `st` (PW alignments from `base`) —
+// work list, walk with the per-candidate emit (PipeEmit), candidate stores through the warp's shared-memory chunk cursor.
 template <int SL, class WS, bool MOTIF, bool VREG, bool BC>
 __device__ __forceinline__ void pipe_process_tile(WS& ws, PipeStage<SL>& st, const BatchView& b, const ScanParams& prm, uint32_t base,
                                                   uint32_t lane, uint32_t vec_end, Cand* __restrict__ out, uint32_t cap,
-                                                  uint32_t* __restrict__ counters, uint32_t& c_cur, uint32_t& c_end) {
-    constexpr bool GENERIC = MOTIF || VREG || BC;
+                                                  uint32_t* __restrict__ counters) {
     const uint32_t n_tile = min((uint32_t)PW, b.n_reads - base);
     const uint32_t lo = st.off[0], hi = st.off[n_tile], a0 = lo & ~3u;
     uint32_t n_st = 0;                                         // words of the slab staged in shared memory (from a0)
@@ -1098,131 +1107,249 @@ __device__ __forceinline__ void pipe_process_tile(WS& ws, PipeStage<SL>& st, con
     // ---- work list of the alignments with more than one CIGAR op (junctions_extractor.cc:379)
     uint32_t n_work;
     {
+        const uint32_t lt = (1u << lane) - 1u;
         const uint4 o = *reinterpret_cast<const uint4*>(&st.off[4 * lane]);
         const uint32_t o4 = st.off[4 * lane + 4];
         const uint32_t r0 = 4 * lane;
-        uint32_t flags = 0;
-        if (r0 + 0 < n_tile && o.y - o.x > 1u) flags |= 1u;
-        if (r0 + 1 < n_tile && o.z - o.y > 1u) flags |= 2u;
-        if (r0 + 2 < n_tile && o.w - o.z > 1u) flags |= 4u;
-        if (r0 + 3 < n_tile && o4 - o.w > 1u) flags |= 8u;
-        const uint32_t cnt = __popc(flags);
-        uint32_t x = cnt;
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
-        n_work = __shfl_sync(0xffffffffu, x, 31);
-        uint32_t p = x - cnt;
-        if (flags & 1u) ws.work[p++] = (uint8_t)(r0 + 0);
-        if (flags & 2u) ws.work[p++] = (uint8_t)(r0 + 1);
-        if (flags & 4u) ws.work[p++] = (uint8_t)(r0 + 2);
-        if (flags & 8u) ws.work[p++] = (uint8_t)(r0 + 3);
+        const bool f0 = r0 + 0 < n_tile && o.y - o.x > 1u, f1 = r0 + 1 < n_tile && o.z - o.y > 1u;
+        const bool f2 = r0 + 2 < n_tile && o.w - o.z > 1u, f3 = r0 + 3 < n_tile && o4 - o.w > 1u;
+        const uint32_t m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
+        const uint32_t m2 = __ballot_sync(0xffffffffu, f2), m3 = __ballot_sync(0xffffffffu, f3);
+        const uint32_t s1 = __popc(m0), s2 = s1 + __popc(m1), s3 = s2 + __popc(m2);
+        n_work = s3 + __popc(m3);
+        if (f0) ws.work[__popc(m0 & lt)] = (uint8_t)(r0 + 0);
+        if (f1) ws.work[s1 + __popc(m1 & lt)] = (uint8_t)(r0 + 1);
+        if (f2) ws.work[s2 + __popc(m2 & lt)] = (uint8_t)(r0 + 2);
+        if (f3) ws.work[s3 + __popc(m3 & lt)] = (uint8_t)(r0 + 3);
     }
     __syncwarp();
 
     // ---- walk, one alignment per lane, rounds of 32
     for (uint32_t w0 = 0; w0 < n_work; w0 += 32) {
         const uint32_t w = w0 + lane;
-        if (!GENERIC) {
-            uint32_t nc = 0, strand = 0;
-            int32_t tid = -1;
-            uint64_t read_ord = 0;
-            WalkCand c0{0, 0, 0, 0, 0}, c1{0, 0, 0, 0, 0};
-            if (w < n_work) {
-                const uint32_t r = ws.work[w];
-                tid = (int32_t)st.tid[r];
-                if (tid >= 0) {
-                    const uint32_t o0 = st.off[r], n = st.off[r + 1] - o0;
-                    strand = read_strand(st.meta[r], prm.strandness);
-                    read_ord = b.first_ordinal + base + r;
-                    const bool in_smem = (o0 - a0) + n <= n_st;
-                    nc = in_smem ? walk_collect<true>(st.slab + (o0 - a0), n, st.pos[r], c0, c1)
-                                 : walk_collect<false>(b.cigar + o0, n, st.pos[r], c0, c1);
-                    if (nc > 2u) pipe_walk_rest(b.cigar + o0, n, st.pos[r], tid, strand, read_ord, out, cap, counters);
-                }
-            }
-            const uint32_t n2 = min(nc, 2u);
-            uint32_t x = n2;
-#pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
-            const uint32_t tot = __shfl_sync(0xffffffffu, x, 31);
-            if (tot) {
-                const uint32_t rem = c_end - c_cur;
-                uint32_t nbase = 0;
-                if (tot > rem) {                              // the chunk runs out inside this round: the rest goes to a new one
-                    if (lane == 0) nbase = atomicAdd(&counters[CTR_NCAND], (uint32_t)PCH);
-                    nbase = __shfl_sync(0xffffffffu, nbase, 0);
-                }
-                const uint32_t j0 = x - n2;
-                if (n2 > 0u) {
-                    const uint64_t ord = read_ord << 16 | c0.k;
-                    store_cand(out, cap, counters, j0 < rem ? c_cur + j0 : nbase + (j0 - rem),
-                               make_uint4(c0.start, c0.end, c0.start - c0.left, c0.end + c0.right),
-                               make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
-                }
-                if (n2 > 1u) {
-                    const uint64_t ord = read_ord << 16 | c1.k;
-                    const uint32_t j1 = j0 + 1u;
-                    store_cand(out, cap, counters, j1 < rem ? c_cur + j1 : nbase + (j1 - rem),
-                               make_uint4(c1.start, c1.end, c1.start - c1.left, c1.end + c1.right),
-                               make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
-                }
-                if (tot > rem) { c_cur = nbase + (tot - rem); c_end = nbase + (uint32_t)PCH; } else c_cur += tot;
-            }
-        } else {
-            // make sure the round starts with a chunk that holds 64 more candidates; pad what is left of the old one
-            if (ws.end - min(ws.cur, ws.end) < 64u) {
-                const uint32_t pc = min(ws.cur, ws.end), pe = ws.end;
-                __syncwarp();
-                for (uint32_t i = pc + lane; i < pe; i += 32) store_cand(out, cap, counters, i, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0xffffffffu, 0));
-                uint32_t nbase = 0;
-                if (lane == 0) nbase = atomicAdd(&counters[CTR_NCAND], 2u * PCH);
-                nbase = __shfl_sync(0xffffffffu, nbase, 0);
-                if (lane == 0) { ws.cur = nbase; ws.end = nbase + 2u * PCH; }
-                __syncwarp();
-            }
-            if (w < n_work) {
-                const uint32_t r = ws.work[w];
-                const int32_t tid = (int32_t)st.tid[r];
-                if (tid >= 0) {
-                    const uint32_t o0 = st.off[r], n = st.off[r + 1] - o0;
-                    uint32_t strand = read_strand(st.meta[r], prm.strandness);
-                    if (BC) strand |= (__ldg(b.bc + base + r) + 1u) << 8;      // set_junction_barcode (:362-374): one barcode per alignment
-                    const uint64_t read_ord = b.first_ordinal + base + r;
-                    uint32_t jstrand = 0;                     // j1.strand == "" before an alignment's first junction
-                    int32_t rspan[2] = {0, 0};
-                    const bool in_smem = (o0 - a0) + n <= n_st;
-                    if (VREG) {                                // endpos = pos + reference length of the CIGAR (sam.c:327-342)
-                        uint32_t rl = 0;
-                        for (uint32_t q = 0; q < n; ++q) {
-                            const uint32_t x = in_smem ? st.slab[o0 - a0 + q] : __ldg(b.cigar + o0 + q);
-                            if ((0x18Du >> (x & 0xfu)) & 1u) rl += x >> 4;      // M, D, N, =, X consume the reference
-                        }
-                        // bam_endpos (sam.c:336-342): an alignment flagged BAM_FUNMAP spans one base whatever its CIGAR says
-                        const bool unmapped = ((st.meta[r] >> 16) & 4u) != 0;
-                        rspan[0] = (int32_t)st.pos[r]; rspan[1] = (int32_t)(st.pos[r] + (unmapped ? 1u : rl));
+        // make sure the round starts with a chunk that holds 64 more candidates; pad what is left of the old one
+        if (ws.end - min(ws.cur, ws.end) < 64u) {
+            const uint32_t pc = min(ws.cur, ws.end), pe = ws.end;
+            __syncwarp();
+            for (uint32_t i = pc + lane; i < pe; i += 32) store_cand(out, cap, counters, i, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0xffffffffu, 0));
+            uint32_t nbase = 0;
+            if (lane == 0) nbase = atomicAdd(&counters[CTR_NCAND], 2u * PCH);
+            nbase = __shfl_sync(0xffffffffu, nbase, 0);
+            if (lane == 0) { ws.cur = nbase; ws.end = nbase + 2u * PCH; }
+            __syncwarp();
+        }
+        if (w < n_work) {
+            const uint32_t r = ws.work[w];
+            const int32_t tid = (int32_t)st.tid[r];
+            if (tid >= 0) {
+                const uint32_t o0 = st.off[r], n = st.off[r + 1] - o0;
+                uint32_t strand = read_strand(st.meta[r], prm.strandness);
+                if (BC) strand |= (__ldg(b.bc + base + r) + 1u) << 8;      // set_junction_barcode (:362-374): one barcode per alignment
+                const uint64_t read_ord = b.first_ordinal + base + r;
+                uint32_t jstrand = 0;                         // j1.strand == "" before an alignment's first junction
+                int32_t rspan[2] = {0, 0};
+                const bool in_smem = (o0 - a0) + n <= n_st;
+                if (VREG) {                                    // endpos = pos + reference length of the CIGAR (sam.c:327-342)
+                    uint32_t rl = 0;
+                    for (uint32_t q = 0; q < n; ++q) {
+                        const uint32_t x = in_smem ? st.slab[o0 - a0 + q] : __ldg(b.cigar + o0 + q);
+                        if ((0x18Du >> (x & 0xfu)) & 1u) rl += x >> 4;      // M, D, N, =, X consume the reference
                     }
-                    const PipeEmit<WS, MOTIF, VREG, BC> emit{ws, out, cap, counters, &prm, &jstrand, rspan};
-                    if (in_smem) walk_fast<true>(st.slab + (o0 - a0), n, st.pos[r], tid, strand, read_ord, emit);
-                    else walk_fast<false>(b.cigar + o0, n, st.pos[r], tid, strand, read_ord, emit);
+                    // bam_endpos (sam.c:336-342): an alignment flagged BAM_FUNMAP spans one base whatever its CIGAR says
+                    const bool unmapped = ((st.meta[r] >> 16) & 4u) != 0;
+                    rspan[0] = (int32_t)st.pos[r]; rspan[1] = (int32_t)(st.pos[r] + (unmapped ? 1u : rl));
+                }
+                const PipeEmit<WS, MOTIF, VREG, BC> emit{ws, out, cap, counters, &prm, &jstrand, rspan};
+                if (in_smem) walk_fast<true>(st.slab + (o0 - a0), n, st.pos[r], tid, strand, read_ord, emit);
+                else walk_fast<false>(b.cigar + o0, n, st.pos[r], tid, strand, read_ord, emit);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// all N ops of an alignment whose CIGAR is too long for the queue (plain mode; rare): one slot each
+__device__ __noinline__ void pipe_walk_all(const uint32_t* __restrict__ ops, uint32_t n, uint32_t pos, int32_t tid, uint32_t strand,
+                                           uint64_t read_ord, Cand* __restrict__ out, uint32_t cap, uint32_t* counters) {
+    const uint32_t ANC = (1u << 0) | (1u << 7);
+    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
+    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
+    uint32_t cur = pos, run = 0;
+    bool pending = false;
+    uint32_t p_start = 0, p_end = 0, p_left = 0, p_k = 0;
+    auto emit = [&]() {
+        const uint64_t ord = read_ord << 16 | p_k;
+        const uint32_t g = atomicAdd(&counters[CTR_NCAND], 1u);
+        store_cand(out, cap, counters, g, make_uint4(p_start, p_end, p_start - p_left, p_end + run),
+                   make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
+    };
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t x = __ldg(ops + i), op = x & 0xfu, len = x >> 4, bit = 1u << op;
+        if (bit & BRK) {
+            if (pending) emit();
+            pending = op == 3u;
+            if (pending) { p_start = cur; p_end = cur + len; p_left = run; p_k = i > 0xffffu ? 0xffffu : i; }
+            run = 0;
+        } else if (bit & ANC) {
+            run += len;
+        }
+        if (bit & REFC) cur += len;
+    }
+    if (pending) emit();
+}
+
+// Plain mode, one round: up to 32 queued alignments (queue slots head .. head + cnt - 1), one per lane, are walked
+// (parse_alignment_into_junctions, junctions_extractor.cc:377-497, closed form of SURVEY App. A.2: branch-free, the first two
+// N ops stay in registers) and their candidates stored into the warp's chunk.
+__device__ __forceinline__ void pipe_walk_round(const PipeQueue& q, uint32_t head, uint32_t cnt, uint32_t lane, const BatchView& b,
+                                                const ScanParams& prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters,
+                                                uint32_t& c_cur, uint32_t& c_end) {
+    const uint32_t ANC = (1u << 0) | (1u << 7);
+    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
+    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
+    const bool act = lane < cnt;
+    const uint32_t s = (head + lane) & (PQ_CAP - 1);
+    const uint32_t n = act ? q.n[s] : 0u;
+    const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
+    uint32_t cur = q.pos[s], run = 0, nc = 0;
+    bool pending = false;
+    WalkCand c0{0, 0, 0, 0, 0}, c1{0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < PQ_OPS; ++i) {
+        if ((uint32_t)i >= nmax) break;                        // warp-uniform
+        const uint32_t x = (uint32_t)i < n ? q.op[i][s] : 0xfu;  // op code 15: transparent filler
+        const uint32_t op = x & 0xfu, len = x >> 4, bit = 1u << op;
+        const bool brk = (bit & BRK) != 0, is_n = op == 3u;
+        const bool close = pending && brk;                  // the open junction ends here: right anchor = run
+        c0.right = (close && nc == 1u) ? run : c0.right;
+        c1.right = (close && nc == 2u) ? run : c1.right;
+        const bool open0 = is_n && nc == 0u, open1 = is_n && nc == 1u;
+        c0.start = open0 ? cur : c0.start; c0.end = open0 ? cur + len : c0.end; c0.left = open0 ? run : c0.left; c0.k = open0 ? (uint32_t)i : c0.k;
+        c1.start = open1 ? cur : c1.start; c1.end = open1 ? cur + len : c1.end; c1.left = open1 ? run : c1.left; c1.k = open1 ? (uint32_t)i : c1.k;
+        nc += is_n ? 1u : 0u;
+        pending = brk ? is_n : pending;
+        run = brk ? 0u : run + ((bit & ANC) ? len : 0u);
+        cur += (bit & REFC) ? len : 0u;
+    }
+    c0.right = (pending && nc == 1u) ? run : c0.right;
+    c1.right = (pending && nc == 2u) ? run : c1.right;
+    const int32_t tid = q.tid[s];
+    const uint32_t strand = read_strand(q.meta[s], prm.strandness);
+    const uint64_t read_ord = b.first_ordinal + q.ordlo[s];
+    if (nc > 2u) pipe_walk_rest(b.cigar + q.o0[s], n, q.pos[s], tid, strand, read_ord, out, cap, counters);
+    // ---- positions in the chunk: first candidates of all lanes, then second candidates
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t b1 = __ballot_sync(0xffffffffu, nc >= 1u), b2 = __ballot_sync(0xffffffffu, nc >= 2u);
+    const uint32_t t1 = __popc(b1), tot = t1 + __popc(b2);
+    if (tot) {
+        const uint32_t rem = c_end - c_cur;
+        uint32_t nbase = 0;
+        if (tot > rem) {                                      // the chunk runs out inside this round: the rest goes to a new one
+            if (lane == 0) nbase = atomicAdd(&counters[CTR_NCAND], (uint32_t)PCH);
+            nbase = __shfl_sync(0xffffffffu, nbase, 0);
+        }
+        if (nc >= 1u) {
+            const uint64_t ord = read_ord << 16 | c0.k;
+            const uint32_t j = __popc(b1 & lt);
+            store_cand(out, cap, counters, j < rem ? c_cur + j : nbase + (j - rem),
+                       make_uint4(c0.start, c0.end, c0.start - c0.left, c0.end + c0.right),
+                       make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
+        }
+        if (nc >= 2u) {
+            const uint64_t ord = read_ord << 16 | c1.k;
+            const uint32_t j = t1 + __popc(b2 & lt);
+            store_cand(out, cap, counters, j < rem ? c_cur + j : nbase + (j - rem),
+                       make_uint4(c1.start, c1.end, c1.start - c1.left, c1.end + c1.right),
+                       make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
+        }
+        if (tot > rem) { c_cur = nbase + (tot - rem); c_end = nbase + (uint32_t)PCH; } else c_cur += tot;
+    }
+}
+
+// Plain mode, per tile: the alignments with more than one CIGAR op (junctions_extractor.cc:379) are listed (ballots, no scan),
+// then — all lanes busy, one listed alignment each — those that carry an N op are moved to the warp's queue together with their
+// first PQ_OPS ops; whenever 32 are queued a round is walked.  The ~55 % of multi-op alignments without an N op (soft clips,
+// indels) cost one filter slot, never a walk.
+template <int SL, class WS>
+__device__ __forceinline__ void pipe_filter_tile(WS& ws, PipeStage<SL>& st, const BatchView& b, const ScanParams& prm, uint32_t base,
+                                                 uint32_t lane, uint32_t vec_end, Cand* __restrict__ out, uint32_t cap,
+                                                 uint32_t* __restrict__ counters, uint32_t& c_cur, uint32_t& c_end,
+                                                 uint32_t& q_head, uint32_t& q_cnt) {
+    PipeQueue& q = ws.q[0];
+    const uint32_t n_tile = min((uint32_t)PW, b.n_reads - base);
+    const uint32_t lo = st.off[0], hi = st.off[n_tile], a0 = lo & ~3u;
+    uint32_t n_st = 0;                                         // words of the slab staged in shared memory (from a0)
+    if (hi > lo) { const uint32_t end = min(min((hi + 3u) & ~3u, a0 + (uint32_t)SL), vec_end); n_st = end > a0 ? end - a0 : 0u; }
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t n_work;
+    {
+        const uint4 o = *reinterpret_cast<const uint4*>(&st.off[4 * lane]);
+        const uint32_t o4 = st.off[4 * lane + 4];
+        const uint32_t r0 = 4 * lane;
+        const bool f0 = r0 + 0 < n_tile && o.y - o.x > 1u, f1 = r0 + 1 < n_tile && o.z - o.y > 1u;
+        const bool f2 = r0 + 2 < n_tile && o.w - o.z > 1u, f3 = r0 + 3 < n_tile && o4 - o.w > 1u;
+        const uint32_t m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
+        const uint32_t m2 = __ballot_sync(0xffffffffu, f2), m3 = __ballot_sync(0xffffffffu, f3);
+        const uint32_t s1 = __popc(m0), s2 = s1 + __popc(m1), s3 = s2 + __popc(m2);
+        n_work = s3 + __popc(m3);
+        if (f0) ws.work[__popc(m0 & lt)] = (uint8_t)(r0 + 0);
+        if (f1) ws.work[s1 + __popc(m1 & lt)] = (uint8_t)(r0 + 1);
+        if (f2) ws.work[s2 + __popc(m2 & lt)] = (uint8_t)(r0 + 2);
+        if (f3) ws.work[s3 + __popc(m3 & lt)] = (uint8_t)(r0 + 3);
+    }
+    __syncwarp();
+    for (uint32_t w0 = 0; w0 < n_work; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        bool take = false;
+        uint32_t r = 0, o0 = 0, n = 0, x[PQ_OPS];
+        int32_t tid = -1;
+        if (w < n_work) {
+            r = ws.work[w];
+            tid = (int32_t)st.tid[r];
+            o0 = st.off[r]; n = st.off[r + 1] - o0;
+            if (tid >= 0) {
+                if (n <= (uint32_t)PQ_OPS) {
+                    const bool in_smem = (o0 - a0) + n <= n_st;
+                    bool has_n = false;
+#pragma unroll
+                    for (int i = 0; i < PQ_OPS; ++i) {
+                        x[i] = (uint32_t)i < n ? (in_smem ? st.slab[o0 - a0 + i] : __ldg(b.cigar + o0 + i)) : 0xfu;
+                        has_n = has_n || (x[i] & 0xfu) == 3u;
+                    }
+                    take = has_n;
+                } else {                                      // long CIGAR: walked right away, out of line
+                    pipe_walk_all(b.cigar + o0, n, st.pos[r], tid, read_strand(st.meta[r], prm.strandness), b.first_ordinal + base + r,
+                                  out, cap, counters);
                 }
             }
+        }
+        const uint32_t tm = __ballot_sync(0xffffffffu, take);
+        if (take) {
+            const uint32_t s = (q_head + q_cnt + __popc(tm & lt)) & (PQ_CAP - 1);
+            q.pos[s] = st.pos[r]; q.meta[s] = st.meta[r]; q.tid[s] = tid; q.ordlo[s] = base + r; q.o0[s] = o0; q.n[s] = n;
+#pragma unroll
+            for (int i = 0; i < PQ_OPS; ++i) q.op[i][s] = x[i];
+        }
+        q_cnt += __popc(tm);
+        __syncwarp();
+        if (q_cnt >= 32u) {
+            pipe_walk_round(q, q_head, 32u, lane, b, prm, out, cap, counters, c_cur, c_end);
+            q_head = (q_head + 32u) & (PQ_CAP - 1); q_cnt -= 32u;
             __syncwarp();
         }
     }
 }
 
-// LOADS: 0 = cp.async (LDGSTS) into a ring of NST stages, NST - 1 tiles in flight per warp;
-//        1 = register-staged: the next tile's 128-bit loads are issued into registers before the current tile is walked and stored
-//            to the (single) stage afterwards — one tile in flight per warp, more warps per SM (NST must be 1).
-template <int SL, int NST, int NWARP, int MINB, int LOADS, bool MOTIF, bool VREG, bool BC>
+// The warp-pipelined kernel: cp.async (LDGSTS) into a ring of NST stages, NST - 1 tiles in flight per warp.
+template <int SL, int NST, int NWARP, int MINB, bool MOTIF, bool VREG, bool BC>
 __global__ void __launch_bounds__(NWARP * 32, MINB)
 cigar_scan_pipe_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
-    using WS = PipeWarpSmem<SL, NST>;
     constexpr bool GENERIC = MOTIF || VREG || BC;
-    static_assert(LOADS == 0 ? NST >= 2 : NST == 1, "ring depth does not fit the load mode");
-    static_assert(SL % 128 == 0, "slab window must be a multiple of 128 words");
-    constexpr int D = LOADS == 0 ? NST - 1 : 1;               // tiles in flight per warp
-    constexpr int SLV = SL / 128;                             // 16-byte slab vectors per lane
+    using WS = PipeWarpSmem<SL, NST, !GENERIC>;
+    static_assert(NST >= 2, "the ring needs two stages");
+    static_assert(SL % 128 == 0 && SL <= 512, "slab window: a multiple of 128 words, at most four 16-byte copies per lane");
+    constexpr int D = NST - 1;                                // tiles in flight per warp
+    constexpr int SLV = SL / 128;                             // 16-byte slab copies per lane
     extern __shared__ __align__(16) unsigned char pipe_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     WS& ws = reinterpret_cast<WS*>(pipe_raw)[warp];
@@ -1242,109 +1369,55 @@ cigar_scan_pipe_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint
         return __ldg(b.cig_off + ((lane & 1u) ? min(base + (uint32_t)PW, b.n_reads) : base));
     };
     uint32_t bq_cur = load_bq(0), bq_next = load_bq(1);
-    auto bounds_of = [&](uint32_t kk, uint32_t& lo, uint32_t& hi) {   // called for kk = 0, 1, 2, ... in order, once each
-        if (kk != 0u && (kk & 15u) == 0u) { bq_cur = bq_next; bq_next = load_bq((kk >> 4) + 1u); }
-        lo = __shfl_sync(0xffffffffu, bq_cur, 2 * (kk & 15u));
-        hi = __shfl_sync(0xffffffffu, bq_cur, 2 * (kk & 15u) + 1);
-    };
     uint32_t c_cur = 0, c_end = 0;                            // plain mode: the warp's chunk (uniform registers)
+    uint32_t q_head = 0, q_cnt = 0;                           // plain mode: the warp's queue
 
-    if (LOADS == 0) {
-        auto issue = [&](uint32_t kk) {
-            uint32_t lo, hi;
-            bounds_of(kk, lo, hi);
-            const uint32_t base = (gw + kk * TW) * PW;
-            PipeStage<SL>& st = ws.st[kk % NST];
-            if (base + PW + 3 <= b.n_reads) {                 // the (PW + 4)-entry cig_off window is in bounds
-                cp_async16(&st.off[4 * lane], b.cig_off + base + 4 * lane);
-                cp_async16(&st.pos[4 * lane], b.pos + base + 4 * lane);
-                cp_async16(&st.meta[4 * lane], b.meta + base + 4 * lane);
-                cp_async16(&st.tid[4 * lane], b.tid + base + 4 * lane);
-                if (lane == 0) cp_async16(&st.off[PW], b.cig_off + base + PW);
-            } else {                                          // ragged tail of the batch: plain loads
-                const uint32_t n_tile = min((uint32_t)PW, b.n_reads - base);
-                for (uint32_t r = lane; r < n_tile; r += 32) {
-                    st.pos[r] = (uint32_t)b.pos[base + r]; st.meta[r] = b.meta[base + r]; st.tid[r] = (uint32_t)b.tid[base + r];
-                }
-                for (uint32_t r = lane; r <= n_tile; r += 32) st.off[r] = b.cig_off[base + r];
+    auto issue = [&](uint32_t kk) {                           // called for kk = 0, 1, 2, ... in order, once each
+        if (kk != 0u && (kk & 15u) == 0u) { bq_cur = bq_next; bq_next = load_bq((kk >> 4) + 1u); }
+        const uint32_t lo = __shfl_sync(0xffffffffu, bq_cur, 2 * (kk & 15u)), hi = __shfl_sync(0xffffffffu, bq_cur, 2 * (kk & 15u) + 1);
+        const uint32_t base = (gw + kk * TW) * PW;
+        PipeStage<SL>& st = ws.st[kk % NST];
+        if (base + PW <= b.n_reads) {                         // a full tile: its closing offset is the slab's upper bound
+            cp_async16(&st.off[4 * lane], b.cig_off + base + 4 * lane);
+            cp_async16(&st.pos[4 * lane], b.pos + base + 4 * lane);
+            cp_async16(&st.meta[4 * lane], b.meta + base + 4 * lane);
+            cp_async16(&st.tid[4 * lane], b.tid + base + 4 * lane);
+            if (lane == 0) st.off[PW] = hi;
+        } else {                                              // ragged tail of the batch: plain loads
+            const uint32_t n_tile = b.n_reads - base;
+            for (uint32_t r = lane; r < n_tile; r += 32) {
+                st.pos[r] = (uint32_t)b.pos[base + r]; st.meta[r] = b.meta[base + r]; st.tid[r] = (uint32_t)b.tid[base + r];
             }
-            if (hi > lo) {
-                const uint32_t a0 = lo & ~3u;
-                const uint32_t end = min(min((hi + 3u) & ~3u, a0 + (uint32_t)SL), vec_end);
-                const uint32_t nv = end > a0 ? (end - a0) >> 2 : 0u;
-                for (uint32_t v = lane; v < nv; v += 32) cp_async16(&st.slab[4 * v], b.cigar + a0 + 4 * v);
-            }
-        };
-#pragma unroll
-        for (int j = 0; j < D; ++j) {                         // prologue: D tiles in flight
-            if ((uint32_t)j < n_my) issue(j);
-            cp_async_commit();
+            for (uint32_t r = lane; r <= n_tile; r += 32) st.off[r] = b.cig_off[base + r];
         }
-        for (uint32_t k = 0; k < n_my; ++k) {
-            if (k + D < n_my) issue(k + D);
-            cp_async_commit();
-            cp_async_wait_n<D>();                             // this lane's copies of tile k have landed ...
-            __syncwarp();                                     // ... and so have every other lane's
-            pipe_process_tile<SL, WS, MOTIF, VREG, BC>(ws, ws.st[k % NST], b, prm, (gw + k * TW) * PW, lane, vec_end, out, cap, counters, c_cur, c_end);
-            __syncwarp();                                     // the stage and the work list are rewritten from the next iteration on
-        }
-    } else {
-        uint4 r_off, r_pos, r_meta, r_tid, r_sl[SLV];
-        uint32_t r_lo = 0, r_hi = 0;
-        auto load_tile = [&](uint32_t kk) {
-            bounds_of(kk, r_lo, r_hi);
-            const uint32_t base = (gw + kk * TW) * PW;
-            if (base + PW + 3 <= b.n_reads) {
-                r_off = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cig_off + base) + lane);
-                r_pos = ldg_stream_u4(reinterpret_cast<const uint4*>(b.pos + base) + lane);
-                r_meta = ldg_stream_u4(reinterpret_cast<const uint4*>(b.meta + base) + lane);
-                r_tid = ldg_stream_u4(reinterpret_cast<const uint4*>(b.tid + base) + lane);
-            }
-            if (r_hi > r_lo) {
-                const uint32_t a0 = r_lo & ~3u;
-                const uint32_t end = min(min((r_hi + 3u) & ~3u, a0 + (uint32_t)SL), vec_end);
-                const uint32_t nv = end > a0 ? (end - a0) >> 2 : 0u;
+        if (hi > lo) {
+            const uint32_t a0 = lo & ~3u;
+            const uint32_t end = min(min((hi + 3u) & ~3u, a0 + (uint32_t)SL), vec_end);
+            const uint32_t nv = end > a0 ? (end - a0) >> 2 : 0u;
+            const uint32_t* src = b.cigar + a0 + 4 * lane;
 #pragma unroll
-                for (int j = 0; j < SLV; ++j)
-                    if (lane + 32u * j < nv) r_sl[j] = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cigar + a0) + lane + 32u * j);
-            }
-        };
-        auto store_tile = [&](uint32_t kk) {                  // registers -> the stage (waits for the loads of tile kk)
-            const uint32_t base = (gw + kk * TW) * PW;
-            PipeStage<SL>& st = ws.st[0];
-            if (base + PW + 3 <= b.n_reads) {
-                *reinterpret_cast<uint4*>(&st.off[4 * lane]) = r_off;
-                *reinterpret_cast<uint4*>(&st.pos[4 * lane]) = r_pos;
-                *reinterpret_cast<uint4*>(&st.meta[4 * lane]) = r_meta;
-                *reinterpret_cast<uint4*>(&st.tid[4 * lane]) = r_tid;
-                if (lane == 0) st.off[PW] = r_hi;
-            } else {
-                const uint32_t n_tile = min((uint32_t)PW, b.n_reads - base);
-                for (uint32_t r = lane; r < n_tile; r += 32) {
-                    st.pos[r] = (uint32_t)b.pos[base + r]; st.meta[r] = b.meta[base + r]; st.tid[r] = (uint32_t)b.tid[base + r];
-                }
-                for (uint32_t r = lane; r <= n_tile; r += 32) st.off[r] = b.cig_off[base + r];
-            }
-            if (r_hi > r_lo) {
-                const uint32_t a0 = r_lo & ~3u;
-                const uint32_t end = min(min((r_hi + 3u) & ~3u, a0 + (uint32_t)SL), vec_end);
-                const uint32_t nv = end > a0 ? (end - a0) >> 2 : 0u;
-#pragma unroll
-                for (int j = 0; j < SLV; ++j)
-                    if (lane + 32u * j < nv) *reinterpret_cast<uint4*>(&st.slab[4 * (lane + 32u * j)]) = r_sl[j];
-            }
-        };
-        load_tile(0);
-        for (uint32_t k = 0; k < n_my; ++k) {
-            store_tile(k);
-            __syncwarp();
-            if (k + 1 < n_my) load_tile(k + 1);               // in flight while tile k is walked
-            pipe_process_tile<SL, WS, MOTIF, VREG, BC>(ws, ws.st[0], b, prm, (gw + k * TW) * PW, lane, vec_end, out, cap, counters, c_cur, c_end);
-            __syncwarp();
+            for (int j = 0; j < SLV; ++j)
+                if (lane + 32u * j < nv) cp_async16(&st.slab[4 * (lane + 32 * j)], src + 128 * j);
         }
+    };
+#pragma unroll
+    for (int j = 0; j < D; ++j) {                             // prologue: D tiles in flight
+        if ((uint32_t)j < n_my) issue(j);
+        cp_async_commit();
     }
-    // ---- unused tail of the warp's last chunk: entries junction_merge skips
+    for (uint32_t k = 0; k < n_my; ++k) {
+        if (k + D < n_my) issue(k + D);
+        cp_async_commit();
+        cp_async_wait_n<D>();                                 // this lane's copies of tile k have landed ...
+        __syncwarp();                                         // ... and so have every other lane's
+        const uint32_t base = (gw + k * TW) * PW;
+        if (GENERIC) pipe_process_tile<SL, WS, MOTIF, VREG, BC>(ws, ws.st[k % NST], b, prm, base, lane, vec_end, out, cap, counters);
+        else pipe_filter_tile<SL, WS>(ws, ws.st[k % NST], b, prm, base, lane, vec_end, out, cap, counters, c_cur, c_end, q_head, q_cnt);
+        __syncwarp();                                         // the stage and the work list are rewritten from the next iteration on
+    }
     if (!GENERIC) {
+        // ---- what is left in the queue, then the unused tail of the warp's last chunk: entries junction_merge skips
+        if (q_cnt) pipe_walk_round(ws.q[0], q_head, q_cnt, lane, b, prm, out, cap, counters, c_cur, c_end);
         for (uint32_t i = c_cur + lane; i < c_end; i += 32) store_cand(out, cap, counters, i, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0xffffffffu, 0));
     } else {
         __syncwarp();
@@ -1377,11 +1450,11 @@ void cigar_scan_region_layout(uint32_t n_reads, uint32_t* n_regions, uint32_t* c
 }
 
 // Launch of the warp-pipelined kernel: persistent grid of BPS blocks per SM, NWARP warps each.
-template <int SL, int NST, int NWARP, int BPS, int LOADS, bool MOTIF, bool VREG, bool BC>
+template <int SL, int NST, int NWARP, int BPS, bool MOTIF, bool VREG, bool BC>
 static void launch_pipe_mode(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap, uint32_t* d_counters, cudaStream_t stream) {
-    constexpr size_t smem = (size_t)NWARP * sizeof(PipeWarpSmem<SL, NST>);
+    constexpr size_t smem = (size_t)NWARP * sizeof(PipeWarpSmem<SL, NST, !(MOTIF || VREG || BC)>);
     static_assert((smem + 1024) * BPS <= 228u * 1024u, "pipelined scan: shared memory of the resident blocks exceeds an SM");
-    auto kern = cigar_scan_pipe_kernel<SL, NST, NWARP, BPS, LOADS, MOTIF, VREG, BC>;
+    auto kern = cigar_scan_pipe_kernel<SL, NST, NWARP, BPS, MOTIF, VREG, BC>;
     static bool once = false;
     if (!once) {
         once = true;
@@ -1390,24 +1463,24 @@ static void launch_pipe_mode(const BatchView& b, const ScanParams& p, Cand* cand
         if (getenv("RTJX_TRACE")) {
             int nb = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NWARP * 32, smem);
-            fprintf(stderr, "[rtjx] cigar_scan_pipe<SL %d, NST %d, %d warps, %d blocks/SM asked, loads %d>: %zu B shared memory per block, %d blocks/SM resident\n",
-                    SL, NST, NWARP, BPS, LOADS, smem, nb);
+            fprintf(stderr, "[rtjx] cigar_scan_pipe<SL %d, NST %d, %d warps, %d blocks/SM asked>: %zu B shared memory per block, %d blocks/SM resident\n",
+                    SL, NST, NWARP, BPS, smem, nb);
         }
     }
     const uint32_t n_wt = (b.n_reads + PW - 1) / PW;
     const uint32_t grid = max(1u, min((n_wt + NWARP - 1) / NWARP, (uint32_t)(num_sms() * BPS)));
     kern<<<grid, NWARP * 32, smem, stream>>>(b, p, cands, cand_cap, d_counters);
 }
-template <int SL, int NST, int NWARP, int BPS, int LOADS = 0, bool SPECIAL = false>
+template <int SL, int NST, int NWARP, int BPS, bool SPECIAL = false>
 static void launch_pipe(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap, uint32_t* d_counters, cudaStream_t stream) {
     if constexpr (SPECIAL) {                                  // intron-motif / variant-region / barcode modes
-        if (b.bc && p.genome) launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, true, false, true>(b, p, cands, cand_cap, d_counters, stream);
-        else if (b.bc) launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, false, false, true>(b, p, cands, cand_cap, d_counters, stream);
-        else if (p.vr.n && p.genome) launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, true, true, false>(b, p, cands, cand_cap, d_counters, stream);
-        else if (p.vr.n) launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, false, true, false>(b, p, cands, cand_cap, d_counters, stream);
-        else launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, true, false, false>(b, p, cands, cand_cap, d_counters, stream);
+        if (b.bc && p.genome) launch_pipe_mode<SL, NST, NWARP, BPS, true, false, true>(b, p, cands, cand_cap, d_counters, stream);
+        else if (b.bc) launch_pipe_mode<SL, NST, NWARP, BPS, false, false, true>(b, p, cands, cand_cap, d_counters, stream);
+        else if (p.vr.n && p.genome) launch_pipe_mode<SL, NST, NWARP, BPS, true, true, false>(b, p, cands, cand_cap, d_counters, stream);
+        else if (p.vr.n) launch_pipe_mode<SL, NST, NWARP, BPS, false, true, false>(b, p, cands, cand_cap, d_counters, stream);
+        else launch_pipe_mode<SL, NST, NWARP, BPS, true, false, false>(b, p, cands, cand_cap, d_counters, stream);
     } else {
-        launch_pipe_mode<SL, NST, NWARP, BPS, LOADS, false, false, false>(b, p, cands, cand_cap, d_counters, stream);
+        launch_pipe_mode<SL, NST, NWARP, BPS, false, false, false>(b, p, cands, cand_cap, d_counters, stream);
     }
 }
 // Candidate slots cigar_scan may reserve beyond the number of N ops of a batch (every warp's last chunk is partly padding).
@@ -1421,21 +1494,16 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
                             reinterpret_cast<uintptr_t>(b.cigar);
     if ((align & 15u) == 0 && p.variant == 8) {
         const bool special = p.genome || p.vr.n || b.bc;
-        if (special) { launch_pipe<384, 3, 8, 2, 0, true>(b, p, cands, cand_cap, d_counters, stream); return; }
-        switch (p.cfg) {                   // A/B configurations; 0 is the production one
-        case 1: launch_pipe<384, 2, 8, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 24 warps/SM, 1 tile in flight each
-        case 2: launch_pipe<384, 4, 4, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 12 warps/SM, 3 in flight
-        case 3: launch_pipe<256, 2, 8, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 32 warps/SM, 1 in flight
-        case 4: launch_pipe<384, 3, 4, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 16 warps/SM as 4 small blocks
-        case 5: launch_pipe<256, 3, 8, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 24 warps/SM, 2 in flight
-        case 6: launch_pipe<384, 3, 8, 1>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 8 warps/SM (latency probe)
-        case 7: launch_pipe<384, 4, 5, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // cp.async: 15 warps/SM, 3 in flight
-        case 10: launch_pipe<384, 1, 8, 2, 1>(b, p, cands, cand_cap, d_counters, stream); break;  // register-staged: 16 warps/SM
-        case 11: launch_pipe<384, 1, 8, 3, 1>(b, p, cands, cand_cap, d_counters, stream); break;  // register-staged: 24 warps/SM
-        case 12: launch_pipe<384, 1, 8, 4, 1>(b, p, cands, cand_cap, d_counters, stream); break;  // register-staged: 32 warps/SM (64 registers)
-        case 13: launch_pipe<384, 1, 4, 5, 1>(b, p, cands, cand_cap, d_counters, stream); break;  // register-staged: 20 warps/SM
-        case 14: launch_pipe<256, 1, 8, 3, 1>(b, p, cands, cand_cap, d_counters, stream); break;  // register-staged, 256-word slab window: 24 warps/SM
-        default: launch_pipe<384, 3, 8, 2>(b, p, cands, cand_cap, d_counters, stream); break;     // cp.async: 16 warps/SM, 2 tiles in flight each
+        if (special) { launch_pipe<384, 3, 8, 2, true>(b, p, cands, cand_cap, d_counters, stream); return; }
+        switch (p.cfg) {                   // A/B configurations; 0 is the production one.  Per warp: NST stages of 3.6 KB (SL 384) + 3 KB queue
+        case 1: launch_pipe<384, 2, 8, 2>(b, p, cands, cand_cap, d_counters, stream); break;      // 16 warps/SM, 1 tile in flight each
+        case 2: launch_pipe<384, 3, 4, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // 16 warps/SM, 2 in flight
+        case 3: launch_pipe<256, 2, 8, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // 24 warps/SM, 1 in flight, 256-word slab window
+        case 4: launch_pipe<384, 4, 4, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // 12 warps/SM, 3 in flight
+        case 5: launch_pipe<256, 3, 4, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // 16 warps/SM, 2 in flight, 256-word slab window
+        case 6: launch_pipe<384, 2, 8, 1>(b, p, cands, cand_cap, d_counters, stream); break;      // 8 warps/SM (latency probe)
+        case 7: launch_pipe<256, 2, 4, 5>(b, p, cands, cand_cap, d_counters, stream); break;      // 20 warps/SM, 1 in flight
+        default: launch_pipe<384, 2, 8, 2>(b, p, cands, cand_cap, d_counters, stream); break;
         }
         return;
     }
