@@ -217,6 +217,10 @@ int         rtjx_load_batch(rtjx_t* h, uint64_t* n_reads, uint64_t* n_ops, int32
  * the inflated byte stream is copied to `out` (host, cap bytes); *out_len receives its length.
  * Test hook for the inflate kernel (replaces bgzf.c:292-316 for whole-file runs). */
 int         rtjx_inflate_file(rtjx_t* h, uint64_t max_blocks, void* out, uint64_t cap, uint64_t* out_len);
+/* Copies the handle's BAM — the compressed file, byte for byte — into device memory.  Later rtjx_run / rtjx_run_regions calls on
+ * this handle read it from there (no host staging, no H2D): the "input already resident in HBM" configuration of bench.py.
+ * The reference has no counterpart (it reads through bgzf_read, bgzf.c:548-577, on every run); results are unchanged. */
+int         rtjx_stage_bam(rtjx_t* h);
 
 /* ---- `regtools junctions annotate` (the downstream consumer of the BED12) -------------------------
  * One call = junctions_annotate (src/junctions/junctions_main.cc:61-92): load the GTF (gtf_parser.cc), read the BED12

@@ -58,7 +58,12 @@ record_walk_kernel(const uint8_t* __restrict__ data, int64_t data_len, int64_t l
     if (i >= n_seg) return;
     int64_t p = seeds[i];
     if (i == 0 && use_carry) p = -(int64_t)state->carry_len;
-    const bool last = i + 1 == n_seg;
+    // Seeds found on the device (block_seeds_kernel) give every BGZF block one segment; blocks without a record start (the tail
+    // of a long record, nothing after the stream's last record) have their seed pulled up to the next block's, data_len at the
+    // end.  Such a segment is empty and reports nothing; the segment in front of a run of them that reaches data_len is the
+    // stream's last one (it owns the carry).
+    if (i > 0 && p >= data_len) { if (lane == 0) seg_cnt[i] = 0; return; }
+    const bool last = i + 1 == n_seg || seeds[i + 1] >= data_len;
     const int64_t end = last ? data_len : seeds[i + 1];
     const int64_t stop_at = limit < end ? limit : end;        // range end (contig shard) may cut the last segment
     uint32_t n = 0;
@@ -137,6 +142,94 @@ record_walk_kernel(const uint8_t* __restrict__ data, int64_t data_len, int64_t l
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Record starts found on the device: one seed per BGZF block
+// ------------------------------------------------------------------------------------------------
+// The BAI gives a record start every 16 kb of REFERENCE, which on deep loci means segments of hundreds of thousands of
+// records walked by one lane (record_walk was 12 % of the GPU time in round 1, at 7.5 % warps active).  The stream itself has
+// a much finer natural grid — the BGZF blocks, <= 64 KiB each — if the first record start inside each block can be found.
+// A warp scans its block from the front, 32 byte offsets per step, for the first offset where a well-formed record begins
+// (the checks bam_read1 makes, sam.c:399-432, plus field ranges, plus the same checks on the record that would follow); real
+// records are a few hundred bytes, so the true start is met within a handful of steps.  The guess needs no trust: record_walk
+// must arrive at every seed exactly from the seed before it (FEED_FLAG_SEED_MISS otherwise, and the run falls back to the
+// index seeds, then to the host feeder), and the first seed of a stream is known, so by induction every seed that the chain
+// reaches is a true record start.
+__device__ __forceinline__ bool plausible_one(const uint8_t* data, int64_t o, int64_t data_len, int32_t n_ref, int64_t* next) {
+    if (o + 36 > data_len) return false;
+    const uint8_t* r = data + o;
+    const int32_t bs = (int32_t)ld_u32_any(r);
+    if (bs < 32 || bs > (1 << 27)) return false;
+    const int32_t tid = (int32_t)ld_u32_any(r + 4), pos = (int32_t)ld_u32_any(r + 8);
+    if (tid < -1 || tid >= n_ref || pos < -1) return false;
+    const int32_t mtid = (int32_t)ld_u32_any(r + 24), mpos = (int32_t)ld_u32_any(r + 28);
+    if (mtid < -1 || mtid >= n_ref || mpos < -1) return false;
+    if (!record_ok(r + 4, bs)) return false;
+    const uint32_t l_qname = r[12], n_cigar = ld_u16_any(r + 16);
+    const int64_t name_end = o + 36 + (int64_t)l_qname;           // one past the NUL of the read name
+    if (name_end <= data_len && data[name_end - 1] != 0) return false;
+    if (n_cigar && name_end + 4 <= data_len && (ld_u32_any(data + name_end) & 0xfu) > 9u) return false;
+    *next = o + 4 + (int64_t)bs;
+    return true;
+}
+__device__ __forceinline__ bool plausible_record(const uint8_t* data, int64_t o, int64_t data_len, int32_t n_ref) {
+    int64_t nxt = 0, nxt2 = 0;
+    if (!plausible_one(data, o, data_len, n_ref, &nxt)) return false;
+    if (nxt + 36 > data_len) return true;                         // the next record lies (partly) in the next chunk
+    return plausible_one(data, nxt, data_len, n_ref, &nxt2);
+}
+
+constexpr int SEED_WARPS = 8;
+// blocks[i] = BgzfBlockDesc of block i (out_off / out_len relative to data).  seeds[0] is the caller's (known start, or the
+// carry); seeds[i >= 1] = offset of the first plausible record start in block i, LLONG_MAX if there is none.
+__global__ void __launch_bounds__(SEED_WARPS * 32)
+block_seeds_kernel(const uint8_t* __restrict__ data, int64_t data_len, const BgzfBlockDesc* __restrict__ blocks, uint32_t n_blocks,
+                   int32_t n_ref, int64_t* __restrict__ seeds) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t i = blockIdx.x * SEED_WARPS + (threadIdx.x >> 5);
+    if (i == 0 || i >= n_blocks) return;
+    const int64_t lo = (int64_t)blocks[i].out_off, hi = lo + (int64_t)blocks[i].out_len;
+    int64_t found = 0x7fffffffffffffffll;
+    for (int64_t o = lo; o < hi; o += 32) {
+        const bool ok = o + lane < hi && plausible_record(data, o + lane, data_len, n_ref);
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (m) { found = o + (__ffs(m) - 1); break; }
+    }
+    if (lane == 0) seeds[i] = found;
+}
+// seeds[i] = min(seeds[i .. n)) with data_len as the identity: blocks without a record start take the next block's seed.
+__global__ void __launch_bounds__(1024)
+seed_suffix_min_kernel(int64_t* __restrict__ seeds, uint32_t n, int64_t data_len) {
+    __shared__ int64_t part[1024];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (n + 1023u) / 1024u;
+    const uint32_t a = min(t * per, n), b = min(a + per, n);
+    int64_t m = data_len;
+    for (uint32_t i = b; i-- > a;) { const int64_t v = seeds[i]; if (i > 0 && v < m) m = v; }
+    part[t] = m;
+    __syncthreads();
+    // suffix minimum over the threads' partial results (Hillis-Steele, 10 steps)
+    for (uint32_t d = 1; d < 1024u; d <<= 1) {
+        const int64_t other = t + d < 1024u ? part[t + d] : data_len;
+        __syncthreads();
+        if (other < part[t]) part[t] = other;
+        __syncthreads();
+    }
+    int64_t run = t + 1 < 1024u ? part[t + 1] : data_len;        // minimum of everything right of this thread's range
+    for (uint32_t i = b; i-- > a;) {
+        if (i == 0) break;                                         // seeds[0] is the caller's
+        const int64_t v = seeds[i];
+        if (v < run) run = v;
+        seeds[i] = run;
+    }
+}
+void launch_block_seeds(const uint8_t* data, int64_t data_len, const void* blocks, uint32_t n_blocks, int32_t n_ref, int64_t* seeds,
+                        cudaStream_t stream) {
+    if (n_blocks <= 1) return;
+    block_seeds_kernel<<<(n_blocks + SEED_WARPS - 1) / SEED_WARPS, SEED_WARPS * 32, 0, stream>>>(data, data_len, static_cast<const BgzfBlockDesc*>(blocks),
+                                                                                               n_blocks, n_ref, seeds);
+    seed_suffix_min_kernel<<<1, 1024, 0, stream>>>(seeds, n_blocks, data_len);
+}
+
 // Gathers the per-segment record lists into one dense array; also fetches n_cigar for the scan.
 __global__ void __launch_bounds__(256)
 record_gather_kernel(const uint8_t* __restrict__ data, const int32_t* __restrict__ rec_off, const uint32_t* __restrict__ seg_base,
@@ -188,12 +281,17 @@ __global__ void __launch_bounds__(256)
 record_extract_kernel(const uint8_t* __restrict__ data, const int32_t* __restrict__ dense, const uint32_t* __restrict__ ncig_scan,
                       const uint32_t* __restrict__ d_n_rec, int32_t n_ref, int xs_mode, uint32_t tag0, uint32_t tag1,
                       int32_t* __restrict__ o_tid, int32_t* __restrict__ o_pos, uint32_t* __restrict__ o_meta,
-                      uint32_t* __restrict__ o_off, uint32_t* __restrict__ o_cigar, uint32_t cigar_cap,
+                      uint32_t* __restrict__ o_off, uint32_t* __restrict__ o_cigar, uint32_t rec_cap, uint32_t cigar_cap,
                       FeedState* __restrict__ state) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_rec = *d_n_rec;
     if (r > n_rec) return;
-    if (r == n_rec) { o_off[r] = ncig_scan[r]; return; }          // closing offset (scan is over n_rec + 1 entries)
+    // this group's alignments go behind the ones already accumulated
+    const uint32_t rb = state->acc_rec, ob = state->acc_ops;
+    if ((unsigned long long)rb + n_rec + 1ull > rec_cap) { if (r == 0) atomicOr(&state->flags, FEED_FLAG_CAPACITY); return; }
+    o_tid += rb; o_pos += rb; o_meta += rb; o_off += rb; o_cigar += ob;
+    cigar_cap -= ob < cigar_cap ? ob : cigar_cap;
+    if (r == n_rec) { o_off[r] = ob + ncig_scan[r]; return; }      // closing offset (scan is over n_rec + 1 entries)
     const uint8_t* rec = data + dense[r];
     const int32_t bl = (int32_t)ld_u32_any(rec);
     const uint8_t* core = rec + 4;
@@ -220,7 +318,7 @@ record_extract_kernel(const uint8_t* __restrict__ data, const int32_t* __restric
     o_tid[r] = tid;
     o_pos[r] = (int32_t)ld_u32_any(core + 4);
     o_meta[r] = flag << 16 | mapq << 8 | strand;
-    o_off[r] = o0;
+    o_off[r] = ob + o0;
 }
 
 // Moves the unfinished tail of this chunk in front of the next chunk's data and publishes counts.
@@ -240,8 +338,24 @@ __global__ void feed_finish_kernel(const uint8_t* __restrict__ data, int64_t dat
     const uint32_t len = s_len;
     const uint8_t* src = data + (data_len - len);
     for (uint32_t k = threadIdx.x; k < len; k += blockDim.x) next_data[(long long)k - (long long)len] = src[k];
-    if (threadIdx.x == 0) state->carry_len = len;
+    if (threadIdx.x == 0) {
+        state->carry_len = len;
+        // (n_rec / n_ops were published by feed_count / feed_ops; a group that raised a flag is never scanned)
+        state->acc_rec += state->n_rec; state->acc_ops += state->n_ops; state->acc_jops += state->n_junction_ops;
+    }
 }
+__global__ void feed_carry_in_kernel(const uint8_t* __restrict__ carry_end, uint8_t* __restrict__ data, const FeedState* __restrict__ state) {
+    const uint32_t len = state->carry_len;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x)
+        data[(long long)k - (long long)len] = carry_end[(long long)k - (long long)len];
+}
+void launch_feed_carry_in(const uint8_t* carry_end, uint8_t* data, const FeedState* state, cudaStream_t stream) {
+    feed_carry_in_kernel<<<8, 256, 0, stream>>>(carry_end, data, state);
+}
+__global__ void feed_acc_reset_kernel(FeedState* state) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { state->acc_rec = state->acc_ops = state->acc_jops = 0; }
+}
+void launch_feed_acc_reset(FeedState* state, cudaStream_t stream) { feed_acc_reset_kernel<<<1, 32, 0, stream>>>(state); }
 
 __global__ void feed_count_kernel(const uint32_t* __restrict__ seg_scan, uint32_t n_seg, FeedState* __restrict__ state) {
     if (threadIdx.x == 0 && blockIdx.x == 0) state->n_rec = seg_scan[n_seg];
@@ -290,10 +404,10 @@ void launch_record_gather(const uint8_t* data, const int32_t* rec_off, const uin
 
 void launch_record_extract(const uint8_t* data, const int32_t* dense, const uint32_t* ncig_scan, uint32_t cap_total,
                            FeedState* state, int32_t n_ref, int xs_mode, uint32_t tag0, uint32_t tag1, int32_t* o_tid,
-                           int32_t* o_pos, uint32_t* o_meta, uint32_t* o_off, uint32_t* o_cigar, uint32_t cigar_cap,
+                           int32_t* o_pos, uint32_t* o_meta, uint32_t* o_off, uint32_t* o_cigar, uint32_t rec_cap, uint32_t cigar_cap,
                            cudaStream_t stream) {
     record_extract_kernel<<<(cap_total + 1 + 255) / 256, 256, 0, stream>>>(data, dense, ncig_scan, &state->n_rec, n_ref, xs_mode, tag0, tag1,
-                                                                          o_tid, o_pos, o_meta, o_off, o_cigar, cigar_cap, state);
+                                                                          o_tid, o_pos, o_meta, o_off, o_cigar, rec_cap, cigar_cap, state);
 }
 
 void launch_feed_finish(const uint8_t* data, int64_t data_len, uint8_t* next_data, uint32_t headroom, const uint32_t* seg_scan,

@@ -547,19 +547,21 @@ int Engine::run_impl() {
     if (bc_mode_ && prm_.shard_world > 1) return fail(RTJX_E_UNSUPPORTED, "-b barcodes are not exchanged between contig shards");
     if (!bc_mode_ && streamable && (prm_.inflate_mode == 2 || (prm_.inflate_mode == 0 && bam->size() >= (1u << 20)))) {
         const rtjx_stats saved = stats_;
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            // first with every record start the index knows (linear index + bin chunk boundaries); if that run is declined
-            // — e.g. an index whose chunk ends are not record boundaries — once more with the linear index alone
-            feed_linear_seeds_only_ = attempt == 1;
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            // Record starts: first found on the device, one per BGZF block, verified by the chain walk; if that run is declined
+            // once more with every record start the index knows (linear index + bin chunk boundaries); if that is declined too —
+            // e.g. an index whose chunk ends are not record boundaries — with the linear index alone; then the host feeder.
+            feed_seed_mode_ = attempt;
             feed_decline_flags_ = 0;
             rc = run_device(*bam, idx, spec);
             if (rc == RTJX_OK) return RTJX_OK;
             if (rc < 0) return rc;
+            if (getenv("RTJX_TRACE")) fprintf(stderr, "[rtjx] device feed declined (seed mode %d, flags %u)\n", attempt, feed_decline_flags_);
             if ((rc = clear())) return rc;                    // declined: start over
             stats_ = saved;
             contigs_ = bam->header().names; rank_dirty_ = true;
-            // (a walk started at a bogus seed can also end in a "malformed record" report, so any decline of the first
-            // attempt is retried; a genuinely malformed file costs one more device pass before the host path below)
+            // (a walk started at a bogus seed can also end in a "malformed record" report, so any decline is retried; a
+            // genuinely malformed file costs two more device passes before the host path below)
         }
     }
     uint32_t reads = prm_.batch_reads ? prm_.batch_reads : (spec.kind == IterSpec::Region ? (1u << 15) : (1u << 20));

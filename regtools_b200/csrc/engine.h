@@ -41,6 +41,7 @@ public:
     int import(const rtjx_junction* j, size_t n);
     int clear();
     int inflate_file(uint64_t max_blocks, void* out, uint64_t cap, uint64_t* out_len);
+    int stage_file();                            // rtjx_stage_bam: compressed BAM -> HBM; later runs read it from there (device_run.cc)
     int load_batch(uint64_t* n_reads, uint64_t* n_ops, int32_t* tid, int32_t* pos, uint32_t* meta,
                    uint32_t* cig_off, uint32_t* cigar);
 
@@ -153,7 +154,7 @@ private:
     struct DeviceFeedDeleter { void operator()(DeviceFeed* p) const; };
     std::unique_ptr<DeviceFeed, DeviceFeedDeleter> dfeed_;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> feed_prof_;
-    bool feed_linear_seeds_only_ = false;       // retry of a declined device run without the bin-chunk seeds
+    int feed_seed_mode_ = 0;                    // record starts of a device run: 0 found on the device, 1 index (linear + bin chunks), 2 linear index only
     uint32_t feed_decline_flags_ = 0;           // FEED_FLAG_* of the group that made the device path decline
 
     // profiling

@@ -417,7 +417,8 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
 //     against 74 ms for the kernel above; profiles/r2_inflate_lanes_v1.txt.)
 //     One loop, one symbol (or one DEFLATE block header) per lane per iteration, so lanes reconverge every iteration; zlib
 //     cuts DEFLATE blocks after a fixed number of symbols, so the lanes of a warp reach their block headers (the divergent
-//     part) in the same iteration.  Literals go straight to their final position, combined into aligned 32-bit stores.
+//     part) in the same iteration.  Literals go straight to their final position (byte stores: combining them into words
+//     was measured and cost more issue slots than it saved transactions).
 //     Matches are NOT copied here — a copy is a dependent global round trip that would stall all 32 lanes — they are
 //     appended to the block's match list (position, length, distance).
 //  2. bgzf_match_resolve_kernel — LZ77 copies.  One warp per BGZF block walks the match list 32 matches at a time: matches
@@ -525,18 +526,12 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
     const uint32_t cap = blk.out_len;
     uint2* my_matches = mlist + (size_t)b * LN_MATCH_CAP;
     uint32_t opos = 0, err = 0, n_match = 0;
-    uint32_t wbuf = 0, pend = 0;                  // literals not yet stored: `pend` bytes ending at dst + opos, the first one 4-byte aligned
     LaneBits br;
     br.init(comp + blk.in_off, blk.in_len);
     uint32_t ul[16], ud[16];                      // upper bounds per code length of the current DEFLATE block's two codes
 #pragma unroll
     for (int i = 0; i < 16; ++i) { ul[i] = 0; ud[i] = 0; }
     bool in_block = false, last = false;
-
-    auto flush_pending = [&]() {                  // pending literals as byte stores (at a block boundary / before stored bytes)
-        for (uint32_t k = 0; k < pend; ++k) dst[opos - pend + k] = (uint8_t)(wbuf >> (8 * k));
-        pend = 0; wbuf = 0;
-    };
 
     for (;;) {
         if (!in_block) {
@@ -549,7 +544,6 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
                 br.drop(br.nb & 7);
                 const uint32_t l = br.get(16), nl = br.get(16);
                 if ((l ^ nl) != 0xffffu || opos + l > cap) { err = 2; continue; }
-                flush_pending();
                 const uint8_t* src = br.byte_ptr();
                 if (src + l > reinterpret_cast<const uint8_t*>(br.lim)) { err = 18; continue; }
                 for (uint32_t i = 0; i < l; ++i) dst[opos + i] = __ldg(src + i);
@@ -618,12 +612,7 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
         br.drop((int)cl);
         if (sym < 256u) {
             if (opos >= cap) { err = 15; in_block = false; continue; }
-            if (pend == 0u && ((reinterpret_cast<uintptr_t>(dst) + opos) & 3u) != 0u) {
-                dst[opos++] = (uint8_t)sym;                            // not on a word boundary yet (stream start / after a match)
-            } else {
-                wbuf |= sym << (8u * pend); ++pend; ++opos;
-                if (pend == 4u) { *reinterpret_cast<uint32_t*>(dst + opos - 4u) = wbuf; pend = 0; wbuf = 0; }
-            }
+            dst[opos++] = (uint8_t)sym;
             continue;
         }
         if (sym == 256u) { in_block = false; if (br.overrun()) err = 18; continue; }
@@ -648,11 +637,9 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
         if (dist > opos) { err = 16; in_block = false; continue; }
         if (opos + len > cap) { err = 15; in_block = false; continue; }
         if (n_match >= LN_MATCH_CAP) { err = 19; in_block = false; continue; }
-        flush_pending();
         my_matches[n_match++] = make_uint2(opos | len << 16, dist);     // the copy itself happens in bgzf_match_resolve_kernel
         opos += len;
     }
-    if (!err) flush_pending();
     if (!err && opos != cap) err = 17;
     status[b] = err;
     mcount[b] = err ? 0u : n_match;

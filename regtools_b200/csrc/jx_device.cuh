@@ -164,19 +164,30 @@ struct FeedState {
     uint32_t flags;
     uint32_t n_rec, n_ops, n_junction_ops;
     uint32_t reached_limit;       // the range end (contig shard) lies in this chunk
+    // alignments appended to the SoA accumulator since the last cigar_scan (survive feed_reset; cleared by feed_acc_reset)
+    uint32_t acc_rec, acc_ops, acc_jops, pad;
 };
 enum { FEED_FLAG_SEED_MISS = 1, FEED_FLAG_CAPACITY = 2, FEED_FLAG_CARRY_TOO_BIG = 4, FEED_FLAG_INFLATE = 8 };
 size_t feed_scan_workspace_bytes(uint32_t n);
 void launch_feed_reset(FeedState* state, int keep_carry, cudaStream_t stream);
+// seeds[1 .. n_blocks) = first record start inside BGZF block i found by plausibility checks (verified by record_walk's chain);
+// seeds[0] is left to the caller.  blocks: BgzfBlockDesc[n_blocks] in device memory.
+void launch_block_seeds(const uint8_t* data, int64_t data_len, const void* blocks, uint32_t n_blocks, int32_t n_ref, int64_t* seeds,
+                        cudaStream_t stream);
 void launch_record_walk(const uint8_t* data, int64_t data_len, int64_t limit, const int64_t* seeds, const uint32_t* seg_base,
                         uint32_t n_seg, int use_carry, FeedState* state, int32_t* rec_off, uint32_t* seg_cnt,
                         cudaStream_t stream);
 void launch_record_gather(const uint8_t* data, const int32_t* rec_off, const uint32_t* seg_base, uint32_t* seg_cnt,
                           uint32_t* seg_scan, uint32_t n_seg, uint32_t cap_total, FeedState* state, int32_t* dense,
                           uint32_t* ncig, uint32_t* ncig_scan, void* ws, size_t ws_bytes, cudaStream_t stream);
+// The group's alignments are appended to the accumulator arrays at state->acc_rec / state->acc_ops (rec_cap / cigar_cap: their sizes).
 void launch_record_extract(const uint8_t* data, const int32_t* dense, const uint32_t* ncig_scan, uint32_t cap_total,
                            FeedState* state, int32_t n_ref, int xs_mode, uint32_t tag0, uint32_t tag1, int32_t* o_tid,
-                           int32_t* o_pos, uint32_t* o_meta, uint32_t* o_off, uint32_t* o_cigar, uint32_t cigar_cap, cudaStream_t stream);
+                           int32_t* o_pos, uint32_t* o_meta, uint32_t* o_off, uint32_t* o_cigar, uint32_t rec_cap, uint32_t cigar_cap,
+                           cudaStream_t stream);
+// carry: the unfinished record feed_finish left right-aligned in front of `carry_end` is copied in front of `data`
+void launch_feed_carry_in(const uint8_t* carry_end, uint8_t* data, const FeedState* state, cudaStream_t stream);
+void launch_feed_acc_reset(FeedState* state, cudaStream_t stream);
 void launch_feed_finish(const uint8_t* data, int64_t data_len, uint8_t* next_data, uint32_t headroom, const uint32_t* seg_scan,
                         uint32_t n_seg, const uint32_t* ncig_scan, FeedState* state, cudaStream_t stream);
 

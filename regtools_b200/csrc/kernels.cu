@@ -1000,21 +1000,14 @@ struct alignas(16) PipeStage {
     uint32_t tid[PW];
     uint32_t slab[SL];
 };
-constexpr int PQ_OPS = 6;                         // CIGAR ops kept per queued alignment (longer CIGARs take the out-of-line walk)
-constexpr int PQ_CAP = 64;                        // queue slots per warp (< 32 left over + <= 32 new per filter round)
-// Plain mode: alignments that carry an N op wait here, with everything their walk needs, until 32 of them fill a round.
-struct alignas(16) PipeQueue {
-    uint32_t pos[PQ_CAP], meta[PQ_CAP], ordlo[PQ_CAP], o0[PQ_CAP], n[PQ_CAP];
-    int32_t  tid[PQ_CAP];
-    uint32_t op[PQ_OPS][PQ_CAP];
-};
-template <int SL, int NST, bool QUEUE>
+constexpr int PN_CAP = 128;                       // N ops listed per detection round (one per lane per pass, four passes at most)
+template <int SL, int NST, bool NLIST>
 struct alignas(16) PipeWarpSmem {
     PipeStage<SL> st[NST];
     uint32_t cur, end;                            // generic path: cursor into the warp's reserved chunk
     uint32_t pad[2];
-    uint8_t  work[PW];
-    PipeQueue q[QUEUE ? 1 : 0];
+    uint8_t  work[PW];                            // generic path: alignments with more than one CIGAR op
+    uint8_t  nlist[NLIST ? PN_CAP : 4];           // plain path: positions (0..127) of the N ops found in the current 128 slab words
 };
 
 __device__ __forceinline__ void store_cand(Cand* __restrict__ out, uint32_t cap, uint32_t* counters, uint32_t idx,
@@ -1168,175 +1161,106 @@ __device__ __forceinline__ void pipe_process_tile(WS& ws, PipeStage<SL>& st, con
     }
 }
 
-// all N ops of an alignment whose CIGAR is too long for the queue (plain mode; rare): one slot each
-__device__ __noinline__ void pipe_walk_all(const uint32_t* __restrict__ ops, uint32_t n, uint32_t pos, int32_t tid, uint32_t strand,
-                                           uint64_t read_ord, Cand* __restrict__ out, uint32_t cap, uint32_t* counters) {
-    const uint32_t ANC = (1u << 0) | (1u << 7);
-    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
-    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
-    uint32_t cur = pos, run = 0;
-    bool pending = false;
-    uint32_t p_start = 0, p_end = 0, p_left = 0, p_k = 0;
-    auto emit = [&]() {
-        const uint64_t ord = read_ord << 16 | p_k;
-        const uint32_t g = atomicAdd(&counters[CTR_NCAND], 1u);
-        store_cand(out, cap, counters, g, make_uint4(p_start, p_end, p_start - p_left, p_end + run),
-                   make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
-    };
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t x = __ldg(ops + i), op = x & 0xfu, len = x >> 4, bit = 1u << op;
-        if (bit & BRK) {
-            if (pending) emit();
-            pending = op == 3u;
-            if (pending) { p_start = cur; p_end = cur + len; p_left = run; p_k = i > 0xffffu ? 0xffffu : i; }
-            run = 0;
-        } else if (bit & ANC) {
-            run += len;
-        }
-        if (bit & REFC) cur += len;
-    }
-    if (pending) emit();
-}
-
-// Plain mode, one round: up to 32 queued alignments (queue slots head .. head + cnt - 1), one per lane, are walked
-// (parse_alignment_into_junctions, junctions_extractor.cc:377-497, closed form of SURVEY App. A.2: branch-free, the first two
-// N ops stay in registers) and their candidates stored into the warp's chunk.
-__device__ __forceinline__ void pipe_walk_round(const PipeQueue& q, uint32_t head, uint32_t cnt, uint32_t lane, const BatchView& b,
-                                                const ScanParams& prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters,
-                                                uint32_t& c_cur, uint32_t& c_end) {
-    const uint32_t ANC = (1u << 0) | (1u << 7);
-    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
-    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
-    const bool act = lane < cnt;
-    const uint32_t s = (head + lane) & (PQ_CAP - 1);
-    const uint32_t n = act ? q.n[s] : 0u;
-    const uint32_t nmax = __reduce_max_sync(0xffffffffu, n);
-    uint32_t cur = q.pos[s], run = 0, nc = 0;
-    bool pending = false;
-    WalkCand c0{0, 0, 0, 0, 0}, c1{0, 0, 0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < PQ_OPS; ++i) {
-        if ((uint32_t)i >= nmax) break;                        // warp-uniform
-        const uint32_t x = (uint32_t)i < n ? q.op[i][s] : 0xfu;  // op code 15: transparent filler
-        const uint32_t op = x & 0xfu, len = x >> 4, bit = 1u << op;
-        const bool brk = (bit & BRK) != 0, is_n = op == 3u;
-        const bool close = pending && brk;                  // the open junction ends here: right anchor = run
-        c0.right = (close && nc == 1u) ? run : c0.right;
-        c1.right = (close && nc == 2u) ? run : c1.right;
-        const bool open0 = is_n && nc == 0u, open1 = is_n && nc == 1u;
-        c0.start = open0 ? cur : c0.start; c0.end = open0 ? cur + len : c0.end; c0.left = open0 ? run : c0.left; c0.k = open0 ? (uint32_t)i : c0.k;
-        c1.start = open1 ? cur : c1.start; c1.end = open1 ? cur + len : c1.end; c1.left = open1 ? run : c1.left; c1.k = open1 ? (uint32_t)i : c1.k;
-        nc += is_n ? 1u : 0u;
-        pending = brk ? is_n : pending;
-        run = brk ? 0u : run + ((bit & ANC) ? len : 0u);
-        cur += (bit & REFC) ? len : 0u;
-    }
-    c0.right = (pending && nc == 1u) ? run : c0.right;
-    c1.right = (pending && nc == 2u) ? run : c1.right;
-    const int32_t tid = q.tid[s];
-    const uint32_t strand = read_strand(q.meta[s], prm.strandness);
-    const uint64_t read_ord = b.first_ordinal + q.ordlo[s];
-    if (nc > 2u) pipe_walk_rest(b.cigar + q.o0[s], n, q.pos[s], tid, strand, read_ord, out, cap, counters);
-    // ---- positions in the chunk: first candidates of all lanes, then second candidates
-    const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t b1 = __ballot_sync(0xffffffffu, nc >= 1u), b2 = __ballot_sync(0xffffffffu, nc >= 2u);
-    const uint32_t t1 = __popc(b1), tot = t1 + __popc(b2);
-    if (tot) {
-        const uint32_t rem = c_end - c_cur;
-        uint32_t nbase = 0;
-        if (tot > rem) {                                      // the chunk runs out inside this round: the rest goes to a new one
-            if (lane == 0) nbase = atomicAdd(&counters[CTR_NCAND], (uint32_t)PCH);
-            nbase = __shfl_sync(0xffffffffu, nbase, 0);
-        }
-        if (nc >= 1u) {
-            const uint64_t ord = read_ord << 16 | c0.k;
-            const uint32_t j = __popc(b1 & lt);
-            store_cand(out, cap, counters, j < rem ? c_cur + j : nbase + (j - rem),
-                       make_uint4(c0.start, c0.end, c0.start - c0.left, c0.end + c0.right),
-                       make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
-        }
-        if (nc >= 2u) {
-            const uint64_t ord = read_ord << 16 | c1.k;
-            const uint32_t j = t1 + __popc(b2 & lt);
-            store_cand(out, cap, counters, j < rem ? c_cur + j : nbase + (j - rem),
-                       make_uint4(c1.start, c1.end, c1.start - c1.left, c1.end + c1.right),
-                       make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
-        }
-        if (tot > rem) { c_cur = nbase + (tot - rem); c_end = nbase + (uint32_t)PCH; } else c_cur += tot;
-    }
-}
-
-// Plain mode, per tile: the alignments with more than one CIGAR op (junctions_extractor.cc:379) are listed (ballots, no scan),
-// then — all lanes busy, one listed alignment each — those that carry an N op are moved to the warp's queue together with their
-// first PQ_OPS ops; whenever 32 are queued a round is walked.  The ~55 % of multi-op alignments without an N op (soft clips,
-// indels) cost one filter slot, never a walk.
+// Plain mode (no FASTA, no variant regions, no barcodes): OP-PARALLEL.  parse_alignment_into_junctions
+// (junctions_extractor.cc:377-497) emits exactly one candidate per N op, and in closed form that candidate
+// depends only on the ops of its own alignment around it.  So the tile's CIGAR slab is searched for N ops directly — four
+// words per lane, ballot compaction — and each N op found gets a lane that
+//   * finds its alignment r by binary search in the tile's cig_off column (shared memory),
+//   * sums the reference-consuming lengths of the ops before it (start) and the M/= runs on either side (anchors),
+//   * stores the candidate into the warp's chunk.
+// The ~55 % of multi-op alignments that carry no N op (soft clips, indels) are never looked at beyond `(word & 15) == 3`, and
+// nothing is walked op by op through a state machine.  (Round-2 measurements that led here: the per-alignment walk kernels,
+// block-tiled or warp-pipelined, sit at 32-42 M warp instructions per 10 M alignments and ~55 % issue utilisation —
+// instruction-bound, not memory-bound; profiles/r2_scan_*.)
 template <int SL, class WS>
-__device__ __forceinline__ void pipe_filter_tile(WS& ws, PipeStage<SL>& st, const BatchView& b, const ScanParams& prm, uint32_t base,
-                                                 uint32_t lane, uint32_t vec_end, Cand* __restrict__ out, uint32_t cap,
-                                                 uint32_t* __restrict__ counters, uint32_t& c_cur, uint32_t& c_end,
-                                                 uint32_t& q_head, uint32_t& q_cnt) {
-    PipeQueue& q = ws.q[0];
+__device__ __forceinline__ void pipe_nops_tile(WS& ws, PipeStage<SL>& st, const BatchView& b, const ScanParams& prm, uint32_t base,
+                                               uint32_t lane, uint32_t vec_end, Cand* __restrict__ out, uint32_t cap,
+                                               uint32_t* __restrict__ counters, uint32_t& c_cur, uint32_t& c_end) {
+    const uint32_t ANC = (1u << 0) | (1u << 7);
+    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
+    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
     const uint32_t n_tile = min((uint32_t)PW, b.n_reads - base);
-    const uint32_t lo = st.off[0], hi = st.off[n_tile], a0 = lo & ~3u;
-    uint32_t n_st = 0;                                         // words of the slab staged in shared memory (from a0)
-    if (hi > lo) { const uint32_t end = min(min((hi + 3u) & ~3u, a0 + (uint32_t)SL), vec_end); n_st = end > a0 ? end - a0 : 0u; }
+    const uint32_t lo = st.off[0], hi = st.off[n_tile];
+    if (hi <= lo) return;
+    const uint32_t a0 = lo & ~3u;
+    const uint32_t end_st = min(min((hi + 3u) & ~3u, a0 + (uint32_t)SL), vec_end);
+    const uint32_t n_st = end_st > a0 ? end_st - a0 : 0u;     // words of the slab staged in shared memory (from a0)
     const uint32_t lt = (1u << lane) - 1u;
-    uint32_t n_work;
-    {
-        const uint4 o = *reinterpret_cast<const uint4*>(&st.off[4 * lane]);
-        const uint32_t o4 = st.off[4 * lane + 4];
-        const uint32_t r0 = 4 * lane;
-        const bool f0 = r0 + 0 < n_tile && o.y - o.x > 1u, f1 = r0 + 1 < n_tile && o.z - o.y > 1u;
-        const bool f2 = r0 + 2 < n_tile && o.w - o.z > 1u, f3 = r0 + 3 < n_tile && o4 - o.w > 1u;
-        const uint32_t m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
-        const uint32_t m2 = __ballot_sync(0xffffffffu, f2), m3 = __ballot_sync(0xffffffffu, f3);
-        const uint32_t s1 = __popc(m0), s2 = s1 + __popc(m1), s3 = s2 + __popc(m2);
-        n_work = s3 + __popc(m3);
-        if (f0) ws.work[__popc(m0 & lt)] = (uint8_t)(r0 + 0);
-        if (f1) ws.work[s1 + __popc(m1 & lt)] = (uint8_t)(r0 + 1);
-        if (f2) ws.work[s2 + __popc(m2 & lt)] = (uint8_t)(r0 + 2);
-        if (f3) ws.work[s3 + __popc(m3 & lt)] = (uint8_t)(r0 + 3);
-    }
-    __syncwarp();
-    for (uint32_t w0 = 0; w0 < n_work; w0 += 32) {
-        const uint32_t w = w0 + lane;
-        bool take = false;
-        uint32_t r = 0, o0 = 0, n = 0, x[PQ_OPS];
-        int32_t tid = -1;
-        if (w < n_work) {
-            r = ws.work[w];
-            tid = (int32_t)st.tid[r];
-            o0 = st.off[r]; n = st.off[r + 1] - o0;
-            if (tid >= 0) {
-                if (n <= (uint32_t)PQ_OPS) {
-                    const bool in_smem = (o0 - a0) + n <= n_st;
-                    bool has_n = false;
-#pragma unroll
-                    for (int i = 0; i < PQ_OPS; ++i) {
-                        x[i] = (uint32_t)i < n ? (in_smem ? st.slab[o0 - a0 + i] : __ldg(b.cigar + o0 + i)) : 0xfu;
-                        has_n = has_n || (x[i] & 0xfu) == 3u;
+    auto op_at = [&](uint32_t j) -> uint32_t {                  // CIGAR word j of the batch
+        return j - a0 < n_st ? st.slab[j - a0] : __ldg(b.cigar + j);
+    };
+    for (uint32_t v0 = a0; v0 < hi; v0 += 128) {              // 128 slab words per round, 4 per lane
+        const uint32_t j0 = v0 + 4 * lane;
+        uint4 w;
+        if (j0 + 4 - a0 <= n_st) w = *reinterpret_cast<const uint4*>(&st.slab[j0 - a0]);
+        else {                                                // outside the staged window (dense tile / ragged end of the array)
+            w.x = j0 + 0 < hi ? __ldg(b.cigar + j0 + 0) : 0u; w.y = j0 + 1 < hi ? __ldg(b.cigar + j0 + 1) : 0u;
+            w.z = j0 + 2 < hi ? __ldg(b.cigar + j0 + 2) : 0u; w.w = j0 + 3 < hi ? __ldg(b.cigar + j0 + 3) : 0u;
+        }
+        uint32_t fm = ((w.x & 0xfu) == 3u ? 1u : 0u) | ((w.y & 0xfu) == 3u ? 2u : 0u) | ((w.z & 0xfu) == 3u ? 4u : 0u) | ((w.w & 0xfu) == 3u ? 8u : 0u);
+        // words in front of the tile's first op (alignment of a0) and behind its last belong to other tiles
+        if (j0 < lo) fm &= 0xfu << (lo - j0);
+        if (j0 + 4 > hi) fm &= j0 < hi ? 0xfu >> (j0 + 4 - hi) : 0u;
+        uint32_t n_n = 0;
+        for (uint32_t any = __ballot_sync(0xffffffffu, fm != 0u); any; any = __ballot_sync(0xffffffffu, fm != 0u)) {
+            if (fm) { const uint32_t c = __ffs(fm) - 1; ws.nlist[n_n + __popc(any & lt)] = (uint8_t)(4 * lane + c); fm &= fm - 1; }
+            n_n += __popc(any);
+        }
+        if (n_n == 0) continue;
+        __syncwarp();
+        // ---- one lane per N op (at most 128 per round: up to four passes)
+        for (uint32_t w0 = 0; w0 < n_n; w0 += 32) {
+            bool have = w0 + lane < n_n;
+            uint32_t start = 0, end = 0, left = 0, right = 0, k = 0, r = 0;
+            int32_t tid = -1;
+            if (have) {
+                const uint32_t J = v0 + ws.nlist[w0 + lane];
+                // alignment of op J: the last r with cig_off[r] <= J (cig_off[0] = lo <= J < hi = cig_off[n_tile])
+                uint32_t rl = 0, rh = n_tile;
+                while (rh - rl > 1u) { const uint32_t mid = (rl + rh) >> 1; if (st.off[mid] <= J) rl = mid; else rh = mid; }
+                r = rl;
+                const uint32_t o0 = st.off[r], n = st.off[r + 1] - o0;
+                tid = (int32_t)st.tid[r];
+                have = n > 1u && tid >= 0;                    // junctions_extractor.cc:379; tid -1: no contig to name
+                if (have) {
+                    k = J - o0;
+                    uint32_t refsum = 0;
+                    bool open = true;
+                    for (uint32_t i = k; i-- > 0u;) {         // ops before the N op: reference offset, left anchor
+                        const uint32_t x = op_at(o0 + i), bit = 1u << (x & 0xfu), len = x >> 4;
+                        refsum += (bit & REFC) ? len : 0u;
+                        open = open && !(bit & BRK);
+                        left += (open && (bit & ANC)) ? len : 0u;
                     }
-                    take = has_n;
-                } else {                                      // long CIGAR: walked right away, out of line
-                    pipe_walk_all(b.cigar + o0, n, st.pos[r], tid, read_strand(st.meta[r], prm.strandness), b.first_ordinal + base + r,
-                                  out, cap, counters);
+                    for (uint32_t i = k + 1; i < n; ++i) {     // ops behind it, up to the first one that ends the exon
+                        const uint32_t x = op_at(o0 + i), bit = 1u << (x & 0xfu);
+                        if (bit & BRK) break;
+                        right += (bit & ANC) ? x >> 4 : 0u;
+                    }
+                    start = st.pos[r] + refsum;
+                    end = start + (op_at(J) >> 4);
+                    k = k > 0xffffu ? 0xffffu : k;
                 }
             }
+            const uint32_t hm = __ballot_sync(0xffffffffu, have);
+            const uint32_t tot = __popc(hm);
+            if (tot) {
+                const uint32_t rem = c_end - c_cur;
+                uint32_t nbase = 0;
+                if (tot > rem) {                              // the chunk runs out inside this round: the rest goes to a new one
+                    if (lane == 0) nbase = atomicAdd(&counters[CTR_NCAND], (uint32_t)PCH);
+                    nbase = __shfl_sync(0xffffffffu, nbase, 0);
+                }
+                if (have) {
+                    const uint64_t ord = (b.first_ordinal + base + r) << 16 | k;
+                    const uint32_t j = __popc(hm & lt);
+                    store_cand(out, cap, counters, j < rem ? c_cur + j : nbase + (j - rem), make_uint4(start, end, start - left, end + right),
+                               make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, read_strand(st.meta[r], prm.strandness)));
+                }
+                if (tot > rem) { c_cur = nbase + (tot - rem); c_end = nbase + (uint32_t)PCH; } else c_cur += tot;
+            }
         }
-        const uint32_t tm = __ballot_sync(0xffffffffu, take);
-        if (take) {
-            const uint32_t s = (q_head + q_cnt + __popc(tm & lt)) & (PQ_CAP - 1);
-            q.pos[s] = st.pos[r]; q.meta[s] = st.meta[r]; q.tid[s] = tid; q.ordlo[s] = base + r; q.o0[s] = o0; q.n[s] = n;
-#pragma unroll
-            for (int i = 0; i < PQ_OPS; ++i) q.op[i][s] = x[i];
-        }
-        q_cnt += __popc(tm);
-        __syncwarp();
-        if (q_cnt >= 32u) {
-            pipe_walk_round(q, q_head, 32u, lane, b, prm, out, cap, counters, c_cur, c_end);
-            q_head = (q_head + 32u) & (PQ_CAP - 1); q_cnt -= 32u;
-            __syncwarp();
-        }
+        __syncwarp();                                         // nlist is rewritten by the next round
     }
 }
 
@@ -1370,7 +1294,6 @@ cigar_scan_pipe_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint
     };
     uint32_t bq_cur = load_bq(0), bq_next = load_bq(1);
     uint32_t c_cur = 0, c_end = 0;                            // plain mode: the warp's chunk (uniform registers)
-    uint32_t q_head = 0, q_cnt = 0;                           // plain mode: the warp's queue
 
     auto issue = [&](uint32_t kk) {                           // called for kk = 0, 1, 2, ... in order, once each
         if (kk != 0u && (kk & 15u) == 0u) { bq_cur = bq_next; bq_next = load_bq((kk >> 4) + 1u); }
@@ -1412,12 +1335,11 @@ cigar_scan_pipe_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint
         __syncwarp();                                         // ... and so have every other lane's
         const uint32_t base = (gw + k * TW) * PW;
         if (GENERIC) pipe_process_tile<SL, WS, MOTIF, VREG, BC>(ws, ws.st[k % NST], b, prm, base, lane, vec_end, out, cap, counters);
-        else pipe_filter_tile<SL, WS>(ws, ws.st[k % NST], b, prm, base, lane, vec_end, out, cap, counters, c_cur, c_end, q_head, q_cnt);
+        else pipe_nops_tile<SL, WS>(ws, ws.st[k % NST], b, prm, base, lane, vec_end, out, cap, counters, c_cur, c_end);
         __syncwarp();                                         // the stage and the work list are rewritten from the next iteration on
     }
     if (!GENERIC) {
-        // ---- what is left in the queue, then the unused tail of the warp's last chunk: entries junction_merge skips
-        if (q_cnt) pipe_walk_round(ws.q[0], q_head, q_cnt, lane, b, prm, out, cap, counters, c_cur, c_end);
+        // ---- the unused tail of the warp's last chunk: entries junction_merge skips
         for (uint32_t i = c_cur + lane; i < c_end; i += 32) store_cand(out, cap, counters, i, make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0xffffffffu, 0));
     } else {
         __syncwarp();
@@ -1495,15 +1417,15 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
     if ((align & 15u) == 0 && p.variant == 8) {
         const bool special = p.genome || p.vr.n || b.bc;
         if (special) { launch_pipe<384, 3, 8, 2, true>(b, p, cands, cand_cap, d_counters, stream); return; }
-        switch (p.cfg) {                   // A/B configurations; 0 is the production one.  Per warp: NST stages of 3.6 KB (SL 384) + 3 KB queue
-        case 1: launch_pipe<384, 2, 8, 2>(b, p, cands, cand_cap, d_counters, stream); break;      // 16 warps/SM, 1 tile in flight each
+        switch (p.cfg) {                   // A/B configurations; 0 is the production one.  Per warp: NST stages of 3.6 KB (SL 384) / 3.1 KB (SL 256)
+        case 1: launch_pipe<384, 2, 8, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // 24 warps/SM, 1 tile in flight each
         case 2: launch_pipe<384, 3, 4, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // 16 warps/SM, 2 in flight
-        case 3: launch_pipe<256, 2, 8, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // 24 warps/SM, 1 in flight, 256-word slab window
+        case 3: launch_pipe<256, 2, 8, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // 32 warps/SM, 1 in flight (64 registers)
         case 4: launch_pipe<384, 4, 4, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // 12 warps/SM, 3 in flight
-        case 5: launch_pipe<256, 3, 4, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // 16 warps/SM, 2 in flight, 256-word slab window
+        case 5: launch_pipe<256, 3, 4, 5>(b, p, cands, cand_cap, d_counters, stream); break;      // 20 warps/SM, 2 in flight
         case 6: launch_pipe<384, 2, 8, 1>(b, p, cands, cand_cap, d_counters, stream); break;      // 8 warps/SM (latency probe)
-        case 7: launch_pipe<256, 2, 4, 5>(b, p, cands, cand_cap, d_counters, stream); break;      // 20 warps/SM, 1 in flight
-        default: launch_pipe<384, 2, 8, 2>(b, p, cands, cand_cap, d_counters, stream); break;
+        case 7: launch_pipe<256, 2, 4, 7>(b, p, cands, cand_cap, d_counters, stream); break;      // 28 warps/SM, 1 in flight
+        default: launch_pipe<384, 2, 8, 3>(b, p, cands, cand_cap, d_counters, stream); break;
         }
         return;
     }

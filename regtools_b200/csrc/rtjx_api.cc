@@ -86,6 +86,10 @@ int rtjx_inflate_file(rtjx_t* h, uint64_t max_blocks, void* out, uint64_t cap, u
     GUARD(h, h->e->inflate_file(max_blocks, out, cap, out_len))
 }
 
+int rtjx_stage_bam(rtjx_t* h) {
+    GUARD(h, h->e->stage_file())
+}
+
 const char* rtjx_contig(rtjx_t* h, int32_t tid) { return h ? h->e->contig(tid) : ""; }
 int32_t rtjx_n_contigs(rtjx_t* h) { return h ? h->e->n_contigs() : 0; }
 int32_t rtjx_intern_contig(rtjx_t* h, const char* name) { return h ? h->e->intern_contig(name) : -1; }

@@ -407,6 +407,10 @@ class JunctionsExtractor:
                                           meta.ctypes.data, off.ctypes.data, cig.ctypes.data))
         return tid, pos, meta, off, cig[:no.value]
 
+    def stage_bam(self) -> None:
+        """Copies the compressed BAM into device memory; later runs of this extractor read it from there (rtjx_stage_bam)."""
+        self._check(L.lib.rtjx_stage_bam(self._handle()))
+
     def inflate_file(self, max_blocks: int = 0) -> bytes:
         """Device BGZF inflate of the BAM (test hook): returns the inflated byte stream."""
         h = self._handle()
