@@ -1,27 +1,31 @@
 #!/usr/bin/env python
 """bench.py — BAM reads/sec through `junctions extract` (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c3|c2] [--reads R]
 
-N = 1 workload (BASELINE.json configs[1]): synthetic 10M-read single-chromosome BAM, 101 bp, ~8 %
-spliced, generated on the box by tools/bamgen (seed 1234).  N > 1 (weak scaling): the same shape N
-times in one BAM — N contigs of the chr1 length, N x 10M reads — so every GPU does exactly the N = 1
-work on its contig shard; junction tables are all-gathered over NCCL (the path's only exchange).
+Workload (N = 1 and N > 1 alike): BASELINE.json configs[2], the configuration the target is quoted on — a synthetic
+100M-read whole-genome BAM (24 contigs, 150 bp paired, 12 % spliced), generated on the box by tools/bamgen (seed 1234,
+BGZF level 6) into /dev/shm.  `--config c2` selects configs[1] (10M reads, one chromosome, 101 bp, 8 % spliced) instead.
+N > 1 is STRONG scaling on the same file: contigs are sharded over the ranks (one process per GPU), the junction tables
+are all-gathered (the path's only exchange) and rank 0 merges and prints.
 
 One "step" = one pass of the hot path over the whole workload.
-  value : reads/s with the SoA batch already resident in HBM: cigar_scan + junction_merge +
-          finalize (compaction, first-seen ranking, sort) + D2H of the junction table
-          [+ all-gather for N > 1]; CUDA events on the launching stream, max over ranks.
-  e2e   : reads/s through the public call (JunctionsExtractor.identify_junctions_from_BAM +
-          print_all_junctions, i.e. rtjx_run + rtjx_write_bed12) on the BAM FILE (host buffers: page
-          cache): compressed bytes staged through pinned memory and copied H2D, BGZF inflate + BAM
-          record split + CIGAR scan + merge on the GPU, junction table D2H, BED12 file written —
-          wall clock, everything inside, a fresh handle per step.
-  roofline : cigar_scan kernel, algorithmic bytes 16*R + 4*C over its CUDA-event duration.
-  cpu_baseline : the UNMODIFIED reference (oracle/_ref/regtools_ref, built by oracle/Makefile)
-          timed on the host cores on a bounded region sample of the same BAM.
+  value : reads/s with the INPUT RESIDENT IN HBM: the compressed BAM bytes sit in device memory (rtjx_stage_bam) before
+          the timed region; a step is BGZF inflate + BAM record split + cigar_scan + junction_merge + finalize (compact,
+          first-seen ranking, sort) on the GPU + D2H of the junction table [+ all-gather and merge for N > 1].
+  e2e   : reads/s through the public call on the BAM FILE (host buffers: page cache): fresh handle per step, compressed
+          bytes staged through pinned memory and copied H2D inside the timed region, BED12 file written and closed —
+          wall clock, warm process.  `e2e.cold` = the same through the CLI binary, one process per run, exec to exit.
+  roofline : the cigar_scan kernel inside the `value` steps: algorithmic bytes 16*R + 4*C over its CUDA-event duration.
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref/regtools_ref, built by oracle/Makefile from /root/reference)
+          on one host core (it has no threading), timed on a bounded sample (`-r chr1`) of the same BAM.
+  identity : sha256 of the BED12 the timed e2e pass wrote == sha256 of the reference's BED12 on the WHOLE file.
+
+`--impl reference` is the reference arm: nothing of the product is imported or loaded; reads are counted by
+oracle/_ref/ref_count (the reference's own htslib).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -35,11 +39,19 @@ sys.path.insert(0, ROOT)
 SCRATCH = os.environ.get("RTJX_SCRATCH", "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp")
 BAMGEN = os.path.join(ROOT, "tools", "bamgen")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "regtools_ref")
+REF_COUNT = os.path.join(ROOT, "oracle", "_ref", "ref_count")
 ORACLE_BIN = os.path.join(ROOT, "oracle", "_ref", "jx_oracle")
+CLI_BIN = os.path.join(ROOT, "regtools_b200", "regtools")
+METRIC = "BAM reads/sec through junctions-extract"
+SAMPLE_REGION = "chr1"                       # the reference arm's bounded sample: every alignment of the first contig
+
+
+def bam_path(config, reads, level):
+    return os.path.join(SCRATCH, f"rtjx_{config}_{reads}_l{level}.bam")
 
 
 def ensure_bam(config, reads, level):
-    path = os.path.join(SCRATCH, f"rtjx_{config}_{reads}_l{level}.bam")
+    path = bam_path(config, reads, level)
     if not (os.path.exists(path) and os.path.exists(path + ".bai")):
         tmp = path + f".tmp{os.getpid()}.bam"
         subprocess.check_call([BAMGEN, "gen", "--out", tmp, "--config", config, "--reads", str(reads), "--seed", "1234",
@@ -47,6 +59,21 @@ def ensure_bam(config, reads, level):
         os.replace(tmp + ".bai", path + ".bai")
         os.replace(tmp, path)
     return path
+
+
+def workload_name(config, reads):
+    if config == "c2":
+        return f"synthetic {reads}-read single-chrom BAM (chr1), 101 bp, ~8% spliced, seed 1234 (BASELINE configs[1])"
+    return (f"synthetic {reads}-read whole-genome BAM (24 contigs chr1..chr22,chrX,chrY), 150 bp paired, 12% spliced, seed 1234 "
+            "(BASELINE configs[2])")
+
+
+def sha256_file(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 22), b""):
+            h.update(chunk)
+    return h.hexdigest()
 
 
 class ClockSampler:
@@ -119,120 +146,168 @@ class ClockSampler:
                 "samples": len(sm), "source": self.source}
 
 
-def time_reference(bam, region, threads_note=1, strand="XS"):
-    """Wall time of the reference CPU implementation on `region` of `bam`; returns (seconds, kind, bed_path)."""
-    out = os.path.join(SCRATCH, f"rtjx_ref_{os.getpid()}.bed")
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's CPU implementation (oracle/_ref, built from /root/reference by oracle/Makefile; else the oracle port)
+# ---------------------------------------------------------------------------------------------------------------------
+def ref_cmd(bam, out, region=None, strand="XS"):
+    """(argv, kind) of one `junctions extract` run of the reference CPU implementation."""
+    r = ["-r", region] if region else []
     if os.path.exists(REF_BIN):
-        cmd, kind = [REF_BIN, "junctions", "extract", "-s", strand, "-r", region, "-o", out, bam], "reference"
-    else:
-        cmd, kind = [ORACLE_BIN, "-s", strand, "-r", region, "-o", out, bam], "port"
+        return [REF_BIN, "junctions", "extract", "-s", strand] + r + ["-o", out, bam], "reference"
+    return [ORACLE_BIN, "-s", strand] + r + ["-o", out, bam], "port"
+
+
+def time_reference(bam, region=None):
+    """Wall time of one reference process, exec to exit; returns (seconds, kind, bed_path)."""
+    out = os.path.join(SCRATCH, f"rtjx_ref_{os.getpid()}_{'all' if region is None else region.replace(':', '_')}.bed")
+    cmd, kind = ref_cmd(bam, out, region)
     t0 = time.perf_counter()
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return time.perf_counter() - t0, kind, out
 
 
-def time_reference_all_cores(bam, contig_len, total_reads, contig="chr1"):
-    """SURVEY 8(d)'s courtesy figure: the reference has no threading, so "all host cores" = one reference process per window
-    of the contig (`-r chr1:a-b`), all started together, wall = the slowest.  NOT output-equivalent (names restart in every
-    process, alignments across a window edge are seen twice) — a throughput figure only, labelled as such."""
-    cores = min(os.cpu_count() or 1, 64)
-    exe = REF_BIN if os.path.exists(REF_BIN) else ORACLE_BIN
-    step = -(-contig_len // cores)
-    procs = []
-    t0 = time.perf_counter()
-    for i in range(cores):
-        region = f"{contig}:{i * step + 1}-{min((i + 1) * step, contig_len)}"
-        out = os.path.join(SCRATCH, f"rtjx_ref_{os.getpid()}_{i}.bed")
-        cmd = ([exe, "junctions", "extract"] if exe == REF_BIN else [exe]) + ["-s", "XS", "-r", region, "-o", out, bam]
-        procs.append(subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
-    rcs = [p.wait() for p in procs]
-    dt = time.perf_counter() - t0
-    for i in range(cores):
+def count_reads_reference(bam, region):
+    """Alignments the reference iterates for `region` — counted by the reference's own htslib (oracle/ref_count.c)."""
+    if os.path.exists(REF_COUNT):
+        return int(subprocess.check_output([REF_COUNT, bam, region], text=True).split()[0]), "oracle/_ref/ref_count (reference htslib)"
+    return None, None
+
+
+def sidecar_path(bam):
+    return bam + ".reference.json"
+
+
+def whole_file_reference(bam, reads_total):
+    """The reference on the WHOLE file, once: its BED12's sha256 and its wall time, cached next to the BAM."""
+    sc = sidecar_path(bam)
+    if os.path.exists(sc):
         try:
-            os.remove(os.path.join(SCRATCH, f"rtjx_ref_{os.getpid()}_{i}.bed"))
-        except OSError:
+            d = json.load(open(sc))
+            if d.get("bam_bytes") == os.path.getsize(bam):
+                return d
+        except Exception:
             pass
+    dt, kind, bed = time_reference(bam, None)
+    d = {"sha256": sha256_file(bed), "seconds": dt, "reads": reads_total, "reads_per_s": reads_total / dt, "kind": kind,
+         "bed12_bytes": os.path.getsize(bed), "bam_bytes": os.path.getsize(bam),
+         "cmd": "regtools junctions extract -s XS -o out.bed <bam>  (whole file, one process, one thread)"}
+    os.remove(bed)
+    tmp = sc + f".tmp{os.getpid()}"
+    json.dump(d, open(tmp, "w"))
+    os.replace(tmp, sc)
+    return d
+
+
+def time_reference_all_cores(bam, contigs):
+    """SURVEY 8(d)'s courtesy figure: the reference has no threading, so "all host cores" = one reference process per contig
+    (`-r chrN`), as many at a time as there are cores, wall = until the last one ends.  NOT output-equivalent (junction names
+    restart in every process) — a throughput figure only, labelled as such."""
+    cores = min(os.cpu_count() or 1, 64)
+    pending = list(contigs)
+    running, rcs = [], []
+    t0 = time.perf_counter()
+    i = 0
+    while pending or running:
+        while pending and len(running) < cores:
+            c = pending.pop(0)
+            out = os.path.join(SCRATCH, f"rtjx_refall_{os.getpid()}_{i}.bed")
+            i += 1
+            cmd, _ = ref_cmd(bam, out, c)
+            running.append((subprocess.Popen(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL), out))
+        time.sleep(0.02)
+        for p, out in list(running):
+            if p.poll() is not None:
+                rcs.append(p.returncode)
+                running.remove((p, out))
+                try:
+                    os.remove(out)
+                except OSError:
+                    pass
+    dt = time.perf_counter() - t0
     if any(rcs):
         return None
-    return {"value": total_reads / dt, "unit": "reads/s", "cores": cores, "seconds": dt,
-            "note": f"courtesy: {cores} concurrent reference processes, one per {step}-bp window of {contig}; not output-equivalent "
-                    "(per-process junction names, alignments on window edges seen twice)"}
+    return {"seconds": dt, "cores": cores, "processes": len(contigs),
+            "note": f"courtesy: one reference process per contig, {cores} at a time; not output-equivalent (per-process junction names)"}
 
 
-def count_reads(bam, region, device):
-    import regtools_b200 as rt
-    ex = rt.JunctionsExtractor(bam, region, 0, "XS", 8, 70, 500000, device=device)
-    ex.identify_junctions_from_BAM()
-    n = ex.stats()["reads"]
-    out = os.path.join(SCRATCH, f"rtjx_ours_{os.getpid()}.bed")
-    ex.output_file_ = out
-    ex.print_all_junctions()
-    ex.close()
-    return n, out
+def config_contigs(config):
+    return ["chr1"] if config == "c2" else [f"chr{i}" for i in range(1, 23)] + ["chrX", "chrY"]
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     n = max(args.gpus, 1)
-    config = "c2" if n == 1 else f"c2x{n}"
-    reads = args.reads * n
-    bam = ensure_bam(config, reads, args.level)
-    # bounded sample: a region holding ~1/5 of a 10M-read workload keeps each step to a few seconds
-    region = "chr1:1-50000000"
-    import regtools_b200 as rt
-    tid, pos, _, _, _ = rt.JunctionsExtractor(bam, region, 0, "XS", 8, 70, 500000, device=-1).load_batch()
-    sample_reads = int(len(tid))
-    times = []
-    kind = "reference"
+    bam = ensure_bam(args.config, args.reads, args.level)
+    # the whole file once, in the background (one core), while the bounded sample is timed step by step on another
+    whole = {}
+    th = threading.Thread(target=lambda: whole.update(whole_file_reference(bam, args.reads)), daemon=True)
+    th.start()
+    sample_reads, counter = count_reads_reference(bam, SAMPLE_REGION)
+    times, kind = [], "reference"
     for i in range(args.warmup + args.steps):
-        dt, kind, _ = time_reference(bam, region)
+        dt, kind, bed = time_reference(bam, SAMPLE_REGION)
+        os.remove(bed)
         if i >= args.warmup:
             times.append(dt)
+    if sample_reads is None:
+        sample_reads = args.reads if args.config == "c2" else None
     ms = 1000.0 * sum(times) / len(times)
-    value = sample_reads / (ms / 1000.0)
+    th.join()
+    value = (sample_reads / (ms / 1000.0)) if sample_reads else whole["reads_per_s"]
     courtesy = None
-    if n == 1:
+    if n == 1 and not args.no_courtesy:
         try:
-            courtesy = time_reference_all_cores(bam, 248956422, reads)
+            courtesy = time_reference_all_cores(bam, config_contigs(args.config))
+            if courtesy:
+                courtesy["value"] = args.reads / courtesy["seconds"]
+                courtesy["unit"] = "reads/s"
         except Exception as e:
             courtesy = {"error": str(e)}
+    sample = (f"regtools junctions extract -s XS -r {SAMPLE_REGION}: {sample_reads} reads per step (counted by {counter}); the reference "
+              f"is single-threaded (host has {os.cpu_count()} cores)")
     line = {
-        "impl": "reference", "metric": "BAM reads/sec through junctions-extract", "value": value, "unit": "reads/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s",
         "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(config, reads), "sample": f"-r {region} ({sample_reads} reads)"},
-        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": 1, "kind": kind,
-                         "sample": f"regtools junctions extract -s XS -r {region}: {sample_reads} reads per step; "
-                                   "the reference is single-threaded",
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, args.reads)},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": 1, "kind": kind, "sample": sample,
+                         "whole_file": {k: whole.get(k) for k in ("seconds", "reads", "reads_per_s", "sha256", "bed12_bytes")},
                          "all_cores_courtesy": courtesy},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_name(config, reads):
-    if config == "c2":
-        return f"synthetic {reads}-read single-chrom BAM (chr1), 101 bp, ~8% spliced, seed 1234 (BASELINE configs[1])"
-    if config.startswith("c2x"):
-        return (f"synthetic {reads}-read BAM of {config[3:]} contigs, each the configs[1] chromosome (101 bp, ~8% spliced, seed 1234): "
-                "one contig shard per GPU, the N=1 work per GPU")
-    return f"synthetic {reads}-read whole-genome BAM (24 contigs), 150 bp paired, 12% spliced, seed 1234, contig-sharded"
+# ---------------------------------------------------------------------------------------------------------------------
+def cold_cli_runs(bam, out_bed, n_runs):
+    """`regtools junctions extract` as a user runs it: one process per run, wall from exec to exit (CUDA context creation,
+    pinned allocations, everything)."""
+    times = []
+    for _ in range(n_runs):
+        t0 = time.perf_counter()
+        subprocess.check_call([CLI_BIN, "junctions", "extract", "-s", "XS", "-o", out_bed, bam], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        times.append(time.perf_counter() - t0)
+    return times
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU")
+    ap.add_argument("--config", default="c3", choices=["c3", "c2"])
+    ap.add_argument("--reads", type=int, default=0, help="reads in the BAM (default: 100M for c3, 10M for c2)")
     ap.add_argument("--level", type=int, default=6, help="BGZF deflate level of the synthetic BAM")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--no-courtesy", action="store_true", help="skip the all-cores courtesy figure")
+    ap.add_argument("--no-reference-check", action="store_true", help="skip the whole-file run of the reference when no cached one exists")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if not args.reads:
+        args.reads = 100_000_000 if args.config == "c3" else 10_000_000
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -264,37 +339,36 @@ def main():
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
     n = max(args.gpus, world)
-    config = "c2" if n == 1 else f"c2x{n}"
-    reads_total = args.reads * n
     if rank == 0:
-        bam = ensure_bam(config, reads_total, args.level)
+        ensure_bam(args.config, args.reads, args.level)
     if world > 1:
         dist.barrier()
-    bam = os.path.join(SCRATCH, f"rtjx_{config}_{reads_total}_l{args.level}.bam")
+    bam = bam_path(args.config, args.reads, args.level)
     host_threads = args.threads or max(1, (os.cpu_count() or 1) // world)
+    shard = dict(shard_rank=rank, shard_world=world)
 
-    # ---- resident batch: this rank's shard as SoA arrays in HBM --------------------------------
-    loader = rt.JunctionsExtractor(bam, ".", 0, "XS", 8, 70, 500000, device=local, shard_rank=rank, shard_world=world,
-                                   n_threads=host_threads)
-    tid, pos, meta, off, cig = loader.load_batch()
-    loader.close()
-    R, C = int(len(tid)), int(len(cig))
-    n_nops = int(np.count_nonzero((cig & 0xF) == 3))
-    d = [torch.from_numpy(x.view(np.int32)).to(dev) for x in (tid, pos, meta, off, cig)]
-    stream = torch.cuda.current_stream().cuda_stream
-    ex = rt.JunctionsExtractor(bam, ".", 0, "XS", 8, 70, 500000, device=local, profile=True)
-    from regtools_b200.distributed import _header_contigs
-    ex.set_contigs(_header_contigs(bam))
+    def gather_and_merge(table, out_bed=None):
+        """N > 1: the path's one exchange + rank 0's merge (and BED12 when asked for); returns the junction count on rank 0."""
+        tabs = all_gather_tables(table, dev)
+        if rank != 0:
+            return 0
+        m = merge_tables(bam, tabs)
+        if out_bed:
+            m.output_file_ = out_bed
+            m.print_all_junctions()
+        nj = len(m.junction_table()) if not out_bed else sum(len(x) for x in tabs)
+        m.close()
+        return nj
+
+    # ---- value: compressed BAM resident in HBM -> junction table on the host ---------------------------------------
+    ex = rt.JunctionsExtractor(bam, ".", 0, "XS", 8, 70, 500000, device=local, profile=True, n_threads=host_threads, **shard)
+    ex.stage_bam()
 
     def step_resident():
         ex.clear()
-        ex.scan_batch(*d, first_ordinal=0, n_junction_ops=n_nops, stream=stream)
-        ex.finalize(stream)
+        ex.identify_junctions_from_BAM()
         t = ex.junction_table()
-        if world > 1:
-            tabs = all_gather_tables(t, dev)
-            return sum(len(x) for x in tabs)
-        return len(t)
+        return gather_and_merge(t) if world > 1 else len(t)
 
     for _ in range(args.warmup):
         step_resident()
@@ -315,56 +389,58 @@ def main():
         dist.barrier()
     ms_total = e0.elapsed_time(e1)
     st = ex.stats()
+    R_rank, C_rank = int(st["reads"]) // args.steps, int(st["cigar_ops"]) // args.steps
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    reads_t = torch.tensor([R], dtype=torch.int64, device=dev)
+    reads_t = torch.tensor([R_rank], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(reads_t, op=dist.ReduceOp.SUM)
     ms_step = float(t_ms.item()) / args.steps
     reads_all = int(reads_t.item())
     value = reads_all / (ms_step / 1000.0)
-    scan_ms = st["scan_ms"] / max(st["batches"], 1)
-    merge_ms = st["merge_ms"] / max(st["batches"], 1)
-    fin_ms = st["finalize_ms"] / max(args.steps, 1)
+    scan_launches = max(int(st["batches"]), 1)
+    scan_ms = st["scan_ms"] / scan_launches
+    merge_ms = st["merge_ms"] / scan_launches
+    resident_stats = {"inflate_ms_per_step": st["inflate_kernel_ms"] / args.steps, "cigar_scan_ms_per_step": st["scan_ms"] / args.steps,
+                      "junction_merge_ms_per_step": st["merge_ms"] / args.steps, "finalize_ms_per_step": st["finalize_ms"] / args.steps,
+                      "cigar_scan_launches_per_step": scan_launches / args.steps, "junction_candidates_per_step": int(st["candidates"]) // args.steps,
+                      "bgzf_blocks_per_step": int(st["bgzf_blocks"]) // args.steps, "inflated_bytes_per_step": int(st["inflated_bytes"]) // args.steps}
     launches_resident = st["kernel_launches"] / max(args.steps, 1)
     ex.close()
 
-    # ---- end to end through the public call, host buffers --------------------------------------
+    # ---- end to end through the public call, host buffers ----------------------------------------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 5)
     out_bed = os.path.join(SCRATCH, f"rtjx_bench_{rank}.bed")
-    e2e_times, h2d, d2h = [], 0, 0
-    for i in range(1 + e2e_steps):                       # one warm-up (page cache, pinned allocs)
+    e2e_times, feeder = [], None
+    for i in range(1 + e2e_steps):                       # one warm-up (page cache, pinned allocations)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        e = rt.JunctionsExtractor(bam, ".", 0, "XS", 8, 70, 500000, device=local, shard_rank=rank, shard_world=world,
-                                  n_threads=host_threads)
+        e = rt.JunctionsExtractor(bam, ".", 0, "XS", 8, 70, 500000, device=local, n_threads=host_threads, **shard)
         e.identify_junctions_from_BAM()
+        t_run = time.perf_counter()
         table = e.junction_table()
+        t_fin = time.perf_counter()
         if world > 1:
-            tabs = all_gather_tables(table, dev)
-            if rank == 0:
-                m = merge_tables(bam, tabs)
-                m.output_file_ = out_bed
-                m.print_all_junctions()
-                m.close()
+            gather_and_merge(table, out_bed)
         else:
             e.output_file_ = out_bed
             e.print_all_junctions()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
         s2 = e.stats()
         e.close()
         if i > 0:
-            e2e_times.append(dt)
-            h2d, d2h = s2["h2d_bytes"], s2["d2h_bytes"]
-            feeder = s2
+            e2e_times.append(t1 - t0)
+            feeder = dict(s2, run_s=t_run - t0, finalize_d2h_s=t_fin - t_run, exchange_merge_bed12_s=t1 - t_fin)
     e2e_t = torch.tensor([sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
+    h2d_t = torch.tensor([int(feeder["h2d_bytes"]), int(feeder["d2h_bytes"])], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(h2d_t, op=dist.ReduceOp.SUM)
     e2e_value = reads_all / float(e2e_t.item())
     clocks = sampler.stop() if rank == 0 else None       # sampled across both timed regions (resident steps + e2e steps)
 
@@ -373,62 +449,88 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (cigar_scan) ------------------------------------------
+    # ---- identity: the BED12 of the timed pass against the reference on the whole file ------------------------------
+    ours_sha = sha256_file(out_bed)
+    identity = {"ours_sha256": ours_sha, "bed12_bytes": os.path.getsize(out_bed), "junction_lines": sum(1 for _ in open(out_bed))}
+    if os.path.exists(sidecar_path(bam)) or not args.no_reference_check:
+        try:
+            whole = whole_file_reference(bam, args.reads)
+            identity.update({"reference_sha256": whole["sha256"], "identical_to_reference_on_whole_file": whole["sha256"] == ours_sha,
+                             "reference_whole_file_seconds": whole["seconds"], "reference_whole_file_reads_per_s": whole["reads_per_s"],
+                             "reference_kind": whole["kind"]})
+        except Exception as ex_:
+            identity["reference_error"] = str(ex_)
+
+    # ---- cold: the CLI binary, one process per run (N = 1; the multi-GPU driver is this script) -----------------------
+    cold = None
+    if world == 1 and os.path.exists(CLI_BIN):
+        cold_bed = os.path.join(SCRATCH, "rtjx_bench_cold.bed")
+        ct = cold_cli_runs(bam, cold_bed, 2)
+        cold = {"value": reads_all / min(ct), "unit": "reads/s", "seconds": ct, "bed12_sha256_equal": sha256_file(cold_bed) == ours_sha,
+                "what": "regtools_b200/regtools junctions extract -s XS -o out.bed <bam>: wall from exec to exit, one process per run, page cache warm"}
+
+    # ---- roofline of the dominant kernel of the junction path (cigar_scan) -------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = 16.0 * R + 4.0 * C
+    alg_bytes = (16.0 * R_rank + 4.0 * C_rank) / (scan_launches / args.steps)       # per launch
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("cigar_scan_dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
     except Exception:
         pass
 
-    # ---- CPU baseline: the reference on a bounded sample of the same BAM (N = 1 only) ----------
+    # ---- CPU baseline: the reference on a bounded sample of the same BAM (N = 1 only) --------------------------------
     cpu = None
     if n == 1:
-        region = "chr1:1-50000000"
-        sample_reads, ours_bed = count_reads(bam, region, local)
-        dt, kind, ref_bed = time_reference(bam, region)
-        same = open(ours_bed).read() == open(ref_bed).read()
-        cpu = {"value": sample_reads / dt, "unit": "reads/s", "cores": 1, "kind": kind,
-               "sample": f"regtools junctions extract -s XS -r {region} on the same BAM: {sample_reads} reads in {dt:.2f} s "
-                         f"(single-threaded reference; host has {os.cpu_count()} cores)",
-               "bed12_identical_to_ours_on_sample": same}
-        try:
-            cpu["all_cores_courtesy"] = time_reference_all_cores(bam, 248956422, reads_total)
-        except Exception as e:          # the courtesy figure must never cost the bench line
-            cpu["all_cores_courtesy"] = {"error": str(e)}
+        sample_reads, counter = count_reads_reference(bam, SAMPLE_REGION)
+        dt, kind, ref_bed = time_reference(bam, SAMPLE_REGION)
+        os.remove(ref_bed)
+        if sample_reads:
+            cpu = {"value": sample_reads / dt, "unit": "reads/s", "cores": 1, "kind": kind,
+                   "sample": f"regtools junctions extract -s XS -r {SAMPLE_REGION} on the same BAM: {sample_reads} reads in {dt:.2f} s "
+                             f"(counted by {counter}; single-threaded reference; host has {os.cpu_count()} cores)"}
+            if "reference_whole_file_reads_per_s" in identity:
+                cpu["whole_file_reads_per_s"] = identity["reference_whole_file_reads_per_s"]
 
     line = {
-        "metric": "BAM reads/sec through junctions-extract", "value": value, "unit": "reads/s", "n_gpus": n,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": n,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(config, reads_total), "reads": reads_all, "cigar_ops": C if world == 1 else None,
-                   "junction_ops": n_nops if world == 1 else None, "junctions": int(n_junc), "bgzf_level": args.level,
-                   "l2_policy": "inputs (>=211 MB per GPU) larger than the 126 MB L2; no flush needed",
-                   "value_region": "cigar_scan + junction_merge + finalize (compact, rank, sort) + D2H table"
-                                   + (" + NCCL all-gather" if world > 1 else ""),
+        "config": {"workload": workload_name(args.config, args.reads), "reads": reads_all,
+                   "cigar_ops": C_rank if world == 1 else None, "junctions": int(n_junc), "bgzf_level": args.level,
+                   "bam_bytes": os.path.getsize(bam),
+                   "l2_policy": "inputs (compressed file, GBs per GPU; SoA batches >= 200 MB) larger than the 126 MB L2; no flush needed",
+                   "value_region": "compressed BAM resident in HBM (rtjx_stage_bam) -> BGZF inflate + record split + cigar_scan + junction_merge "
+                                   "+ finalize (compact, rank, sort) + D2H of the junction table" + (" + NCCL all-gather + merge on rank 0" if world > 1 else ""),
                    "host_threads_per_rank": host_threads, "parallelism": f"contig-shard x{world}" if world > 1 else "single GPU"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        "resident": resident_stats,
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d_t[0].item()), "d2h_bytes_per_step": int(h2d_t[1].item()),
                 "ms_per_step": 1000.0 * float(e2e_t.item()), "steps": e2e_steps,
-                "region": "fresh handle + rtjx_run (BAM file -> pinned staging -> H2D of compressed bytes -> device BGZF inflate "
-                          "+ record split + cigar_scan + junction_merge) + finalize + BED12 file write",
+                "region": "fresh handle + rtjx_run (BAM file in the page cache -> pinned staging -> H2D of compressed bytes -> device BGZF inflate "
+                          "+ record split + cigar_scan + junction_merge) + finalize + BED12 file written and closed; warm process",
                 "feeder": "device" if feeder["host_parse_s"] == 0.0 and feeder["inflated_bytes"] else "host",
-                "compressed_bytes": int(feeder["compressed_bytes"]), "inflated_bytes": int(feeder["inflated_bytes"]),
-                "host_staging_s": feeder["host_inflate_s"], "host_parse_s": feeder["host_parse_s"],
-                "gpu_wait_s": feeder["host_wait_s"], "gpu_launches": int(feeder["kernel_launches"])},
+                "stages_rank0_s": {"host_staging_memcpy": feeder["host_inflate_s"], "host_wait_for_gpu": feeder["host_wait_s"],
+                                   "rtjx_run_total": feeder["run_s"], "finalize_and_d2h": feeder["finalize_d2h_s"],
+                                   ("exchange_merge_bed12" if world > 1 else "bed12_write"): feeder["exchange_merge_bed12_s"],
+                                   "host_parse": feeder["host_parse_s"]},
+                "compressed_bytes_rank0": int(feeder["compressed_bytes"]), "inflated_bytes_rank0": int(feeder["inflated_bytes"]),
+                "gpu_launches": int(feeder["kernel_launches"]),
+                "cold": cold, "identity": identity},
         "gpu_launches": int(round(launches_resident * args.steps)),
-        "roofline": {"bound": "hbm", "kernel": "cigar_scan_small_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms,
+        "roofline": {"bound": "hbm", "kernel": "cigar_scan_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None,
+                     "traffic": traffic.get("cigar_scan_dram_bytes_per_launch") if traffic else None,
+                     "traffic_source": (f"profiles/roofline_traffic.json ({traffic.get('workload')}; ncu capture, not measured in this run)" if traffic else None),
+                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms, "launches_per_step": scan_launches / args.steps,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                     "other_kernels_ms": {"junction_merge": merge_ms, "finalize(compact+rank+sort)": fin_ms}},
+                     "other_kernels_ms": {"junction_merge": merge_ms, "bgzf_inflate_per_step": resident_stats["inflate_ms_per_step"],
+                                          "finalize(compact+rank+sort)_per_step": resident_stats["finalize_ms_per_step"]}},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))

@@ -165,8 +165,18 @@ __device__ __forceinline__ bool plausible_one(const uint8_t* data, int64_t o, in
     if (mtid < -1 || mtid >= n_ref || mpos < -1) return false;
     if (!record_ok(r + 4, bs)) return false;
     const uint32_t l_qname = r[12], n_cigar = ld_u16_any(r + 16);
+    // what the fixed fields account for must leave a sane amount of aux data: a start guessed a byte or two early reads a
+    // block_size that is the true one shifted left, i.e. megabytes too large (seen at a rate of ~1e-3 per BGZF block)
+    const int32_t l_qseq = (int32_t)ld_u32_any(r + 20);
+    const long long fixed = 32ll + l_qname + 4ll * n_cigar + ((long long)l_qseq + 1) / 2 + l_qseq;
+    if ((long long)bs - fixed > (1ll << 20)) return false;
     const int64_t name_end = o + 36 + (int64_t)l_qname;           // one past the NUL of the read name
     if (name_end <= data_len && data[name_end - 1] != 0) return false;
+    // read names are printable ([!-~], SAM spec 1.4): checked on the first characters
+    for (uint32_t c = 0; c + 1 < l_qname && c < 6u && o + 36 + c < data_len; ++c) {
+        const uint32_t ch = data[o + 36 + c];
+        if (ch < 33u || ch > 126u) return false;
+    }
     if (n_cigar && name_end + 4 <= data_len && (ld_u32_any(data + name_end) & 0xfu) > 9u) return false;
     *next = o + 4 + (int64_t)bs;
     return true;

@@ -6,9 +6,9 @@
 // CIGAR scan, junction merge) runs on the GPU.
 //
 // Round-2 shape of the pipeline (round 1: one stream, one group at a time, scan per group):
-//   * a GROUP of consecutive BGZF blocks is the unit of device work; two group slots are in flight: the inflate of group
-//     g+1 (its own stream) overlaps the record walk / extraction of group g (the chain stream), and both overlap the H2D
-//     copies of group g+2's bytes (copy stream);
+//   * a GROUP of consecutive BGZF blocks is the unit of device work; four group slots are in flight: the inflates of the
+//     groups behind g (each on its slot's stream; the lane-per-stream decoder is latency-bound, so concurrent launches add up)
+//     overlap the record walk / extraction of group g (the chain stream), and all overlap the H2D copies (copy stream);
 //   * record starts are found ON the device, one per BGZF block (block_seeds_kernel), instead of every 16 kb of reference
 //     from the index — segments of <= 64 KiB instead of hundreds of thousands of records on deep loci; the chain walk verifies
 //     every guessed start, a miss makes the run start over with the index seeds of round 1 (then the linear index alone,
@@ -75,11 +75,10 @@ size_t parallel_pread(int fd, uint8_t* dst, size_t n, uint64_t file_off, int thr
 
 struct Engine::DeviceFeed {
     static constexpr uint32_t HEAD = 4u << 20;           // carry headroom in front of the inflated data
-    static constexpr int NSLOT = 2;                      // groups in flight
+    static constexpr int NSLOT = 4;                      // groups in flight (their inflates run concurrently, each on its slot's stream)
     static constexpr int NSTAGE = 3;                     // pinned staging chunks
     uint8_t* h_comp[NSTAGE] = {nullptr, nullptr, nullptr};
     cudaEvent_t comp_free[NSTAGE] = {nullptr, nullptr, nullptr};
-    cudaStream_t inf_stream = nullptr;                   // inflate + record-start discovery; the engine's stream_ runs the chain
     struct GroupSlot {
         uint8_t* d_comp = nullptr; size_t comp_cap = 0;  // compressed bytes of the group (file mode)
         uint8_t* d_infl = nullptr; size_t infl_cap = 0;  // HEAD + data + pad
@@ -89,8 +88,10 @@ struct Engine::DeviceFeed {
         int32_t* d_recoff = nullptr; int32_t* d_dense = nullptr; uint32_t* d_ncig = nullptr; uint32_t* d_ncigscan = nullptr; size_t rec_cap = 0;
         void* d_ws = nullptr; size_t ws_cap = 0;
         FeedState* h_state = nullptr;                    // pinned copy of the device state after this slot's group
+        cudaStream_t inf_stream = nullptr;               // inflate + record-start discovery of this slot's group; the engine's stream_ runs the chain
         cudaEvent_t copied = nullptr, inflated = nullptr, done = nullptr;
         bool busy = false;                               // a group was launched into this slot and not yet checked
+        uint32_t dbg_nb = 0, dbg_nseg = 0; uint64_t dbg_out_total = 0; bool dbg_first = false;   // RTJX_FEED_DEBUG
     } slot[NSLOT];
     FeedState* d_state = nullptr;
     uint8_t* d_carry = nullptr;                          // HEAD bytes: the unfinished record at the end of a group, right-aligned
@@ -110,11 +111,11 @@ struct Engine::DeviceFeed {
             if (s.copied) cudaEventDestroy(s.copied);
             if (s.inflated) cudaEventDestroy(s.inflated);
             if (s.done) cudaEventDestroy(s.done);
+            if (s.inf_stream) cudaStreamDestroy(s.inf_stream);
         }
         cached_dev_free(d_state); cached_dev_free(d_carry);
         cached_dev_free(a_tid); cached_dev_free(a_pos); cached_dev_free(a_meta); cached_dev_free(a_off); cached_dev_free(a_cigar);
         cached_dev_free(d_file);
-        if (inf_stream) cudaStreamDestroy(inf_stream);
     }
 };
 
@@ -170,7 +171,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     const int n_threads = prm_.n_threads > 0 ? prm_.n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     const int copy_threads = std::min(n_threads, 16);
     const uint64_t STAGE = 32ull << 20;                  // compressed bytes per pinned staging chunk
-    static const uint64_t GROUP = [] { const char* v = getenv("RTJX_GROUP_MB"); return (uint64_t)(v ? atoi(v) : 512) << 20; }();
+    static const uint64_t GROUP = [] { const char* v = getenv("RTJX_GROUP_MB"); return (uint64_t)(v ? atoi(v) : 256) << 20; }();
     // the first group of a range is smaller: the GPU starts after a few ms of staging instead of a full group's worth
     static const uint64_t FIRST_GROUP = [] { const char* v = getenv("RTJX_FIRST_GROUP_MB"); return (uint64_t)(v ? atoi(v) : 128) << 20; }();
     // alignments (upper bound, 64 bytes of stream each) accumulated before cigar_scan runs
@@ -211,8 +212,8 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     if (!F.d_state) {
         CKD(cached_dev_malloc(&F.d_state, sizeof(FeedState)));
         CKD(cached_dev_malloc(&F.d_carry, (size_t)DeviceFeed::HEAD + 256));
-        CKD(cudaStreamCreateWithFlags(&F.inf_stream, cudaStreamNonBlocking));
         for (DeviceFeed::GroupSlot& s : F.slot) {
+            CKD(cudaStreamCreateWithFlags(&s.inf_stream, cudaStreamNonBlocking));
             CKD(cached_host_alloc(&s.h_state, sizeof(FeedState)));
             CKD(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
             CKD(cudaEventCreateWithFlags(&s.inflated, cudaEventDisableTiming));
@@ -224,7 +225,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             CKD(cudaEventCreateWithFlags(&F.comp_free[i], cudaEventDisableTiming));
             CKD(cached_host_alloc(&F.h_comp[i], STAGE + (1u << 17) + 256));
         }
-    auto drain = [&]() { cudaStreamSynchronize(stream_); cudaStreamSynchronize(copy_stream_); cudaStreamSynchronize(F.inf_stream); };
+    auto drain = [&]() { cudaStreamSynchronize(stream_); cudaStreamSynchronize(copy_stream_); for (DeviceFeed::GroupSlot& q : F.slot) cudaStreamSynchronize(q.inf_stream); };
     auto grow_dev = [&](void** p, size_t* cap, size_t want, size_t elem) -> cudaError_t {
         if (want <= *cap) return cudaSuccess;
         if (*p) drain();                                 // only a live buffer needs the streams drained
@@ -255,7 +256,38 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
         stats_.host_wait_s += now_s() - tw;
         stats_.d2h_bytes += sizeof(FeedState);
         const FeedState& st = *s.h_state;
-        if (st.flags || st.bad_offset != LLONG_MAX) { declined = true; feed_decline_flags_ = st.flags; }
+        if (st.flags || st.bad_offset != LLONG_MAX) {
+            declined = true; feed_decline_flags_ = st.flags;
+            if (getenv("RTJX_FEED_DEBUG") && s.dbg_nb) {
+                // developer aid: which seed did the chain miss?  Walks the group's inflated stream on the host.
+                drain();
+                std::vector<int64_t> seeds(s.dbg_nseg);
+                std::vector<uint8_t> data((size_t)s.dbg_out_total);
+                std::vector<BgzfBlockDesc> desc(s.dbg_nb);
+                cudaMemcpy(seeds.data(), s.d_seeds, seeds.size() * 8, cudaMemcpyDeviceToHost);
+                cudaMemcpy(data.data(), s.d_infl + DeviceFeed::HEAD, data.size(), cudaMemcpyDeviceToHost);
+                cudaMemcpy(desc.data(), s.d_desc, desc.size() * sizeof(BgzfBlockDesc), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[rtjx dbg] group declined: flags %u bad_offset %lld n_seg %u out_total %llu first_of_range %d carry_len %u\n", st.flags,
+                        st.bad_offset, s.dbg_nseg, (unsigned long long)s.dbg_out_total, (int)s.dbg_first, st.carry_len);
+                if (seeds.size() > 2) {
+                    int64_t p = s.dbg_first ? seeds[0] : seeds[1]; size_t si = s.dbg_first ? 1 : 2; int shown = 0;
+                    while (p + 4 <= (int64_t)data.size() && shown < 8) {
+                        int32_t bl; memcpy(&bl, &data[(size_t)p], 4);
+                        while (si < seeds.size() && seeds[si] < p) {
+                            fprintf(stderr, "[rtjx dbg]   seed %zu = %lld is NOT a record start (chain passed it at %lld; block out_off %u len %u)\n", si,
+                                    (long long)seeds[si], (long long)p, desc[si].out_off, desc[si].out_len);
+                            ++si; ++shown;
+                        }
+                        if (si < seeds.size() && seeds[si] == p) ++si;
+                        if (bl < 32) { fprintf(stderr, "[rtjx dbg]   bad block_size %d at %lld\n", bl, (long long)p); break; }
+                        p += 4 + (int64_t)bl;
+                    }
+                    fprintf(stderr, "[rtjx dbg]   host chain ended at %lld of %zu; seeds matched up to %zu of %zu\n", (long long)p, data.size(), si, seeds.size());
+                    for (size_t k = 1; k < seeds.size() && k < 4; ++k) fprintf(stderr, "[rtjx dbg]   seed[%zu] = %lld (block out_off %u)\n", k, (long long)seeds[k], desc[k].out_off);
+                    for (size_t k = seeds.size() > 3 ? seeds.size() - 3 : 1; k < seeds.size(); ++k) fprintf(stderr, "[rtjx dbg]   seed[%zu] = %lld (block out_off %u len %u)\n", k, (long long)seeds[k], desc[k].out_off, desc[k].out_len);
+                }
+            }
+        }
         if (st.reached_limit) reached_limit = true;
         return 0;
     };
@@ -397,7 +429,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             t_alloc += now_s() - ta0;
             uint8_t* data = S.d_infl + DeviceFeed::HEAD;
             const uint8_t* comp = resident ? F.d_file + G.first_coff : S.d_comp;
-            cudaStream_t is = F.inf_stream, cs = stream_;
+            cudaStream_t is = S.inf_stream, cs = stream_;
             // ---- inflate stream: block table, inflate, record starts
             // small tables go through the (pageable) vectors: cudaMemcpyAsync stages them synchronously, they are tiny
             CKD(cudaMemcpyAsync(S.d_desc, G.desc.data(), (size_t)nb * sizeof(BgzfBlockDesc), cudaMemcpyHostToDevice, is));
@@ -432,6 +464,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             stats_.bgzf_blocks += nb; stats_.inflated_bytes += G.out_total;
             acc_rec_upper += cap_total; acc_ops_upper += cig_upper; acc_dirty = true;
             S.busy = true;
+            S.dbg_nb = nb; S.dbg_nseg = n_seg; S.dbg_out_total = G.out_total; S.dbg_first = G.first_of_range;
             ++n_groups;
             return 0;
         };

@@ -82,11 +82,11 @@ ScanParams Engine::scan_params() const {
     static const int env_variant = getenv("RTJX_SCAN_VARIANT") ? atoi(getenv("RTJX_SCAN_VARIANT")) : 0;
     static const int env_cfg = getenv("RTJX_SCAN_CFG") ? atoi(getenv("RTJX_SCAN_CFG")) : 0;
     s.debug = prm_.scan_debug ? prm_.scan_debug : dbg;
-    s.variant = prm_.scan_variant ? prm_.scan_variant : (env_variant ? env_variant : 8);
+    s.variant = prm_.scan_variant ? prm_.scan_variant : (env_variant ? env_variant : 5);
     s.cfg = prm_.scan_cfg ? prm_.scan_cfg : env_cfg;
     s.genome = d_genome_; s.g_off = d_g_off_; s.g_len = d_g_len_; s.g_n = d_genome_ ? g_n_ : 0u;
     s.vr = vr_;
-    if ((d_genome_ || vr_.n || bc_mode_) && s.variant != 5) { s.variant = 8; s.cfg = 0; }   // the intron-motif, variant-region and barcode modes live in the two tiled scan kernels only
+    if ((d_genome_ || vr_.n || bc_mode_) && s.variant != 8) { s.variant = 5; s.cfg = 0; }   // the intron-motif, variant-region and barcode modes live in the two tiled scan kernels only
     return s;
 }
 

@@ -411,8 +411,8 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
 //  1. bgzf_inflate_lanes_kernel — Huffman decoding.  No lookup tables: a canonical code is decoded by COUNTING, over the 15
 //     code lengths, how many left-justified upper bounds `ub[len]` the next 15 stream bits (bit-reversed) reach — thirty
 //     compare/add instructions on registers, no branch, no memory access — followed by two small shared-memory reads
-//     (adj[len], then the symbol).  A lane therefore needs only 676 bytes of shared memory (symbols in canonical order +
-//     per-length adjustments), ten warps fit on an SM, and that occupancy — not table size — is what hides the symbol chain's
+//     (adj[len], then the symbol).  A lane therefore needs only 420 bytes of shared memory (symbols in canonical order, one
+//     byte each, + per-length adjustments), sixteen warps fit on an SM, and that occupancy — not table size — is what hides the symbol chain's
 //     latency.  (First round-2 build: 10-bit lookup tables, 3.2 KB per lane, two warps per SM: 337 ms for the 2.1 GB C2 stream
 //     against 74 ms for the kernel above; profiles/r2_inflate_lanes_v1.txt.)
 //     One loop, one symbol (or one DEFLATE block header) per lane per iteration, so lanes reconverge every iteration; zlib
@@ -427,12 +427,12 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
 //
 // Error codes are those of the kernel above (+18 input overrun, 19 match list full); any non-zero status sends the run to the
 // warp-per-block kernel's / host feeder's path.
-constexpr int LN_STRIDE = 676;                    // bytes of shared memory per lane: 169 words (odd: lanes on distinct banks)
-constexpr int LN_LIT_SYM = 0;                     // uint16[288] literal/length symbols in canonical order
-constexpr int LN_LIT_ADJ = 576;                   // int16[16]   offset[len] - first_code[len]
-constexpr int LN_DIST_ADJ = 608;                  // int16[16]
-constexpr int LN_DIST_SYM = 640;                  // uint8[32]
-constexpr int LN_WARPS_PER_SM = 10;
+constexpr int LN_SHARED = 256;                    // per CTA: length / distance base+extra tables (RFC 1951 3.2.5), 64 words
+constexpr int LN_STRIDE = 420;                    // bytes of shared memory per lane: 105 words (odd: lanes on distinct banks)
+constexpr int LN_LIT_SYM = 0;                     // uint8[288]  low byte of the literal/length symbols in canonical order
+constexpr int LN_LIT_AH = 288;                    // uint32[16]  per code length: int16 adj = offset - first_code | uint16 index from which symbols are >= 256
+constexpr int LN_DIST_ADJ = 352;                  // int16[16]
+constexpr int LN_DIST_SYM = 384;                  // uint8[32]
 
 // LSB-first bit reader of one lane: 64-bit buffer, 32-bit aligned refills, the next word always already requested.
 struct LaneBits {
@@ -455,7 +455,6 @@ struct LaneBits {
             bb |= (uint64_t)ahead << nb; nb += 32;
             if (p < lim) {
                 ahead = __ldg(p);
-                if ((reinterpret_cast<uintptr_t>(p) & 127u) == 0 && p + 128 < lim) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 128));
             } else ahead = 0;
             ++p;
         }
@@ -468,14 +467,18 @@ struct LaneBits {
     __device__ __forceinline__ const uint8_t* byte_ptr() const { return reinterpret_cast<const uint8_t*>(p - 1) - (nb >> 3); }
 };
 
-// Canonical code of `n` symbols with lengths len[]: ub[l] (l = 1..15, registers), adj[l] and the symbol table (shared memory).
-// Returns false on an over-subscribed code.  ub[l] = (first_code[l] + count[l]) << (15 - l): a 15-bit left-justified window v
-// holds a code of length 1 + #{l : v >= ub[l]}.
-template <class SymT>
-__device__ __forceinline__ bool lane_build(const uint8_t* len, int n, uint32_t (&ub)[16], int16_t* adj, SymT* symtab) {
+// Canonical code of `n` symbols with lengths len[]: ub[l] (l = 1..15, registers), per-length adjustments and the symbol table
+// (shared memory).  Returns false on an over-subscribed code.  ub[l] = (first_code[l] + count[l]) << (15 - l): a 15-bit
+// left-justified window v holds a code of length 1 + #{l : v >= ub[l]}; its symbol sits at (v >> (15 - l)) + adj[l] of the
+// table, adj[l] = offset[l] - first_code[l].  LIT: symbols are stored as their low byte; within one code length the canonical
+// order is ascending, so the symbols >= 256 (end of block, lengths) are the tail of each length's run and one index per
+// length (`hi`) tells them apart: ah[l] = uint16(adj[l]) | hi[l] << 16.
+template <bool LIT>
+__device__ __forceinline__ bool lane_build(const uint8_t* len, int n, uint32_t (&ub)[16], void* adj_out, uint8_t* symtab) {
     uint16_t count[16], offs[16];
+    int16_t adj[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) count[i] = 0;
+    for (int i = 0; i < 16; ++i) { count[i] = 0; adj[i] = 0; }
     for (int i = 0; i < n; ++i) count[len[i]]++;
     int left = 1;
     uint32_t code = 0, off = 0;
@@ -492,9 +495,21 @@ __device__ __forceinline__ bool lane_build(const uint8_t* len, int n, uint32_t (
         code = (code + c) << 1;
     }
     if (!ok) return false;
-    for (int s = 0; s < n; ++s) {
+    const int n_lo = LIT ? (n < 256 ? n : 256) : n;
+    for (int s = 0; s < n_lo; ++s) {
         const int l = len[s];
-        if (l) symtab[offs[l]++] = (SymT)s;
+        if (l) symtab[offs[l]++] = (uint8_t)s;
+    }
+    if (LIT) {
+        uint32_t* ah = static_cast<uint32_t*>(adj_out);
+        for (int l = 1; l <= 15; ++l) ah[l] = (uint32_t)(uint16_t)adj[l] | (uint32_t)offs[l] << 16;
+        for (int s = 256; s < n; ++s) {
+            const int l = len[s];
+            if (l) symtab[offs[l]++] = (uint8_t)s;
+        }
+    } else {
+        int16_t* a = static_cast<int16_t*>(adj_out);
+        for (int l = 1; l <= 15; ++l) a[l] = adj[l];
     }
     return true;
 }
@@ -509,17 +524,23 @@ __device__ __forceinline__ uint32_t lane_code_len(uint32_t v, const uint32_t (&u
 
 constexpr uint32_t LN_MATCH_CAP = 12288;          // match records per BGZF block (a block of nothing but 5-byte matches)
 
-__global__ void __launch_bounds__(32)
+constexpr int LN_THREADS = 64;                    // two warps per CTA: 8 CTAs = 16 warps per SM within the shared-memory budget
+__global__ void __launch_bounds__(LN_THREADS, 8)
 bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, uint32_t n_blocks,
                           uint8_t* __restrict__ out, uint32_t* __restrict__ status, uint2* __restrict__ mlist, uint32_t* __restrict__ mcount) {
     extern __shared__ __align__(16) uint8_t lane_smem[];
-    const uint32_t b = blockIdx.x * 32u + threadIdx.x;
-    if (b >= n_blocks) return;
-    uint8_t* T = lane_smem + threadIdx.x * LN_STRIDE;
-    uint16_t* lit_sym = reinterpret_cast<uint16_t*>(T + LN_LIT_SYM);
-    int16_t* lit_adj = reinterpret_cast<int16_t*>(T + LN_LIT_ADJ);
+    const uint32_t b = blockIdx.x * LN_THREADS + threadIdx.x;
+    // per-CTA tables: length symbol -> base | extra bits << 16 (29 entries), distance symbol likewise (30 entries, from word 32)
+    uint32_t* s_tab = reinterpret_cast<uint32_t*>(lane_smem);
+    if (threadIdx.x < 29) { const uint32_t y = threadIdx.x; s_tab[y] = c_len_base[y] | (uint32_t)c_len_extra[y] << 16; }
+    if (threadIdx.x < 30) { const uint32_t y = threadIdx.x; s_tab[32 + y] = c_dist_base[y] | (uint32_t)c_dist_extra[y] << 16; }
+    __syncthreads();
+    uint8_t* T = lane_smem + LN_SHARED + threadIdx.x * LN_STRIDE;
+    uint8_t* lit_sym = T + LN_LIT_SYM;
+    uint32_t* lit_ah = reinterpret_cast<uint32_t*>(T + LN_LIT_AH);
     int16_t* dist_adj = reinterpret_cast<int16_t*>(T + LN_DIST_ADJ);
     uint8_t* dist_sym = T + LN_DIST_SYM;
+    if (b >= n_blocks) return;
 
     const BgzfBlock blk = blocks[b];
     uint8_t* dst = out + blk.out_off;
@@ -598,8 +619,8 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
                 for (int i = hlit; i < 288; ++i) lens[i] = 0;
                 for (int i = hdist; i < 30; ++i) lens[288 + i] = 0;
             }
-            if (!lane_build<uint16_t>(lens, 288, ul, lit_adj, lit_sym)) { err = 9; continue; }
-            if (!lane_build<uint8_t>(lens + 288, 30, ud, dist_adj, dist_sym)) { err = 10; continue; }
+            if (!lane_build<true>(lens, 288, ul, lit_ah, lit_sym)) { err = 9; continue; }
+            if (!lane_build<false>(lens + 288, 30, ud, dist_adj, dist_sym)) { err = 10; continue; }
             in_block = true;
             continue;
         }
@@ -608,7 +629,9 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
         uint32_t v = __brev((uint32_t)br.bb) >> 17;                    // next 15 bits, first bit most significant
         uint32_t cl = lane_code_len(v, ul);
         if (cl > 15u) { err = 11; in_block = false; continue; }
-        uint32_t sym = lit_sym[(int)(v >> (15u - cl)) + (int)lit_adj[cl]];
+        const uint32_t ah = lit_ah[cl];
+        const uint32_t ix = (v >> (15u - cl)) + (uint32_t)(int)(int16_t)(ah & 0xffffu);
+        uint32_t sym = (uint32_t)lit_sym[ix] + (ix >= (ah >> 16) ? 256u : 0u);
         br.drop((int)cl);
         if (sym < 256u) {
             if (opos >= cap) { err = 15; in_block = false; continue; }
@@ -619,9 +642,8 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
         sym -= 257u;
         if (sym >= 29u) { err = 12; in_block = false; continue; }
         // length: base and extra bits from the symbol (RFC 1951 3.2.5)
-        const uint32_t lx = sym < 8u ? 0u : (sym == 28u ? 0u : (sym - 4u) >> 2);
-        const uint32_t lbase = sym < 8u ? sym + 3u : (sym == 28u ? 258u : ((4u + (sym & 3u)) << lx) + 3u);
-        const uint32_t len = lbase + br.peek((int)lx);
+        const uint32_t lt = s_tab[sym], lx = lt >> 16;
+        const uint32_t len = (lt & 0xffffu) + br.peek((int)lx);
         br.drop((int)lx);
         br.refill();
         v = __brev((uint32_t)br.bb) >> 17;
@@ -630,13 +652,12 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
         const uint32_t ds = dist_sym[(int)(v >> (15u - cl)) + (int)dist_adj[cl]];
         br.drop((int)cl);
         if (ds >= 30u) { err = 14; in_block = false; continue; }
-        const uint32_t dx = ds < 4u ? 0u : (ds - 2u) >> 1;
-        const uint32_t dbase = ds < 4u ? ds + 1u : ((2u + (ds & 1u)) << dx) + 1u;
-        const uint32_t dist = dbase + br.peek((int)dx);
+        const uint32_t dt = s_tab[32u + ds], dx = dt >> 16;
+        const uint32_t dist = (dt & 0xffffu) + br.peek((int)dx);
         br.drop((int)dx);
-        if (dist > opos) { err = 16; in_block = false; continue; }
-        if (opos + len > cap) { err = 15; in_block = false; continue; }
-        if (n_match >= LN_MATCH_CAP) { err = 19; in_block = false; continue; }
+        if (dist > opos || opos + len > cap || n_match >= LN_MATCH_CAP) {
+            err = dist > opos ? 16u : (opos + len > cap ? 15u : 19u); in_block = false; continue;
+        }
         my_matches[n_match++] = make_uint2(opos | len << 16, dist);     // the copy itself happens in bgzf_match_resolve_kernel
         opos += len;
     }
@@ -688,7 +709,7 @@ bgzf_match_resolve_kernel(const BgzfBlock* __restrict__ blocks, uint32_t n_block
 size_t bgzf_inflate_scratch_bytes(uint32_t n_blocks) { return (size_t)n_blocks * LN_MATCH_CAP * sizeof(uint2) + (size_t)n_blocks * 4 + 256; }
 
 static void launch_lanes(const uint8_t* comp, const BgzfBlock* bl, uint32_t n_blocks, uint8_t* out, uint32_t* status, void* scratch, cudaStream_t stream) {
-    constexpr int sh = 32 * LN_STRIDE;
+    constexpr int sh = LN_SHARED + LN_THREADS * LN_STRIDE;
     static bool attr = false;
     if (!attr) {
         attr = true;
@@ -696,7 +717,7 @@ static void launch_lanes(const uint8_t* comp, const BgzfBlock* bl, uint32_t n_bl
     }
     uint32_t* mcount = static_cast<uint32_t*>(scratch);
     uint2* mlist = reinterpret_cast<uint2*>(static_cast<uint8_t*>(scratch) + (((size_t)n_blocks * 4 + 255) & ~(size_t)255));
-    bgzf_inflate_lanes_kernel<<<(n_blocks + 31) / 32, 32, sh, stream>>>(comp, bl, n_blocks, out, status, mlist, mcount);
+    bgzf_inflate_lanes_kernel<<<(n_blocks + LN_THREADS - 1) / LN_THREADS, LN_THREADS, sh, stream>>>(comp, bl, n_blocks, out, status, mlist, mcount);
     bgzf_match_resolve_kernel<<<(n_blocks + MR_WARPS - 1) / MR_WARPS, MR_WARPS * 32, 0, stream>>>(bl, n_blocks, out, mlist, mcount);
 }
 

@@ -620,12 +620,9 @@ struct S5Emit {
     const ScanParams* prm; uint32_t* jstrand;                 // intron-motif mode: parameters + the alignment's running strand
     const int32_t* rspan;                                     // variant-region mode: [pos, endpos) of the alignment being walked
     __device__ __forceinline__ void push(const uint4& a, const uint4& b) const {
-        const uint32_t mask = __activemask();
-        const uint32_t lane = threadIdx.x & 31u;
-        const int leader = __ffs(mask) - 1;
-        uint32_t i = 0;
-        if ((int)lane == leader) i = atomicAdd(&sm.n_out, (uint32_t)__popc(mask));
-        i = __shfl_sync(mask, i, leader) + __popc(mask & ((1u << lane) - 1u));
+        // one shared-memory atomic per candidate: emit sites are divergent (and the variant-region loop has per-lane trip
+        // counts), where __activemask() does not promise that the lanes it names are converged at a following shuffle
+        const uint32_t i = atomicAdd(&sm.n_out, 1u);
         if (i < S5_OUT) {
             sm.out[2 * i] = a; sm.out[2 * i + 1] = b;
         } else {
