@@ -151,6 +151,19 @@ int         rtjx_run_regions(rtjx_t* h, const char* const* regions, size_t n_reg
 int64_t     rtjx_region_count(rtjx_t* h, size_t region);
 int64_t     rtjx_region_get(rtjx_t* h, size_t region, rtjx_junction* out, size_t cap);
 
+/* The rest of that caller's loop (cis_splice_effects_identifier.cc:292-299), on the tables of the last rtjx_run_regions:
+ * region i stands for variant i with the window [win_start[i], win_end[i]] (v1.cis_effect_start / cis_effect_end, both
+ * inclusive).  Every junction of region i whose start or end lies inside the window (:294-295) is inserted, regions in order
+ * and junctions in table order, into the reference's `set<Junction> unique_junctions_` and `map<Junction, set<variant>>
+ * junction_to_variant_`.  Both compare through the implicit Junction -> AnnotatedJunction conversion
+ * (junctions_annotator.h:155-177): contig name (std::string <), start, end — strand-blind — and the first insert wins.
+ * rtjx_unique_get returns the set in its iteration order (the record of the winning insert, `first_region` = its variant);
+ * rtjx_unique_regions(i) the variants of unique junction i in ascending order.  Counts are returned, negative = error. */
+int         rtjx_unique_junctions(rtjx_t* h, const uint32_t* win_start, const uint32_t* win_end, size_t n_regions);
+int64_t     rtjx_unique_count(rtjx_t* h);
+int64_t     rtjx_unique_get(rtjx_t* h, rtjx_junction* out, uint32_t* first_region, size_t cap);
+int64_t     rtjx_unique_regions(rtjx_t* h, size_t i, uint32_t* out, size_t cap);
+
 /* parse_alignment_into_junctions over a prepared batch (junctions_extractor.cc:377-497):
  * launches cigar_scan + junction_merge on `stream` (a cudaStream_t, NULL = default stream).
  * location = RTJX_LOC_HOST: arrays are host memory and are copied in; RTJX_LOC_DEVICE: the

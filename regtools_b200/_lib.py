@@ -97,6 +97,10 @@ SIGNATURES = {
     "rtjx_run_regions": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_size_t]),
     "rtjx_region_count": (C.c_int64, [C.c_void_p, C.c_size_t]),
     "rtjx_region_get": (C.c_int64, [C.c_void_p, C.c_size_t, C.POINTER(Junction), C.c_size_t]),
+    "rtjx_unique_junctions": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t]),
+    "rtjx_unique_count": (C.c_int64, [C.c_void_p]),
+    "rtjx_unique_get": (C.c_int64, [C.c_void_p, C.POINTER(Junction), C.POINTER(C.c_uint32), C.c_size_t]),
+    "rtjx_unique_regions": (C.c_int64, [C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t]),
     "rtjx_scan_batch": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int, C.c_void_p]),
     "rtjx_add": (C.c_int, [C.c_void_p, C.POINTER(Candidate), C.c_size_t]),
     "rtjx_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),

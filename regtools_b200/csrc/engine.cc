@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <unordered_map>
 
@@ -700,6 +701,57 @@ int64_t Engine::region_get(size_t i, rtjx_junction* out, size_t cap) {
     const std::vector<rtjx_junction>& t = region_tables_[i];
     if (out && cap) memcpy(out, t.data(), std::min(cap, t.size()) * sizeof(rtjx_junction));
     return (int64_t)t.size();
+}
+
+// ---- the second caller's unique-junction set ---------------------------------------------------------
+// cis_splice_effects_identifier.cc:288-299: for every variant, in order, the junctions of its region (get_all_junctions: sorted
+// by compare_junctions) whose start OR end lies inside the variant's window [cis_effect_start, cis_effect_end] (both bounds
+// inclusive, :294-295) are inserted into set<Junction> and map<Junction, set<variant>>.  Junction has no operator<: both
+// containers compare through the implicit conversion to AnnotatedJunction (junctions_annotator.h:155-177) — contig NAME,
+// start, end, strand-blind — and set::insert keeps the element that came first.
+int Engine::unique_build(const uint32_t* win_start, const uint32_t* win_end, size_t n) {
+    if (n != region_tables_.size()) return fail(RTJX_E_ARG, "one window per region of the last rtjx_run_regions call is needed");
+    if (n && (!win_start || !win_end)) return fail(RTJX_E_ARG, "null window arrays");
+    const std::vector<uint32_t> cr = contig_ranks(contigs_);
+    struct Key {
+        uint32_t crank, start, end;
+        bool operator<(const Key& o) const { return crank != o.crank ? crank < o.crank : (start != o.start ? start < o.start : end < o.end); }
+    };
+    std::map<Key, size_t> index;                 // -> position in first-insert order
+    std::vector<rtjx_junction> js; std::vector<uint32_t> first; std::vector<std::vector<uint32_t>> regs;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t cs = win_start[i], ce = win_end[i];
+        for (const rtjx_junction& j : region_tables_[i]) {
+            if (!((j.start >= cs && j.start <= ce) || (j.end <= ce && j.end >= cs))) continue;
+            const Key k{(uint32_t)j.tid < cr.size() ? cr[(size_t)j.tid] : 0x40000000u + (uint32_t)j.tid, j.start, j.end};
+            auto it = index.find(k);
+            if (it == index.end()) {
+                index.emplace(k, js.size());
+                js.push_back(j); first.push_back((uint32_t)i); regs.emplace_back(1, (uint32_t)i);
+            } else if (regs[it->second].back() != (uint32_t)i) {
+                regs[it->second].push_back((uint32_t)i);
+            }
+        }
+    }
+    unique_.clear(); unique_first_.clear(); unique_regions_.clear();
+    unique_.reserve(js.size());
+    for (const auto& kv : index) {               // set order
+        unique_.push_back(js[kv.second]); unique_first_.push_back(first[kv.second]); unique_regions_.push_back(std::move(regs[kv.second]));
+    }
+    return RTJX_OK;
+}
+int64_t Engine::unique_count() { return (int64_t)unique_.size(); }
+int64_t Engine::unique_get(rtjx_junction* out, uint32_t* first_region, size_t cap) {
+    const size_t m = std::min(cap, unique_.size());
+    if (out && m) memcpy(out, unique_.data(), m * sizeof(rtjx_junction));
+    if (first_region && m) memcpy(first_region, unique_first_.data(), m * sizeof(uint32_t));
+    return (int64_t)unique_.size();
+}
+int64_t Engine::unique_regions(size_t i, uint32_t* out, size_t cap) {
+    if (i >= unique_regions_.size()) return fail(RTJX_E_ARG, "unique junction index out of range");
+    const std::vector<uint32_t>& v = unique_regions_[i];
+    if (out && cap) memcpy(out, v.data(), std::min(cap, v.size()) * sizeof(uint32_t));
+    return (int64_t)v.size();
 }
 
 // ---- device inflate test hook ----------------------------------------------------------------------

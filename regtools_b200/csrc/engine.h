@@ -25,6 +25,11 @@ public:
     int run_regions(const char* const* regions, size_t n);
     int64_t region_count(size_t i);
     int64_t region_get(size_t i, rtjx_junction* out, size_t cap);
+    // cis_splice_effects_identifier.cc:292-299 on the tables of the last run_regions: the unique-junction set + junction -> variants
+    int unique_build(const uint32_t* win_start, const uint32_t* win_end, size_t n);
+    int64_t unique_count();
+    int64_t unique_get(rtjx_junction* out, uint32_t* first_region, size_t cap);
+    int64_t unique_regions(size_t i, uint32_t* out, size_t cap);
     int scan_batch(const rtjx_batch& b, int location, cudaStream_t stream);
     int add(const rtjx_candidate* c, size_t n);
     int finalize(cudaStream_t stream);
@@ -104,6 +109,9 @@ private:
     VariantRegions vr_{nullptr, nullptr, nullptr, 0, 0};
     std::vector<uint32_t> vr_orig_;             // sorted index -> caller's index
     std::vector<std::vector<rtjx_junction>> region_tables_;
+    std::vector<rtjx_junction> unique_;          // set<Junction> of the second caller, in its order (contig name, start, end)
+    std::vector<uint32_t> unique_first_;         // region (variant) whose insert won
+    std::vector<std::vector<uint32_t>> unique_regions_;   // junction_to_variant_: regions whose window holds the junction, ascending
     OutJunctionR* d_out_r_ = nullptr; uint32_t fin_r_cap_ = 0; void* d_ws_r_ = nullptr; size_t ws_r_cap_ = 0;
     OutJunctionR* h_final_r_ = nullptr; uint32_t h_final_r_cap_ = 0;
     int finalize_regions();

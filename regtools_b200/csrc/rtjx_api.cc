@@ -57,6 +57,10 @@ int rtjx_run(rtjx_t* h) { GUARD(h, h->e->run()) }
 int rtjx_run_regions(rtjx_t* h, const char* const* regions, size_t n) { GUARD(h, h->e->run_regions(regions, n)) }
 int64_t rtjx_region_count(rtjx_t* h, size_t region) { GUARD(h, h->e->region_count(region)) }
 int64_t rtjx_region_get(rtjx_t* h, size_t region, rtjx_junction* out, size_t cap) { GUARD(h, h->e->region_get(region, out, cap)) }
+int rtjx_unique_junctions(rtjx_t* h, const uint32_t* win_start, const uint32_t* win_end, size_t n_regions) { GUARD(h, h->e->unique_build(win_start, win_end, n_regions)) }
+int64_t rtjx_unique_count(rtjx_t* h) { GUARD(h, h->e->unique_count()) }
+int64_t rtjx_unique_get(rtjx_t* h, rtjx_junction* out, uint32_t* first_region, size_t cap) { GUARD(h, h->e->unique_get(out, first_region, cap)) }
+int64_t rtjx_unique_regions(rtjx_t* h, size_t i, uint32_t* out, size_t cap) { GUARD(h, h->e->unique_regions(i, out, cap)) }
 
 int rtjx_scan_batch(rtjx_t* h, const rtjx_batch* b, int location, void* stream) {
     if (!h) return RTJX_E_ARG;

@@ -10,7 +10,7 @@ import getopt
 import os
 import sys
 from dataclasses import dataclass
-from typing import List, Optional, Sequence
+from typing import Tuple, List, Optional, Sequence
 
 import numpy as np
 
@@ -284,6 +284,31 @@ class JunctionsExtractor:
                 self._check(L.lib.rtjx_region_get(h, i, t.ctypes.data_as(C.POINTER(L.Junction)), n))
             out.append(t)
         return out
+
+    def unique_junctions_in_windows(self, regions: Sequence[str], windows: Sequence[Tuple[int, int]]):
+        """The junction side of `cis-splice-effects identify`'s per-variant loop (cis_splice_effects_identifier.cc:288-299):
+        ``regions[i]`` / ``windows[i] = (cis_effect_start, cis_effect_end)`` describe variant i.  Returns
+        (table, first_region, variants): the reference's ``unique_junctions_`` set in its iteration order (ordered and deduplicated
+        by contig name, start, end — strand-blind, first insert wins, junctions_annotator.h:155-177), the variant whose insert
+        won, and for every unique junction the ascending list of variants whose window holds it (``junction_to_variant_``)."""
+        self.identify_junctions_in_regions(regions)
+        h = self._handle()
+        n = len(regions)
+        ws = (C.c_uint32 * max(n, 1))(*[int(w[0]) & 0xFFFFFFFF for w in windows])
+        we = (C.c_uint32 * max(n, 1))(*[int(w[1]) & 0xFFFFFFFF for w in windows])
+        self._check(L.lib.rtjx_unique_junctions(h, ws, we, n))
+        u = self._check(L.lib.rtjx_unique_count(h))
+        t = np.zeros(u, dtype=JUNCTION_DTYPE)
+        first = np.zeros(u, dtype=np.uint32)
+        if u:
+            self._check(L.lib.rtjx_unique_get(h, t.ctypes.data_as(C.POINTER(L.Junction)), first.ctypes.data_as(C.POINTER(C.c_uint32)), u))
+        variants = []
+        for i in range(u):
+            m = self._check(L.lib.rtjx_unique_regions(h, i, None, 0))
+            v = np.zeros(m, dtype=np.uint32)
+            self._check(L.lib.rtjx_unique_regions(h, i, v.ctypes.data_as(C.POINTER(C.c_uint32)), m))
+            variants.append(v.tolist())
+        return t, first, variants
 
     def get_new_junction_name(self) -> str:
         """get_new_junction_name (junctions_extractor.cc:152-157)."""

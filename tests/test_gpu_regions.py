@@ -110,3 +110,55 @@ def test_unmapped_flag_alignment_spans_one_base(tmp_path):
     regions = ["10:3459-603459", "10:1072-1072", "10:1073-1200", "10:3501-3501", "10:3502-3600", "10:603459-603459", "10:603460-700000", "10"]
     n, _ = _check(bam, regions, a=8, m=8)
     assert n == 3 + 1 + 1 + 2 + 1 + 1 + 0 + 4
+
+
+def _unique_lines(bam, regions, windows, strandness, anchor, M, contigs, **kw):
+    import regtools_b200 as rt
+    ex = rt.JunctionsExtractor.from_region(bam, ".", strandness, "XS", anchor, 70, M, **kw)
+    t, first, variants = ex.unique_junctions_in_windows(regions, windows)
+    ex.close()
+    return ["\t".join(map(str, [contigs[j["tid"]], j["start"], j["end"], "JUNC%08d" % j["name_index"], j["read_count"], chr(j["strand"]),
+                                j["thick_start"], j["thick_end"], ",".join(map(str, v))])) + "\n" for j, v in zip(t, variants)], first
+
+
+@pytest.mark.parametrize("strandness", [0, 1])
+def test_unique_junction_set_matches_the_reference_loop(strandness, golden_dir, tmp_path):
+    """SURVEY 8(f)-2, the rest of the row: the window filter and the strand-blind, first-insert-wins `set<Junction>` of
+    cis_splice_effects_identifier.cc:292-299 (ordering through the implicit Junction -> AnnotatedJunction conversion,
+    junctions_annotator.h:155-177) against oracle/_ref/regtools_ref_cse — that very loop compiled around the unmodified
+    reference classes.  Overlapping and repeated regions make several variants insert the same junction; mixed XS tags make
+    the same (start, end) appear with different strands inside one region."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "regtools_ref_cse")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref/regtools_ref_cse not built (needs the reference tree)")
+    rng = np.random.default_rng(100 + strandness)
+    for bam_name, contigs, lens in (("kat.bam", ["1", "10", "2"], {"1": 20000, "10": 8000, "2": 5010000}),
+                                    ("synth.bam", ["1", "10", "2"], {"1": 3000000, "10": 2000000, "2": 2500000})):
+        bam = os.path.join(golden_dir, "kat", bam_name)
+        regions, windows = [], []
+        for _ in range(120):
+            c = contigs[int(rng.integers(0, 3))]
+            centre = int(rng.integers(1, lens[c]))
+            w = int(rng.choice([50, 500, 5000, 60000]))
+            a, b = max(1, centre - w), centre + w
+            regions.append(f"{c}:{a}-{b}")
+            # cis_effect window: usually the region itself, sometimes narrower / shifted / empty / huge
+            r = rng.random()
+            if r < 0.6:
+                windows.append((a, b))
+            elif r < 0.8:
+                windows.append((centre - w // 4, centre + w // 4))
+            elif r < 0.9:
+                windows.append((b, a))
+            else:
+                windows.append((0, 4000000000))
+        regions += regions[:10]
+        windows += windows[5:15]
+        tsv = tmp_path / "regions.tsv"
+        tsv.write_text("".join(f"{r}\t{max(ws, 0)}\t{max(we, 0)}\n" for r, (ws, we) in zip(regions, windows)))
+        windows = [(max(ws, 0), max(we, 0)) for ws, we in windows]
+        want = subprocess.run([ref, bam, str(strandness), "XS", "8", "70", "500000", str(tsv)], capture_output=True, text=True)
+        assert want.returncode == 0, want.stderr
+        got, first = _unique_lines(bam, regions, windows, strandness, 8, 500000, contigs)
+        assert "".join(got) == want.stdout
+        assert len(got) > 20 and all(0 <= f < len(regions) for f in first)
