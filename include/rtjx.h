@@ -63,12 +63,8 @@ typedef struct {
     int32_t     shard_world;      /* number of shards, default 1                               */
     int32_t     inflate_mode;     /* 0 auto, 1 host zlib workers, 2 device inflate kernel      */
     int32_t     profile;          /* 1: bracket every kernel with CUDA events (rtjx_get_stats) */
-    int32_t     scan_variant;     /* 0 = default (5: cigar_scan -> candidate list -> junction_merge);
-                                     6 = fused cigar_scan that aggregates per tile and updates the
-                                     junction table itself (needs rtjx_batch.n_junction_ops);
-                                     7 = gather variant (stages cig_off + CIGAR slab only; A/B build)  */
-    int32_t     scan_cfg;         /* tile configuration of the variant, 0 = production (A/B knob)     */
-    uint32_t    scan_debug;       /* developer switches for A/B timing; results are WRONG if non-zero */
+    int32_t     scan_variant;     /* cigar_scan kernel: 0 / 5 = block per tile (default), 8 = warp-pipelined persistent   */
+    int32_t     scan_cfg;         /* configuration of the warp-pipelined kernel (ring depth / warps per SM), 0 = default */
     const char* barcode_tag;      /* barcode_tag_ (junctions_extractor.h:181), NULL = "CB"; the reference has no flag for it */
 } rtjx_params;
 

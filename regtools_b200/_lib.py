@@ -33,7 +33,7 @@ class Params(C.Structure):
         ("batch_reads", C.c_uint32), ("table_log2", C.c_uint32),
         ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
         ("inflate_mode", C.c_int32), ("profile", C.c_int32),
-        ("scan_variant", C.c_int32), ("scan_cfg", C.c_int32), ("scan_debug", C.c_uint32),
+        ("scan_variant", C.c_int32), ("scan_cfg", C.c_int32),
         ("barcode_tag", C.c_char_p),
     ]
 

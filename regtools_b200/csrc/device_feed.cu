@@ -164,7 +164,12 @@ __device__ __forceinline__ bool plausible_one(const uint8_t* data, int64_t o, in
     const int32_t mtid = (int32_t)ld_u32_any(r + 24), mpos = (int32_t)ld_u32_any(r + 28);
     if (mtid < -1 || mtid >= n_ref || mpos < -1) return false;
     if (!record_ok(r + 4, bs)) return false;
-    const uint32_t l_qname = r[12], n_cigar = ld_u16_any(r + 16);
+    const uint32_t l_qname = r[12], n_cigar = ld_u16_any(r + 16), flag = ld_u16_any(r + 18);
+    // a start guessed one to three bytes early reads every field shifted: it survives the range checks above when the true
+    // fields are small numbers (refID 0, short template lengths), so the fields that cannot be small by accident are checked
+    // too — a non-empty printable read name (SAM 1.4: [!-?A-~]{1,254}), no undefined flag bits, and below a CIGAR whose query
+    // length equals l_seq (seen before these checks: ~1e-3 false starts per BGZF block, each one a declined run)
+    if (l_qname < 2u || (flag & 0xf000u)) return false;
     // what the fixed fields account for must leave a sane amount of aux data: a start guessed a byte or two early reads a
     // block_size that is the true one shifted left, i.e. megabytes too large (seen at a rate of ~1e-3 per BGZF block)
     const int32_t l_qseq = (int32_t)ld_u32_any(r + 20);
@@ -177,15 +182,25 @@ __device__ __forceinline__ bool plausible_one(const uint8_t* data, int64_t o, in
         const uint32_t ch = data[o + 36 + c];
         if (ch < 33u || ch > 126u) return false;
     }
-    if (n_cigar && name_end + 4 <= data_len && (ld_u32_any(data + name_end) & 0xfu) > 9u) return false;
+    if (n_cigar && n_cigar <= 16u && l_qseq > 0 && !(flag & 4u) && name_end + 4ll * n_cigar <= data_len) {
+        uint32_t qlen = 0;
+        for (uint32_t c = 0; c < n_cigar; ++c) {
+            const uint32_t w = ld_u32_any(data + name_end + 4 * c), op = w & 0xfu;
+            if (op > 9u) return false;
+            if ((0x193u >> op) & 1u) qlen += w >> 4;              // M, I, S, =, X consume the query
+        }
+        if (qlen != (uint32_t)l_qseq) return false;
+    } else if (n_cigar && name_end + 4 <= data_len && (ld_u32_any(data + name_end) & 0xfu) > 9u) return false;
     *next = o + 4 + (int64_t)bs;
     return true;
 }
 __device__ __forceinline__ bool plausible_record(const uint8_t* data, int64_t o, int64_t data_len, int32_t n_ref) {
-    int64_t nxt = 0, nxt2 = 0;
+    int64_t nxt = 0, nxt2 = 0, nxt3 = 0;
     if (!plausible_one(data, o, data_len, n_ref, &nxt)) return false;
     if (nxt + 36 > data_len) return true;                         // the next record lies (partly) in the next chunk
-    return plausible_one(data, nxt, data_len, n_ref, &nxt2);
+    if (!plausible_one(data, nxt, data_len, n_ref, &nxt2)) return false;
+    if (nxt2 + 36 > data_len) return true;
+    return plausible_one(data, nxt2, data_len, n_ref, &nxt3);
 }
 
 constexpr int SEED_WARPS = 8;

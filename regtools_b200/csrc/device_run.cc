@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <unordered_map>
 #include <unistd.h>
 
 namespace rtjx {
@@ -98,8 +99,11 @@ struct Engine::DeviceFeed {
     // SoA accumulator: the alignments extracted since the last cigar_scan
     int32_t* a_tid = nullptr; int32_t* a_pos = nullptr; uint32_t* a_meta = nullptr; uint32_t* a_off = nullptr; size_t acc_rec_cap = 0;
     uint32_t* a_cigar = nullptr; size_t acc_ops_cap = 0;
-    // compressed file staged in HBM (rtjx_stage_bam)
+    // compressed file staged in HBM (rtjx_stage_bam); the BGZF header walk of every chunk of it is remembered (the file does
+    // not change under a staged handle), so later runs do no host pass over the file at all
     uint8_t* d_file = nullptr; size_t file_bytes = 0;
+    struct ChunkScan { std::vector<BgzfBlockInfo> blocks; uint64_t c_end; uint64_t end_coff; size_t got; bool stop, partial, untrusted; };
+    std::unordered_map<uint64_t, ChunkScan> scans;
 
     ~DeviceFeed() {
         for (int i = 0; i < NSTAGE; ++i) { cached_host_free(h_comp[i]); if (comp_free[i]) cudaEventDestroy(comp_free[i]); }
@@ -142,7 +146,7 @@ int Engine::stage_file() {
     if (!dfeed_) dfeed_.reset(new DeviceFeed());
     DeviceFeed& F = *dfeed_;
     CKD(cudaDeviceSynchronize());
-    cached_dev_free(F.d_file); F.d_file = nullptr; F.file_bytes = 0;
+    cached_dev_free(F.d_file); F.d_file = nullptr; F.file_bytes = 0; F.scans.clear();
     CKD(cached_dev_malloc(&F.d_file, bam.size() + 256));
     const size_t CH = 64u << 20;
     uint8_t* h = nullptr;
@@ -368,8 +372,11 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                 if (k < nb && G.coffs[k] == ec) limit = (int64_t)G.desc[k].out_off + (int64_t)eu;
                 else if (k == nb && eu == 0 && G.coffs.back() < ec) limit = (int64_t)G.out_total;
             }
-            // ---- device buffers of the slot and the accumulator
+            // ---- device buffers of the slot and the accumulator.  A range's first group is a small one: its slot's buffers are
+            // sized for the full-size group that slot will see next, so nothing is reallocated (and no stream drained) mid-run
             const double ta0 = now_s();
+            const double grow = std::min(8.0, std::max(1.0, 1.05 * (double)(GROUP + STAGE) / (double)std::max<uint64_t>(G.comp_bytes, 1)));
+            auto sized = [&](size_t need) -> size_t { return (size_t)((double)need * grow) + 64; };
             const uint64_t cig_upper = (DeviceFeed::HEAD + G.out_total) / 32 + 4096;   // > 12.5 % of the bytes being CIGAR -> capacity flag
             if (acc_rec_upper + cap_total + 8 > F.acc_rec_cap || acc_ops_upper + cig_upper + 8 > F.acc_ops_cap) {
                 // the accumulator is scanned (and emptied) before it would overflow; it only ever grows while empty
@@ -396,7 +403,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             if (DeviceFeed::HEAD + G.out_total + 64 > S.infl_cap) {
                 if (S.d_infl) drain();
                 cached_dev_free(S.d_infl); S.d_infl = nullptr;
-                const size_t want = DeviceFeed::HEAD + G.out_total + 64;
+                const size_t want = DeviceFeed::HEAD + sized(G.out_total);
                 const size_t cap = want + want / 8;
                 CKD(cached_dev_malloc(&S.d_infl, cap + 256));
                 S.infl_cap = cap;
@@ -404,21 +411,21 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             if ((size_t)nb + 2 > S.desc_cap) {
                 if (S.d_desc) drain();
                 cached_dev_free(S.d_desc); cached_dev_free(S.d_status); S.d_desc = nullptr; S.d_status = nullptr;
-                S.desc_cap = (size_t)nb * 2 + 1024;
+                S.desc_cap = sized((size_t)nb) + 1024;
                 CKD(cached_dev_malloc(&S.d_desc, S.desc_cap * sizeof(BgzfBlockDesc))); CKD(cached_dev_malloc(&S.d_status, S.desc_cap * 4));
             }
-            CKD(grow_dev(&S.d_scratch, &S.scratch_cap, bgzf_inflate_scratch_bytes(nb), 1));
+            if (bgzf_inflate_scratch_bytes(nb) > S.scratch_cap) CKD(grow_dev(&S.d_scratch, &S.scratch_cap, bgzf_inflate_scratch_bytes((uint32_t)sized(nb)), 1));
             if ((size_t)n_seg + 2 > S.seed_cap) {
                 if (S.d_seeds) drain();
                 cached_dev_free(S.d_seeds); cached_dev_free(S.d_segbase); cached_dev_free(S.d_segcnt); cached_dev_free(S.d_segscan);
                 S.d_seeds = nullptr; S.d_segbase = S.d_segcnt = S.d_segscan = nullptr;
-                S.seed_cap = (size_t)n_seg * 2 + 1024;
+                S.seed_cap = sized((size_t)n_seg) + 1024;
                 CKD(cached_dev_malloc(&S.d_seeds, S.seed_cap * 8)); CKD(cached_dev_malloc(&S.d_segbase, S.seed_cap * 4));
                 CKD(cached_dev_malloc(&S.d_segcnt, S.seed_cap * 4)); CKD(cached_dev_malloc(&S.d_segscan, S.seed_cap * 4));
             }
             if ((size_t)cap_total + 8 > S.rec_cap) {
                 if (S.d_recoff) drain();
-                const size_t cap = (size_t)cap_total + cap_total / 8 + 1024;
+                const size_t cap = sized((size_t)cap_total) + 1024;
                 cached_dev_free(S.d_recoff); cached_dev_free(S.d_dense); cached_dev_free(S.d_ncig); cached_dev_free(S.d_ncigscan); cached_dev_free(S.d_ws);
                 S.d_recoff = S.d_dense = nullptr; S.d_ncig = S.d_ncigscan = nullptr; S.d_ws = nullptr;
                 S.ws_cap = feed_scan_workspace_bytes((uint32_t)cap + 8);
@@ -494,7 +501,20 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                 src = F.h_comp[buf];
             }
             const double ts0 = now_s();
-            const uint64_t c_end = scan_bgzf_blocks_mem(src, got_bytes, c_first, end_coff, &blocks, &stop, &partial, &untrusted);
+            uint64_t c_end;
+            if (resident) {
+                auto it = F.scans.find(c_first);
+                if (it == F.scans.end() || it->second.end_coff != end_coff || it->second.got != got_bytes) {
+                    DeviceFeed::ChunkScan cs;
+                    cs.c_end = scan_bgzf_blocks_mem(src, got_bytes, c_first, end_coff, &cs.blocks, &cs.stop, &cs.partial, &cs.untrusted);
+                    cs.end_coff = end_coff; cs.got = got_bytes;
+                    it = F.scans.insert_or_assign(c_first, std::move(cs)).first;
+                }
+                blocks = it->second.blocks; stop = it->second.stop; partial = it->second.partial; untrusted = it->second.untrusted;
+                c_end = it->second.c_end;
+            } else {
+                c_end = scan_bgzf_blocks_mem(src, got_bytes, c_first, end_coff, &blocks, &stop, &partial, &untrusted);
+            }
             t_scanhdr += now_s() - ts0;
             coff = c_end;
             if (untrusted) { declined = true; break; }     // a trailer that cannot be taken at its word: the host feeder decides

@@ -68,7 +68,7 @@ Engine::~Engine() {
         cached_dev_free(d_out_r_); cached_dev_free(d_ws_r_); cached_host_free(h_final_r_);
         cached_dev_free(d_fold_table_); cached_dev_free(d_fold_list_); cached_dev_free(d_fold_counters_);
         cached_dev_free(d_counters_); cached_host_free(h_counters_);
-        cached_dev_free(d_table_); cached_dev_free(d_spill_); cached_dev_free(d_cands_); cached_dev_free(d_tile_off_); cached_dev_free(d_regions_); cached_dev_free(d_region_cnt_);
+        cached_dev_free(d_table_); cached_dev_free(d_spill_); cached_dev_free(d_cands_);
         cached_dev_free(d_out_); cached_dev_free(d_ws_); cached_dev_free(d_rank_); cached_host_free(h_final_); cached_dev_free(d_slot_list_);
         if (stream_) cudaStreamDestroy(stream_);
         if (copy_stream_) cudaStreamDestroy(copy_stream_);
@@ -79,15 +79,13 @@ ScanParams Engine::scan_params() const {
     ScanParams s;
     s.strandness = prm_.strandness; s.min_anchor = prm_.min_anchor;
     s.min_intron = prm_.min_intron; s.max_intron = prm_.max_intron;
-    static const uint32_t dbg = getenv("RTJX_SCAN_DEBUG") ? (uint32_t)atoi(getenv("RTJX_SCAN_DEBUG")) : 0u;
     static const int env_variant = getenv("RTJX_SCAN_VARIANT") ? atoi(getenv("RTJX_SCAN_VARIANT")) : 0;
     static const int env_cfg = getenv("RTJX_SCAN_CFG") ? atoi(getenv("RTJX_SCAN_CFG")) : 0;
-    s.debug = prm_.scan_debug ? prm_.scan_debug : dbg;
     s.variant = prm_.scan_variant ? prm_.scan_variant : (env_variant ? env_variant : 5);
+    if (s.variant != 8) s.variant = 5;
     s.cfg = prm_.scan_cfg ? prm_.scan_cfg : env_cfg;
     s.genome = d_genome_; s.g_off = d_g_off_; s.g_len = d_g_len_; s.g_n = d_genome_ ? g_n_ : 0u;
     s.vr = vr_;
-    if ((d_genome_ || vr_.n || bc_mode_) && s.variant != 8) { s.variant = 5; s.cfg = 0; }   // the intron-motif, variant-region and barcode modes live in the two tiled scan kernels only
     return s;
 }
 
@@ -221,35 +219,22 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
     const bool known = cand_bound != 0;
     if ((rc = ensure_genome())) return rc;
     const ScanParams sp = scan_params();
+    if (sp.vr.n && ((reinterpret_cast<uintptr_t>(v.tid) | reinterpret_cast<uintptr_t>(v.pos) | reinterpret_cast<uintptr_t>(v.meta) |
+                     reinterpret_cast<uintptr_t>(v.cig_off) | reinterpret_cast<uintptr_t>(v.cigar)) & 15u))
+        return fail(RTJX_E_STATE, "internal: variant-region batches must be 16-byte aligned");
     if (sp.genome && ((reinterpret_cast<uintptr_t>(v.tid) | reinterpret_cast<uintptr_t>(v.pos) | reinterpret_cast<uintptr_t>(v.meta) |
                        reinterpret_cast<uintptr_t>(v.cig_off) | reinterpret_cast<uintptr_t>(v.cigar)) & 15u))
         return fail(RTJX_E_ARG, "device batch arrays must be 16-byte aligned when a FASTA is given");
     if (v.bc && ((reinterpret_cast<uintptr_t>(v.tid) | reinterpret_cast<uintptr_t>(v.pos) | reinterpret_cast<uintptr_t>(v.meta) |
                   reinterpret_cast<uintptr_t>(v.cig_off) | reinterpret_cast<uintptr_t>(v.cigar)) & 15u))
         return fail(RTJX_E_STATE, "internal: -b batches must be 16-byte aligned (only the tiled scan kernel knows barcodes)");
-    if (sp.variant == 6 && known && ((reinterpret_cast<uintptr_t>(v.tid) | reinterpret_cast<uintptr_t>(v.pos) |
-                                      reinterpret_cast<uintptr_t>(v.meta) | reinterpret_cast<uintptr_t>(v.cig_off) |
-                                      reinterpret_cast<uintptr_t>(v.cigar)) & 15u) == 0) {
-        // fused path: one kernel walks the CIGARs and updates the junction table; no candidate list
-        if ((rc = ensure_table(cand_bound, stream))) return rc;
-        ProfEv pe{nullptr, nullptr, nullptr};
-        if (prm_.profile) { pe.a = get_event(); pe.b = get_event(); pe.c = get_event(); cudaEventRecord(pe.a, stream); }
-        launch_cigar_scan_fused(v, sp, table_ref(), d_spill_, spill_cap_, d_counters_, stream);
-        if (prm_.profile) { cudaEventRecord(pe.b, stream); cudaEventRecord(pe.c, stream); prof_pending_.push_back(pe); }
-        CK(cudaGetLastError());
-        stats_.kernel_launches += v.n_reads ? 1 : 0;
-        stats_.reads += v.n_reads; stats_.cigar_ops += v.n_ops; stats_.batches++;
-        dirty_ = true; finalized_ = false;
-        if (prof_pending_.size() > 4096) resolve_profile_events();
-        return RTJX_OK;
-    }
     if (sp.vr.n) {
         // variant-region mode: an alignment yields one candidate per region it belongs to, so the candidate count is only
         // known after the scan: scan, read the count back, grow and re-scan if the buffer was too small, then merge
         if ((rc = ensure_cands(std::max(std::max(cand_bound, v.n_ops / 4u) * 2u, 1u << 16) + cigar_scan_cand_slack()))) return rc;
         for (int attempt = 0;; ++attempt) {
             CK(cudaMemsetAsync(d_counters_ + CTR_NCAND, 0, 2 * sizeof(uint32_t), stream));       // NCAND + CAND_OVERFLOW
-            launch_cigar_scan(v, sp, d_cands_, cand_cap_, d_counters_, nullptr, CandRegions{nullptr, nullptr, 0, 0}, stream);
+            launch_cigar_scan(v, sp, d_cands_, cand_cap_, d_counters_, stream);
             CK(cudaMemcpyAsync(h_counters_, d_counters_, CTR_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
             CK(cudaStreamSynchronize(stream));
             stats_.kernel_launches++;
@@ -263,8 +248,7 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
         unique_upper_ = h_counters_[CTR_NUNIQUE];
         if (n_cand) {
             if ((rc = ensure_table(n_cand, stream))) return rc;
-            launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, n_cand, CandRegions{nullptr, nullptr, 0, 0}, sp, table_ref(),
-                                  d_spill_, spill_cap_, d_counters_, stream);
+            launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, n_cand, sp, table_ref(), d_spill_, spill_cap_, d_counters_, stream);
             stats_.kernel_launches++;
         }
         CK(cudaGetLastError());
@@ -277,41 +261,16 @@ int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaSt
     if ((rc = ensure_cands((known ? cand_bound : std::max(v.n_ops, 1u)) + slack))) return rc;
     if (known && (rc = ensure_table(cand_bound, stream))) return rc;
     CK(cudaMemsetAsync(d_counters_ + CTR_NCAND, 0, sizeof(uint32_t), stream));
-    CK(cudaMemsetAsync(d_counters_ + CTR_NREGION, 0, sizeof(uint32_t), stream));
     ProfEv pe{nullptr, nullptr, nullptr};
     if (prm_.profile) { pe.a = get_event(); pe.b = get_event(); pe.c = get_event(); cudaEventRecord(pe.a, stream); }
-    {
-        const uint32_t need = cigar_scan_tiles(v.n_reads) + 2;
-        if (need > tile_off_cap_) {
-            CK(cudaStreamSynchronize(stream));
-            cached_dev_free(d_tile_off_); d_tile_off_ = nullptr;
-            tile_off_cap_ = need + need / 4 + 1024;
-            CK(cached_dev_malloc(&d_tile_off_, (size_t)tile_off_cap_ * 4));
-        }
-    }
-    CandRegions rgn{nullptr, nullptr, 0, 0};
-    {
-        uint32_t nr = 0, rcap = 0;
-        cigar_scan_region_layout(v.n_reads, &nr, &rcap);
-        if (nr && !v.bc) {
-            if ((size_t)nr * rcap > regions_cap_ || nr > region_cnt_cap_) {
-                CK(cudaStreamSynchronize(stream));
-                cached_dev_free(d_regions_); cached_dev_free(d_region_cnt_); d_regions_ = nullptr; d_region_cnt_ = nullptr;
-                regions_cap_ = (size_t)nr * rcap + (size_t)nr * rcap / 8; region_cnt_cap_ = nr + nr / 8 + 64;
-                CK(cached_dev_malloc(&d_regions_, regions_cap_ * sizeof(Cand)));
-                CK(cached_dev_malloc(&d_region_cnt_, region_cnt_cap_ * sizeof(uint32_t)));
-            }
-            rgn = CandRegions{d_regions_, d_region_cnt_, nr, rcap};
-        }
-    }
-    launch_cigar_scan(v, scan_params(), d_cands_, cand_cap_, d_counters_, d_tile_off_, rgn, stream);
+    launch_cigar_scan(v, sp, d_cands_, cand_cap_, d_counters_, stream);
     if (prm_.profile) cudaEventRecord(pe.b, stream);
     if (!known) {
         if ((rc = sync_counters(stream))) return rc;     // also tightens unique_upper_
-        cand_bound = h_counters_[CTR_NCAND] + h_counters_[CTR_NREGION];
+        cand_bound = h_counters_[CTR_NCAND];
         if ((rc = ensure_table(std::max(cand_bound, 1u), stream))) return rc;
     }
-    launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, known ? cand_bound + slack : cand_bound, rgn, scan_params(), table_ref(),
+    launch_junction_merge(d_cands_, d_counters_ + CTR_NCAND, known ? cand_bound + slack : cand_bound, sp, table_ref(),
                           d_spill_, spill_cap_, d_counters_, stream);
     if (prm_.profile) { cudaEventRecord(pe.c, stream); prof_pending_.push_back(pe); }
     CK(cudaGetLastError());
@@ -413,8 +372,7 @@ int Engine::add(const rtjx_candidate* c, size_t n) {
         if ((rc = ensure_cands((uint32_t)m))) return rc;
         if ((rc = ensure_table((uint32_t)m, stream_))) return rc;
         CK(cudaMemcpyAsync(d_cands_, h.data(), m * sizeof(Cand), cudaMemcpyHostToDevice, stream_));
-        launch_junction_merge(d_cands_, nullptr, (uint32_t)m, CandRegions{nullptr, nullptr, 0, 0}, scan_params(), table_ref(), d_spill_, spill_cap_,
-                              d_counters_, stream_);
+        launch_junction_merge(d_cands_, nullptr, (uint32_t)m, scan_params(), table_ref(), d_spill_, spill_cap_, d_counters_, stream_);
         CK(cudaStreamSynchronize(stream_));
         add_ord_ += m; stats_.kernel_launches++; stats_.h2d_bytes += m * sizeof(Cand);
     }

@@ -91,8 +91,6 @@ private:
     TableRef table_ref() const { return TableRef{d_table_, table_slots_ - 1, d_slot_list_, table_slots_}; }
     Slot* d_spill_ = nullptr; uint32_t spill_cap_ = 0;
     Cand* d_cands_ = nullptr; uint32_t cand_cap_ = 0;
-    Cand* d_regions_ = nullptr; uint32_t* d_region_cnt_ = nullptr; size_t regions_cap_ = 0, region_cnt_cap_ = 0;   // per-tile candidate regions
-    uint32_t* d_tile_off_ = nullptr; uint32_t tile_off_cap_ = 0;   // per-tile CIGAR offsets (cigar_scan pre-pass)
     uint64_t unique_upper_ = 0;                 // host-side upper bound of occupied slots
     uint64_t add_ord_ = 0;                      // ordinal of the next rtjx_add candidate
     bool dirty_ = false;                        // device table changed since the last finalize

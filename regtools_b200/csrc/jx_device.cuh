@@ -62,8 +62,7 @@ struct VariantRegions {
 struct ScanParams {
     int32_t  strandness;          // 0 XS, 1 RF, 2/3 FR
     uint32_t min_anchor, min_intron, max_intron;
-    uint32_t debug;               // developer switches for A/B measurements (0 in production)
-    int32_t  variant;             // cigar_scan variant: 8 = warp-pipelined persistent scan -> candidates -> junction_merge (default), 5 = block per tile, 6 = fused scan + table update
+    int32_t  variant;             // cigar_scan kernel: 5 = block per tile (default), 8 = warp-pipelined persistent
     int32_t  cfg;                 // tile configuration of the variant (0 = production)
     // intron-motif strand mode (a FASTA was given): the genome as one byte per base in HBM.  NULL = off.
     const uint8_t*            genome;
@@ -87,18 +86,6 @@ struct BatchView {
     const uint32_t* bc = nullptr;
 };
 
-// Per-tile candidate regions: cigar_scan writes the first round of every tile into a fixed region of
-// `cap` candidates (no global reservation, so the block never waits for an atomic round trip); later rounds
-// of dense tiles and staging overflow go to the dense overflow list.  junction_merge reads both.
-struct CandRegions {
-    Cand*     base;               // n_regions * cap candidates; NULL = regions not in use
-    uint32_t* cnt;                // candidates stored in each region
-    uint32_t  n_regions;
-    uint32_t  cap;
-};
-// Layout the scan kernel will use for a batch of n_reads alignments (n_regions = number of tiles).
-void cigar_scan_region_layout(uint32_t n_reads, uint32_t* n_regions, uint32_t* cap);
-
 // The device-wide junction table as the kernels see it.
 struct TableRef {
     Slot*     slots;
@@ -108,23 +95,14 @@ struct TableRef {
 };
 
 // Launchers (kernels.cu).  All are asynchronous on `stream`.
-// tile_off_scratch: cigar_scan_tiles(n_reads) + 1 words of device scratch for the per-tile CIGAR offsets (may be NULL)
-uint32_t cigar_scan_tiles(uint32_t n_reads);
-// Candidate slots cigar_scan may reserve beyond the N ops of a batch (chunked reservation, see the pipelined kernel):
-// size the candidate buffer, and junction_merge's bound, as N ops + this.
+// Candidate slots cigar_scan may reserve beyond the N ops of a batch (the warp-pipelined kernel reserves in chunks and pads
+// the tail of every warp's last chunk with tid = -1 entries): size the candidate buffer, and junction_merge's bound, as
+// N ops + this.
 uint32_t cigar_scan_cand_slack();
 void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
-                       uint32_t* d_counters /* [0]=n_cand, [1]=overflowed */, uint32_t* tile_off_scratch,
-                       const CandRegions& regions, cudaStream_t stream);
-// Fused path (variant 6): CIGAR walk, junction_qc and the per-tile pre-aggregation happen in one kernel that upserts
-// straight into the junction table; no candidate ever travels through HBM.  The caller must have sized
-// the table for the batch (load <= 0.5 with every N op a new key).  Returns false when the batch cannot take this path
-// (arrays not 16-byte aligned): use launch_cigar_scan + launch_junction_merge then.
-bool launch_cigar_scan_fused(const BatchView& b, const ScanParams& p, const TableRef& tb, Slot* spill, uint32_t spill_cap,
-                             uint32_t* d_counters, cudaStream_t stream);
-void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound, const CandRegions& regions,
-                           const ScanParams& p, const TableRef& tb, Slot* spill, uint32_t spill_cap,
-                           uint32_t* d_counters /* [2]=n_unique,[3]=n_spill */, cudaStream_t stream);
+                       uint32_t* d_counters /* [0]=n_cand, [1]=overflowed */, cudaStream_t stream);
+void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound, const ScanParams& p, const TableRef& tb,
+                           Slot* spill, uint32_t spill_cap, uint32_t* d_counters /* [2]=n_unique,[3]=n_spill */, cudaStream_t stream);
 void launch_table_rehash(const Slot* old_table, uint32_t old_slots, const TableRef& tb, uint32_t* d_counters,
                          cudaStream_t stream);
 void launch_table_clear(const TableRef& tb, const uint32_t* d_n_unique, uint32_t n_bound, cudaStream_t stream);
@@ -192,7 +170,7 @@ void launch_feed_finish(const uint8_t* data, int64_t data_len, uint8_t* next_dat
                         uint32_t n_seg, const uint32_t* ncig_scan, FeedState* state, cudaStream_t stream);
 
 // counters layout in d_counters (uint32 each)
-enum { CTR_NCAND = 0, CTR_CAND_OVERFLOW = 1, CTR_NUNIQUE = 2, CTR_NSPILL = 3, CTR_NOUT = 4, CTR_NREGION = 5 /* candidates in regions */,
+enum { CTR_NCAND = 0, CTR_CAND_OVERFLOW = 1, CTR_NUNIQUE = 2, CTR_NSPILL = 3, CTR_NOUT = 4, CTR_UNUSED5 = 5,
        CTR_TOTAL_CAND64 = 6 /* 64-bit, two words */, CTR_GENOME_MISS = 8 /* 1 + tid of a contig the FASTA lacks */,
        CTR_GENOME_MISS_POS = 9 /* start of one such junction */, CTR_COUNT = 10 };
 

@@ -10,6 +10,9 @@
 // alignments is a SoA slab in HBM (16 B per read + 4 B per CIGAR op) streamed once with coalesced
 // 128-bit loads, and the map is a device-wide open-addressed hash updated with atomics after a
 // shared-memory pre-aggregation per block.  Integer only; HBM-bound; no tensor cores.
+// Two cigar_scan kernels are kept: the block-per-tile kernel (default) and the warp-pipelined persistent kernel (opt-in,
+// rtjx_params.scan_variant = 8); the round-1 A/B builds (variants 1, 4, 6, 7 and the probe kernels) are gone — their
+// measurements live in profiles/r1_scan_ab.md.
 #include "jx_device.cuh"
 #include <cub/device/device_merge_sort.cuh>
 #include <cstdlib>
@@ -107,258 +110,7 @@ __device__ __noinline__ uint32_t motif_strand(const ScanParams& p, int32_t tid, 
     return '?';
 }
 
-// ------------------------------------------------------------------------------------------------
-// cigar_scan
-// ------------------------------------------------------------------------------------------------
-// One block = one tile of SCAN_TILE consecutive alignments.  Thread t owns alignments
-// base + t + j*SCAN_THREADS (j < SCAN_RPT): every metadata load of a warp is one fully coalesced
-// 128-byte request, and all 4*SCAN_RPT loads of a thread are issued before the first use.  The
-// tile's CIGAR ops are one contiguous slab of the `cigar` array; it is staged into shared memory
-// with 128-bit streaming loads and walked from there.  Candidates are staged in shared memory and
-// flushed with one global atomicAdd per block and coalesced 128-bit stores.
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_RPT     = 4;
-constexpr int SCAN_TILE    = SCAN_THREADS * SCAN_RPT;   // 1024 alignments
-constexpr int SCAN_SLAB    = 6144;                      // CIGAR words staged per tile (24 KB)
-constexpr int SCAN_STAGE   = 512;                       // candidates staged per tile (16 KB)
-
-struct ScanSmem {
-    uint32_t slab[SCAN_SLAB];
-    uint4    stage[SCAN_STAGE * 2];
-    uint32_t n_stage;
-    uint32_t flush_base;
-};
-
-__device__ __forceinline__ void scan_emit(ScanSmem& sm, Cand* __restrict__ out, uint32_t cap, uint32_t* counters,
-                                          uint32_t start, uint32_t end, uint32_t left, uint32_t right,
-                                          uint64_t ord, int32_t tid, uint32_t strand) {
-    uint4 a = make_uint4(start, end, start - left, end + right);
-    uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
-    uint32_t i = atomicAdd(&sm.n_stage, 1u);
-    if (i < SCAN_STAGE) {
-        sm.stage[2 * i] = a;
-        sm.stage[2 * i + 1] = b;
-    } else {                                   // tile denser than the staging buffer: go to HBM directly
-        uint32_t g = atomicAdd(&counters[CTR_NCAND], 1u);
-        if (g < cap) {
-            uint4* o = reinterpret_cast<uint4*>(out + g);
-            o[0] = a; o[1] = b;
-        } else {
-            atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
-        }
-    }
-}
-
-// Closed form of the reference's per-op state machine: for the N op k,
-//   start = pos + sum(len of M,=,D,X,N before k),  end = start + len_k,
-//   left  = sum(len of M,=) since the last of {N,D,X,I,S},  right likewise up to the next one.
-// H, P, B and op codes 10..15 change nothing.
-template <bool FROM_SMEM>
-__device__ __forceinline__ void scan_walk(ScanSmem& sm, const uint32_t* __restrict__ ops, uint32_t n,
-                                          uint32_t pos, int32_t tid, uint32_t strand, uint64_t read_ord,
-                                          Cand* __restrict__ out, uint32_t cap, uint32_t* counters) {
-    uint32_t cur = pos, run = 0;
-    bool pending = false;
-    uint32_t p_start = 0, p_end = 0, p_left = 0, p_k = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        uint32_t w = FROM_SMEM ? ops[i] : __ldg(ops + i);
-        uint32_t op = w & 0xfu, len = w >> 4;
-        // bit masks over op codes: M=0 I=1 D=2 N=3 S=4 H=5 P=6 '='=7 X=8 B=9
-        const uint32_t ANC = (1u << 0) | (1u << 7);
-        const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
-        const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
-        uint32_t bit = 1u << op;
-        if (bit & BRK) {
-            if (pending) {
-                scan_emit(sm, out, cap, counters, p_start, p_end, p_left, run,
-                          read_ord << 16 | (p_k > 0xffffu ? 0xffffu : p_k), tid, strand);
-                pending = false;
-            }
-            if (op == 3u) {
-                pending = true; p_start = cur; p_end = cur + len; p_left = run; p_k = i;
-            }
-            run = 0;
-        } else if (bit & ANC) {
-            run += len;
-        }
-        if (bit & REFC) cur += len;
-    }
-    if (pending)
-        scan_emit(sm, out, cap, counters, p_start, p_end, p_left, run,
-                  read_ord << 16 | (p_k > 0xffffu ? 0xffffu : p_k), tid, strand);
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS, 4)
-cigar_scan_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
-    __shared__ ScanSmem sm;
-    const uint32_t t = threadIdx.x;
-    const uint32_t base = blockIdx.x * SCAN_TILE;
-    const uint32_t n_tile = min((uint32_t)SCAN_TILE, b.n_reads - base);
-
-    // ---- phase 1: issue every metadata load of this thread (coalesced, streaming) ----
-    uint32_t off0[SCAN_RPT], off1[SCAN_RPT], pos[SCAN_RPT], meta[SCAN_RPT];
-    int32_t tid[SCAN_RPT];
-#pragma unroll
-    for (int j = 0; j < SCAN_RPT; ++j) {
-        uint32_t r = t + j * SCAN_THREADS;
-        bool ok = r < n_tile;
-        uint32_t i = base + (ok ? r : 0);
-        off0[j] = __ldg(b.cig_off + i);
-        off1[j] = __ldg(b.cig_off + i + 1);          // same lines as off0: merged in L1
-        pos[j]  = ldg_stream_u32(reinterpret_cast<const uint32_t*>(b.pos) + i);
-        meta[j] = ldg_stream_u32(b.meta + i);
-        tid[j]  = (int32_t)ldg_stream_u32(reinterpret_cast<const uint32_t*>(b.tid) + i);
-        if (!ok) { off1[j] = off0[j]; }
-    }
-    if (t == 0) sm.n_stage = 0;
-
-    // ---- phase 2: stage the tile's CIGAR slab ----
-    const uint32_t slab_lo = __ldg(b.cig_off + base);
-    const uint32_t slab_hi = __ldg(b.cig_off + base + n_tile);
-    const uint32_t a0 = slab_lo & ~3u;                        // 16-byte aligned start (word index)
-    const bool staged = (slab_hi - a0) <= (uint32_t)SCAN_SLAB;
-    if (staged) {
-        const uint32_t n_vec = (slab_hi - a0 + 3u) >> 2;
-        const uint32_t full_vec = b.n_ops >> 2;               // vectors that lie fully inside the array
-        const uint4* src = reinterpret_cast<const uint4*>(b.cigar) + (a0 >> 2);
-        uint4* dst = reinterpret_cast<uint4*>(sm.slab);
-        for (uint32_t v = t; v < n_vec; v += SCAN_THREADS) {
-            if ((a0 >> 2) + v < full_vec) {
-                dst[v] = ldg_stream_u4(src + v);
-            } else {                                          // ragged tail of the array
-                uint32_t w0 = a0 + 4 * v;
-                uint4 x;
-                x.x = w0 + 0 < b.n_ops ? __ldg(b.cigar + w0 + 0) : 0u;
-                x.y = w0 + 1 < b.n_ops ? __ldg(b.cigar + w0 + 1) : 0u;
-                x.z = w0 + 2 < b.n_ops ? __ldg(b.cigar + w0 + 2) : 0u;
-                x.w = w0 + 3 < b.n_ops ? __ldg(b.cigar + w0 + 3) : 0u;
-                dst[v] = x;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 3: walk the (few) multi-op alignments ----
-#pragma unroll
-    for (int j = 0; j < SCAN_RPT; ++j) {
-        uint32_t n = off1[j] - off0[j];
-        if (n > 1u && tid[j] >= 0) {                          // junctions_extractor.cc:379
-            uint64_t read_ord = b.first_ordinal + base + t + j * SCAN_THREADS;
-            uint32_t strand = read_strand(meta[j], prm.strandness);
-            if (staged)
-                scan_walk<true>(sm, sm.slab + (off0[j] - a0), n, pos[j], tid[j], strand, read_ord, out, cap, counters);
-            else
-                scan_walk<false>(sm, b.cigar + off0[j], n, pos[j], tid[j], strand, read_ord, out, cap, counters);
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 4: flush staged candidates, one reservation per block ----
-    const uint32_t n_st = min(sm.n_stage, (uint32_t)SCAN_STAGE);
-    if (n_st == 0) return;
-    if (t == 0) sm.flush_base = atomicAdd(&counters[CTR_NCAND], n_st);
-    __syncthreads();
-    const uint32_t fb = sm.flush_base;
-    uint4* o = reinterpret_cast<uint4*>(out);
-    for (uint32_t v = t; v < 2 * n_st; v += SCAN_THREADS) {
-        uint32_t c = fb + (v >> 1);
-        if (c < cap) o[2ull * fb + v] = sm.stage[v];
-        else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
-    }
-}
-
 static int num_sms();
-
-// ---- mbarrier / bulk-copy primitives (used by the warp-specialised variant) ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-// 1-D bulk async copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-
-// ------------------------------------------------------------------------------------------------
-// cigar_scan, warp-specialised persistent version (variant 4, the one normally launched)
-// ------------------------------------------------------------------------------------------------
-// 8 consumer warps + 1 service warp per CTA, two CTAs per SM, tiles of 1024 alignments strided
-// over the grid.  The service warp is the only one that talks to HBM: it keeps a 3-stage ring of
-// tile metadata (pos, meta, tid, cig_off: 16 KB) and CIGAR slabs full with 1-D bulk async copies
-// (cp.async.bulk -> UBLKCP) that complete on mbarriers, and it drains the double-buffered
-// candidate staging area with one global reservation per tile.  Consumers never wait for a load
-// they could have been told about earlier, never wait for a flush, and synchronise among
-// themselves once per tile (named barrier after the compaction pass).
-constexpr int S4_CONSUMERS = 256;
-constexpr int S4_THREADS   = S4_CONSUMERS + 32;
-constexpr int S4_TILE      = 1024;
-constexpr int S4_STAGES    = 3;
-constexpr int S4_SLAB      = 2560;               // CIGAR words per stage (10 KB)
-constexpr int S4_OUT       = 384;                // staged candidates per buffer (12 KB), two buffers
-
-struct alignas(16) S4Stage {
-    uint32_t pos[S4_TILE];
-    uint32_t meta[S4_TILE];
-    uint32_t tid[S4_TILE];
-    uint32_t off[S4_TILE + 4];
-    uint32_t slab[S4_SLAB];
-};
-struct alignas(16) S4Smem {
-    S4Stage st[S4_STAGES];
-    uint4 out[2][S4_OUT * 2];
-    unsigned long long meta_full[S4_STAGES];
-    unsigned long long slab_full[S4_STAGES];
-    unsigned long long tile_done[2];
-    unsigned long long out_free[2];
-    uint32_t slab_a0[S4_STAGES];
-    uint32_t slab_direct[S4_STAGES];
-    uint32_t n_work[2], n_out[2];
-    uint16_t work[2][S4_TILE];
-};
-
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-constexpr int S4_L2_AHEAD = 3;                   // tiles prefetched into L2 beyond the shared-memory ring
-
-struct S4Emit {
-    S4Smem& sm; uint32_t buf; Cand* __restrict__ out; uint32_t cap; uint32_t* counters; uint32_t dbg;
-    __device__ __forceinline__ void operator()(uint32_t start, uint32_t end, uint32_t left, uint32_t right,
-                                               uint64_t ord, int32_t tid, uint32_t strand) const {
-        uint4 a = make_uint4(start, end, start - left, end + right);
-        uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
-        if (dbg & 4u) { if ((a.x ^ a.y ^ a.z ^ a.w ^ b.x) == 0x9e3779b9u) sm.n_out[buf] = 1; return; }
-        // one shared-memory atomic per converged group of lanes instead of one per lane
-        const uint32_t mask = __activemask();
-        const uint32_t lane = threadIdx.x & 31u;
-        const int leader = __ffs(mask) - 1;
-        uint32_t i = 0;
-        if ((int)lane == leader) i = atomicAdd(&sm.n_out[buf], (uint32_t)__popc(mask));
-        i = __shfl_sync(mask, i, leader) + __popc(mask & ((1u << lane) - 1u));
-        if (i < S4_OUT) {
-            sm.out[buf][2 * i] = a; sm.out[buf][2 * i + 1] = b;
-        } else {
-            uint32_t g = atomicAdd(&counters[CTR_NCAND], 1u);
-            if (g < cap) { uint4* o = reinterpret_cast<uint4*>(out + g); o[0] = a; o[1] = b; }
-            else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
-        }
-    }
-};
 
 // Walk with the first 8 ops preloaded by independent loads and a predicated (branch-free) state
 // update; only the emits diverge.  Same arithmetic as walk_lin; op code 15 is a transparent filler.
@@ -398,194 +150,6 @@ __device__ __forceinline__ void walk_fast(const uint32_t* __restrict__ ops, uint
     if (pending) emit(p_start, p_end, p_left, run, read_ord << 16 | (p_k > 0xffffu ? 0xffffu : p_k), tid, strand);
 }
 
-__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(S4_CONSUMERS) : "memory"); }
-
-// one warp copies the staged candidates of buffer `buf` to HBM with a single reservation
-__device__ __forceinline__ void s4_flush(S4Smem& sm, uint32_t buf, uint32_t lane, Cand* __restrict__ out, uint32_t cap,
-                                         uint32_t* counters) {
-    const uint32_t n_st = min(sm.n_out[buf], (uint32_t)S4_OUT);
-    __syncwarp();
-    if (n_st) {
-        uint32_t fb = 0;
-        if (lane == 0) fb = atomicAdd(&counters[CTR_NCAND], n_st);
-        fb = __shfl_sync(0xffffffffu, fb, 0);
-        uint4* o = reinterpret_cast<uint4*>(out);
-        for (uint32_t v = lane; v < 2 * n_st; v += 32) {
-            if (fb + (v >> 1) < cap) o[2ull * fb + v] = sm.out[buf][v];
-            else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
-        }
-    }
-    __syncwarp();
-    if (lane == 0) sm.n_out[buf] = 0;
-}
-
-__global__ void __launch_bounds__(S4_THREADS, 2)
-cigar_scan_ws_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
-    extern __shared__ __align__(128) unsigned char s4_raw[];
-    S4Smem& sm = *reinterpret_cast<S4Smem*>(s4_raw);
-    const uint32_t t = threadIdx.x, lane = t & 31u;
-    const uint32_t n_tiles = (b.n_reads + S4_TILE - 1) / S4_TILE;
-    const uint32_t n_ops_vec_end = b.n_ops & ~3u;
-    const uint32_t n_my = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
-    auto tile_of = [&](uint32_t kk) { return blockIdx.x + kk * gridDim.x; };
-
-    if (t == 0) {
-        for (int s = 0; s < S4_STAGES; ++s) { mbar_init(&sm.meta_full[s], 1); mbar_init(&sm.slab_full[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm.tile_done[i], S4_CONSUMERS / 32); mbar_init(&sm.out_free[i], 1); }
-        sm.n_work[0] = sm.n_work[1] = 0; sm.n_out[0] = sm.n_out[1] = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (t >= (uint32_t)S4_CONSUMERS) {
-        // ======================= service warp: loads and stores =======================
-        auto issue_meta = [&](uint32_t tile, int s) {
-            const uint32_t base = tile * S4_TILE;
-            S4Stage& st = sm.st[s];
-            if (base + S4_TILE + 3 <= b.n_reads) {
-                if (lane == 0) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive_expect_tx(&sm.meta_full[s], 3 * S4_TILE * 4 + (S4_TILE + 4) * 4);
-                    bulk_g2s(st.off, b.cig_off + base, (S4_TILE + 4) * 4, &sm.meta_full[s]);
-                    bulk_g2s(st.pos, b.pos + base, S4_TILE * 4, &sm.meta_full[s]);
-                    bulk_g2s(st.meta, b.meta + base, S4_TILE * 4, &sm.meta_full[s]);
-                    bulk_g2s(st.tid, b.tid + base, S4_TILE * 4, &sm.meta_full[s]);
-                }
-            } else {                                           // ragged tail of the batch: plain loads
-                const uint32_t n_tile = min((uint32_t)S4_TILE, b.n_reads - base);
-                for (uint32_t r = lane; r < n_tile; r += 32) {
-                    st.pos[r] = (uint32_t)b.pos[base + r]; st.meta[r] = b.meta[base + r]; st.tid[r] = (uint32_t)b.tid[base + r];
-                }
-                for (uint32_t r = lane; r <= n_tile; r += 32) st.off[r] = b.cig_off[base + r];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.meta_full[s]);
-            }
-        };
-        auto issue_slab = [&](uint32_t kk) {                  // lane 0; tile index kk of this CTA
-            const int s = (int)(kk % S4_STAGES);
-            mbar_wait(&sm.meta_full[s], (kk / S4_STAGES) & 1u);
-            S4Stage& st = sm.st[s];
-            const uint32_t n_tile = min((uint32_t)S4_TILE, b.n_reads - tile_of(kk) * S4_TILE);
-            const uint32_t lo = st.off[0], hi = st.off[n_tile];
-            const uint32_t a0 = lo & ~3u, end4 = (hi + 3u) & ~3u;
-            sm.slab_a0[s] = a0;
-            if (hi <= lo) {
-                sm.slab_direct[s] = 0; mbar_arrive(&sm.slab_full[s]);
-            } else if (end4 - a0 > (uint32_t)S4_SLAB || end4 > n_ops_vec_end) {
-                sm.slab_direct[s] = 1; mbar_arrive(&sm.slab_full[s]);
-            } else {
-                sm.slab_direct[s] = 0;
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive_expect_tx(&sm.slab_full[s], (end4 - a0) * 4);
-                bulk_g2s(st.slab, b.cigar + a0, (end4 - a0) * 4, &sm.slab_full[s]);
-            }
-        };
-        // L2 prefetch of a tile's metadata columns (lanes 0..3 take one column each): keeps more bytes in
-        // flight to HBM than the shared-memory ring alone can hold
-        auto prefetch_meta = [&](uint32_t kk) {
-            if (kk >= n_my || (prm.debug & 16u)) return;
-            const uint32_t base = tile_of(kk) * S4_TILE;
-            if (base + S4_TILE + 3 > b.n_reads) return;
-            if (lane == 0) bulk_prefetch_l2(b.cig_off + base, (S4_TILE + 4) * 4);
-            else if (lane == 1) bulk_prefetch_l2(b.pos + base, S4_TILE * 4);
-            else if (lane == 2) bulk_prefetch_l2(b.meta + base, S4_TILE * 4);
-            else if (lane == 3) bulk_prefetch_l2(b.tid + base, S4_TILE * 4);
-        };
-        for (uint32_t i = 0; i < (uint32_t)S4_STAGES && i < n_my; ++i) issue_meta(tile_of(i), (int)i);
-        for (uint32_t i = 0; i < (uint32_t)S4_L2_AHEAD; ++i) prefetch_meta(S4_STAGES + i);
-        if (lane == 0) for (uint32_t i = 0; i < (uint32_t)S4_STAGES && i < n_my; ++i) issue_slab(i);
-        for (uint32_t k = 0; k < n_my; ++k) {
-            const uint32_t cb = k & 1u;
-            mbar_wait(&sm.tile_done[cb], (k / 2) & 1u);        // every consumer warp is past tile k
-            if (k + S4_STAGES < n_my) issue_meta(tile_of(k + S4_STAGES), (int)(k % S4_STAGES));
-            prefetch_meta(k + S4_STAGES + S4_L2_AHEAD);
-            if (prm.debug & 8u) { if (lane == 0) sm.n_out[cb] = 0; } else s4_flush(sm, cb, lane, out, cap, counters);
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&sm.out_free[cb]);
-                // the slab of tile k+3 goes out as soon as its cig_off column (issued above) has landed:
-                // the dependent load gets ~two tiles of slack before consumers need it
-                if (k + S4_STAGES < n_my) issue_slab(k + S4_STAGES);
-            }
-            __syncwarp();
-        }
-        return;
-    }
-
-    // ============================ consumer warps ============================
-    for (uint32_t k = 0; k < n_my; ++k) {
-        const uint32_t tile = tile_of(k);
-        const int s = (int)(k % S4_STAGES);
-        const uint32_t parity = (k / S4_STAGES) & 1u;
-        const uint32_t cb = k & 1u;
-        mbar_wait(&sm.meta_full[s], parity);
-        S4Stage& st = sm.st[s];
-        const uint32_t base = tile * S4_TILE;
-        const uint32_t n_tile = min((uint32_t)S4_TILE, b.n_reads - base);
-
-        // ---- phase A: compact the alignments that have more than one CIGAR op (junctions_extractor.cc:379)
-        {
-            const uint4 o = *reinterpret_cast<const uint4*>(&st.off[4 * t]);
-            const uint32_t o4 = st.off[4 * t + 4];
-            const uint32_t r0 = 4 * t;
-            uint32_t flags = 0;
-            if (r0 + 0 < n_tile && o.y - o.x > 1u) flags |= 1u;
-            if (r0 + 1 < n_tile && o.z - o.y > 1u) flags |= 2u;
-            if (r0 + 2 < n_tile && o.w - o.z > 1u) flags |= 4u;
-            if (r0 + 3 < n_tile && o4 - o.w > 1u) flags |= 8u;
-            const uint32_t cnt = __popc(flags);
-            uint32_t x = cnt;
-#pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
-            uint32_t wbase = 0;
-            if (lane == 31 && x) wbase = atomicAdd(&sm.n_work[cb], x);
-            wbase = __shfl_sync(0xffffffffu, wbase, 31);
-            uint32_t p = wbase + x - cnt;
-            uint16_t* work = sm.work[cb];
-            if (flags & 1u) work[p++] = (uint16_t)(r0 + 0);
-            if (flags & 2u) work[p++] = (uint16_t)(r0 + 1);
-            if (flags & 4u) work[p++] = (uint16_t)(r0 + 2);
-            if (flags & 8u) work[p++] = (uint16_t)(r0 + 3);
-        }
-        consumer_bar();
-        if (t == 0) sm.n_work[cb ^ 1u] = 0;                   // for tile k+1; nobody reads it any more
-
-        // ---- phase B: walk the compacted alignments, one per thread, in rounds of 256
-        {
-            const uint32_t n_work = (prm.debug & 1u) ? 0u : sm.n_work[cb];
-            // unconditional: these waits also keep consumers at most two tiles ahead of the service warp,
-            // which the 1-bit phase parity of tile_done / slab_full relies on
-            mbar_wait(&sm.slab_full[s], parity);
-            if (k >= 2) mbar_wait(&sm.out_free[cb], ((k / 2) - 1u) & 1u);       // staging buffer drained (tile k-2)
-            const uint32_t a0 = sm.slab_a0[s];
-            const bool direct = sm.slab_direct[s] != 0;
-            const S4Emit emit{sm, cb, out, cap, counters, prm.debug};
-            const uint16_t* work = sm.work[cb];
-            for (uint32_t w0 = 0; w0 < n_work; w0 += S4_CONSUMERS) {
-                const uint32_t w = w0 + t;
-                if (w < n_work) {
-                    const uint32_t r = work[w];
-                    const int32_t tid = (int32_t)st.tid[r];
-                    if (tid >= 0) {
-                        const uint32_t o0 = st.off[r], n = st.off[r + 1] - o0;
-                        const uint32_t strand = read_strand(st.meta[r], prm.strandness);
-                        const uint64_t read_ord = b.first_ordinal + base + r;
-                        if (!direct) walk_fast<true>(st.slab + (o0 - a0), n, st.pos[r], tid, strand, read_ord, emit);
-                        else walk_fast<false>(b.cigar + o0, n, st.pos[r], tid, strand, read_ord, emit);
-                    }
-                }
-                if (w0 + S4_CONSUMERS < n_work) {              // dense tile: drain the staging buffer between rounds
-                    consumer_bar();
-                    if (t < 32) s4_flush(sm, cb, lane, out, cap, counters);
-                    consumer_bar();
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.tile_done[cb]);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // cigar_scan, many-small-blocks version (variant 5)
 // ------------------------------------------------------------------------------------------------
@@ -616,7 +180,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <class Smem, int S5_OUT, bool MOTIF, bool VREG, bool BC = false>
 struct S5Emit {
-    Smem& sm; Cand* __restrict__ out; uint32_t cap; uint32_t* counters; uint32_t dbg;
+    Smem& sm; Cand* __restrict__ out; uint32_t cap; uint32_t* counters;
     const ScanParams* prm; uint32_t* jstrand;                 // intron-motif mode: parameters + the alignment's running strand
     const int32_t* rspan;                                     // variant-region mode: [pos, endpos) of the alignment being walked
     __device__ __forceinline__ void push(const uint4& a, const uint4& b) const {
@@ -645,7 +209,6 @@ struct S5Emit {
         }
         const uint4 a = make_uint4(start, end, start - left, end + right);
         const uint4 b = make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand);
-        if (dbg & 4u) { if ((a.x ^ a.y ^ a.z ^ a.w ^ b.x) == 0x9e3779b9u) sm.n_out = 1; return; }
         if (!VREG) { push(a, b); return; }
         // one candidate per variant region the ALIGNMENT belongs to (tid, pos < end, endpos > beg; hts.c:1941-1963)
         const VariantRegions& vr = prm->vr;
@@ -664,11 +227,9 @@ struct S5Emit {
     }
 };
 
-// MINB > 1 asks ptxas for that many resident blocks per SM (A/B configurations 8-10, see launch_cigar_scan)
-template <int S5_THREADS, int S5_SLAB, int S5_OUT, bool MOTIF = false, bool VREG = false, bool BC = false, int MINB = 1>
-__global__ void __launch_bounds__(S5_THREADS, MINB)
-cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters,
-                        const uint32_t* __restrict__ tile_off, CandRegions rg) {
+template <int S5_THREADS, int S5_SLAB, int S5_OUT, bool MOTIF = false, bool VREG = false, bool BC = false>
+__global__ void __launch_bounds__(S5_THREADS)
+cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
     using Smem = S5SmemT<S5_THREADS, S5_SLAB, S5_OUT>;
     constexpr int S5_TILE = Smem::S5_TILE;
     __shared__ Smem sm;
@@ -692,12 +253,10 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
     }
     if (t == 0) { sm.n_work = 0; sm.n_out = 0; }
     cp_async_commit();
-    // ---- CIGAR slab of the tile.  Its address depends on cig_off; the per-tile offsets gathered by the pre-pass
-    // (tile_offsets_kernel, L2-resident) let the slab request go out together with the metadata instead of one
-    // DRAM round trip later.
-    uint32_t lo, hi;
-    if (tile_off) { lo = __ldg(tile_off + blockIdx.x); hi = __ldg(tile_off + blockIdx.x + 1); }
-    else { cp_async_wait_all(); __syncthreads(); lo = sm.off[0]; hi = sm.off[n_tile]; }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- CIGAR slab of the tile: its address is the one data-dependent address of the path
+    const uint32_t lo = sm.off[0], hi = sm.off[n_tile];
     const uint32_t a0 = lo & ~3u;
     // words of the tile's slab staged in shared memory (from a0): all of it unless the tile is denser than S5_SLAB or
     // touches the ragged end of the array; alignments outside the staged window read their ops from global memory
@@ -708,9 +267,7 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
         for (uint32_t v = t; v < (n_st >> 2); v += S5_THREADS) cp_async16(&sm.slab[4 * v], b.cigar + a0 + 4 * v);
     }
     cp_async_commit();
-    if (tile_off) { cp_async_wait_all(); __syncthreads(); }
-    cp_async_commit();
-    {
+    {   // ---- while the slab is in flight: list the alignments with more than one CIGAR op (junctions_extractor.cc:379)
         const uint4 o = *reinterpret_cast<const uint4*>(&sm.off[4 * t]);
         const uint32_t o4 = sm.off[4 * t + 4];
         const uint32_t r0 = 4 * t;
@@ -735,20 +292,20 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
     cp_async_wait_all();
     __syncthreads();
 
-    // ---- walk the compacted alignments, one per thread, in rounds of 128
-    const uint32_t n_work = (prm.debug & 1u) ? 0u : sm.n_work;
+    // ---- walk the listed alignments, one per thread, in rounds of S5_THREADS
+    const uint32_t n_work = sm.n_work;
     uint32_t jstrand = 0;                                      // j1.strand == "" before an alignment's first junction
     int32_t rspan[2] = {0, 0};
-    const S5Emit<Smem, S5_OUT, MOTIF, VREG, BC> emit{sm, out, cap, counters, prm.debug, &prm, &jstrand, rspan};
-    auto flush = [&]() {                                        // warp 0
-        const uint32_t n_st = (prm.debug & 8u) ? 0u : min(sm.n_out, (uint32_t)S5_OUT);
+    const S5Emit<Smem, S5_OUT, MOTIF, VREG, BC> emit{sm, out, cap, counters, &prm, &jstrand, rspan};
+    auto flush = [&]() {                                        // warp 0: staged candidates -> HBM, one reservation
+        const uint32_t n_out = min(sm.n_out, (uint32_t)S5_OUT);
         __syncwarp();
-        if (n_st) {
+        if (n_out) {
             uint32_t fb = 0;
-            if (lane == 0) fb = atomicAdd(&counters[CTR_NCAND], n_st);
+            if (lane == 0) fb = atomicAdd(&counters[CTR_NCAND], n_out);
             fb = __shfl_sync(0xffffffffu, fb, 0);
             uint4* o = reinterpret_cast<uint4*>(out);
-            for (uint32_t v = lane; v < 2 * n_st; v += 32) {
+            for (uint32_t v = lane; v < 2 * n_out; v += 32) {
                 if (fb + (v >> 1) < cap) o[2ull * fb + v] = sm.out[v];
                 else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
             }
@@ -783,189 +340,9 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
             }
         }
         __syncthreads();
-        if (w0 == 0 && rg.base && !(prm.debug & 8u)) {
-            // first round -> this tile's own region: plain stores by every thread, nobody waits for an atomic
-            const uint32_t n_st = min(sm.n_out, (uint32_t)S5_OUT);
-            uint4* o = reinterpret_cast<uint4*>(rg.base + (size_t)blockIdx.x * rg.cap);
-            for (uint32_t v = t; v < 2 * n_st; v += S5_THREADS) o[v] = sm.out[v];
-            if (t == 0) { rg.cnt[blockIdx.x] = n_st; if (n_st) atomicAdd(&counters[CTR_NREGION], n_st); }   // no return value used: a RED, nobody waits
-            if (w0 + S5_THREADS < n_work) { __syncthreads(); if (t == 0) sm.n_out = 0; __syncthreads(); }
-        } else {
-            if (t < 32) flush();
-            if (w0 + S5_THREADS < n_work) __syncthreads();
-        }
-    }
-    if (n_work == 0 && rg.base && t == 0) rg.cnt[blockIdx.x] = 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// cigar_scan, gather variant (variant 7; opt-in A/B build written at the end of round 1, NOT yet measured)
-// ------------------------------------------------------------------------------------------------
-// Why: Little's law on the round-1 numbers of the kernel above — 12 resident blocks x (8 KB columns + 2.7 KB slab) in flight
-// per SM over a ~6.5 us block life = 2.9 TB/s, which is the measured rate.  The 12 comes from two limits at once
-// (40 registers x 128 threads, 19.5 KB shared memory).  Only `cig_off` is needed for every alignment (to find n_cigar > 1);
-// pos / meta / tid matter for the ~17 % that go on the work list.  This kernel stages only `cig_off`, the slab and the
-// candidates (9.2 KB per block) and runs at <= 32 registers, so 16 blocks fit; the three columns of a work item are
-// fetched by its thread straight from global memory (neighbouring work items are ~6 alignments apart, so a warp touches a
-// handful of sectors per column) and that gather is issued BEFORE the wait for the slab, so it rides on the same round trip.
-template <int THREADS, int SLAB, int OUTN>
-struct alignas(16) S7SmemT {
-    static constexpr int S5_TILE = THREADS * 4;
-    uint32_t off[S5_TILE + 4];
-    uint32_t slab[SLAB];
-    uint4 out[OUTN * 2];
-    uint32_t n_work, n_out;
-    uint16_t work[S5_TILE];
-};
-
-template <int THREADS, int SLAB, int OUTN, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-cigar_scan_gather_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
-    using Smem = S7SmemT<THREADS, SLAB, OUTN>;
-    constexpr int TILE = Smem::S5_TILE;
-    __shared__ Smem sm;
-    const uint32_t t = threadIdx.x, lane = t & 31u;
-    const uint32_t base = blockIdx.x * TILE;
-    const uint32_t n_tile = min((uint32_t)TILE, b.n_reads - base);
-    const bool full = base + TILE + 3 <= b.n_reads;
-
-    // ---- cig_off of the tile: global -> shared
-    if (full) {
-        cp_async16(&sm.off[4 * t], b.cig_off + base + 4 * t);
-        if (t == 0) cp_async16(&sm.off[TILE], b.cig_off + base + TILE);
-    } else {
-        for (uint32_t r = t; r <= n_tile; r += THREADS) sm.off[r] = b.cig_off[base + r];
-    }
-    if (t == 0) { sm.n_work = 0; sm.n_out = 0; }
-    cp_async_commit();
-    cp_async_wait_all();
-    __syncthreads();
-    // ---- CIGAR slab (same window rules as cigar_scan_small_kernel)
-    const uint32_t lo = sm.off[0], hi = sm.off[n_tile];
-    const uint32_t a0 = lo & ~3u;
-    uint32_t n_st = 0;
-    if (hi > lo) {
-        const uint32_t end = min(min((hi + 3u) & ~3u, a0 + (uint32_t)SLAB), b.n_ops & ~3u);
-        n_st = end > a0 ? end - a0 : 0u;
-        for (uint32_t v = t; v < (n_st >> 2); v += THREADS) cp_async16(&sm.slab[4 * v], b.cigar + a0 + 4 * v);
-    }
-    cp_async_commit();
-    // ---- work list of the alignments with n_cigar > 1 (junctions_extractor.cc:379)
-    {
-        const uint4 o = *reinterpret_cast<const uint4*>(&sm.off[4 * t]);
-        const uint32_t o4 = sm.off[4 * t + 4];
-        const uint32_t r0 = 4 * t;
-        uint32_t flags = 0;
-        if (r0 + 0 < n_tile && o.y - o.x > 1u) flags |= 1u;
-        if (r0 + 1 < n_tile && o.z - o.y > 1u) flags |= 2u;
-        if (r0 + 2 < n_tile && o.w - o.z > 1u) flags |= 4u;
-        if (r0 + 3 < n_tile && o4 - o.w > 1u) flags |= 8u;
-        const uint32_t cnt = __popc(flags);
-        uint32_t x = cnt;
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
-        uint32_t wbase = 0;
-        if (lane == 31 && x) wbase = atomicAdd(&sm.n_work, x);
-        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        uint32_t p = wbase + x - cnt;
-        if (flags & 1u) sm.work[p++] = (uint16_t)(r0 + 0);
-        if (flags & 2u) sm.work[p++] = (uint16_t)(r0 + 1);
-        if (flags & 4u) sm.work[p++] = (uint16_t)(r0 + 2);
-        if (flags & 8u) sm.work[p++] = (uint16_t)(r0 + 3);
-    }
-    __syncthreads();                                            // work list complete
-    const uint32_t n_work = sm.n_work;
-    // ---- columns of the first round's work item, requested before the slab is waited for
-    uint32_t g_r = 0, g_pos = 0, g_meta = 0;
-    int32_t g_tid = -1;
-    if (t < n_work) {
-        g_r = sm.work[t];
-        g_tid = __ldg(b.tid + base + g_r); g_pos = (uint32_t)__ldg(b.pos + base + g_r); g_meta = __ldg(b.meta + base + g_r);
-    }
-    cp_async_wait_all();
-    __syncthreads();
-
-    uint32_t jstrand = 0;
-    int32_t rspan[2] = {0, 0};
-    const S5Emit<Smem, OUTN, false, false, false> emit{sm, out, cap, counters, 0u, &prm, &jstrand, rspan};
-    auto flush = [&]() {                                        // warp 0
-        const uint32_t n_out = min(sm.n_out, (uint32_t)OUTN);
-        __syncwarp();
-        if (n_out) {
-            uint32_t fb = 0;
-            if (lane == 0) fb = atomicAdd(&counters[CTR_NCAND], n_out);
-            fb = __shfl_sync(0xffffffffu, fb, 0);
-            uint4* o = reinterpret_cast<uint4*>(out);
-            for (uint32_t v = lane; v < 2 * n_out; v += 32) {
-                if (fb + (v >> 1) < cap) o[2ull * fb + v] = sm.out[v];
-                else atomicExch(&counters[CTR_CAND_OVERFLOW], 1u);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) sm.n_out = 0;
-    };
-    for (uint32_t w0 = 0; w0 < n_work; w0 += THREADS) {
-        const uint32_t w = w0 + t;
-        if (w < n_work) {
-            uint32_t r = g_r, pos = g_pos, meta = g_meta;
-            int32_t tid = g_tid;
-            if (w0) {                                           // later rounds of a dense tile: plain loads
-                r = sm.work[w];
-                tid = __ldg(b.tid + base + r); pos = (uint32_t)__ldg(b.pos + base + r); meta = __ldg(b.meta + base + r);
-            }
-            if (tid >= 0) {
-                const uint32_t o0 = sm.off[r], n = sm.off[r + 1] - o0;
-                const uint32_t strand = read_strand(meta, prm.strandness);
-                const uint64_t read_ord = b.first_ordinal + base + r;
-                if ((o0 - a0) + n <= n_st) walk_fast<true>(sm.slab + (o0 - a0), n, pos, tid, strand, read_ord, emit);
-                else walk_fast<false>(b.cigar + o0, n, pos, tid, strand, read_ord, emit);
-            }
-        }
-        __syncthreads();
         if (t < 32) flush();
-        if (w0 + THREADS < n_work) __syncthreads();
+        if (w0 + S5_THREADS < n_work) __syncthreads();
     }
-}
-
-struct WalkCand { uint32_t start, end, left, right, k; };
-
-// Forward walk that records the first two N ops in registers (c0, c1) and counts all of them.  Predicated, no
-// branches and no calls: same arithmetic as walk_fast, the first four ops are fetched by independent loads (op code
-// 15 is a transparent filler), the rest in a loop.  Alignments with more than two N ops (rare) are finished by
-// fused_walk_rest.  Returns the number of N ops.
-template <bool FROM_SMEM>
-__device__ __forceinline__ uint32_t walk_collect(const uint32_t* __restrict__ ops, uint32_t n, uint32_t pos,
-                                                 WalkCand& c0, WalkCand& c1) {
-    const uint32_t ANC = (1u << 0) | (1u << 7);
-    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
-    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
-    constexpr int PRE = 4;
-    uint32_t w[PRE];
-#pragma unroll
-    for (int i = 0; i < PRE; ++i) w[i] = (uint32_t)i < n ? (FROM_SMEM ? ops[i] : __ldg(ops + i)) : 0xfu;
-    uint32_t cur = pos, run = 0, nc = 0;
-    bool pending = false;
-    auto step = [&](uint32_t x, uint32_t i) {
-        const uint32_t op = x & 0xfu, len = x >> 4, bit = 1u << op;
-        const bool brk = (bit & BRK) != 0, is_n = op == 3u;
-        const bool close = pending && brk;                  // the open junction ends here: right anchor = run
-        c0.right = (close && nc == 1u) ? run : c0.right;
-        c1.right = (close && nc == 2u) ? run : c1.right;
-        const bool open0 = is_n && nc == 0u, open1 = is_n && nc == 1u;
-        const uint32_t kk = i > 0xffffu ? 0xffffu : i;
-        c0.start = open0 ? cur : c0.start; c0.end = open0 ? cur + len : c0.end; c0.left = open0 ? run : c0.left; c0.k = open0 ? kk : c0.k;
-        c1.start = open1 ? cur : c1.start; c1.end = open1 ? cur + len : c1.end; c1.left = open1 ? run : c1.left; c1.k = open1 ? kk : c1.k;
-        nc += is_n ? 1u : 0u;
-        pending = brk ? is_n : pending;
-        run = brk ? 0u : run + ((bit & ANC) ? len : 0u);
-        cur += (bit & REFC) ? len : 0u;
-    };
-#pragma unroll
-    for (int i = 0; i < PRE; ++i) step(w[i], (uint32_t)i);
-    for (uint32_t i = PRE; i < n; ++i) step(FROM_SMEM ? ops[i] : __ldg(ops + i), i);
-    c0.right = (pending && nc == 1u) ? run : c0.right;
-    c1.right = (pending && nc == 2u) ? run : c1.right;
-    return nc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1345,27 +722,25 @@ cigar_scan_pipe_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint
     }
 }
 
-// pre-pass: tile_off[t] = cig_off[min(t * S5_TILE, n_reads)] (one 4-byte load per tile; the result stays in L2)
-__global__ void tile_offsets_kernel(const uint32_t* __restrict__ cig_off, uint32_t n_reads, uint32_t n_tiles, uint32_t tile, uint32_t* __restrict__ tile_off) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t <= n_tiles) tile_off[t] = cig_off[min(t * tile, n_reads)];
-}
-uint32_t cigar_scan_tiles(uint32_t n_reads) { return (n_reads + 255) / 256; }   // upper bound over the tile sizes in use
-static int scan_variant() {
-    static int variant = -1;
-    if (variant < 0) { const char* v = getenv("RTJX_SCAN_VARIANT"); variant = v ? atoi(v) : 5; if (variant != 1 && variant != 4) variant = 5; }
-    return variant;
-}
-static int scan_cfg() {
-    static int cfg = -1;
-    if (cfg < 0) { const char* v = getenv("RTJX_SCAN_CFG"); cfg = v ? atoi(v) : 0; }
-    return cfg;
-}
-void cigar_scan_region_layout(uint32_t n_reads, uint32_t* n_regions, uint32_t* cap) {
-    static int use = -1;
-    if (use < 0) { const char* v = getenv("RTJX_SCAN_REGIONS"); use = v ? atoi(v) : 0; }   // measured: no gain (A/B option)
-    if (use && scan_variant() == 5 && scan_cfg() == 0) { *n_regions = (n_reads + 511) / 512; *cap = 192; }
-    else { *n_regions = 0; *cap = 0; }
+// Element-wise fallback for caller-owned device arrays that are not 16-byte aligned (rtjx_scan_batch, RTJX_LOC_DEVICE): one
+// thread per alignment, ops read from global memory, one slot reservation per candidate.  Plain mode only.
+struct DirectEmit {
+    Cand* __restrict__ out; uint32_t cap; uint32_t* counters;
+    __device__ __forceinline__ void operator()(uint32_t start, uint32_t end, uint32_t left, uint32_t right, uint64_t ord, int32_t tid,
+                                               uint32_t strand) const {
+        store_cand(out, cap, counters, atomicAdd(&counters[CTR_NCAND], 1u), make_uint4(start, end, start - left, end + right),
+                   make_uint4((uint32_t)ord, (uint32_t)(ord >> 32), (uint32_t)tid, strand));
+    }
+};
+__global__ void __launch_bounds__(256)
+cigar_scan_unaligned_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_reads) return;
+    const uint32_t o0 = b.cig_off[i], n = b.cig_off[i + 1] - o0;
+    const int32_t tid = b.tid[i];
+    if (n <= 1u || tid < 0) return;                           // junctions_extractor.cc:379
+    walk_fast<false>(b.cigar + o0, n, (uint32_t)b.pos[i], tid, read_strand(b.meta[i], prm.strandness), b.first_ordinal + i,
+                     DirectEmit{out, cap, counters});
 }
 
 // Launch of the warp-pipelined kernel: persistent grid of BPS blocks per SM, NWARP warps each.
@@ -1405,86 +780,34 @@ static void launch_pipe(const BatchView& b, const ScanParams& p, Cand* cands, ui
 // Candidate slots cigar_scan may reserve beyond the number of N ops of a batch (every warp's last chunk is partly padding).
 uint32_t cigar_scan_cand_slack() { return (uint32_t)num_sms() * 64u * 2u * (uint32_t)PCH + 1024u; }
 
-void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap,
-                       uint32_t* d_counters, uint32_t* tile_off_scratch, const CandRegions& regions, cudaStream_t stream) {
+void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uint32_t cand_cap, uint32_t* d_counters, cudaStream_t stream) {
     if (b.n_reads == 0) return;
     const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
                             reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
                             reinterpret_cast<uintptr_t>(b.cigar);
-    if ((align & 15u) == 0 && p.variant == 8) {
-        const bool special = p.genome || p.vr.n || b.bc;
+    const bool special = p.genome || p.vr.n || b.bc;
+    if ((align & 15u) == 0 && p.variant == 8) {               // warp-pipelined kernel (opt-in: rtjx_params.scan_variant = 8)
         if (special) { launch_pipe<384, 3, 8, 2, true>(b, p, cands, cand_cap, d_counters, stream); return; }
-        switch (p.cfg) {                   // A/B configurations; 0 is the production one.  Per warp: NST stages of 3.6 KB (SL 384) / 3.1 KB (SL 256)
-        case 1: launch_pipe<384, 2, 8, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // 24 warps/SM, 1 tile in flight each
-        case 2: launch_pipe<384, 3, 4, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // 16 warps/SM, 2 in flight
-        case 3: launch_pipe<256, 2, 8, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // 32 warps/SM, 1 in flight (64 registers)
-        case 4: launch_pipe<384, 4, 4, 3>(b, p, cands, cand_cap, d_counters, stream); break;      // 12 warps/SM, 3 in flight
-        case 5: launch_pipe<256, 3, 4, 5>(b, p, cands, cand_cap, d_counters, stream); break;      // 20 warps/SM, 2 in flight
-        case 6: launch_pipe<384, 2, 8, 1>(b, p, cands, cand_cap, d_counters, stream); break;      // 8 warps/SM (latency probe)
-        case 7: launch_pipe<256, 2, 4, 7>(b, p, cands, cand_cap, d_counters, stream); break;      // 28 warps/SM, 1 in flight
-        default: launch_pipe<384, 2, 8, 3>(b, p, cands, cand_cap, d_counters, stream); break;
+        switch (p.cfg) {                   // ring / occupancy configurations measured in profiles/r2_scan_ab_*.json
+        case 1: launch_pipe<384, 3, 4, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // 16 warps/SM, 2 tiles in flight each
+        case 2: launch_pipe<256, 2, 8, 4>(b, p, cands, cand_cap, d_counters, stream); break;      // 32 warps/SM, 1 in flight
+        case 3: launch_pipe<256, 2, 4, 7>(b, p, cands, cand_cap, d_counters, stream); break;      // 28 warps/SM, 1 in flight
+        default: launch_pipe<384, 2, 8, 3>(b, p, cands, cand_cap, d_counters, stream); break;     // 24 warps/SM, 1 in flight
         }
         return;
     }
-    const int variant = (p.genome || p.vr.n || b.bc) ? 5 : ((p.variant == 1 || p.variant == 4 || p.variant == 7) ? p.variant : scan_variant());   // only variant 5 knows the intron-motif and variant-region modes
-    if ((align & 15u) == 0 && variant == 5) {
-        static int prepass = -1;
-        const int cfg = b.bc ? 0 : (p.variant == 5 && p.cfg ? p.cfg : scan_cfg());
-        if (prepass < 0) { const char* v = getenv("RTJX_SCAN_PREPASS"); prepass = v ? atoi(v) : 0; }   // measured: no gain on B200
-        const uint32_t threads = cfg == 2 ? 64u : cfg == 3 ? 256u : 128u;
-        const uint32_t tile = threads * 4, tiles = (b.n_reads + tile - 1) / tile;
-        const uint32_t* toff = nullptr;
-        if (prepass && tile_off_scratch && tiles >= 64) {
-            tile_offsets_kernel<<<(tiles + 1 + 255) / 256, 256, 0, stream>>>(b.cig_off, b.n_reads, tiles, tile, tile_off_scratch);
-            toff = tile_off_scratch;
-        }
-        CandRegions none{nullptr, nullptr, 0, 0};
-        switch (cfg) {          // A/B configurations (RTJX_SCAN_CFG); 0 is the production one
-        case 1: cigar_scan_small_kernel<128, 768, 128><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
-        case 2: cigar_scan_small_kernel<64, 512, 96><<<tiles, 64, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
-        case 3: cigar_scan_small_kernel<256, 2048, 384><<<tiles, 256, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
-        case 4: cigar_scan_small_kernel<128, 1024, 96><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
-        case 5: cigar_scan_small_kernel<128, 2048, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
-        case 6: cigar_scan_small_kernel<128, 2048, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
-        case 7: cigar_scan_small_kernel<128, 1536, 160><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
-        // Occupancy experiments for round 2 (not yet measured).  Little's law on the round-1 numbers: 12 resident blocks x
-        // (8 KB columns + 2.7 KB slab) in flight per SM over a ~6.5 us block life = 2.9 TB/s, which IS the measured rate; the
-        // 12 comes from both limits at once (40 registers x 128 threads -> 12.8 blocks, 19.5 KB shared -> 11.6).  These
-        // configurations lift both: <= 32 registers (launch bound 16) and <= 14 KB shared memory per block.
-        case 8: cigar_scan_small_kernel<128, 768, 64, false, false, false, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
-        case 9: cigar_scan_small_kernel<128, 768, 96, false, false, false, 14><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;
-        case 10: cigar_scan_small_kernel<128, 1024, 192, false, false, false, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none); break;   // registers only
-        default:
-            if (b.bc && p.genome) cigar_scan_small_kernel<128, 1024, 192, true, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
-            else if (b.bc) cigar_scan_small_kernel<128, 1024, 192, false, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
-            else if (p.vr.n && p.genome) cigar_scan_small_kernel<128, 1024, 192, true, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
-            else if (p.vr.n) cigar_scan_small_kernel<128, 1024, 192, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, none);
-            else if (p.genome) cigar_scan_small_kernel<128, 1024, 192, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions);
-            else cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters, toff, regions);
-            break;
-        }
+    // block-per-tile kernel (the default): 16-byte aligned arrays; anything else takes the element-wise fallback below
+    const uint32_t tiles = (b.n_reads + 511u) / 512u;
+    if ((align & 15u) == 0) {
+        if (b.bc && p.genome) cigar_scan_small_kernel<128, 1024, 192, true, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
+        else if (b.bc) cigar_scan_small_kernel<128, 1024, 192, false, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
+        else if (p.vr.n && p.genome) cigar_scan_small_kernel<128, 1024, 192, true, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
+        else if (p.vr.n) cigar_scan_small_kernel<128, 1024, 192, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
+        else if (p.genome) cigar_scan_small_kernel<128, 1024, 192, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
+        else cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
         return;
     }
-    if ((align & 15u) == 0 && variant == 7) {                  // gather variant, A/B configurations via scan_cfg
-        const uint32_t tiles = (b.n_reads + 511u) / 512u;
-        switch (p.variant == 7 ? p.cfg : scan_cfg()) {
-        case 1: cigar_scan_gather_kernel<128, 1024, 96, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
-        case 2: cigar_scan_gather_kernel<128, 768, 96, 1><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
-        case 3: cigar_scan_gather_kernel<128, 1024, 192, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
-        case 4: cigar_scan_gather_kernel<128, 768, 96, 14><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
-        default: cigar_scan_gather_kernel<128, 768, 96, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
-        }
-        return;
-    }
-    if ((align & 15u) == 0 && variant == 4) {
-        static bool attr4 = false;
-        if (!attr4) { cudaFuncSetAttribute(cigar_scan_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S4Smem)); attr4 = true; }
-        const uint32_t tiles = (b.n_reads + S4_TILE - 1) / S4_TILE;
-        cigar_scan_ws_kernel<<<min(tiles, (uint32_t)(2 * num_sms())), S4_THREADS, sizeof(S4Smem), stream>>>(b, p, cands, cand_cap, d_counters);
-        return;
-    }
-    uint32_t grid = (b.n_reads + SCAN_TILE - 1) / SCAN_TILE;
-    cigar_scan_kernel<<<grid, SCAN_THREADS, 0, stream>>>(b, p, cands, cand_cap, d_counters);
+    cigar_scan_unaligned_kernel<<<(b.n_reads + 255u) / 256u, 256, 0, stream>>>(b, p, cands, cand_cap, d_counters);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1550,143 +873,112 @@ constexpr int MERGE_SLOTS   = 2048;                          // shared-memory ha
 constexpr int MERGE_PROBES  = 32;
 constexpr unsigned long long SKEY_EMPTY = ~0ull;
 constexpr int MERGE_PAL = 4;                               // (contig, region) pairs per chunk in the shared-memory table's 62-bit key
-constexpr int MERGE_RGROUP = 32;                            // scan tiles (candidate regions) per merge tile
 
 struct MergeSmem {
     unsigned long long key[MERGE_SLOTS];
     unsigned long long nfirst[MERGE_SLOTS];
     unsigned long long last[MERGE_SLOTS];
     uint32_t count[MERGE_SLOTS], nts[MERGE_SLOTS], te[MERGE_SLOTS], lr[MERGE_SLOTS];
-    unsigned long long pal[MERGE_PAL];           // region << 32 | tid of the (contig, region) pairs the chunk's shared-memory table knows
-    uint32_t rpre[MERGE_RGROUP + 1];             // prefix of the region counts of a region tile
+    unsigned long long pal[MERGE_PAL];           // region << 32 | tid of the (contig, region) pairs the tile's shared-memory table knows
 };
 
 __global__ void __launch_bounds__(MERGE_THREADS, 2)
-junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict__ d_n_cand, uint32_t n_bound, CandRegions rg,
+junction_merge_kernel(const Cand* __restrict__ cands, const uint32_t* __restrict__ d_n_cand, uint32_t n_bound,
                       ScanParams prm, TableRef tb, Slot* __restrict__ spill, uint32_t spill_cap,
                       uint32_t* __restrict__ counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MergeSmem& sm = *reinterpret_cast<MergeSmem*>(smem_raw);
     const uint32_t t = threadIdx.x;
     const uint32_t n = d_n_cand ? min(*d_n_cand, n_bound) : n_bound;
-    const uint32_t n_otiles = (n + MERGE_TILE - 1) / MERGE_TILE;                                   // dense overflow list
-    const uint32_t n_rtiles = rg.base ? (rg.n_regions + MERGE_RGROUP - 1) / MERGE_RGROUP : 0u;     // per-tile regions
-    uint32_t n_valid = 0;                                       // candidates seen (tid >= 0: not the padding of the scan's chunks)
+    const uint32_t n_tiles = (n + MERGE_TILE - 1) / MERGE_TILE;
+    uint32_t n_valid = 0;                                       // candidates seen (tid >= 0: not the padding of a scan kernel's chunks)
 
-    for (uint32_t tile = blockIdx.x; tile < n_rtiles + n_otiles; tile += gridDim.x) {
-        // ---- where this tile's candidates are
-        const bool is_region = tile < n_rtiles;
-        uint32_t total, g0 = 0;
-        if (is_region) {
-            g0 = tile * MERGE_RGROUP;
-            const uint32_t ng = min((uint32_t)MERGE_RGROUP, rg.n_regions - g0);
-            if (t < 32) {                                       // warp 0: inclusive scan of the region counts
-                uint32_t c = t < ng ? min(rg.cnt[g0 + t], rg.cap) : 0u, x = c;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, d); if ((int)t >= d) x += y; }
-                sm.rpre[t + 1] = x;
-                if (t == 0) sm.rpre[0] = 0;
-            }
-            __syncthreads();
-            total = sm.rpre[MERGE_RGROUP];
-        } else {
-            const uint32_t tb0 = (tile - n_rtiles) * MERGE_TILE;
-            total = min((uint32_t)MERGE_TILE, n - tb0);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t tb0 = tile * MERGE_TILE;
+        const uint32_t m = min((uint32_t)MERGE_TILE, n - tb0);
+        for (uint32_t s = t; s < MERGE_SLOTS; s += MERGE_THREADS) {
+            sm.key[s] = SKEY_EMPTY; sm.nfirst[s] = 0ull; sm.last[s] = 0ull;
+            sm.count[s] = 0u; sm.nts[s] = 0u; sm.te[s] = 0u; sm.lr[s] = 0u;
         }
-        auto cand_ptr = [&](uint32_t i) -> const uint4* {       // i-th candidate of the tile
-            if (!is_region) return reinterpret_cast<const uint4*>(cands + (size_t)(tile - n_rtiles) * MERGE_TILE + i);
-            uint32_t lo = 0, hi = MERGE_RGROUP;                 // last g with rpre[g] <= i
-            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.rpre[mid] <= i) lo = mid; else hi = mid; }
-            return reinterpret_cast<const uint4*>(rg.base + (size_t)(g0 + lo) * rg.cap + (i - sm.rpre[lo]));
-        };
-
-        for (uint32_t c0 = 0; c0 < total; c0 += MERGE_TILE) {   // a region tile may hold more than MERGE_TILE candidates
-            const uint32_t m = min((uint32_t)MERGE_TILE, total - c0);
-            for (uint32_t s = t; s < MERGE_SLOTS; s += MERGE_THREADS) {
-                sm.key[s] = SKEY_EMPTY; sm.nfirst[s] = 0ull; sm.last[s] = 0ull;
-                sm.count[s] = 0u; sm.nts[s] = 0u; sm.te[s] = 0u; sm.lr[s] = 0u;
-            }
-            if (t < MERGE_PAL) sm.pal[t] = SKEY_EMPTY;
-            // all loads of the chunk first (two 128-bit loads per candidate)
-            uint4 ca[MERGE_CPT], cb[MERGE_CPT];
+        if (t < MERGE_PAL) sm.pal[t] = SKEY_EMPTY;
+        // all loads of the tile first (two 128-bit loads per candidate)
+        uint4 ca[MERGE_CPT], cb[MERGE_CPT];
 #pragma unroll
-            for (int j = 0; j < MERGE_CPT; ++j) {
-                const uint32_t i = t + j * MERGE_THREADS;
-                if (i < m) {
-                    const uint4* p = cand_ptr(c0 + i);
-                    ca[j] = ldg_stream_u4(p);
-                    cb[j] = ldg_stream_u4(p + 1);
-                } else {
-                    ca[j] = make_uint4(0, 0, 0, 0);
-                    cb[j] = make_uint4(0, 0, 0xffffffffu, 0);      // tid = -1: skipped
+        for (int j = 0; j < MERGE_CPT; ++j) {
+            const uint32_t i = t + j * MERGE_THREADS;
+            if (i < m) {
+                const uint4* p = reinterpret_cast<const uint4*>(cands + (size_t)tb0 + i);
+                ca[j] = ldg_stream_u4(p);
+                cb[j] = ldg_stream_u4(p + 1);
+            } else {
+                ca[j] = make_uint4(0, 0, 0, 0);
+                cb[j] = make_uint4(0, 0, 0xffffffffu, 0);      // tid = -1: skipped
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < MERGE_CPT; ++j) {
+            const uint32_t start = ca[j].x, end = ca[j].y, ts = ca[j].z, te = ca[j].w;
+            const int32_t tid = (int32_t)cb[j].z;
+            if (tid < 0) continue;
+            ++n_valid;
+            const uint32_t ilen = end - start;                                   // uint32, :161-162
+            if (ilen < prm.min_intron || ilen > prm.max_intron) continue;         // junction_qc
+            const uint32_t lr = ((start - ts) >= prm.min_anchor ? 1u : 0u) | ((te - end) >= prm.min_anchor ? 2u : 0u);
+            const uint32_t sc = cb[j].w & 0xffu, vreg = cb[j].w >> 8;           // vreg = variant region + 1 / barcode id + 1 (0 outside those modes)
+            const uint32_t proxy = sc == '+' ? 0u : (sc == '-' ? 1u : 2u);         // :186-193
+            const unsigned long long ord = (unsigned long long)cb[j].y << 32 | cb[j].x;
+            const unsigned long long nfirst = ~ord;
+            const unsigned long long last = proxy == 2u ? ((ord >> 16) << 8 | sc) : 0ull;
+            bool done = false;
+            // (contig, region) -> palette index: the first MERGE_PAL distinct pairs of the tile (a BAM is sorted: nearly always 1-2)
+            uint32_t pi = MERGE_PAL;
+            {
+                const unsigned long long ck = (unsigned long long)vreg << 32 | (uint32_t)tid;
+#pragma unroll
+                for (uint32_t q = 0; q < (uint32_t)MERGE_PAL; ++q) {
+                    unsigned long long cur = sm.pal[q];
+                    if (cur == SKEY_EMPTY) cur = atomicCAS(&sm.pal[q], SKEY_EMPTY, ck);
+                    if (cur == SKEY_EMPTY || cur == ck) { pi = q; break; }
                 }
             }
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < MERGE_CPT; ++j) {
-                const uint32_t start = ca[j].x, end = ca[j].y, ts = ca[j].z, te = ca[j].w;
-                const int32_t tid = (int32_t)cb[j].z;
-                if (tid < 0) continue;
-                ++n_valid;
-                const uint32_t ilen = end - start;                                   // uint32, :161-162
-                if (ilen < prm.min_intron || ilen > prm.max_intron) continue;         // junction_qc
-                const uint32_t lr = ((start - ts) >= prm.min_anchor ? 1u : 0u) | ((te - end) >= prm.min_anchor ? 2u : 0u);
-                const uint32_t sc = cb[j].w & 0xffu, vreg = cb[j].w >> 8;           // vreg = variant region + 1 (0 outside that mode)
-                const uint32_t proxy = sc == '+' ? 0u : (sc == '-' ? 1u : 2u);         // :186-193
-                const unsigned long long ord = (unsigned long long)cb[j].y << 32 | cb[j].x;
-                const unsigned long long nfirst = ~ord;
-                const unsigned long long last = proxy == 2u ? ((ord >> 16) << 8 | sc) : 0ull;
-                bool done = false;
-                // (contig, region) -> palette index: the first MERGE_PAL distinct pairs of the chunk (a BAM is sorted: nearly always 1-2)
-                uint32_t pi = MERGE_PAL;
-                {
-                    const unsigned long long ck = (unsigned long long)vreg << 32 | (uint32_t)tid;
-#pragma unroll
-                    for (uint32_t q = 0; q < (uint32_t)MERGE_PAL; ++q) {
-                        unsigned long long cur = sm.pal[q];
-                        if (cur == SKEY_EMPTY) cur = atomicCAS(&sm.pal[q], SKEY_EMPTY, ck);
-                        if (cur == SKEY_EMPTY || cur == ck) { pi = q; break; }
+            if (pi < (uint32_t)MERGE_PAL && ilen < (1u << 26)) {
+                const unsigned long long k = (unsigned long long)start << 30 | (unsigned long long)ilen << 4 | pi << 2 | proxy;
+                uint32_t s = mix_key(k, 0ull) & (MERGE_SLOTS - 1);
+                for (int probe = 0; probe < MERGE_PROBES; ++probe, s = (s + 1) & (MERGE_SLOTS - 1)) {
+                    unsigned long long cur = sm.key[s];
+                    if (cur == SKEY_EMPTY) cur = atomicCAS(&sm.key[s], SKEY_EMPTY, k);
+                    if (cur == SKEY_EMPTY || cur == k) {
+                        atomicAdd(&sm.count[s], 1u);
+                        atomicMax(&sm.nts[s], ~ts);
+                        atomicMax(&sm.te[s], te);
+                        if (lr) atomicOr(&sm.lr[s], lr);
+                        atomicMax(&sm.nfirst[s], nfirst);
+                        if (last) atomicMax(&sm.last[s], last);
+                        done = true;
+                        break;
                     }
                 }
-                if (pi < (uint32_t)MERGE_PAL && ilen < (1u << 26)) {
-                    const unsigned long long k = (unsigned long long)start << 30 | (unsigned long long)ilen << 4 | pi << 2 | proxy;
-                    uint32_t s = mix_key(k, 0ull) & (MERGE_SLOTS - 1);
-                    for (int probe = 0; probe < MERGE_PROBES; ++probe, s = (s + 1) & (MERGE_SLOTS - 1)) {
-                        unsigned long long cur = sm.key[s];
-                        if (cur == SKEY_EMPTY) cur = atomicCAS(&sm.key[s], SKEY_EMPTY, k);
-                        if (cur == SKEY_EMPTY || cur == k) {
-                            atomicAdd(&sm.count[s], 1u);
-                            atomicMax(&sm.nts[s], ~ts);
-                            atomicMax(&sm.te[s], te);
-                            if (lr) atomicOr(&sm.lr[s], lr);
-                            atomicMax(&sm.nfirst[s], nfirst);
-                            if (last) atomicMax(&sm.last[s], last);
-                            done = true;
-                            break;
-                        }
-                    }
-                }
-                if (!done) {
-                    K128 key{(unsigned long long)start << 32 | end, (unsigned long long)vreg << 34 | ((unsigned long long)(uint32_t)(tid + 1)) << 2 | proxy};
-                    if (!table_upsert(tb, key, 1u, ~ts, te, lr, nfirst, last, counters))
-                        spill_entry(spill, spill_cap, counters, key, 1u, ~ts, te, lr, nfirst, last);
-                }
             }
-            __syncthreads();
-            // one global upsert per distinct junction of the chunk
-            for (uint32_t s = t; s < MERGE_SLOTS; s += MERGE_THREADS) {
-                const unsigned long long k = sm.key[s];
-                if (k == SKEY_EMPTY) continue;
-                const uint32_t start = (uint32_t)(k >> 30), ilen = (uint32_t)(k >> 4) & 0x03ffffffu, proxy = (uint32_t)k & 3u;
-                const unsigned long long ck = sm.pal[((uint32_t)k >> 2) & 3u];
-                K128 key{(unsigned long long)start << 32 | (uint32_t)(start + ilen),
-                         (ck >> 32) << 34 | ((unsigned long long)((uint32_t)ck + 1u)) << 2 | proxy};
-                if (!table_upsert(tb, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s], counters))
-                    spill_entry(spill, spill_cap, counters, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s]);
+            if (!done) {
+                K128 key{(unsigned long long)start << 32 | end, (unsigned long long)vreg << 34 | ((unsigned long long)(uint32_t)(tid + 1)) << 2 | proxy};
+                if (!table_upsert(tb, key, 1u, ~ts, te, lr, nfirst, last, counters))
+                    spill_entry(spill, spill_cap, counters, key, 1u, ~ts, te, lr, nfirst, last);
             }
-            __syncthreads();
         }
-        __syncthreads();            // rpre is rewritten by the next region tile
+        __syncthreads();
+        // one global upsert per distinct junction of the tile
+        for (uint32_t s = t; s < MERGE_SLOTS; s += MERGE_THREADS) {
+            const unsigned long long k = sm.key[s];
+            if (k == SKEY_EMPTY) continue;
+            const uint32_t start = (uint32_t)(k >> 30), ilen = (uint32_t)(k >> 4) & 0x03ffffffu, proxy = (uint32_t)k & 3u;
+            const unsigned long long ck = sm.pal[((uint32_t)k >> 2) & 3u];
+            K128 key{(unsigned long long)start << 32 | (uint32_t)(start + ilen),
+                     (ck >> 32) << 34 | ((unsigned long long)((uint32_t)ck + 1u)) << 2 | proxy};
+            if (!table_upsert(tb, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s], counters))
+                spill_entry(spill, spill_cap, counters, key, sm.count[s], sm.nts[s], sm.te[s], sm.lr[s], sm.nfirst[s], sm.last[s]);
+        }
+        __syncthreads();
     }
     n_valid = __reduce_add_sync(0xffffffffu, n_valid);
     if ((t & 31u) == 0 && n_valid) atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_TOTAL_CAND64), (unsigned long long)n_valid);
@@ -1703,426 +995,17 @@ static int num_sms() {
     return g_num_sms;
 }
 
-void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound, const CandRegions& regions,
-                           const ScanParams& p, const TableRef& tb, Slot* spill_slots, uint32_t spill_cap, uint32_t* d_counters,
-                           cudaStream_t stream) {
-    if (n_cand_bound == 0 && !regions.base) return;
+void launch_junction_merge(const Cand* cands, const uint32_t* d_n_cand, uint32_t n_cand_bound, const ScanParams& p, const TableRef& tb,
+                           Slot* spill_slots, uint32_t spill_cap, uint32_t* d_counters, cudaStream_t stream) {
+    if (n_cand_bound == 0) return;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(junction_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MergeSmem));
         attr_set = true;
     }
-    uint32_t tiles = (n_cand_bound + MERGE_TILE - 1) / MERGE_TILE + (regions.base ? (regions.n_regions + MERGE_RGROUP - 1) / MERGE_RGROUP : 0u);
-    uint32_t grid = max(1u, min(tiles, (uint32_t)(2 * num_sms())));
-    junction_merge_kernel<<<grid, MERGE_THREADS, sizeof(MergeSmem), stream>>>(
-        cands, d_n_cand, n_cand_bound, regions, p, tb, spill_slots, spill_cap, d_counters);
-}
-
-// ------------------------------------------------------------------------------------------------
-// cigar_scan, fused version (variant 6; opt-in: rtjx_params.scan_variant = 6)
-// ------------------------------------------------------------------------------------------------
-// parse_alignment_into_junctions (:377-497) + set_junction_strand (:345-359) + junction_qc (:160-170) +
-// add_junction (:174-235) in ONE kernel: no candidate list in HBM, no second kernel.
-// Measured on the 10M-read C2 batch: 117 us for scan + merge in one launch against 71 + 58 us for the default
-// two-kernel path (variant 5); variant 5 stays the default because its scan kernel alone is the path's roofline line.
-//
-// Shape, as measured on B200 (tools/ab_scan.py):
-//  * one block = one tile of 4*THREADS consecutive alignments, many small blocks per SM whose phases the block
-//    scheduler overlaps (persistent rings with deeper prefetch were measured and are slower on this path);
-//  * tiles are REGISTER-staged: 128-bit ld.global of the four metadata columns -> st.shared, then (its address is
-//    the only data-dependent one) the tile's CIGAR slab the same way.  cp.async/LDGSTS and bulk copies top out at
-//    ~0.66 of the copy peak for this tile pattern, plain loads reach 0.76 (the practical ceiling for 212 MB);
-//  * while the slab is in flight the n_cigar > 1 alignments are compacted (ballot + warp prefix) into a work list;
-//  * one thread per compacted alignment walks the CIGAR (closed form, SURVEY App. A.2, first four ops loaded
-//    independently, up to two candidates kept in registers) and applies QC;
-//  * the lanes of a warp that hold the same junction are combined by a leader-election loop (ballot + redux; a
-//    BAM is coordinate sorted, so a warp usually holds 1-5 distinct junctions), the leaders accumulate into the
-//    block's 128-slot shared-memory table (32-bit tile-local ordinals);
-//  * one upsert per distinct junction of the tile goes to the device-wide table (128-bit CAS claim + REDs).
-constexpr int S6_HS = 128;                                   // shared-memory table slots per block
-constexpr int S6_PROBES = 16;
-constexpr int S6_SV = 4;                                     // slab vectors (16 B) staged per thread: 2048 words cover a fully spliced tile
-template <int THREADS>
-struct alignas(16) S6Smem {
-    uint32_t off[THREADS * 4 + 4];
-    uint32_t pos[THREADS * 4];
-    uint32_t meta[THREADS * 4];
-    uint32_t tid[THREADS * 4];
-    uint32_t slab[THREADS * 4 * S6_SV];
-    unsigned long long hkey[S6_HS];
-    uint32_t hval[6][S6_HS];                                 // count, ~thick_start, thick_end, lr, ~first(local), last(local)
-    uint16_t work[THREADS * 4];
-    uint32_t n_work, sink;
-};
-
-struct FusedCtx { TableRef tb; Slot* spill; uint32_t spill_cap; uint32_t* counters; };
-
-// One (already combined) update of the device-wide table; tile-local 32-bit ordinals become global here.
-// Kept out of line: it has several call sites and the scan kernel's hot path has to stay small.
-__device__ __noinline__ void fused_global_upsert(const FusedCtx& cx, uint64_t ord0, uint32_t start, uint32_t end, int32_t tid,
-                                                 uint32_t proxy, uint32_t count, uint32_t nts, uint32_t te, uint32_t lr,
-                                                 uint32_t nfirst_l, uint32_t last_l) {
-    const uint32_t lord = ~nfirst_l;
-    const unsigned long long nfirst = ~(((ord0 + (lord >> 16)) << 16) | (lord & 0xffffu));
-    const unsigned long long last = last_l ? ((ord0 + (last_l >> 8)) << 8 | (last_l & 0xffu)) : 0ull;
-    const K128 key{(unsigned long long)start << 32 | end, ((unsigned long long)(uint32_t)(tid + 1)) << 2 | proxy};
-    if (!table_upsert(cx.tb, key, count, nts, te, lr, nfirst, last, cx.counters))
-    spill_entry(cx.spill, cx.spill_cap, cx.counters, key, count, nts, te, lr, nfirst, last);
-}
-
-// The third and later N ops of one alignment (long-read style CIGARs; rare): plain walk from global memory, QC,
-// one global upsert each.  Out of line so that the hot walk carries no call.
-__device__ __noinline__ void fused_walk_rest(const FusedCtx& cx, const ScanParams& prm, uint64_t ord0, const uint32_t* __restrict__ ops,
-                                             uint32_t n, uint32_t pos, uint32_t r, int32_t tid, uint32_t sc) {
-    const uint32_t ANC = (1u << 0) | (1u << 7);
-    const uint32_t BRK = (1u << 3) | (1u << 2) | (1u << 8) | (1u << 1) | (1u << 4);
-    const uint32_t REFC = ANC | (1u << 2) | (1u << 8) | (1u << 3);
-    const uint32_t proxy = sc == '+' ? 0u : (sc == '-' ? 1u : 2u);
-    uint32_t cur = pos, run = 0, nc = 0;
-    bool pending = false;
-    WalkCand c{0, 0, 0, 0, 0};
-    auto emit = [&]() {
-        const uint32_t ilen = c.end - c.start;
-        if (nc <= 2u || ilen < prm.min_intron || ilen > prm.max_intron) return;
-        fused_global_upsert(cx, ord0, c.start, c.end, tid, proxy, 1u, ~(c.start - c.left), c.end + c.right,
-                            (c.left >= prm.min_anchor ? 1u : 0u) | (c.right >= prm.min_anchor ? 2u : 0u),
-                            ~(r << 16 | c.k), proxy == 2u ? (r << 8 | sc) : 0u);
-    };
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t x = __ldg(ops + i), op = x & 0xfu, len = x >> 4, bit = 1u << op;
-        if (bit & BRK) {
-            if (pending) { c.right = run; emit(); }
-            pending = op == 3u;
-            if (pending) { c.start = cur; c.end = cur + len; c.left = run; c.k = i > 0xffffu ? 0xffffu : i; ++nc; }
-            run = 0;
-        } else if (bit & ANC) {
-            run += len;
-        }
-        if (bit & REFC) cur += len;
-    }
-    if (pending) { c.right = run; emit(); }
-}
-
-template <int THREADS, int MIN_BLOCKS>
-__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
-cigar_scan_fused_kernel(BatchView b, ScanParams prm, TableRef tb, Slot* __restrict__ spill, uint32_t spill_cap,
-                        uint32_t* __restrict__ counters) {
-    using Smem = S6Smem<THREADS>;
-    constexpr uint32_t TILE = THREADS * 4, SLAB = THREADS * 4 * S6_SV;
-    __shared__ Smem sm;
-    const uint32_t t = threadIdx.x, lane = t & 31u;
-    const uint32_t base = blockIdx.x * TILE;
-    const uint32_t n_tile = min(TILE, b.n_reads - base);
-    const uint32_t vec_end = b.n_ops & ~3u;
-
-    // ---- phase 1: the four metadata columns, 128-bit loads -> registers -> shared memory
-    if (base + TILE + 3 <= b.n_reads) {
-        const uint4 o = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cig_off + base) + t);
-        const uint4 p = ldg_stream_u4(reinterpret_cast<const uint4*>(b.pos + base) + t);
-        const uint4 m = ldg_stream_u4(reinterpret_cast<const uint4*>(b.meta + base) + t);
-        const uint4 d = ldg_stream_u4(reinterpret_cast<const uint4*>(b.tid + base) + t);
-        if (t == 0) sm.off[TILE] = __ldg(b.cig_off + base + TILE);
-        *reinterpret_cast<uint4*>(&sm.off[4 * t]) = o;
-        *reinterpret_cast<uint4*>(&sm.pos[4 * t]) = p;
-        *reinterpret_cast<uint4*>(&sm.meta[4 * t]) = m;
-        *reinterpret_cast<uint4*>(&sm.tid[4 * t]) = d;
-    } else {                                                 // ragged tail of the batch
-        for (uint32_t r = t; r < n_tile; r += THREADS) {
-            sm.pos[r] = (uint32_t)b.pos[base + r]; sm.meta[r] = b.meta[base + r]; sm.tid[r] = (uint32_t)b.tid[base + r];
-        }
-        for (uint32_t r = t; r <= n_tile; r += THREADS) sm.off[r] = b.cig_off[base + r];
-    }
-    for (uint32_t s = t; s < (uint32_t)S6_HS; s += THREADS) {
-        sm.hkey[s] = SKEY_EMPTY;
-#pragma unroll
-        for (int f = 0; f < 6; ++f) sm.hval[f][s] = 0u;
-    }
-    if (t == 0) { sm.n_work = 0; sm.sink = 0; }
-    __syncthreads();
-    if (prm.debug & 16u) return;
-
-    // ---- phase 2: the tile's CIGAR slab [lo, hi) (the only data-dependent address of the path); at most SLAB words
-    // are staged, the rest of a dense tile is warmed in L2 and read from there
-    const uint32_t lo = sm.off[0], hi = sm.off[n_tile], a0 = lo & ~3u;
-    uint32_t n_st = 0;
-    if (hi > lo) {
-        const uint32_t end = min(min((hi + 3u) & ~3u, a0 + SLAB), vec_end);
-        n_st = end > a0 ? end - a0 : 0u;
-    }
-    uint4 sv[S6_SV];
-#pragma unroll
-    for (int j = 0; j < S6_SV; ++j) {
-        const uint32_t v = t + j * THREADS;
-        if (4u * v < n_st) sv[j] = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cigar + a0) + v);
-    }
-    if (t == 32 % THREADS && hi > lo) {
-        const uint32_t end = min((hi + 3u) & ~3u, vec_end);
-        if (end > a0 + n_st) bulk_prefetch_l2(b.cigar + a0 + n_st, (end - a0 - n_st) * 4u);
-    }
-    // ---- while the slab is in flight: compact the alignments with more than one CIGAR op (junctions_extractor.cc:379)
-    {
-        const uint4 o = *reinterpret_cast<const uint4*>(&sm.off[4 * t]);
-        const uint32_t o4 = sm.off[4 * t + 4];
-        const uint32_t r0 = 4 * t;
-        uint32_t flags = 0;
-        if (r0 + 0 < n_tile && o.y - o.x > 1u) flags |= 1u;
-        if (r0 + 1 < n_tile && o.z - o.y > 1u) flags |= 2u;
-        if (r0 + 2 < n_tile && o.w - o.z > 1u) flags |= 4u;
-        if (r0 + 3 < n_tile && o4 - o.w > 1u) flags |= 8u;
-        const uint32_t cnt = __popc(flags);
-        uint32_t x = cnt;
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
-        uint32_t wbase = 0;
-        if (lane == 31 && x) wbase = atomicAdd(&sm.n_work, x);
-        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        uint32_t p = wbase + x - cnt;
-        if (flags & 1u) sm.work[p++] = (uint16_t)(r0 + 0);
-        if (flags & 2u) sm.work[p++] = (uint16_t)(r0 + 1);
-        if (flags & 4u) sm.work[p++] = (uint16_t)(r0 + 2);
-        if (flags & 8u) sm.work[p++] = (uint16_t)(r0 + 3);
-    }
-#pragma unroll
-    for (int j = 0; j < S6_SV; ++j) {
-        const uint32_t v = t + j * THREADS;
-        if (4u * v < n_st) *reinterpret_cast<uint4*>(&sm.slab[4 * v]) = sv[j];
-    }
-    __syncthreads();
-    const uint32_t n_work = (prm.debug & 1u) ? 0u : sm.n_work;
-    if (n_work == 0) return;
-
-    // ---- phase 3: walk, QC, combine, accumulate
-    const FusedCtx cx{tb, spill, spill_cap, counters};
-    const int32_t base_tid = (int32_t)sm.tid[0];
-    const uint64_t ord0 = b.first_ordinal + base;
-    uint32_t my_cands = 0;
-    for (uint32_t w0 = 0; w0 < n_work; w0 += THREADS) {      // warp-uniform trip count
-        const uint32_t i = w0 + t;
-        uint32_t nc = 0, r = 0, sc = 0;
-        int32_t tid = -1;
-        WalkCand c0{0, 0, 0, 0, 0}, c1{0, 0, 0, 0, 0};
-        if (i < n_work) {
-            r = sm.work[i];
-            tid = (int32_t)sm.tid[r];
-            if (tid >= 0) {
-                const uint32_t o0 = sm.off[r], n = sm.off[r + 1] - o0;
-                sc = read_strand(sm.meta[r], prm.strandness);
-                nc = (o0 - a0) + n <= n_st ? walk_collect<true>(sm.slab + (o0 - a0), n, sm.pos[r], c0, c1)
-                                           : walk_collect<false>(b.cigar + o0, n, sm.pos[r], c0, c1);
-                my_cands += nc;
-                if (nc > 2u && !(prm.debug & 2u)) fused_walk_rest(cx, prm, ord0, b.cigar + o0, n, sm.pos[r], r, tid, sc);
-            }
-        }
-        // junction_qc (:160-170) + add_junction (:174-235): warp-uniform passes over the (at most two) register
-        // candidates of every lane
-        for (uint32_t pass = 0; pass < 2u; ++pass) {
-            bool has = nc > pass;
-            if (!__any_sync(0xffffffffu, has)) break;
-            const WalkCand c = pass ? c1 : c0;
-            const uint32_t ilen = c.end - c.start;                                      // uint32, :161-162
-            has = has && ilen >= prm.min_intron && ilen <= prm.max_intron;
-            const uint32_t nts = ~(c.start - c.left), te = c.end + c.right;
-            const uint32_t lr = (c.left >= prm.min_anchor ? 1u : 0u) | (c.right >= prm.min_anchor ? 2u : 0u);
-            const uint32_t proxy = sc == '+' ? 0u : (sc == '-' ? 1u : 2u);               // :186-193
-            const uint32_t nfirst_l = ~(r << 16 | c.k);
-            const uint32_t last_l = proxy == 2u ? (r << 8 | sc) : 0u;
-            if (prm.debug & 2u) { if (has && (nts ^ te ^ lr ^ nfirst_l ^ last_l) == 0x9e3779b9u) sm.sink = 1; continue; }
-            if (has && (tid != base_tid || ilen >= (1u << 28))) {                      // not expressible in the block table's key
-                fused_global_upsert(cx, ord0, c.start, c.end, tid, proxy, 1u, nts, te, lr, nfirst_l, last_l);
-                has = false;
-            }
-            const unsigned long long key = (unsigned long long)c.start << 30 | (unsigned long long)ilen << 2 | proxy;
-            // leader election: every distinct junction of the warp is reduced onto its first lane
-            uint32_t todo = __ballot_sync(0xffffffffu, has);
-            bool leader = false;
-            uint32_t g_cnt = 0, g_nts = 0, g_te = 0, g_lr = 0, g_nf = 0, g_last = 0;
-            while (todo) {
-                const int src = __ffs(todo) - 1;
-                const unsigned long long k = __shfl_sync(0xffffffffu, key, src);
-                const bool in = has && key == k;
-                const uint32_t grp = __ballot_sync(0xffffffffu, in);
-                const uint32_t a1 = __reduce_max_sync(0xffffffffu, in ? nts : 0u), a2 = __reduce_max_sync(0xffffffffu, in ? te : 0u);
-                const uint32_t a3 = __reduce_or_sync(0xffffffffu, in ? lr : 0u), a4 = __reduce_max_sync(0xffffffffu, in ? nfirst_l : 0u);
-                const uint32_t a5 = __reduce_max_sync(0xffffffffu, in ? last_l : 0u);
-                if ((int)lane == src) { leader = true; g_cnt = __popc(grp); g_nts = a1; g_te = a2; g_lr = a3; g_nf = a4; g_last = a5; }
-                todo &= ~grp;
-            }
-            if (leader) {                                    // all leaders of the pass insert in parallel (distinct keys)
-                uint32_t s = ((uint32_t)key * 0x9E3779B1u ^ (uint32_t)(key >> 32) * 0x85EBCA77u) >> 25;   // 7 bits: S6_HS = 128
-                bool done = false;
-                for (int probe = 0; probe < S6_PROBES && !done; ++probe, s = (s + 1u) & (S6_HS - 1)) {
-                    unsigned long long curk = sm.hkey[s];
-                    if (curk == SKEY_EMPTY) curk = atomicCAS(&sm.hkey[s], SKEY_EMPTY, key);
-                    if (curk == SKEY_EMPTY || curk == key) {
-                        atomicAdd(&sm.hval[0][s], g_cnt);
-                        atomicMax(&sm.hval[1][s], g_nts);
-                        atomicMax(&sm.hval[2][s], g_te);
-                        if (g_lr) atomicOr(&sm.hval[3][s], g_lr);
-                        atomicMax(&sm.hval[4][s], g_nf);
-                        if (g_last) atomicMax(&sm.hval[5][s], g_last);
-                        done = true;
-                    }
-                }
-                if (!done) fused_global_upsert(cx, ord0, c.start, c.end, tid, proxy, g_cnt, g_nts, g_te, g_lr, g_nf, g_last);
-            }
-        }
-    }
-    __syncthreads();
-    // ---- phase 4: one global upsert per distinct junction of the tile
-    if (!(prm.debug & 8u)) {
-        for (uint32_t s = t; s < (uint32_t)S6_HS; s += THREADS) {
-            const unsigned long long key = sm.hkey[s];
-            if (key == SKEY_EMPTY) continue;
-            const uint32_t start = (uint32_t)(key >> 30), ilen = (uint32_t)(key >> 2) & 0x0fffffffu;
-            fused_global_upsert(cx, ord0, start, start + ilen, base_tid, (uint32_t)key & 3u, sm.hval[0][s], sm.hval[1][s], sm.hval[2][s],
-                                sm.hval[3][s], sm.hval[4][s], sm.hval[5][s]);
-        }
-    }
-    // statistics: N ops seen (before QC), one 64-bit RED per warp
-    my_cands = __reduce_add_sync(0xffffffffu, my_cands);
-    if (lane == 0 && my_cands) atomicAdd(reinterpret_cast<unsigned long long*>(counters + CTR_TOTAL_CAND64), (unsigned long long)my_cands);
-}
-
-// A/B probe (scan_debug bit 5): reads the five arrays of the batch once with plain 128-bit loads and nothing else —
-// the practical read ceiling of the device for a batch of this size, next to which cigar_scan's time is judged.
-__global__ void __launch_bounds__(256)
-stream_probe_kernel(BatchView b, uint32_t* __restrict__ counters) {
-    const uint4* cols[5] = {reinterpret_cast<const uint4*>(b.tid), reinterpret_cast<const uint4*>(b.pos),
-                            reinterpret_cast<const uint4*>(b.meta), reinterpret_cast<const uint4*>(b.cig_off),
-                            reinterpret_cast<const uint4*>(b.cigar)};
-    const size_t nvec[5] = {b.n_reads / 4u, b.n_reads / 4u, b.n_reads / 4u, b.n_reads / 4u, b.n_ops / 4u};
-    uint32_t acc = 0;
-    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-#pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        size_t i = t0;
-        for (; i + 3 * stride < nvec[c]; i += 4 * stride) {
-            const uint4 x0 = ldg_stream_u4(cols[c] + i), x1 = ldg_stream_u4(cols[c] + i + stride);
-            const uint4 x2 = ldg_stream_u4(cols[c] + i + 2 * stride), x3 = ldg_stream_u4(cols[c] + i + 3 * stride);
-            acc ^= x0.x ^ x0.y ^ x0.z ^ x0.w ^ x1.x ^ x1.y ^ x1.z ^ x1.w ^ x2.x ^ x2.y ^ x2.z ^ x2.w ^ x3.x ^ x3.y ^ x3.z ^ x3.w;
-        }
-        for (; i < nvec[c]; i += stride) { const uint4 x = ldg_stream_u4(cols[c] + i); acc ^= x.x ^ x.y ^ x.z ^ x.w; }
-    }
-    if (acc == 0x9e3779b9u) atomicAdd(&counters[CTR_NOUT], 1u);
-}
-
-// A/B probe (scan_debug bit 6): the SAME access pattern as cigar_scan (512-alignment tiles: 2 KB of each of the four
-// columns + the tile's CIGAR slab, tiles strided over a persistent grid) but with plain register loads and no shared
-// memory: separates "the pattern" from "the cp.async staging".
-template <bool STAGE>
-__global__ void __launch_bounds__(128)
-tile_probe_kernel(BatchView b, uint32_t* __restrict__ counters) {
-    __shared__ uint4 stage[STAGE ? 680 : 1];
-    const uint32_t t = threadIdx.x, n_tiles = b.n_reads / 512u;
-    uint32_t acc = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t base = tile * 512u;
-        const uint4 o = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cig_off + base) + t);
-        const uint4 p = ldg_stream_u4(reinterpret_cast<const uint4*>(b.pos + base) + t);
-        const uint4 m = ldg_stream_u4(reinterpret_cast<const uint4*>(b.meta + base) + t);
-        const uint4 d = ldg_stream_u4(reinterpret_cast<const uint4*>(b.tid + base) + t);
-        const uint32_t lo = __shfl_sync(0xffffffffu, o.x, 0);           // warp 0's lane 0 holds cig_off[base]; good enough for a probe
-        const uint32_t a0 = (lo & ~3u) + 4u * t;
-        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-        if (a0 + 4u <= b.n_ops) c0 = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cigar + a0));
-        if (t < 40u && a0 + 516u <= b.n_ops) c1 = ldg_stream_u4(reinterpret_cast<const uint4*>(b.cigar + a0 + 512u));
-        if (STAGE) {                                          // register-staged copy into shared memory + block barrier per tile
-            __syncthreads();
-            stage[t] = o; stage[128 + t] = p; stage[256 + t] = m; stage[384 + t] = d; stage[512 + t] = c0;
-            if (t < 40u) stage[640 + t] = c1;
-            __syncthreads();
-            acc ^= stage[(t * 7u) % 680u].y;
-        } else {
-            acc ^= o.x ^ o.w ^ p.x ^ p.w ^ m.x ^ m.w ^ d.x ^ d.w ^ c0.x ^ c0.w ^ c1.x ^ c1.w;
-        }
-    }
-    if (acc == 0x9e3779b9u) atomicAdd(&counters[CTR_NOUT], 1u);
-}
-
-// A/B probe (scan_debug bit 18 with bit 6; hint in bits 16-17): the tile pattern through cp.async (LDGSTS) into a 2-deep shared-memory
-// ring, with an optional L2 prefetch-size hint on the copies.  HINT: 0 none, 1 L2::128B, 2 L2::256B.
-template <int HINT>
-__device__ __forceinline__ void cp_async16_hint(void* dst, const void* src) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-    if (HINT == 2) asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-    else if (HINT == 1) asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-}
-template <int HINT>
-__global__ void __launch_bounds__(128)
-tile_probe_async_kernel(BatchView b, uint32_t* __restrict__ counters) {
-    __shared__ uint4 ring[2][768];
-    const uint32_t t = threadIdx.x, n_tiles = b.n_reads / 512u;
-    const uint32_t words_per_tile = (b.n_ops / n_tiles) & ~3u;          // stand-in for the slab address: no dependent load in a probe
-    uint32_t acc = 0, it = 0;
-    auto issue = [&](uint32_t tile, uint4* buf) {
-        const uint32_t base = tile * 512u;
-        cp_async16_hint<HINT>(buf + t, reinterpret_cast<const uint4*>(b.cig_off + base) + t);
-        cp_async16_hint<HINT>(buf + 128 + t, reinterpret_cast<const uint4*>(b.pos + base) + t);
-        cp_async16_hint<HINT>(buf + 256 + t, reinterpret_cast<const uint4*>(b.meta + base) + t);
-        cp_async16_hint<HINT>(buf + 384 + t, reinterpret_cast<const uint4*>(b.tid + base) + t);
-        const uint32_t a0 = tile * words_per_tile + 4u * t;
-        if (a0 + 4u <= b.n_ops) cp_async16_hint<HINT>(buf + 512 + t, b.cigar + a0);
-        if (t < 40u && a0 + 516u <= b.n_ops) cp_async16_hint<HINT>(buf + 640 + t, b.cigar + a0 + 512u);
-    };
-    if (blockIdx.x < n_tiles) issue(blockIdx.x, ring[0]);
-    cp_async_commit();
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        if (tile + gridDim.x < n_tiles) issue(tile + gridDim.x, ring[(it + 1) & 1]);
-        cp_async_commit();
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncthreads();
-        acc ^= ring[it & 1][(t * 7u) % 680u].y;
-        __syncthreads();
-    }
-    if (acc == 0x9e3779b9u) atomicAdd(&counters[CTR_NOUT], 1u);
-}
-
-template <int THREADS, int MIN_BLOCKS>
-static void launch_fused_cfg(const BatchView& b, const ScanParams& p, const TableRef& tb, Slot* spill, uint32_t spill_cap,
-                             uint32_t* d_counters, cudaStream_t stream) {
-    static bool once = false;
-    if (!once) {
-        once = true;
-        cudaFuncSetAttribute(cigar_scan_fused_kernel<THREADS, MIN_BLOCKS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        if (getenv("RTJX_TRACE")) {
-            int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cigar_scan_fused_kernel<THREADS, MIN_BLOCKS>, THREADS, 0);
-            fprintf(stderr, "[rtjx] cigar_scan_fused<%d,%d>: %zu B shared memory, %d blocks/SM, %d SMs\n", THREADS, MIN_BLOCKS,
-                    sizeof(S6Smem<THREADS>), nb, num_sms());
-        }
-    }
-    const uint32_t tiles = (b.n_reads + THREADS * 4 - 1) / (THREADS * 4);
-    cigar_scan_fused_kernel<THREADS, MIN_BLOCKS><<<tiles, THREADS, 0, stream>>>(b, p, tb, spill, spill_cap, d_counters);
-}
-
-bool launch_cigar_scan_fused(const BatchView& b, const ScanParams& p, const TableRef& tb, Slot* spill, uint32_t spill_cap,
-                             uint32_t* d_counters, cudaStream_t stream) {
-    if (b.n_reads == 0) return true;
-    const uintptr_t align = reinterpret_cast<uintptr_t>(b.tid) | reinterpret_cast<uintptr_t>(b.pos) |
-                            reinterpret_cast<uintptr_t>(b.meta) | reinterpret_cast<uintptr_t>(b.cig_off) |
-                            reinterpret_cast<uintptr_t>(b.cigar);
-    if (align & 15u) return false;
-    if (p.debug & 32u) { stream_probe_kernel<<<num_sms() * 8, 256, 0, stream>>>(b, d_counters); return true; }
-    if (p.debug & 64u) {
-        const uint32_t per_sm = ((p.debug >> 8) & 0xffu) ? ((p.debug >> 8) & 0xffu) : 16u;
-        if (p.debug & (1u << 18)) {
-            const uint32_t hint = (p.debug >> 16) & 3u;
-            if (hint == 2) tile_probe_async_kernel<2><<<num_sms() * per_sm, 128, 0, stream>>>(b, d_counters);
-            else if (hint == 1) tile_probe_async_kernel<1><<<num_sms() * per_sm, 128, 0, stream>>>(b, d_counters);
-            else tile_probe_async_kernel<0><<<num_sms() * per_sm, 128, 0, stream>>>(b, d_counters);
-        } else if (p.debug & 128u) tile_probe_kernel<true><<<num_sms() * per_sm, 128, 0, stream>>>(b, d_counters);
-        else tile_probe_kernel<false><<<num_sms() * per_sm, 128, 0, stream>>>(b, d_counters);
-        return true;
-    }
-    switch (p.cfg) {            // A/B configurations; 0 is the production one
-    case 1: launch_fused_cfg<128, 10>(b, p, tb, spill, spill_cap, d_counters, stream); break;
-    case 2: launch_fused_cfg<64, 16>(b, p, tb, spill, spill_cap, d_counters, stream); break;
-    case 3: launch_fused_cfg<256, 4>(b, p, tb, spill, spill_cap, d_counters, stream); break;
-    case 4: launch_fused_cfg<128, 6>(b, p, tb, spill, spill_cap, d_counters, stream); break;
-    default: launch_fused_cfg<128, 8>(b, p, tb, spill, spill_cap, d_counters, stream); break;
-    }
-    return true;
+    const uint32_t tiles = (n_cand_bound + MERGE_TILE - 1) / MERGE_TILE;
+    const uint32_t grid = max(1u, min(tiles, (uint32_t)(2 * num_sms())));
+    junction_merge_kernel<<<grid, MERGE_THREADS, sizeof(MergeSmem), stream>>>(cands, d_n_cand, n_cand_bound, p, tb, spill_slots, spill_cap, d_counters);
 }
 
 // Re-inserts every occupied slot of `src` (an old table, or the spill list) into the table.

@@ -76,7 +76,7 @@ class JunctionsExtractor:
                  min_anchor_length: int = 8, min_intron_length: int = 70, max_intron_length: int = 500000,
                  ref: str = "NA", *, device: int = 0, n_threads: int = 0, batch_reads: int = 0,
                  shard_rank: int = 0, shard_world: int = 1, profile: bool = False, table_log2: int = 0,
-                 inflate_mode: int = 0, scan_variant: int = 0, scan_cfg: int = 0, scan_debug: int = 0,
+                 inflate_mode: int = 0, scan_variant: int = 0, scan_cfg: int = 0,
                  _ctor8: bool = False):
         self.bam_ = bam
         self.region_ = region
@@ -93,8 +93,7 @@ class JunctionsExtractor:
         self.barcode_tag_ = "CB"                    # junctions_extractor.h:192,204
         self._opts = dict(device=device, n_threads=n_threads, batch_reads=batch_reads, shard_rank=shard_rank,
                           shard_world=shard_world, profile=int(profile), table_log2=table_log2,
-                          inflate_mode=inflate_mode, scan_variant=scan_variant, scan_cfg=scan_cfg,
-                          scan_debug=scan_debug)
+                          inflate_mode=inflate_mode, scan_variant=scan_variant, scan_cfg=scan_cfg)
         self._h = None
 
     @classmethod

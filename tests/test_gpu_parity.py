@@ -31,7 +31,7 @@ def tables_equal(gpu, cpu):
 
 def run_gpu_batch(arrs, strandness=0, a=8, m=70, M=500000, contigs=("1", "10", "2"), device_resident=False, split=1,
                   variant=0, cfg=0, known=True):
-    """variant 0/5 = cigar_scan + junction_merge, 6 = fused cigar_scan (needs the N-op count: known=True)."""
+    """variant 0/5 = block-per-tile cigar_scan (default), 8 = warp-pipelined cigar_scan; both feed junction_merge."""
     rt = _rt()
     ex = rt.JunctionsExtractor(strandness=strandness, min_anchor_length=a, min_intron_length=m, max_intron_length=M,
                                scan_variant=variant, scan_cfg=cfg)
@@ -69,7 +69,7 @@ def run_oracle_batch(arrs, strandness=0, a=8, m=70, M=500000, contigs=("1", "10"
     return o.table(), o.bed12()
 
 
-@pytest.mark.parametrize("variant,known", [(0, True), (6, True), (0, False)])
+@pytest.mark.parametrize("variant,known", [(0, True), (8, True), (0, False), (8, False)])
 @pytest.mark.parametrize("strandness", [0, 1, 2])
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_random_batches_match_oracle(seed, strandness, variant, known):
@@ -384,8 +384,8 @@ def test_large_generated_bam_property_checks(tmp_path):
 def test_full_size_c2_three_paths_agree():
     """BASELINE configs[1] at full size (10M reads, the bench's BAM): size-independent properties.  The device feeder
     (GPU inflate + record split), the host feeder and the kernel-level batch path must give the same table; names are a
-    permutation of 1..U; order is compare_junctions'; read counts add up to the QC-passing candidates; the fused scan
-    (variant 6) agrees; a sub-region agrees with the oracle run on that region."""
+    permutation of 1..U; order is compare_junctions'; read counts add up to the QC-passing candidates; the warp-pipelined
+    scan kernel (variant 8) agrees; a sub-region agrees with the oracle run on that region."""
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
@@ -408,7 +408,7 @@ def test_full_size_c2_three_paths_agree():
     n_n = synth.count_n_ops(arrs[4])
     assert n_n == st_dev["candidates"]
     d = [torch.from_numpy(x.view(np.int32)).cuda() for x in arrs]
-    for variant in (5, 6):
+    for variant in (5, 8):
         ex = rt.JunctionsExtractor(bam, ".", 0, scan_variant=variant)
         ex.set_contigs(["chr1"])
         ex.scan_batch(*d, n_junction_ops=n_n)

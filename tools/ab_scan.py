@@ -24,12 +24,11 @@ alg = 16.0 * R + 4.0 * C
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 out = {"reads": R, "cigar_ops": C, "n_ops_N": n_nops, "algorithmic_bytes": alg, "peak_gbs": peak, "runs": []}
 ref = None
-CASES = [(5, 0, 0), (6, 0, 0), (6, 1, 0), (6, 2, 0), (6, 3, 0), (6, 0, 16), (6, 0, 1), (6, 0, 2), (6, 0, 8), (6, 0, 0)]
+CASES = [(5, 0, 0), (8, 0, 0), (8, 1, 0), (8, 2, 0), (8, 3, 0), (5, 0, 0)]
 if os.environ.get('AB_CASES'):
     CASES = [tuple(int(x) for x in c.split(':')) for c in os.environ['AB_CASES'].split(',')]
 for variant, cfg, dbg in CASES:
-    ex = rt.JunctionsExtractor(bam, ".", 0, "XS", 8, 70, 500000, device=0, profile=True, scan_variant=variant, scan_cfg=cfg,
-                               scan_debug=dbg)
+    ex = rt.JunctionsExtractor(bam, ".", 0, "XS", 8, 70, 500000, device=0, profile=True, scan_variant=variant, scan_cfg=cfg)
     ex.set_contigs(contigs)
     for i in range(3 + steps):
         if i == 3:
