@@ -401,9 +401,10 @@ def main():
     scan_launches = max(int(st["batches"]), 1)
     scan_ms = st["scan_ms"] / scan_launches
     merge_ms = st["merge_ms"] / scan_launches
-    resident_stats = {"inflate_ms_per_step": st["inflate_kernel_ms"] / args.steps, "cigar_scan_ms_per_step": st["scan_ms"] / args.steps,
+    resident_stats = {"inflate_kernel_ms_sum_per_step": st["inflate_kernel_ms"] / args.steps,   # summed over launches that run CONCURRENTLY on 4 streams
+                       "cigar_scan_ms_per_step": st["scan_ms"] / args.steps,
                       "junction_merge_ms_per_step": st["merge_ms"] / args.steps, "finalize_ms_per_step": st["finalize_ms"] / args.steps,
-                      "cigar_scan_launches_per_step": scan_launches / args.steps, "junction_candidates_per_step": int(st["candidates"]) // args.steps,
+                      "cigar_scan_launches_per_step": scan_launches / args.steps, "junction_candidates_per_step": int(st["candidates"]),
                       "bgzf_blocks_per_step": int(st["bgzf_blocks"]) // args.steps, "inflated_bytes_per_step": int(st["inflated_bytes"]) // args.steps}
     launches_resident = st["kernel_launches"] / max(args.steps, 1)
     ex.close()
@@ -523,13 +524,13 @@ def main():
                 "gpu_launches": int(feeder["kernel_launches"]),
                 "cold": cold, "identity": identity},
         "gpu_launches": int(round(launches_resident * args.steps)),
-        "roofline": {"bound": "hbm", "kernel": "cigar_scan_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "cigar_scan_small_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None,
                      "traffic": traffic.get("cigar_scan_dram_bytes_per_launch") if traffic else None,
                      "traffic_source": (f"profiles/roofline_traffic.json ({traffic.get('workload')}; ncu capture, not measured in this run)" if traffic else None),
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms, "launches_per_step": scan_launches / args.steps,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                     "other_kernels_ms": {"junction_merge": merge_ms, "bgzf_inflate_per_step": resident_stats["inflate_ms_per_step"],
+                     "other_kernels_ms": {"junction_merge": merge_ms, "bgzf_inflate_lanes_sum_over_concurrent_launches_per_step": resident_stats["inflate_kernel_ms_sum_per_step"],
                                           "finalize(compact+rank+sort)_per_step": resident_stats["finalize_ms_per_step"]}},
         "cpu_baseline": cpu,
     }

@@ -166,6 +166,7 @@ int Engine::stage_file() {
 
 // Returns RTJX_OK, a negative status, or +1 = "device path declined, use the next seed mode / the host feeder".
 int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& spec) {
+    NvtxRange nvtx_run("rtjx:device_feed");
     const double t_begin = now_s();
     int rc = ensure_device();
     if (rc) return rc;
@@ -246,7 +247,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     double t_stage = 0, t_launch = 0, t_scanhdr = 0, t_seeds = now_s() - t_begin, t_slot = 0, t_alloc = 0;
     const int xs_mode = prm_.strandness == 0;
     const int32_t n_ref = (int32_t)bam.header().names.size();
-    uint64_t ordinal = 0;                                // alignments handed to cigar_scan so far
+    uint64_t ordinal = run_ord_base_;                    // ordinal of the next alignment handed to cigar_scan
     uint64_t acc_rec_upper = 0, acc_ops_upper = 0;       // host-side upper bounds of what the accumulator holds
     bool declined = false, reached_limit = false, acc_dirty = false;
     int n_groups = 0;
@@ -297,6 +298,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     };
     // flush(): cigar_scan + junction_merge over what the accumulator holds
     auto flush = [&]() -> int {
+        NvtxRange nvtx("rtjx:flush accumulator (wait + scan + merge)");
         for (DeviceFeed::GroupSlot& s : F.slot) { int r = check(s); if (r) return r; }
         if (declined || !acc_dirty) return 0;
         CKD(cudaStreamSynchronize(stream_));
@@ -330,6 +332,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
 
         // launch(G, S): inflate + record starts on the inflate stream; walk + gather + extract + carry on the chain stream
         auto launch = [&](FeedGroup& G, DeviceFeed::GroupSlot& S) -> int {
+            NvtxRange nvtx("rtjx:group (inflate | record starts | walk + gather + extract) enqueue");
             const double tl0 = now_s();
             struct TL { double* acc; double t0; ~TL() { *acc += now_s() - t0; } } tl{&t_launch, tl0};
             const uint32_t nb = (uint32_t)G.desc.size();
@@ -495,6 +498,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                 src = bam.data() + c_first;
             } else {
                 { const double tq = now_s(); CKD(cudaEventSynchronize(F.comp_free[buf])); t_slot += now_s() - tq; }   // pinned chunk free again
+                NvtxRange nvtx("rtjx:stage chunk (page cache -> pinned)");
                 const double t0 = now_s();
                 got_bytes = parallel_pread(bam.fd(), F.h_comp[buf], want_bytes, c_first, copy_threads);
                 t_stage += now_s() - t0; stats_.host_inflate_s += now_s() - t0;   // host staging time (nothing is inflated on the host)

@@ -100,6 +100,7 @@ cudaEvent_t Engine::get_event() {
 int Engine::ensure_device() {
     if (dev_ready_) { cudaSetDevice(prm_.device); return RTJX_OK; }
     if (host_only()) return fail(RTJX_E_CUDA, "this handle was created host-only (device = -1); compute entry points need a CUDA device");
+    const double t_dev0 = now_s();
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0)
@@ -115,6 +116,7 @@ int Engine::ensure_device() {
     spill_cap_ = 4096;
     CK(cached_dev_malloc(&d_spill_, spill_cap_ * sizeof(Slot)));
     dev_ready_ = true;
+    if (getenv("RTJX_TRACE")) fprintf(stderr, "[rtjx] device ready (CUDA context, streams, first allocations): %.1f ms\n", 1e3 * (now_s() - t_dev0));
     return RTJX_OK;
 }
 
@@ -215,8 +217,10 @@ int Engine::ensure_genome() {
 // copying CIGARs); 0 = unknown: size the candidate buffer for the worst case and read the real
 // count back after cigar_scan (one stream synchronisation) before sizing the merge.
 int Engine::process_device_batch(const BatchView& v, uint32_t cand_bound, cudaStream_t stream) {
+    NvtxRange nvtx("rtjx:cigar_scan + junction_merge (enqueue)");
     int rc;
     const bool known = cand_bound != 0;
+    next_ord_ = std::max<uint64_t>(next_ord_, v.first_ordinal + v.n_reads);
     if ((rc = ensure_genome())) return rc;
     const ScanParams sp = scan_params();
     if (sp.vr.n && ((reinterpret_cast<uintptr_t>(v.tid) | reinterpret_cast<uintptr_t>(v.pos) | reinterpret_cast<uintptr_t>(v.meta) |
@@ -367,14 +371,14 @@ int Engine::add(const rtjx_candidate* c, size_t n) {
             const rtjx_candidate& s = c[o + i];
             Cand& d = h[i];
             d.start = s.start; d.end = s.end; d.ts = s.thick_start; d.te = s.thick_end;
-            d.ord = (add_ord_ + i) << 16; d.tid = s.tid; d.strand = s.strand;
+            d.ord = (next_ord_ + i) << 16; d.tid = s.tid; d.strand = s.strand;
         }
         if ((rc = ensure_cands((uint32_t)m))) return rc;
         if ((rc = ensure_table((uint32_t)m, stream_))) return rc;
         CK(cudaMemcpyAsync(d_cands_, h.data(), m * sizeof(Cand), cudaMemcpyHostToDevice, stream_));
         launch_junction_merge(d_cands_, nullptr, (uint32_t)m, scan_params(), table_ref(), d_spill_, spill_cap_, d_counters_, stream_);
         CK(cudaStreamSynchronize(stream_));
-        add_ord_ += m; stats_.kernel_launches++; stats_.h2d_bytes += m * sizeof(Cand);
+        next_ord_ += m; stats_.kernel_launches++; stats_.h2d_bytes += m * sizeof(Cand);
     }
     dirty_ = true; finalized_ = false;
     return RTJX_OK;
@@ -445,7 +449,7 @@ struct EngineSink : BatchSink {
         e->stats_.h2d_bytes += (size_t)b.n_reads * 16 + 4 + (size_t)b.n_ops * 4;
         cudaStreamWaitEvent(ks, done[j], 0);
         BatchView v;
-        v.n_reads = b.n_reads; v.n_ops = b.n_ops; v.first_ordinal = b.first_ordinal;
+        v.n_reads = b.n_reads; v.n_ops = b.n_ops; v.first_ordinal = e->run_ord_base_ + b.first_ordinal;
         v.tid = d.tid; v.pos = d.pos; v.meta = d.meta; v.cig_off = d.cig_off; v.cigar = d.cigar;
         v.bc = e->bc_mode_ ? d.bc : nullptr;
         r = e->process_device_batch(v, b.n_junction_ops, ks);
@@ -494,7 +498,9 @@ int Engine::run() {
 }
 
 int Engine::run_impl() {
+    NvtxRange nvtx("rtjx:run (identify_junctions_from_BAM)");
     const double t_start = now_s();
+    run_ord_base_ = next_ord_;                  // alignments of this run are numbered after everything the handle has seen (rtjx_add included)
     std::unique_ptr<BamFile> bam; BaiIndex idx; IterSpec spec;
     int rc = open_bam(&bam, &idx, &spec);
     if (rc) return rc;
@@ -970,6 +976,7 @@ int Engine::ensure_finalize_buffers(uint32_t n, size_t n_contigs) {
 
 int Engine::finalize(cudaStream_t user_stream) {
     if (finalized_ && !dirty_) return RTJX_OK;
+    NvtxRange nvtx("rtjx:finalize (compact + first-seen rank + sort + D2H)");
     final_.clear(); pinned_final_n_ = 0;
     uint32_t n = 0;
     if (dev_ready_ && d_table_) {
@@ -1035,7 +1042,7 @@ int Engine::import(const rtjx_junction* j, size_t n) {
 
 int Engine::clear() {
     const uint64_t known_unique = unique_upper_;      // upper bound of occupied slots
-    final_.clear(); pinned_final_n_ = 0; imported_.clear(); import_sizes_.clear(); finalized_ = false; dirty_ = false; unique_upper_ = 0; add_ord_ = 0;
+    final_.clear(); pinned_final_n_ = 0; imported_.clear(); import_sizes_.clear(); finalized_ = false; dirty_ = false; unique_upper_ = 0; next_ord_ = 0; run_ord_base_ = 0;
     bc_pairs_n_ = 0;
     bc_dict_.clear();                                  // the ids live in the table keys: both go together
     if (dev_ready_) {
@@ -1178,6 +1185,7 @@ inline char* put_u32(char* p, uint32_t v) {
 int Engine::write_bed12(int fd) {
     int rc = finalize(nullptr);
     if (rc) return rc;
+    NvtxRange nvtx("rtjx:write_bed12");
     // one pass into a 4 MB buffer, no per-line allocation or printf (43k lines used to cost 5 ms of a 120 ms run)
     const size_t CAP = 4u << 20;
     std::vector<char> buf(CAP);

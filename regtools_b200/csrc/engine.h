@@ -9,11 +9,21 @@
 #include "fasta.h"
 #include "jx_device.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <memory>
 #include <string>
 #include <vector>
 
 namespace rtjx {
+
+// NVTX range over a scope: the stages of a run show up by name in Nsight Systems / ncu --nvtx (SURVEY §5 tracing row)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 class Engine {
 public:
@@ -92,7 +102,9 @@ private:
     Slot* d_spill_ = nullptr; uint32_t spill_cap_ = 0;
     Cand* d_cands_ = nullptr; uint32_t cand_cap_ = 0;
     uint64_t unique_upper_ = 0;                 // host-side upper bound of occupied slots
-    uint64_t add_ord_ = 0;                      // ordinal of the next rtjx_add candidate
+    uint64_t next_ord_ = 0;                     // one ordinal space per handle (first-seen names, last-writer strand): the next unused
+                                                // alignment ordinal, shared by rtjx_add, rtjx_scan_batch and the BAM runs
+    uint64_t run_ord_base_ = 0;                 // next_ord_ when the current BAM run started
     bool dirty_ = false;                        // device table changed since the last finalize
 
     // intron-motif mode: genome in HBM (one byte per base) and the BAM-tid -> sequence map

@@ -210,7 +210,7 @@ vector<vector<Junction> > JunctionsExtractor::get_all_junctions_in_regions(const
 // print_barcodes lines of the printed junctions (junctions_extractor.cc:255-257,272-273,278-279)
 void JunctionsExtractor::print_barcodes_file() {
     if (output_barcodes_file_ == string("NA")) return;
-    int fd = ::open(output_barcodes_file_.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    int fd = ::open(output_barcodes_file_.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
     if (fd < 0) return;        // an ofstream that failed to open swallows the lines
     int rc = rtjx_write_barcodes(handle(), fd);
     ::close(fd);
@@ -221,7 +221,7 @@ void JunctionsExtractor::print_all_junctions(ostream& out) {
     rtjx_t* h = handle();
     print_barcodes_file();
     if (output_file_ != string("NA")) {
-        int fd = ::open(output_file_.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        int fd = ::open(output_file_.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
         if (fd >= 0) {
             int rc = rtjx_write_bed12(h, fd);
             ::close(fd);
