@@ -7,7 +7,7 @@ Workload (N = 1 and N > 1 alike): BASELINE.json configs[2], the configuration th
 100M-read whole-genome BAM (24 contigs, 150 bp paired, 12 % spliced), generated on the box by tools/bamgen (seed 1234,
 BGZF level 6) into /dev/shm.  `--config c2` selects configs[1] (10M reads, one chromosome, 101 bp, 8 % spliced) instead.
 N > 1 is STRONG scaling on the same file: contigs are sharded over the ranks (one process per GPU), the junction tables
-are all-gathered (the path's only exchange) and rank 0 merges and prints.
+go to rank 0 over NCCL inside the library (rtjx_gather, the path's only exchange), which ranks, sorts and prints.
 
 One "step" = one pass of the hot path over the whole workload.
   value : reads/s with the INPUT RESIDENT IN HBM: the compressed BAM bytes sit in device memory (rtjx_stage_bam) before
@@ -316,7 +316,6 @@ def main():
     import torch
     import torch.distributed as dist
     import regtools_b200 as rt
-    from regtools_b200.distributed import all_gather_tables, merge_tables
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: regtools_b200 has no CPU fallback")
@@ -347,28 +346,27 @@ def main():
     host_threads = args.threads or max(1, (os.cpu_count() or 1) // world)
     shard = dict(shard_rank=rank, shard_world=world)
 
-    def gather_and_merge(table, out_bed=None):
-        """N > 1: the path's one exchange + rank 0's merge (and BED12 when asked for); returns the junction count on rank 0."""
-        tabs = all_gather_tables(table, dev)
-        if rank != 0:
-            return 0
-        m = merge_tables(bam, tabs)
-        if out_bed:
-            m.output_file_ = out_bed
-            m.print_all_junctions()
-        nj = len(m.junction_table()) if not out_bed else sum(len(x) for x in tabs)
-        m.close()
-        return nj
+    if world > 1:
+        # the exchange lives in the library (rtjx_gather: NCCL from HBM to HBM, merge on the root's GPU); torch.distributed only
+        # carries the 128-byte NCCL id from rank 0 to the others
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(rt.JunctionsExtractor.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        comm_id = bytes(idt.cpu().numpy().tobytes())
 
     # ---- value: compressed BAM resident in HBM -> junction table on the host ---------------------------------------
     ex = rt.JunctionsExtractor(bam, ".", 0, "XS", 8, 70, 500000, device=local, profile=True, n_threads=host_threads, **shard)
+    if world > 1:
+        ex.comm_init(comm_id, rank, world)               # process-wide communicator: later handles reuse it
     ex.stage_bam()
 
     def step_resident():
         ex.clear()
         ex.identify_junctions_from_BAM()
-        t = ex.junction_table()
-        return gather_and_merge(t) if world > 1 else len(t)
+        if world > 1:
+            ex.gather(0)                                 # rank 0 then holds the merged table
+        return len(ex.junction_table())
 
     for _ in range(args.warmup):
         step_resident()
@@ -421,11 +419,11 @@ def main():
         e = rt.JunctionsExtractor(bam, ".", 0, "XS", 8, 70, 500000, device=local, n_threads=host_threads, **shard)
         e.identify_junctions_from_BAM()
         t_run = time.perf_counter()
+        if world > 1:
+            e.gather(0)
         table = e.junction_table()
         t_fin = time.perf_counter()
-        if world > 1:
-            gather_and_merge(table, out_bed)
-        else:
+        if rank == 0:
             e.output_file_ = out_bed
             e.print_all_junctions()
         torch.cuda.synchronize()
@@ -507,7 +505,7 @@ def main():
                    "bam_bytes": os.path.getsize(bam),
                    "l2_policy": "inputs (compressed file, GBs per GPU; SoA batches >= 200 MB) larger than the 126 MB L2; no flush needed",
                    "value_region": "compressed BAM resident in HBM (rtjx_stage_bam) -> BGZF inflate + record split + cigar_scan + junction_merge "
-                                   "+ finalize (compact, rank, sort) + D2H of the junction table" + (" + NCCL all-gather + merge on rank 0" if world > 1 else ""),
+                                   "+ finalize (compact, rank, sort) + D2H of the junction table" + (" (per contig shard) + rtjx_gather: NCCL send/recv of the shard tables to rank 0, ranked and sorted on its GPU" if world > 1 else ""),
                    "host_threads_per_rank": host_threads, "parallelism": f"contig-shard x{world}" if world > 1 else "single GPU"},
         "clocks": clocks,
         "resident": resident_stats,
@@ -517,8 +515,8 @@ def main():
                           "+ record split + cigar_scan + junction_merge) + finalize + BED12 file written and closed; warm process",
                 "feeder": "device" if feeder["host_parse_s"] == 0.0 and feeder["inflated_bytes"] else "host",
                 "stages_rank0_s": {"host_staging_memcpy": feeder["host_inflate_s"], "host_wait_for_gpu": feeder["host_wait_s"],
-                                   "rtjx_run_total": feeder["run_s"], "finalize_and_d2h": feeder["finalize_d2h_s"],
-                                   ("exchange_merge_bed12" if world > 1 else "bed12_write"): feeder["exchange_merge_bed12_s"],
+                                   "rtjx_run_total": feeder["run_s"], ("nccl_gather_rank_sort_d2h" if world > 1 else "finalize_and_d2h"): feeder["finalize_d2h_s"],
+                                   "bed12_write": feeder["exchange_merge_bed12_s"],
                                    "host_parse": feeder["host_parse_s"]},
                 "compressed_bytes_rank0": int(feeder["compressed_bytes"]), "inflated_bytes_rank0": int(feeder["inflated_bytes"]),
                 "gpu_launches": int(feeder["kernel_launches"]),

@@ -231,6 +231,21 @@ int         rtjx_inflate_file(rtjx_t* h, uint64_t max_blocks, void* out, uint64_
  * The reference has no counterpart (it reads through bgzf_read, bgzf.c:548-577, on every run); results are unchanged. */
 int         rtjx_stage_bam(rtjx_t* h);
 
+/* ---- multi-GPU: the path's one exchange -------------------------------------------------------------
+ * One process per GPU; every rank runs rtjx_run on its contig shard (rtjx_params.shard_rank / shard_world).  The junction
+ * keys of different contigs are disjoint, so the merge is a concatenation + the global first-seen ranking + the sort.
+ * rtjx_gather does it with NCCL from inside the library: counts all-gathered, every rank's compacted table sent from HBM to
+ * the root's HBM (ncclSend / ncclRecv, exact sizes), names ranked and the table sorted on the root's GPU, one D2H.
+ * Afterwards the ROOT's handle serves the merged table (rtjx_count / rtjx_get / rtjx_write_bed12); the other ranks keep their
+ * own shard.  The communicator is process-wide: rank 0 calls rtjx_comm_unique_id and hands the bytes to the other ranks by
+ * whatever launcher it has (MPI, torch.distributed, a file); every rank then calls rtjx_comm_init once.  NCCL is loaded with
+ * dlopen at that moment, not before.  The reference has no counterpart (single process, single thread). */
+#define RTJX_COMM_ID_BYTES 128
+int         rtjx_comm_unique_id(void* id /* RTJX_COMM_ID_BYTES */);
+int         rtjx_comm_init(rtjx_t* h, const void* id, int rank, int world);
+void        rtjx_comm_destroy(void);
+int         rtjx_gather(rtjx_t* h, int root);
+
 /* ---- `regtools junctions annotate` (the downstream consumer of the BED12) -------------------------
  * One call = junctions_annotate (src/junctions/junctions_main.cc:61-92): load the GTF (gtf_parser.cc), read the BED12
  * junctions (BedFile), and for every line adjust_junction_ends + get_splice_site + annotate_junction_with_gtf

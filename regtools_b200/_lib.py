@@ -124,6 +124,10 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rtjx_inflate_file": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]),
     "rtjx_stage_bam": (C.c_int, [C.c_void_p]),
+    "rtjx_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "rtjx_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "rtjx_comm_destroy": (None, []),
+    "rtjx_gather": (C.c_int, [C.c_void_p, C.c_int]),
     "rtjx_annotate_params_default": (None, [C.POINTER(AnnotateParams)]),
     "rtjx_annotate": (C.c_int, [C.POINTER(AnnotateParams), C.c_int, C.POINTER(C.c_uint64), C.c_char_p, C.c_size_t]),
     "rtjx_last_error": (C.c_char_p, [C.c_void_p]),

@@ -947,6 +947,8 @@ void Engine::host_rank_and_sort() {
     });
 }
 
+std::vector<uint32_t> Engine::contig_rank_table() const { return contig_ranks(contigs_); }
+
 int Engine::ensure_finalize_buffers(uint32_t n, size_t n_contigs) {
     if (n > fin_cap_) {
         CK(cudaDeviceSynchronize());

@@ -25,6 +25,11 @@ struct NvtxRange {
     NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
+// process-wide NCCL communicator (exchange.cc)
+int comm_unique_id(void* id, std::string* err);
+int comm_init(const void* id, int rank, int world, int device, std::string* err);
+void comm_destroy();
+
 class Engine {
 public:
     explicit Engine(const rtjx_params& p);
@@ -56,6 +61,8 @@ public:
     int import(const rtjx_junction* j, size_t n);
     int clear();
     int inflate_file(uint64_t max_blocks, void* out, uint64_t cap, uint64_t* out_len);
+    int gather(int root);                        // rtjx_gather: NCCL exchange of the shard tables, merged table on the root (exchange.cc)
+    std::vector<uint32_t> contig_rank_table() const;
     int stage_file();                            // rtjx_stage_bam: compressed BAM -> HBM; later runs read it from there (device_run.cc)
     int load_batch(uint64_t* n_reads, uint64_t* n_ops, int32_t* tid, int32_t* pos, uint32_t* meta,
                    uint32_t* cig_off, uint32_t* cigar);
@@ -69,6 +76,7 @@ public:
     const char* last_error() const { return err_.c_str(); }
     int fail(int status, const std::string& msg) { err_ = msg; return status; }
     bool host_only() const { return prm_.device < 0; }
+    int device() const { return prm_.device; }
 
 private:
     friend struct EngineSink;

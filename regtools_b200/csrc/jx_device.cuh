@@ -121,8 +121,9 @@ void launch_finalize_sort_regions(OutJunctionR* entries, uint32_t n, const uint3
                                   void* workspace, size_t workspace_bytes, cudaStream_t stream);
 // ranks entries by first_ord (name_index) and sorts them in place by (contig_rank[tid], ts, te, name_index)
 size_t finalize_sort_workspace_bytes(uint32_t n);
+// rank_by_contig: the entries come from several contig shards (rtjx_gather): first appearance = (contig, first_ord) order
 void launch_finalize_sort(OutJunction* entries, uint32_t n, const uint32_t* contig_rank, uint32_t n_contigs,
-                          void* workspace, size_t workspace_bytes, cudaStream_t stream);
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream, bool rank_by_contig = false);
 
 // BGZF inflate on the device (inflate.cu).  `blocks` is an array of BgzfBlockDesc in device memory.
 struct BgzfBlockDesc { uint32_t in_off, in_len, out_off, out_len; };

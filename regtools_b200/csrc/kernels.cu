@@ -1090,6 +1090,12 @@ void launch_table_compact(const TableRef& tb, uint32_t n, OutJunction* out, cuda
 struct ByFirstOrd {
     __device__ __forceinline__ bool operator()(const OutJunction& a, const OutJunction& b) const { return a.first_ord < b.first_ord; }
 };
+// merged table of contig shards: ordinals restart on every rank, but a contig lives on one rank and contigs follow the file
+struct ByContigFirstOrd {
+    __device__ __forceinline__ bool operator()(const OutJunction& a, const OutJunction& b) const {
+        return a.tid != b.tid ? a.tid < b.tid : a.first_ord < b.first_ord;
+    }
+};
 // compare_junctions (junctions_extractor.h:117-140) with the contig string order precomputed as a rank
 struct ByBedOrder {
     const uint32_t* contig_rank; uint32_t n_contigs;
@@ -1110,17 +1116,20 @@ __global__ void fin_assign_names(OutJunction* __restrict__ e, uint32_t n) {
 }
 
 size_t finalize_sort_workspace_bytes(uint32_t n) {
-    size_t a = 0, b = 0;
+    size_t a = 0, b = 0, c = 0;
+    cub::DeviceMergeSort::SortKeys(nullptr, c, (OutJunction*)nullptr, (int)n, ByContigFirstOrd());
     cub::DeviceMergeSort::SortKeys(nullptr, a, (OutJunction*)nullptr, (int)n, ByFirstOrd());
+    if (c > a) a = c;
     cub::DeviceMergeSort::SortKeys(nullptr, b, (OutJunction*)nullptr, (int)n, ByBedOrder{nullptr, 0});
     return (a > b ? a : b) + 256;
 }
 
 // entries[0..n): ranked by first_ord (name_index), then sorted in place by (contig string, ts, te, name).
 void launch_finalize_sort(OutJunction* entries, uint32_t n, const uint32_t* contig_rank, uint32_t n_contigs,
-                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream, bool rank_by_contig) {
     if (n == 0) return;
-    cub::DeviceMergeSort::SortKeys(workspace, workspace_bytes, entries, (int)n, ByFirstOrd(), stream);
+    if (rank_by_contig) cub::DeviceMergeSort::SortKeys(workspace, workspace_bytes, entries, (int)n, ByContigFirstOrd(), stream);
+    else cub::DeviceMergeSort::SortKeys(workspace, workspace_bytes, entries, (int)n, ByFirstOrd(), stream);
     fin_assign_names<<<(n + 255u) / 256u, 256, 0, stream>>>(entries, n);
     cub::DeviceMergeSort::SortKeys(workspace, workspace_bytes, entries, (int)n, ByBedOrder{contig_rank, n_contigs}, stream);
 }

@@ -90,6 +90,23 @@ int rtjx_inflate_file(rtjx_t* h, uint64_t max_blocks, void* out, uint64_t cap, u
     GUARD(h, h->e->inflate_file(max_blocks, out, cap, out_len))
 }
 
+int rtjx_comm_unique_id(void* id) {
+    std::string err;
+    if (!id) return RTJX_E_ARG;
+    int rc = rtjx::comm_unique_id(id, &err);
+    if (rc) snprintf(g_create_err, sizeof g_create_err, "%s", err.c_str());
+    return rc;
+}
+int rtjx_comm_init(rtjx_t* h, const void* id, int rank, int world) {
+    if (!h || !id) return RTJX_E_ARG;
+    std::string err;
+    int rc = rtjx::comm_init(id, rank, world, h->e->device(), &err);
+    if (rc) return h->e->fail(rc, err);
+    return RTJX_OK;
+}
+void rtjx_comm_destroy(void) { rtjx::comm_destroy(); }
+int rtjx_gather(rtjx_t* h, int root) { GUARD(h, h->e->gather(root)) }
+
 int rtjx_stage_bam(rtjx_t* h) {
     GUARD(h, h->e->stage_file())
 }

@@ -431,6 +431,24 @@ class JunctionsExtractor:
                                           meta.ctypes.data, off.ctypes.data, cig.ctypes.data))
         return tid, pos, meta, off, cig[:no.value]
 
+    # ------------------------------------------------------------------ multi-GPU exchange (NCCL inside the library)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """rtjx_comm_unique_id: the 128 bytes rank 0 hands to every other rank before comm_init."""
+        buf = C.create_string_buffer(128)
+        rc = L.lib.rtjx_comm_unique_id(buf)
+        if rc != L.RTJX_OK:
+            raise RuntimeError(f"rtjx_comm_unique_id: {L.lib.rtjx_last_error(None).decode()} ({rc})")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        """rtjx_comm_init: joins the process-wide NCCL communicator (once per process; later handles reuse it)."""
+        self._check(L.lib.rtjx_comm_init(self._handle(), unique_id, rank, world))
+
+    def gather(self, root: int = 0) -> None:
+        """rtjx_gather: all shard tables to the root over NCCL; the root then holds the merged, ranked, sorted table."""
+        self._check(L.lib.rtjx_gather(self._handle(), root))
+
     def stage_bam(self) -> None:
         """Copies the compressed BAM into device memory; later runs of this extractor read it from there (rtjx_stage_bam)."""
         self._check(L.lib.rtjx_stage_bam(self._handle()))
