@@ -227,8 +227,9 @@ struct S5Emit {
     }
 };
 
-template <int S5_THREADS, int S5_SLAB, int S5_OUT, bool MOTIF = false, bool VREG = false, bool BC = false>
-__global__ void __launch_bounds__(S5_THREADS)
+// MINB: resident blocks per SM asked of ptxas (caps the registers per thread at 65536 / (S5_THREADS * MINB))
+template <int S5_THREADS, int S5_SLAB, int S5_OUT, bool MOTIF = false, bool VREG = false, bool BC = false, int MINB = 1>
+__global__ void __launch_bounds__(S5_THREADS, MINB)
 cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counters) {
     using Smem = S5SmemT<S5_THREADS, S5_SLAB, S5_OUT>;
     constexpr int S5_TILE = Smem::S5_TILE;
@@ -804,7 +805,13 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
         else if (p.vr.n && p.genome) cigar_scan_small_kernel<128, 1024, 192, true, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
         else if (p.vr.n) cigar_scan_small_kernel<128, 1024, 192, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
         else if (p.genome) cigar_scan_small_kernel<128, 1024, 192, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
-        else cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
+        else switch (p.cfg) {             // occupancy configurations of the plain mode (profiles/r2_scan_ab_block_tiled.json)
+            case 1: cigar_scan_small_kernel<128, 1024, 128, false, false, false, 12><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
+            case 2: cigar_scan_small_kernel<128, 1024, 96, false, false, false, 14><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
+            case 3: cigar_scan_small_kernel<128, 768, 96, false, false, false, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
+            case 4: cigar_scan_small_kernel<128, 1024, 192, false, false, false, 12><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
+            default: cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
+        }
         return;
     }
     cigar_scan_unaligned_kernel<<<(b.n_reads + 255u) / 256u, 256, 0, stream>>>(b, p, cands, cand_cap, d_counters);
