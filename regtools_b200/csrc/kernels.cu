@@ -265,30 +265,30 @@ cigar_scan_small_kernel(BatchView b, ScanParams prm, Cand* __restrict__ out, uin
     if (hi > lo) {
         const uint32_t end = min(min((hi + 3u) & ~3u, a0 + (uint32_t)S5_SLAB), b.n_ops & ~3u);
         n_st = end > a0 ? end - a0 : 0u;
-        for (uint32_t v = t; v < (n_st >> 2); v += S5_THREADS) cp_async16(&sm.slab[4 * v], b.cigar + a0 + 4 * v);
+        const uint32_t nv = n_st >> 2;                         // 16-byte vectors: at most S5_SLAB / 4, i.e. a fixed few per thread
+        const uint32_t* src = b.cigar + a0 + 4 * t;
+#pragma unroll
+        for (int j = 0; j < (S5_SLAB / 4 + S5_THREADS - 1) / S5_THREADS; ++j)
+            if (t + j * S5_THREADS < nv) cp_async16(&sm.slab[4 * (t + j * S5_THREADS)], src + 4 * j * S5_THREADS);
     }
     cp_async_commit();
-    {   // ---- while the slab is in flight: list the alignments with more than one CIGAR op (junctions_extractor.cc:379)
+    {   // ---- while the slab is in flight: list the alignments with more than one CIGAR op (junctions_extractor.cc:379);
+        // ballots, no scan: the order of the list does not matter
         const uint4 o = *reinterpret_cast<const uint4*>(&sm.off[4 * t]);
         const uint32_t o4 = sm.off[4 * t + 4];
-        const uint32_t r0 = 4 * t;
-        uint32_t flags = 0;
-        if (r0 + 0 < n_tile && o.y - o.x > 1u) flags |= 1u;
-        if (r0 + 1 < n_tile && o.z - o.y > 1u) flags |= 2u;
-        if (r0 + 2 < n_tile && o.w - o.z > 1u) flags |= 4u;
-        if (r0 + 3 < n_tile && o4 - o.w > 1u) flags |= 8u;
-        const uint32_t cnt = __popc(flags);
-        uint32_t x = cnt;
-#pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, dlt); if ((int)lane >= dlt) x += y; }
+        const uint32_t r0 = 4 * t, lt = (1u << lane) - 1u;
+        const bool f0 = r0 + 0 < n_tile && o.y - o.x > 1u, f1 = r0 + 1 < n_tile && o.z - o.y > 1u;
+        const bool f2 = r0 + 2 < n_tile && o.w - o.z > 1u, f3 = r0 + 3 < n_tile && o4 - o.w > 1u;
+        const uint32_t m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
+        const uint32_t m2 = __ballot_sync(0xffffffffu, f2), m3 = __ballot_sync(0xffffffffu, f3);
+        const uint32_t s1 = __popc(m0), s2 = s1 + __popc(m1), s3 = s2 + __popc(m2), tot = s3 + __popc(m3);
         uint32_t wbase = 0;
-        if (lane == 31 && x) wbase = atomicAdd(&sm.n_work, x);
-        wbase = __shfl_sync(0xffffffffu, wbase, 31);
-        uint32_t p = wbase + x - cnt;
-        if (flags & 1u) sm.work[p++] = (uint16_t)(r0 + 0);
-        if (flags & 2u) sm.work[p++] = (uint16_t)(r0 + 1);
-        if (flags & 4u) sm.work[p++] = (uint16_t)(r0 + 2);
-        if (flags & 8u) sm.work[p++] = (uint16_t)(r0 + 3);
+        if (lane == 0 && tot) wbase = atomicAdd(&sm.n_work, tot);
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (f0) sm.work[wbase + __popc(m0 & lt)] = (uint16_t)(r0 + 0);
+        if (f1) sm.work[wbase + s1 + __popc(m1 & lt)] = (uint16_t)(r0 + 1);
+        if (f2) sm.work[wbase + s2 + __popc(m2 & lt)] = (uint16_t)(r0 + 2);
+        if (f3) sm.work[wbase + s3 + __popc(m3 & lt)] = (uint16_t)(r0 + 3);
     }
     cp_async_wait_all();
     __syncthreads();
@@ -805,12 +805,15 @@ void launch_cigar_scan(const BatchView& b, const ScanParams& p, Cand* cands, uin
         else if (p.vr.n && p.genome) cigar_scan_small_kernel<128, 1024, 192, true, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
         else if (p.vr.n) cigar_scan_small_kernel<128, 1024, 192, false, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
         else if (p.genome) cigar_scan_small_kernel<128, 1024, 192, true><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters);
-        else switch (p.cfg) {             // occupancy configurations of the plain mode (profiles/r2_scan_ab_block_tiled.json)
+        // plain mode: occupancy configurations (profiles/r2_scan_ab_block_tiled_*.json; an L2 prefetch of later tiles' columns was
+        // measured too and changes nothing: profiles/r2_scan_ab_l2_prefetch_*.json)
+        else switch (p.cfg) {
             case 1: cigar_scan_small_kernel<128, 1024, 128, false, false, false, 12><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
             case 2: cigar_scan_small_kernel<128, 1024, 96, false, false, false, 14><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
             case 3: cigar_scan_small_kernel<128, 768, 96, false, false, false, 16><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
             case 4: cigar_scan_small_kernel<128, 1024, 192, false, false, false, 12><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
-            default: cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
+            case 5: cigar_scan_small_kernel<128, 1024, 192><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
+            default: cigar_scan_small_kernel<128, 1024, 128, false, false, false, 12><<<tiles, 128, 0, stream>>>(b, p, cands, cand_cap, d_counters); break;
         }
         return;
     }
