@@ -42,7 +42,9 @@ def main():
             ex.print_all_junctions(b)
             one.close()
             assert len(merged) == len(want) and len(merged) > own > 0, (len(merged), len(want), own)
-            assert np.array_equal(merged, want), "merged table differs from the single-GPU table"
+            # every field the reference's Junction has; first_ord (an ordinal inside a shard's own stream) is bookkeeping
+            for f in ("tid", "start", "end", "thick_start", "thick_end", "read_count", "name_index", "strand", "left_ok", "right_ok"):
+                assert np.array_equal(merged[f], want[f]), f"merged table differs from the single-GPU table in {f}"
             assert a.getvalue() == b.getvalue() and len(a.getvalue()) > 1000
         else:
             assert len(merged) == own                         # the other ranks keep their shard
