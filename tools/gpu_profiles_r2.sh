@@ -1,31 +1,47 @@
 #!/bin/bash
 # Round-2 profiling pass (one GPU): everything the numbers in DESIGN.md / profiles/ come from.
-#   gpurun --timeout 2700 -- tools/gpu_profiles_r2.sh
-# Results land in gpurun_out/ (the summaries that should be judged are copied into profiles/ afterwards).
+#   gpurun --timeout 2700 -- tools/gpu_profiles_r2.sh [bench|ncu|side|sanitizer ...]   (default: bench ncu side)
+# Results land in gpurun_out/ (<= 64 MiB come back: ncu reports are reduced to CSV on the box, only the two headline
+# kernels' reports are kept); what should be judged is copied into profiles/ afterwards.
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 O=gpurun_out
+WHAT="${*:-bench ncu side}"
+raw() {   # raw() report -> small CSV of every metric, then drop the report
+  ncu -i $O/$1.ncu-rep --page raw --csv > $O/$1.raw.csv 2>/dev/null; rm -f $O/$1.ncu-rep
+}
 {
-  echo "== bench, reference arm then ours (C3, 100M reads)"
-  timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/r2_bench_c3_ref.json 2> $O/r2_bench_c3_ref.err; tail -c 600 $O/r2_bench_c3_ref.json; echo
-  timeout 900 python bench.py > $O/r2_bench_c3.json 2> $O/r2_bench_c3.err; cut -c1-400 $O/r2_bench_c3.json; echo
-  echo "== ncu launch list of the bench command"
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-courtesy > $O/r2_bench_under_ncu.log 2>&1
-  wc -l $O/r2_launches.csv
-  echo "== ncu --set full: cigar_scan on a 30M-read C3 batch, bgzf_inflate_lanes + match_resolve + block_seeds + record_walk on the C2 file"
-  AB_CASES=5:0:0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:cigar_scan -s 6 -c 1 -o $O/r2_cigar_scan python tools/ab_scan.py 30000000 6 c3 > $O/ncu_scan.log 2>&1
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:junction_merge -s 6 -c 1 -o $O/r2_junction_merge python tools/ab_scan.py 30000000 6 c3 > $O/ncu_merge.log 2>&1
-  RTJX_INFLATE_VARIANT=3 timeout 400 ncu --set full --clock-control none --import-source on -k regex:bgzf_inflate_lanes -c 1 -o $O/r2_inflate_lanes python tools/prof_inflate.py 10000000 > $O/ncu_inflate.log 2>&1
-  timeout 400 ncu --set full --clock-control none --import-source on -k "regex:bgzf_match_resolve|block_seeds|record_walk|record_extract|record_gather" -s 10 -c 5 -o $O/r2_feed_kernels python tools/prof_e2e.py 10000000 0 1 > $O/ncu_feed.log 2>&1
-  echo "== C4 shape: 50k variant windows on the 100M-read BAM"
-  timeout 900 python tools/bench_regions.py 100000000 50000 c3 > $O/r2_regions_c4.json 2> $O/r2_regions_c4.err; cat $O/r2_regions_c4.json; tail -3 $O/r2_regions_c4.err
-  echo "== junctions annotate side bench + ncu"
-  timeout 900 python tools/bench_annotate.py --steps 3 --warmup 1 > $O/r2_annotate.json 2> $O/r2_annotate.err; cat $O/r2_annotate.json; tail -2 $O/r2_annotate.err
-  d=/tmp/rtjx_bench_annotate/c8_m30
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:annotate_kernel -c 1 -o $O/r2_annotate_kernel regtools_b200/regtools junctions annotate -o /tmp/a.tsv $d/junctions_x*.bed $d/ref.fa $d/ann.gtf > $O/ncu_annotate.log 2>&1
-  echo "== compute-sanitizer (memcheck, racecheck) over the kernel-level parity tests at small sizes"
-  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scan_pipe.py tests/test_gpu_inflate.py -q -x -k "random_batches or ring_configs or fixture_bams or stored_fixed or hot" > $O/r2_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 $O/r2_sanitizer_memcheck.log
-  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scan_pipe.py tests/test_gpu_inflate.py -q -x -k "random_batches or ring_configs or fixture_bams or hot" > $O/r2_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 $O/r2_sanitizer_racecheck.log
-  timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_device_feed.py tests/test_gpu_regions.py -q -x > $O/r2_sanitizer_memcheck_feed.log 2>&1; echo "memcheck feed rc=$?"; tail -4 $O/r2_sanitizer_memcheck_feed.log
+  if [[ $WHAT == *bench* ]]; then
+    echo "== bench, reference arm then ours (C3, 100M reads)"
+    timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/r2_bench_c3_ref.json 2> $O/r2_bench_c3_ref.err; tail -c 300 $O/r2_bench_c3_ref.json; echo
+    timeout 900 python bench.py > $O/r2_bench_c3.json 2> $O/r2_bench_c3.err; cut -c1-300 $O/r2_bench_c3.json; echo
+    echo "== ncu launch list of the bench command"
+    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-courtesy > $O/r2_bench_under_ncu.log 2>&1
+    wc -l $O/r2_launches.csv
+  fi
+  if [[ $WHAT == *ncu* ]]; then
+    echo "== ncu --set full: cigar_scan + junction_merge on a 30M-read C3 batch, inflate / feed kernels on the C2 file"
+    AB_CASES=5:0:0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:cigar_scan -s 6 -c 1 -o $O/r2_cigar_scan python tools/ab_scan.py 30000000 6 c3 > $O/ncu_scan.log 2>&1
+    ncu -i $O/r2_cigar_scan.ncu-rep --page raw --csv > $O/r2_cigar_scan.raw.csv 2>/dev/null
+    AB_CASES=5:0:0 timeout 400 ncu --set full --clock-control none -k regex:junction_merge -s 6 -c 1 -o $O/r2_junction_merge python tools/ab_scan.py 30000000 6 c3 > $O/ncu_merge.log 2>&1; raw r2_junction_merge
+    RTJX_INFLATE_VARIANT=3 timeout 400 ncu --set full --clock-control none --import-source on -k regex:bgzf_inflate_lanes -c 1 -o $O/r2_inflate_lanes python tools/prof_inflate.py 10000000 > $O/ncu_inflate.log 2>&1
+    ncu -i $O/r2_inflate_lanes.ncu-rep --page raw --csv > $O/r2_inflate_lanes.raw.csv 2>/dev/null
+    timeout 400 ncu --set full --clock-control none -k "regex:bgzf_match_resolve|block_seeds|record_walk|record_extract|record_gather" -s 10 -c 5 -o $O/r2_feed_kernels python tools/prof_e2e.py 10000000 0 1 > $O/ncu_feed.log 2>&1; raw r2_feed_kernels
+  fi
+  if [[ $WHAT == *side* ]]; then
+    echo "== C4 shape: 50k variant windows on the 100M-read BAM"
+    timeout 900 python tools/bench_regions.py 100000000 50000 c3 > $O/r2_regions_c4.json 2> $O/r2_regions_c4.err; cat $O/r2_regions_c4.json; tail -3 $O/r2_regions_c4.err
+    echo "== junctions annotate side bench + ncu"
+    timeout 900 python tools/bench_annotate.py --steps 3 --warmup 1 > $O/r2_annotate.json 2> $O/r2_annotate.err; cat $O/r2_annotate.json; tail -2 $O/r2_annotate.err
+    d=/tmp/rtjx_bench_annotate/c8_m30
+    timeout 400 ncu --set full --clock-control none -k regex:annotate_kernel -c 1 -o $O/r2_annotate_kernel regtools_b200/regtools junctions annotate -o /tmp/a.tsv $d/junctions_x*.bed $d/ref.fa $d/ann.gtf > $O/ncu_annotate.log 2>&1; raw r2_annotate_kernel
+  fi
+  if [[ $WHAT == *sanitizer* ]]; then
+    echo "== compute-sanitizer (memcheck, racecheck) over the kernel-level parity tests at small sizes"
+    timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scan_pipe.py tests/test_gpu_inflate.py -q -x -k "random_batches or ring_configs or fixture_bams or stored_fixed or hot" > $O/r2_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 $O/r2_sanitizer_memcheck.log
+    timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scan_pipe.py tests/test_gpu_inflate.py -q -x -k "random_batches or ring_configs or fixture_bams or hot" > $O/r2_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 $O/r2_sanitizer_racecheck.log
+    timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_device_feed.py tests/test_gpu_regions.py -q -x > $O/r2_sanitizer_memcheck_feed.log 2>&1; echo "memcheck feed rc=$?"; tail -4 $O/r2_sanitizer_memcheck_feed.log
+  fi
+  du -sh $O
 } > $O/r2_profiles.log 2>&1
-tail -60 $O/r2_profiles.log | cut -c1-600
+tail -40 $O/r2_profiles.log | cut -c1-500
