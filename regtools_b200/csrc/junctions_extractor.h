@@ -11,12 +11,22 @@
 #define RTJX_JUNCTIONS_EXTRACTOR_H_
 
 #include <stdint.h>
+// (the standard headers the reference's header pulls in — its callers lean on them transitively, e.g. setw in
+// cis_splice_effects_identifier.cc:251)
+#include <iomanip>
 #include <iostream>
+#include <map>
+#include <sstream>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/rtjx.h"
+
+// The reference header opens namespace std for everything that includes it (junctions_extractor.h:36) and its callers rely
+// on that (tests/lib/junctions/test_junctions_extractor.cc uses an unqualified `string`): kept, for source compatibility.
+using namespace std;
 
 #ifndef BEDFILE_H   // when built inside the reference tree, bedFile.h supplies BED and CHRPOS
 typedef uint32_t CHRPOS;                               // src/utils/bedtools/bedFile/bedFile.h:40
@@ -47,6 +57,9 @@ struct Junction : BED {
     bool has_left_min_anchor, has_right_min_anchor;
     std::string color;
     int nblocks;
+    // `-b` single cell: barcode -> count (junctions_extractor.h:57-58).  The engine keeps the barcode lists of a run on its side
+    // (rtjx_write_barcodes prints them); this member exists for the reference's callers and for junctions built by hand.
+    std::unordered_map<std::string, int> barcodes;
     Junction() : read_count(0), thick_start(0), thick_end(0), added(false), has_left_min_anchor(false),
                  has_right_min_anchor(false), color("255,0,0"), nblocks(2) { name = "NA"; }
     Junction(std::string chrom1, CHRPOS start1, CHRPOS end1, CHRPOS thick_start1, CHRPOS thick_end1, std::string strand1)
@@ -58,6 +71,14 @@ struct Junction : BED {
         out << chrom << "\t" << thick_start << "\t" << thick_end << "\t" << name << "\t" << read_count << "\t" << strand
             << "\t" << thick_start << "\t" << thick_end << "\t" << color << "\t" << nblocks
             << "\t" << start - thick_start << "," << thick_end - end << "\t" << "0," << end - thick_start << std::endl;
+    }
+    void print_barcodes(std::ostream& out) const {     // junctions_extractor.h:99-111
+        out << barcodes.size() << "\t";
+        for (std::unordered_map<std::string, int>::const_iterator it = barcodes.begin(); it != barcodes.end(); it++) {
+            if (it != barcodes.begin()) out << ",";
+            out << it->first << ":" << it->second;
+        }
+        out << std::endl;
     }
 };
 

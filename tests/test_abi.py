@@ -168,3 +168,32 @@ def test_python_mirror_texts_equal_the_reference(tmp_path):
         r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", ref_bin), "junctions", sub] + args, capture_output=True, cwd=tmp_path)
         o = subprocess.run([sys.executable, "-c", runner, sub] + args, capture_output=True, cwd=tmp_path, env=env)
         assert (r.returncode, r.stdout, r.stderr) == (o.returncode, o.stdout, o.stderr), (sub, args)
+
+
+def test_reference_callers_compile_against_the_shim_header(tmp_path):
+    """The drop-in claim of INTEGRATION.md §2, checked: the reference's OWN callers of the class — `junctions_main.cc`
+    (CLI glue), `cis_splice_effects_identifier.cc` (the 8-arg-ctor caller) and its gtest file
+    `tests/lib/junctions/test_junctions_extractor.cc` — compile, unchanged, with the shim's junctions_extractor.h in front of
+    the reference's.  Needs the reference tree (dev container); nothing is linked or run."""
+    import shutil
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "src", "junctions")) or shutil.which("g++") is None:
+        pytest.skip("needs /root/reference and g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # a maintainer replaces src/junctions/junctions_extractor.h in place; here: a shadow of that directory (links to the
+    # reference's files) in which only that header is the shim — quoted includes resolve next to the including file
+    shadow = tmp_path / "junctions"
+    shadow.mkdir()
+    for f in os.listdir(os.path.join(ref, "src", "junctions")):
+        if f != "junctions_extractor.h":
+            os.symlink(os.path.join(ref, "src", "junctions", f), shadow / f)
+    (shadow / "junctions_extractor.h").write_text('#include "%s"\n' % os.path.join(root, "regtools_b200", "csrc", "junctions_extractor.h"))
+    inc = [f"-I{shadow}", f"-I{root}/include"] + [f"-I{ref}/{d}" for d in (
+        "src/utils", "src/utils/htslib", "src/utils/bedtools/bedFile", "src/utils/bedtools/lineFileUtilities",
+        "src/utils/bedtools/gzstream", "src/utils/bedtools/fileType", "src/utils/bedtools/stringUtilities", "src/gtf", "src/variants",
+        "src/cis-splice-effects", "src/utils/gtest-1.7.0/include")]
+    for src in (str(shadow / "junctions_main.cc"), os.path.join(ref, "src/cis-splice-effects/cis_splice_effects_identifier.cc"),
+                os.path.join(ref, "tests/lib/junctions/test_junctions_extractor.cc")):
+        p = subprocess.run(["g++", "-std=c++11", "-w", "-fsyntax-only", "-DRTJX_SHIM_CHECK", src] + inc, capture_output=True, text=True)
+        assert p.returncode == 0, f"{src} does not compile against the shim:\n{p.stderr[:3000]}"
