@@ -7,8 +7,10 @@ cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 O=gpurun_out
 WHAT="${*:-bench ncu side}"
-raw() {   # raw() report -> small CSV of every metric, then drop the report
-  ncu -i $O/$1.ncu-rep --page raw --csv > $O/$1.raw.csv 2>/dev/null; rm -f $O/$1.ncu-rep
+reduce() {   # reduce() report: raw metrics + per-SASS-instruction table as CSV, then drop the (large) report
+  ncu -i $O/$1.ncu-rep --page raw --csv > $O/$1.raw.csv 2>/dev/null
+  ncu -i $O/$1.ncu-rep --page source --csv > $O/$1.source.csv 2>/dev/null
+  rm -f $O/$1.ncu-rep
 }
 {
   if [[ $WHAT == *bench* ]]; then
@@ -21,12 +23,12 @@ raw() {   # raw() report -> small CSV of every metric, then drop the report
   fi
   if [[ $WHAT == *ncu* ]]; then
     echo "== ncu --set full: cigar_scan + junction_merge on a 30M-read C3 batch, inflate / feed kernels on the C2 file"
-    AB_CASES=5:0:0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:cigar_scan -s 6 -c 1 -o $O/r2_cigar_scan python tools/ab_scan.py 30000000 6 c3 > $O/ncu_scan.log 2>&1
-    ncu -i $O/r2_cigar_scan.ncu-rep --page raw --csv > $O/r2_cigar_scan.raw.csv 2>/dev/null
-    AB_CASES=5:0:0 timeout 400 ncu --set full --clock-control none -k regex:junction_merge -s 6 -c 1 -o $O/r2_junction_merge python tools/ab_scan.py 30000000 6 c3 > $O/ncu_merge.log 2>&1; raw r2_junction_merge
-    RTJX_INFLATE_VARIANT=3 timeout 400 ncu --set full --clock-control none --import-source on -k regex:bgzf_inflate_lanes -c 1 -o $O/r2_inflate_lanes python tools/prof_inflate.py 10000000 > $O/ncu_inflate.log 2>&1
-    ncu -i $O/r2_inflate_lanes.ncu-rep --page raw --csv > $O/r2_inflate_lanes.raw.csv 2>/dev/null
-    timeout 400 ncu --set full --clock-control none -k "regex:bgzf_match_resolve|block_seeds|record_walk|record_extract|record_gather" -s 10 -c 5 -o $O/r2_feed_kernels python tools/prof_e2e.py 10000000 0 1 > $O/ncu_feed.log 2>&1; raw r2_feed_kernels
+    AB_CASES=5:0:0 timeout 400 ncu --set full --clock-control none -k regex:cigar_scan -s 6 -c 1 -o $O/r2_cigar_scan python tools/ab_scan.py 30000000 6 c3 > $O/ncu_scan.log 2>&1
+    reduce r2_cigar_scan
+    AB_CASES=5:0:0 timeout 400 ncu --set full --clock-control none -k regex:junction_merge -s 6 -c 1 -o $O/r2_junction_merge python tools/ab_scan.py 30000000 6 c3 > $O/ncu_merge.log 2>&1; reduce r2_junction_merge
+    RTJX_INFLATE_VARIANT=3 timeout 400 ncu --set full --clock-control none -k regex:bgzf_inflate_lanes -c 1 -o $O/r2_inflate_lanes python tools/prof_inflate.py 10000000 > $O/ncu_inflate.log 2>&1
+    reduce r2_inflate_lanes
+    timeout 400 ncu --set full --clock-control none -k "regex:bgzf_match_resolve|block_seeds|record_walk|record_extract|record_gather" -s 10 -c 5 -o $O/r2_feed_kernels python tools/prof_e2e.py 10000000 0 1 > $O/ncu_feed.log 2>&1; reduce r2_feed_kernels
   fi
   if [[ $WHAT == *side* ]]; then
     echo "== C4 shape: 50k variant windows on the 100M-read BAM"
@@ -34,7 +36,7 @@ raw() {   # raw() report -> small CSV of every metric, then drop the report
     echo "== junctions annotate side bench + ncu"
     timeout 900 python tools/bench_annotate.py --steps 3 --warmup 1 > $O/r2_annotate.json 2> $O/r2_annotate.err; cat $O/r2_annotate.json; tail -2 $O/r2_annotate.err
     d=/tmp/rtjx_bench_annotate/c8_m30
-    timeout 400 ncu --set full --clock-control none -k regex:annotate_kernel -c 1 -o $O/r2_annotate_kernel regtools_b200/regtools junctions annotate -o /tmp/a.tsv $d/junctions_x*.bed $d/ref.fa $d/ann.gtf > $O/ncu_annotate.log 2>&1; raw r2_annotate_kernel
+    timeout 400 ncu --set full --clock-control none -k regex:annotate_kernel -c 1 -o $O/r2_annotate_kernel regtools_b200/regtools junctions annotate -o /tmp/a.tsv $d/junctions_x*.bed $d/ref.fa $d/ann.gtf > $O/ncu_annotate.log 2>&1; reduce r2_annotate_kernel
   fi
   if [[ $WHAT == *sanitizer* ]]; then
     echo "== compute-sanitizer (memcheck, racecheck) over the kernel-level parity tests at small sizes"
@@ -42,6 +44,8 @@ raw() {   # raw() report -> small CSV of every metric, then drop the report
     timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scan_pipe.py tests/test_gpu_inflate.py -q -x -k "random_batches or ring_configs or fixture_bams or hot" > $O/r2_sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?"; tail -4 $O/r2_sanitizer_racecheck.log
     timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_device_feed.py tests/test_gpu_regions.py -q -x > $O/r2_sanitizer_memcheck_feed.log 2>&1; echo "memcheck feed rc=$?"; tail -4 $O/r2_sanitizer_memcheck_feed.log
   fi
-  du -sh $O
+  rm -f $O/*.ncu-rep; ls -laS $O | head -12; du -sh $O
 } > $O/r2_profiles.log 2>&1
+# never come home empty-handed: drop the largest files until the directory fits the 64 MiB return limit
+while [ "$(du -sm $O | cut -f1)" -gt 55 ]; do f=$(ls -S $O | head -1); echo "dropping $O/$f ($(du -sh $O/$f | cut -f1))" >> $O/r2_profiles.log; rm -f "$O/$f"; done
 tail -40 $O/r2_profiles.log | cut -c1-500
