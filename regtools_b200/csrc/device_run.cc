@@ -6,7 +6,7 @@
 // CIGAR scan, junction merge) runs on the GPU.
 //
 // Round-2 shape of the pipeline (round 1: one stream, one group at a time, scan per group):
-//   * a GROUP of consecutive BGZF blocks is the unit of device work; four group slots are in flight: the inflates of the
+//   * a GROUP of consecutive BGZF blocks is the unit of device work; up to ten group slots are in flight: the inflates of the
 //     groups behind g (each on its slot's stream; the lane-per-stream decoder is latency-bound, so concurrent launches add up)
 //     overlap the record walk / extraction of group g (the chain stream), and all overlap the H2D copies (copy stream);
 //   * record starts are found ON the device, one per BGZF block (block_seeds_kernel), instead of every 16 kb of reference
@@ -76,7 +76,8 @@ size_t parallel_pread(int fd, uint8_t* dst, size_t n, uint64_t file_off, int thr
 
 struct Engine::DeviceFeed {
     static constexpr uint32_t HEAD = 4u << 20;           // carry headroom in front of the inflated data
-    static constexpr int NSLOT = 4;                      // groups in flight (their inflates run concurrently, each on its slot's stream)
+    static constexpr int NSLOT = 10;                     // groups in flight (their inflates run concurrently, each on its slot's stream:
+                                                         // a 256 MB group occupies ~1.4 of the 16 warps per SM the lane decoder can hold)
     static constexpr int NSTAGE = 3;                     // pinned staging chunks
     uint8_t* h_comp[NSTAGE] = {nullptr, nullptr, nullptr};
     cudaEvent_t comp_free[NSTAGE] = {nullptr, nullptr, nullptr};

@@ -189,7 +189,9 @@ struct BgzfBlock {   // same layout as BgzfBlockDesc (jx_device.cuh)
 // lane groups run the (serial) symbol loop in lockstep, so one issued instruction advances 32/L streams, and
 // each group of L lanes places its own round of L symbols.  Every warp-level primitive below is restricted to
 // the group's lane mask.
-template <int L>
+// ONLY_STATUS != 0: the launch is a second chance — only blocks whose status holds that value are decoded (the lane-per-stream
+// decoder gives up on a block with more matches than its list holds; everything else of such a launch returns at once).
+template <int L, uint32_t ONLY_STATUS = 0>
 __global__ void __launch_bounds__(INF_WARPS * 32)
 bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, uint32_t n_blocks,
                     uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
@@ -201,6 +203,7 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
     const uint32_t gmask = (L == 32 ? 0xffffffffu : ((1u << (L & 31)) - 1u) << gshift);
     const uint32_t b = blockIdx.x * DEC_PER_CTA + wib;
     if (b >= n_blocks) return;
+    if (ONLY_STATUS != 0 && status[b] != ONLY_STATUS) return;
     InflateWarpSmem& sm = smem[wib];
     const BgzfBlock blk = blocks[b];
     uint8_t* dst = out + blk.out_off;
@@ -522,7 +525,7 @@ __device__ __forceinline__ uint32_t lane_code_len(uint32_t v, const uint32_t (&u
     return cnt;
 }
 
-constexpr uint32_t LN_MATCH_CAP = 12288;          // match records per BGZF block (a block of nothing but 5-byte matches)
+constexpr uint32_t LN_MATCH_CAP = 8192;           // match records per BGZF block; a block with more is decoded again by the warp-per-block kernel
 
 constexpr int LN_THREADS = 64;                    // two warps per CTA: 8 CTAs = 16 warps per SM within the shared-memory budget
 __global__ void __launch_bounds__(LN_THREADS, 8)
@@ -719,6 +722,13 @@ static void launch_lanes(const uint8_t* comp, const BgzfBlock* bl, uint32_t n_bl
     uint2* mlist = reinterpret_cast<uint2*>(static_cast<uint8_t*>(scratch) + (((size_t)n_blocks * 4 + 255) & ~(size_t)255));
     bgzf_inflate_lanes_kernel<<<(n_blocks + LN_THREADS - 1) / LN_THREADS, LN_THREADS, sh, stream>>>(comp, bl, n_blocks, out, status, mlist, mcount);
     bgzf_match_resolve_kernel<<<(n_blocks + MR_WARPS - 1) / MR_WARPS, MR_WARPS * 32, 0, stream>>>(bl, n_blocks, out, mlist, mcount);
+    // second chance for blocks whose match list overflowed (status 19): the warp-per-block decoder has no such limit
+    {
+        constexpr int D = INF_WARPS * 32 / 16; const size_t shw = D * sizeof(InflateWarpSmem);
+        static bool a = false;
+        if (!a) { cudaFuncSetAttribute(bgzf_inflate_kernel<16, 19u>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shw); a = true; }
+        bgzf_inflate_kernel<16, 19u><<<(n_blocks + D - 1) / D, INF_WARPS * 32, shw, stream>>>(comp, bl, n_blocks, out, status);
+    }
 }
 
 __global__ void inflate_status_reduce_kernel(const uint32_t* __restrict__ status, uint32_t n, uint32_t* __restrict__ flags) {

@@ -125,8 +125,9 @@ def test_fuzzed_variant_regions_match_oracle(block, tmp_path):
 def test_damaged_files_match_oracle(block, tmp_path):
     """Truncated / bit-flipped / zeroed / wrong-ISIZE copies of fuzzed BAMs through the whole product: the BED12 must be what
     the oracle prints (= what the unmodified reference prints before it stops, tests/test_host_logic.py::
-    test_feeder_on_damaged_files).  These files are small, so the host feeder runs; the device feeder on damaged files (it must
-    decline or agree: inflate status, record checks, untrusted ISIZE) is to be fuzzed with inflate_mode=2 in round 2."""
+    test_feeder_on_damaged_files).  inflate_mode 0 / 1 take the host feeder on files this small; inflate_mode 2 forces the
+    device feeder (lane-per-stream or warp-per-block inflate, record starts found on the device, chain walk), which has to
+    decline — inflate status, record checks, a missed seed, an untrusted ISIZE — or agree."""
     import regtools_b200 as rt
     for seed in range(block * 12, block * 12 + 12):
         bam = ff.make_cigar_fuzz_bam(str(tmp_path / "a.bam"), seed)
@@ -139,17 +140,26 @@ def test_damaged_files_match_oracle(block, tmp_path):
                 want = o.bed12()
             except RuntimeError:
                 want = None
-            for inflate_mode in (0, 1):
-                ex = rt.JunctionsExtractor(bad, reg, 0, "XS", 0, 0, 500000, inflate_mode=inflate_mode)
+            # (inflate_mode, RTJX_INFLATE_VARIANT): 2 forces the device feeder onto the damaged file — with the warp-per-block
+            # decoder (1) and with the lane-per-stream decoder + match resolve (3) — and it must decline or agree
+            for inflate_mode, variant in ((0, None), (1, None), (2, "1"), (2, "3")):
+                if variant is None:
+                    os.environ.pop("RTJX_INFLATE_VARIANT", None)
+                else:
+                    os.environ["RTJX_INFLATE_VARIANT"] = variant
                 try:
-                    ex.identify_junctions_from_BAM()
-                    buf = io.StringIO()
-                    ex.print_all_junctions(buf)
-                    got = buf.getvalue()
-                except RuntimeError:
-                    got = None
-                ex.close()
-                assert got == want, (seed, mode, reg, inflate_mode)
+                    ex = rt.JunctionsExtractor(bad, reg, 0, "XS", 0, 0, 500000, inflate_mode=inflate_mode)
+                    try:
+                        ex.identify_junctions_from_BAM()
+                        buf = io.StringIO()
+                        ex.print_all_junctions(buf)
+                        got = buf.getvalue()
+                    except RuntimeError:
+                        got = None
+                    ex.close()
+                finally:
+                    os.environ.pop("RTJX_INFLATE_VARIANT", None)
+                assert got == want, (seed, mode, reg, inflate_mode, variant)
 
 
 @pytest.mark.parametrize("block", range(2))

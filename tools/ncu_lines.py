@@ -12,7 +12,8 @@ for f in os.listdir(tmp):
         d = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
         if kernel in d:
             dis = d.split("\n")
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+# `rep` is an .ncu-rep, or the CSV of its source page made on the GPU box (`ncu -i x.ncu-rep --page source --csv > x.source.csv`)
+out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 his = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
 # pick the table whose preceding "Kernel Name" row mentions the kernel
