@@ -524,8 +524,13 @@ def main():
         "gpu_launches": int(round(launches_resident * args.steps)),
         "roofline": {"bound": "hbm", "kernel": "cigar_scan_small_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None,
-                     "traffic": traffic.get("cigar_scan_dram_bytes_per_launch") if traffic else None,
-                     "traffic_source": (f"profiles/roofline_traffic.json ({traffic.get('workload')}; ncu capture, not measured in this run)" if traffic else None),
+                     # ncu's DRAM bytes of one captured launch, scaled to this run's launch size by the algorithmic bytes (same
+                     # workload family: traffic is linear in the batch)
+                     "traffic": (traffic["cigar_scan_dram_bytes_per_launch"] * alg_bytes / traffic["algorithmic_read_bytes"]
+                                 if traffic and traffic.get("algorithmic_read_bytes") else None),
+                     "traffic_source": (f"profiles/roofline_traffic.json: {traffic['cigar_scan_dram_bytes_per_launch']:.0f} B read+written by one launch over "
+                                        f"{traffic['algorithmic_read_bytes']:.0f} algorithmic bytes ({traffic.get('workload')}; ncu --set full capture, not measured "
+                                        "in this run), scaled to this run's launch size" if traffic and traffic.get("algorithmic_read_bytes") else None),
                      "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": scan_ms, "launches_per_step": scan_launches / args.steps,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                      "other_kernels_ms": {"junction_merge": merge_ms, "bgzf_inflate_lanes_sum_over_concurrent_launches_per_step": resident_stats["inflate_kernel_ms_sum_per_step"],

@@ -21,13 +21,17 @@
 // Engine::run fall back, so results never depend on this path accepting bad input.
 #include "engine.h"
 #include "buffer_cache.h"
+#include "stage_pipe.h"
 
 #include <algorithm>
 #include <chrono>
+#include <atomic>
 #include <climits>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <unordered_map>
 #include <unistd.h>
@@ -65,6 +69,7 @@ size_t parallel_pread(int fd, uint8_t* dst, size_t n, uint64_t file_off, int thr
     for (int t = 0; t < used; ++t) { total += got[(size_t)t]; if (got[(size_t)t] < std::min(per, n - (size_t)t * per)) break; }
     return total;
 }
+
 }  // namespace
 
 #define CKD(call)                                                                                    \
@@ -78,9 +83,9 @@ struct Engine::DeviceFeed {
     static constexpr uint32_t HEAD = 4u << 20;           // carry headroom in front of the inflated data
     static constexpr int NSLOT = 10;                     // groups in flight (their inflates run concurrently, each on its slot's stream:
                                                          // a 256 MB group occupies ~1.4 of the 16 warps per SM the lane decoder can hold)
-    static constexpr int NSTAGE = 3;                     // pinned staging chunks
-    uint8_t* h_comp[NSTAGE] = {nullptr, nullptr, nullptr};
-    cudaEvent_t comp_free[NSTAGE] = {nullptr, nullptr, nullptr};
+    static constexpr int NSTAGE = StagePipe::NBUF;       // pinned staging windows (read ahead by StagePipe)
+    uint8_t* h_comp[NSTAGE] = {};
+    cudaEvent_t comp_free[NSTAGE] = {};
     struct GroupSlot {
         uint8_t* d_comp = nullptr; size_t comp_cap = 0;  // compressed bytes of the group (file mode)
         uint8_t* d_infl = nullptr; size_t infl_cap = 0;  // HEAD + data + pad
@@ -93,6 +98,7 @@ struct Engine::DeviceFeed {
         cudaStream_t inf_stream = nullptr;               // inflate + record-start discovery of this slot's group; the engine's stream_ runs the chain
         cudaEvent_t copied = nullptr, inflated = nullptr, done = nullptr;
         bool busy = false;                               // a group was launched into this slot and not yet checked
+        uint64_t seq = 0, cap_rec = 0, cap_ops = 0;      // launch number; upper bounds of what the group appends to the accumulator
         uint32_t dbg_nb = 0, dbg_nseg = 0; uint64_t dbg_out_total = 0; bool dbg_first = false;   // RTJX_FEED_DEBUG
     } slot[NSLOT];
     FeedState* d_state = nullptr;
@@ -176,7 +182,8 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     const bool resident = F.d_file != nullptr && F.file_bytes == bam.size();
     const int n_threads = prm_.n_threads > 0 ? prm_.n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     const int copy_threads = std::min(n_threads, 16);
-    const uint64_t STAGE = 32ull << 20;                  // compressed bytes per pinned staging chunk
+    const uint64_t STAGE = 16ull << 20;                  // compressed bytes per pinned staging window (plus WIN_SLACK: the block that straddles its end)
+    const uint64_t WIN_SLACK = 128u << 10;
     static const uint64_t GROUP = [] { const char* v = getenv("RTJX_GROUP_MB"); return (uint64_t)(v ? atoi(v) : 256) << 20; }();
     // the first group of a range is smaller: the GPU starts after a few ms of staging instead of a full group's worth
     static const uint64_t FIRST_GROUP = [] { const char* v = getenv("RTJX_FIRST_GROUP_MB"); return (uint64_t)(v ? atoi(v) : 128) << 20; }();
@@ -229,7 +236,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     if (!resident && !F.h_comp[0])
         for (int i = 0; i < DeviceFeed::NSTAGE; ++i) {
             CKD(cudaEventCreateWithFlags(&F.comp_free[i], cudaEventDisableTiming));
-            CKD(cached_host_alloc(&F.h_comp[i], STAGE + (1u << 17) + 256));
+            CKD(cached_host_alloc(&F.h_comp[i], STAGE + WIN_SLACK + 512));
         }
     auto drain = [&]() { cudaStreamSynchronize(stream_); cudaStreamSynchronize(copy_stream_); for (DeviceFeed::GroupSlot& q : F.slot) cudaStreamSynchronize(q.inf_stream); };
     auto grow_dev = [&](void** p, size_t* cap, size_t want, size_t elem) -> cudaError_t {
@@ -242,6 +249,8 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
         return e;
     };
     for (DeviceFeed::GroupSlot& s : F.slot) s.busy = false;
+    std::unique_ptr<StagePipe> pipe;
+    if (!resident) pipe.reset(new StagePipe(bam.fd(), bam.size(), F.h_comp, [&F](int b) { cudaEventSynchronize(F.comp_free[b]); }, STAGE + WIN_SLACK, STAGE, copy_threads));
     launch_feed_acc_reset(F.d_state, stream_);           // a declined earlier run may have left alignments in the accumulator
 
     static const bool trace = getenv("RTJX_TRACE") != nullptr;
@@ -249,7 +258,9 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     const int xs_mode = prm_.strandness == 0;
     const int32_t n_ref = (int32_t)bam.header().names.size();
     uint64_t ordinal = run_ord_base_;                    // ordinal of the next alignment handed to cigar_scan
-    uint64_t acc_rec_upper = 0, acc_ops_upper = 0;       // host-side upper bounds of what the accumulator holds
+    // What the accumulator holds, as far as the host knows: the exact counts after the newest group it has seen finish, plus upper
+    // bounds (64 B of stream per alignment, 32 B per CIGAR op) for the groups still in flight
+    uint64_t known_rec = 0, known_ops = 0, known_seq = 0, infl_rec = 0, infl_ops = 0, launch_seq = 0;
     bool declined = false, reached_limit = false, acc_dirty = false;
     int n_groups = 0;
 
@@ -262,6 +273,8 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
         stats_.host_wait_s += now_s() - tw;
         stats_.d2h_bytes += sizeof(FeedState);
         const FeedState& st = *s.h_state;
+        infl_rec -= s.cap_rec; infl_ops -= s.cap_ops;
+        if (s.seq > known_seq) { known_seq = s.seq; known_rec = st.acc_rec; known_ops = st.acc_ops; }
         if (st.flags || st.bad_offset != LLONG_MAX) {
             declined = true; feed_decline_flags_ = st.flags;
             if (getenv("RTJX_FEED_DEBUG") && s.dbg_nb) {
@@ -315,7 +328,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
         }
         launch_feed_acc_reset(F.d_state, stream_);
         stats_.kernel_launches++;
-        acc_rec_upper = acc_ops_upper = 0; acc_dirty = false;
+        known_rec = known_ops = infl_rec = infl_ops = 0; known_seq = launch_seq; acc_dirty = false;
         return 0;
     };
 
@@ -328,6 +341,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
         bool first_group = true, stream_ends = false;
         reached_limit = false;
         int buf = 0;
+        uint64_t win = coff;                                 // first byte of the staging window being consumed (file mode)
         FeedGroup g;
         g.first_of_range = true; g.v_lo = rg.beg;
 
@@ -382,7 +396,16 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             const double grow = std::min(8.0, std::max(1.0, 1.05 * (double)(GROUP + STAGE) / (double)std::max<uint64_t>(G.comp_bytes, 1)));
             auto sized = [&](size_t need) -> size_t { return (size_t)((double)need * grow) + 64; };
             const uint64_t cig_upper = (DeviceFeed::HEAD + G.out_total) / 32 + 4096;   // > 12.5 % of the bytes being CIGAR -> capacity flag
-            if (acc_rec_upper + cap_total + 8 > F.acc_rec_cap || acc_ops_upper + cig_upper + 8 > F.acc_ops_cap) {
+            auto acc_full = [&] { return known_rec + infl_rec + cap_total + 8 > F.acc_rec_cap || known_ops + infl_ops + cig_upper + 8 > F.acc_ops_cap; };
+            if (acc_full()) {
+                // groups that have finished tighten the bound: look at them (oldest first) before giving up on the room
+                for (int k = 0; k < DeviceFeed::NSLOT && acc_full(); ++k) {
+                    int r = check(F.slot[(n_groups + k) % DeviceFeed::NSLOT]);
+                    if (r) return r;
+                    if (declined) return 0;
+                }
+            }
+            if (acc_full()) {
                 // the accumulator is scanned (and emptied) before it would overflow; it only ever grows while empty
                 if (acc_dirty) { int r = flush(); if (r) return r; if (declined) return 0; }
                 const uint64_t want_rec = std::max<uint64_t>(std::min<uint64_t>(ACC_REC, (uint64_t)(bam.size() / 16)), cap_total + 8);
@@ -473,7 +496,8 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             stats_.kernel_launches += 10 + (seed_mode == 0 ? 2 : 0) + (G.first_of_range ? 0 : 1);
             stats_.h2d_bytes += (size_t)nb * sizeof(BgzfBlockDesc) + (size_t)n_seg * 12;
             stats_.bgzf_blocks += nb; stats_.inflated_bytes += G.out_total;
-            acc_rec_upper += cap_total; acc_ops_upper += cig_upper; acc_dirty = true;
+            S.seq = ++launch_seq; S.cap_rec = cap_total; S.cap_ops = cig_upper;
+            infl_rec += cap_total; infl_ops += cig_upper; acc_dirty = true;
             S.busy = true;
             S.dbg_nb = nb; S.dbg_nseg = n_seg; S.dbg_out_total = G.out_total; S.dbg_first = G.first_of_range;
             ++n_groups;
@@ -487,23 +511,30 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             blocks.clear();
             bool stop = false, partial = false, untrusted = false;
             const uint64_t c_first = coff;
-            const size_t want_bytes = (size_t)std::min<uint64_t>(STAGE + (1u << 16), bam.size() - c_first);
             const uint8_t* src = nullptr;
-            size_t got_bytes = want_bytes;
+            size_t got_bytes = 0;
+            uint64_t scan_lim = end_coff;
             if (g.comp_bytes == 0) {
-                // a new group starts: its slot must be free (the group that used it is checked here, two groups later)
+                // a new group starts: its slot must be free (the group that used it is checked here, NSLOT groups later)
                 if ((rc = check(S))) return rc;
                 if (declined || reached_limit) break;
             }
             if (resident) {
                 src = bam.data() + c_first;
+                got_bytes = (size_t)std::min<uint64_t>(STAGE + (1u << 16), bam.size() - c_first);
             } else {
-                { const double tq = now_s(); CKD(cudaEventSynchronize(F.comp_free[buf])); t_slot += now_s() - tq; }   // pinned chunk free again
-                NvtxRange nvtx("rtjx:stage chunk (page cache -> pinned)");
+                // windows sit on a fixed grid from the range's first block (that is what lets StagePipe read ahead); a chunk is the
+                // blocks that START inside its window
+                while (c_first >= win + STAGE) win += STAGE;
+                NvtxRange nvtx("rtjx:stage window (wait for the read-ahead)");
                 const double t0 = now_s();
-                got_bytes = parallel_pread(bam.fd(), F.h_comp[buf], want_bytes, c_first, copy_threads);
+                size_t win_got = 0;
+                const uint8_t* w = pipe->get(win, end_coff, &win_got, &buf);
                 t_stage += now_s() - t0; stats_.host_inflate_s += now_s() - t0;   // host staging time (nothing is inflated on the host)
-                src = F.h_comp[buf];
+                if (!w) return fail(RTJX_E_IO, "short read while staging the BAM");
+                src = w + (c_first - win);
+                got_bytes = win_got - (size_t)(c_first - win);
+                scan_lim = std::min<uint64_t>(end_coff, win + STAGE);
             }
             const double ts0 = now_s();
             uint64_t c_end;
@@ -518,7 +549,8 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                 blocks = it->second.blocks; stop = it->second.stop; partial = it->second.partial; untrusted = it->second.untrusted;
                 c_end = it->second.c_end;
             } else {
-                c_end = scan_bgzf_blocks_mem(src, got_bytes, c_first, end_coff, &blocks, &stop, &partial, &untrusted);
+                c_end = scan_bgzf_blocks_mem(src, got_bytes, c_first, scan_lim, &blocks, &stop, &partial, &untrusted);
+                if (stop && scan_lim < end_coff && c_end >= scan_lim) stop = false;   // the window ended, not the stream
             }
             t_scanhdr += now_s() - ts0;
             coff = c_end;
@@ -541,10 +573,9 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                         }
                     }
                     if (g.comp_bytes + bytes + 64 > S.comp_cap) return fail(RTJX_E_STATE, "device feed: group buffer overflow");
-                    memset(F.h_comp[buf] + bytes, 0, 64);
-                    CKD(cudaMemcpyAsync(S.d_comp + g.comp_bytes, F.h_comp[buf], bytes + 64, cudaMemcpyHostToDevice, copy_stream_));
+                    CKD(cudaMemcpyAsync(S.d_comp + g.comp_bytes, src, bytes, cudaMemcpyHostToDevice, copy_stream_));
+                    CKD(cudaMemsetAsync(S.d_comp + g.comp_bytes + bytes, 0, 64, copy_stream_));   // the bit readers look a few words past a payload
                     CKD(cudaEventRecord(F.comp_free[buf], copy_stream_));
-                    buf = (buf + 1) % DeviceFeed::NSTAGE;
                     stats_.h2d_bytes += bytes;
                 }
                 for (const BgzfBlockInfo& b : blocks) {

@@ -477,7 +477,8 @@ struct LaneBits {
 // order is ascending, so the symbols >= 256 (end of block, lengths) are the tail of each length's run and one index per
 // length (`hi`) tells them apart: ah[l] = uint16(adj[l]) | hi[l] << 16.
 template <bool LIT>
-__device__ __forceinline__ bool lane_build(const uint8_t* len, int n, uint32_t (&ub)[16], void* adj_out, uint8_t* symtab) {
+__device__ __forceinline__ bool lane_build(const uint8_t* len, int n, uint32_t (&pk)[8], void* adj_out, uint8_t* symtab) {
+    uint32_t ub[16];
     uint16_t count[16], offs[16];
     int16_t adj[16];
 #pragma unroll
@@ -498,6 +499,10 @@ __device__ __forceinline__ bool lane_build(const uint8_t* len, int n, uint32_t (
         code = (code + c) << 1;
     }
     if (!ok) return false;
+    // two bounds per register (lane_code_len): lengths 1..8 in the low halves, 9..15 in the high halves; the 16th slot holds
+    // 0x8000, which no 15-bit window reaches
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pk[i] = ub[i + 1] | (i < 7 ? ub[i + 9] : 0x8000u) << 16;
     const int n_lo = LIT ? (n < 256 ? n : 256) : n;
     for (int s = 0; s < n_lo; ++s) {
         const int l = len[s];
@@ -517,13 +522,27 @@ __device__ __forceinline__ bool lane_build(const uint8_t* len, int n, uint32_t (
     return true;
 }
 
-// code length of the 15-bit window v (MSB-first): 1 + the number of bounds it reaches; 16 = no code of this table
-__device__ __forceinline__ uint32_t lane_code_len(uint32_t v, const uint32_t (&ub)[16]) {
-    uint32_t cnt = 1;
+// code length of the 15-bit window v (MSB-first): 1 + the number of bounds it reaches; 16 = no code of this table.
+// Bounds are <= 0x8000 and v < 0x8000, so (v | 0x8000) - bound stays within its 16-bit half (no borrow between the halves) and
+// has bit 15 set exactly when v >= bound: one subtraction compares two lengths, and the fifteen flags are summed by two
+// independent accumulators instead of a fifteen-deep chain of predicated increments.
+__device__ __forceinline__ uint32_t lane_code_len(uint32_t v, const uint32_t (&pk)[8]) {
+    const uint32_t vv = (v | 0x8000u) * 0x10001u;
+    uint32_t hi = 0, lo = 0;
 #pragma unroll
-    for (int l = 1; l <= 15; ++l) cnt += v >= ub[l] ? 1u : 0u;
-    return cnt;
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t t = vv - pk[i];
+        hi += t >> 31;
+        lo += t & 0x8000u;
+    }
+    return 1u + hi + (lo >> 15);
 }
+
+// shared-memory loads of the symbol loop by 32-bit shared address: the lane's table base is computed once (a generic pointer
+// makes the compiler rebuild the shared window base — S2R + LEA + two IMADs — at every use when registers are tight)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int32_t lds_s16(uint32_t a) { int32_t v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
 constexpr uint32_t LN_MATCH_CAP = 8192;           // match records per BGZF block; a block with more is decoded again by the warp-per-block kernel
 
@@ -544,6 +563,9 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
     int16_t* dist_adj = reinterpret_cast<int16_t*>(T + LN_DIST_ADJ);
     uint8_t* dist_sym = T + LN_DIST_SYM;
     if (b >= n_blocks) return;
+    uint32_t sT, sTab;                            // shared-space addresses of the lane's tables and of the CTA's base/extra table
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(sT) : "l"(T));
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(sTab) : "l"(s_tab));
 
     const BgzfBlock blk = blocks[b];
     uint8_t* dst = out + blk.out_off;
@@ -552,9 +574,9 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
     uint32_t opos = 0, err = 0, n_match = 0;
     LaneBits br;
     br.init(comp + blk.in_off, blk.in_len);
-    uint32_t ul[16], ud[16];                      // upper bounds per code length of the current DEFLATE block's two codes
+    uint32_t ul[8], ud[8];                        // upper bounds per code length of the current DEFLATE block's two codes, two per register
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { ul[i] = 0; ud[i] = 0; }
+    for (int i = 0; i < 8; ++i) { ul[i] = 0; ud[i] = 0; }
     bool in_block = false, last = false;
 
     for (;;) {
@@ -632,9 +654,9 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
         uint32_t v = __brev((uint32_t)br.bb) >> 17;                    // next 15 bits, first bit most significant
         uint32_t cl = lane_code_len(v, ul);
         if (cl > 15u) { err = 11; in_block = false; continue; }
-        const uint32_t ah = lit_ah[cl];
+        const uint32_t ah = lds_u32(sT + LN_LIT_AH + 4u * cl);
         const uint32_t ix = (v >> (15u - cl)) + (uint32_t)(int)(int16_t)(ah & 0xffffu);
-        uint32_t sym = (uint32_t)lit_sym[ix] + (ix >= (ah >> 16) ? 256u : 0u);
+        uint32_t sym = lds_u8(sT + LN_LIT_SYM + ix) + (ix >= (ah >> 16) ? 256u : 0u);
         br.drop((int)cl);
         if (sym < 256u) {
             if (opos >= cap) { err = 15; in_block = false; continue; }
@@ -645,17 +667,17 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
         sym -= 257u;
         if (sym >= 29u) { err = 12; in_block = false; continue; }
         // length: base and extra bits from the symbol (RFC 1951 3.2.5)
-        const uint32_t lt = s_tab[sym], lx = lt >> 16;
+        const uint32_t lt = lds_u32(sTab + 4u * sym), lx = lt >> 16;
         const uint32_t len = (lt & 0xffffu) + br.peek((int)lx);
         br.drop((int)lx);
         br.refill();
         v = __brev((uint32_t)br.bb) >> 17;
         cl = lane_code_len(v, ud);
         if (cl > 15u) { err = 13; in_block = false; continue; }
-        const uint32_t ds = dist_sym[(int)(v >> (15u - cl)) + (int)dist_adj[cl]];
+        const uint32_t ds = lds_u8(sT + LN_DIST_SYM + (uint32_t)((int)(v >> (15u - cl)) + lds_s16(sT + LN_DIST_ADJ + 2u * cl)));
         br.drop((int)cl);
         if (ds >= 30u) { err = 14; in_block = false; continue; }
-        const uint32_t dt = s_tab[32u + ds], dx = dt >> 16;
+        const uint32_t dt = lds_u32(sTab + 128u + 4u * ds), dx = dt >> 16;
         const uint32_t dist = (dt & 0xffffu) + br.peek((int)dx);
         br.drop((int)dx);
         if (dist > opos || opos + len > cap || n_match >= LN_MATCH_CAP) {
