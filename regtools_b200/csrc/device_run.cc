@@ -81,8 +81,10 @@ size_t parallel_pread(int fd, uint8_t* dst, size_t n, uint64_t file_off, int thr
 
 struct Engine::DeviceFeed {
     static constexpr uint32_t HEAD = 4u << 20;           // carry headroom in front of the inflated data
-    static constexpr int NSLOT = 10;                     // groups in flight (their inflates run concurrently, each on its slot's stream:
-                                                         // a 256 MB group occupies ~1.4 of the 16 warps per SM the lane decoder can hold)
+    static constexpr int MAXSLOT = 16;
+    int NSLOT = 10;                                      // groups in flight (their inflates run concurrently, each on its slot's stream:
+                                                         // a 256 MB group occupies ~1.4 of the 16 warps per SM the lane decoder can hold);
+                                                         // RTJX_FEED_SLOTS overrides (developer knob)
     static constexpr int NSTAGE = StagePipe::NBUF;       // pinned staging windows (read ahead by StagePipe)
     uint8_t* h_comp[NSTAGE] = {};
     cudaEvent_t comp_free[NSTAGE] = {};
@@ -100,7 +102,7 @@ struct Engine::DeviceFeed {
         bool busy = false;                               // a group was launched into this slot and not yet checked
         uint64_t seq = 0, cap_rec = 0, cap_ops = 0;      // launch number; upper bounds of what the group appends to the accumulator
         uint32_t dbg_nb = 0, dbg_nseg = 0; uint64_t dbg_out_total = 0; bool dbg_first = false;   // RTJX_FEED_DEBUG
-    } slot[NSLOT];
+    } slot[MAXSLOT];
     FeedState* d_state = nullptr;
     uint8_t* d_carry = nullptr;                          // HEAD bytes: the unfinished record at the end of a group, right-aligned
     // SoA accumulator: the alignments extracted since the last cigar_scan
@@ -223,10 +225,15 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
 
     // ---- fixed-size device state, pinned staging, streams
     if (!F.d_state) {
+        if (const char* v = getenv("RTJX_FEED_SLOTS")) F.NSLOT = std::min(std::max(atoi(v), 2), (int)DeviceFeed::MAXSLOT);
+        // the inflate streams run at the lowest priority, the engine's stream (record split, scan, merge) at the highest: the chain of a
+        // finished group must not queue behind the long-running decoder CTAs of the groups after it
+        int prio_lo = 0, prio_hi = 0;
+        CKD(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         CKD(cached_dev_malloc(&F.d_state, sizeof(FeedState)));
         CKD(cached_dev_malloc(&F.d_carry, (size_t)DeviceFeed::HEAD + 256));
         for (DeviceFeed::GroupSlot& s : F.slot) {
-            CKD(cudaStreamCreateWithFlags(&s.inf_stream, cudaStreamNonBlocking));
+            CKD(cudaStreamCreateWithPriority(&s.inf_stream, cudaStreamNonBlocking, prio_lo));
             CKD(cached_host_alloc(&s.h_state, sizeof(FeedState)));
             CKD(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
             CKD(cudaEventCreateWithFlags(&s.inflated, cudaEventDisableTiming));
@@ -399,8 +406,8 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             auto acc_full = [&] { return known_rec + infl_rec + cap_total + 8 > F.acc_rec_cap || known_ops + infl_ops + cig_upper + 8 > F.acc_ops_cap; };
             if (acc_full()) {
                 // groups that have finished tighten the bound: look at them (oldest first) before giving up on the room
-                for (int k = 0; k < DeviceFeed::NSLOT && acc_full(); ++k) {
-                    int r = check(F.slot[(n_groups + k) % DeviceFeed::NSLOT]);
+                for (int k = 0; k < F.NSLOT && acc_full(); ++k) {
+                    int r = check(F.slot[(n_groups + k) % F.NSLOT]);
                     if (r) return r;
                     if (declined) return 0;
                 }
@@ -506,7 +513,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
 
         std::vector<BgzfBlockInfo> blocks;
         while (!stream_ends && !declined && !reached_limit) {
-            DeviceFeed::GroupSlot& S = F.slot[n_groups % DeviceFeed::NSLOT];
+            DeviceFeed::GroupSlot& S = F.slot[n_groups % F.NSLOT];
             // ---- one chunk of compressed bytes: headers scanned on the host; page cache -> pinned -> the slot's device buffer
             blocks.clear();
             bool stop = false, partial = false, untrusted = false;

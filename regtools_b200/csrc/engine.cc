@@ -108,7 +108,11 @@ int Engine::ensure_device() {
                                      "); regtools-b200 has no CPU fallback for the junction kernels");
     if (prm_.device >= n) return fail(RTJX_E_CUDA, "CUDA device ordinal out of range");
     CK(cudaSetDevice(prm_.device));
-    CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    {
+        int prio_lo = 0, prio_hi = 0;                    // (numerically lower = higher priority)
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, prio_hi));
+    }
     CK(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     CK(cached_dev_malloc(&d_counters_, CTR_COUNT * sizeof(uint32_t)));
     CK(cudaMemset(d_counters_, 0, CTR_COUNT * sizeof(uint32_t)));

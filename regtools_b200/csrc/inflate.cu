@@ -189,9 +189,7 @@ struct BgzfBlock {   // same layout as BgzfBlockDesc (jx_device.cuh)
 // lane groups run the (serial) symbol loop in lockstep, so one issued instruction advances 32/L streams, and
 // each group of L lanes places its own round of L symbols.  Every warp-level primitive below is restricted to
 // the group's lane mask.
-// ONLY_STATUS != 0: the launch is a second chance — only blocks whose status holds that value are decoded (the lane-per-stream
-// decoder gives up on a block with more matches than its list holds; everything else of such a launch returns at once).
-template <int L, uint32_t ONLY_STATUS = 0>
+template <int L>
 __global__ void __launch_bounds__(INF_WARPS * 32)
 bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, uint32_t n_blocks,
                     uint8_t* __restrict__ out, uint32_t* __restrict__ status) {
@@ -203,7 +201,6 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
     const uint32_t gmask = (L == 32 ? 0xffffffffu : ((1u << (L & 31)) - 1u) << gshift);
     const uint32_t b = blockIdx.x * DEC_PER_CTA + wib;
     if (b >= n_blocks) return;
-    if (ONLY_STATUS != 0 && status[b] != ONLY_STATUS) return;
     InflateWarpSmem& sm = smem[wib];
     const BgzfBlock blk = blocks[b];
     uint8_t* dst = out + blk.out_off;
@@ -428,7 +425,7 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
 //     whose source lies before the round's first byte are copied by their own lanes in parallel, the others (and long ones)
 //     cooperatively in order — the placement logic of the warp-per-block kernel, without its decoder.
 //
-// Error codes are those of the kernel above (+18 input overrun, 19 match list full); any non-zero status sends the run to the
+// Error codes are those of the kernel above (+18 input overrun, 19 match list full — not reachable for a block of <= 64 KiB); any non-zero status sends the run to the
 // warp-per-block kernel's / host feeder's path.
 constexpr int LN_SHARED = 256;                    // per CTA: length / distance base+extra tables (RFC 1951 3.2.5), 64 words
 constexpr int LN_STRIDE = 420;                    // bytes of shared memory per lane: 105 words (odd: lanes on distinct banks)
@@ -544,7 +541,9 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volati
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int32_t lds_s16(uint32_t a) { int32_t v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
-constexpr uint32_t LN_MATCH_CAP = 8192;           // match records per BGZF block; a block with more is decoded again by the warp-per-block kernel
+// match records per BGZF block: a match covers >= 3 of the block's <= 65536 bytes, so no valid block has more.  The lists live
+// in scratch HBM (175 KB per block, ~1.1 GB per 256 MB group); only the entries a block uses are ever touched.
+constexpr uint32_t LN_MATCH_CAP = 21846;
 
 constexpr int LN_THREADS = 64;                    // two warps per CTA: 8 CTAs = 16 warps per SM within the shared-memory budget
 __global__ void __launch_bounds__(LN_THREADS, 8)
@@ -734,23 +733,19 @@ bgzf_match_resolve_kernel(const BgzfBlock* __restrict__ blocks, uint32_t n_block
 size_t bgzf_inflate_scratch_bytes(uint32_t n_blocks) { return (size_t)n_blocks * LN_MATCH_CAP * sizeof(uint2) + (size_t)n_blocks * 4 + 256; }
 
 static void launch_lanes(const uint8_t* comp, const BgzfBlock* bl, uint32_t n_blocks, uint8_t* out, uint32_t* status, void* scratch, cudaStream_t stream) {
-    constexpr int sh = LN_SHARED + LN_THREADS * LN_STRIDE;
+    // RTJX_LANES_SMEM_PAD (developer knob): extra dynamic shared memory per CTA, i.e. fewer resident CTAs per SM
+    static const int pad = [] { const char* v = getenv("RTJX_LANES_SMEM_PAD"); return v ? atoi(v) : 0; }();
+    const int sh = LN_SHARED + LN_THREADS * LN_STRIDE + pad;
     static bool attr = false;
     if (!attr) {
         attr = true;
         cudaFuncSetAttribute(bgzf_inflate_lanes_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (sh > 48 * 1024) cudaFuncSetAttribute(bgzf_inflate_lanes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sh);
     }
     uint32_t* mcount = static_cast<uint32_t*>(scratch);
     uint2* mlist = reinterpret_cast<uint2*>(static_cast<uint8_t*>(scratch) + (((size_t)n_blocks * 4 + 255) & ~(size_t)255));
     bgzf_inflate_lanes_kernel<<<(n_blocks + LN_THREADS - 1) / LN_THREADS, LN_THREADS, sh, stream>>>(comp, bl, n_blocks, out, status, mlist, mcount);
     bgzf_match_resolve_kernel<<<(n_blocks + MR_WARPS - 1) / MR_WARPS, MR_WARPS * 32, 0, stream>>>(bl, n_blocks, out, mlist, mcount);
-    // second chance for blocks whose match list overflowed (status 19): the warp-per-block decoder has no such limit
-    {
-        constexpr int D = INF_WARPS * 32 / 16; const size_t shw = D * sizeof(InflateWarpSmem);
-        static bool a = false;
-        if (!a) { cudaFuncSetAttribute(bgzf_inflate_kernel<16, 19u>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shw); a = true; }
-        bgzf_inflate_kernel<16, 19u><<<(n_blocks + D - 1) / D, INF_WARPS * 32, shw, stream>>>(comp, bl, n_blocks, out, status);
-    }
 }
 
 __global__ void inflate_status_reduce_kernel(const uint32_t* __restrict__ status, uint32_t n, uint32_t* __restrict__ flags) {

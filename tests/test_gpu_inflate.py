@@ -83,7 +83,7 @@ def test_stored_fixed_and_repetitive_blocks(tmp_path):
         (bytes(rng.integers(0, 256, 65280, dtype=np.uint8)), 6, zlib.Z_DEFAULT_STRATEGY),           # incompressible, max size
         (b"x", 6, zlib.Z_DEFAULT_STRATEGY), (bytes(rng.integers(60, 70, 3000, dtype=np.uint8)), 1, zlib.Z_HUFFMAN_ONLY),
         (bytes(np.repeat(rng.integers(0, 256, 300, dtype=np.uint8), 200)), 6, zlib.Z_RLE),
-        # ~16k four-byte matches in one block: more than the lane decoder's match list holds (8192) -> its second-chance launch
+        # ~16k four-byte matches in one block: close to the most a block can hold (21845); the lane decoder's lists are sized for it
         (rng.integers(0, 256, (64, 4), dtype=np.uint8)[rng.integers(0, 64, 16000)].tobytes(), 9, zlib.Z_DEFAULT_STRATEGY),
     ]
     path = str(tmp_path / "mix.bam")
