@@ -415,7 +415,7 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
 //     byte each, + per-length adjustments), sixteen warps fit on an SM, and that occupancy — not table size — is what hides the symbol chain's
 //     latency.  (First round-2 build: 10-bit lookup tables, 3.2 KB per lane, two warps per SM: 337 ms for the 2.1 GB C2 stream
 //     against 74 ms for the kernel above; profiles/r2_inflate_lanes_v1.txt.)
-//     One loop, one symbol (or one DEFLATE block header) per lane per iteration, so lanes reconverge every iteration; zlib
+//     One loop, up to two literals and a match (or one DEFLATE block header) per lane per iteration, so lanes reconverge every iteration; zlib
 //     cuts DEFLATE blocks after a fixed number of symbols, so the lanes of a warp reach their block headers (the divergent
 //     part) in the same iteration.  Literals go straight to their final position (byte stores: combining them into words
 //     was measured and cost more issue slots than it saved transactions).
@@ -648,28 +648,42 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
             in_block = true;
             continue;
         }
-        // ================= one symbol =================
+        // ================= up to two literal/length symbols, then (if the last one was a length) one match =================
+        // Nine tokens in ten of a BAM's DEFLATE streams are literals, and a warp pays for the match path whenever ANY lane has a
+        // match: two literal slots per trip through it.  The second code's length is worked out before the first symbol's table
+        // lookups have come back (pure register arithmetic on bits already in the buffer: 33 >= 15 + 15 + 3).
         br.refill();
         uint32_t v = __brev((uint32_t)br.bb) >> 17;                    // next 15 bits, first bit most significant
         uint32_t cl = lane_code_len(v, ul);
         if (cl > 15u) { err = 11; in_block = false; continue; }
-        const uint32_t ah = lds_u32(sT + LN_LIT_AH + 4u * cl);
-        const uint32_t ix = (v >> (15u - cl)) + (uint32_t)(int)(int16_t)(ah & 0xffffu);
-        uint32_t sym = lds_u8(sT + LN_LIT_SYM + ix) + (ix >= (ah >> 16) ? 256u : 0u);
+        uint32_t ah = lds_u32(sT + LN_LIT_AH + 4u * cl);
         br.drop((int)cl);
+        const uint32_t v2 = __brev((uint32_t)br.bb) >> 17;
+        const uint32_t cl2 = lane_code_len(v2, ul);                    // (meaningless, and unused, if the first symbol is not a literal)
+        uint32_t ix = (v >> (15u - cl)) + (uint32_t)(int)(int16_t)(ah & 0xffffu);
+        uint32_t sym = lds_u8(sT + LN_LIT_SYM + ix) + (ix >= (ah >> 16) ? 256u : 0u);
         if (sym < 256u) {
             if (opos >= cap) { err = 15; in_block = false; continue; }
             dst[opos++] = (uint8_t)sym;
-            continue;
+            if (cl2 > 15u) { err = 11; in_block = false; continue; }
+            ah = lds_u32(sT + LN_LIT_AH + 4u * cl2);
+            br.drop((int)cl2);
+            ix = (v2 >> (15u - cl2)) + (uint32_t)(int)(int16_t)(ah & 0xffffu);
+            sym = lds_u8(sT + LN_LIT_SYM + ix) + (ix >= (ah >> 16) ? 256u : 0u);
+            if (sym < 256u) {
+                if (opos >= cap) { err = 15; in_block = false; continue; }
+                dst[opos++] = (uint8_t)sym;
+                continue;
+            }
         }
         if (sym == 256u) { in_block = false; if (br.overrun()) err = 18; continue; }
         sym -= 257u;
         if (sym >= 29u) { err = 12; in_block = false; continue; }
         // length: base and extra bits from the symbol (RFC 1951 3.2.5)
+        br.refill();                                                   // 33 bits: length extra (<= 5) + distance code (<= 15) + distance extra (<= 13)
         const uint32_t lt = lds_u32(sTab + 4u * sym), lx = lt >> 16;
         const uint32_t len = (lt & 0xffffu) + br.peek((int)lx);
         br.drop((int)lx);
-        br.refill();
         v = __brev((uint32_t)br.bb) >> 17;
         cl = lane_code_len(v, ud);
         if (cl > 15u) { err = 13; in_block = false; continue; }
@@ -709,10 +723,17 @@ bgzf_match_resolve_kernel(const BgzfBlock* __restrict__ blocks, uint32_t n_block
         const uint32_t round_first = __shfl_sync(0xffffffffu, mypos, 0);
         // A match whose source lies entirely before this round's first byte depends on nothing the round writes
         const bool indep = have && mlen <= 32u && mypos + (mlen < mdist ? mlen : mdist) <= round_first + mdist;
+        // (plain loads: every byte of this block is written by this warp — its L1 sees its own stores — or by the kernel before)
         if (indep) {
+            // the source bytes all lie before the round's first byte: eight loads in flight, then eight stores
             const uint8_t* srcp = dst + mypos - mdist;
-            if (mdist >= mlen) { for (uint32_t k = 0; k < mlen; ++k) dst[mypos + k] = __ldcg(srcp + k); }
-            else { for (uint32_t k = 0; k < mlen; ++k) dst[mypos + k] = __ldcg(srcp + (k % mdist)); }
+            for (uint32_t k0 = 0; k0 < mlen; k0 += 8) {
+                uint8_t t[8];
+#pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) if (k0 + j < mlen) t[j] = srcp[mdist >= mlen ? k0 + j : (k0 + j) % mdist];
+#pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) if (k0 + j < mlen) dst[mypos + k0 + j] = t[j];
+            }
         }
         uint32_t mm = __ballot_sync(0xffffffffu, have && !indep);
         while (mm) {
@@ -721,9 +742,9 @@ bgzf_match_resolve_kernel(const BgzfBlock* __restrict__ blocks, uint32_t n_block
             __syncwarp();                                          // earlier stores of this warp are visible
             const uint8_t* srcp = dst + pj - dist;
             if (dist >= len) {
-                for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + k);
+                for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = srcp[k];
             } else {                                               // overlapping run: periodic with period dist
-                for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = __ldcg(srcp + (k % dist));
+                for (uint32_t k = lane; k < len; k += 32) dst[pj + k] = srcp[k % dist];
             }
         }
         __syncwarp();

@@ -54,3 +54,10 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
             srcs.setdefault(k[0], open(path).read().split("\n"))
             text = srcs[k[0]][k[1] - 1].strip()[:105]
     print(f"{(k[0] if k else '?'):>16}:{(k[1] if k else 0):<5d} inst {100*v[0]/ti:5.1f}%  stall {100*v[1]/ts:5.1f}%  {text}")
+# optional: shares of line ranges, e.g. "inflate.cu:583-650" (argv[4:])
+for spec in sys.argv[4:]:
+    f, rg = spec.split(":"); lo, hi = (int(x) for x in rg.split("-"))
+    a = [0, 0]
+    for k, v in agg.items():
+        if k and k[0] == f and lo <= k[1] <= hi: a[0] += v[0]; a[1] += v[1]
+    print(f"{spec:>28} inst {100*a[0]/ti:5.1f}%  stall {100*a[1]/ts:5.1f}%")
