@@ -12,7 +12,7 @@ struct Cache {
     std::unordered_map<void*, std::pair<size_t, int>> live;          // ptr -> (bytes, device or -1 for host)
     std::multimap<std::pair<int, size_t>, void*> free_list;          // (device, bytes) -> ptr
     size_t cached_dev = 0, cached_host = 0;
-    static constexpr size_t MAX_DEV = 24ull << 30, MAX_HOST = 2ull << 30;
+    static constexpr size_t MAX_DEV = 64ull << 30, MAX_HOST = 2ull << 30;   // (a 100M-read run holds ~25 GB of slot buffers and accumulators)
 };
 Cache& C() { static Cache* c = new Cache(); return *c; }     // intentionally leaked: the driver reclaims at exit
 
