@@ -5,6 +5,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <thread>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -1192,52 +1194,74 @@ int Engine::write_bed12(int fd) {
     int rc = finalize(nullptr);
     if (rc) return rc;
     NvtxRange nvtx("rtjx:write_bed12");
-    // one pass into a 4 MB buffer, no per-line allocation or printf (43k lines used to cost 5 ms of a 120 ms run)
-    const size_t CAP = 4u << 20;
-    std::vector<char> buf(CAP);
-    char* const base = buf.data();
-    char* p = base;
-    auto flush = [&]() -> bool {
-        size_t off = 0; const size_t n = (size_t)(p - base);
-        while (off < n) {
-            ssize_t w = ::write(fd, base + off, n - off);
+    // Junction::print (junctions_extractor.h:90-98) without per-line allocation or printf; large tables are formatted by a few
+    // threads, each into its own buffer, and written in order (43 MB for the 100M-read BAM: 37 -> ~15 ms)
+    std::vector<size_t> clen(contigs_.size());
+    for (size_t i = 0; i < contigs_.size(); ++i) clen[i] = contigs_[i].size();
+    size_t max_name = 8;
+    for (size_t l : clen) max_name = std::max(max_name, l);
+    const rtjx_junction* fin = final_data();
+    const size_t fn = final_size();
+    const size_t line_cap = max_name + 192;
+    auto format_range = [&](size_t lo, size_t hi, std::vector<char>& out) {
+        out.resize((hi - lo) * line_cap + 64);
+        char* p = out.data();
+        for (size_t fi = lo; fi < hi; ++fi) {
+            const rtjx_junction& j = fin[fi];
+            if (!(j.left_ok && j.right_ok)) continue;
+            const bool known = j.tid >= 0 && (size_t)j.tid < contigs_.size();
+            if (known) { memcpy(p, contigs_[(size_t)j.tid].data(), clen[(size_t)j.tid]); p += clen[(size_t)j.tid]; }
+            else p += snprintf(p, 32, "tid%d", (int)j.tid);
+            *p++ = '\t'; p = put_u32(p, j.thick_start);
+            *p++ = '\t'; p = put_u32(p, j.thick_end);
+            memcpy(p, "\tJUNC", 5); p += 5;
+            {   // setfill('0') << setw(8) << int (junctions_extractor.cc:152-157)
+                const int v = (int)j.name_index;
+                if (v >= 0 && v < 100000000) { uint32_t x = (uint32_t)v; for (int d = 7; d >= 0; --d) { p[d] = (char)('0' + x % 10); x /= 10; } p += 8; }
+                else { p += snprintf(p, 16, "%08d", v); }
+            }
+            *p++ = '\t'; p = put_u32(p, j.read_count);
+            *p++ = '\t'; *p++ = (char)j.strand;
+            *p++ = '\t'; p = put_u32(p, j.thick_start);
+            *p++ = '\t'; p = put_u32(p, j.thick_end);
+            memcpy(p, "\t255,0,0\t2\t", 11); p += 11;
+            p = put_u32(p, j.start - j.thick_start); *p++ = ','; p = put_u32(p, j.thick_end - j.end);
+            memcpy(p, "\t0,", 3); p += 3;
+            p = put_u32(p, j.end - j.thick_start);
+            *p++ = '\n';
+        }
+        out.resize((size_t)(p - out.data()));
+    };
+    auto write_all = [&](const std::vector<char>& v) -> bool {
+        size_t off = 0;
+        while (off < v.size()) {
+            ssize_t w = ::write(fd, v.data() + off, v.size() - off);
             if (w <= 0) return false;
             off += (size_t)w;
         }
-        p = base;
         return true;
     };
-    std::vector<size_t> clen(contigs_.size());
-    for (size_t i = 0; i < contigs_.size(); ++i) clen[i] = contigs_[i].size();
-    const rtjx_junction* fin = final_data();
-    for (size_t fi = 0, fn = final_size(); fi < fn; ++fi) {
-        const rtjx_junction& j = fin[fi];
-        if (!(j.left_ok && j.right_ok)) continue;
-        const bool known = j.tid >= 0 && (size_t)j.tid < contigs_.size();
-        const char* chrom = known ? contigs_[(size_t)j.tid].c_str() : contig(j.tid);
-        const size_t cl = known ? clen[(size_t)j.tid] : strlen(chrom);
-        if ((size_t)(p - base) + cl + 192 > CAP) { if (!flush()) return fail(RTJX_E_IO, "write failed"); }
-        if (cl + 192 > CAP) return fail(RTJX_E_ARG, "contig name too long");
-        memcpy(p, chrom, cl); p += cl;
-        *p++ = '\t'; p = put_u32(p, j.thick_start);
-        *p++ = '\t'; p = put_u32(p, j.thick_end);
-        memcpy(p, "\tJUNC", 5); p += 5;
-        {   // setfill('0') << setw(8) << int (junctions_extractor.cc:152-157)
-            const int v = (int)j.name_index;
-            if (v >= 0 && v < 100000000) { uint32_t x = (uint32_t)v; for (int d = 7; d >= 0; --d) { p[d] = (char)('0' + x % 10); x /= 10; } p += 8; }
-            else { p += snprintf(p, 16, "%08d", v); }
+    const size_t CHUNK = 32768;                                  // junctions per formatting task
+    const int hw = prm_.n_threads > 0 ? prm_.n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    const int T = fn >= 4 * CHUNK ? std::min(8, hw) : 1;
+    if (T <= 1) {
+        std::vector<char> out;
+        for (size_t lo = 0; lo < fn; lo += CHUNK) {
+            format_range(lo, std::min(fn, lo + CHUNK), out);
+            if (!write_all(out)) return fail(RTJX_E_IO, "write failed");
         }
-        *p++ = '\t'; p = put_u32(p, j.read_count);
-        *p++ = '\t'; *p++ = (char)j.strand;
-        *p++ = '\t'; p = put_u32(p, j.thick_start);
-        *p++ = '\t'; p = put_u32(p, j.thick_end);
-        memcpy(p, "\t255,0,0\t2\t", 11); p += 11;
-        p = put_u32(p, j.start - j.thick_start); *p++ = ','; p = put_u32(p, j.thick_end - j.end);
-        memcpy(p, "\t0,", 3); p += 3;
-        p = put_u32(p, j.end - j.thick_start);
-        *p++ = '\n';
+        return RTJX_OK;
     }
-    if (!flush()) return fail(RTJX_E_IO, "write failed");
+    const size_t n_chunks = (fn + CHUNK - 1) / CHUNK;
+    std::vector<std::vector<char>> outs(n_chunks);
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; ++t)
+        pool.emplace_back([&] {
+            for (size_t c; (c = next.fetch_add(1)) < n_chunks;) format_range(c * CHUNK, std::min(fn, (c + 1) * CHUNK), outs[c]);
+        });
+    for (auto& th : pool) th.join();
+    for (const auto& o : outs) if (!write_all(o)) return fail(RTJX_E_IO, "write failed");
     return RTJX_OK;
 }
 

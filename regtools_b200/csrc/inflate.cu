@@ -415,7 +415,7 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
 //     byte each, + per-length adjustments), sixteen warps fit on an SM, and that occupancy — not table size — is what hides the symbol chain's
 //     latency.  (First round-2 build: 10-bit lookup tables, 3.2 KB per lane, two warps per SM: 337 ms for the 2.1 GB C2 stream
 //     against 74 ms for the kernel above; profiles/r2_inflate_lanes_v1.txt.)
-//     One loop, two Huffman codes (or one DEFLATE block header) per lane per iteration, so lanes reconverge every iteration; zlib
+//     One loop, up to two literals and a match (or one DEFLATE block header) per lane per iteration, so lanes reconverge every iteration; zlib
 //     cuts DEFLATE blocks after a fixed number of symbols, so the lanes of a warp reach their block headers (the divergent
 //     part) in the same iteration.  Literals go straight to their final position (byte stores: combining them into words
 //     was measured and cost more issue slots than it saved transactions).
@@ -539,7 +539,6 @@ __device__ __forceinline__ uint32_t lane_code_len(uint32_t v, const uint32_t (&p
 // makes the compiler rebuild the shared window base — S2R + LEA + two IMADs — at every use when registers are tight)
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int32_t lds_s16(uint32_t a) { int32_t v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
 // match records per BGZF block: a match covers >= 3 of the block's <= 65536 bytes, so no valid block has more.  The lists live
@@ -578,7 +577,6 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ul[i] = 0; ud[i] = 0; }
     bool in_block = false, last = false;
-    uint32_t pend_len = 0;                        // length of the match whose distance code comes next (0: none)
 
     for (;;) {
         if (!in_block) {
@@ -650,70 +648,56 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
             in_block = true;
             continue;
         }
-        // ================= one step: two Huffman codes =================
-        // Nine tokens in ten of a BAM's DEFLATE streams are literals, yet a warp pays for a separate match path whenever ANY lane has
-        // a match.  So there is no match path: a lane that has read a length symbol remembers the length (`pend_len`) and decodes its
-        // distance code in the NEXT step, in the same instructions in which the other lanes decode literals — the code bounds and
-        // table addresses are selected per lane.  Each step also decodes a second code, speculatively as a literal/length code that
-        // follows a literal: its length comes from register arithmetic on bits already in the buffer, its table lookups are issued
-        // together with the first code's, so the two dependent shared-memory round trips of a symbol are paid once per step.
-        // Bits: a step consumes at most 15 + 15 (two codes), 15 + 5 (length) or 15 + 13 (distance) of the >= 33 in the buffer.
+        // ================= up to two literal/length symbols, then (if the last one was a length) one match =================
+        // Nine tokens in ten of a BAM's DEFLATE streams are literals, and a warp pays for the match path whenever ANY lane has a
+        // match: two literal slots per trip through it.  The second code's length is worked out before the first symbol's table
+        // lookups have come back (pure register arithmetic on bits already in the buffer: 33 >= 15 + 15 + 3).
         br.refill();
-        const bool dstate = pend_len != 0u;
-        uint32_t pa[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) pa[i] = dstate ? ud[i] : ul[i];
-        const uint32_t v1 = __brev((uint32_t)br.bb) >> 17;             // next 15 bits, first bit most significant
-        const uint32_t cl1 = lane_code_len(v1, pa);
-        if (cl1 > 15u) { err = dstate ? 13u : 11u; in_block = false; continue; }
-        const uint32_t v2 = __brev((uint32_t)(br.bb >> cl1)) >> 17;
-        const uint32_t cl2 = lane_code_len(v2, ul);                    // (meaningless, and unused, unless the first code is a literal)
-        const uint32_t c2 = cl2 < 15u ? cl2 : 15u;
-        const int32_t adj1 = lds_s16(sT + (dstate ? LN_DIST_ADJ + 2u * cl1 : LN_LIT_AH + 4u * cl1));
-        const uint32_t hi1 = lds_u16(sT + LN_LIT_AH + 4u * cl1 + 2u);
-        const uint32_t ah2 = lds_u32(sT + LN_LIT_AH + 4u * c2);
-        const uint32_t ix1 = (v1 >> (15u - cl1)) + (uint32_t)adj1;
-        uint32_t ix2 = (v2 >> (15u - c2)) + (uint32_t)(int)(int16_t)(ah2 & 0xffffu);
-        ix2 = ix2 < 287u ? ix2 : 287u;                                 // (a window that is not a code may point anywhere)
-        const uint32_t s1 = lds_u8(sT + (dstate ? LN_DIST_SYM : LN_LIT_SYM) + ix1);
-        const uint32_t s2 = lds_u8(sT + LN_LIT_SYM + ix2);
-        br.drop((int)cl1);
-        if (dstate) {
-            // ---- distance: base and extra bits from the symbol (RFC 1951 3.2.5); the match goes to the list
-            if (s1 >= 30u) { err = 14; in_block = false; continue; }
-            const uint32_t dt = lds_u32(sTab + 128u + 4u * s1), dx = dt >> 16;
-            const uint32_t dist = (dt & 0xffffu) + br.peek((int)dx);
-            br.drop((int)dx);
-            const uint32_t len = pend_len;
-            pend_len = 0;
-            if (dist > opos || opos + len > cap || n_match >= LN_MATCH_CAP) {
-                err = dist > opos ? 16u : (opos + len > cap ? 15u : 19u); in_block = false; continue;
-            }
-            my_matches[n_match++] = make_uint2(opos | len << 16, dist);     // the copy itself happens in bgzf_match_resolve_kernel
-            opos += len;
-            continue;
-        }
-        uint32_t sym = s1 + (ix1 >= hi1 ? 256u : 0u);
+        uint32_t v = __brev((uint32_t)br.bb) >> 17;                    // next 15 bits, first bit most significant
+        uint32_t cl = lane_code_len(v, ul);
+        if (cl > 15u) { err = 11; in_block = false; continue; }
+        uint32_t ah = lds_u32(sT + LN_LIT_AH + 4u * cl);
+        br.drop((int)cl);
+        const uint32_t v2 = __brev((uint32_t)br.bb) >> 17;
+        const uint32_t cl2 = lane_code_len(v2, ul);                    // (meaningless, and unused, if the first symbol is not a literal)
+        uint32_t ix = (v >> (15u - cl)) + (uint32_t)(int)(int16_t)(ah & 0xffffu);
+        uint32_t sym = lds_u8(sT + LN_LIT_SYM + ix) + (ix >= (ah >> 16) ? 256u : 0u);
         if (sym < 256u) {
             if (opos >= cap) { err = 15; in_block = false; continue; }
             dst[opos++] = (uint8_t)sym;
             if (cl2 > 15u) { err = 11; in_block = false; continue; }
+            ah = lds_u32(sT + LN_LIT_AH + 4u * cl2);
             br.drop((int)cl2);
-            sym = s2 + (ix2 >= (ah2 >> 16) ? 256u : 0u);
+            ix = (v2 >> (15u - cl2)) + (uint32_t)(int)(int16_t)(ah & 0xffffu);
+            sym = lds_u8(sT + LN_LIT_SYM + ix) + (ix >= (ah >> 16) ? 256u : 0u);
             if (sym < 256u) {
                 if (opos >= cap) { err = 15; in_block = false; continue; }
                 dst[opos++] = (uint8_t)sym;
                 continue;
             }
-            br.refill();                                               // two codes are gone: a length's extra bits may need more
         }
         if (sym == 256u) { in_block = false; if (br.overrun()) err = 18; continue; }
         sym -= 257u;
         if (sym >= 29u) { err = 12; in_block = false; continue; }
-        // ---- length: base and extra bits from the symbol; its distance code is the next step's first code
+        // length: base and extra bits from the symbol (RFC 1951 3.2.5)
+        br.refill();                                                   // 33 bits: length extra (<= 5) + distance code (<= 15) + distance extra (<= 13)
         const uint32_t lt = lds_u32(sTab + 4u * sym), lx = lt >> 16;
-        pend_len = (lt & 0xffffu) + br.peek((int)lx);
+        const uint32_t len = (lt & 0xffffu) + br.peek((int)lx);
         br.drop((int)lx);
+        v = __brev((uint32_t)br.bb) >> 17;
+        cl = lane_code_len(v, ud);
+        if (cl > 15u) { err = 13; in_block = false; continue; }
+        const uint32_t ds = lds_u8(sT + LN_DIST_SYM + (uint32_t)((int)(v >> (15u - cl)) + lds_s16(sT + LN_DIST_ADJ + 2u * cl)));
+        br.drop((int)cl);
+        if (ds >= 30u) { err = 14; in_block = false; continue; }
+        const uint32_t dt = lds_u32(sTab + 128u + 4u * ds), dx = dt >> 16;
+        const uint32_t dist = (dt & 0xffffu) + br.peek((int)dx);
+        br.drop((int)dx);
+        if (dist > opos || opos + len > cap || n_match >= LN_MATCH_CAP) {
+            err = dist > opos ? 16u : (opos + len > cap ? 15u : 19u); in_block = false; continue;
+        }
+        my_matches[n_match++] = make_uint2(opos | len << 16, dist);     // the copy itself happens in bgzf_match_resolve_kernel
+        opos += len;
     }
     if (!err && opos != cap) err = 17;
     status[b] = err;
