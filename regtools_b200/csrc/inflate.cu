@@ -428,43 +428,62 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
 // Error codes are those of the kernel above (+18 input overrun, 19 match list full — not reachable for a block of <= 64 KiB); any non-zero status sends the run to the
 // warp-per-block kernel's / host feeder's path.
 constexpr int LN_SHARED = 256;                    // per CTA: length / distance base+extra tables (RFC 1951 3.2.5), 64 words
-constexpr int LN_STRIDE = 420;                    // bytes of shared memory per lane: 105 words (odd: lanes on distinct banks)
+constexpr int LN_STRIDE = 428;                    // bytes of shared memory per lane: 107 words (odd: lanes on distinct banks)
 constexpr int LN_LIT_SYM = 0;                     // uint8[288]  low byte of the literal/length symbols in canonical order
 constexpr int LN_LIT_AH = 288;                    // uint32[16]  per code length: int16 adj = offset - first_code | uint16 index from which symbols are >= 256
 constexpr int LN_DIST_ADJ = 352;                  // int16[16]
 constexpr int LN_DIST_SYM = 384;                  // uint8[32]
+constexpr int LN_RING = 416;                      // uint32[2]   the bit reader's look-ahead words (cp.async destination)
 
-// LSB-first bit reader of one lane: 64-bit buffer, 32-bit aligned refills, the next word always already requested.
+// LSB-first bit reader of one lane: 64-bit buffer, 32-bit aligned refills.  The next TWO words are always already requested,
+// with cp.async into a two-word ring in the lane's shared memory — not into a register: a register that is the destination
+// of a load in flight blocks every later instruction of the WARP that touches it, and since the lanes of a warp refill in
+// different iterations, a register-staged look-ahead word made each iteration wait for the load the previous one had issued
+// (ncu: 1.5 of 6.5 stall cycles per instruction on the long scoreboard).  cp.async.wait_group 1 leaves the newest request in
+// flight and waits only for requests at least two refills old.
+__device__ __forceinline__ void lane_request(uint32_t slot, const uint32_t* src, bool in_range) {
+    if (in_range) {
+        asm volatile("{ .reg .u64 g; cvta.to.global.u64 g, %1; cp.async.ca.shared.global [%0], [g], 4; }" :: "r"(slot), "l"(src) : "memory");
+    } else {
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(slot), "r"(0u) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 struct LaneBits {
-    const uint32_t* p;      // address of the word after `ahead`
+    const uint32_t* p;      // address of the next word to request
     const uint32_t* lim;    // first word that must not be read (end of this block's payload + slack)
     uint64_t bb;
     int nb;
-    uint32_t ahead;
-    __device__ __forceinline__ void init(const uint8_t* src, uint32_t len) {
+    uint32_t rb, sel;       // shared-space address of the ring; byte offset (0 / 4) of the slot holding the OLDER of the two words
+    __device__ __forceinline__ void init(const uint8_t* src, uint32_t len, uint32_t ring) {
+        asm volatile("cp.async.wait_all;" ::: "memory");                 // (a re-init after a stored block: nothing of the old stream may still land)
         const uintptr_t a = reinterpret_cast<uintptr_t>(src);
         p = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
         lim = reinterpret_cast<const uint32_t*>((a + len + 3) & ~(uintptr_t)3) + 2;    // the BGZF trailer (CRC32, ISIZE) follows every payload
         const int mis = (int)(a & 3);
         bb = (uint64_t)__ldg(p++) >> (8 * mis);
         nb = 32 - 8 * mis;
-        ahead = __ldg(p++);
+        rb = ring; sel = 0;
+        lane_request(rb, p, p < lim); ++p;
+        lane_request(rb + 4u, p, p < lim); ++p;
     }
     __device__ __forceinline__ void refill() {                         // afterwards nb >= 33
         if (nb <= 32) {
-            bb |= (uint64_t)ahead << nb; nb += 32;
-            if (p < lim) {
-                ahead = __ldg(p);
-            } else ahead = 0;
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            uint32_t w;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(rb + sel) : "memory");
+            bb |= (uint64_t)w << nb; nb += 32;
+            lane_request(rb + sel, p, p < lim);
+            sel ^= 4u;
             ++p;
         }
     }
-    __device__ __forceinline__ bool overrun() const { return p > lim + 2; }
+    __device__ __forceinline__ bool overrun() const { return p > lim + 3; }
     __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)bb & ((1u << n) - 1u); }
     __device__ __forceinline__ void drop(int n) { bb >>= n; nb -= n; }
     __device__ __forceinline__ uint32_t get(int n) { refill(); const uint32_t v = peek(n); drop(n); return v; }   // n <= 16
-    // address of the next unread byte after discarding the bits of a partial byte (stored blocks)
-    __device__ __forceinline__ const uint8_t* byte_ptr() const { return reinterpret_cast<const uint8_t*>(p - 1) - (nb >> 3); }
+    // address of the next unread byte after discarding the bits of a partial byte (stored blocks): two words wait in the ring
+    __device__ __forceinline__ const uint8_t* byte_ptr() const { return reinterpret_cast<const uint8_t*>(p - 2) - (nb >> 3); }
 };
 
 // Canonical code of `n` symbols with lengths len[]: ub[l] (l = 1..15, registers), per-length adjustments and the symbol table
@@ -572,7 +591,7 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
     uint2* my_matches = mlist + (size_t)b * LN_MATCH_CAP;
     uint32_t opos = 0, err = 0, n_match = 0;
     LaneBits br;
-    br.init(comp + blk.in_off, blk.in_len);
+    br.init(comp + blk.in_off, blk.in_len, sT + LN_RING);
     uint32_t ul[8], ud[8];                        // upper bounds per code length of the current DEFLATE block's two codes, two per register
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ul[i] = 0; ud[i] = 0; }
@@ -593,7 +612,7 @@ bgzf_inflate_lanes_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __r
                 if (src + l > reinterpret_cast<const uint8_t*>(br.lim)) { err = 18; continue; }
                 for (uint32_t i = 0; i < l; ++i) dst[opos + i] = __ldg(src + i);
                 opos += l;
-                br.init(src + l, (uint32_t)(reinterpret_cast<const uint8_t*>(br.lim - 2) - (src + l)));
+                br.init(src + l, (uint32_t)(reinterpret_cast<const uint8_t*>(br.lim - 2) - (src + l)), sT + LN_RING);
                 continue;
             }
             if (btype == 3) { err = 3; continue; }

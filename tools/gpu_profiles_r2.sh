@@ -20,13 +20,17 @@ reduce() {   # reduce() report: raw metrics + per-SASS-instruction table as CSV,
     echo "== ncu launch list of the bench command"
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-courtesy > $O/r2_bench_under_ncu.log 2>&1
     wc -l $O/r2_launches.csv
+    echo "== cold CLI run with the engine's trace"
+    bam=$(python -c "import bench; print(bench.ensure_bam('c3', 100000000, 6))" 2>/dev/null | tail -1)
+    for i in 1 2; do /usr/bin/time -f "%e s wall" env RTJX_TRACE=1 regtools_b200/regtools junctions extract -s XS -o /tmp/cold.bed $bam 2>&1 | cut -c1-400; done
   fi
   if [[ $WHAT == *ncu* ]]; then
-    echo "== ncu --set full: cigar_scan + junction_merge on a 30M-read C3 batch, inflate / feed kernels on the C2 file"
+    echo "== ncu --set full: cigar_scan + junction_merge on a 30M-read C3 batch, the lane decoder on a 13M-read C3 file in one launch (57k blocks, 12 warps per SM), feed kernels on the C2 file"
     AB_CASES=5:0:0 timeout 400 ncu --set full --clock-control none -k regex:cigar_scan -s 6 -c 1 -o $O/r2_cigar_scan python tools/ab_scan.py 30000000 6 c3 > $O/ncu_scan.log 2>&1
     reduce r2_cigar_scan
     AB_CASES=5:0:0 timeout 400 ncu --set full --clock-control none -k regex:junction_merge -s 6 -c 1 -o $O/r2_junction_merge python tools/ab_scan.py 30000000 6 c3 > $O/ncu_merge.log 2>&1; reduce r2_junction_merge
-    RTJX_INFLATE_VARIANT=3 timeout 400 ncu --set full --clock-control none -k regex:bgzf_inflate_lanes -c 1 -o $O/r2_inflate_lanes python tools/prof_inflate.py 10000000 > $O/ncu_inflate.log 2>&1
+    timeout 400 python tools/prof_inflate.py 13000000 0 c3 > $O/r2_inflate_standalone.txt 2>&1; tail -2 $O/r2_inflate_standalone.txt
+    RTJX_INFLATE_VARIANT=3 timeout 400 ncu --set full --clock-control none -k regex:bgzf_inflate_lanes -c 1 -o $O/r2_inflate_lanes python tools/prof_inflate.py 13000000 0 c3 > $O/ncu_inflate.log 2>&1
     reduce r2_inflate_lanes
     timeout 400 ncu --set full --clock-control none -k "regex:bgzf_match_resolve|block_seeds|record_walk|record_extract|record_gather" -s 10 -c 5 -o $O/r2_feed_kernels python tools/prof_e2e.py 10000000 0 1 > $O/ncu_feed.log 2>&1; reduce r2_feed_kernels
   fi
