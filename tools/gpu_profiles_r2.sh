@@ -42,6 +42,10 @@ reduce() {   # reduce() report: raw metrics + per-SASS-instruction table as CSV,
     d=/tmp/rtjx_bench_annotate/c8_m30
     timeout 400 ncu --set full --clock-control none -k regex:annotate_kernel -c 1 -o $O/r2_annotate_kernel regtools_b200/regtools junctions annotate -o /tmp/a.tsv $d/junctions_x*.bed $d/ref.fa $d/ann.gtf > $O/ncu_annotate.log 2>&1; reduce r2_annotate_kernel
   fi
+  if [[ $WHAT == *side* ]]; then
+    echo "== -b single-cell mode at scale (10M reads, 5000 barcodes) through the CLI, reference on a region beside it"
+    timeout 600 python tools/bench_barcodes.py 10000000 5000 > $O/r2_barcodes.json 2> $O/r2_barcodes.err; cat $O/r2_barcodes.json; tail -2 $O/r2_barcodes.err
+  fi
   if [[ $WHAT == *sanitizer* ]]; then
     echo "== compute-sanitizer (memcheck, racecheck) over the kernel-level parity tests at small sizes"
     timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scan_pipe.py tests/test_gpu_inflate.py -q -x -k "random_batches or ring_configs or fixture_bams or stored_fixed or hot" > $O/r2_sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -4 $O/r2_sanitizer_memcheck.log
