@@ -20,9 +20,12 @@ reduce() {   # reduce() report: raw metrics + per-SASS-instruction table as CSV,
     echo "== ncu launch list of the bench command"
     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/r2_launches.csv python bench.py --steps 2 --warmup 1 --no-courtesy > $O/r2_bench_under_ncu.log 2>&1
     wc -l $O/r2_launches.csv
-    echo "== cold CLI run with the engine's trace"
+  fi
+  if [[ $WHAT == *cold* ]]; then
+    echo "== cold CLI runs with the engine's trace (exec to exit, page cache warm)"
     bam=$(python -c "import bench; print(bench.ensure_bam('c3', 100000000, 6))" 2>/dev/null | tail -1)
-    for i in 1 2; do /usr/bin/time -f "%e s wall" env RTJX_TRACE=1 regtools_b200/regtools junctions extract -s XS -o /tmp/cold.bed $bam 2>&1 | cut -c1-400; done
+    cat $bam > /dev/null
+    for i in 1 2 3; do s=$(date +%s.%N); RTJX_TRACE=1 regtools_b200/regtools junctions extract -s XS -o /tmp/cold.bed $bam 2>&1 | cut -c1-400; e=$(date +%s.%N); echo "cold run $i: $(python -c "print(round($e - $s, 3))") s wall"; done
   fi
   if [[ $WHAT == *ncu* ]]; then
     echo "== ncu --set full: cigar_scan + junction_merge on a 30M-read C3 batch, the lane decoder on a 13M-read C3 file in one launch (57k blocks, 12 warps per SM), feed kernels on the C2 file"
@@ -45,6 +48,11 @@ reduce() {   # reduce() report: raw metrics + per-SASS-instruction table as CSV,
   if [[ $WHAT == *side* ]]; then
     echo "== -b single-cell mode at scale (10M reads, 5000 barcodes) through the CLI, reference on a region beside it"
     timeout 600 python tools/bench_barcodes.py 10000000 5000 > $O/r2_barcodes.json 2> $O/r2_barcodes.err; cat $O/r2_barcodes.json; tail -2 $O/r2_barcodes.err
+  fi
+  if [[ $WHAT == *tests* ]]; then
+    echo "== full GPU suite + smoke()"
+    timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -5 | tee $O/r2_pytest_gpu_final.log
+    timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee -a $O/r2_pytest_gpu_final.log
   fi
   if [[ $WHAT == *sanitizer* ]]; then
     echo "== compute-sanitizer (memcheck, racecheck) over the kernel-level parity tests at small sizes"
