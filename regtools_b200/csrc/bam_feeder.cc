@@ -298,6 +298,7 @@ inline int32_t record_endpos(const uint8_t* core) {
 void feed_region(const BamFile& bam, const std::vector<Chunk64>& off, const IterSpec& spec, BatchWriter& w,
                  FeederStats* st) {
     if (off.empty()) return;
+    const double t_begin = now_s();
     SeqBgzf fp(bam.data(), bam.size());
     std::vector<uint8_t> rec;
     long long ci = -1; uint64_t curr_off = 0;
@@ -320,6 +321,7 @@ void feed_region(const BamFile& bam, const std::vector<Chunk64>& off, const Iter
         if (record_endpos(rec.data()) > spec.beg && spec.end > pos) w.push(rec.data(), block_len - 32);
         if (st) st->inflated_bytes += 4 + (uint64_t)block_len;
     }
+    if (st) st->parse_s += now_s() - t_begin;            // (inflate and record split alternate on this one thread)
 }
 
 // ---- parallel stream: [voffset, EOF or end voffset) ranges -----------------------------------------

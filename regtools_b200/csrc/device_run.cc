@@ -202,6 +202,11 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
         ranges.push_back(Chunk64{off0, UINT64_MAX});
     } else if (spec.kind == IterSpec::Contigs) {
         ranges = coalesced_contig_ranges(idx, spec.contigs);   // a shard of consecutive contigs streams as one range
+    } else if (spec.kind == IterSpec::Region) {
+        // (Engine::run_impl: only with the one-region filter installed) first to last chunk of hts_itr_query, as one byte span
+        const std::vector<Chunk64> off = idx.query(spec.tid, spec.beg, spec.end);
+        if (off.empty()) return RTJX_OK;
+        ranges.push_back(Chunk64{off.front().beg, off.back().end});
     } else {
         return 1;
     }

@@ -513,7 +513,32 @@ int Engine::run_impl() {
     if ((rc = ensure_device())) return rc;
     // Whole-file and contig-shard runs inflate and split records on the GPU (inflate_mode 0 = auto, 2 = force);
     // regions, tiny files and anything the device path declines go through the host feeder below.
-    const bool streamable = spec.kind == IterSpec::WholeFile || spec.kind == IterSpec::Contigs;
+    bool streamable = spec.kind == IterSpec::WholeFile || spec.kind == IterSpec::Contigs;
+    // A `-r` region that spans enough of the file goes the same way (round 2; it used to be the single-threaded, htslib-shaped
+    // reader below whatever its size): the byte span from the first to the last index chunk of the query streams through the
+    // device feeder, and cigar_scan keeps the alignments hts_itr_next would return — tid equal, pos < end, endpos > beg
+    // (hts.c:1941-1963) — with the variant-region test of rtjx_run_regions on ONE region that tags nothing.  Equivalent for an
+    // index that is consistent with its file: no alignment in front of the linear index's offset overlaps the region, every
+    // overlapping alignment behind it lies in a chunk of the query, and in a sorted file nothing after the iterator's stop
+    // (tid changes or pos >= end) passes the test.  Anything odd makes the device feeder decline, and the reader below decides.
+    struct FilterGuard { Engine* e; bool on; ~FilterGuard() { if (on) e->vr_ = VariantRegions{nullptr, nullptr, nullptr, 0, 0, 0}; } } filter_guard{this, false};
+    if (spec.kind == IterSpec::Region && !bc_mode_ && vr_.n == 0 && spec.end >= spec.beg && (size_t)spec.tid < idx.refs.size()) {
+        const std::vector<Chunk64> off = idx.query(spec.tid, spec.beg, spec.end);
+        static const uint64_t min_span = [] { const char* v = getenv("RTJX_REGION_DEVICE_MB"); return (uint64_t)(v ? atoi(v) : 8) << 20; }();
+        if (!off.empty() && (prm_.inflate_mode == 2 || (prm_.inflate_mode == 0 && (off.back().end >> 16) - (off.front().beg >> 16) >= min_span))) {
+            if (vr_cap_ == 0) {
+                vr_cap_ = 64;
+                CK(cached_dev_malloc(&d_vr_tid_, (size_t)vr_cap_ * 4)); CK(cached_dev_malloc(&d_vr_beg_, (size_t)vr_cap_ * 4));
+                CK(cached_dev_malloc(&d_vr_end_, (size_t)vr_cap_ * 4));
+            }
+            const int32_t t = spec.tid, b = (int32_t)std::max<int64_t>(spec.beg, 0), e = (int32_t)std::min<int64_t>(spec.end, INT32_MAX);
+            CK(cudaMemcpy(d_vr_tid_, &t, 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_vr_beg_, &b, 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d_vr_end_, &e, 4, cudaMemcpyHostToDevice));
+            vr_ = VariantRegions{d_vr_tid_, d_vr_beg_, d_vr_end_, 1u, (uint32_t)std::max<int64_t>((int64_t)e - b, 1), 0u};
+            filter_guard.on = true;
+            streamable = true;
+        }
+    }
     // `-b`: the barcode strings are dictionary-encoded by the host feeder, so that mode never takes the device feeder
     if (bc_mode_ && prm_.shard_world > 1) return fail(RTJX_E_UNSUPPORTED, "-b barcodes are not exchanged between contig shards");
     if (!bc_mode_ && streamable && (prm_.inflate_mode == 2 || (prm_.inflate_mode == 0 && bam->size() >= (1u << 20)))) {
@@ -535,6 +560,7 @@ int Engine::run_impl() {
             // genuinely malformed file costs two more device passes before the host path below)
         }
     }
+    if (filter_guard.on) { vr_ = VariantRegions{nullptr, nullptr, nullptr, 0, 0, 0}; filter_guard.on = false; }   // the reader below applies the iterator's own test
     uint32_t reads = prm_.batch_reads ? prm_.batch_reads : (spec.kind == IterSpec::Region ? (1u << 15) : (1u << 20));
     reads = std::max(reads, 1024u);
     uint32_t ops = std::max<uint32_t>(2 * reads, 1u << 17);      // one read may carry 65535 ops
@@ -605,10 +631,10 @@ int Engine::run_regions(const char* const* regions, size_t n) {
         CK(cudaMemcpy(d_vr_end_, e.data(), n * 4, cudaMemcpyHostToDevice));
         stats_.h2d_bytes += n * 12;
     }
-    vr_ = VariantRegions{d_vr_tid_, d_vr_beg_, d_vr_end_, (uint32_t)n, max_len};
+    vr_ = VariantRegions{d_vr_tid_, d_vr_beg_, d_vr_end_, (uint32_t)n, max_len, 1u};
     rc = run();                                        // whole-file pass; the scan kernel does the region membership
     if (rc == RTJX_OK) rc = finalize_regions();
-    vr_ = VariantRegions{nullptr, nullptr, nullptr, 0, 0};
+    vr_ = VariantRegions{nullptr, nullptr, nullptr, 0, 0, 0};
     const int rc2 = clear();                           // the handle's own table stays empty: results live in region_tables_
     return rc ? rc : rc2;
 }

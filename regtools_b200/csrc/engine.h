@@ -124,7 +124,7 @@ private:
 
     // batched variant regions: device copy sorted by (tid, beg) + per-region results in the caller's order
     int32_t* d_vr_tid_ = nullptr; int32_t* d_vr_beg_ = nullptr; int32_t* d_vr_end_ = nullptr; uint32_t vr_cap_ = 0;
-    VariantRegions vr_{nullptr, nullptr, nullptr, 0, 0};
+    VariantRegions vr_{nullptr, nullptr, nullptr, 0, 0, 0};
     std::vector<uint32_t> vr_orig_;             // sorted index -> caller's index
     std::vector<std::vector<rtjx_junction>> region_tables_;
     std::vector<rtjx_junction> unique_;          // set<Junction> of the second caller, in its order (contig name, start, end)

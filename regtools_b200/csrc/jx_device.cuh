@@ -57,6 +57,7 @@ struct VariantRegions {
     const int32_t* tid; const int32_t* beg; const int32_t* end;
     uint32_t n;
     uint32_t max_len;             // max(end - beg), bounds the backward search
+    uint32_t tag;                 // 1: candidates carry their region's index (rtjx_run_regions); 0: the regions only FILTER (a `-r` run on the device feeder)
 };
 
 struct ScanParams {

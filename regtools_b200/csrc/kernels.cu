@@ -222,7 +222,7 @@ struct S5Emit {
         for (uint32_t i = lo; i-- > 0;) {
             if (vr.tid[i] != tid) break;
             if ((long long)vr.beg[i] + (long long)vr.max_len <= (long long)rp) break;    // no earlier region can reach pos
-            if (vr.end[i] > rp) push(a, make_uint4(b.x, b.y, b.z, strand | (i + 1u) << 8));
+            if (vr.end[i] > rp) push(a, make_uint4(b.x, b.y, b.z, vr.tag ? strand | (i + 1u) << 8 : strand));
         }
     }
 };
@@ -423,7 +423,7 @@ struct PipeEmit {
         for (uint32_t i = lo; i-- > 0;) {
             if (vr.tid[i] != tid) break;
             if ((long long)vr.beg[i] + (long long)vr.max_len <= (long long)rp) break;    // no earlier region can reach pos
-            if (vr.end[i] > rp) push(a, make_uint4(b.x, b.y, b.z, strand | (i + 1u) << 8));
+            if (vr.end[i] > rp) push(a, make_uint4(b.x, b.y, b.z, vr.tag ? strand | (i + 1u) << 8 : strand));
         }
     }
 };

@@ -162,3 +162,54 @@ def test_unique_junction_set_matches_the_reference_loop(strandness, golden_dir, 
         got, first = _unique_lines(bam, regions, windows, strandness, 8, 500000, contigs)
         assert "".join(got) == want.stdout
         assert len(got) > 20 and all(0 <= f < len(regions) for f in first)
+
+
+# ---- a single `-r` region through the device feeder (round 2: large regions stream the byte span of their index chunks) ----
+def _single_region(bam, region, mode, strandness=0, a=8, m=70, M=500000):
+    import io
+    import regtools_b200 as rt
+    ex = rt.JunctionsExtractor(bam, region, strandness, "XS", a, m, M, inflate_mode=mode)
+    ex.identify_junctions_from_BAM()
+    t = ex.junction_table()
+    buf = io.StringIO()
+    ex.print_all_junctions(buf)
+    st = ex.stats()
+    ex.close()
+    return t, buf.getvalue(), st
+
+
+@pytest.mark.parametrize("strandness", [0, 1])
+def test_single_regions_on_the_device_feeder_match_host_reader_and_oracle(strandness, golden_dir):
+    """inflate_mode=2 sends ANY region down the device path (auto mode only those spanning >= 8 MB of file): the table and the
+    BED12 must be those of the htslib-shaped host reader and of the oracle, names included (first-seen order inside the region)."""
+    cases = [(os.path.join(golden_dir, "kat", "kat.bam"), ["1:5000-6200", "1:900-1300", "2", "1:1-100", "10", "1:1000-1001", "1:2000-14100",
+                                                           "2:5,000,050-5,000,060", "1", "10:3459-603459", "10:1073-1200"]),
+             (os.path.join(golden_dir, "kat", "synth.bam"), ["1:1-1900000", "10:5000-800000", "2", "1:100000-100200"]),
+             (os.path.join(golden_dir, "hcc1395", "test_hcc1395.bam"), ["22", "22:1-50000000"])]
+    took_device = 0
+    for bam, regions in cases:
+        for reg in regions:
+            t_dev, bed_dev, st_dev = _single_region(bam, reg, 2, strandness)
+            t_host, bed_host, _ = _single_region(bam, reg, 1, strandness)
+            assert bed_dev == bed_host, (bam, reg)
+            assert np.array_equal(t_dev, t_host), (bam, reg)
+            o = Oracle(8, 70, 500000, strandness)
+            o.extract_bam(bam, reg)
+            assert bed_dev == o.bed12(), (bam, reg)
+            took_device += int(st_dev["host_parse_s"] == 0.0 and st_dev["inflated_bytes"] > 0)
+    assert took_device >= 8                                       # (regions with no index chunk at all never reach a feeder)
+
+
+def test_large_region_of_a_generated_bam_takes_the_device_feeder_by_itself(tmp_path):
+    """Auto mode: a whole-contig region of a 1.2M-read BAM spans > 8 MB of file -> device feeder; a 20 kb window stays on the host."""
+    bam = str(tmp_path / "r.bam")
+    subprocess.check_call([os.path.join(ROOT, "tools", "bamgen"), "gen", "--out", bam, "--config", "c3", "--reads", "1200000", "--seed", "5", "--level", "6"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for reg, want_device in (("chr1", True), ("chr2:1000000-200000000", True), ("chr3:5000000-5020000", False)):
+        t_auto, bed_auto, st = _single_region(bam, reg, 0)
+        t_host, bed_host, _ = _single_region(bam, reg, 1)
+        assert bed_auto == bed_host and np.array_equal(t_auto, t_host), reg
+        o = Oracle(8, 70, 500000, 0)
+        o.extract_bam(bam, reg)
+        assert bed_auto == o.bed12(), reg
+        assert (st["host_parse_s"] == 0.0 and st["inflated_bytes"] > 0) == want_device, (reg, st["host_parse_s"], st["inflated_bytes"])
