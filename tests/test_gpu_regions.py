@@ -192,7 +192,8 @@ def test_single_regions_on_the_device_feeder_match_host_reader_and_oracle(strand
             t_dev, bed_dev, st_dev = _single_region(bam, reg, 2, strandness)
             t_host, bed_host, _ = _single_region(bam, reg, 1, strandness)
             assert bed_dev == bed_host, (bam, reg)
-            assert np.array_equal(t_dev, t_host), (bam, reg)
+            for f in FIELDS:                                      # (first_ord counts the alignments streamed, not those kept: it may differ)
+                assert np.array_equal(t_dev[f], t_host[f]), (bam, reg, f)
             o = Oracle(8, 70, 500000, strandness)
             o.extract_bam(bam, reg)
             assert bed_dev == o.bed12(), (bam, reg)
@@ -208,7 +209,7 @@ def test_large_region_of_a_generated_bam_takes_the_device_feeder_by_itself(tmp_p
     for reg, want_device in (("chr1", True), ("chr2:1000000-200000000", True), ("chr3:5000000-5020000", False)):
         t_auto, bed_auto, st = _single_region(bam, reg, 0)
         t_host, bed_host, _ = _single_region(bam, reg, 1)
-        assert bed_auto == bed_host and np.array_equal(t_auto, t_host), reg
+        assert bed_auto == bed_host and all(np.array_equal(t_auto[f], t_host[f]) for f in FIELDS), reg
         o = Oracle(8, 70, 500000, 0)
         o.extract_bam(bam, reg)
         assert bed_auto == o.bed12(), reg

@@ -9,6 +9,7 @@ t() { local s=$(date +%s.%N); "$@" > /dev/null 2>&1; local rc=$?; local e=$(date
 echo "reads in $REG: $(oracle/_ref/ref_count $bam $REG 2>/dev/null | cut -f1)"
 echo -n "ours (auto: device feeder for large regions), run 1: "; t regtools_b200/regtools junctions extract -s XS -r $REG -o /tmp/reg_ours.bed $bam
 echo -n "ours, run 2: "; t regtools_b200/regtools junctions extract -s XS -r $REG -o /tmp/reg_ours.bed $bam
+echo "trace of a third run:"; RTJX_TRACE=1 regtools_b200/regtools junctions extract -s XS -r $REG -o /tmp/reg_ours.bed $bam 2>&1 | grep "^\[rtjx" | cut -c1-400
 echo -n "ours with RTJX_REGION_DEVICE_MB=1000000 (host reader, the round-1 path): "; RTJX_REGION_DEVICE_MB=1000000 t regtools_b200/regtools junctions extract -s XS -r $REG -o /tmp/reg_host.bed $bam
 if [ -x oracle/_ref/regtools_ref ]; then
   echo -n "reference: "; t oracle/_ref/regtools_ref junctions extract -s XS -r $REG -o /tmp/reg_ref.bed $bam
