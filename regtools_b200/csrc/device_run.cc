@@ -400,7 +400,10 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                 const uint64_t ec = rg.end >> 16, eu = rg.end & 0xffff;
                 size_t k = std::lower_bound(G.coffs.begin(), G.coffs.end(), ec) - G.coffs.begin();
                 if (k < nb && G.coffs[k] == ec) limit = (int64_t)G.desc[k].out_off + (int64_t)eu;
-                else if (k == nb && eu == 0 && G.coffs.back() < ec) limit = (int64_t)G.out_total;
+                // (the range ends exactly where this group's last block ends: only the group whose compressed bytes reach `ec` — any
+                // earlier group also has all its blocks in front of `ec`, and a walk that happened to end on its last byte would
+                // report the range finished: shard 1 of 4 of the 100M-read file stopped after 78k of its 119k blocks that way)
+                else if (k == nb && eu == 0 && G.first_coff + G.comp_bytes == ec) limit = (int64_t)G.out_total;
             }
             // ---- device buffers of the slot and the accumulator.  A range's first group is a small one: its slot's buffers are
             // sized for the full-size group that slot will see next, so nothing is reallocated (and no stream drained) mid-run

@@ -4,6 +4,7 @@ import io
 import os
 import shutil
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -75,6 +76,20 @@ def test_contig_shards_on_device(tmp_path):
     buf = io.StringIO()
     merged.print_all_junctions(buf)
     assert buf.getvalue() == whole_bed and reads == 400000
+
+
+def test_contig_shards_with_many_small_groups(tmp_path):
+    """Bounded byte ranges (contig shards) cut into 1 MB groups: every group boundary of every shard of worlds 2..7, file mode,
+    resident file and host feeder alike (round 2: a group that happened to end on a record boundary made the run of a shard
+    whose range ends on a block boundary stop early — 9.4 M alignments of a 100M-read file at world 4)."""
+    bam = str(tmp_path / "s.bam")
+    subprocess.check_call([BAMGEN, "gen", "--out", bam, "--config", "c3", "--reads", "900000", "--seed", "11", "--level", "1"],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    env = dict(os.environ, RTJX_GROUP_MB="1", RTJX_FIRST_GROUP_MB="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "shard_groups_worker.py"), bam, "2,3,4,5,7"], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-3000:]
+    assert p.stdout.startswith("ok")
 
 
 def test_truncated_file_device(tmp_path):
