@@ -6,7 +6,7 @@
 // CIGAR scan, junction merge) runs on the GPU.
 //
 // Round-2 shape of the pipeline (round 1: one stream, one group at a time, scan per group):
-//   * a GROUP of consecutive BGZF blocks is the unit of device work; up to ten group slots are in flight: the inflates of the
+//   * a GROUP of consecutive BGZF blocks is the unit of device work; up to eight group slots are in flight: the inflates of the
 //     groups behind g (each on its slot's stream; the lane-per-stream decoder is latency-bound, so concurrent launches add up)
 //     overlap the record walk / extraction of group g (the chain stream), and all overlap the H2D copies (copy stream);
 //   * record starts are found ON the device, one per BGZF block (block_seeds_kernel), instead of every 16 kb of reference
@@ -82,9 +82,12 @@ size_t parallel_pread(int fd, uint8_t* dst, size_t n, uint64_t file_off, int thr
 struct Engine::DeviceFeed {
     static constexpr uint32_t HEAD = 4u << 20;           // carry headroom in front of the inflated data
     static constexpr int MAXSLOT = 16;
-    int NSLOT = 10;                                      // groups in flight (their inflates run concurrently, each on its slot's stream:
-                                                         // a 256 MB group occupies ~1.4 of the 16 warps per SM the lane decoder can hold);
-                                                         // RTJX_FEED_SLOTS overrides (developer knob)
+    int NSLOT = 8;                                       // groups in flight (their inflates run concurrently, each on its slot's stream:
+                                                         // a 384 MB group occupies ~2 of the 16 warps per SM the lane decoder can hold);
+                                                         // RTJX_FEED_SLOTS overrides.  Measured on the 100M-read file, resident pass:
+                                                         // 256 MB x 10 slots 386 ms, 384 x 8 330, 512 x 6 332, 512 x 10 320 (twice the
+                                                         // buffers), 1024 x 5 379, 128 x 16 675: a launch ends with its slowest warp, and
+                                                         // the fewer, larger launches there are, the less of the GPU waits on such tails
     static constexpr int NSTAGE = StagePipe::NBUF;       // pinned staging windows (read ahead by StagePipe)
     uint8_t* h_comp[NSTAGE] = {};
     cudaEvent_t comp_free[NSTAGE] = {};
@@ -186,11 +189,11 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     const int copy_threads = std::min(n_threads, 16);
     const uint64_t STAGE = 16ull << 20;                  // compressed bytes per pinned staging window (plus WIN_SLACK: the block that straddles its end)
     const uint64_t WIN_SLACK = 128u << 10;
-    static const uint64_t GROUP = [] { const char* v = getenv("RTJX_GROUP_MB"); return (uint64_t)(v ? atoi(v) : 256) << 20; }();
+    static const uint64_t GROUP = [] { const char* v = getenv("RTJX_GROUP_MB"); return (uint64_t)(v ? atoi(v) : 384) << 20; }();
     // the first group of a range is smaller: the GPU starts after a few ms of staging instead of a full group's worth
     static const uint64_t FIRST_GROUP = [] { const char* v = getenv("RTJX_FIRST_GROUP_MB"); return (uint64_t)(v ? atoi(v) : 128) << 20; }();
     // alignments (upper bound, 64 bytes of stream each) accumulated before cigar_scan runs
-    static const uint64_t ACC_REC = [] { const char* v = getenv("RTJX_SCAN_BATCH_M"); return (uint64_t)(v ? atoi(v) : 160) << 20; }();
+    static const uint64_t ACC_REC = [] { const char* v = getenv("RTJX_SCAN_BATCH_M"); return (uint64_t)(v ? atoi(v) : 192) << 20; }();
     const int seed_mode = feed_seed_mode_;               // 0 device-found starts, 1 index (linear + bin chunks), 2 linear index only
 
     // ---- ranges to stream (same as the host feeder)
