@@ -414,7 +414,7 @@ bgzf_inflate_kernel(const uint8_t* __restrict__ comp, const BgzfBlock* __restric
 //     (adj[len], then the symbol).  A lane therefore needs only 420 bytes of shared memory (symbols in canonical order, one
 //     byte each, + per-length adjustments), sixteen warps fit on an SM, and that occupancy — not table size — is what hides the symbol chain's
 //     latency.  (First round-2 build: 10-bit lookup tables, 3.2 KB per lane, two warps per SM: 337 ms for the 2.1 GB C2 stream
-//     against 74 ms for the kernel above; profiles/r2_inflate_lanes_v1.txt.)
+//     against 74 ms for the kernel above.)
 //     One loop, up to two literals and a match (or one DEFLATE block header) per lane per iteration, so lanes reconverge every iteration; zlib
 //     cuts DEFLATE blocks after a fixed number of symbols, so the lanes of a warp reach their block headers (the divergent
 //     part) in the same iteration.  Literals go straight to their final position (byte stores: combining them into words
