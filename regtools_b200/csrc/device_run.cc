@@ -194,6 +194,7 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
     static const uint64_t FIRST_GROUP = [] { const char* v = getenv("RTJX_FIRST_GROUP_MB"); return (uint64_t)(v ? atoi(v) : 128) << 20; }();
     // alignments (upper bound, 64 bytes of stream each) accumulated before cigar_scan runs
     static const uint64_t ACC_REC = [] { const char* v = getenv("RTJX_SCAN_BATCH_M"); return (uint64_t)(v ? atoi(v) : 192) << 20; }();
+    const uint64_t OUT_CAP = 1280ull << 20;              // inflated bytes at which a group is closed whatever its compressed size
     const int seed_mode = feed_seed_mode_;               // 0 device-found starts, 1 index (linear + bin chunks), 2 linear index only
 
     // ---- ranges to stream (same as the host feeder)
@@ -396,7 +397,9 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                 cap_total += (uint64_t)(span / 64 + 4);     // records are >= 37 bytes; denser than 64 B/record -> capacity flag -> fall back
             }
             segbase[n_seg] = (uint32_t)cap_total;
-            if (cap_total > 0x7ffffff0ull || G.out_total > 0x7ff00000ull) return fail(RTJX_E_STATE, "device feed: group too large");
+            // (record offsets inside a group are 31-bit: a group of a very compressible file that still got too large is left to the
+            // host feeder — groups are closed at OUT_CAP inflated bytes below, so this takes a chunk that inflates 50-fold)
+            if (cap_total > 0x7ffffff0ull || G.out_total > 0x7ff00000ull) { declined = true; feed_decline_flags_ = 0x80000000u; return 0; }
             // range end inside this group?
             int64_t limit = LLONG_MAX;
             if (bounded) {
@@ -411,7 +414,11 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
             // ---- device buffers of the slot and the accumulator.  A range's first group is a small one: its slot's buffers are
             // sized for the full-size group that slot will see next, so nothing is reallocated (and no stream drained) mid-run
             const double ta0 = now_s();
-            const double grow = std::min(8.0, std::max(1.0, 1.05 * (double)(GROUP + STAGE) / (double)std::max<uint64_t>(G.comp_bytes, 1)));
+            // (a full-size group: GROUP compressed bytes, or OUT_CAP inflated ones — whichever closes it first — plus the chunk that
+            // crosses the line)
+            const double ratio = (double)std::max<uint64_t>(G.out_total, 1) / (double)std::max<uint64_t>(G.comp_bytes, 1);
+            const double full_out = std::min((double)(GROUP + STAGE) * ratio, (double)OUT_CAP + (double)STAGE * ratio);
+            const double grow = std::min(8.0, std::max(1.0, 1.05 * full_out / (double)std::max<uint64_t>(G.out_total, 1)));
             auto sized = [&](size_t need) -> size_t { return (size_t)((double)need * grow) + 64; };
             const uint64_t cig_upper = (DeviceFeed::HEAD + G.out_total) / 32 + 4096;   // > 12.5 % of the bytes being CIGAR -> capacity flag
             auto acc_full = [&] { return known_rec + infl_rec + cap_total + 8 > F.acc_rec_cap || known_ops + infl_ops + cig_upper + 8 > F.acc_ops_cap; };
@@ -607,7 +614,9 @@ int Engine::run_device(const BamFile& bam, const BaiIndex& idx, const IterSpec& 
                 stats_.compressed_bytes += bytes;
             }
             // ---- close the group?
-            if (!g.desc.empty() && (g.comp_bytes >= (first_group ? std::min(GROUP, FIRST_GROUP) : GROUP) || stream_ends)) {
+            // (by compressed bytes, or — a file that compresses better than ~3.5x — by inflated bytes: a group's stream must stay
+            // well below 2 GiB)
+            if (!g.desc.empty() && (g.comp_bytes >= (first_group ? std::min(GROUP, FIRST_GROUP) : GROUP) || g.out_total >= OUT_CAP || stream_ends)) {
                 if ((rc = launch(g, S))) return rc;
                 if (declined) break;
                 first_group = false;
