@@ -457,6 +457,9 @@ def main():
             identity.update({"reference_sha256": whole["sha256"], "identical_to_reference_on_whole_file": whole["sha256"] == ours_sha,
                              "reference_whole_file_seconds": whole["seconds"], "reference_whole_file_reads_per_s": whole["reads_per_s"],
                              "reference_kind": whole["kind"]})
+            if whole["sha256"] != ours_sha:
+                sys.stderr.write("bench.py: the BED12 of the timed pass DIFFERS from the reference's on the whole file "
+                                 f"({ours_sha[:16]} vs {whole['sha256'][:16]}): the numbers of this line describe a wrong result\n")
         except Exception as ex_:
             identity["reference_error"] = str(ex_)
 
