@@ -545,3 +545,55 @@ def test_feeder_on_damaged_indexes(tmp_path):
                 got = (1, "")
             if p.returncode >= 0:
                 assert (p.returncode, p.stdout) == got, (seed, mode, reg)
+
+
+# ---- the equivalence the device feeder's `-r` path rests on -----------------------------------------------
+def _endpos(pos, meta, off, cig):
+    """bam_endpos (sam.c:336-342): pos + reference length of the CIGAR for a mapped alignment with a CIGAR, else pos + 1."""
+    n = len(pos)
+    ncig = (off[1:] - off[:-1]).astype(np.int64)
+    op = cig & 0xF
+    ln = (cig >> 4).astype(np.int64)
+    ref = np.where(np.isin(op, [0, 2, 3, 7, 8]), ln, 0)                # M D N = X consume the reference
+    csum = np.concatenate([[0], np.cumsum(ref)])
+    rlen = csum[off[1:].astype(np.int64)] - csum[off[:-1].astype(np.int64)]
+    unmapped = ((meta >> 16) & 4) != 0
+    return pos.astype(np.int64) + np.where(unmapped | (ncig == 0), 1, rlen), n
+
+
+@pytest.mark.parametrize("bam", [HCC, KAT, SYN, "generated"])
+def test_region_iterator_equals_the_overlap_test_over_the_whole_file(bam, tmp_path):
+    """hts_itr_next over the index's chunks (the host reader) returns exactly the alignments of the whole file with tid equal,
+    pos < end and endpos > beg, in file order — the test cigar_scan applies when a large `-r` region streams through the
+    device feeder as one byte span.  Random regions: whole contigs, windows of every size, empty stretches, odd bounds."""
+    if bam == "generated":
+        bam = str(tmp_path / "g.bam")
+        subprocess.check_call([BAMGEN, "gen", "--out", bam, "--config", "c3", "--reads", "60000", "--seed", "21", "--level", "1"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    ex = rt().JunctionsExtractor(bam, ".", 0, "XS", 8, 70, 500000, device=-1, n_threads=2)
+    tid, pos, meta, off, cig = ex.load_batch()
+    names = ex.contig_names()
+    ex.close()
+    endpos, n = _endpos(pos, meta, off, cig)
+    rng = np.random.default_rng(5)
+    present = sorted(set(int(t) for t in np.unique(tid) if t >= 0))
+    checked = nonempty = 0
+    for k in range(60):
+        t = int(rng.choice(present)) if k % 7 else int(rng.integers(0, len(names)))
+        on = pos[tid == t]
+        lo, hi = (int(on.min()), int(on.max())) if len(on) else (0, 1000)
+        if k % 5 == 0:
+            region, beg, end = names[t], 0, 2**31 - 1
+        else:
+            b = int(rng.integers(max(lo - 2000, 0), hi + 2000))
+            w = int(rng.choice([1, 50, 2000, 100000, 30000000]))
+            region, beg, end = f"{names[t]}:{b + 1}-{b + w}", b, b + w          # 1-based inclusive string -> 0-based [beg, end)
+        want = np.flatnonzero((tid == t) & (pos < end) & (endpos > beg))
+        rx = rt().JunctionsExtractor(bam, region, 0, "XS", 8, 70, 500000, device=-1, n_threads=2)
+        rtid, rpos, rmeta, roff, rcig = rx.load_batch()
+        rx.close()
+        assert len(rtid) == len(want), (region, len(rtid), len(want))
+        assert np.array_equal(rpos, pos[want]) and np.array_equal(rmeta, meta[want]), region
+        assert np.array_equal(roff[1:] - roff[:-1], (off[1:] - off[:-1])[want]), region
+        checked += 1; nonempty += int(len(want) > 0)
+    assert checked == 60 and nonempty >= 20
